@@ -1,0 +1,208 @@
+/* subzero_b200.h — C ABI of the B200-native floe-interaction hot path.
+ *
+ * This is the drop-in boundary for the four calls inside the reference's
+ * `timestep_sim!` (src/simulation_components/simulation.jl:94-220):
+ *
+ *   add_ghosts!(floes, domain)                      simulation.jl:102   -> sz_add_ghosts
+ *   timestep_collisions!(floes, n_init, domain,     simulation.jl:109   -> sz_step_collisions
+ *        consts, Δt, collision_settings, spinlock)
+ *   (ghost deletion loop)                           simulation.jl:138   -> sz_remove_ghosts
+ *   timestep_coupling!(model, Δt, consts,           simulation.jl:155   -> sz_step_coupling
+ *        coupling_settings, floe_settings)
+ *   timestep_floe_properties!(floes, tstep, Δt,     simulation.jl:165   -> sz_step_floe_properties
+ *        floe_settings)
+ *
+ * The reference has no FFI of its own (it is 100 % Julia); a Julia host binds these
+ * entry points with `ccall`.  Everything crossing the ABI is a
+ * plain pointer, a size or a POD struct.  All pointers are caller-owned HOST memory,
+ * read or written synchronously and never retained.  Every function returns an int32
+ * status (0 = SZ_OK, negative = error; sz_last_error gives the text).  A handle is not
+ * thread-safe: one host thread per handle.
+ *
+ * Indices: floe indices inside `interactions` rows and the pair getters are 1-BASED
+ * (they are stored in the Float64 `floeidx` column exactly like the reference,
+ * collisions.jl:297); domain elements are -1..-4 (N,S,E,W) and -(4+k) for topography
+ * element k (collisions.jl:612-654).
+ *
+ * The same header is compiled with -DSZ_ORACLE_BUILD by oracle/ (test infrastructure);
+ * the exported names then carry the prefix `szo_` instead of `sz_`.
+ */
+#ifndef SUBZERO_B200_H
+#define SUBZERO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef SZ_ORACLE_BUILD
+#define SZ_FN(name) szo_##name
+#else
+#define SZ_FN(name) sz_##name
+#endif
+
+#define SZ_OK 0
+#define SZ_ERR_INVALID (-1)     /* bad argument / call order */
+#define SZ_ERR_CUDA (-2)        /* CUDA runtime failure */
+#define SZ_ERR_CAPACITY (-3)    /* a device buffer overflowed (pairs, regions, rows, ghosts) */
+#define SZ_ERR_UNSUPPORTED (-4) /* feature outside the hot-path scope (e.g. two-way coupling) */
+#define SZ_ERR_NOMEM (-5)
+
+/* Status tags, src/simulation_components/floe.jl:8-12 */
+#define SZ_STATUS_ACTIVE 1
+#define SZ_STATUS_REMOVE 2
+#define SZ_STATUS_FUSE 3
+
+/* Boundary kinds, src/simulation_components/domain_components/boundaries.jl:153,240,327,415 */
+#define SZ_BOUNDARY_OPEN 0
+#define SZ_BOUNDARY_PERIODIC 1
+#define SZ_BOUNDARY_COLLISION 2
+#define SZ_BOUNDARY_MOVING 3
+
+/* Wall order everywhere in this ABI: 0 = North, 1 = South, 2 = East, 3 = West
+ * (element ids -1, -2, -3, -4 of collisions.jl:612-642). */
+
+/* Per-floe warning bits returned by sz_get_warnings; the host re-emits the reference's
+ * @warn messages (update_floe.jl:483,488,528,541). */
+#define SZ_WARN_HEIGHT_CAPPED 1u
+#define SZ_WARN_FORCE_SCALED 2u
+#define SZ_WARN_VELOCITY_LIMITED 4u
+#define SZ_WARN_XI_CLAMPED 8u
+
+typedef struct sz_handle sz_handle;
+
+typedef struct sz_config {
+    /* Constants, simulation.jl:5-18 */
+    double rho_o, rho_a, Cd_io, Cd_ia, Cd_ao, f, turn_theta, L, k, nu, mu, E;
+    /* CollisionSettings, process_settings.jl:183-229 */
+    double floe_floe_max_overlap, floe_domain_max_overlap;
+    /* FloeSettings subset, process_settings.jl:20-100; stress_calculators.jl:81-92 (λ) */
+    double rho_i, max_floe_height, maximum_xi, stress_lambda;
+    /* CouplingSettings, process_settings.jl:133-167 */
+    int32_t coupling_dd;         /* Δd knot buffer; does not change a bilinear result */
+    int32_t two_way_coupling_on; /* must be 0: two-way coupling is SURVEY §8(f) "next" */
+    /* Simulation.Δt (Int seconds), simulation.jl:49-81 */
+    int32_t dt;
+    /* execution */
+    int32_t device;               /* CUDA ordinal (ignored by the oracle build) */
+    int32_t max_regions_per_pair; /* overlap regions kept per pair; 0 -> 4 */
+    int32_t max_pairs_per_floe;   /* capacity hint for the candidate list; 0 -> 24 */
+    int32_t threads;              /* oracle build only: OpenMP threads, 0 -> all */
+    int32_t reserved0;
+    int64_t floe_capacity;        /* 0 -> sized at upload (n + ghosts headroom) */
+} sz_config;
+
+/* Structure-of-arrays view of a floe list (a1: floe.jl:24-77).  Used for upload (read)
+ * and download (written; caller allocates using sz_get_counts).  Any pointer may be NULL
+ * on download to skip that field.  2x2 tensors are 4 doubles per floe in Julia's
+ * column-major order (11, 21, 12, 22). */
+typedef struct sz_floe_soa {
+    int64_t n;      /* floes in the arrays: parents first, then ghosts (if any) */
+    int64_t n_init; /* number of non-ghost floes */
+    double *centroid_x, *centroid_y;
+    double *height, *area, *mass, *rmax, *moment;
+    double *alpha, *u, *v, *xi;
+    double *fxOA, *fyOA, *trqOA, *hflx_factor, *overarea;
+    double *collision_force; /* [n][2] */
+    double *collision_trq;
+    double *stress_accum, *stress_instant, *strain; /* [n][4] */
+    double *p_dxdt, *p_dydt, *p_dudt, *p_dvdt, *p_dxidt, *p_dalphadt;
+    int32_t *status_tag;
+    int64_t *id, *ghost_id;
+    int64_t *ghost_offsets; /* [n+1] CSR of each floe's `ghosts` list; NULL = no ghosts */
+    int64_t *ghost_index;   /* 1-based indices into this floe list */
+    int64_t *vert_offsets;  /* [n+1], in points; ring i = points [off[i], off[i+1]) closed */
+    double *vert_xy;        /* [V][2] interleaved x,y */
+    int64_t *mc_offsets;    /* [n+1]; x/y_subfloe_points (body frame, floe.jl:37-38) */
+    double *mc_x, *mc_y;
+} sz_floe_soa;
+
+typedef struct sz_counts {
+    int64_t n_init;        /* non-ghost floes */
+    int64_t n_total;       /* floes incl. ghosts currently in the store */
+    int64_t n_vertices;    /* ring points over n_total floes */
+    int64_t n_mc;          /* Monte-Carlo points over n_init floes */
+    int64_t n_ghost_links; /* total length of all `ghosts` lists */
+    int64_t n_candidates;  /* floe pairs (i<j) passing the bounding-circle test */
+    int64_t n_pairs;       /* candidates left after the id / ghost-image filter */
+    int64_t n_overlap;     /* pairs with total overlap area > 0 */
+    int64_t n_fuse;        /* (i,j) pairs tagged for fusion this step */
+    int64_t n_rows;        /* interaction rows over n_total floes */
+    int64_t n_domain_pairs;/* (floe, element) checks issued */
+    int64_t n_clip_fail;   /* pairs whose region trace hit a degenerate configuration */
+} sz_counts;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+void SZ_FN(default_config)(sz_config *cfg); /* reference defaults (Constants(), *Settings()) */
+int32_t SZ_FN(create)(const sz_config *cfg, sz_handle **out);
+void SZ_FN(destroy)(sz_handle *h);
+const char *SZ_FN(last_error)(sz_handle *h);
+const char *SZ_FN(version)(void);
+
+/* ---- model description (a20) ---------------------------------------------------------- */
+/* RegRectilinearGrid, grids.jl:106-116 */
+int32_t SZ_FN(set_grid)(sz_handle *h, int32_t Nx, int32_t Ny, double x0, double xf, double y0,
+                        double yf);
+/* Ocean u, v, hflx_factor (oceans.jl:74-99) and Atmos u, v (atmos.jl:4-16): column-major
+ * (Nx+1) x (Ny+1), element [ix + (Nx+1)*iy] == Julia A[ix+1, iy+1]. */
+int32_t SZ_FN(set_fields)(sz_handle *h, const double *ocean_u, const double *ocean_v,
+                          const double *ocean_hflx, const double *atmos_u,
+                          const double *atmos_v);
+/* Domain, domains.jl:4-34.  rect[w] = {xmin, xmax, ymin, ymax} of wall w's rectangle
+ * (boundaries.jl:29-33,65-69,102-106,139-143); uv[w] = MovingBoundary velocity.  Topography:
+ * closed rings in CSR form plus centroid / rmax per element (topography.jl:5-9). */
+int32_t SZ_FN(set_domain)(sz_handle *h, const int32_t kinds[4], const double vals[4],
+                          const double uv[8], const double rect[16], int32_t n_topo,
+                          const int64_t *topo_offsets, const double *topo_xy,
+                          const double *topo_centroid, const double *topo_rmax);
+/* Current wall positions (moving walls advance in sz_step_collisions, collisions.jl:565-571) */
+int32_t SZ_FN(get_domain)(sz_handle *h, double vals[4], double rect[16]);
+
+/* ---- floe state ---------------------------------------------------------------------------- */
+int32_t SZ_FN(upload_floes)(sz_handle *h, const sz_floe_soa *floes);
+int32_t SZ_FN(get_counts)(sz_handle *h, sz_counts *out);
+int32_t SZ_FN(download_floes)(sz_handle *h, sz_floe_soa *floes);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+int32_t SZ_FN(add_ghosts)(sz_handle *h, int64_t *n_total);        /* collisions.jl:1060-1174 */
+int32_t SZ_FN(step_collisions)(sz_handle *h);                     /* collisions.jl:734-864 */
+int32_t SZ_FN(remove_ghosts)(sz_handle *h);                       /* simulation.jl:138-144 */
+int32_t SZ_FN(step_coupling)(sz_handle *h);                       /* coupling.jl:1705-1738 */
+int32_t SZ_FN(step_floe_properties)(sz_handle *h, int64_t tstep); /* update_floe.jl:469-551 */
+/* One fused timestep without intermediate host synchronisation: add_ghosts, collisions,
+ * remove_ghosts, coupling (iff do_coupling != 0), floe properties. */
+int32_t SZ_FN(step)(sz_handle *h, int64_t tstep, int32_t do_coupling);
+
+/* ---- results ------------------------------------------------------------------------------- */
+/* interactions: offsets[n_total+1] and rows[n_rows][7] =
+ * (floeidx, xforce, yforce, xpoint, ypoint, torque, overlap), floe.jl:102-110.  Row order
+ * per floe follows the reference: own pairs (j ascending, regions in clip order), walls
+ * N,S,E,W, topography, mirrored rows, ghost rows.  Valid until the next step_collisions;
+ * after remove_ghosts only the first n_init floes are reported. */
+int32_t SZ_FN(get_interactions)(sz_handle *h, int64_t *offsets, double *rows);
+/* Seed the rows from the host (offsets[n_total+1], rows[C][7]); only needed when
+ * step_floe_properties is called without a preceding step_collisions on this handle
+ * (calc_stress! reads rows 1:num_inters, update_floe.jl:392-414). */
+int32_t SZ_FN(set_interactions)(sz_handle *h, const int64_t *offsets, const double *rows);
+/* (i,j) 1-based, lexicographically sorted; which = 0 candidates, 1 filtered pairs,
+ * 2 overlap pairs (total area > 0), 3 fuse pairs. `pairs` holds 2*count int64. */
+int32_t SZ_FN(get_pairs)(sz_handle *h, int32_t which, int64_t *pairs);
+int32_t SZ_FN(get_warnings)(sz_handle *h, uint32_t *bits); /* [n_init] */
+/* Device (or oracle wall-clock) time of the phases of the last step, milliseconds:
+ * [0] ghosts [1] broad phase [2] narrow phase [3] row assembly+reduction [4] coupling
+ * [5] floe properties [6] total */
+int32_t SZ_FN(get_timings)(sz_handle *h, double ms[8]);
+
+/* ---- geometry service (test hook; also what SURVEY §8(f) rank 2 reuses) ---------------------- */
+/* Clip two closed rings; regions are written as consecutive closed rings into out_xy
+ * (capacity cap_points points), region r = points [out_offsets[r], out_offsets[r+1]).
+ * Returns the number of regions (>= 0) or a negative status. */
+int32_t SZ_FN(clip_polygons)(sz_handle *h, const double *p_xy, int32_t np, const double *q_xy,
+                             int32_t nq, int32_t cap_regions, int32_t cap_points,
+                             int32_t *out_offsets, double *out_xy, double *out_areas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBZERO_B200_H */

@@ -1,0 +1,347 @@
+"""ctypes binding of include/subzero_b200.h.
+
+`Library(path, prefix)` binds one shared object.  The product library is
+`csrc/libsubzero_b200.so` (prefix `sz_`, CUDA sm_100a); the CPU oracle under `oracle/`
+exports the same ABI with prefix `szo_` and is bound with the same class — but ONLY by
+tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs (see oracle/szo.py).
+
+There is no CPU fallback: `product()` raises if the CUDA library is missing or fails to
+load, and `Handle` calls raise `SubzeroError` on any non-zero status.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(HERE, "csrc", "libsubzero_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_i64_p = C.POINTER(C.c_int64)
+c_i32_p = C.POINTER(C.c_int32)
+c_u32_p = C.POINTER(C.c_uint32)
+
+STATUS_ACTIVE, STATUS_REMOVE, STATUS_FUSE = 1, 2, 3
+BOUNDARY_OPEN, BOUNDARY_PERIODIC, BOUNDARY_COLLISION, BOUNDARY_MOVING = 0, 1, 2, 3
+WARN_HEIGHT_CAPPED, WARN_FORCE_SCALED, WARN_VELOCITY_LIMITED, WARN_XI_CLAMPED = 1, 2, 4, 8
+
+
+class SubzeroError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("subzero_b200 status %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "rho_o", "rho_a", "Cd_io", "Cd_ia", "Cd_ao", "f", "turn_theta", "L", "k", "nu", "mu", "E",
+        "floe_floe_max_overlap", "floe_domain_max_overlap",
+        "rho_i", "max_floe_height", "maximum_xi", "stress_lambda")] + [
+        (n, C.c_int32) for n in (
+            "coupling_dd", "two_way_coupling_on", "dt", "device", "max_regions_per_pair",
+            "max_pairs_per_floe", "threads", "reserved0")] + [("floe_capacity", C.c_int64)]
+
+
+DOUBLE_FIELDS = (
+    "centroid_x", "centroid_y", "height", "area", "mass", "rmax", "moment", "alpha", "u", "v",
+    "xi", "fxOA", "fyOA", "trqOA", "hflx_factor", "overarea", "collision_force", "collision_trq",
+    "stress_accum", "stress_instant", "strain", "p_dxdt", "p_dydt", "p_dudt", "p_dvdt", "p_dxidt",
+    "p_dalphadt")
+FIELD_WIDTH = {"collision_force": 2, "stress_accum": 4, "stress_instant": 4, "strain": 4}
+
+
+class FloeSoA(C.Structure):
+    _fields_ = ([("n", C.c_int64), ("n_init", C.c_int64)] +
+                [(n, c_double_p) for n in DOUBLE_FIELDS] +
+                [("status_tag", c_i32_p), ("id", c_i64_p), ("ghost_id", c_i64_p),
+                 ("ghost_offsets", c_i64_p), ("ghost_index", c_i64_p),
+                 ("vert_offsets", c_i64_p), ("vert_xy", c_double_p),
+                 ("mc_offsets", c_i64_p), ("mc_x", c_double_p), ("mc_y", c_double_p)])
+
+
+class Counts(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "n_init", "n_total", "n_vertices", "n_mc", "n_ghost_links", "n_candidates", "n_pairs",
+        "n_overlap", "n_fuse", "n_rows", "n_domain_pairs", "n_clip_fail")]
+
+    def asdict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_i64_p) if a is not None else None
+
+
+class Library:
+    """One loaded shared object exporting the subzero_b200 C ABI under `prefix`."""
+
+    SIGS = {
+        "default_config": (None, [C.POINTER(Config)]),
+        "create": (C.c_int32, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+        "destroy": (None, [C.c_void_p]),
+        "last_error": (C.c_char_p, [C.c_void_p]),
+        "version": (C.c_char_p, []),
+        "set_grid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_double] * 4),
+        "set_fields": (C.c_int32, [C.c_void_p] + [c_double_p] * 5),
+        "set_domain": (C.c_int32, [C.c_void_p, c_i32_p, c_double_p, c_double_p, c_double_p,
+                                   C.c_int32, c_i64_p, c_double_p, c_double_p, c_double_p]),
+        "get_domain": (C.c_int32, [C.c_void_p, c_double_p, c_double_p]),
+        "upload_floes": (C.c_int32, [C.c_void_p, C.POINTER(FloeSoA)]),
+        "get_counts": (C.c_int32, [C.c_void_p, C.POINTER(Counts)]),
+        "download_floes": (C.c_int32, [C.c_void_p, C.POINTER(FloeSoA)]),
+        "add_ghosts": (C.c_int32, [C.c_void_p, c_i64_p]),
+        "step_collisions": (C.c_int32, [C.c_void_p]),
+        "remove_ghosts": (C.c_int32, [C.c_void_p]),
+        "step_coupling": (C.c_int32, [C.c_void_p]),
+        "step_floe_properties": (C.c_int32, [C.c_void_p, C.c_int64]),
+        "step": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32]),
+        "get_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
+        "set_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
+        "get_pairs": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
+        "get_warnings": (C.c_int32, [C.c_void_p, c_u32_p]),
+        "get_timings": (C.c_int32, [C.c_void_p, c_double_p]),
+        "clip_polygons": (C.c_int32, [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
+                                      C.c_int32, C.c_int32, c_i32_p, c_double_p, c_double_p]),
+    }
+
+    def __init__(self, path, prefix="sz_"):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "%s not found — build it first (python -c 'import __graft_entry__ as g; g.build()')" % path)
+        self.path, self.prefix = path, prefix
+        self.dll = C.CDLL(path)
+        for name, (res, args) in self.SIGS.items():
+            fn = getattr(self.dll, prefix + name)  # AttributeError if a symbol is missing
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name, fn)
+
+    def exported(self):
+        return [self.prefix + n for n in self.SIGS]
+
+    def default_config_struct(self):
+        cfg = Config()
+        self.default_config(C.byref(cfg))
+        return cfg
+
+
+_product = None
+
+
+def product():
+    """The CUDA product library.  Fails loudly when it is missing: no CPU fallback exists."""
+    global _product
+    if _product is None:
+        _product = Library(PRODUCT_LIB, "sz_")
+    return _product
+
+
+class FloeArrays:
+    """Host-side SoA container matching sz_floe_soa (numpy arrays, caller-owned)."""
+
+    def __init__(self, n, n_init=None):
+        self.n = int(n)
+        self.n_init = self.n if n_init is None else int(n_init)
+        for name in DOUBLE_FIELDS:
+            w = FIELD_WIDTH.get(name, 1)
+            setattr(self, name, np.zeros((self.n, w) if w > 1 else self.n, dtype=np.float64))
+        self.status_tag = np.full(self.n, STATUS_ACTIVE, dtype=np.int32)
+        self.id = np.arange(1, self.n + 1, dtype=np.int64)
+        self.ghost_id = np.zeros(self.n, dtype=np.int64)
+        self.ghost_offsets = np.zeros(self.n + 1, dtype=np.int64)
+        self.ghost_index = np.zeros(0, dtype=np.int64)
+        self.vert_offsets = np.zeros(self.n + 1, dtype=np.int64)
+        self.vert_xy = np.zeros((0, 2), dtype=np.float64)
+        self.mc_offsets = np.zeros(self.n + 1, dtype=np.int64)
+        self.mc_x = np.zeros(0, dtype=np.float64)
+        self.mc_y = np.zeros(0, dtype=np.float64)
+
+    def as_struct(self):
+        s = FloeSoA()
+        s.n, s.n_init = self.n, self.n_init
+        keep = []
+        for name in DOUBLE_FIELDS + ("vert_xy", "mc_x", "mc_y"):
+            a = np.ascontiguousarray(getattr(self, name), dtype=np.float64)
+            setattr(self, name, a)
+            keep.append(a)
+            setattr(s, name, _dp(a))
+        a = np.ascontiguousarray(self.status_tag, dtype=np.int32)
+        self.status_tag = a
+        s.status_tag = a.ctypes.data_as(c_i32_p)
+        for name in ("id", "ghost_id", "ghost_offsets", "ghost_index", "vert_offsets", "mc_offsets"):
+            a = np.ascontiguousarray(getattr(self, name), dtype=np.int64)
+            setattr(self, name, a)
+            setattr(s, name, _ip(a))
+        s._keep = keep
+        return s
+
+    def ring(self, i):
+        return self.vert_xy[self.vert_offsets[i]:self.vert_offsets[i + 1]]
+
+    def ghosts(self, i):
+        return list(self.ghost_index[self.ghost_offsets[i]:self.ghost_offsets[i + 1]])
+
+
+class Handle:
+    """RAII wrapper of sz_handle for one Library."""
+
+    def __init__(self, lib, cfg=None, **overrides):
+        self.lib = lib
+        self.cfg = cfg if cfg is not None else lib.default_config_struct()
+        for k, v in overrides.items():
+            if not hasattr(self.cfg, k):
+                raise AttributeError("sz_config has no field %r" % k)
+            setattr(self.cfg, k, v)
+        self.h = C.c_void_p()
+        rc = lib.create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            raise SubzeroError(rc, "sz_create failed (library %s)" % lib.path)
+
+    def close(self):
+        if self.h:
+            self.lib.destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.last_error(self.h)
+            raise SubzeroError(rc, msg.decode() if msg else "")
+
+    # model description ------------------------------------------------------------------
+    def set_grid(self, Nx, Ny, x0, xf, y0, yf):
+        self._ck(self.lib.set_grid(self.h, Nx, Ny, x0, xf, y0, yf))
+        self.Nx, self.Ny = Nx, Ny
+
+    def set_fields(self, ocean_u, ocean_v, ocean_hflx, atmos_u, atmos_v):
+        arrs = []
+        for a in (ocean_u, ocean_v, ocean_hflx, atmos_u, atmos_v):
+            a = np.asarray(a, dtype=np.float64)
+            assert a.shape == (self.Nx + 1, self.Ny + 1), (a.shape, self.Nx, self.Ny)
+            arrs.append(np.asfortranarray(a).ravel(order="F"))  # element [ix + (Nx+1) iy]
+        self._ck(self.lib.set_fields(self.h, *[_dp(a) for a in arrs]))
+
+    def set_domain(self, kinds, vals, uv, rect, topo_rings=(), topo_centroid=None, topo_rmax=None):
+        kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(8)
+        rect = np.ascontiguousarray(rect, dtype=np.float64).reshape(16)
+        nt = len(topo_rings)
+        offs = np.zeros(nt + 1, dtype=np.int64)
+        for k, r in enumerate(topo_rings):
+            offs[k + 1] = offs[k] + len(r)
+        xy = (np.concatenate([np.asarray(r, dtype=np.float64) for r in topo_rings])
+              if nt else np.zeros((0, 2)))
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        cen = np.ascontiguousarray(topo_centroid if nt else np.zeros((0, 2)), dtype=np.float64)
+        rm = np.ascontiguousarray(topo_rmax if nt else np.zeros(0), dtype=np.float64)
+        self._ck(self.lib.set_domain(self.h, kinds.ctypes.data_as(c_i32_p), _dp(vals), _dp(uv),
+                                     _dp(rect), nt, _ip(offs), _dp(xy), _dp(cen), _dp(rm)))
+
+    def get_domain(self):
+        vals, rect = np.zeros(4), np.zeros(16)
+        self._ck(self.lib.get_domain(self.h, _dp(vals), _dp(rect)))
+        return vals, rect.reshape(4, 4)
+
+    # floe state ---------------------------------------------------------------------------
+    def upload_floes(self, fa):
+        s = fa.as_struct()
+        self._ck(self.lib.upload_floes(self.h, C.byref(s)))
+
+    def counts(self):
+        c = Counts()
+        self._ck(self.lib.get_counts(self.h, C.byref(c)))
+        return c.asdict()
+
+    def download_floes(self):
+        c = self.counts()
+        fa = FloeArrays(c["n_total"], c["n_init"])
+        fa.vert_xy = np.zeros((c["n_vertices"], 2))
+        fa.mc_x = np.zeros(c["n_mc"])
+        fa.mc_y = np.zeros(c["n_mc"])
+        fa.ghost_index = np.zeros(c["n_ghost_links"], dtype=np.int64)
+        s = fa.as_struct()
+        self._ck(self.lib.download_floes(self.h, C.byref(s)))
+        return fa
+
+    # hot path -------------------------------------------------------------------------------
+    def add_ghosts(self):
+        n = C.c_int64(0)
+        self._ck(self.lib.add_ghosts(self.h, C.byref(n)))
+        return n.value
+
+    def step_collisions(self):
+        self._ck(self.lib.step_collisions(self.h))
+
+    def remove_ghosts(self):
+        self._ck(self.lib.remove_ghosts(self.h))
+
+    def step_coupling(self):
+        self._ck(self.lib.step_coupling(self.h))
+
+    def step_floe_properties(self, tstep=0):
+        self._ck(self.lib.step_floe_properties(self.h, tstep))
+
+    def step(self, tstep=0, do_coupling=True):
+        self._ck(self.lib.step(self.h, tstep, 1 if do_coupling else 0))
+
+    # results ----------------------------------------------------------------------------------
+    def interactions(self):
+        c = self.counts()
+        offs = np.zeros(c["n_total"] + 1, dtype=np.int64)
+        rows = np.zeros((max(c["n_rows"], 1), 7))
+        self._ck(self.lib.get_interactions(self.h, _ip(offs), _dp(rows)))
+        return offs, rows[:c["n_rows"]]
+
+    def set_interactions(self, rows_per_floe):
+        n = len(rows_per_floe)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        for i, r in enumerate(rows_per_floe):
+            offs[i + 1] = offs[i] + len(r)
+        rows = (np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, 7) for r in rows_per_floe])
+                if offs[-1] else np.zeros((1, 7)))
+        rows = np.ascontiguousarray(rows)
+        self._ck(self.lib.set_interactions(self.h, _ip(offs), _dp(rows)))
+
+    def floe_interactions(self, i):
+        """Rows of floe i (0-based), shape (k, 7)."""
+        offs, rows = self.interactions()
+        return rows[offs[i]:offs[i + 1]]
+
+    def pairs(self, which):
+        key = ("n_candidates", "n_pairs", "n_overlap", "n_fuse")[which]
+        m = self.counts()[key]
+        out = np.zeros((max(m, 1), 2), dtype=np.int64)
+        self._ck(self.lib.get_pairs(self.h, which, _ip(out)))
+        return out[:m]
+
+    def warnings(self):
+        n = self.counts()["n_init"]
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._ck(self.lib.get_warnings(self.h, out.ctypes.data_as(c_u32_p)))
+        return out[:n]
+
+    def timings(self):
+        ms = np.zeros(8)
+        self._ck(self.lib.get_timings(self.h, _dp(ms)))
+        return dict(zip(("ghosts", "broad", "narrow", "reduce", "coupling", "update", "total"), ms[:7]))
+
+    def clip_polygons(self, p, q, cap_regions=64, cap_points=8192):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        offs = np.zeros(cap_regions + 1, dtype=np.int32)
+        xy = np.zeros((cap_points, 2))
+        areas = np.zeros(cap_regions)
+        n = self.lib.clip_polygons(self.h, _dp(p), len(p), _dp(q), len(q), cap_regions, cap_points,
+                                   offs.ctypes.data_as(c_i32_p), _dp(xy), _dp(areas))
+        if n < 0:
+            raise SubzeroError(n, "clip_polygons")
+        return [xy[offs[r]:offs[r + 1]].copy() for r in range(n)], areas[:n].copy()
