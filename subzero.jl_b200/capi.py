@@ -178,8 +178,20 @@ class FloeArrays:
         s._keep = keep
         return s
 
+    def adopt(self, fa):
+        """Take over the arrays of a downloaded FloeArrays (host-only attributes are kept)."""
+        keep = {k: getattr(self, k) for k in ("interactions", "num_inters", "fuse_idx", "warnings") if hasattr(self, k)}
+        self.__dict__.update(fa.__dict__)
+        self.__dict__.update(keep)
+
     def ring(self, i):
         return self.vert_xy[self.vert_offsets[i]:self.vert_offsets[i + 1]]
+
+    def centroid(self, i):
+        return np.array([self.centroid_x[i], self.centroid_y[i]])
+
+    def coords(self, i):
+        return self.ring(i)
 
     def ghosts(self, i):
         return list(self.ghost_index[self.ghost_offsets[i]:self.ghost_offsets[i + 1]])

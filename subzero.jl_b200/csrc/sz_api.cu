@@ -1,0 +1,879 @@
+// sz_api.cu — the C ABI of include/subzero_b200.h on top of the sm_100a kernels.
+//
+// Host side only: handle lifetime, device-store allocation / growth, host<->device marshalling
+// of the reference's Floe struct-of-arrays, stream / event plumbing and the capacity-overflow
+// retry loop.  No numerical work of the hot path happens here and there is no CPU fallback: when
+// no CUDA device is usable sz_create fails with SZ_ERR_CUDA.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "sz_common.cuh"
+
+#define NEV 8
+
+struct FloeArr {
+    void **ptr;
+    size_t elem;  // bytes per floe
+};
+
+struct sz_handle {
+    sz_config cfg;
+    char err[512];
+    Launch L;
+    Params P;
+    bool have_grid, have_fields, have_domain, have_floes;
+    DomainDev hD;
+    Store S;
+    StepBuf B;
+    std::vector<FloeArr> floe_arrays;   // persistent per-floe arrays (grown with a copy)
+    std::vector<void **> floe_scratch;  // int [cap_floes+1] scratch arrays (grown without)
+    int n_init, n_total, n_verts, n_verts_init;
+    long long n_mc;
+    int n_topo, topo_verts_n;
+    size_t field_n;
+    Counters *h_cnt;  // pinned mirror
+    Counters last;    // counters of the last collision step
+    int n_rows_host;
+    cudaEvent_t ev[NEV];
+    double ms[8];
+};
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            snprintf(h->err, sizeof(h->err), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                     __FILE__, __LINE__);                                                                \
+            return SZ_ERR_CUDA;                                                                          \
+        }                                                                                                \
+    } while (0)
+
+static int32_t fail(sz_handle *h, int32_t code, const char *msg) {
+    if (h) snprintf(h->err, sizeof(h->err), "%s", msg);
+    return code;
+}
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t count) {
+    *p = nullptr;
+    return cudaMalloc((void **)p, sizeof(T) * std::max<size_t>(count, 1));
+}
+template <typename T>
+static void dfree(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+extern "C" void sz_default_config(sz_config *c) {
+    memset(c, 0, sizeof(*c));
+    // Constants(), simulation.jl:5-18
+    c->rho_o = 1027.0; c->rho_a = 1.2; c->Cd_io = 3e-3; c->Cd_ia = 1e-3; c->Cd_ao = 1.25e-3;
+    c->f = 1.4e-4; c->turn_theta = 15.0 * 3.14159265358979323846 / 180.0; c->L = 2.93e5; c->k = 2.14;
+    c->nu = 0.3; c->mu = 0.2; c->E = 6e6;
+    // CollisionSettings(), process_settings.jl:183-187
+    c->floe_floe_max_overlap = 0.55; c->floe_domain_max_overlap = 0.75;
+    // FloeSettings(), process_settings.jl:20-32; DecayAreaScaledCalculator, stress_calculators.jl:82
+    c->rho_i = 920.0; c->max_floe_height = 10.0; c->maximum_xi = 1e-5; c->stress_lambda = 0.2;
+    c->coupling_dd = 1; c->two_way_coupling_on = 0; c->dt = 10; c->device = 0;
+    c->max_regions_per_pair = 4; c->max_pairs_per_floe = 24;
+}
+
+extern "C" const char *sz_version(void) { return "subzero-b200 0.1 (CUDA sm_100a)"; }
+extern "C" const char *sz_last_error(sz_handle *h) { return h ? h->err : "null handle"; }
+
+static void register_arrays(sz_handle *h) {
+    Store &S = h->S;
+    StepBuf &B = h->B;
+    auto add = [&](void **p, size_t e) { h->floe_arrays.push_back({p, e}); };
+#define D1(f) add((void **)&S.f, sizeof(double));
+    D1(cx) D1(cy) D1(height) D1(area) D1(mass) D1(rmax) D1(moment) D1(alpha) D1(u) D1(v) D1(xi) D1(fxOA) D1(fyOA)
+    D1(trqOA) D1(hflx) D1(overarea) D1(cfx) D1(cfy) D1(ctrq) D1(p_dxdt) D1(p_dydt) D1(p_dudt) D1(p_dvdt) D1(p_dxidt)
+    D1(p_dalphadt)
+#undef D1
+    add((void **)&S.stress_accum, 4 * sizeof(double));
+    add((void **)&S.stress_instant, 4 * sizeof(double));
+    add((void **)&S.strain, 4 * sizeof(double));
+    add((void **)&S.status, sizeof(int));
+    add((void **)&S.id, sizeof(long long));
+    add((void **)&S.ghost_id, sizeof(long long));
+    add((void **)&S.parent, sizeof(int));
+    add((void **)&S.nghost, sizeof(int));
+    add((void **)&S.ghost_slot, SZ_MAX_GHOSTS * sizeof(int));
+    add((void **)&S.warn, sizeof(uint32_t));
+    add((void **)&S.vstart, sizeof(int));
+    add((void **)&S.vcount, sizeof(int));
+    void **scr[] = {(void **)&B.cell_of, (void **)&B.cell_items, (void **)&B.up_count, (void **)&B.up_off,
+                    (void **)&B.low_count, (void **)&B.low_off, (void **)&B.dom_count, (void **)&B.dom_off,
+                    (void **)&B.row_pre, (void **)&B.row_count, (void **)&B.row_off, (void **)&B.g_flag,
+                    (void **)&B.g_cnt, (void **)&B.g_off, (void **)&B.g_vcnt, (void **)&B.g_voff};
+    for (void **p : scr) h->floe_scratch.push_back(p);
+}
+
+// grow every per-floe array to new_cap floes, keeping the first `keep` entries
+static int32_t grow_floes(sz_handle *h, int new_cap, int keep) {
+    for (FloeArr &a : h->floe_arrays) {
+        void *np = nullptr;
+        CK(cudaMalloc(&np, a.elem * (size_t)std::max(new_cap, 1)));
+        if (keep > 0 && *a.ptr) CK(cudaMemcpyAsync(np, *a.ptr, a.elem * (size_t)keep, cudaMemcpyDeviceToDevice, h->L.stream));
+        CK(cudaStreamSynchronize(h->L.stream));
+        if (*a.ptr) cudaFree(*a.ptr);
+        *a.ptr = np;
+    }
+    for (void **p : h->floe_scratch) {
+        void *np = nullptr;
+        CK(cudaMalloc(&np, sizeof(int) * ((size_t)new_cap + 2)));
+        if (p == (void **)&h->B.row_off) {
+            CK(cudaMemsetAsync(np, 0, sizeof(int) * ((size_t)new_cap + 2), h->L.stream));
+            if (keep > 0 && *p) CK(cudaMemcpyAsync(np, *p, sizeof(int) * ((size_t)keep + 1), cudaMemcpyDeviceToDevice, h->L.stream));
+            CK(cudaStreamSynchronize(h->L.stream));
+        }
+        if (*p) cudaFree(*p);
+        *p = np;
+    }
+    h->S.cap_floes = new_cap;
+    // grid cells and scan scratch follow the floe capacity
+    int cells = 4 * new_cap + 64;
+    dfree(h->B.cell_count); dfree(h->B.cell_start); dfree(h->B.cell_fill); dfree(h->B.scan_block);
+    CK(dalloc(&h->B.cell_count, (size_t)cells + 2));
+    CK(dalloc(&h->B.cell_start, (size_t)cells + 2));
+    CK(dalloc(&h->B.cell_fill, (size_t)cells + 2));
+    CK(dalloc(&h->B.scan_block, (size_t)cells / 4096 + 8));
+    h->B.cap_cells = cells;
+    return SZ_OK;
+}
+
+static int32_t grow_verts(sz_handle *h, int new_cap, int keep) {
+    double2 *np = nullptr;
+    CK(dalloc(&np, (size_t)new_cap));
+    if (keep > 0 && h->S.verts) CK(cudaMemcpy(np, h->S.verts, sizeof(double2) * (size_t)keep, cudaMemcpyDeviceToDevice));
+    dfree(h->S.verts);
+    h->S.verts = np;
+    h->S.cap_verts = new_cap;
+    return SZ_OK;
+}
+
+static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
+    StepBuf &B = h->B;
+    dfree(B.pair_i); dfree(B.pair_j); dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem);
+    dfree(B.item_nrows); dfree(B.item_row0); dfree(B.item_flags); dfree(B.large_items);
+    CK(dalloc(&B.pair_i, (size_t)cap_pairs));
+    CK(dalloc(&B.pair_j, (size_t)cap_pairs));
+    CK(dalloc(&B.low_pair, (size_t)cap_pairs));
+    CK(dalloc(&B.keep, (size_t)cap_pairs));
+    CK(dalloc(&B.dom_floe, (size_t)cap_dom));
+    CK(dalloc(&B.dom_elem, (size_t)cap_dom));
+    size_t items = (size_t)cap_pairs + cap_dom;
+    CK(dalloc(&B.item_nrows, items));
+    CK(dalloc(&B.item_row0, items));
+    CK(dalloc(&B.item_flags, items));
+    CK(dalloc(&B.large_items, items));
+    B.cap_pairs = cap_pairs;
+    B.cap_dom = cap_dom;
+    return SZ_OK;
+}
+static int32_t set_pool_cap(sz_handle *h, int cap) {
+    dfree(h->B.pool);
+    CK(dalloc(&h->B.pool, (size_t)cap * NPOOL));
+    h->B.cap_pool = cap;
+    return SZ_OK;
+}
+static int32_t set_row_cap(sz_handle *h, int cap) {
+    dfree(h->B.rows);
+    CK(dalloc(&h->B.rows, (size_t)cap * NCOL));
+    h->B.cap_rows = cap;
+    return SZ_OK;
+}
+static int32_t set_fuse_cap(sz_handle *h, int cap) {
+    dfree(h->B.fuse_pairs);
+    CK(dalloc(&h->B.fuse_pairs, (size_t)cap));
+    h->B.cap_fuse = cap;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
+    if (!cfg || !out) return SZ_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->two_way_coupling_on) return SZ_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) return SZ_ERR_CUDA;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return SZ_ERR_CUDA;
+    sz_handle *h = new (std::nothrow) sz_handle();
+    if (!h) return SZ_ERR_NOMEM;
+    memset(&h->S, 0, sizeof(h->S));
+    memset(&h->B, 0, sizeof(h->B));
+    memset(&h->hD, 0, sizeof(h->hD));
+    memset(&h->P, 0, sizeof(h->P));
+    memset(&h->last, 0, sizeof(h->last));
+    memset(h->ms, 0, sizeof(h->ms));
+    h->err[0] = 0;
+    h->cfg = *cfg;
+    h->P.cfg = *cfg;
+    h->have_grid = h->have_fields = h->have_domain = h->have_floes = false;
+    h->n_init = h->n_total = h->n_verts = h->n_verts_init = 0;
+    h->n_mc = 0; h->n_topo = 0; h->topo_verts_n = 0; h->field_n = 0; h->n_rows_host = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    h->L.sms = prop.multiProcessorCount;
+    h->L.maxv_large = 1024;
+    h->L.maxx_large = 256;
+    if (cudaStreamCreateWithFlags(&h->L.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    for (int k = 0; k < NEV; ++k) cudaEventCreate(&h->ev[k]);
+    if (cudaMallocHost((void **)&h->h_cnt, sizeof(Counters)) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    memset(h->h_cnt, 0, sizeof(Counters));
+    if (dalloc(&h->S.cnt, 1) != cudaSuccess || dalloc(&h->S.dom, 1) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    cudaMemset(h->S.cnt, 0, sizeof(Counters));
+    cudaMemset(h->S.dom, 0, sizeof(DomainDev));
+    if (szk_configure(h->L) != 0) { delete h; return SZ_ERR_CUDA; }
+    register_arrays(h);
+    *out = h;
+    return SZ_OK;
+}
+
+extern "C" void sz_destroy(sz_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->L.stream);
+    for (FloeArr &a : h->floe_arrays) if (*a.ptr) cudaFree(*a.ptr);
+    for (void **p : h->floe_scratch) if (*p) cudaFree(*p);
+    Store &S = h->S;
+    StepBuf &B = h->B;
+    dfree(S.verts); dfree(S.mc_off); dfree(S.mc); dfree(S.topo_vstart); dfree(S.topo_vcount); dfree(S.topo_verts);
+    dfree(S.topo_cx); dfree(S.topo_cy); dfree(S.topo_rmax); dfree(S.ocn_u); dfree(S.ocn_v); dfree(S.ocn_hflx);
+    dfree(S.atm_u); dfree(S.atm_v); dfree(S.cnt); dfree(S.dom);
+    dfree(B.cell_count); dfree(B.cell_start); dfree(B.cell_fill); dfree(B.scan_block); dfree(B.pair_i); dfree(B.pair_j);
+    dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
+    dfree(B.item_flags); dfree(B.large_items); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    for (int k = 0; k < NEV; ++k) cudaEventDestroy(h->ev[k]);
+    cudaStreamDestroy(h->L.stream);
+    delete h;
+}
+
+// ---- model description ---------------------------------------------------------------------------
+extern "C" int32_t sz_set_grid(sz_handle *h, int32_t Nx, int32_t Ny, double x0, double xf, double y0, double yf) {
+    if (!h || Nx < 1 || Ny < 1 || !(xf > x0) || !(yf > y0)) return fail(h, SZ_ERR_INVALID, "set_grid: bad extent");
+    h->P.Nx = Nx; h->P.Ny = Ny; h->P.x0 = x0; h->P.xf = xf; h->P.y0 = y0; h->P.yf = yf;
+    h->P.dx = (xf - x0) / Nx;  // grids.jl:180-211
+    h->P.dy = (yf - y0) / Ny;
+    h->have_grid = true;
+    h->have_fields = false;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_set_fields(sz_handle *h, const double *ou, const double *ov, const double *oh, const double *au,
+                                 const double *av) {
+    if (!h || !h->have_grid) return fail(h, SZ_ERR_INVALID, "set_fields before set_grid");
+    cudaSetDevice(h->cfg.device);
+    size_t n = (size_t)(h->P.Nx + 1) * (size_t)(h->P.Ny + 1);
+    Store &S = h->S;
+    if (n != h->field_n) {
+        dfree(S.ocn_u); dfree(S.ocn_v); dfree(S.ocn_hflx); dfree(S.atm_u); dfree(S.atm_v);
+        CK(dalloc(&S.ocn_u, n)); CK(dalloc(&S.ocn_v, n)); CK(dalloc(&S.ocn_hflx, n));
+        CK(dalloc(&S.atm_u, n)); CK(dalloc(&S.atm_v, n));
+        h->field_n = n;
+    }
+    const double *src[5] = {ou, ov, oh, au, av};
+    double *dst[5] = {S.ocn_u, S.ocn_v, S.ocn_hflx, S.atm_u, S.atm_v};
+    for (int k = 0; k < 5; ++k) {
+        if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], sizeof(double) * n, cudaMemcpyHostToDevice, h->L.stream));
+        else CK(cudaMemsetAsync(dst[k], 0, sizeof(double) * n, h->L.stream));
+    }
+    CK(cudaStreamSynchronize(h->L.stream));
+    h->have_fields = true;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_set_domain(sz_handle *h, const int32_t kinds[4], const double vals[4], const double uv[8],
+                                 const double rect[16], int32_t n_topo, const int64_t *toff, const double *txy,
+                                 const double *tcent, const double *trmax) {
+    if (!h || !kinds || !vals || !rect) return fail(h, SZ_ERR_INVALID, "set_domain: null argument");
+    // domains.jl:11-33
+    if ((kinds[0] == SZ_BOUNDARY_PERIODIC) != (kinds[1] == SZ_BOUNDARY_PERIODIC) ||
+        (kinds[2] == SZ_BOUNDARY_PERIODIC) != (kinds[3] == SZ_BOUNDARY_PERIODIC))
+        return fail(h, SZ_ERR_INVALID, "set_domain: periodic boundaries must be paired");
+    if (!(vals[0] > vals[1]) || !(vals[2] > vals[3])) return fail(h, SZ_ERR_INVALID, "set_domain: north <= south or east <= west");
+    if (n_topo < 0 || (n_topo > 0 && (!toff || !txy || !tcent || !trmax))) return fail(h, SZ_ERR_INVALID, "set_domain: topography arrays missing");
+    cudaSetDevice(h->cfg.device);
+    DomainDev &D = h->hD;
+    for (int w = 0; w < 4; ++w) {
+        D.kind[w] = kinds[w];
+        D.val[w] = vals[w];
+        D.wu[w] = uv ? uv[2 * w] : 0.0;
+        D.wv[w] = uv ? uv[2 * w + 1] : 0.0;
+        for (int k = 0; k < 4; ++k) D.rect[w][k] = rect[4 * w + k];
+    }
+    D.n_topo = n_topo;
+    Store &S = h->S;
+    dfree(S.topo_vstart); dfree(S.topo_vcount); dfree(S.topo_verts); dfree(S.topo_cx); dfree(S.topo_cy); dfree(S.topo_rmax);
+    if (n_topo > 0) {
+        std::vector<int> vs(n_topo), vc(n_topo);
+        std::vector<double> cx(n_topo), cy(n_topo);
+        for (int k = 0; k < n_topo; ++k) {
+            vs[k] = (int)toff[k];
+            vc[k] = (int)(toff[k + 1] - toff[k]);
+            if (vc[k] < 4) return fail(h, SZ_ERR_INVALID, "set_domain: a topography ring needs >= 4 points (closed)");
+            if (vc[k] > h->L.maxv_large) return fail(h, SZ_ERR_UNSUPPORTED, "set_domain: topography ring exceeds 1024 points");
+            cx[k] = tcent[2 * k];
+            cy[k] = tcent[2 * k + 1];
+        }
+        size_t nv = (size_t)toff[n_topo];
+        CK(dalloc(&S.topo_vstart, n_topo)); CK(dalloc(&S.topo_vcount, n_topo)); CK(dalloc(&S.topo_verts, nv));
+        CK(dalloc(&S.topo_cx, n_topo)); CK(dalloc(&S.topo_cy, n_topo)); CK(dalloc(&S.topo_rmax, n_topo));
+        CK(cudaMemcpy(S.topo_vstart, vs.data(), sizeof(int) * n_topo, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.topo_vcount, vc.data(), sizeof(int) * n_topo, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.topo_verts, txy, sizeof(double2) * nv, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.topo_cx, cx.data(), sizeof(double) * n_topo, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.topo_cy, cy.data(), sizeof(double) * n_topo, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.topo_rmax, trmax, sizeof(double) * n_topo, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpy(S.dom, &D, sizeof(DomainDev), cudaMemcpyHostToDevice));
+    h->n_topo = n_topo;
+    h->have_domain = true;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_get_domain(sz_handle *h, double vals[4], double rect[16]) {
+    if (!h || !h->have_domain) return fail(h, SZ_ERR_INVALID, "get_domain before set_domain");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    CK(cudaMemcpy(&h->hD, h->S.dom, sizeof(DomainDev), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < 4; ++w) {
+        vals[w] = h->hD.val[w];
+        for (int k = 0; k < 4; ++k) rect[4 * w + k] = h->hD.rect[w][k];
+    }
+    return SZ_OK;
+}
+
+// ---- floe state -----------------------------------------------------------------------------------
+static int32_t sync_counters(sz_handle *h) {
+    CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->L.stream));
+    CK(cudaStreamSynchronize(h->L.stream));
+    h->n_total = h->h_cnt->n_total;
+    h->n_verts = h->h_cnt->n_verts;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
+    if (!h || !s || s->n < 0 || s->n_init < 0 || s->n_init > s->n) return fail(h, SZ_ERR_INVALID, "upload_floes: bad sizes");
+    if (s->n > 0 && (!s->centroid_x || !s->centroid_y || !s->area || !s->rmax || !s->vert_offsets || !s->vert_xy))
+        return fail(h, SZ_ERR_INVALID, "upload_floes: geometry arrays are required");
+    if (s->n > (1ll << 28)) return fail(h, SZ_ERR_UNSUPPORTED, "upload_floes: too many floes");
+    cudaSetDevice(h->cfg.device);
+    const int n = (int)s->n, n_init = (int)s->n_init;
+    const long long V = n > 0 ? s->vert_offsets[n] : 0;
+    const long long M = (s->mc_offsets && n > 0) ? s->mc_offsets[n] : 0;
+    if (V > (1ll << 30)) return fail(h, SZ_ERR_UNSUPPORTED, "upload_floes: too many vertices");
+    std::vector<int> vstart(n), vcount(n), parent(n, -1), nghost(n, 0), gslot((size_t)n * SZ_MAX_GHOSTS, 0);
+    for (int i = 0; i < n; ++i) {
+        long long a = s->vert_offsets[i], b = s->vert_offsets[i + 1];
+        if (b - a < 4) return fail(h, SZ_ERR_INVALID, "upload_floes: a ring needs >= 4 points (closed)");
+        if (b - a > h->L.maxv_large) return fail(h, SZ_ERR_UNSUPPORTED, "upload_floes: a ring exceeds 1024 points");
+        const double *r = s->vert_xy + 2 * a;
+        if (r[0] != r[2 * (b - a - 1)] || r[1] != r[2 * (b - a - 1) + 1]) return fail(h, SZ_ERR_INVALID, "upload_floes: rings must be closed");
+        vstart[i] = (int)a;
+        vcount[i] = (int)(b - a);
+    }
+    if (s->ghost_offsets) {
+        for (int i = 0; i < n; ++i) {
+            long long a = s->ghost_offsets[i], b = s->ghost_offsets[i + 1];
+            if (b - a > SZ_MAX_GHOSTS) return fail(h, SZ_ERR_INVALID, "upload_floes: a floe has more than 3 ghosts");
+            nghost[i] = (int)(b - a);
+            for (long long g = a; g < b; ++g) {
+                long long gi = s->ghost_index[g] - 1;
+                if (gi < 0 || gi >= n) return fail(h, SZ_ERR_INVALID, "upload_floes: ghost index out of range");
+                gslot[(size_t)i * SZ_MAX_GHOSTS + (g - a)] = (int)gi;
+                parent[gi] = i;
+            }
+        }
+    }
+    // capacities
+    int want_cap = h->cfg.floe_capacity > 0 ? (int)h->cfg.floe_capacity
+                                            : n + std::max(64, std::min(3 * n_init, n_init / 2 + 4096));
+    if (want_cap < n) want_cap = n;
+    if (want_cap > h->S.cap_floes || !h->S.cx) {
+        int32_t rc = grow_floes(h, want_cap, 0);
+        if (rc) return rc;
+    }
+    long long want_v = V + (long long)(n_init > 0 ? (V / std::max(n, 1) + 1) : 0) * (h->S.cap_floes - n) + 64;
+    if (want_v > h->S.cap_verts || !h->S.verts) {
+        int32_t rc = grow_verts(h, (int)std::min<long long>(want_v, 1ll << 30), 0);
+        if (rc) return rc;
+    }
+    Store &S = h->S;
+    if (M > S.cap_mc || !S.mc) {
+        dfree(S.mc);
+        CK(dalloc(&S.mc, (size_t)M));
+        S.cap_mc = M;
+    }
+    dfree(S.mc_off);
+    CK(dalloc(&S.mc_off, (size_t)n_init + 2));
+    StepBuf &B = h->B;
+    int ppf = h->cfg.max_pairs_per_floe > 0 ? h->cfg.max_pairs_per_floe : 24;
+    long long want_pairs = (long long)ppf * S.cap_floes / 2 + 1024, want_domc = (long long)S.cap_floes / 2 + 4096 + 4ll * n;
+    if (h->n_topo > 0) want_domc += (long long)S.cap_floes;
+    want_pairs = std::min<long long>(want_pairs, 1ll << 30);
+    want_domc = std::min<long long>(want_domc, 1ll << 30);
+    if (want_pairs > B.cap_pairs || want_domc > B.cap_dom || !B.pair_i) {
+        int32_t rc = set_pair_cap(h, (int)std::max<long long>(want_pairs, B.cap_pairs), (int)std::max<long long>(want_domc, B.cap_dom));
+        if (rc) return rc;
+    }
+    long long want_pool = want_pairs / 2 + want_domc + 1024;
+    if (want_pool > B.cap_pool || !B.pool) { int32_t rc = set_pool_cap(h, (int)want_pool); if (rc) return rc; }
+    long long want_rows = 2 * want_pool;
+    if (want_rows > B.cap_rows || !B.rows) { int32_t rc = set_row_cap(h, (int)std::min<long long>(want_rows, 1ll << 28)); if (rc) return rc; }
+    if (!B.fuse_pairs) { int32_t rc = set_fuse_cap(h, std::max(1024, S.cap_floes)); if (rc) return rc; }
+    // copies
+    cudaStream_t st = h->L.stream;
+    std::vector<double> zeros;
+    auto up = [&](double *dst, const double *src, size_t w) -> cudaError_t {
+        if (n == 0) return cudaSuccess;
+        if (src) return cudaMemcpyAsync(dst, src, sizeof(double) * w * n, cudaMemcpyHostToDevice, st);
+        return cudaMemsetAsync(dst, 0, sizeof(double) * w * n, st);
+    };
+    CK(up(S.cx, s->centroid_x, 1)); CK(up(S.cy, s->centroid_y, 1)); CK(up(S.height, s->height, 1));
+    CK(up(S.area, s->area, 1)); CK(up(S.mass, s->mass, 1)); CK(up(S.rmax, s->rmax, 1)); CK(up(S.moment, s->moment, 1));
+    CK(up(S.alpha, s->alpha, 1)); CK(up(S.u, s->u, 1)); CK(up(S.v, s->v, 1)); CK(up(S.xi, s->xi, 1));
+    CK(up(S.fxOA, s->fxOA, 1)); CK(up(S.fyOA, s->fyOA, 1)); CK(up(S.trqOA, s->trqOA, 1));
+    CK(up(S.hflx, s->hflx_factor, 1)); CK(up(S.overarea, s->overarea, 1)); CK(up(S.ctrq, s->collision_trq, 1));
+    CK(up(S.p_dxdt, s->p_dxdt, 1)); CK(up(S.p_dydt, s->p_dydt, 1)); CK(up(S.p_dudt, s->p_dudt, 1));
+    CK(up(S.p_dvdt, s->p_dvdt, 1)); CK(up(S.p_dxidt, s->p_dxidt, 1)); CK(up(S.p_dalphadt, s->p_dalphadt, 1));
+    CK(up(S.stress_accum, s->stress_accum, 4)); CK(up(S.stress_instant, s->stress_instant, 4)); CK(up(S.strain, s->strain, 4));
+    std::vector<double> cf((size_t)2 * n, 0.0);
+    if (s->collision_force)
+        for (int i = 0; i < n; ++i) { cf[i] = s->collision_force[2 * i]; cf[(size_t)n + i] = s->collision_force[2 * i + 1]; }
+    std::vector<int> status(n, SZ_STATUS_ACTIVE);
+    std::vector<long long> id(n), gid(n, 0);
+    for (int i = 0; i < n; ++i) {
+        if (s->status_tag) status[i] = s->status_tag[i];
+        id[i] = s->id ? s->id[i] : i + 1;
+        if (s->ghost_id) gid[i] = s->ghost_id[i];
+    }
+    if (n > 0) {
+        CK(cudaMemcpyAsync(S.cfx, cf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.cfy, cf.data() + n, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.status, status.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.id, id.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.ghost_id, gid.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.parent, parent.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.nghost, nghost.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.ghost_slot, gslot.data(), sizeof(int) * SZ_MAX_GHOSTS * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.vstart, vstart.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.vcount, vcount.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(S.warn, 0, sizeof(uint32_t) * n, st));
+        CK(cudaMemcpyAsync(S.verts, s->vert_xy, sizeof(double2) * (size_t)V, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<long long> mo((size_t)n_init + 1, 0);
+    if (s->mc_offsets) for (int i = 0; i <= n_init; ++i) mo[i] = s->mc_offsets[i];
+    CK(cudaMemcpyAsync(S.mc_off, mo.data(), sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyHostToDevice, st));
+    long long Mi = mo[n_init];
+    if (Mi > 0) {
+        double *tx = nullptr, *ty = nullptr;
+        CK(dalloc(&tx, (size_t)Mi)); CK(dalloc(&ty, (size_t)Mi));
+        CK(cudaMemcpyAsync(tx, s->mc_x, sizeof(double) * Mi, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ty, s->mc_y, sizeof(double) * Mi, cudaMemcpyHostToDevice, st));
+        szk_interleave(h->L, tx, ty, S.mc, Mi);
+        CK(cudaStreamSynchronize(st));
+        cudaFree(tx); cudaFree(ty);
+    }
+    CK(cudaMemsetAsync(B.row_off, 0, sizeof(int) * ((size_t)S.cap_floes + 2), st));
+    S.n_init = n_init;
+    szk_set_counts(h->L, S, n, (int)V);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    h->n_init = n_init; h->n_total = n; h->n_verts = (int)V; h->n_mc = Mi;
+    h->n_verts_init = n_init > 0 ? (int)s->vert_offsets[n_init] : 0;
+    h->n_rows_host = 0;
+    memset(&h->last, 0, sizeof(h->last));
+    h->have_floes = true;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_get_counts(sz_handle *h, sz_counts *c) {
+    if (!h || !c) return SZ_ERR_INVALID;
+    memset(c, 0, sizeof(*c));
+    c->n_init = h->n_init;
+    c->n_total = h->n_total;
+    c->n_vertices = h->n_verts;
+    c->n_mc = h->n_mc;
+    if (h->have_floes && h->n_total > 0) {
+        cudaSetDevice(h->cfg.device);
+        std::vector<int> ng(h->n_total);
+        CK(cudaMemcpy(ng.data(), h->S.nghost, sizeof(int) * h->n_total, cudaMemcpyDeviceToHost));
+        for (int v : ng) c->n_ghost_links += v;
+        int nr = 0;
+        CK(cudaMemcpy(&nr, h->B.row_off + h->n_total, sizeof(int), cudaMemcpyDeviceToHost));
+        c->n_rows = nr;
+    }
+    c->n_candidates = h->last.n_cand;
+    c->n_pairs = h->last.n_kept;
+    c->n_overlap = h->last.n_overlap;
+    c->n_fuse = h->last.n_fuse;
+    c->n_domain_pairs = h->last.n_domchecks;
+    c->n_clip_fail = h->last.n_clipfail;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_download_floes(sz_handle *h, sz_floe_soa *s) {
+    if (!h || !s) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "download_floes before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    cudaStream_t st = h->L.stream;
+    CK(cudaStreamSynchronize(st));
+    const int n = h->n_total, n_init = h->n_init;
+    Store &S = h->S;
+    s->n = n;
+    s->n_init = n_init;
+    if (n == 0) return SZ_OK;
+    auto dn = [&](double *dst, const double *src, size_t w) -> cudaError_t {
+        if (!dst) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, sizeof(double) * w * n, cudaMemcpyDeviceToHost, st);
+    };
+    CK(dn(s->centroid_x, S.cx, 1)); CK(dn(s->centroid_y, S.cy, 1)); CK(dn(s->height, S.height, 1));
+    CK(dn(s->area, S.area, 1)); CK(dn(s->mass, S.mass, 1)); CK(dn(s->rmax, S.rmax, 1)); CK(dn(s->moment, S.moment, 1));
+    CK(dn(s->alpha, S.alpha, 1)); CK(dn(s->u, S.u, 1)); CK(dn(s->v, S.v, 1)); CK(dn(s->xi, S.xi, 1));
+    CK(dn(s->fxOA, S.fxOA, 1)); CK(dn(s->fyOA, S.fyOA, 1)); CK(dn(s->trqOA, S.trqOA, 1));
+    CK(dn(s->hflx_factor, S.hflx, 1)); CK(dn(s->overarea, S.overarea, 1)); CK(dn(s->collision_trq, S.ctrq, 1));
+    CK(dn(s->p_dxdt, S.p_dxdt, 1)); CK(dn(s->p_dydt, S.p_dydt, 1)); CK(dn(s->p_dudt, S.p_dudt, 1));
+    CK(dn(s->p_dvdt, S.p_dvdt, 1)); CK(dn(s->p_dxidt, S.p_dxidt, 1)); CK(dn(s->p_dalphadt, S.p_dalphadt, 1));
+    CK(dn(s->stress_accum, S.stress_accum, 4)); CK(dn(s->stress_instant, S.stress_instant, 4)); CK(dn(s->strain, S.strain, 4));
+    std::vector<double> cf;
+    if (s->collision_force) {
+        cf.resize((size_t)2 * n);
+        CK(cudaMemcpyAsync(cf.data(), S.cfx, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cf.data() + n, S.cfy, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int> status, vstart(n), vcount(n), nghost(n), gslot((size_t)n * SZ_MAX_GHOSTS);
+    if (s->status_tag) CK(cudaMemcpyAsync(s->status_tag, S.status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (s->id) CK(cudaMemcpyAsync(s->id, S.id, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    if (s->ghost_id) CK(cudaMemcpyAsync(s->ghost_id, S.ghost_id, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vstart.data(), S.vstart, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vcount.data(), S.vcount, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nghost.data(), S.nghost, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(gslot.data(), S.ghost_slot, sizeof(int) * SZ_MAX_GHOSTS * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (s->collision_force)
+        for (int i = 0; i < n; ++i) { s->collision_force[2 * i] = cf[i]; s->collision_force[2 * i + 1] = cf[(size_t)n + i]; }
+    // rings: the device keeps them in floe order (ghost rings appended), so one contiguous copy
+    long long vo = 0;
+    bool contiguous = true;
+    for (int i = 0; i < n; ++i) {
+        if (vstart[i] != vo) contiguous = false;
+        if (s->vert_offsets) s->vert_offsets[i] = vo;
+        vo += vcount[i];
+    }
+    if (s->vert_offsets) s->vert_offsets[n] = vo;
+    if (s->vert_xy) {
+        if (contiguous) {
+            CK(cudaMemcpy(s->vert_xy, S.verts, sizeof(double2) * (size_t)vo, cudaMemcpyDeviceToHost));
+        } else {
+            long long o = 0;
+            for (int i = 0; i < n; ++i) {
+                CK(cudaMemcpy(s->vert_xy + 2 * o, S.verts + vstart[i], sizeof(double2) * vcount[i], cudaMemcpyDeviceToHost));
+                o += vcount[i];
+            }
+        }
+    }
+    if (s->mc_offsets) {
+        std::vector<long long> mo((size_t)n_init + 1);
+        CK(cudaMemcpy(mo.data(), S.mc_off, sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyDeviceToHost));
+        for (int i = 0; i <= n; ++i) s->mc_offsets[i] = mo[std::min(i, n_init)];
+    }
+    if ((s->mc_x || s->mc_y) && h->n_mc > 0) {
+        double *tx = nullptr, *ty = nullptr;
+        CK(dalloc(&tx, (size_t)h->n_mc)); CK(dalloc(&ty, (size_t)h->n_mc));
+        szk_deinterleave(h->L, S.mc, tx, ty, h->n_mc);
+        if (s->mc_x) CK(cudaMemcpyAsync(s->mc_x, tx, sizeof(double) * h->n_mc, cudaMemcpyDeviceToHost, st));
+        if (s->mc_y) CK(cudaMemcpyAsync(s->mc_y, ty, sizeof(double) * h->n_mc, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        cudaFree(tx); cudaFree(ty);
+    }
+    long long go = 0;
+    for (int i = 0; i < n; ++i) {
+        if (s->ghost_offsets) s->ghost_offsets[i] = go;
+        for (int g = 0; g < nghost[i]; ++g) {
+            if (s->ghost_index) s->ghost_index[go] = gslot[(size_t)i * SZ_MAX_GHOSTS + g] + 1;
+            go++;
+        }
+    }
+    if (s->ghost_offsets) s->ghost_offsets[n] = go;
+    return SZ_OK;
+}
+
+// ---- the hot path ---------------------------------------------------------------------------------------
+static const char *errbits(uint32_t e, char *buf, size_t len) {
+    snprintf(buf, len, "device buffer overflow:%s%s%s%s%s%s%s%s%s", (e & ERR_PAIR_CAP) ? " pairs" : "",
+             (e & ERR_POOL_CAP) ? " contact-pool" : "", (e & ERR_ROW_CAP) ? " rows" : "", (e & ERR_GHOST_CAP) ? " ghost-floes" : "",
+             (e & ERR_VERT_CAP) ? " ghost-vertices" : "", (e & ERR_FUSE_CAP) ? " fuse-pairs" : "",
+             (e & ERR_POLY_TOO_LARGE) ? " polygon-workspace(>1024 points or >256 crossings)" : "",
+             (e & ERR_DOM_CAP) ? " domain-items" : "", (e & ERR_GHOST_SLOTS) ? " ghost-slots(>3 images)" : "");
+    return buf;
+}
+
+// grow whatever overflowed; returns SZ_OK if a retry makes sense
+static int32_t handle_overflow(sz_handle *h, const Counters &c) {
+    uint32_t e = c.error;
+    char buf[256];
+    if (e & (ERR_POLY_TOO_LARGE | ERR_GHOST_SLOTS)) return fail(h, (e & ERR_POLY_TOO_LARGE) ? SZ_ERR_UNSUPPORTED : SZ_ERR_CAPACITY, errbits(e, buf, sizeof(buf)));
+    int32_t rc = SZ_OK;
+    if (e & (ERR_PAIR_CAP | ERR_DOM_CAP)) {
+        long long wp = (e & ERR_PAIR_CAP) ? (long long)c.want_pairs * 5 / 4 + 1024 : h->B.cap_pairs;
+        long long wd = (e & ERR_DOM_CAP) ? (long long)c.want_dom * 5 / 4 + 1024 : h->B.cap_dom;
+        if (wp > (1ll << 30) || wd > (1ll << 30)) return fail(h, SZ_ERR_CAPACITY, errbits(e, buf, sizeof(buf)));
+        if ((rc = set_pair_cap(h, (int)wp, (int)wd))) return rc;
+    }
+    if (e & ERR_POOL_CAP) {
+        long long w = std::max<long long>(c.n_pool, h->B.cap_pool) * 2 + 1024;
+        if ((rc = set_pool_cap(h, (int)std::min<long long>(w, 1ll << 28)))) return rc;
+    }
+    if (e & ERR_ROW_CAP) {
+        long long w = (long long)c.want_rows * 5 / 4 + 1024;
+        if ((rc = set_row_cap(h, (int)std::min<long long>(w, 1ll << 28)))) return rc;
+    }
+    if (e & ERR_FUSE_CAP) {
+        if ((rc = set_fuse_cap(h, std::max(c.n_fuse, h->B.cap_fuse) * 2 + 1024))) return rc;
+    }
+    if (e & ERR_GHOST_CAP) {
+        if ((rc = grow_floes(h, c.want_floes * 5 / 4 + 64, h->n_total))) return rc;
+    }
+    if (e & ERR_VERT_CAP) {
+        if ((rc = grow_verts(h, c.want_verts * 5 / 4 + 64, h->n_verts))) return rc;
+    }
+    szk_clear_error(h->L, h->S);
+    return SZ_OK;
+}
+
+static int pairs_hint(sz_handle *h) {
+    long long g = h->last.n_cand > 0 ? (long long)h->last.n_cand * 2 : 8ll * h->n_total;
+    return (int)std::min<long long>(std::max<long long>(g, 1024), h->B.cap_pairs);
+}
+static int floes_hint(sz_handle *h) { return std::min(h->S.cap_floes, h->n_total + h->n_total / 4 + 64); }
+
+static void enqueue_ghosts(sz_handle *h) {
+    // collisions.jl:1171-1172: east/west pass, then north/south pass
+    if (h->hD.kind[2] == SZ_BOUNDARY_PERIODIC) szk_ghost_pass(h->L, h->S, h->B, 0, floes_hint(h));
+    if (h->hD.kind[0] == SZ_BOUNDARY_PERIODIC) szk_ghost_pass(h->L, h->S, h->B, 1, floes_hint(h));
+}
+
+static double ev_ms(sz_handle *h, int a, int b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
+    return (double)ms;
+}
+
+extern "C" int32_t sz_add_ghosts(sz_handle *h, int64_t *n_total) {
+    if (!h || !h->have_domain) return fail(h, SZ_ERR_INVALID, "add_ghosts before set_domain");
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "add_ghosts before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    for (int axis = 0; axis < 2; ++axis) {
+        if (h->hD.kind[axis == 0 ? 2 : 0] != SZ_BOUNDARY_PERIODIC) continue;
+        for (int attempt = 0;; ++attempt) {
+            cudaEventRecord(h->ev[0], h->L.stream);
+            szk_ghost_pass(h->L, h->S, h->B, axis, floes_hint(h));
+            cudaEventRecord(h->ev[1], h->L.stream);
+            int32_t rc = sync_counters(h);
+            if (rc) return rc;
+            CK(cudaGetLastError());
+            if (!h->h_cnt->error) break;
+            if (attempt >= 4) return fail(h, SZ_ERR_CAPACITY, "add_ghosts: capacity retry limit");
+            if ((rc = handle_overflow(h, *h->h_cnt))) return rc;
+        }
+        h->ms[0] = (axis == 0 ? 0.0 : h->ms[0]) + ev_ms(h, 0, 1);
+    }
+    if (n_total) *n_total = h->n_total;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_remove_ghosts(sz_handle *h) {
+    if (!h || !h->have_floes) return fail(h, SZ_ERR_INVALID, "remove_ghosts before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    szk_remove_ghosts(h->L, h->S, h->n_verts_init);
+    int32_t rc = sync_counters(h);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_step_collisions(sz_handle *h) {
+    if (!h || !h->have_domain) return fail(h, SZ_ERR_INVALID, "step_collisions before set_domain");
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "step_collisions before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    for (int attempt = 0;; ++attempt) {
+        cudaEventRecord(h->ev[0], h->L.stream);
+        szk_collisions(h->L, h->S, h->B, h->P, floes_hint(h), pairs_hint(h), &h->ev[1]);
+        int32_t rc = sync_counters(h);
+        if (rc) return rc;
+        CK(cudaGetLastError());
+        if (!h->h_cnt->error) break;
+        if (attempt >= 6) return fail(h, SZ_ERR_CAPACITY, "step_collisions: capacity retry limit");
+        if ((rc = handle_overflow(h, *h->h_cnt))) return rc;
+    }
+    h->last = *h->h_cnt;
+    h->ms[1] = ev_ms(h, 0, 1);
+    h->ms[2] = ev_ms(h, 1, 2);
+    h->ms[3] = ev_ms(h, 2, 3);
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_step_coupling(sz_handle *h) {
+    if (!h || !h->have_domain || !h->have_fields) return fail(h, SZ_ERR_INVALID, "step_coupling before set_domain/set_fields");
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "step_coupling before upload_floes");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step_coupling with ghosts present (call remove_ghosts)");
+    cudaSetDevice(h->cfg.device);
+    cudaEventRecord(h->ev[0], h->L.stream);
+    szk_coupling(h->L, h->S, h->P);
+    cudaEventRecord(h->ev[1], h->L.stream);
+    CK(cudaStreamSynchronize(h->L.stream));
+    CK(cudaGetLastError());
+    h->ms[4] = ev_ms(h, 0, 1);
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_step_floe_properties(sz_handle *h, int64_t tstep) {
+    (void)tstep;
+    if (!h || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step_floe_properties before upload_floes");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step_floe_properties with ghosts present");
+    cudaSetDevice(h->cfg.device);
+    cudaEventRecord(h->ev[0], h->L.stream);
+    szk_update(h->L, h->S, h->B, h->P);
+    cudaEventRecord(h->ev[1], h->L.stream);
+    CK(cudaStreamSynchronize(h->L.stream));
+    CK(cudaGetLastError());
+    h->ms[5] = ev_ms(h, 0, 1);
+    return SZ_OK;
+}
+
+// One whole timestep enqueued back to back; a single host synchronisation at the end.
+extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
+    (void)tstep;
+    if (!h || !h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step before set_domain/upload_floes");
+    if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step with coupling before set_fields");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
+    cudaSetDevice(h->cfg.device);
+    cudaStream_t st = h->L.stream;
+    for (int attempt = 0;; ++attempt) {
+        cudaEventRecord(h->ev[0], st);
+        enqueue_ghosts(h);
+        cudaEventRecord(h->ev[1], st);
+        // the ghost count of this step is not known on the host: size grids from the capacity-bounded hint
+        szk_collisions(h->L, h->S, h->B, h->P, floes_hint(h), pairs_hint(h), &h->ev[2]);
+        CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        szk_remove_ghosts(h->L, h->S, h->n_verts_init);
+        cudaEventRecord(h->ev[5], st);
+        if (do_coupling) szk_coupling(h->L, h->S, h->P);
+        cudaEventRecord(h->ev[6], st);
+        szk_update(h->L, h->S, h->B, h->P);
+        cudaEventRecord(h->ev[7], st);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (!h->h_cnt->error) break;
+        // every kernel after the overflow returned at once; only ghosts (and parents wrapped into
+        // the domain) may have been written, which a fresh add_ghosts! reproduces
+        Counters c = *h->h_cnt;
+        h->n_total = c.n_total;
+        h->n_verts = c.n_verts;
+        if (attempt >= 6) return fail(h, SZ_ERR_CAPACITY, "step: capacity retry limit");
+        int32_t rc = handle_overflow(h, c);
+        if (rc) return rc;
+        szk_remove_ghosts(h->L, h->S, h->n_verts_init);
+        CK(cudaStreamSynchronize(st));
+        h->n_total = h->n_init;
+        h->n_verts = h->n_verts_init;
+    }
+    h->last = *h->h_cnt;
+    h->n_total = h->n_init;
+    h->n_verts = h->n_verts_init;
+    h->ms[0] = ev_ms(h, 0, 1);
+    h->ms[1] = ev_ms(h, 1, 2);
+    h->ms[2] = ev_ms(h, 2, 3);
+    h->ms[3] = ev_ms(h, 3, 5);
+    h->ms[4] = ev_ms(h, 5, 6);
+    h->ms[5] = ev_ms(h, 6, 7);
+    h->ms[6] = ev_ms(h, 0, 7);
+    return SZ_OK;
+}
+
+// ---- results -----------------------------------------------------------------------------------------------
+extern "C" int32_t sz_get_interactions(sz_handle *h, int64_t *offsets, double *rows) {
+    if (!h || !offsets) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "get_interactions before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    int n = h->n_total;
+    std::vector<int> off((size_t)n + 1);
+    CK(cudaMemcpy(off.data(), h->B.row_off, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+    for (int i = 0; i <= n; ++i) offsets[i] = off[i];
+    if (rows && off[n] > 0) CK(cudaMemcpy(rows, h->B.rows, sizeof(double) * NCOL * (size_t)off[n], cudaMemcpyDeviceToHost));
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_set_interactions(sz_handle *h, const int64_t *offsets, const double *rows) {
+    if (!h || !offsets) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "set_interactions before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    int n = h->n_total;
+    long long tot = offsets[n];
+    if (tot > h->B.cap_rows) {
+        int32_t rc = set_row_cap(h, (int)tot + 1024);
+        if (rc) return rc;
+    }
+    std::vector<int> off((size_t)n + 1);
+    for (int i = 0; i <= n; ++i) off[i] = (int)offsets[i];
+    CK(cudaMemcpy(h->B.row_off, off.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+    if (tot > 0) {
+        if (!rows) return fail(h, SZ_ERR_INVALID, "set_interactions: rows missing");
+        CK(cudaMemcpy(h->B.rows, rows, sizeof(double) * NCOL * (size_t)tot, cudaMemcpyHostToDevice));
+    }
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_get_pairs(sz_handle *h, int32_t which, int64_t *pairs) {
+    if (!h || !pairs) return SZ_ERR_INVALID;
+    if (which < 0 || which > 3) return fail(h, SZ_ERR_INVALID, "get_pairs: which must be 0..3");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    int np = h->last.n_cand;
+    if (np == 0) return SZ_OK;
+    std::vector<int> pi(np), pj(np);
+    std::vector<unsigned char> keep(np);
+    std::vector<uint32_t> fl(np);
+    CK(cudaMemcpy(pi.data(), h->B.pair_i, sizeof(int) * np, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pj.data(), h->B.pair_j, sizeof(int) * np, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(keep.data(), h->B.keep, np, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fl.data(), h->B.item_flags, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost));
+    long long m = 0;
+    for (int p = 0; p < np; ++p) {
+        bool take = which == 0 || (which == 1 && keep[p]) || (which == 2 && keep[p] && (fl[p] & IT_OVERLAP)) ||
+                    (which == 3 && keep[p] && (fl[p] & IT_FUSE));
+        if (take) {
+            pairs[2 * m] = pi[p] + 1;
+            pairs[2 * m + 1] = pj[p] + 1;
+            m++;
+        }
+    }
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_get_warnings(sz_handle *h, uint32_t *bits) {
+    if (!h || !bits) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "get_warnings before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    if (h->n_init > 0) CK(cudaMemcpy(bits, h->S.warn, sizeof(uint32_t) * h->n_init, cudaMemcpyDeviceToHost));
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_get_timings(sz_handle *h, double ms[8]) {
+    if (!h || !ms) return SZ_ERR_INVALID;
+    memcpy(ms, h->ms, sizeof(double) * 8);
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_clip_polygons(sz_handle *h, const double *p_xy, int32_t np, const double *q_xy, int32_t nq,
+                                    int32_t cap_regions, int32_t cap_points, int32_t *out_offsets, double *out_xy,
+                                    double *out_areas) {
+    if (!h || !p_xy || !q_xy || !out_offsets || !out_xy || np < 1 || nq < 1) return SZ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    return szk_debug_clip(h->L, p_xy, np, q_xy, nq, cap_regions, cap_points, out_offsets, out_xy, out_areas);
+}

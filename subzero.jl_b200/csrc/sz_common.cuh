@@ -1,0 +1,171 @@
+// sz_common.cuh — device store layout and launch helpers shared by all kernels.
+//
+// Data layout in HBM: one SoA of per-floe scalars (a1: floe.jl:24-77),
+// CSR-packed ring vertices (double2, closed rings), CSR-packed body-frame Monte-Carlo
+// points (double2).  Ghost floes are appended behind the n_init parents exactly like the
+// reference appends them to its StructArray (collisions.jl:881-1047).  All sizes that
+// change inside a step (n_total, vertex count, pair counts) live in device memory
+// (`Counters`) so a whole timestep is enqueued without host synchronisation; kernels are
+// launched on grids sized from host-side capacities and stride over the device-side counts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/subzero_b200.h"
+
+#define SZ_MAX_GHOSTS 3  // a parent has at most 3 periodic images (collisions.jl:891-897)
+
+// Interaction-row columns, floe.jl:102-110
+enum { COL_IDX = 0, COL_FX, COL_FY, COL_PX, COL_PY, COL_TRQ, COL_OV, NCOL = 7 };
+// contact-pool row: fx, fy, px, py, overlap
+#define NPOOL 5
+
+// per work-item flags written by the narrow phase
+enum : uint32_t {
+    IT_OVERLAP = 1u,    // total overlap area > 0
+    IT_FUSE = 2u,       // floe_floe_max_overlap exceeded (collisions.jl:366-368)
+    IT_REMOVE = 4u,     // open wall hit / floe_domain_max_overlap exceeded (:438,:524)
+    IT_CLIPFAIL = 8u,   // region trace met a degenerate configuration
+    IT_NEEDLARGE = 16u, // exceeded the shared-memory budget of the small kernel
+    IT_DONE = 32u,
+};
+
+// device-side error bits (Counters::error); the host maps them to SZ_ERR_CAPACITY and
+// grows the named buffer before retrying the step
+enum : uint32_t {
+    ERR_PAIR_CAP = 1u,
+    ERR_POOL_CAP = 2u,
+    ERR_ROW_CAP = 4u,
+    ERR_GHOST_CAP = 8u,
+    ERR_VERT_CAP = 16u,
+    ERR_FUSE_CAP = 32u,
+    ERR_POLY_TOO_LARGE = 64u,
+    ERR_DOM_CAP = 128u,
+    ERR_GHOST_SLOTS = 256u,
+};
+
+struct Counters {
+    int n_total;   // floes incl. ghosts
+    int n_verts;   // ring points in use
+    int n_cand;    // pairs (i<j) passing the circle test
+    int n_dom;     // (floe, element) work items
+    int n_rows;    // interaction rows over all floes
+    int n_fuse;    // fuse pairs this step
+    int n_pool;    // contact rows in the pool
+    int n_clipfail;
+    int n_kept;    // pairs after the image filter
+    int n_overlap;
+    int n_large;   // work items deferred to the large-polygon kernel
+    uint32_t error;
+    int want_pairs, want_pool, want_rows, want_floes, want_verts, want_dom, want_fuse;  // sizes asked for on overflow
+    int gnx, gny, n_cells;
+    int n_domchecks;  // (floe, element) checks incl. periodic walls (diagnostic)
+    // broad-phase bounding box, order-preserving uint64 encodings (k_bbox)
+    unsigned long long bb[5];  // min x, min y, max x, max y, max rmax
+    double gx0, gy0, cell;
+};
+
+struct DomainDev {
+    int kind[4];
+    double val[4], wu[4], wv[4];
+    double rect[4][4];  // xmin, xmax, ymin, ymax
+    int n_topo;
+    int pad;
+};
+
+struct Params {
+    sz_config cfg;
+    int Nx, Ny;
+    double x0, xf, y0, yf, dx, dy;
+};
+
+// Everything a kernel needs, passed by value.
+struct Store {
+    int n_init, cap_floes, cap_verts;
+    long long cap_mc;
+    // per-floe scalars
+    double *cx, *cy, *height, *area, *mass, *rmax, *moment, *alpha, *u, *v, *xi;
+    double *fxOA, *fyOA, *trqOA, *hflx, *overarea, *cfx, *cfy, *ctrq;
+    double *p_dxdt, *p_dydt, *p_dudt, *p_dvdt, *p_dxidt, *p_dalphadt;
+    double *stress_accum, *stress_instant, *strain;  // 4 per floe
+    int *status;
+    long long *id, *ghost_id;
+    int *parent;      // -1 for a parent floe, else index of its parent
+    int *nghost;      // number of ghosts of a parent
+    int *ghost_slot;  // [cap][SZ_MAX_GHOSTS]
+    uint32_t *warn;
+    // CSR geometry
+    int *vstart, *vcount;  // ring of floe f = verts[vstart[f] .. vstart[f]+vcount[f]), closed
+    double2 *verts;
+    long long *mc_off;  // [n_init+1]
+    double2 *mc;        // body-frame Monte-Carlo points
+    // topography
+    int *topo_vstart, *topo_vcount;
+    double2 *topo_verts;
+    double *topo_cx, *topo_cy, *topo_rmax;
+    // fields (Nx+1)x(Ny+1), [ix + (Nx+1) iy]
+    double *ocn_u, *ocn_v, *ocn_hflx, *atm_u, *atm_v;
+    Counters *cnt;
+    DomainDev *dom;
+};
+
+// Work buffers of one collision step.
+struct StepBuf {
+    int cap_pairs, cap_dom, cap_rows, cap_fuse, cap_pool, cap_cells;
+    // uniform grid
+    int *cell_of;     // [cap_floes]
+    int *cell_count;  // [cap_cells+1]
+    int *cell_start;  // [cap_cells+1]
+    int *cell_fill;   // [cap_cells]
+    int *cell_items;  // [cap_floes]
+    // neighbour lists
+    int *up_count, *up_off;    // [cap_floes+1] pairs (i, j>i)
+    int *low_count, *low_off;  // [cap_floes+1] pairs (i<j, j) seen from j
+    int *pair_i, *pair_j;      // [cap_pairs] sorted (i, j)
+    int *low_pair;             // [cap_pairs] per floe j: pair indices p of (i<j, j), i ascending
+    unsigned char *keep;       // [cap_pairs] survives the image filter
+    // domain work items
+    int *dom_count, *dom_off;  // [cap_floes+1]
+    int *dom_floe, *dom_elem;  // [cap_dom]
+    // narrow-phase output, item w = pair p (w < cap_pairs) or cap_pairs + q
+    int *item_nrows;     // contact rows written
+    int *item_row0;      // first pool row
+    uint32_t *item_flags;
+    double *pool;        // [cap_pool][NPOOL] = fx, fy, px, py, overlap
+    int *large_items;    // [cap_pairs + cap_dom] work list of the large-polygon kernel
+    // per-floe rows
+    int *row_pre, *row_count, *row_off;  // [cap_floes+1]
+    double *rows;                        // [cap_rows][7]
+    int2 *fuse_pairs;                    // [cap_fuse]
+    // ghost scratch
+    int *g_flag, *g_cnt, *g_off, *g_vcnt, *g_voff;  // [cap_floes+1]
+    // scan scratch
+    int *scan_block;
+};
+
+__host__ __device__ inline int sz_div_up(long long a, int b) { return (int)((a + b - 1) / b); }
+
+struct Launch {
+    cudaStream_t stream;
+    int sms;  // multiprocessor count: persistent grids are sized in multiples of it
+    int maxv_large, maxx_large;  // workspace of the large-polygon kernels
+};
+
+// ---- host-callable launchers (sz_kernels.cu) -------------------------------------------------
+// one periodic axis of add_ghosts! (0 = east/west, 1 = north/south)
+void szk_ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_floes_hint);
+void szk_remove_ghosts(const Launch &L, const Store &S, int n_verts_init);
+// ev (optional, 3 events): recorded after the broad phase, the narrow phase and the row assembly
+void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_floes_hint,
+                    int n_pairs_hint, cudaEvent_t *ev);
+int szk_configure(const Launch &L);
+void szk_coupling(const Launch &L, const Store &S, const Params &P);
+void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P);
+void szk_interleave(const Launch &L, const double *x, const double *y, double2 *out, long long n);
+void szk_deinterleave(const Launch &L, const double2 *in, double *x, double *y, long long n);
+void szk_set_counts(const Launch &L, const Store &S, int n_total, int n_verts);
+void szk_clear_error(const Launch &L, const Store &S);
+int szk_debug_clip(const Launch &L, const double *p_xy, int np, const double *q_xy, int nq, int cap_regions,
+                   int cap_points, int *out_offsets, double *out_xy, double *out_areas);
+size_t szk_large_smem(int maxv, int maxx);

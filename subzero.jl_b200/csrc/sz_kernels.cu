@@ -1,0 +1,1467 @@
+// sz_kernels.cu — the sm_100a kernels of the floe-interaction hot path and their launchers.
+//
+//   K8  ghosts      add_ghosts!                 collisions.jl:881-1174
+//   K1  broad phase potential_interaction       collisions.jl:705-710,745-763  (uniform grid)
+//   K2  image filter collide_pairs Dict         collisions.jl:743,751-775
+//   K3  narrow phase floe_floe_interaction!     collisions.jl:347-408 (warp per pair)
+//   K4  domain       floe_domain_interaction!   collisions.jl:427-662
+//   K5  rows         mirror/ghost rows, torque, totals  collisions.jl:799-862 (segmented, no float atomics)
+//   K6  coupling     calc_one_way_coupling!     coupling.jl:1486-1589
+//   K7  update       timestep_floe_properties!  update_floe.jl:392-551
+//
+// Compiled with -fmad=false (see sz_geom.cuh).  Every kernel strides over device-side counts
+// (Counters) and returns at once when Counters::error is set, so an overflowing step leaves
+// the floe state untouched and the host can grow the buffer and run the step again.
+#include "sz_geom.cuh"
+
+#define TPB 256
+
+// ---- small helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long enc_f64(double x) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_f64(unsigned long long e) {
+    unsigned long long u = (e >> 63) ? (e ^ 0x8000000000000000ull) : ~e;
+    return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ bool potential_interaction(double xi, double yi, double ri, double xj, double yj,
+                                                      double rj) {
+    double dx = xi - xj, dy = yi - yj, rr = ri + rj;  // collisions.jl:705-710
+    return dx * dx + dy * dy < rr * rr;
+}
+
+// ---- exclusive scan (3 launches; lengths live on the device) --------------------------------------
+#define SCAN_T 512
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_T * SCAN_ITEMS)
+
+__device__ __forceinline__ int block_excl_scan_512(int v, int *total) {
+    __shared__ int warp_sums[16];
+    __shared__ int blk_total;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(FULLMASK, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < 16 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            int y = __shfl_up_sync(FULLMASK, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < 16) warp_sums[lane] = s;  // inclusive
+        if (lane == 15) blk_total = s;
+    }
+    __syncthreads();
+    int off = wid ? warp_sums[wid - 1] : 0;
+    *total = blk_total;
+    int r = off + x - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_tiles(const int *__restrict__ in, int *__restrict__ out,
+                                                       const int *len_ptr, int len_add, int *block_sums,
+                                                       const Counters *cnt) {
+    if (cnt->error) return;
+    int len = *len_ptr + len_add;
+    int base = blockIdx.x * SCAN_TILE;
+    if (base >= len) return;
+    int v[SCAN_ITEMS], s = 0;
+    int i0 = base + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (i0 + k < len) ? in[i0 + k] : 0;
+        s += v[k];
+    }
+    int tot;
+    int pre = block_excl_scan_512(s, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (i0 + k < len) out[i0 + k] = pre;
+        pre += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_sums(int *block_sums, const int *len_ptr, int len_add,
+                                                      const Counters *cnt) {
+    if (cnt->error) return;
+    int len = *len_ptr + len_add;
+    int ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+    int carry = 0;
+    for (int base = 0; base < ntiles; base += SCAN_T) {
+        int i = base + threadIdx.x;
+        int v = i < ntiles ? block_sums[i] : 0;
+        int tot;
+        int pre = block_excl_scan_512(v, &tot);
+        if (i < ntiles) block_sums[i] = carry + pre;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) block_sums[ntiles] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_add(int *out, const int *len_ptr, int len_add,
+                                                     const int *block_sums, int *total_out, const Counters *cnt) {
+    if (cnt->error) return;
+    int len = *len_ptr + len_add;
+    int ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+    int base = blockIdx.x * SCAN_TILE;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[len] = block_sums[ntiles];
+        if (total_out) *total_out = block_sums[ntiles];
+    }
+    if (base >= len) return;
+    int off = block_sums[blockIdx.x];
+    int i0 = base + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (i0 + k < len) out[i0 + k] += off;
+}
+
+// out[0..len] = exclusive prefix sums of in[0..len), len = *len_ptr + len_add <= max_len
+static void scan_excl(const Launch &L, const Store &S, const int *in, int *out, const int *len_ptr, int len_add,
+                      int max_len, int *scratch, int *total_out) {
+    int tiles = sz_div_up((long long)max_len, SCAN_TILE);
+    if (tiles < 1) tiles = 1;
+    k_scan_tiles<<<tiles, SCAN_T, 0, L.stream>>>(in, out, len_ptr, len_add, scratch, S.cnt);
+    k_scan_sums<<<1, SCAN_T, 0, L.stream>>>(scratch, len_ptr, len_add, S.cnt);
+    k_scan_add<<<tiles, SCAN_T, 0, L.stream>>>(out, len_ptr, len_add, scratch, total_out, S.cnt);
+}
+
+static inline int grid_for(const Launch &L, long long work_items, int per_block) {
+    long long b = (work_items + per_block - 1) / per_block;
+    long long cap = (long long)L.sms * 32;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---- misc small kernels ----------------------------------------------------------------------------
+__global__ void k_interleave(const double *__restrict__ x, const double *__restrict__ y, double2 *__restrict__ out,
+                             long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = make_double2(x[i], y[i]);
+}
+__global__ void k_deinterleave(const double2 *__restrict__ in, double *__restrict__ x, double *__restrict__ y,
+                               long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double2 p = in[i];
+        x[i] = p.x;
+        y[i] = p.y;
+    }
+}
+void szk_interleave(const Launch &L, const double *x, const double *y, double2 *out, long long n) {
+    if (n > 0) k_interleave<<<grid_for(L, n, TPB), TPB, 0, L.stream>>>(x, y, out, n);
+}
+void szk_deinterleave(const Launch &L, const double2 *in, double *x, double *y, long long n) {
+    if (n > 0) k_deinterleave<<<grid_for(L, n, TPB), TPB, 0, L.stream>>>(in, x, y, n);
+}
+
+__global__ void k_set_counts(Counters *cnt, int n_total, int n_verts) {
+    cnt->n_total = n_total;
+    cnt->n_verts = n_verts;
+    cnt->error = 0;
+}
+void szk_set_counts(const Launch &L, const Store &S, int n_total, int n_verts) {
+    k_set_counts<<<1, 1, 0, L.stream>>>(S.cnt, n_total, n_verts);
+}
+__global__ void k_clear_error(Counters *cnt) { cnt->error = 0; }
+void szk_clear_error(const Launch &L, const Store &S) { k_clear_error<<<1, 1, 0, L.stream>>>(S.cnt); }
+
+// ---- K8: ghosts (collisions.jl:881-1174) -------------------------------------------------------------
+// One pass per periodic axis (E-W first, then N-S: collisions.jl:1171-1172).  Each active
+// parent decides on its own (the reference's loop carries no dependency between parents other
+// than the append position, which a prefix sum reproduces):
+//   flag   c - r < min wall  ->  test the min wall, ghost translated by +L   (elseif: max wall, -L)
+//   clip   intersect_polys(poly, wall.poly) non-empty                         (:889)
+//   write  copies of the parent's existing ghosts, then of the parent (:891-895); ghost_id =
+//          running number (:1034-1040); parent swapped with its last ghost when its centroid
+//          lies outside the domain (:943-949)
+struct GhostAxis {
+    int axis, wmin, wmax;
+};
+
+__global__ void k_ghost_flag(Store S, StepBuf B, GhostAxis A) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const DomainDev *D = S.dom;
+    int n0 = cnt->n_total;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += gridDim.x * blockDim.x) {
+        int flag = 0;
+        if (S.status[i] == SZ_STATUS_ACTIVE && S.ghost_id[i] == 0) {
+            double c = A.axis == 0 ? S.cx[i] : S.cy[i], r = S.rmax[i];
+            if (c - r < D->val[A.wmin]) flag = 1;
+            else if (c + r > D->val[A.wmax]) flag = 2;
+        }
+        B.g_flag[i] = flag;
+        B.g_cnt[i] = 0;
+        B.g_vcnt[i] = 0;
+    }
+}
+
+__device__ __forceinline__ void stage_wall_ring(double2 *Q, const DomainDev *D, int wall, int lane) {
+    // _make_bounding_box_polygon, floe_utils.jl:104-108
+    if (lane < 5) {
+        double xmin = D->rect[wall][0], xmax = D->rect[wall][1], ymin = D->rect[wall][2], ymax = D->rect[wall][3];
+        double2 p;
+        switch (lane) {
+        case 1: p = make_double2(xmin, ymax); break;
+        case 2: p = make_double2(xmax, ymax); break;
+        case 3: p = make_double2(xmax, ymin); break;
+        default: p = make_double2(xmin, ymin); break;
+        }
+        Q[lane] = p;
+    }
+}
+
+__global__ void k_ghost_clip(Store S, StepBuf B, GhostAxis A, int maxv, int maxx, int large) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    Ws w = ws_carve(smem + (size_t)wib * ws_bytes(maxv, maxx), maxv, maxx);
+    int n0 = cnt->n_total;
+    for (int i = blockIdx.x * wpb + wib; i < n0; i += gridDim.x * wpb) {
+        int flag = B.g_flag[i];
+        if (flag == 0) continue;
+        if (large ? !(flag & 4) : (flag & 4)) continue;
+        int side = flag & 3;
+        int npp = S.vcount[i];
+        bool defer = npp > w.maxv;
+        int nreg = 0, status = CLIP_OK;
+        if (!defer) {
+            const double2 *gP = S.verts + S.vstart[i];
+            for (int k = lane; k < npp; k += 32) w.P[k] = gP[k];
+            stage_wall_ring(w.Q, S.dom, side == 1 ? A.wmin : A.wmax, lane);
+            __syncwarp();
+            nreg = warp_clip(w, w.P, npp, w.Q, 5, w.R1, w.rs1, w.re1, status);
+            defer = status == CLIP_OVERFLOW;
+        }
+        if (lane == 0) {
+            if (defer) {
+                if (large) atomicOr(&cnt->error, ERR_POLY_TOO_LARGE);
+                else B.g_flag[i] = side | 4;
+            } else if (nreg > 0) {
+                int ng = S.nghost[i], vc = npp;
+                for (int k = 0; k < ng; ++k) vc += S.vcount[S.ghost_slot[i * SZ_MAX_GHOSTS + k]];
+                B.g_flag[i] = side;
+                B.g_cnt[i] = ng + 1;
+                B.g_vcnt[i] = vc;
+                if (2 * ng + 1 > SZ_MAX_GHOSTS) atomicOr(&cnt->error, ERR_GHOST_SLOTS);
+            } else {
+                B.g_flag[i] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_ghost_check(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n0 = cnt->n_total;
+    int add = B.g_off[n0], vadd = B.g_voff[n0];
+    if (n0 + add > S.cap_floes) {
+        cnt->error |= ERR_GHOST_CAP;
+        cnt->want_floes = n0 + add;
+    }
+    if (cnt->n_verts + vadd > S.cap_verts) {
+        cnt->error |= ERR_VERT_CAP;
+        cnt->want_verts = cnt->n_verts + vadd;
+    }
+}
+
+// deepcopy_floe, floe_utils.jl:120-161 (Monte-Carlo points are not copied: coupling runs after
+// the ghosts are deleted, simulation.jl:138-161)
+__device__ void copy_floe_scalars(const Store &S, int src, int dst) {
+#define CP(f) S.f[dst] = S.f[src];
+    CP(cx) CP(cy) CP(height) CP(area) CP(mass) CP(rmax) CP(moment) CP(alpha) CP(u) CP(v) CP(xi) CP(fxOA) CP(fyOA)
+    CP(trqOA) CP(hflx) CP(overarea) CP(cfx) CP(cfy) CP(ctrq) CP(p_dxdt) CP(p_dydt) CP(p_dudt) CP(p_dvdt)
+    CP(p_dxidt) CP(p_dalphadt) CP(status) CP(id)
+#undef CP
+    for (int k = 0; k < 4; ++k) {
+        S.stress_accum[4 * dst + k] = S.stress_accum[4 * src + k];
+        S.stress_instant[4 * dst + k] = S.stress_instant[4 * src + k];
+        S.strain[4 * dst + k] = S.strain[4 * src + k];
+    }
+    S.warn[dst] = 0;
+    S.nghost[dst] = 0;
+}
+
+__global__ void k_ghost_write(Store S, StepBuf B, GhostAxis A) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const DomainDev *D = S.dom;
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    int n0 = cnt->n_total, v0 = cnt->n_verts;
+    double Lp = D->val[A.wmax] - D->val[A.wmin];
+    for (int i = blockIdx.x * wpb + wib; i < n0; i += gridDim.x * wpb) {
+        int cntg = B.g_cnt[i];
+        if (cntg == 0) continue;
+        int side = B.g_flag[i] & 3;
+        double t = side == 1 ? Lp : -Lp;
+        double tx = A.axis == 0 ? t : 0.0, ty = A.axis == 0 ? 0.0 : t;
+        int base = n0 + B.g_off[i], vbase = v0 + B.g_voff[i];
+        int ng = S.nghost[i];
+        for (int k = 0; k < cntg; ++k) {
+            int src = k < ng ? S.ghost_slot[i * SZ_MAX_GHOSTS + k] : i, dst = base + k;
+            int nv = S.vcount[src], vs = S.vstart[src];
+            if (lane == 0) {
+                copy_floe_scalars(S, src, dst);
+                S.cx[dst] += tx;  // _translate_floe!, floe_utils.jl:66-72
+                S.cy[dst] += ty;
+                S.ghost_id[dst] = (long long)((k + 1) + ng);  // collisions.jl:1036-1038
+                S.parent[dst] = i;
+                S.vstart[dst] = vbase;
+                S.vcount[dst] = nv;
+            }
+            for (int q = lane; q < nv; q += 32) {
+                double2 p = S.verts[vs + q];
+                p.x += tx;
+                p.y += ty;
+                S.verts[vbase + q] = p;
+            }
+            vbase += nv;
+        }
+        __syncwarp();
+        // parent / last-ghost swap, collisions.jl:943-949
+        double c = A.axis == 0 ? S.cx[i] : S.cy[i];
+        double sw = 0.0;
+        if (c < D->val[A.wmin]) sw = Lp;
+        else if (D->val[A.wmax] < c) sw = -Lp;
+        __syncwarp();
+        if (sw != 0.0) {
+            double sx = A.axis == 0 ? sw : 0.0, sy = A.axis == 0 ? 0.0 : sw;
+            int last = base + cntg - 1;
+            int vs = S.vstart[i], nv = S.vcount[i];
+            for (int q = lane; q < nv; q += 32) {
+                double2 p = S.verts[vs + q];
+                p.x += sx;
+                p.y += sy;
+                S.verts[vs + q] = p;
+            }
+            int vl = v0 + B.g_voff[i] + B.g_vcnt[i] - nv;  // the parent's copy is the last ring written
+            for (int q = lane; q < nv; q += 32) {
+                double2 p = S.verts[vl + q];
+                p.x += -sx;
+                p.y += -sy;
+                S.verts[vl + q] = p;
+            }
+            if (lane == 0) {
+                S.cx[i] += sx;
+                S.cy[i] += sy;
+                S.cx[last] += -sx;
+                S.cy[last] += -sy;
+            }
+        }
+        if (lane == 0) {
+            for (int k = 0; k < cntg; ++k) S.ghost_slot[i * SZ_MAX_GHOSTS + ng + k] = base + k;
+            S.nghost[i] = ng + cntg;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_ghost_commit(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n0 = cnt->n_total;
+    cnt->n_verts += B.g_voff[n0];
+    cnt->n_total = n0 + B.g_off[n0];
+}
+
+static void ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_hint) {
+    GhostAxis A;
+    A.axis = axis;
+    A.wmax = axis == 0 ? 2 : 0;
+    A.wmin = axis == 0 ? 3 : 1;
+    const int maxv_s = 32, maxx_s = 16, wpb = 4;
+    k_ghost_flag<<<grid_for(L, n_hint, TPB), TPB, 0, L.stream>>>(S, B, A);
+    k_ghost_clip<<<grid_for(L, n_hint, wpb), wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), L.stream>>>(S, B, A, maxv_s,
+                                                                                                   maxx_s, 0);
+    k_ghost_clip<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), L.stream>>>(S, B, A, L.maxv_large, L.maxx_large,
+                                                                              1);
+    scan_excl(L, S, B.g_cnt, B.g_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, nullptr);
+    scan_excl(L, S, B.g_vcnt, B.g_voff, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, nullptr);
+    k_ghost_check<<<1, 1, 0, L.stream>>>(S, B);
+    k_ghost_write<<<grid_for(L, n_hint, 8), 256, 0, L.stream>>>(S, B, A);
+    k_ghost_commit<<<1, 1, 0, L.stream>>>(S, B);
+}
+
+void szk_ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_hint) {
+    ghost_pass(L, S, B, axis, n_hint);
+}
+
+// simulation.jl:138-144
+__global__ void k_remove_ghosts(Store S, int n_verts_init) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n_init; i += gridDim.x * blockDim.x) S.nghost[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt->n_total = S.n_init;
+        cnt->n_verts = n_verts_init;
+    }
+}
+void szk_remove_ghosts(const Launch &L, const Store &S, int n_verts_init) {
+    k_remove_ghosts<<<grid_for(L, S.n_init, TPB), TPB, 0, L.stream>>>(S, n_verts_init);
+}
+
+// ---- K1: broad phase -----------------------------------------------------------------------------------
+__global__ void k_step_reset(Store S) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        S.cfx[i] = 0.0;  // collisions.jl:747-749
+        S.cfy[i] = 0.0;
+        S.ctrq[i] = 0.0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt->n_cand = cnt->n_dom = cnt->n_rows = cnt->n_fuse = cnt->n_pool = 0;
+        cnt->n_clipfail = cnt->n_kept = cnt->n_overlap = cnt->n_large = 0;
+        cnt->n_domchecks = 0;
+        cnt->bb[0] = cnt->bb[1] = ~0ull;
+        cnt->bb[2] = cnt->bb[3] = cnt->bb[4] = 0ull;
+    }
+}
+
+__global__ void k_bbox(Store S) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    double xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY, rm = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double x = S.cx[i], y = S.cy[i];
+        xmin = fmin(xmin, x);
+        xmax = fmax(xmax, x);
+        ymin = fmin(ymin, y);
+        ymax = fmax(ymax, y);
+        rm = fmax(rm, S.rmax[i]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(FULLMASK, xmin, o));
+        ymin = fmin(ymin, __shfl_xor_sync(FULLMASK, ymin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(FULLMASK, xmax, o));
+        ymax = fmax(ymax, __shfl_xor_sync(FULLMASK, ymax, o));
+        rm = fmax(rm, __shfl_xor_sync(FULLMASK, rm, o));
+    }
+    if (lane_id() == 0 && xmin <= xmax) {
+        atomicMin(&cnt->bb[0], enc_f64(xmin));
+        atomicMin(&cnt->bb[1], enc_f64(ymin));
+        atomicMax(&cnt->bb[2], enc_f64(xmax));
+        atomicMax(&cnt->bb[3], enc_f64(ymax));
+        atomicMax(&cnt->bb[4], enc_f64(rm));
+    }
+}
+
+// cell edge >= 2 rmax_max, so every pair passing the circle test lies in adjacent cells; the
+// grid only proposes pairs, the exact predicate decides
+__global__ void k_grid_setup(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    if (cnt->n_total == 0) {
+        cnt->gx0 = cnt->gy0 = 0.0;
+        cnt->cell = 1.0;
+        cnt->gnx = cnt->gny = 1;
+        return;
+    }
+    double xmin = dec_f64(cnt->bb[0]), ymin = dec_f64(cnt->bb[1]);
+    double xmax = dec_f64(cnt->bb[2]), ymax = dec_f64(cnt->bb[3]), rm = dec_f64(cnt->bb[4]);
+    double cs = 2.0 * rm * (1.0 + 1e-6) + 1e-6;
+    double ex = xmax - xmin, ey = ymax - ymin;
+    double fx = floor(ex / cs) + 1.0, fy = floor(ey / cs) + 1.0;
+    while (fx * fy > (double)B.cap_cells) {
+        cs *= 1.5;
+        fx = floor(ex / cs) + 1.0;
+        fy = floor(ey / cs) + 1.0;
+    }
+    cnt->gx0 = xmin;
+    cnt->gy0 = ymin;
+    cnt->cell = cs;
+    cnt->gnx = (int)fx;
+    cnt->gny = (int)fy;
+}
+
+__global__ void k_cell_zero(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int nc = cnt->gnx * cnt->gny;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nc; c += gridDim.x * blockDim.x) {
+        B.cell_count[c] = 0;
+        if (c < nc) B.cell_fill[c] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->n_cells = nc;
+}
+
+__global__ void k_cell_count(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total, gnx = cnt->gnx, gny = cnt->gny;
+    double gx0 = cnt->gx0, gy0 = cnt->gy0, cs = cnt->cell;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int ix = (int)floor((S.cx[i] - gx0) / cs), iy = (int)floor((S.cy[i] - gy0) / cs);
+        ix = min(max(ix, 0), gnx - 1);
+        iy = min(max(iy, 0), gny - 1);
+        int c = iy * gnx + ix;
+        B.cell_of[i] = c;
+        atomicAdd(&B.cell_count[c], 1);
+    }
+}
+
+__global__ void k_cell_fill(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int c = B.cell_of[i];
+        int pos = atomicAdd(&B.cell_fill[c], 1);
+        B.cell_items[B.cell_start[c] + pos] = i;  // order inside a cell is irrelevant: lists are sorted below
+    }
+}
+
+// floe_domain_interaction! triggers, collisions.jl:608-660: bit k of the mask = element k hit
+// (walls N,S,E,W then topography is handled separately)
+__device__ __forceinline__ int wall_mask(const DomainDev *D, double cx, double cy, double r) {
+    int m = 0;
+    if (cy + r > D->val[0]) m |= 1;
+    if (cy - r < D->val[1]) m |= 2;
+    if (cx + r > D->val[2]) m |= 4;
+    if (cx - r < D->val[3]) m |= 8;
+    return m;
+}
+
+template <bool WRITE>
+__global__ void k_neighbours(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const DomainDev *D = S.dom;
+    int n = cnt->n_total, gnx = cnt->gnx, gny = cnt->gny;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int c = B.cell_of[i], ix = c % gnx, iy = c / gnx;
+        double xi = S.cx[i], yi = S.cy[i], ri = S.rmax[i];
+        int up = 0, low = 0;
+        int ub = 0, lb = 0;
+        if (WRITE) {
+            ub = B.up_off[i];
+            lb = B.low_off[i];
+        }
+        for (int yy = max(iy - 1, 0); yy <= min(iy + 1, gny - 1); ++yy)
+            for (int xx = max(ix - 1, 0); xx <= min(ix + 1, gnx - 1); ++xx) {
+                int cc = yy * gnx + xx;
+                for (int k = B.cell_start[cc], ke = B.cell_start[cc + 1]; k < ke; ++k) {
+                    int j = B.cell_items[k];
+                    if (j == i) continue;
+                    if (!potential_interaction(xi, yi, ri, S.cx[j], S.cy[j], S.rmax[j])) continue;
+                    if (j > i) {
+                        if (WRITE) B.pair_j[ub + up] = j;
+                        up++;
+                    } else {
+                        if (WRITE) B.low_pair[lb + low] = j;
+                        low++;
+                    }
+                }
+            }
+        int wm = wall_mask(D, xi, yi, ri);
+        int dc = 0, checks = __popc(wm);
+        int db = WRITE ? B.dom_off[i] : 0;
+        for (int wl = 0; wl < 4; ++wl)
+            if ((wm >> wl) & 1) {
+                if (D->kind[wl] != SZ_BOUNDARY_PERIODIC) {  // collisions.jl:459-468: periodic walls do nothing
+                    if (WRITE) {
+                        B.dom_floe[db + dc] = i;
+                        B.dom_elem[db + dc] = wl;
+                    }
+                    dc++;
+                }
+            }
+        for (int k = 0; k < D->n_topo; ++k)
+            if (potential_interaction(S.topo_cx[k], S.topo_cy[k], S.topo_rmax[k], xi, yi, ri)) {  // :650
+                if (WRITE) {
+                    B.dom_floe[db + dc] = i;
+                    B.dom_elem[db + dc] = 4 + k;
+                }
+                dc++;
+                checks++;
+            }
+        if (!WRITE) {
+            B.up_count[i] = up;
+            B.low_count[i] = low;
+            B.dom_count[i] = dc;
+            if (checks) atomicAdd(&cnt->n_domchecks, checks);
+        } else {
+            // ascending j (own pairs) and ascending i (mirrored rows): the reference's loop order
+            for (int a = 1; a < up; ++a) {
+                int v = B.pair_j[ub + a], b = a - 1;
+                while (b >= 0 && B.pair_j[ub + b] > v) {
+                    B.pair_j[ub + b + 1] = B.pair_j[ub + b];
+                    --b;
+                }
+                B.pair_j[ub + b + 1] = v;
+            }
+            for (int a = 0; a < up; ++a) B.pair_i[ub + a] = i;
+            for (int a = 1; a < low; ++a) {
+                int v = B.low_pair[lb + a], b = a - 1;
+                while (b >= 0 && B.low_pair[lb + b] > v) {
+                    B.low_pair[lb + b + 1] = B.low_pair[lb + b];
+                    --b;
+                }
+                B.low_pair[lb + b + 1] = v;
+            }
+        }
+    }
+}
+
+__global__ void k_pair_check(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    if (cnt->n_cand > B.cap_pairs) {
+        cnt->error |= ERR_PAIR_CAP;
+        cnt->want_pairs = cnt->n_cand;
+    }
+    if (cnt->n_dom > B.cap_dom) {
+        cnt->error |= ERR_DOM_CAP;
+        cnt->want_dom = cnt->n_dom;
+    }
+}
+
+__device__ __forceinline__ int find_pair(const StepBuf &B, int lo, int hi) {
+    int a = B.up_off[lo], b = B.up_off[lo + 1];
+    while (a < b) {
+        int m = (a + b) >> 1;
+        int v = B.pair_j[m];
+        if (v < hi) a = m + 1;
+        else b = m;
+    }
+    return (a < B.up_off[lo + 1] && B.pair_j[a] == hi) ? a : -1;
+}
+
+__global__ void k_low_link(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        for (int t = B.low_off[j], te = B.low_off[j + 1]; t < te; ++t) B.low_pair[t] = find_pair(B, B.low_pair[t], j);
+}
+
+// ---- K2: image-pair filter (collide_pairs Dict, collisions.jl:743,751-775) ------------------------------
+// The reference keeps, per id pair, the ghost ids of the FIRST (i, j) met in its serial loop; a
+// later image pair runs iff at least one of its ghost ids matches.  "First in the serial loop"
+// is the smallest pair index p, found by looking up every image combination of the two parents
+// in the sorted pair list — no hash table, no atomics, same answer on every run.
+__global__ void k_filter(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int np = cnt->n_cand;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        int i = B.pair_i[p], j = B.pair_j[p];
+        long long idi = S.id[i], idj = S.id[j];
+        unsigned char keep = 0;
+        if (idi != idj) {
+            int ri = S.parent[i] >= 0 ? S.parent[i] : i, rj = S.parent[j] >= 0 ? S.parent[j] : j;
+            int ngi = S.nghost[ri], ngj = S.nghost[rj];
+            if (ngi == 0 && ngj == 0) keep = 1;
+            else {
+                int pmin = p;
+                for (int a = -1; a < ngi; ++a) {
+                    int fa = a < 0 ? ri : S.ghost_slot[ri * SZ_MAX_GHOSTS + a];
+                    for (int b = -1; b < ngj; ++b) {
+                        int fb = b < 0 ? rj : S.ghost_slot[rj * SZ_MAX_GHOSTS + b];
+                        int q = find_pair(B, min(fa, fb), max(fa, fb));
+                        if (q >= 0 && q < pmin) pmin = q;
+                    }
+                }
+                int ci = B.pair_i[pmin], cj = B.pair_j[pmin];
+                long long g1, g2, G1, G2;
+                if (idi > idj) { g1 = S.ghost_id[i]; g2 = S.ghost_id[j]; }
+                else { g1 = S.ghost_id[j]; g2 = S.ghost_id[i]; }
+                if (S.id[ci] > S.id[cj]) { G1 = S.ghost_id[ci]; G2 = S.ghost_id[cj]; }
+                else { G1 = S.ghost_id[cj]; G2 = S.ghost_id[ci]; }
+                bool ma = g1 == G1, mb = g2 == G2;
+                keep = (ma && mb) || (ma != mb);
+            }
+        }
+        B.keep[p] = keep;
+    }
+}
+
+// ---- K3/K4: narrow phase -------------------------------------------------------------------------------------
+__device__ void narrow_item(const Ws &w, const Store &S, const StepBuf &B, const Params &P, int slot, bool large) {
+    const int lane = lane_id();
+    Counters *cnt = S.cnt;
+    const DomainDev *D = S.dom;
+    const bool is_pair = slot < B.cap_pairs;
+    int fi, fj = -1, elem = -1;
+    if (is_pair) {
+        fi = B.pair_i[slot];
+        fj = B.pair_j[slot];
+    } else {
+        int q = slot - B.cap_pairs;
+        fi = B.dom_floe[q];
+        elem = B.dom_elem[q];
+    }
+    const int npp = S.vcount[fi];
+    int nqp, kind = SZ_BOUNDARY_COLLISION;
+    const double2 *gQ = nullptr;
+    if (is_pair) {
+        nqp = S.vcount[fj];
+        gQ = S.verts + S.vstart[fj];
+    } else if (elem < 4) {
+        nqp = 5;
+        kind = D->kind[elem];
+    } else {
+        nqp = S.topo_vcount[elem - 4];
+        gQ = S.topo_verts + S.topo_vstart[elem - 4];
+    }
+    int status = CLIP_OK;
+    uint32_t flags = 0;
+    int nrows = 0;
+    if (npp > w.maxv || nqp > w.maxv) status = CLIP_OVERFLOW;
+    if (status == CLIP_OK) {
+        const double2 *gP = S.verts + S.vstart[fi];
+        for (int k = lane; k < npp; k += 32) w.P[k] = gP[k];
+        if (gQ) {
+            for (int k = lane; k < nqp; k += 32) w.Q[k] = gQ[k];
+        } else {
+            stage_wall_ring(w.Q, D, elem, lane);
+        }
+        __syncwarp();
+        int nreg = warp_clip(w, w.P, npp, w.Q, nqp, w.R1, w.rs1, w.re1, status);
+        if (status == CLIP_FAIL) {
+            flags |= IT_CLIPFAIL;
+            status = CLIP_OK;
+        }
+        if (status == CLIP_OK) {
+            for (int r = lane; r < nreg; r += 32) w.area1[r] = ring_area_seq(w.R1 + w.rs1[r], w.re1[r] - w.rs1[r]);
+            __syncwarp();
+            double total = 0.0, max_area = 0.0;
+            for (int r = 0; r < nreg; ++r) {
+                double a = w.area1[r];
+                total += a;
+                if (a > max_area) max_area = a;
+            }
+            const double ai = S.area[fi], hi = S.height[fi];
+            int ncontact = 0;
+            double ju = 0.0, jv = 0.0, jxi = 0.0, jcx = 0.0, jcy = 0.0;
+            if (is_pair) {
+                if (total > 0) {  // collisions.jl:364-405
+                    flags |= IT_OVERLAP;
+                    const double aj = S.area[fj];
+                    if (fmax(total / ai, total / aj) > P.cfg.floe_floe_max_overlap) {
+                        flags |= IT_FUSE;
+                    } else {
+                        const double hj = S.height[fj];
+                        double ir = sqrt(ai), jr = sqrt(aj);
+                        double ff = (ir > 1e5 || jr > 1e5) ? P.cfg.E * fmin(hi, hj) / fmin(ir, jr)
+                                                           : P.cfg.E * (hi * hj) / (hi * jr + hj * ir);
+                        ncontact = warp_elastic_forces(w, w.P, npp, w.Q, nqp, nreg, ff, status, flags);
+                        ju = S.u[fj];
+                        jv = S.v[fj];
+                        jxi = S.xi[fj];
+                        jcx = S.cx[fj];
+                        jcy = S.cy[fj];
+                    }
+                }
+            } else if (kind == SZ_BOUNDARY_OPEN) {  // collisions.jl:427-441
+                if (total > 0) flags |= IT_OVERLAP | IT_REMOVE;
+            } else if (max_area > 0) {  // collisions.jl:522-555
+                flags |= IT_OVERLAP;
+                if (max_area / ai > P.cfg.floe_domain_max_overlap) {
+                    flags |= IT_REMOVE;
+                } else {
+                    double ff = P.cfg.E * hi / sqrt(ai);
+                    ncontact = warp_elastic_forces(w, w.P, npp, w.Q, nqp, nreg, ff, status, flags);
+                    if (elem < 4 && kind == SZ_BOUNDARY_MOVING) {  // boundaries.jl:522
+                        ju = D->wu[elem];
+                        jv = D->wv[elem];
+                    }
+                }
+            }
+            if (status == CLIP_OK && lane == 0 && ncontact > 0) {
+                const double iu = S.u[fi], iv = S.v[fi], ixi = S.xi[fi], icx = S.cx[fi], icy = S.cy[fi];
+                for (int k = 0; k < ncontact; ++k) {
+                    double *c = w.ct + 6 * k;
+                    if (!is_pair && elem < 4) {  // _normal_direction_correct!, boundaries.jl:37-40,73-76,110-113,147-150
+                        if (elem == 0 && c[3] >= D->val[0]) c[0] = 0.0;
+                        if (elem == 1 && c[3] <= D->val[1]) c[0] = 0.0;
+                        if (elem == 2 && c[2] >= D->val[2]) c[1] = 0.0;
+                        if (elem == 3 && c[2] <= D->val[3]) c[1] = 0.0;
+                    }
+                    double fr[2];
+                    friction_force(P.cfg.E, P.cfg.nu, P.cfg.mu, (double)P.cfg.dt, iu, iv, ixi, icx, icy, ju, jv, jxi,
+                                   jcx, jcy, c, fr);
+                    double fx = c[0] + fr[0], fy = c[1] + fr[1];
+                    if (fx != 0 || fy != 0) {  // add_interactions!, collisions.jl:288
+                        double *o = w.ct + 6 * nrows;
+                        double px = c[2], py = c[3], ov = c[4];
+                        o[0] = fx;
+                        o[1] = fy;
+                        o[2] = px;
+                        o[3] = py;
+                        o[4] = ov;
+                        nrows++;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        if (status == CLIP_OVERFLOW) {
+            if (large) {
+                atomicOr(&cnt->error, ERR_POLY_TOO_LARGE);
+            } else {
+                int s = atomicAdd(&cnt->n_large, 1);
+                B.large_items[s] = slot;
+            }
+            B.item_nrows[slot] = 0;
+            B.item_flags[slot] = IT_NEEDLARGE;
+        } else {
+            int row0 = 0;
+            if (nrows > 0) {
+                row0 = atomicAdd(&cnt->n_pool, nrows);
+                if (row0 + nrows > B.cap_pool) {
+                    atomicOr(&cnt->error, ERR_POOL_CAP);
+                    nrows = 0;
+                } else {
+                    for (int k = 0; k < nrows; ++k)
+                        for (int q = 0; q < NPOOL; ++q) B.pool[(size_t)(row0 + k) * NPOOL + q] = w.ct[6 * k + q];
+                }
+            }
+            B.item_nrows[slot] = nrows;
+            B.item_row0[slot] = row0;
+            B.item_flags[slot] = flags | IT_DONE;
+            if (flags & IT_CLIPFAIL) atomicAdd(&cnt->n_clipfail, 1);
+            if (is_pair && (flags & IT_OVERLAP)) atomicAdd(&cnt->n_overlap, 1);
+            if (flags & IT_FUSE) {
+                int s = atomicAdd(&cnt->n_fuse, 1);
+                if (s < B.cap_fuse) B.fuse_pairs[s] = make_int2(fi, fj);
+                else atomicOr(&cnt->error, ERR_FUSE_CAP);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void k_narrow(Store S, StepBuf B, Params P, int maxv, int maxx, int large) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    Ws w = ws_carve(smem + (size_t)wib * ws_bytes(maxv, maxx), maxv, maxx);
+    if (!large) {
+        int np = cnt->n_cand, total = np + cnt->n_dom;
+        for (int it = blockIdx.x * wpb + wib; it < total; it += gridDim.x * wpb) {
+            int slot = it < np ? it : B.cap_pairs + (it - np);
+            if (it < np && !B.keep[it]) {
+                if (lane_id() == 0) {
+                    B.item_nrows[slot] = 0;
+                    B.item_flags[slot] = 0;
+                }
+                continue;
+            }
+            narrow_item(w, S, B, P, slot, false);
+        }
+    } else {
+        int nl = cnt->n_large;
+        for (int it = blockIdx.x * wpb + wib; it < nl; it += gridDim.x * wpb) narrow_item(w, S, B, P, B.large_items[it], true);
+    }
+}
+
+__global__ void k_pool_check(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->n_pool > B.cap_pool) cnt->want_pool = cnt->n_pool;
+    if (cnt->n_fuse > B.cap_fuse) cnt->want_fuse = cnt->n_fuse;
+}
+
+// ---- K5: status, rows, totals ------------------------------------------------------------------------------------
+// status.tag after the pair loop and floe_domain_interaction! (collisions.jl:366-368,438,524),
+// in the reference's order: fuse from own pairs first, then a domain removal overrides it.
+__global__ void k_status(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int s = S.status[i];
+        for (int p = B.up_off[i], pe = B.up_off[i + 1]; p < pe; ++p)
+            if (B.keep[p] && (B.item_flags[p] & IT_FUSE)) s = SZ_STATUS_FUSE;
+        for (int q = B.dom_off[i], qe = B.dom_off[i + 1]; q < qe; ++q)
+            if (B.item_flags[B.cap_pairs + q] & IT_REMOVE) s = SZ_STATUS_REMOVE;
+        S.status[i] = s;
+    }
+}
+
+// serial fuse propagation, collisions.jl:799-806: ascending i hands its tag to the partners in
+// fuse_idx; since partners recorded by the pair loop are always j > i the serial result is the
+// closure of "i fused => j fused" over the fuse pairs, computed here as a fixed point.
+__global__ void k_fuse_propagate(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int nf = min(cnt->n_fuse, B.cap_fuse);
+    if (nf == 0) return;
+    __shared__ int changed;
+    do {
+        __syncthreads();
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+            int2 pr = B.fuse_pairs[k];
+            if (S.status[pr.x] == SZ_STATUS_FUSE && S.status[pr.y] != SZ_STATUS_FUSE) {
+                S.status[pr.y] = SZ_STATUS_FUSE;
+                changed = 1;
+            }
+        }
+        __syncthreads();
+    } while (changed);
+}
+
+__global__ void k_row_count(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+        int c = 0;
+        for (int p = B.up_off[f], pe = B.up_off[f + 1]; p < pe; ++p)
+            if (B.keep[p]) c += B.item_nrows[p];
+        for (int q = B.dom_off[f], qe = B.dom_off[f + 1]; q < qe; ++q) c += B.item_nrows[B.cap_pairs + q];
+        for (int t = B.low_off[f], te = B.low_off[f + 1]; t < te; ++t) {
+            int p = B.low_pair[t];
+            if (B.keep[p]) c += B.item_nrows[p];
+        }
+        B.row_pre[f] = c;
+    }
+}
+
+__global__ void k_row_total(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+        int c = B.row_pre[f];
+        if (f < S.n_init)
+            for (int g = 0, ng = S.nghost[f]; g < ng; ++g) c += B.row_pre[S.ghost_slot[f * SZ_MAX_GHOSTS + g]];
+        B.row_count[f] = c;
+    }
+}
+
+__global__ void k_row_check(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    if (cnt->n_rows > B.cap_rows) {
+        cnt->error |= ERR_ROW_CAP;
+        cnt->want_rows = cnt->n_rows;
+    }
+}
+
+// rows of floe f in the reference's order: own pairs (j ascending, regions in clip order), walls
+// N,S,E,W, topography (collisions.jl:776-794), mirrored rows (i ascending, :808-827).  (sx, sy)
+// is the ghost->parent shift of the contact points (:835-838).
+__device__ int emit_base_rows(const Store &S, const StepBuf &B, int f, double *dst, double sx, double sy, bool shift) {
+    int n = 0;
+    for (int p = B.up_off[f], pe = B.up_off[f + 1]; p < pe; ++p) {
+        if (!B.keep[p]) continue;
+        const double *src = B.pool + (size_t)B.item_row0[p] * NPOOL;
+        double idx = (double)(B.pair_j[p] + 1);
+        for (int k = 0, nk = B.item_nrows[p]; k < nk; ++k, ++n) {
+            double *r = dst + (size_t)n * NCOL;
+            const double *c = src + k * NPOOL;
+            r[COL_IDX] = idx;
+            r[COL_FX] = c[0];
+            r[COL_FY] = c[1];
+            r[COL_PX] = shift ? c[2] - sx : c[2];
+            r[COL_PY] = shift ? c[3] - sy : c[3];
+            r[COL_TRQ] = 0.0;
+            r[COL_OV] = c[4];
+        }
+    }
+    for (int q = B.dom_off[f], qe = B.dom_off[f + 1]; q < qe; ++q) {
+        int slot = B.cap_pairs + q;
+        const double *src = B.pool + (size_t)B.item_row0[slot] * NPOOL;
+        double idx = (double)(-(B.dom_elem[q] + 1));
+        for (int k = 0, nk = B.item_nrows[slot]; k < nk; ++k, ++n) {
+            double *r = dst + (size_t)n * NCOL;
+            const double *c = src + k * NPOOL;
+            r[COL_IDX] = idx;
+            r[COL_FX] = c[0];
+            r[COL_FY] = c[1];
+            r[COL_PX] = shift ? c[2] - sx : c[2];
+            r[COL_PY] = shift ? c[3] - sy : c[3];
+            r[COL_TRQ] = 0.0;
+            r[COL_OV] = c[4];
+        }
+    }
+    for (int t = B.low_off[f], te = B.low_off[f + 1]; t < te; ++t) {
+        int p = B.low_pair[t];
+        if (!B.keep[p]) continue;
+        const double *src = B.pool + (size_t)B.item_row0[p] * NPOOL;
+        double idx = (double)(B.pair_i[p] + 1);
+        for (int k = 0, nk = B.item_nrows[p]; k < nk; ++k, ++n) {
+            double *r = dst + (size_t)n * NCOL;
+            const double *c = src + k * NPOOL;
+            r[COL_IDX] = idx;
+            r[COL_FX] = -c[0];
+            r[COL_FY] = -c[1];
+            r[COL_PX] = shift ? c[2] - sx : c[2];
+            r[COL_PY] = shift ? c[3] - sy : c[3];
+            r[COL_TRQ] = 0.0;
+            r[COL_OV] = c[4];
+        }
+    }
+    return n;
+}
+
+// one thread per floe: its rows are written and summed in row order, so collision_force /
+// collision_trq / overarea are the same bits on every run (collisions.jl:830-862, 673-686)
+__global__ void k_row_write(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+        double *dst = B.rows + (size_t)B.row_off[f] * NCOL;
+        int par = S.parent[f];
+        int nr;
+        if (f >= S.n_init && par >= 0) {
+            nr = emit_base_rows(S, B, f, dst, S.cx[f] - S.cx[par], S.cy[f] - S.cy[par], true);
+        } else {
+            nr = emit_base_rows(S, B, f, dst, 0.0, 0.0, false);
+        }
+        if (f < S.n_init) {
+            for (int g = 0, ng = S.nghost[f]; g < ng; ++g) {
+                int gi = S.ghost_slot[f * SZ_MAX_GHOSTS + g];
+                nr += emit_base_rows(S, B, gi, dst + (size_t)nr * NCOL, S.cx[gi] - S.cx[f], S.cy[gi] - S.cy[f], true);
+            }
+        }
+        double oa = S.overarea[f];
+        double sx = 0.0, sy = 0.0, st = 0.0;
+        const double cx = S.cx[f], cy = S.cy[f];
+        for (int k = 0; k < nr; ++k) {
+            double *r = dst + (size_t)k * NCOL;
+            oa += r[COL_OV];
+            if (f < S.n_init) {
+                double xp = r[COL_PX] - cx, yp = r[COL_PY] - cy;
+                double trq = xp * r[COL_FY] - yp * r[COL_FX];
+                r[COL_TRQ] = trq;
+                sx += r[COL_FX];
+                sy += r[COL_FY];
+                st += trq;
+            }
+        }
+        S.overarea[f] = oa;
+        if (f < S.n_init) {
+            S.cfx[f] += sx;
+            S.cfy[f] += sy;
+            S.ctrq[f] += st;
+        }
+    }
+}
+
+// update_boundaries!, collisions.jl:565-571; _update_boundary!, boundaries.jl:526-544
+__global__ void k_update_boundaries(Store S, Params P) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    DomainDev *D = S.dom;
+    for (int wl = 0; wl < 4; ++wl) {
+        if (D->kind[wl] != SZ_BOUNDARY_MOVING) continue;
+        if (wl < 2) {
+            double d = D->wv[wl] * P.cfg.dt;
+            D->rect[wl][2] += d;
+            D->rect[wl][3] += d;
+            D->val[wl] += d;
+        } else {
+            double d = D->wu[wl] * P.cfg.dt;
+            D->rect[wl][0] += d;
+            D->rect[wl][1] += d;
+            D->val[wl] += d;
+        }
+    }
+}
+
+__global__ void k_kept_count(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int np = cnt->n_cand, c = 0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) c += B.keep[p];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULLMASK, c, o);
+    if (lane_id() == 0 && c) atomicAdd(&cnt->n_kept, c);
+}
+
+void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_hint, int pairs_hint,
+                    cudaEvent_t *ev) {
+    cudaStream_t st = L.stream;
+    int gf = grid_for(L, n_hint, TPB);
+    k_step_reset<<<gf, TPB, 0, st>>>(S);
+    k_bbox<<<gf, TPB, 0, st>>>(S);
+    k_grid_setup<<<1, 1, 0, st>>>(S, B);
+    k_cell_zero<<<grid_for(L, B.cap_cells, TPB), TPB, 0, st>>>(S, B);
+    k_cell_count<<<gf, TPB, 0, st>>>(S, B);
+    scan_excl(L, S, B.cell_count, B.cell_start, &S.cnt->n_cells, 0, B.cap_cells, B.scan_block, nullptr);
+    k_cell_fill<<<gf, TPB, 0, st>>>(S, B);
+    k_neighbours<false><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
+    scan_excl(L, S, B.up_count, B.up_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, &S.cnt->n_cand);
+    scan_excl(L, S, B.low_count, B.low_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, nullptr);
+    scan_excl(L, S, B.dom_count, B.dom_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, &S.cnt->n_dom);
+    k_pair_check<<<1, 1, 0, st>>>(S, B);
+    k_neighbours<true><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
+    k_low_link<<<gf, TPB, 0, st>>>(S, B);
+    int gp = grid_for(L, pairs_hint, TPB);
+    k_filter<<<gp, TPB, 0, st>>>(S, B);
+    k_kept_count<<<gp, TPB, 0, st>>>(S, B);
+    if (ev) cudaEventRecord(ev[0], st);
+    const int maxv_s = 32, maxx_s = 16, wpb = 4;
+    long long items = (long long)pairs_hint + n_hint / 8 + 64;
+    k_narrow<<<grid_for(L, items, wpb), wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
+    k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
+    k_pool_check<<<1, 1, 0, st>>>(S, B);
+    if (ev) cudaEventRecord(ev[1], st);
+    k_status<<<gf, TPB, 0, st>>>(S, B);
+    k_fuse_propagate<<<1, 1024, 0, st>>>(S, B);
+    k_row_count<<<gf, TPB, 0, st>>>(S, B);
+    k_row_total<<<gf, TPB, 0, st>>>(S, B);
+    scan_excl(L, S, B.row_count, B.row_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, &S.cnt->n_rows);
+    k_row_check<<<1, 1, 0, st>>>(S, B);
+    k_row_write<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
+    k_update_boundaries<<<1, 1, 0, st>>>(S, P);
+    if (ev) cudaEventRecord(ev[2], st);
+}
+
+// ---- K6: one-way ocean/atmosphere coupling (coupling.jl:1486-1589) ---------------------------------------------------
+// One warp per floe.  Lanes read the floe's body-frame Monte-Carlo points as consecutive double2
+// (512 B per warp load), rotate/translate them (calc_subfloe_values!, :627-657), drop points
+// outside a non-periodic grid extent (in_bounds, :494-597), gather the five fields bilinearly
+// (mc_interpolation :845-902 == bilinear on the lattice; periodic axes wrap on lines 1..N) and
+// reduce stress and torque with shuffles in a fixed order.  With r = (xc, yc), theta = atan(yc, xc):
+// rad sin(theta) = yc and rad cos(theta) = xc, so the reference's u - xi rad sin(theta) (:1534-1537)
+// and (-tx sin + ty cos) rad (:1562) are evaluated without transcendental calls (agreement ~1e-16).
+__device__ __forceinline__ double bilin(const double *__restrict__ F, size_t s, int i0, int i1, int j0, int j1,
+                                        double wx, double wy) {
+    double f00 = __ldg(F + i0 + s * j0), f10 = __ldg(F + i1 + s * j0), f01 = __ldg(F + i0 + s * j1),
+           f11 = __ldg(F + i1 + s * j1);
+    return (1 - wy) * ((1 - wx) * f00 + wx * f10) + wy * ((1 - wx) * f01 + wx * f11);
+}
+
+__global__ void __launch_bounds__(256) k_coupling(Store S, Params P) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const DomainDev *D = S.dom;
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const bool per_x = D->kind[2] == SZ_BOUNDARY_PERIODIC, per_y = D->kind[0] == SZ_BOUNDARY_PERIODIC;
+    const int Nx = P.Nx, Ny = P.Ny;
+    const size_t s = (size_t)(Nx + 1);
+    const double ct = cos(P.cfg.turn_theta), sn = sin(P.cfg.turn_theta);
+    const double ka = P.cfg.rho_a * P.cfg.Cd_ia, ko = P.cfg.rho_o * P.cfg.Cd_io;
+    const int n = S.n_init;
+    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
+        const double a = S.alpha[i], cx = S.cx[i], cy = S.cy[i], u = S.u[i], v = S.v[i], xi = S.xi[i];
+        const double ca = cos(a), sa = sin(a);
+        const double ma_ratio = S.mass[i] / S.area[i];
+        const double mf = ma_ratio * P.cfg.f;
+        double tx_s = 0, ty_s = 0, trq_s = 0, hf_s = 0;
+        int npts = 0;
+        const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
+        for (long long k = m0 + lane; k < m1; k += 32) {
+            double2 b = S.mc[k];
+            double px = ca * b.x - sa * b.y, py = sa * b.x + ca * b.y;
+            double x = px + cx, y = py + cy;
+            bool inb = (per_x || (P.x0 <= x && x <= P.xf)) && (per_y || (P.y0 <= y && y <= P.yf));
+            if (!inb) continue;
+            npts++;
+            double xc = x - cx, yc = y - cy;
+            double up = u - xi * yc, vp = v + xi * xc;
+            double gx = (x - P.x0) / P.dx, gy = (y - P.y0) / P.dy;
+            double fx = floor(gx), fy = floor(gy);
+            long long ci = (long long)fx, cj = (long long)fy;
+            double wx = gx - fx, wy = gy - fy;
+            int i0, i1, j0, j1;
+            if (per_x) {
+                i0 = (int)(((ci % Nx) + Nx) % Nx);
+                i1 = (i0 + 1) % Nx;
+            } else {
+                if (ci >= Nx) { ci = Nx - 1; wx = 1.0; }
+                if (ci < 0) { ci = 0; wx = 0.0; }
+                i0 = (int)ci;
+                i1 = i0 + 1;
+            }
+            if (per_y) {
+                j0 = (int)(((cj % Ny) + Ny) % Ny);
+                j1 = (j0 + 1) % Ny;
+            } else {
+                if (cj >= Ny) { cj = Ny - 1; wy = 1.0; }
+                if (cj < 0) { cj = 0; wy = 0.0; }
+                j0 = (int)cj;
+                j1 = j0 + 1;
+            }
+            double uatm = bilin(S.atm_u, s, i0, i1, j0, j1, wx, wy), vatm = bilin(S.atm_v, s, i0, i1, j0, j1, wx, wy);
+            double uocn = bilin(S.ocn_u, s, i0, i1, j0, j1, wx, wy), vocn = bilin(S.ocn_v, s, i0, i1, j0, j1, wx, wy);
+            double hfl = bilin(S.ocn_hflx, s, i0, i1, j0, j1, wx, wy);
+            double dua = uatm - up, dva = vatm - vp;  // calc_atmosphere_forcing, coupling.jl:1212-1232
+            double na = sqrt(dua * dua + dva * dva);
+            double tax = ka * na * dua, tay = ka * na * dva;
+            double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
+            double no = sqrt(duo * duo + dvo * dvo);
+            double tox = ko * no * (ct * duo - sn * dvo), toy = ko * no * (sn * duo + ct * dvo);
+            double tpx = -mf * vocn, tpy = mf * uocn;
+            double tx = tax + tpx + tox, ty = tay + tpy + toy;
+            tx_s += tx;
+            ty_s += ty;
+            trq_s += -tx * yc + ty * xc;
+            hf_s += hfl;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            tx_s += __shfl_xor_sync(FULLMASK, tx_s, o);
+            ty_s += __shfl_xor_sync(FULLMASK, ty_s, o);
+            trq_s += __shfl_xor_sync(FULLMASK, trq_s, o);
+            hf_s += __shfl_xor_sync(FULLMASK, hf_s, o);
+            npts += __shfl_xor_sync(FULLMASK, npts, o);
+        }
+        if (lane == 0) {
+            if (npts == 0) {
+                S.status[i] = SZ_STATUS_REMOVE;  // coupling.jl:1507-1508
+            } else {
+                double np_ = (double)npts, ar = S.area[i];
+                double tot_x = np_ * (mf * v) + tx_s, tot_y = -np_ * (mf * u) + ty_s;  // Coriolis, :1522-1525
+                S.fxOA[i] = tot_x / np_ * ar;  // :1583-1586
+                S.fyOA[i] = tot_y / np_ * ar;
+                S.trqOA[i] = trq_s / np_ * ar;
+                S.hflx[i] = hf_s / np_;
+            }
+        }
+    }
+}
+
+void szk_coupling(const Launch &L, const Store &S, const Params &P) {
+    if (S.n_init > 0) k_coupling<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, P);
+}
+
+// ---- K7: state update (update_floe.jl:392-551) ---------------------------------------------------------------------------
+// One warp per floe: scalars are computed by every lane (uniform), vertices and the strain sum are
+// spread over the lanes.
+__global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const double dt = (double)P.cfg.dt;
+    const int n = S.n_init;
+    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
+        uint32_t warn = 0;
+        double cfx = S.cfx[i], cfy = S.cfy[i], ctrq = S.ctrq[i];
+        const double cx = S.cx[i], cy = S.cy[i], area = S.area[i];
+        double height = S.height[i];
+        // calc_stress!, :392-414 (pre-move centroid)
+        double s11 = 0, s12 = 0, s22 = 0;
+        int r0 = B.row_off[i], r1 = B.row_off[i + 1];
+        if (r1 > r0) {
+            for (int k = r0; k < r1; ++k) {
+                const double *r = B.rows + (size_t)k * NCOL;
+                double fx = r[COL_FX], fy = r[COL_FY], px = r[COL_PX], py = r[COL_PY];
+                s11 += (px - cx) * fx;
+                s12 += (py - cy) * fx + (px - cx) * fy;
+                s22 += (py - cy) * fy;
+            }
+            s12 *= 0.5;
+            double inv = 1 / (area * height);
+            s11 *= inv;
+            s12 *= inv;
+            s22 *= inv;
+        }
+        double stv[4] = {s11, s12, s12, s22};
+        double lam = P.cfg.stress_lambda;  // stress_calculators.jl:118-122
+        if (lane < 4) {
+            S.stress_accum[4 * i + lane] = (1 - lam) * S.stress_accum[4 * i + lane] + lam * stv[lane];
+            S.stress_instant[4 * i + lane] = stv[lane];
+        }
+        if (height > P.cfg.max_floe_height) {  // :482-485
+            height = P.cfg.max_floe_height;
+            warn |= SZ_WARN_HEIGHT_CAPPED;
+        }
+        double mass = S.mass[i], moment = S.moment[i];
+        while (fmax(fabs(cfx), fabs(cfy)) > mass / (5 * dt)) {  // :487-491
+            cfx = cfx / 10;
+            cfy = cfy / 10;
+            ctrq = ctrq / 10;
+            warn |= SZ_WARN_FORCE_SCALED;
+        }
+        double hh = height;  // :494-500
+        double dh = S.hflx[i] / hh;
+        double hfrac = (hh + dh) / hh;
+        mass *= hfrac;
+        moment *= hfrac;
+        height -= dh;
+        hh = height;
+        const double u0 = S.u[i], v0 = S.v[i], xi0 = S.xi[i];
+        double Dx = 1.5 * dt * u0 - 0.5 * dt * S.p_dxdt[i];  // :503-506
+        double Dy = 1.5 * dt * v0 - 0.5 * dt * S.p_dydt[i];
+        double Da = 1.5 * dt * xi0 - 0.5 * dt * S.p_dalphadt[i];
+        // _move_floe! / _move_poly, floe_utils.jl:74-93: p -> R p + ((R(-c) + c) + D)
+        double sn = sin(Da), cs = cos(Da);
+        double tx = ((cs * (-cx) - sn * (-cy)) + cx) + Dx;
+        double ty = ((sn * (-cx) + cs * (-cy)) + cy) + Dy;
+        const double ncx = cx + Dx, ncy = cy + Dy;
+        double dudt = (S.fxOA[i] + cfx) / mass;  // :514-531
+        double dvdt = (S.fyOA[i] + cfy) / mass;
+        double frac = 1;
+        double au = fabs(dt * dudt), av = fabs(dt * dvdt), lim = hh / 2;
+        double sgu = (double)((dudt > 0) - (dudt < 0)), sgv = (double)((dvdt > 0) - (dvdt < 0));
+        if (au > lim && av > lim) {
+            double f1 = (sgu * hh / (2 * dt)) / dudt, f2 = (sgv * hh / (2 * dt)) / dvdt;
+            frac = f1 < f2 ? f1 : f2;
+        } else if (au > lim && av < lim) frac = (sgu * hh / (2 * dt)) / dudt;
+        else if (au < lim && av > lim) frac = (sgv * hh / (2 * dt)) / dvdt;
+        if (frac != 1) {
+            dudt = frac * dudt;
+            dvdt = frac * dvdt;
+            warn |= SZ_WARN_VELOCITY_LIMITED;
+        }
+        const double un = u0 + (1.5 * dt * dudt - 0.5 * dt * S.p_dudt[i]);  // :532-535
+        const double vn = v0 + (1.5 * dt * dvdt - 0.5 * dt * S.p_dvdt[i]);
+        double dxidt = (S.trqOA[i] + ctrq) / moment;  // :537-545
+        dxidt = frac * dxidt;
+        double xin = xi0 + 1.5 * dt * dxidt - 0.5 * dt * S.p_dxidt[i];
+        if (fabs(xin) > P.cfg.maximum_xi) {
+            xin = (double)((xin > 0) - (xin < 0)) * P.cfg.maximum_xi;
+            warn |= SZ_WARN_XI_CLAMPED;
+        }
+        // rigid move of the ring + calc_strain! (:425-453; v-terms use floe.u as the reference does)
+        const int vs = S.vstart[i], nv = S.vcount[i];
+        double e11 = 0, e12 = 0, e22 = 0;
+        for (int base = 0; base < nv; base += 32) {
+            const int k = base + lane;
+            const bool act = k < nv;
+            double2 p = act ? S.verts[vs + k] : make_double2(0.0, 0.0);
+            double2 q = make_double2((cs * p.x - sn * p.y) + tx, (sn * p.x + cs * p.y) + ty);
+            if (k + 1 < nv) {
+                double2 p2 = S.verts[vs + k + 1];
+                double2 q2 = make_double2((cs * p2.x - sn * p2.y) + tx, (sn * p2.x + cs * p2.y) + ty);
+                double x1 = q.x + (-ncx), y1 = q.y + (-ncy), x2 = q2.x + (-ncx), y2 = q2.y + (-ncy);
+                double xd = x2 - x1, yd = y2 - y1;
+                double ra1 = sqrt(x1 * x1 + y1 * y1), ra2 = sqrt(x2 * x2 + y2 * y2);
+                double t1 = atan2(y1, x1), t2 = atan2(y2, x2);
+                double u1 = un - xin * ra1 * sin(t1), u2 = un - xin * ra2 * sin(t2);
+                double v1 = un + xin * ra1 * cos(t1), v2 = un + xin * ra2 * cos(t2);
+                double ud = u2 - u1, vd = v2 - v1;
+                e11 += ud * yd;
+                e12 += ud * xd + vd * yd;
+                e22 += vd * xd;
+            }
+            __syncwarp();
+            if (act) S.verts[vs + k] = q;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            e11 += __shfl_xor_sync(FULLMASK, e11, o);
+            e12 += __shfl_xor_sync(FULLMASK, e12, o);
+            e22 += __shfl_xor_sync(FULLMASK, e22, o);
+        }
+        if (lane == 0) {
+            e12 *= 0.5;
+            double den = 2 * area;
+            S.strain[4 * i + 0] = e11 / den;
+            S.strain[4 * i + 1] = e12 / den;
+            S.strain[4 * i + 2] = e12 / den;
+            S.strain[4 * i + 3] = e22 / den;
+            S.height[i] = height;
+            S.mass[i] = mass;
+            S.moment[i] = moment;
+            S.alpha[i] = S.alpha[i] + Da;
+            S.cx[i] = ncx;
+            S.cy[i] = ncy;
+            S.p_dxdt[i] = u0;  // :509-511
+            S.p_dydt[i] = v0;
+            S.p_dalphadt[i] = xi0;
+            S.u[i] = un;
+            S.v[i] = vn;
+            S.p_dudt[i] = dudt;
+            S.p_dvdt[i] = dvdt;
+            S.xi[i] = xin;
+            S.p_dxidt[i] = dxidt;
+            S.warn[i] = warn;
+        }
+    }
+}
+
+void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P) {
+    if (S.n_init > 0) k_update<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, B, P);
+}
+
+// ---- geometry service / test hook -------------------------------------------------------------------------------------------
+__global__ void k_debug_clip(const double2 *gP, int npp, const double2 *gQ, int nqp, int maxv, int maxx, int cap_regions,
+                             int cap_points, int *out_offsets, double2 *out_xy, double *out_areas, int *out_n) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Ws w = ws_carve(smem, maxv, maxx);
+    const int lane = lane_id();
+    if (npp > maxv || nqp > maxv) {
+        if (lane == 0) *out_n = SZ_ERR_CAPACITY;
+        return;
+    }
+    for (int k = lane; k < npp; k += 32) w.P[k] = gP[k];
+    for (int k = lane; k < nqp; k += 32) w.Q[k] = gQ[k];
+    __syncwarp();
+    int status;
+    int nreg = warp_clip(w, w.P, npp, w.Q, nqp, w.R1, w.rs1, w.re1, status);
+    if (lane == 0) {
+        if (status == CLIP_OVERFLOW) *out_n = SZ_ERR_CAPACITY;
+        else if (status == CLIP_FAIL) *out_n = -100;
+        else {
+            int o = 0, ok = nreg <= cap_regions;
+            out_offsets[0] = 0;
+            for (int r = 0; r < nreg && ok; ++r) {
+                int a = w.rs1[r], b = w.re1[r];
+                if (o + (b - a) > cap_points) { ok = 0; break; }
+                for (int k = a; k < b; ++k) out_xy[o++] = w.R1[k];
+                out_offsets[r + 1] = o;
+                out_areas[r] = ring_area_seq(w.R1 + a, b - a);
+            }
+            *out_n = ok ? nreg : SZ_ERR_CAPACITY;
+        }
+    }
+}
+
+size_t szk_large_smem(int maxv, int maxx) { return ws_bytes(maxv, maxx); }
+
+int szk_debug_clip(const Launch &L, const double *p_xy, int np, const double *q_xy, int nq, int cap_regions,
+                   int cap_points, int *out_offsets, double *out_xy, double *out_areas) {
+    double2 *dP = nullptr, *dQ = nullptr, *dxy = nullptr;
+    double *dar = nullptr;
+    int *doff = nullptr, *dn = nullptr;
+    int rc = SZ_ERR_CUDA, n = 0;
+    if (cudaMalloc(&dP, sizeof(double2) * np) != cudaSuccess) goto done;
+    if (cudaMalloc(&dQ, sizeof(double2) * nq) != cudaSuccess) goto done;
+    if (cudaMalloc(&dxy, sizeof(double2) * (cap_points + 1)) != cudaSuccess) goto done;
+    if (cudaMalloc(&dar, sizeof(double) * (cap_regions + 1)) != cudaSuccess) goto done;
+    if (cudaMalloc(&doff, sizeof(int) * (cap_regions + 2)) != cudaSuccess) goto done;
+    if (cudaMalloc(&dn, sizeof(int)) != cudaSuccess) goto done;
+    cudaMemcpyAsync(dP, p_xy, sizeof(double2) * np, cudaMemcpyHostToDevice, L.stream);
+    cudaMemcpyAsync(dQ, q_xy, sizeof(double2) * nq, cudaMemcpyHostToDevice, L.stream);
+    k_debug_clip<<<1, 32, ws_bytes(L.maxv_large, L.maxx_large), L.stream>>>(dP, np, dQ, nq, L.maxv_large, L.maxx_large,
+                                                                           cap_regions, cap_points, doff, dxy, dar, dn);
+    cudaMemcpyAsync(&n, dn, sizeof(int), cudaMemcpyDeviceToHost, L.stream);
+    if (cudaStreamSynchronize(L.stream) != cudaSuccess) goto done;
+    rc = n;
+    if (n > 0) {
+        cudaMemcpy(out_offsets, doff, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost);
+        cudaMemcpy(out_xy, dxy, sizeof(double2) * out_offsets[n], cudaMemcpyDeviceToHost);
+        if (out_areas) cudaMemcpy(out_areas, dar, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    } else if (n == 0) {
+        out_offsets[0] = 0;
+    }
+done:
+    cudaFree(dP); cudaFree(dQ); cudaFree(dxy); cudaFree(dar); cudaFree(doff); cudaFree(dn);
+    return rc;
+}
+
+// opt in to > 48 KB dynamic shared memory for the large-polygon kernels (called once per handle)
+int szk_configure(const Launch &L) {
+    size_t lb = ws_bytes(L.maxv_large, L.maxx_large);
+    if (cudaFuncSetAttribute(k_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_ghost_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_debug_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
+    return 0;
+}

@@ -352,19 +352,6 @@ class FloeField(capi.FloeArrays):
     def __len__(self):
         return self.n
 
-    def coords(self, i):
-        return self.ring(i)
-
-    def centroid(self, i):
-        return np.array([self.centroid_x[i], self.centroid_y[i]])
-
-    def adopt(self, fa):
-        """Take over the arrays of a downloaded FloeArrays."""
-        keep = {k: getattr(self, k) for k in ("interactions", "num_inters", "fuse_idx", "warnings")}
-        self.__dict__.update(fa.__dict__)
-        for k, v in keep.items():
-            setattr(self, k, v)
-
 
 def initialize_floe_field(coords, domain=None, hmean=0.25, dh=0.0, floe_settings=None, rng=None, **kw):
     """floe.jl:361-411 (from coordinates): ids are 1..n in order."""

@@ -1,0 +1,176 @@
+"""Parity of the CUDA product against the CPU oracle on the same seeded inputs, through the C ABI.
+
+Bar (BASELINE.json north_star): candidate / filtered / overlap / fuse pair sets and the
+interaction rows bit-exact; per-floe force, torque and updated state within 1e-9 relative.
+One step from identical state, never trajectories (the dynamics are chaotic).
+"""
+import numpy as np
+import pytest
+
+import fields
+from parity_util import RTOL, compare_collision_outputs, compare_state, rel_err
+from subzero_jl_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [
+    # n, scale, walls, flow
+    (60, 1.01, "collision", "random"),
+    (300, 1.01, "shear", "random"),
+    (300, 1.03, "periodic", "converging"),
+    (2000, 1.01, "periodic", "random"),
+    (2000, 0.99, "collision", "converging"),
+    (10000, 1.01, "shear", "random"),
+]
+
+
+def handles(field, product_lib, oracle_lib, **kw):
+    return synth.setup_handle(field, product_lib, **kw), synth.setup_handle(field, oracle_lib, **kw)
+
+
+def assert_ok(bad):
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: "n%d_s%g_%s_%s" % c)
+def test_phase_by_phase(cfg, product_lib, oracle_lib):
+    n, scale, walls, flow = cfg
+    f = synth.make_field(n, scale=scale, walls=walls, flow=flow, npoints=150, cache=False)
+    fields.perturb_state(f.floes)
+    hg, ho = handles(f, product_lib, oracle_lib)
+    # add_ghosts!: ghost order, ids, translated rings — exact
+    ng, no = hg.add_ghosts(), ho.add_ghosts()
+    assert ng == no
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes(), exact=("vert_xy", "centroid_x", "centroid_y")))
+    # timestep_collisions!
+    hg.step_collisions()
+    ho.step_collisions()
+    assert_ok(compare_collision_outputs(hg, ho))
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes(),
+                            exact=("collision_force", "collision_trq", "overarea", "vert_xy")))
+    assert hg.counts()["n_overlap"] > 0 or scale < 1
+    # ghost removal, timestep_coupling!, timestep_floe_properties!
+    for h in (hg, ho):
+        h.remove_ghosts()
+        h.step_coupling()
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes()))
+    for h in (hg, ho):
+        h.step_floe_properties(0)
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes()))
+    assert np.array_equal(hg.warnings(), ho.warnings())
+
+
+@pytest.mark.parametrize("walls", ["collision", "periodic"])
+def test_fused_step_matches_phases(walls, product_lib, oracle_lib):
+    f = synth.make_field(1500, scale=1.01, walls=walls, npoints=100, cache=False)
+    fields.perturb_state(f.floes)
+    hg, ho = handles(f, product_lib, oracle_lib)
+    hg.step(0, True)
+    ho.step(0, True)
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes()))
+    assert hg.counts()["n_candidates"] == ho.counts()["n_candidates"]
+    # a short trajectory stays close (loose: contact sets may start to differ in later steps)
+    for t in range(1, 4):
+        hg.step(t, t % 2 == 0)
+        ho.step(t, t % 2 == 0)
+    a, b = hg.download_floes(), ho.download_floes()
+    assert rel_err(a.centroid_x, b.centroid_x) < 1e-6 and rel_err(a.u, b.u) < 1e-4
+
+
+def test_nonconvex_fixture_shapes(product_lib, oracle_lib):
+    """The reference's own 462 floe shapes (7-591 vertices, non-convex): multi-region clips,
+    the large-polygon kernel, wall contacts."""
+    f = fields.fixture_shape_field(scale=1.04, walls="collision")
+    hg, ho = handles(f, product_lib, oracle_lib)
+    for h in (hg, ho):
+        h.add_ghosts()
+        h.step_collisions()
+    assert_ok(compare_collision_outputs(hg, ho))
+    for h in (hg, ho):
+        h.remove_ghosts()
+        h.step_coupling()
+        h.step_floe_properties(0)
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes()))
+
+
+def test_nonconvex_periodic_ghosts(product_lib, oracle_lib):
+    f = fields.fixture_shape_field(scale=1.02, walls="periodic")
+    hg, ho = handles(f, product_lib, oracle_lib)
+    assert hg.add_ghosts() == ho.add_ghosts()
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes(), exact=("vert_xy",)))
+    hg.step_collisions()
+    ho.step_collisions()
+    assert_ok(compare_collision_outputs(hg, ho))
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes(), exact=("collision_force", "collision_trq")))
+
+
+def test_clip_service_bit_exact(product_lib, oracle_lib):
+    rng = np.random.default_rng(11)
+    f = fields.fixture_shape_field(scale=1.0, nmax=40)
+    hg = capi.Handle(product_lib)
+    ho = capi.Handle(oracle_lib)
+    fa = f.floes
+    tested = 0
+    for _ in range(60):
+        i, j = rng.integers(0, fa.n, 2)
+        p = fa.ring(i).copy()
+        q = fa.ring(j) + (fa.centroid(i) - fa.centroid(j)) + rng.uniform(-2e3, 2e3, 2)
+        rg, ag = hg.clip_polygons(p, q)
+        ro, ao = ho.clip_polygons(p, q)
+        assert len(rg) == len(ro)
+        for a, b in zip(rg, ro):
+            assert np.array_equal(a, b)
+        assert np.array_equal(ag, ao)
+        tested += len(ro)
+    assert tested > 30
+
+
+def test_deterministic_and_capacity_retry(product_lib):
+    f = synth.make_field(3000, scale=1.02, walls="periodic", npoints=50, cache=False)
+    a = synth.setup_handle(f, product_lib)
+    # tiny capacity hint: the candidate list overflows, the step must grow the buffers and rerun
+    b = synth.setup_handle(f, product_lib, max_pairs_per_floe=1)
+    for h in (a, b):
+        h.step(0, True)
+        h.step(1, False)
+    x, y = a.download_floes(), b.download_floes()
+    assert_ok(compare_state(x, y, exact=("centroid_x", "centroid_y", "u", "v", "xi", "vert_xy", "collision_force",
+                                         "collision_trq", "fxOA", "fyOA", "trqOA", "strain", "stress_accum")))
+
+
+def test_empty_and_single(product_lib, oracle_lib):
+    f = synth.make_field(4, scale=0.5, walls="collision", npoints=20, cache=False)
+    hg, ho = handles(f, product_lib, oracle_lib)
+    hg.step(0, True)
+    ho.step(0, True)
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes()))
+    assert hg.counts()["n_overlap"] == 0 and hg.counts()["n_rows"] == 0
+    # an empty floe list is legal
+    e = capi.FloeArrays(0)
+    hg.upload_floes(e)
+    hg.step(0, True)
+    assert hg.counts()["n_total"] == 0
+
+
+def test_full_size_properties(product_lib):
+    """BASELINE config 3 scale (100k floes): size-independent properties instead of an oracle run —
+    sorted unique candidate list, i < j, mirrored rows antisymmetric, Newton's third law."""
+    f = synth.make_field(100000, scale=1.01, walls="collision", npoints=50)
+    h = synth.setup_handle(f, product_lib)
+    h.step_collisions()
+    c = h.counts()
+    p = h.pairs(0)
+    assert len(p) == c["n_candidates"] and np.all(p[:, 0] < p[:, 1])
+    key = p[:, 0] * (c["n_total"] + 1) + p[:, 1]
+    assert np.all(np.diff(key) > 0)  # lexicographically sorted, no duplicates
+    offs, rows = h.interactions()
+    fa = h.download_floes()
+    floe_of_row = np.repeat(np.arange(c["n_total"]), np.diff(offs))
+    ff = rows[:, 0] > 0  # floe-floe rows
+    # every floe-floe row has its mirror: sum of all floe-floe forces vanishes to rounding
+    tot = np.abs(rows[ff, 1]).sum()
+    assert abs(rows[ff, 1].sum()) <= 1e-9 * tot and abs(rows[ff, 2].sum()) <= 1e-9 * tot
+    # per-floe totals are the row sums
+    fx = np.bincount(floe_of_row, weights=rows[:, 1], minlength=c["n_total"])
+    assert rel_err(fa.collision_force[:, 0], fx) < 1e-9
+    assert c["n_overlap"] > 2 * c["n_init"] and c["n_clip_fail"] == 0
