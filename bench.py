@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — sim timesteps/s of the floe-interaction hot path (BASELINE.json metric).
+
+One "step" = one reference timestep restricted to the replaced calls (simulation.jl:94-170):
+add_ghosts! -> timestep_collisions! -> ghost removal -> timestep_coupling! -> timestep_floe_properties!
+on a synthetic Voronoi-packed floe field; coupling runs EVERY step here (the
+reference default is every 10th), so the number is a lower bound for default settings.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--floes 100000] [--npoints 1000] [--walls collision|periodic|shear]
+
+N = 1: BASELINE config 3 (100k floes, collisions + ocean/atmosphere coupling) on one B200.
+N > 1 (torchrun, one rank per GPU): weak scaling, every rank owns a slab of `--floes` floes.
+--impl reference: the CPU oracle (the reference is pure Julia and cannot run in this image, so the
+reference arm is the oracle "port") on the host cores of rank 0, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import szload  # noqa: E402,F401  (registers the package directory `subzero.jl_b200` as subzero_jl_b200)
+
+METRIC = "sim timesteps/sec (collisions + one-way ocean/atmosphere coupling + state update)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--floes", type=int, default=100000, help="floes per GPU")
+    ap.add_argument("--npoints", type=int, default=1000, help="Monte-Carlo draws per floe (about 59 % are kept)")
+    ap.add_argument("--walls", default="collision", choices=["collision", "periodic", "shear"])
+    ap.add_argument("--scale", type=float, default=1.01)
+    ap.add_argument("--cpu-sample", type=int, default=25000, help="floes of the cpu_baseline sample field")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pin_floe_arrays(fa):
+    """Move every array of a FloeArrays into pinned host memory (torch allocator)."""
+    import torch
+    keep = []
+    for name, v in list(fa.__dict__.items()):
+        if isinstance(v, np.ndarray) and v.size > 0:
+            v = np.ascontiguousarray(v)
+            t = torch.empty(v.shape, dtype=torch.from_numpy(np.empty(0, dtype=v.dtype)).dtype, pin_memory=True)
+            t.numpy()[...] = v
+            keep.append(t)
+            setattr(fa, name, t.numpy())
+    fa._pinned = keep
+    return fa
+
+
+def dyn_bytes(fa):
+    """Bytes of the dynamic state crossing PCIe in one direction (scalars + tensors + status + rings)."""
+    from subzero_jl_b200 import capi
+    b = 0
+    for name in capi.DOUBLE_FIELDS:
+        b += getattr(fa, name).nbytes
+    return b + fa.status_tag.nbytes + fa.vert_xy.nbytes
+
+
+def oracle_steps_per_s(args, n_sample, steps, warmup, threads=0):
+    """Time the CPU oracle on a field of n_sample floes with the same generator/statistics;
+    returns (steps/s on the sample, threads used, counts)."""
+    from subzero_jl_b200 import synth
+    from oracle import szo
+    lib = szo.oracle()
+    f = synth.make_field(n_sample, scale=args.scale, walls=args.walls, npoints=args.npoints)
+    h = synth.setup_handle(f, lib, threads=threads)
+    for t in range(warmup):
+        h.step(t, True)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        h.step(warmup + t, True)
+    dt = time.perf_counter() - t0
+    c = h.counts()
+    h.close()
+    return steps / dt, (threads or os.cpu_count()), c
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    # calibrate on a small field, then size the sample so that K + W steps take about two minutes
+    n0 = min(5000, args.floes)
+    sps0, cores, _ = oracle_steps_per_s(args, n0, 1, 1)
+    budget = 120.0
+    per_floe = 1.0 / (sps0 * n0)
+    n_sample = int(min(args.floes, max(n0, budget / ((args.steps + args.warmup) * per_floe))))
+    n_sample = max(1000, (n_sample // 1000) * 1000)
+    sps, cores, c = oracle_steps_per_s(args, n_sample, args.steps, args.warmup)
+    value = sps * n_sample / args.floes  # O(N) path: steps/s scale inversely with the floe count
+    sample = ("oracle port (OpenMP, %d threads) on a %d-floe field of the same generator; steps/s scaled by %d/%d "
+              "to the %d-floe workload" % (cores, n_sample, n_sample, args.floes, args.floes))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference (Subzero.jl) is pure Julia; no julia binary exists in this image, so the reference arm "
+                "is the CPU oracle restating its algorithm (O(N) grid broad phase instead of the reference's O(N^2) loop)",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "synthetic Voronoi-packed %d floes per GPU (BASELINE config 3), scale %.2f dense contacts, "
+                        "%s walls, collisions + one-way ocean/atmosphere coupling every step + state update"
+                        % (args.floes, args.scale, args.walls),
+            "floes_per_gpu": args.floes, "mc_draws_per_floe": args.npoints, "coupling_every": 1, "dt_s": 10,
+            "parallelism": "1 GPU" if world == 1 else "%d spatial slabs, one rank per GPU" % world,
+            "l2": "Monte-Carlo points (%.2f GB per GPU at 100k floes) exceed the 126 MB L2; no explicit flush" % 0.95}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    import szload  # noqa: F401
+    from subzero_jl_b200 import capi, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prod = capi.product()
+
+    f = synth.make_field(args.floes, scale=args.scale, walls=args.walls, npoints=args.npoints, seed=args.floes + rank)
+    h = synth.setup_handle(f, prod, device=local_rank)
+    fa0 = f.floes
+    N, M, V = fa0.n, int(fa0.mc_offsets[-1]), int(fa0.vert_offsets[-1])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    for t in range(args.warmup):
+        h.step(t, True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    phase = np.zeros(8)
+    launches = 0
+    t0 = time.perf_counter()
+    for t in range(args.steps):
+        h.step(args.warmup + t, True)
+        ms = h.timings_raw()
+        phase += ms
+        launches += int(ms[7])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+    c = h.counts()
+    dev_ms = phase[6] / args.steps  # CUDA events on the library's stream, first to last kernel of a step
+    t_rank = torch.tensor([wall, phase[6] / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
+    wall_max, dev_max = float(t_rank[0]), float(t_rank[1])
+    value = args.steps / wall_max
+
+    # ---- end to end through the C ABI with pinned host buffers ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_fa = pin_floe_arrays(h.download_floes(mc=False))
+        h2d = dyn_bytes(host_fa)
+        for t in range(2):
+            h.upload_state(host_fa)
+            h.step(t, True)
+            h.download_floes(into=host_fa, mc=False)
+        barrier()
+        t0 = time.perf_counter()
+        ne = max(3, min(args.steps, 10))
+        for t in range(ne):
+            h.upload_state(host_fa)          # H2D: every per-floe scalar + ring coordinates
+            h.step(t, True)
+            h.download_floes(into=host_fa, mc=False)   # D2H: the same state back
+            _ = float(host_fa.collision_force[0, 0])
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        d2h = h2d + host_fa.id.nbytes + host_fa.ghost_id.nbytes
+        e2e = {"value": ne / float(te[0]), "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "call": "sz_upload_state + sz_step + sz_download_floes on pinned host arrays"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    g = f.grid
+    per = phase / args.steps
+    P, C = c["n_pairs"], c["n_rows"]
+    nbar = V / max(N, 1)
+    kernels = {
+        "k_coupling": (per[4], 16.0 * M + 120.0 * N + 40.0 * (g.Nx + 1) * (g.Ny + 1)),
+        "k_narrow": (per[2], P * (16.0 * (2 * nbar) + 128.0) + 112.0 * C),
+        "k_update": (per[5], 440.0 * N + 32.0 * V + 56.0 * C),
+    }
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    kms, kbytes = kernels[dom]
+    achieved = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": kbytes, "kernel_ms": kms,
+                "phase_ms": {"ghosts": per[0], "broad": per[1], "narrow": per[2], "rows": per[3], "coupling": per[4],
+                             "update": per[5], "step_device": per[6]}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ns = min(args.cpu_sample, args.floes)
+        sps, cores, _ = oracle_steps_per_s(args, ns, 2, 1)
+        cpu = {"value": sps * ns / args.floes, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": "oracle port (OpenMP, %d threads), 2 timed steps on a %d-floe field of the same generator, "
+                         "steps/s scaled by %d/%d" % (cores, ns, ns, args.floes)}
+
+    line = {
+        "metric": METRIC, "value": value * 1.0, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "floes_total": N * world, "floe_steps_per_s": value * N * world,
+        "contacts_per_s": value * c["n_overlap"] * world, "candidate_pairs_per_s": value * c["n_candidates"] * world,
+        "mc_points_per_s": value * M * world,
+        "device_ms_per_step": 1e3 * dev_max / args.steps,
+        "counts": {k: c[k] for k in ("n_init", "n_candidates", "n_pairs", "n_overlap", "n_rows", "n_mc", "n_vertices")},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

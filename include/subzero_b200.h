@@ -161,6 +161,12 @@ int32_t SZ_FN(get_domain)(sz_handle *h, double vals[4], double rect[16]);
 
 /* ---- floe state ---------------------------------------------------------------------------- */
 int32_t SZ_FN(upload_floes)(sz_handle *h, const sz_floe_soa *floes);
+/* Refresh the DYNAMIC state of the resident floes from the host: every per-floe scalar and the
+ * ring coordinates of the same floe list (same n, n_init and ring sizes as the last
+ * sz_upload_floes, no ghosts present).  Monte-Carlo points, ids and ghost links stay resident.
+ * This is what the Julia shim calls after a host process changed floe state in place without
+ * changing the floe list (simulation.jl:121-214). */
+int32_t SZ_FN(upload_state)(sz_handle *h, const sz_floe_soa *floes);
 int32_t SZ_FN(get_counts)(sz_handle *h, sz_counts *out);
 int32_t SZ_FN(download_floes)(sz_handle *h, sz_floe_soa *floes);
 
@@ -191,7 +197,7 @@ int32_t SZ_FN(get_pairs)(sz_handle *h, int32_t which, int64_t *pairs);
 int32_t SZ_FN(get_warnings)(sz_handle *h, uint32_t *bits); /* [n_init] */
 /* Device (or oracle wall-clock) time of the phases of the last step, milliseconds:
  * [0] ghosts [1] broad phase [2] narrow phase [3] row assembly+reduction [4] coupling
- * [5] floe properties [6] total */
+ * [5] floe properties [6] total [7] kernels launched by the last sz_step */
 int32_t SZ_FN(get_timings)(sz_handle *h, double ms[8]);
 
 /* ---- geometry service (test hook; also what SURVEY §8(f) rank 2 reuses) ---------------------- */

@@ -317,6 +317,32 @@ int32_t szo_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     return SZ_OK;
 }
 
+int32_t szo_upload_state(sz_handle *h, const sz_floe_soa *s) {
+    if (!h || !s) return SZ_ERR_INVALID;
+    if (s->n != h->n || s->n_init != h->n_init || h->n != h->n_init) return fail(h, SZ_ERR_INVALID, "upload_state: floe list differs from the resident store");
+#define CP(dst, src) for (int64_t i = 0; i < s->n; ++i) h->dst[i] = s->src ? s->src[i] : 0.0;
+    CP(cx, centroid_x) CP(cy, centroid_y) CP(height, height) CP(area, area) CP(mass, mass)
+    CP(rmax, rmax) CP(moment, moment) CP(alpha, alpha) CP(u, u) CP(v, v) CP(xi, xi) CP(fxOA, fxOA)
+    CP(fyOA, fyOA) CP(trqOA, trqOA) CP(hflx, hflx_factor) CP(overarea, overarea)
+    CP(ctrq, collision_trq) CP(p_dxdt, p_dxdt) CP(p_dydt, p_dydt) CP(p_dudt, p_dudt)
+    CP(p_dvdt, p_dvdt) CP(p_dxidt, p_dxidt) CP(p_dalphadt, p_dalphadt)
+#undef CP
+    int64_t vo = 0;
+    for (int64_t i = 0; i < s->n; ++i) {
+        h->cfx[i] = s->collision_force ? s->collision_force[2 * i] : 0.0;
+        h->cfy[i] = s->collision_force ? s->collision_force[2 * i + 1] : 0.0;
+        for (int k = 0; k < 4; ++k) {
+            h->stress_accum[4 * i + k] = s->stress_accum ? s->stress_accum[4 * i + k] : 0.0;
+            h->stress_instant[4 * i + k] = s->stress_instant ? s->stress_instant[4 * i + k] : 0.0;
+            h->strain[4 * i + k] = s->strain ? s->strain[4 * i + k] : 0.0;
+        }
+        if (s->status_tag) h->status[i] = s->status_tag[i];
+        memcpy(h->ring[i], s->vert_xy + 2 * vo, sizeof(szo_pt) * (size_t)h->npts[i]);
+        vo += h->npts[i];
+    }
+    return SZ_OK;
+}
+
 int32_t szo_get_counts(sz_handle *h, sz_counts *c) {
     if (!h || !c) return SZ_ERR_INVALID;
     memset(c, 0, sizeof(*c));

@@ -91,6 +91,7 @@ class Library:
                                    C.c_int32, c_i64_p, c_double_p, c_double_p, c_double_p]),
         "get_domain": (C.c_int32, [C.c_void_p, c_double_p, c_double_p]),
         "upload_floes": (C.c_int32, [C.c_void_p, C.POINTER(FloeSoA)]),
+        "upload_state": (C.c_int32, [C.c_void_p, C.POINTER(FloeSoA)]),
         "get_counts": (C.c_int32, [C.c_void_p, C.POINTER(Counts)]),
         "download_floes": (C.c_int32, [C.c_void_p, C.POINTER(FloeSoA)]),
         "add_ghosts": (C.c_int32, [C.c_void_p, c_i64_p]),
@@ -268,19 +269,30 @@ class Handle:
         s = fa.as_struct()
         self._ck(self.lib.upload_floes(self.h, C.byref(s)))
 
+    def upload_state(self, fa):
+        s = fa.as_struct()
+        self._ck(self.lib.upload_state(self.h, C.byref(s)))
+
     def counts(self):
         c = Counts()
         self._ck(self.lib.get_counts(self.h, C.byref(c)))
         return c.asdict()
 
-    def download_floes(self):
-        c = self.counts()
-        fa = FloeArrays(c["n_total"], c["n_init"])
-        fa.vert_xy = np.zeros((c["n_vertices"], 2))
-        fa.mc_x = np.zeros(c["n_mc"])
-        fa.mc_y = np.zeros(c["n_mc"])
-        fa.ghost_index = np.zeros(c["n_ghost_links"], dtype=np.int64)
+    def download_floes(self, into=None, mc=True):
+        """Download the floe list.  `into`: a FloeArrays of matching sizes to reuse (e.g. backed
+        by pinned memory); mc=False skips the (static) Monte-Carlo points."""
+        if into is None:
+            c = self.counts()
+            fa = FloeArrays(c["n_total"], c["n_init"])
+            fa.vert_xy = np.zeros((c["n_vertices"], 2))
+            fa.mc_x = np.zeros(c["n_mc"] if mc else 0)
+            fa.mc_y = np.zeros(c["n_mc"] if mc else 0)
+            fa.ghost_index = np.zeros(c["n_ghost_links"], dtype=np.int64)
+        else:
+            fa = into
         s = fa.as_struct()
+        if not mc:
+            s.mc_x, s.mc_y = None, None
         self._ck(self.lib.download_floes(self.h, C.byref(s)))
         return fa
 
@@ -340,6 +352,11 @@ class Handle:
         out = np.zeros(max(n, 1), dtype=np.uint32)
         self._ck(self.lib.get_warnings(self.h, out.ctypes.data_as(c_u32_p)))
         return out[:n]
+
+    def timings_raw(self):
+        ms = np.zeros(8)
+        self._ck(self.lib.get_timings(self.h, _dp(ms)))
+        return ms
 
     def timings(self):
         ms = np.zeros(8)

@@ -355,6 +355,35 @@ static int32_t sync_counters(sz_handle *h) {
     return SZ_OK;
 }
 
+// every per-floe double array of the SoA (a NULL source zero-fills)
+static int32_t upload_scalars(sz_handle *h, const sz_floe_soa *s, int n) {
+    Store &S = h->S;
+    cudaStream_t st = h->L.stream;
+    if (n == 0) return SZ_OK;
+    auto up = [&](double *dst, const double *src, size_t w) -> cudaError_t {
+        if (src) return cudaMemcpyAsync(dst, src, sizeof(double) * w * n, cudaMemcpyHostToDevice, st);
+        return cudaMemsetAsync(dst, 0, sizeof(double) * w * n, st);
+    };
+    CK(up(S.cx, s->centroid_x, 1)); CK(up(S.cy, s->centroid_y, 1)); CK(up(S.height, s->height, 1));
+    CK(up(S.area, s->area, 1)); CK(up(S.mass, s->mass, 1)); CK(up(S.rmax, s->rmax, 1)); CK(up(S.moment, s->moment, 1));
+    CK(up(S.alpha, s->alpha, 1)); CK(up(S.u, s->u, 1)); CK(up(S.v, s->v, 1)); CK(up(S.xi, s->xi, 1));
+    CK(up(S.fxOA, s->fxOA, 1)); CK(up(S.fyOA, s->fyOA, 1)); CK(up(S.trqOA, s->trqOA, 1));
+    CK(up(S.hflx, s->hflx_factor, 1)); CK(up(S.overarea, s->overarea, 1)); CK(up(S.ctrq, s->collision_trq, 1));
+    CK(up(S.p_dxdt, s->p_dxdt, 1)); CK(up(S.p_dydt, s->p_dydt, 1)); CK(up(S.p_dudt, s->p_dudt, 1));
+    CK(up(S.p_dvdt, s->p_dvdt, 1)); CK(up(S.p_dxidt, s->p_dxidt, 1)); CK(up(S.p_dalphadt, s->p_dalphadt, 1));
+    CK(up(S.stress_accum, s->stress_accum, 4)); CK(up(S.stress_instant, s->stress_instant, 4)); CK(up(S.strain, s->strain, 4));
+    // collision_force is [n][2] on the host, two columns on the device
+    if (s->collision_force) {
+        CK(cudaMemcpy2DAsync(S.cfx, sizeof(double), s->collision_force, 2 * sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpy2DAsync(S.cfy, sizeof(double), s->collision_force + 1, 2 * sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice, st));
+    } else {
+        CK(cudaMemsetAsync(S.cfx, 0, sizeof(double) * n, st));
+        CK(cudaMemsetAsync(S.cfy, 0, sizeof(double) * n, st));
+    }
+    if (s->status_tag) CK(cudaMemcpyAsync(S.status, s->status_tag, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    return SZ_OK;
+}
+
 extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     if (!h || !s || s->n < 0 || s->n_init < 0 || s->n_init > s->n) return fail(h, SZ_ERR_INVALID, "upload_floes: bad sizes");
     if (s->n > 0 && (!s->centroid_x || !s->centroid_y || !s->area || !s->rmax || !s->vert_offsets || !s->vert_xy))
@@ -426,34 +455,15 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     if (!B.fuse_pairs) { int32_t rc = set_fuse_cap(h, std::max(1024, S.cap_floes)); if (rc) return rc; }
     // copies
     cudaStream_t st = h->L.stream;
-    std::vector<double> zeros;
-    auto up = [&](double *dst, const double *src, size_t w) -> cudaError_t {
-        if (n == 0) return cudaSuccess;
-        if (src) return cudaMemcpyAsync(dst, src, sizeof(double) * w * n, cudaMemcpyHostToDevice, st);
-        return cudaMemsetAsync(dst, 0, sizeof(double) * w * n, st);
-    };
-    CK(up(S.cx, s->centroid_x, 1)); CK(up(S.cy, s->centroid_y, 1)); CK(up(S.height, s->height, 1));
-    CK(up(S.area, s->area, 1)); CK(up(S.mass, s->mass, 1)); CK(up(S.rmax, s->rmax, 1)); CK(up(S.moment, s->moment, 1));
-    CK(up(S.alpha, s->alpha, 1)); CK(up(S.u, s->u, 1)); CK(up(S.v, s->v, 1)); CK(up(S.xi, s->xi, 1));
-    CK(up(S.fxOA, s->fxOA, 1)); CK(up(S.fyOA, s->fyOA, 1)); CK(up(S.trqOA, s->trqOA, 1));
-    CK(up(S.hflx, s->hflx_factor, 1)); CK(up(S.overarea, s->overarea, 1)); CK(up(S.ctrq, s->collision_trq, 1));
-    CK(up(S.p_dxdt, s->p_dxdt, 1)); CK(up(S.p_dydt, s->p_dydt, 1)); CK(up(S.p_dudt, s->p_dudt, 1));
-    CK(up(S.p_dvdt, s->p_dvdt, 1)); CK(up(S.p_dxidt, s->p_dxidt, 1)); CK(up(S.p_dalphadt, s->p_dalphadt, 1));
-    CK(up(S.stress_accum, s->stress_accum, 4)); CK(up(S.stress_instant, s->stress_instant, 4)); CK(up(S.strain, s->strain, 4));
-    std::vector<double> cf((size_t)2 * n, 0.0);
-    if (s->collision_force)
-        for (int i = 0; i < n; ++i) { cf[i] = s->collision_force[2 * i]; cf[(size_t)n + i] = s->collision_force[2 * i + 1]; }
+    { int32_t rc = upload_scalars(h, s, n); if (rc) return rc; }
     std::vector<int> status(n, SZ_STATUS_ACTIVE);
     std::vector<long long> id(n), gid(n, 0);
     for (int i = 0; i < n; ++i) {
-        if (s->status_tag) status[i] = s->status_tag[i];
         id[i] = s->id ? s->id[i] : i + 1;
         if (s->ghost_id) gid[i] = s->ghost_id[i];
     }
     if (n > 0) {
-        CK(cudaMemcpyAsync(S.cfx, cf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(S.cfy, cf.data() + n, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(S.status, status.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        if (!s->status_tag) CK(cudaMemcpyAsync(S.status, status.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(S.id, id.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(S.ghost_id, gid.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(S.parent, parent.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
@@ -487,6 +497,23 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     h->n_rows_host = 0;
     memset(&h->last, 0, sizeof(h->last));
     h->have_floes = true;
+    return SZ_OK;
+}
+
+// Refresh the dynamic state of the resident floes (same floe list and ring sizes as the last
+// sz_upload_floes); Monte-Carlo points, ids and ghost links stay resident.
+extern "C" int32_t sz_upload_state(sz_handle *h, const sz_floe_soa *s) {
+    if (!h || !s) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "upload_state before upload_floes");
+    if (s->n != h->n_total || s->n_init != h->n_init) return fail(h, SZ_ERR_INVALID, "upload_state: floe count differs from the resident store");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "upload_state with ghosts present");
+    if (!s->centroid_x || !s->centroid_y || !s->area || !s->rmax || !s->vert_xy) return fail(h, SZ_ERR_INVALID, "upload_state: geometry arrays are required");
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = upload_scalars(h, s, h->n_total);
+    if (rc) return rc;
+    if (s->vert_offsets && s->vert_offsets[h->n_total] != h->n_verts) return fail(h, SZ_ERR_INVALID, "upload_state: vertex count differs from the resident store");
+    if (h->n_verts > 0) CK(cudaMemcpyAsync(h->S.verts, s->vert_xy, sizeof(double2) * (size_t)h->n_verts, cudaMemcpyHostToDevice, h->L.stream));
+    CK(cudaStreamSynchronize(h->L.stream));
     return SZ_OK;
 }
 
@@ -752,6 +779,7 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
     cudaSetDevice(h->cfg.device);
     cudaStream_t st = h->L.stream;
+    szk_launch_count(true);
     for (int attempt = 0;; ++attempt) {
         cudaEventRecord(h->ev[0], st);
         enqueue_ghosts(h);
@@ -791,6 +819,7 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     h->ms[4] = ev_ms(h, 5, 6);
     h->ms[5] = ev_ms(h, 6, 7);
     h->ms[6] = ev_ms(h, 0, 7);
+    h->ms[7] = (double)szk_launch_count(true);  // kernels launched by this call
     return SZ_OK;
 }
 

@@ -169,3 +169,4 @@ void szk_clear_error(const Launch &L, const Store &S);
 int szk_debug_clip(const Launch &L, const double *p_xy, int np, const double *q_xy, int nq, int cap_regions,
                    int cap_points, int *out_offsets, double *out_xy, double *out_areas);
 size_t szk_large_smem(int maxv, int maxx);
+long long szk_launch_count(bool reset);

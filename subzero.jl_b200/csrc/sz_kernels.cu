@@ -16,6 +16,14 @@
 
 #define TPB 256
 
+// kernels launched since the last szk_launch_count(true) (bench.py reports it as gpu_launches)
+static long long g_launch_count = 0;
+long long szk_launch_count(bool reset) {
+    long long v = g_launch_count;
+    if (reset) g_launch_count = 0;
+    return v;
+}
+
 // ---- small helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long enc_f64(double x) {
     unsigned long long u = (unsigned long long)__double_as_longlong(x);
@@ -133,6 +141,7 @@ static void scan_excl(const Launch &L, const Store &S, const int *in, int *out, 
     k_scan_tiles<<<tiles, SCAN_T, 0, L.stream>>>(in, out, len_ptr, len_add, scratch, S.cnt);
     k_scan_sums<<<1, SCAN_T, 0, L.stream>>>(scratch, len_ptr, len_add, S.cnt);
     k_scan_add<<<tiles, SCAN_T, 0, L.stream>>>(out, len_ptr, len_add, scratch, total_out, S.cnt);
+    g_launch_count += 3;
 }
 
 static inline int grid_for(const Launch &L, long long work_items, int per_block) {
@@ -393,6 +402,7 @@ static void ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int ax
     k_ghost_check<<<1, 1, 0, L.stream>>>(S, B);
     k_ghost_write<<<grid_for(L, n_hint, 8), 256, 0, L.stream>>>(S, B, A);
     k_ghost_commit<<<1, 1, 0, L.stream>>>(S, B);
+    g_launch_count += 6;
 }
 
 void szk_ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_hint) {
@@ -411,6 +421,7 @@ __global__ void k_remove_ghosts(Store S, int n_verts_init) {
 }
 void szk_remove_ghosts(const Launch &L, const Store &S, int n_verts_init) {
     k_remove_ghosts<<<grid_for(L, S.n_init, TPB), TPB, 0, L.stream>>>(S, n_verts_init);
+    g_launch_count += 1;
 }
 
 // ---- K1: broad phase -----------------------------------------------------------------------------------
@@ -1129,6 +1140,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_row_write<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
     k_update_boundaries<<<1, 1, 0, st>>>(S, P);
     if (ev) cudaEventRecord(ev[2], st);
+    g_launch_count += 22;  // + 5 scans counted in scan_excl
 }
 
 // ---- K6: one-way ocean/atmosphere coupling (coupling.jl:1486-1589) ---------------------------------------------------
@@ -1237,7 +1249,10 @@ __global__ void __launch_bounds__(256) k_coupling(Store S, Params P) {
 }
 
 void szk_coupling(const Launch &L, const Store &S, const Params &P) {
-    if (S.n_init > 0) k_coupling<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, P);
+    if (S.n_init > 0) {
+        k_coupling<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, P);
+        g_launch_count += 1;
+    }
 }
 
 // ---- K7: state update (update_floe.jl:392-551) ---------------------------------------------------------------------------
@@ -1388,7 +1403,10 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
 }
 
 void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P) {
-    if (S.n_init > 0) k_update<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, B, P);
+    if (S.n_init > 0) {
+        k_update<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, B, P);
+        g_launch_count += 1;
+    }
 }
 
 // ---- geometry service / test hook -------------------------------------------------------------------------------------------
