@@ -57,9 +57,11 @@ struct Counters {
     int n_kept;    // pairs after the image filter
     int n_overlap;
     int n_large;   // work items deferred to the large-polygon kernel
+    int n_mid;     // work items the thread-per-item kernel handed to the warp-per-item kernel
     uint32_t error;
     int want_pairs, want_pool, want_rows, want_floes, want_verts, want_dom, want_fuse;  // sizes asked for on overflow
-    int gnx, gny, n_cells;
+    int gnx, gny;
+    int n_cells;
     int n_domchecks;  // (floe, element) checks incl. periodic walls (diagnostic)
     // broad-phase bounding box, order-preserving uint64 encodings (k_bbox)
     unsigned long long bb[5];  // min x, min y, max x, max y, max rmax
@@ -134,6 +136,7 @@ struct StepBuf {
     uint32_t *item_flags;
     double *pool;        // [cap_pool][NPOOL] = fx, fy, px, py, overlap
     int *large_items;    // [cap_pairs + cap_dom] work list of the large-polygon kernel
+    int *mid_items;      // [cap_pairs + cap_dom] work list of the warp-per-item kernel
     // per-floe rows
     int *row_pre, *row_count, *row_off;  // [cap_floes+1]
     double *rows;                        // [cap_rows][7]

@@ -13,6 +13,7 @@
 // (Counters) and returns at once when Counters::error is set, so an overflowing step leaves
 // the floe state untouched and the host can grow the buffer and run the step again.
 #include "sz_geom.cuh"
+#include "sz_narrow_thread.cuh"
 
 #define TPB 256
 
@@ -436,7 +437,7 @@ __global__ void k_step_reset(Store S) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         cnt->n_cand = cnt->n_dom = cnt->n_rows = cnt->n_fuse = cnt->n_pool = 0;
-        cnt->n_clipfail = cnt->n_kept = cnt->n_overlap = cnt->n_large = 0;
+        cnt->n_clipfail = cnt->n_kept = cnt->n_overlap = cnt->n_large = cnt->n_mid = 0;
         cnt->n_domchecks = 0;
         cnt->bb[0] = cnt->bb[1] = ~0ull;
         cnt->bb[2] = cnt->bb[3] = cnt->bb[4] = 0ull;
@@ -866,23 +867,9 @@ __global__ void k_narrow(Store S, StepBuf B, Params P, int maxv, int maxx, int l
     if (cnt->error) return;
     const int wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
     Ws w = ws_carve(smem + (size_t)wib * ws_bytes(maxv, maxx), maxv, maxx);
-    if (!large) {
-        int np = cnt->n_cand, total = np + cnt->n_dom;
-        for (int it = blockIdx.x * wpb + wib; it < total; it += gridDim.x * wpb) {
-            int slot = it < np ? it : B.cap_pairs + (it - np);
-            if (it < np && !B.keep[it]) {
-                if (lane_id() == 0) {
-                    B.item_nrows[slot] = 0;
-                    B.item_flags[slot] = 0;
-                }
-                continue;
-            }
-            narrow_item(w, S, B, P, slot, false);
-        }
-    } else {
-        int nl = cnt->n_large;
-        for (int it = blockIdx.x * wpb + wib; it < nl; it += gridDim.x * wpb) narrow_item(w, S, B, P, B.large_items[it], true);
-    }
+    const int nl = large ? cnt->n_large : cnt->n_mid;
+    const int *list = large ? B.large_items : B.mid_items;
+    for (int it = blockIdx.x * wpb + wib; it < nl; it += gridDim.x * wpb) narrow_item(w, S, B, P, list[it], large != 0);
 }
 
 __global__ void k_pool_check(Store S, StepBuf B) {
@@ -1126,8 +1113,10 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_kept_count<<<gp, TPB, 0, st>>>(S, B);
     if (ev) cudaEventRecord(ev[0], st);
     const int maxv_s = 32, maxx_s = 16, wpb = 4;
-    long long items = (long long)pairs_hint + n_hint / 8 + 64;
-    k_narrow<<<grid_for(L, items, wpb), wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
+    // thread-per-item fast path (small polygons), then warp-per-item for what it handed on, then the
+    // large-polygon workspace for what that one handed on
+    k_narrow_thread<<<L.sms, TN_NT, TN_SMEM_BYTES, st>>>(S, B, P);
+    k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
     k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
     k_pool_check<<<1, 1, 0, st>>>(S, B);
     if (ev) cudaEventRecord(ev[1], st);
@@ -1140,7 +1129,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_row_write<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
     k_update_boundaries<<<1, 1, 0, st>>>(S, P);
     if (ev) cudaEventRecord(ev[2], st);
-    g_launch_count += 22;  // + 5 scans counted in scan_excl
+    g_launch_count += 23;  // + 5 scans counted in scan_excl
 }
 
 // ---- K6: one-way ocean/atmosphere coupling (coupling.jl:1486-1589) ---------------------------------------------------
@@ -1481,5 +1470,6 @@ int szk_configure(const Launch &L) {
     if (cudaFuncSetAttribute(k_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_ghost_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_debug_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_narrow_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_BYTES) != cudaSuccess) return -1;
     return 0;
 }

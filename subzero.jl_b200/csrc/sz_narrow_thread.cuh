@@ -1,0 +1,633 @@
+// sz_narrow_thread.cuh — thread-per-item narrow phase for SMALL polygons (K3/K4 fast path).
+//
+// ncu on the warp-per-pair kernel (profiles/r1a_*) showed 3.4 k warp instructions per pair at
+// 13/32 active lanes and `no_inst` (instruction fetch) as the top stall: a 7-gon pair has ~36 edge
+// pairs, far too little to feed 32 lanes, while the sequential parts (trace, ranks, sorts) run on
+// one lane.  Voronoi-packed fields are almost entirely such pairs, so they get this kernel: one
+// THREAD owns one (polygon, polygon) item, a warp works on 32 items at once, and the rings live
+// in shared memory laid out [point][thread] (a warp reading "its point k" touches 32 consecutive
+// double2 = the 4-wavefront minimum, no bank conflicts).  The arithmetic is the same sequence of
+// unfused FP64 operations as the warp kernel and the definition the parity tests check, so the
+// results are bit-identical; anything that exceeds the fixed capacities below (more than 10 edges,
+// more than 4 crossings, more than 2 regions, a degenerate trace) is handed to the warp kernel.
+#pragma once
+#include "sz_geom.cuh"
+
+#define TN_NT 128    // threads per block
+#define TN_MAXV 11   // ring points incl. the closing point (<= 10 edges)
+#define TN_MAXX 4    // crossings per clip
+#define TN_MAXREG 2  // regions per clip
+#define TN_RCAP 26   // points of all regions of one clip
+#define TN_MAXIP 8   // raw intersection points
+
+enum { TN_OK = 0, TN_DEFER = 1 };
+
+// a ring in [point][thread] shared memory, optionally translated on the fly (P2 = P + dir is
+// never stored: reading P[k] + dir yields the same bits every time)
+struct TRing {
+    const double2 *b;
+    int n;
+    double sx, sy;
+    bool shifted;
+};
+__device__ __forceinline__ double2 tget(const TRing &r, int k) {
+    double2 v = r.b[k * TN_NT];
+    if (r.shifted) {
+        v.x = v.x + r.sx;
+        v.y = v.y + r.sy;
+    }
+    return v;
+}
+__device__ __forceinline__ TRing tring(const double2 *b, int n) {
+    TRing r;
+    r.b = b;
+    r.n = n;
+    r.sx = r.sy = 0.0;
+    r.shifted = false;
+    return r;
+}
+
+__device__ __noinline__ double t_area2(const TRing &r) {
+    double a = 0.0;
+    double2 p = tget(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 q = tget(r, k + 1);
+        a += p.x * q.y - p.y * q.x;
+        p = q;
+    }
+    return a;
+}
+__device__ __forceinline__ double t_area(const TRing &r) { return fabs(t_area2(r) / 2.0); }
+__device__ __noinline__ double2 t_centroid(const TRing &r) {
+    double a = 0.0, cx = 0.0, cy = 0.0;
+    double2 p = tget(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 q = tget(r, k + 1);
+        double c = p.x * q.y - p.y * q.x;
+        a += c;
+        cx += (p.x + q.x) * c;
+        cy += (p.y + q.y) * c;
+        p = q;
+    }
+    a /= 2.0;
+    return make_double2(cx / (6.0 * a), cy / (6.0 * a));
+}
+__device__ __noinline__ bool t_point_in_ring_q(double2 p, const TRing &r) {
+    bool in = false;
+    double2 c = tget(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 d = tget(r, k + 1);
+        if (c.y < p.y && p.y <= d.y) {
+            if (side_q(orient2d(c, d, p), c, d)) in = !in;
+        } else if (d.y < p.y && p.y <= c.y) {
+            if (!side_q(orient2d(c, d, p), c, d)) in = !in;
+        }
+        c = d;
+    }
+    return in;
+}
+__device__ __noinline__ bool t_point_in_ring_p(double2 q, const TRing &r) {
+    bool in = false;
+    double2 a = tget(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 b = tget(r, k + 1);
+        if (a.y <= q.y && q.y < b.y) {
+            if (side_p(orient2d(a, b, q), a, b)) in = !in;
+        } else if (b.y <= q.y && q.y < a.y) {
+            if (!side_p(orient2d(a, b, q), a, b)) in = !in;
+        }
+        a = b;
+    }
+    return in;
+}
+__device__ __noinline__ bool t_point_coveredby(double2 p, const TRing &r) {
+    bool onb = false, in = false;
+    double2 a = tget(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 b = tget(r, k + 1);
+        if (orient2d(a, b, p) == 0.0 && p.x >= fmin(a.x, b.x) && p.x <= fmax(a.x, b.x) && p.y >= fmin(a.y, b.y) &&
+            p.y <= fmax(a.y, b.y))
+            onb = true;
+        if ((a.y > p.y) != (b.y > p.y)) {
+            double xi = a.x + (p.y - a.y) / (b.y - a.y) * (b.x - a.x);
+            if (p.x < xi) in = !in;
+        }
+        a = b;
+    }
+    return onb || in;
+}
+__device__ __noinline__ double t_point_ring_distance(double2 p, const TRing &r) {
+    double best = INFINITY;
+    double2 a = tget(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 b = tget(r, k + 1);
+        best = fmin(best, point_segment_distance(p, a, b));
+        a = b;
+    }
+    return best;
+}
+__device__ __noinline__ bool t_rings_intersect(const TRing &A, const TRing &B) {
+    for (int e = 0; e + 1 < A.n; ++e) {
+        double2 a = tget(A, e), b = tget(A, e + 1);
+        for (int f = 0; f + 1 < B.n; ++f) {
+            double2 p0, p1;
+            if (segment_intersection(a, b, tget(B, f), tget(B, f + 1), p0, p1) > 0) return true;
+        }
+    }
+    if (t_point_coveredby(tget(A, 0), B)) return true;
+    if (t_point_coveredby(tget(B, 0), A)) return true;
+    return false;
+}
+
+// intersect_polys for one thread; regions go to R ([point][thread]) as closed rings
+// [rs[r], re[r]), ordered by first crossing along P.
+__device__ __noinline__ int t_clip(const TRing &P, const TRing &Q, double2 *R, int *rs, int *re, int &status) {
+    const int np = P.n - 1, nq = Q.n - 1;
+    status = TN_OK;
+    if (np < 3 || nq < 3) return 0;
+    const bool q_ccw = t_area2(Q) > 0.0;
+    const bool same = (t_area2(P) > 0.0) == q_ccw;
+    int xe[TN_MAXX], xf[TN_MAXX], rankP[TN_MAXX], rankQ[TN_MAXX], ordP[TN_MAXX], ordQ[TN_MAXX];
+    double xt[TN_MAXX], xs[TN_MAXX];
+    double2 xp[TN_MAXX];
+    bool xent[TN_MAXX], xvis[TN_MAXX];
+    int K = 0;
+    for (int e = 0; e < np; ++e) {
+        double2 a = tget(P, e), b = tget(P, e + 1);
+        double2 c = tget(Q, 0);
+        for (int f = 0; f < nq; ++f) {
+            double2 d = tget(Q, f + 1);
+            double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
+            bool sa = side_q(o1, c, d), sb = side_q(o2, c, d);
+            if (sa != sb) {
+                double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
+                bool sc = side_p(o3, a, b), sd = side_p(o4, a, b);
+                if (sc != sd) {
+                    if (K == TN_MAXX) {
+                        status = TN_DEFER;
+                        return 0;
+                    }
+                    double t = o1 / (o1 - o2);
+                    xe[K] = e;
+                    xf[K] = f;
+                    xt[K] = t;
+                    xs[K] = o3 / (o3 - o4);
+                    xp[K] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
+                    xent[K] = (sb == q_ccw);
+                    xvis[K] = false;
+                    K++;
+                }
+            }
+            c = d;
+        }
+    }
+    if (K == 0) {
+        bool pin = t_point_in_ring_q(tget(P, 0), Q);
+        bool qin = pin ? false : t_point_in_ring_p(tget(Q, 0), P);
+        if (!pin && !qin) return 0;
+        const TRing &src = pin ? P : Q;
+        for (int k = 0; k < src.n; ++k) R[k * TN_NT] = tget(src, k);
+        rs[0] = 0;
+        re[0] = src.n;
+        return 1;
+    }
+    int nentry = 0;
+    for (int k = 0; k < K; ++k) {
+        int rp = 0, rq = 0;
+        for (int m = 0; m < K; ++m) {
+            if (m == k) continue;
+            if (xe[m] < xe[k] || (xe[m] == xe[k] && (xt[m] < xt[k] || (xt[m] == xt[k] && m < k)))) rp++;
+            if (xf[m] < xf[k] || (xf[m] == xf[k] && (xs[m] < xs[k] || (xs[m] == xs[k] && m < k)))) rq++;
+        }
+        rankP[k] = rp;
+        rankQ[k] = rq;
+        ordP[rp] = k;
+        ordQ[rq] = k;
+        nentry += xent[k];
+    }
+    if ((K & 1) || 2 * nentry != K) {
+        status = TN_DEFER;  // the warp kernel records the degenerate trace
+        return 0;
+    }
+    int nreg = 0, npts = 0, minrank[TN_MAXREG];
+#define TN_PUSH(pt)                                                                                  \
+    do {                                                                                             \
+        double2 _p = (pt);                                                                           \
+        double2 _l = npts > start ? R[(npts - 1) * TN_NT] : make_double2(0.0, 0.0);                  \
+        if (!(npts > start && _l.x == _p.x && _l.y == _p.y)) {                                       \
+            if (npts >= TN_RCAP - 1) {                                                               \
+                status = TN_DEFER;                                                                   \
+                return 0;                                                                            \
+            }                                                                                        \
+            R[(npts++) * TN_NT] = _p;                                                                \
+        }                                                                                            \
+    } while (0)
+    for (int r = 0; r < K; ++r) {
+        int startk = ordP[r];
+        if (!xent[startk] || xvis[startk]) continue;
+        int start = npts, cur = startk, mr = K, guard = 0;
+        while (true) {
+            if (xvis[cur]) { status = TN_DEFER; return 0; }
+            xvis[cur] = true;
+            if (rankP[cur] < mr) mr = rankP[cur];
+            TN_PUSH(xp[cur]);
+            int rn = rankP[cur] + 1 == K ? 0 : rankP[cur] + 1, nx = ordP[rn];
+            int cnt = xe[nx] - xe[cur] + (rn == 0 ? np : 0);
+            for (int k = 0, v = xe[cur] + 1; k < cnt; ++k, ++v) {
+                if (v >= np) v -= np;
+                TN_PUSH(tget(P, v));
+            }
+            if (xent[nx] || xvis[nx]) { status = TN_DEFER; return 0; }
+            xvis[nx] = true;
+            if (rankP[nx] < mr) mr = rankP[nx];
+            TN_PUSH(xp[nx]);
+            int nn;
+            if (same) {
+                int rq = rankQ[nx] + 1 == K ? 0 : rankQ[nx] + 1;
+                nn = ordQ[rq];
+                cnt = xf[nn] - xf[nx] + (rq == 0 ? nq : 0);
+                for (int k = 0, v = xf[nx] + 1; k < cnt; ++k, ++v) {
+                    if (v >= nq) v -= nq;
+                    TN_PUSH(tget(Q, v));
+                }
+            } else {
+                int rq = rankQ[nx] == 0 ? K - 1 : rankQ[nx] - 1;
+                nn = ordQ[rq];
+                cnt = xf[nx] - xf[nn] + (rankQ[nx] == 0 ? nq : 0);
+                for (int k = 0, v = xf[nx]; k < cnt; ++k, --v) {
+                    if (v < 0) v += nq;
+                    TN_PUSH(tget(Q, v));
+                }
+            }
+            if (!xent[nn]) { status = TN_DEFER; return 0; }
+            if (nn == startk) break;
+            cur = nn;
+            if (++guard > K) { status = TN_DEFER; return 0; }
+        }
+        {
+            double2 f0 = R[start * TN_NT], l0 = R[(npts - 1) * TN_NT];
+            if (npts - start > 1 && l0.x == f0.x && l0.y == f0.y) npts--;
+        }
+        if (npts - start < 3) {
+            npts = start;
+            continue;
+        }
+        R[npts * TN_NT] = R[start * TN_NT];
+        npts++;
+        if (t_area2(tring(R + start * TN_NT, npts - start)) == 0.0) {
+            npts = start;
+            continue;
+        }
+        if (nreg >= TN_MAXREG) {
+            status = TN_DEFER;
+            return 0;
+        }
+        int pos = nreg;
+        while (pos > 0 && minrank[pos - 1] > mr) {
+            minrank[pos] = minrank[pos - 1];
+            rs[pos] = rs[pos - 1];
+            re[pos] = re[pos - 1];
+            --pos;
+        }
+        minrank[pos] = mr;
+        rs[pos] = start;
+        re[pos] = npts;
+        nreg++;
+    }
+#undef TN_PUSH
+    return nreg;
+}
+
+// GO.intersection_points, de-duplicated in discovery order; ip is [point][thread]
+__device__ __noinline__ int t_intersection_points(const TRing &P, const TRing &Q, double2 *ip, int &status) {
+    int n = 0;
+    for (int e = 0; e + 1 < P.n; ++e) {
+        double2 a = tget(P, e), b = tget(P, e + 1);
+        double2 c = tget(Q, 0);
+        for (int f = 0; f + 1 < Q.n; ++f) {
+            double2 d = tget(Q, f + 1);
+            double2 t0, t1;
+            int cnt = segment_intersection(a, b, c, d, t0, t1);
+            for (int k = 0; k < cnt; ++k) {
+                double2 t = k == 0 ? t0 : t1;
+                bool dup = false;
+                for (int m = 0; m < n && !dup; ++m) {
+                    double2 v = ip[m * TN_NT];
+                    dup = (v.x == t.x && v.y == t.y);
+                }
+                if (dup) continue;
+                if (n == TN_MAXIP) {
+                    status = TN_DEFER;
+                    return 0;
+                }
+                ip[(n++) * TN_NT] = t;
+            }
+            c = d;
+        }
+    }
+    return n;
+}
+
+// which_vertices_match_points, floe_utils.jl:331-352
+__device__ __noinline__ int t_match_vertices(const double2 *ip, int nip, const TRing &reg, int *idx) {
+    int m = 0, npoints = nip;
+    if (nip > 0) {
+        double2 f = ip[0], l = ip[(nip - 1) * TN_NT];
+        if (f.x == l.x && f.y == l.y) npoints -= 1;
+    }
+    for (int i = 0; i < npoints; ++i) {
+        double2 p = ip[i * TN_NT];
+        double min_dist = INFINITY;
+        int min_vert = 0;
+        for (int j = 0; j < reg.n; ++j) {
+            double2 v = tget(reg, j);
+            double dx = v.x - p.x, dy = v.y - p.y;
+            double dist = sqrt(sqrt(dx * dx + dy * dy));
+            if (dist < min_dist) {
+                min_dist = dist;
+                min_vert = j;
+            }
+        }
+        if (min_dist < 1.0) idx[m++] = min_vert;
+    }
+    for (int a = 1; a < m; ++a) {
+        int v = idx[a], b = a - 1;
+        while (b >= 0 && idx[b] > v) {
+            idx[b + 1] = idx[b];
+            --b;
+        }
+        idx[b + 1] = v;
+    }
+    return m;
+}
+
+// _many_intersect_normal_force!, collisions.jl:78-119
+__device__ __noinline__ double t_many_intersect_normal(double dir[2], const TRing &reg, const TRing &P, double ff) {
+    double x1 = 0, y1 = 0, dl = 0, Fx = 0, Fy = 0;
+    int n_pts = 0;
+    for (int i = 0; i < reg.n; ++i) {
+        double2 v = tget(reg, i);
+        double x2 = v.x, y2 = v.y;
+        if (i == 0) {
+            x1 = x2;
+            y1 = y2;
+            continue;
+        }
+        double xmid = 0.5 * (x2 + x1), ymid = 0.5 * (y2 + y1);
+        double dist = t_point_ring_distance(make_double2(xmid, ymid), P);
+        if (dist < 1e-8) {
+            double dx = x2 - x1, dy = y2 - y1;
+            double mag = sqrt(dx * dx + dy * dy);
+            double xt = xmid + (-dy / (100 * mag));
+            double yt = ymid + (dx / (100 * mag));
+            bool in_region = t_point_coveredby(make_double2(xt, yt), reg);
+            double fs = (in_region ? 1.0 : -1.0) * ff;
+            Fx = Fx + fs * (-dy);
+            Fy = Fy + fs * dx;
+            dl += mag;
+            n_pts += 1;
+        }
+        x1 = x2;
+        y1 = y2;
+    }
+    if (0 < n_pts && n_pts < reg.n - 1) {
+        dl /= n_pts;
+        if (dl > 0.1) {
+            double nf = sqrt(Fx * Fx + Fy * Fy);
+            dir[0] = Fx / nf;
+            dir[1] = Fy / nf;
+        }
+    }
+    return dl;
+}
+
+struct TWs {
+    double2 *P, *Q, *R1, *R2, *ip;  // [cap][TN_NT], already offset by the thread index
+};
+
+// calc_normal_force, collisions.jl:30-70
+__device__ __noinline__ double t_normal_force(const TWs &w, const TRing &P, const TRing &Q, const TRing &reg,
+                                              double area, int nip, double ff, double force[2], int &status) {
+    double dir[2] = {0.0, 0.0}, dl = 0.0;
+    int idx[TN_MAXIP];
+    int m = t_match_vertices(w.ip, nip, reg, idx);
+    if (m == 2) {
+        double2 v0 = tget(reg, idx[0]), v1 = tget(reg, idx[1]);
+        double dx = v1.x - v0.x, dy = v1.y - v0.y;
+        dl = sqrt(dx * dx + dy * dy);
+        if (dl > 0.1) {
+            dir[0] = -dy / dl;
+            dir[1] = dx / dl;
+        }
+    } else if (m != 0) {
+        dl = t_many_intersect_normal(dir, reg, P, ff);
+    }
+    if (dl > 0.1) {
+        TRing P2 = P;
+        P2.shifted = true;
+        P2.sx = dir[0];
+        P2.sy = dir[1];
+        int rs2[TN_MAXREG], re2[TN_MAXREG];
+        int nreg2 = t_clip(P2, Q, w.R2, rs2, re2, status);
+        if (status != TN_OK) return 0.0;
+        for (int r = 0; r < nreg2; ++r) {
+            TRing nr = tring(w.R2 + rs2[r] * TN_NT, re2[r] - rs2[r]);
+            if (t_rings_intersect(nr, reg) && t_area(nr) / area > 1) {
+                dir[0] *= -1;
+                dir[1] *= -1;
+            }
+        }
+    }
+    force[0] = dir[0] * area * ff;
+    force[1] = dir[1] * area * ff;
+    return dl;
+}
+
+// One work item, one thread.  Returns false when the item must go to the warp kernel.
+__device__ bool thread_item(const TWs &w, const Store &S, const StepBuf &B, const Params &P, int slot) {
+    Counters *cnt = S.cnt;
+    const DomainDev *D = S.dom;
+    const bool is_pair = slot < B.cap_pairs;
+    int fi, fj = -1, elem = -1;
+    if (is_pair) {
+        fi = B.pair_i[slot];
+        fj = B.pair_j[slot];
+    } else {
+        int q = slot - B.cap_pairs;
+        fi = B.dom_floe[q];
+        elem = B.dom_elem[q];
+    }
+    const int npp = S.vcount[fi];
+    int nqp, kind = SZ_BOUNDARY_COLLISION;
+    const double2 *gQ = nullptr;
+    if (is_pair) {
+        nqp = S.vcount[fj];
+        gQ = S.verts + S.vstart[fj];
+    } else if (elem < 4) {
+        nqp = 5;
+        kind = D->kind[elem];
+    } else {
+        nqp = S.topo_vcount[elem - 4];
+        gQ = S.topo_verts + S.topo_vstart[elem - 4];
+    }
+    if (npp > TN_MAXV || nqp > TN_MAXV) return false;
+    {
+        const double2 *gP = S.verts + S.vstart[fi];
+        for (int k = 0; k < npp; ++k) w.P[k * TN_NT] = gP[k];
+        if (gQ) {
+            for (int k = 0; k < nqp; ++k) w.Q[k * TN_NT] = gQ[k];
+        } else {  // _make_bounding_box_polygon, floe_utils.jl:104-108
+            double xmin = D->rect[elem][0], xmax = D->rect[elem][1], ymin = D->rect[elem][2], ymax = D->rect[elem][3];
+            w.Q[0 * TN_NT] = make_double2(xmin, ymin);
+            w.Q[1 * TN_NT] = make_double2(xmin, ymax);
+            w.Q[2 * TN_NT] = make_double2(xmax, ymax);
+            w.Q[3 * TN_NT] = make_double2(xmax, ymin);
+            w.Q[4 * TN_NT] = make_double2(xmin, ymin);
+        }
+    }
+    const TRing Pr = tring(w.P, npp), Qr = tring(w.Q, nqp);
+    int status = TN_OK;
+    uint32_t flags = 0;
+    int rs1[TN_MAXREG], re1[TN_MAXREG];
+    double area1[TN_MAXREG];
+    int nreg = t_clip(Pr, Qr, w.R1, rs1, re1, status);
+    if (status != TN_OK) return false;
+    double total = 0.0, max_area = 0.0;
+    for (int r = 0; r < nreg; ++r) {
+        area1[r] = t_area(tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]));
+        total += area1[r];
+        if (area1[r] > max_area) max_area = area1[r];
+    }
+    const double ai = S.area[fi], hi = S.height[fi];
+    bool forces = false;
+    double ff = 0.0, ju = 0.0, jv = 0.0, jxi = 0.0, jcx = 0.0, jcy = 0.0;
+    if (is_pair) {
+        if (total > 0) {  // collisions.jl:364-405
+            flags |= IT_OVERLAP;
+            const double aj = S.area[fj];
+            if (fmax(total / ai, total / aj) > P.cfg.floe_floe_max_overlap) {
+                flags |= IT_FUSE;
+            } else {
+                const double hj = S.height[fj];
+                double ir = sqrt(ai), jr = sqrt(aj);
+                ff = (ir > 1e5 || jr > 1e5) ? P.cfg.E * fmin(hi, hj) / fmin(ir, jr) : P.cfg.E * (hi * hj) / (hi * jr + hj * ir);
+                forces = true;
+                ju = S.u[fj];
+                jv = S.v[fj];
+                jxi = S.xi[fj];
+                jcx = S.cx[fj];
+                jcy = S.cy[fj];
+            }
+        }
+    } else if (kind == SZ_BOUNDARY_OPEN) {  // collisions.jl:427-441
+        if (total > 0) flags |= IT_OVERLAP | IT_REMOVE;
+    } else if (max_area > 0) {  // collisions.jl:522-555
+        flags |= IT_OVERLAP;
+        if (max_area / ai > P.cfg.floe_domain_max_overlap) {
+            flags |= IT_REMOVE;
+        } else {
+            ff = P.cfg.E * hi / sqrt(ai);
+            forces = true;
+            if (elem < 4 && kind == SZ_BOUNDARY_MOVING) {
+                ju = D->wu[elem];
+                jv = D->wv[elem];
+            }
+        }
+    }
+    double rows[TN_MAXREG][NPOOL];
+    int nrows = 0;
+    if (forces) {
+        // calc_elastic_forces, collisions.jl:149-188
+        int nip = t_intersection_points(Pr, Qr, w.ip, status);
+        if (status != TN_OK) return false;
+        if (nip >= 2) {
+            int n1 = npp - 1, n2 = nqp - 1;
+            double min_area = (double)((n1 < n2 ? n1 : n2) * 100) / 1.75;
+            const double iu = S.u[fi], iv = S.v[fi], ixi = S.xi[fi], icx = S.cx[fi], icy = S.cy[fi];
+            for (int r = 0; r < nreg; ++r) {
+                if (area1[r] < min_area) continue;
+                double c[6] = {0.0, 0.0, 0.0, 0.0, area1[r], 0.0};
+                if (area1[r] != 0) {
+                    TRing reg = tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]);
+                    double2 ce = t_centroid(reg);
+                    c[2] = ce.x;
+                    c[3] = ce.y;
+                    double force[2];
+                    c[5] = t_normal_force(w, Pr, Qr, reg, area1[r], nip, ff, force, status);
+                    if (status != TN_OK) return false;
+                    c[0] = force[0];
+                    c[1] = force[1];
+                }
+                if (!is_pair && elem < 4) {  // _normal_direction_correct!, boundaries.jl:37-40,73-76,110-113,147-150
+                    if (elem == 0 && c[3] >= D->val[0]) c[0] = 0.0;
+                    if (elem == 1 && c[3] <= D->val[1]) c[0] = 0.0;
+                    if (elem == 2 && c[2] >= D->val[2]) c[1] = 0.0;
+                    if (elem == 3 && c[2] <= D->val[3]) c[1] = 0.0;
+                }
+                double fr[2];
+                friction_force(P.cfg.E, P.cfg.nu, P.cfg.mu, (double)P.cfg.dt, iu, iv, ixi, icx, icy, ju, jv, jxi, jcx, jcy, c,
+                               fr);
+                double fx = c[0] + fr[0], fy = c[1] + fr[1];
+                if (fx != 0 || fy != 0) {  // add_interactions!, collisions.jl:288
+                    rows[nrows][0] = fx;
+                    rows[nrows][1] = fy;
+                    rows[nrows][2] = c[2];
+                    rows[nrows][3] = c[3];
+                    rows[nrows][4] = c[4];
+                    nrows++;
+                }
+            }
+        }
+    }
+    int row0 = 0;
+    if (nrows > 0) {
+        row0 = atomicAdd(&cnt->n_pool, nrows);
+        if (row0 + nrows > B.cap_pool) {
+            atomicOr(&cnt->error, ERR_POOL_CAP);
+            nrows = 0;
+        } else {
+            for (int k = 0; k < nrows; ++k)
+                for (int q = 0; q < NPOOL; ++q) B.pool[(size_t)(row0 + k) * NPOOL + q] = rows[k][q];
+        }
+    }
+    B.item_nrows[slot] = nrows;
+    B.item_row0[slot] = row0;
+    B.item_flags[slot] = flags | IT_DONE;
+    if (is_pair && (flags & IT_OVERLAP)) atomicAdd(&cnt->n_overlap, 1);
+    if (flags & IT_FUSE) {
+        int s = atomicAdd(&cnt->n_fuse, 1);
+        if (s < B.cap_fuse) B.fuse_pairs[s] = make_int2(fi, fj);
+        else atomicOr(&cnt->error, ERR_FUSE_CAP);
+    }
+    return true;
+}
+
+#define TN_SMEM_BYTES (sizeof(double2) * TN_NT * (2 * TN_MAXV + 2 * TN_RCAP + TN_MAXIP))
+
+__global__ void __launch_bounds__(TN_NT, 1) k_narrow_thread(Store S, StepBuf B, Params P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    double2 *base = (double2 *)smem + threadIdx.x;
+    TWs w;
+    w.P = base;
+    w.Q = w.P + TN_MAXV * TN_NT;
+    w.R1 = w.Q + TN_MAXV * TN_NT;
+    w.R2 = w.R1 + TN_RCAP * TN_NT;
+    w.ip = w.R2 + TN_RCAP * TN_NT;
+    const int np = cnt->n_cand, total = np + cnt->n_dom;
+    for (int it = blockIdx.x * TN_NT + threadIdx.x; it < total; it += gridDim.x * TN_NT) {
+        int slot = it < np ? it : B.cap_pairs + (it - np);
+        if (it < np && !B.keep[it]) {
+            B.item_nrows[slot] = 0;
+            B.item_flags[slot] = 0;
+            continue;
+        }
+        if (!thread_item(w, S, B, P, slot)) {
+            int s = atomicAdd(&cnt->n_mid, 1);
+            B.mid_items[s] = slot;
+            B.item_nrows[slot] = 0;
+            B.item_flags[slot] = IT_NEEDLARGE;
+        }
+    }
+}
