@@ -135,7 +135,8 @@ static int32_t grow_floes(sz_handle *h, int new_cap, int keep) {
     h->S.cap_floes = new_cap;
     // grid cells and scan scratch follow the floe capacity
     int cells = 4 * new_cap + 64;
-    dfree(h->B.cell_count); dfree(h->B.cell_start); dfree(h->B.cell_fill); dfree(h->B.scan_block);
+    dfree(h->B.cell_count); dfree(h->B.cell_start); dfree(h->B.cell_fill); dfree(h->B.scan_block); dfree(h->B.cell_circ);
+    CK(dalloc(&h->B.cell_circ, 2 * (size_t)new_cap + 2));
     CK(dalloc(&h->B.cell_count, (size_t)cells + 2));
     CK(dalloc(&h->B.cell_start, (size_t)cells + 2));
     CK(dalloc(&h->B.cell_fill, (size_t)cells + 2));
@@ -242,8 +243,8 @@ extern "C" void sz_destroy(sz_handle *h) {
     StepBuf &B = h->B;
     dfree(S.verts); dfree(S.mc_off); dfree(S.mc); dfree(S.topo_vstart); dfree(S.topo_vcount); dfree(S.topo_verts);
     dfree(S.topo_cx); dfree(S.topo_cy); dfree(S.topo_rmax); dfree(S.ocn_u); dfree(S.ocn_v); dfree(S.ocn_hflx);
-    dfree(S.atm_u); dfree(S.atm_v); dfree(S.cnt); dfree(S.dom);
-    dfree(B.cell_count); dfree(B.cell_start); dfree(B.cell_fill); dfree(B.scan_block); dfree(B.pair_i); dfree(B.pair_j);
+    dfree(S.atm_u); dfree(S.atm_v); dfree(S.fields8); dfree(S.cnt); dfree(S.dom);
+    dfree(B.cell_count); dfree(B.cell_start); dfree(B.cell_fill); dfree(B.scan_block); dfree(B.cell_circ); dfree(B.pair_i); dfree(B.pair_j);
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -273,6 +274,8 @@ extern "C" int32_t sz_set_fields(sz_handle *h, const double *ou, const double *o
         dfree(S.ocn_u); dfree(S.ocn_v); dfree(S.ocn_hflx); dfree(S.atm_u); dfree(S.atm_v);
         CK(dalloc(&S.ocn_u, n)); CK(dalloc(&S.ocn_v, n)); CK(dalloc(&S.ocn_hflx, n));
         CK(dalloc(&S.atm_u, n)); CK(dalloc(&S.atm_v, n));
+        dfree(S.fields8);
+        CK(dalloc(&S.fields8, 8 * n));
         h->field_n = n;
     }
     const double *src[5] = {ou, ov, oh, au, av};
@@ -281,7 +284,9 @@ extern "C" int32_t sz_set_fields(sz_handle *h, const double *ou, const double *o
         if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], sizeof(double) * n, cudaMemcpyHostToDevice, h->L.stream));
         else CK(cudaMemsetAsync(dst[k], 0, sizeof(double) * n, h->L.stream));
     }
+    szk_pack_fields(h->L, S, (int)n);
     CK(cudaStreamSynchronize(h->L.stream));
+    CK(cudaGetLastError());
     h->have_fields = true;
     return SZ_OK;
 }
@@ -306,6 +311,8 @@ extern "C" int32_t sz_set_domain(sz_handle *h, const int32_t kinds[4], const dou
         for (int k = 0; k < 4; ++k) D.rect[w][k] = rect[4 * w + k];
     }
     D.n_topo = n_topo;
+    h->P.per_x = kinds[2] == SZ_BOUNDARY_PERIODIC;
+    h->P.per_y = kinds[0] == SZ_BOUNDARY_PERIODIC;
     Store &S = h->S;
     dfree(S.topo_vstart); dfree(S.topo_vcount); dfree(S.topo_verts); dfree(S.topo_cx); dfree(S.topo_cy); dfree(S.topo_rmax);
     if (n_topo > 0) {

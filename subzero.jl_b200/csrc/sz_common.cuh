@@ -80,6 +80,7 @@ struct Params {
     sz_config cfg;
     int Nx, Ny;
     double x0, xf, y0, yf, dx, dy;
+    int per_x, per_y;  // periodic east/west, north/south (domain kinds)
 };
 
 // Everything a kernel needs, passed by value.
@@ -108,6 +109,7 @@ struct Store {
     double *topo_cx, *topo_cy, *topo_rmax;
     // fields (Nx+1)x(Ny+1), [ix + (Nx+1) iy]
     double *ocn_u, *ocn_v, *ocn_hflx, *atm_u, *atm_v;
+    double *fields8;  // the five fields interleaved per node (8 doubles, see sz_kernels_fp.cu)
     Counters *cnt;
     DomainDev *dom;
 };
@@ -121,6 +123,7 @@ struct StepBuf {
     int *cell_start;  // [cap_cells+1]
     int *cell_fill;   // [cap_cells]
     int *cell_items;  // [cap_floes]
+    double2 *cell_circ;  // [cap_floes][2] cell-sorted (cx, cy), (rmax, index)
     // neighbour lists
     int *up_count, *up_off;    // [cap_floes+1] pairs (i, j>i)
     int *low_count, *low_off;  // [cap_floes+1] pairs (i<j, j) seen from j
@@ -163,6 +166,7 @@ void szk_remove_ghosts(const Launch &L, const Store &S, int n_verts_init);
 void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_floes_hint,
                     int n_pairs_hint, cudaEvent_t *ev);
 int szk_configure(const Launch &L);
+void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);
 void szk_coupling(const Launch &L, const Store &S, const Params &P);
 void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P);
 void szk_interleave(const Launch &L, const double *x, const double *y, double2 *out, long long n);
@@ -173,3 +177,4 @@ int szk_debug_clip(const Launch &L, const double *p_xy, int np, const double *q_
                    int cap_points, int *out_offsets, double *out_xy, double *out_areas);
 size_t szk_large_smem(int maxv, int maxx);
 long long szk_launch_count(bool reset);
+void szk_count_launches(int n);

@@ -24,6 +24,7 @@ long long szk_launch_count(bool reset) {
     if (reset) g_launch_count = 0;
     return v;
 }
+void szk_count_launches(int n) { g_launch_count += n; }
 
 // ---- small helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long enc_f64(double x) {
@@ -528,14 +529,19 @@ __global__ void k_cell_count(Store S, StepBuf B) {
     }
 }
 
+// counting-sort scatter; next to the floe index each slot gets a packed copy (cx, cy, rmax, index)
+// so the neighbour search below reads contiguous 32-byte records cell by cell instead of gathering
+// three scalars per candidate
 __global__ void k_cell_fill(Store S, StepBuf B) {
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     int n = cnt->n_total;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int c = B.cell_of[i];
-        int pos = atomicAdd(&B.cell_fill[c], 1);
-        B.cell_items[B.cell_start[c] + pos] = i;  // order inside a cell is irrelevant: lists are sorted below
+        int slot = B.cell_start[c] + atomicAdd(&B.cell_fill[c], 1);
+        B.cell_items[slot] = i;  // order inside a cell is irrelevant: lists are sorted below
+        B.cell_circ[2 * slot] = make_double2(S.cx[i], S.cy[i]);
+        B.cell_circ[2 * slot + 1] = make_double2(S.rmax[i], __longlong_as_double((long long)i));
     }
 }
 
@@ -550,37 +556,41 @@ __device__ __forceinline__ int wall_mask(const DomainDev *D, double cx, double c
     return m;
 }
 
+// one thread per SORTED slot: neighbouring threads are spatial neighbours and walk the same three
+// contiguous runs of records (a row of three cells is contiguous in the cell-sorted order)
 template <bool WRITE>
 __global__ void k_neighbours(Store S, StepBuf B) {
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const DomainDev *D = S.dom;
     int n = cnt->n_total, gnx = cnt->gnx, gny = cnt->gny;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const double2 me0 = B.cell_circ[2 * t], me1 = B.cell_circ[2 * t + 1];
+        const int i = (int)__double_as_longlong(me1.y);
         int c = B.cell_of[i], ix = c % gnx, iy = c / gnx;
-        double xi = S.cx[i], yi = S.cy[i], ri = S.rmax[i];
+        double xi = me0.x, yi = me0.y, ri = me1.x;
         int up = 0, low = 0;
         int ub = 0, lb = 0;
         if (WRITE) {
             ub = B.up_off[i];
             lb = B.low_off[i];
         }
-        for (int yy = max(iy - 1, 0); yy <= min(iy + 1, gny - 1); ++yy)
-            for (int xx = max(ix - 1, 0); xx <= min(ix + 1, gnx - 1); ++xx) {
-                int cc = yy * gnx + xx;
-                for (int k = B.cell_start[cc], ke = B.cell_start[cc + 1]; k < ke; ++k) {
-                    int j = B.cell_items[k];
-                    if (j == i) continue;
-                    if (!potential_interaction(xi, yi, ri, S.cx[j], S.cy[j], S.rmax[j])) continue;
-                    if (j > i) {
-                        if (WRITE) B.pair_j[ub + up] = j;
-                        up++;
-                    } else {
-                        if (WRITE) B.low_pair[lb + low] = j;
-                        low++;
-                    }
+        const int x_lo = max(ix - 1, 0), x_hi = min(ix + 1, gnx - 1);
+        for (int yy = max(iy - 1, 0); yy <= min(iy + 1, gny - 1); ++yy) {
+            for (int k = B.cell_start[yy * gnx + x_lo], ke = B.cell_start[yy * gnx + x_hi + 1]; k < ke; ++k) {
+                if (k == t) continue;
+                const double2 o0 = B.cell_circ[2 * k], o1 = B.cell_circ[2 * k + 1];
+                if (!potential_interaction(xi, yi, ri, o0.x, o0.y, o1.x)) continue;
+                const int j = (int)__double_as_longlong(o1.y);
+                if (j > i) {
+                    if (WRITE) B.pair_j[ub + up] = j;
+                    up++;
+                } else {
+                    if (WRITE) B.low_pair[lb + low] = j;
+                    low++;
                 }
             }
+        }
         int wm = wall_mask(D, xi, yi, ri);
         int dc = 0, checks = __popc(wm);
         int db = WRITE ? B.dom_off[i] : 0;
@@ -1130,272 +1140,6 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_update_boundaries<<<1, 1, 0, st>>>(S, P);
     if (ev) cudaEventRecord(ev[2], st);
     g_launch_count += 23;  // + 5 scans counted in scan_excl
-}
-
-// ---- K6: one-way ocean/atmosphere coupling (coupling.jl:1486-1589) ---------------------------------------------------
-// One warp per floe.  Lanes read the floe's body-frame Monte-Carlo points as consecutive double2
-// (512 B per warp load), rotate/translate them (calc_subfloe_values!, :627-657), drop points
-// outside a non-periodic grid extent (in_bounds, :494-597), gather the five fields bilinearly
-// (mc_interpolation :845-902 == bilinear on the lattice; periodic axes wrap on lines 1..N) and
-// reduce stress and torque with shuffles in a fixed order.  With r = (xc, yc), theta = atan(yc, xc):
-// rad sin(theta) = yc and rad cos(theta) = xc, so the reference's u - xi rad sin(theta) (:1534-1537)
-// and (-tx sin + ty cos) rad (:1562) are evaluated without transcendental calls (agreement ~1e-16).
-__device__ __forceinline__ double bilin(const double *__restrict__ F, size_t s, int i0, int i1, int j0, int j1,
-                                        double wx, double wy) {
-    double f00 = __ldg(F + i0 + s * j0), f10 = __ldg(F + i1 + s * j0), f01 = __ldg(F + i0 + s * j1),
-           f11 = __ldg(F + i1 + s * j1);
-    return (1 - wy) * ((1 - wx) * f00 + wx * f10) + wy * ((1 - wx) * f01 + wx * f11);
-}
-
-__global__ void __launch_bounds__(256) k_coupling(Store S, Params P) {
-    Counters *cnt = S.cnt;
-    if (cnt->error) return;
-    const DomainDev *D = S.dom;
-    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
-    const bool per_x = D->kind[2] == SZ_BOUNDARY_PERIODIC, per_y = D->kind[0] == SZ_BOUNDARY_PERIODIC;
-    const int Nx = P.Nx, Ny = P.Ny;
-    const size_t s = (size_t)(Nx + 1);
-    const double ct = cos(P.cfg.turn_theta), sn = sin(P.cfg.turn_theta);
-    const double ka = P.cfg.rho_a * P.cfg.Cd_ia, ko = P.cfg.rho_o * P.cfg.Cd_io;
-    const int n = S.n_init;
-    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
-        const double a = S.alpha[i], cx = S.cx[i], cy = S.cy[i], u = S.u[i], v = S.v[i], xi = S.xi[i];
-        const double ca = cos(a), sa = sin(a);
-        const double ma_ratio = S.mass[i] / S.area[i];
-        const double mf = ma_ratio * P.cfg.f;
-        double tx_s = 0, ty_s = 0, trq_s = 0, hf_s = 0;
-        int npts = 0;
-        const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
-        for (long long k = m0 + lane; k < m1; k += 32) {
-            double2 b = S.mc[k];
-            double px = ca * b.x - sa * b.y, py = sa * b.x + ca * b.y;
-            double x = px + cx, y = py + cy;
-            bool inb = (per_x || (P.x0 <= x && x <= P.xf)) && (per_y || (P.y0 <= y && y <= P.yf));
-            if (!inb) continue;
-            npts++;
-            double xc = x - cx, yc = y - cy;
-            double up = u - xi * yc, vp = v + xi * xc;
-            double gx = (x - P.x0) / P.dx, gy = (y - P.y0) / P.dy;
-            double fx = floor(gx), fy = floor(gy);
-            long long ci = (long long)fx, cj = (long long)fy;
-            double wx = gx - fx, wy = gy - fy;
-            int i0, i1, j0, j1;
-            if (per_x) {
-                i0 = (int)(((ci % Nx) + Nx) % Nx);
-                i1 = (i0 + 1) % Nx;
-            } else {
-                if (ci >= Nx) { ci = Nx - 1; wx = 1.0; }
-                if (ci < 0) { ci = 0; wx = 0.0; }
-                i0 = (int)ci;
-                i1 = i0 + 1;
-            }
-            if (per_y) {
-                j0 = (int)(((cj % Ny) + Ny) % Ny);
-                j1 = (j0 + 1) % Ny;
-            } else {
-                if (cj >= Ny) { cj = Ny - 1; wy = 1.0; }
-                if (cj < 0) { cj = 0; wy = 0.0; }
-                j0 = (int)cj;
-                j1 = j0 + 1;
-            }
-            double uatm = bilin(S.atm_u, s, i0, i1, j0, j1, wx, wy), vatm = bilin(S.atm_v, s, i0, i1, j0, j1, wx, wy);
-            double uocn = bilin(S.ocn_u, s, i0, i1, j0, j1, wx, wy), vocn = bilin(S.ocn_v, s, i0, i1, j0, j1, wx, wy);
-            double hfl = bilin(S.ocn_hflx, s, i0, i1, j0, j1, wx, wy);
-            double dua = uatm - up, dva = vatm - vp;  // calc_atmosphere_forcing, coupling.jl:1212-1232
-            double na = sqrt(dua * dua + dva * dva);
-            double tax = ka * na * dua, tay = ka * na * dva;
-            double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
-            double no = sqrt(duo * duo + dvo * dvo);
-            double tox = ko * no * (ct * duo - sn * dvo), toy = ko * no * (sn * duo + ct * dvo);
-            double tpx = -mf * vocn, tpy = mf * uocn;
-            double tx = tax + tpx + tox, ty = tay + tpy + toy;
-            tx_s += tx;
-            ty_s += ty;
-            trq_s += -tx * yc + ty * xc;
-            hf_s += hfl;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            tx_s += __shfl_xor_sync(FULLMASK, tx_s, o);
-            ty_s += __shfl_xor_sync(FULLMASK, ty_s, o);
-            trq_s += __shfl_xor_sync(FULLMASK, trq_s, o);
-            hf_s += __shfl_xor_sync(FULLMASK, hf_s, o);
-            npts += __shfl_xor_sync(FULLMASK, npts, o);
-        }
-        if (lane == 0) {
-            if (npts == 0) {
-                S.status[i] = SZ_STATUS_REMOVE;  // coupling.jl:1507-1508
-            } else {
-                double np_ = (double)npts, ar = S.area[i];
-                double tot_x = np_ * (mf * v) + tx_s, tot_y = -np_ * (mf * u) + ty_s;  // Coriolis, :1522-1525
-                S.fxOA[i] = tot_x / np_ * ar;  // :1583-1586
-                S.fyOA[i] = tot_y / np_ * ar;
-                S.trqOA[i] = trq_s / np_ * ar;
-                S.hflx[i] = hf_s / np_;
-            }
-        }
-    }
-}
-
-void szk_coupling(const Launch &L, const Store &S, const Params &P) {
-    if (S.n_init > 0) {
-        k_coupling<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, P);
-        g_launch_count += 1;
-    }
-}
-
-// ---- K7: state update (update_floe.jl:392-551) ---------------------------------------------------------------------------
-// One warp per floe: scalars are computed by every lane (uniform), vertices and the strain sum are
-// spread over the lanes.
-__global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
-    Counters *cnt = S.cnt;
-    if (cnt->error) return;
-    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
-    const double dt = (double)P.cfg.dt;
-    const int n = S.n_init;
-    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
-        uint32_t warn = 0;
-        double cfx = S.cfx[i], cfy = S.cfy[i], ctrq = S.ctrq[i];
-        const double cx = S.cx[i], cy = S.cy[i], area = S.area[i];
-        double height = S.height[i];
-        // calc_stress!, :392-414 (pre-move centroid)
-        double s11 = 0, s12 = 0, s22 = 0;
-        int r0 = B.row_off[i], r1 = B.row_off[i + 1];
-        if (r1 > r0) {
-            for (int k = r0; k < r1; ++k) {
-                const double *r = B.rows + (size_t)k * NCOL;
-                double fx = r[COL_FX], fy = r[COL_FY], px = r[COL_PX], py = r[COL_PY];
-                s11 += (px - cx) * fx;
-                s12 += (py - cy) * fx + (px - cx) * fy;
-                s22 += (py - cy) * fy;
-            }
-            s12 *= 0.5;
-            double inv = 1 / (area * height);
-            s11 *= inv;
-            s12 *= inv;
-            s22 *= inv;
-        }
-        double stv[4] = {s11, s12, s12, s22};
-        double lam = P.cfg.stress_lambda;  // stress_calculators.jl:118-122
-        if (lane < 4) {
-            S.stress_accum[4 * i + lane] = (1 - lam) * S.stress_accum[4 * i + lane] + lam * stv[lane];
-            S.stress_instant[4 * i + lane] = stv[lane];
-        }
-        if (height > P.cfg.max_floe_height) {  // :482-485
-            height = P.cfg.max_floe_height;
-            warn |= SZ_WARN_HEIGHT_CAPPED;
-        }
-        double mass = S.mass[i], moment = S.moment[i];
-        while (fmax(fabs(cfx), fabs(cfy)) > mass / (5 * dt)) {  // :487-491
-            cfx = cfx / 10;
-            cfy = cfy / 10;
-            ctrq = ctrq / 10;
-            warn |= SZ_WARN_FORCE_SCALED;
-        }
-        double hh = height;  // :494-500
-        double dh = S.hflx[i] / hh;
-        double hfrac = (hh + dh) / hh;
-        mass *= hfrac;
-        moment *= hfrac;
-        height -= dh;
-        hh = height;
-        const double u0 = S.u[i], v0 = S.v[i], xi0 = S.xi[i];
-        double Dx = 1.5 * dt * u0 - 0.5 * dt * S.p_dxdt[i];  // :503-506
-        double Dy = 1.5 * dt * v0 - 0.5 * dt * S.p_dydt[i];
-        double Da = 1.5 * dt * xi0 - 0.5 * dt * S.p_dalphadt[i];
-        // _move_floe! / _move_poly, floe_utils.jl:74-93: p -> R p + ((R(-c) + c) + D)
-        double sn = sin(Da), cs = cos(Da);
-        double tx = ((cs * (-cx) - sn * (-cy)) + cx) + Dx;
-        double ty = ((sn * (-cx) + cs * (-cy)) + cy) + Dy;
-        const double ncx = cx + Dx, ncy = cy + Dy;
-        double dudt = (S.fxOA[i] + cfx) / mass;  // :514-531
-        double dvdt = (S.fyOA[i] + cfy) / mass;
-        double frac = 1;
-        double au = fabs(dt * dudt), av = fabs(dt * dvdt), lim = hh / 2;
-        double sgu = (double)((dudt > 0) - (dudt < 0)), sgv = (double)((dvdt > 0) - (dvdt < 0));
-        if (au > lim && av > lim) {
-            double f1 = (sgu * hh / (2 * dt)) / dudt, f2 = (sgv * hh / (2 * dt)) / dvdt;
-            frac = f1 < f2 ? f1 : f2;
-        } else if (au > lim && av < lim) frac = (sgu * hh / (2 * dt)) / dudt;
-        else if (au < lim && av > lim) frac = (sgv * hh / (2 * dt)) / dvdt;
-        if (frac != 1) {
-            dudt = frac * dudt;
-            dvdt = frac * dvdt;
-            warn |= SZ_WARN_VELOCITY_LIMITED;
-        }
-        const double un = u0 + (1.5 * dt * dudt - 0.5 * dt * S.p_dudt[i]);  // :532-535
-        const double vn = v0 + (1.5 * dt * dvdt - 0.5 * dt * S.p_dvdt[i]);
-        double dxidt = (S.trqOA[i] + ctrq) / moment;  // :537-545
-        dxidt = frac * dxidt;
-        double xin = xi0 + 1.5 * dt * dxidt - 0.5 * dt * S.p_dxidt[i];
-        if (fabs(xin) > P.cfg.maximum_xi) {
-            xin = (double)((xin > 0) - (xin < 0)) * P.cfg.maximum_xi;
-            warn |= SZ_WARN_XI_CLAMPED;
-        }
-        // rigid move of the ring + calc_strain! (:425-453; v-terms use floe.u as the reference does)
-        const int vs = S.vstart[i], nv = S.vcount[i];
-        double e11 = 0, e12 = 0, e22 = 0;
-        for (int base = 0; base < nv; base += 32) {
-            const int k = base + lane;
-            const bool act = k < nv;
-            double2 p = act ? S.verts[vs + k] : make_double2(0.0, 0.0);
-            double2 q = make_double2((cs * p.x - sn * p.y) + tx, (sn * p.x + cs * p.y) + ty);
-            if (k + 1 < nv) {
-                double2 p2 = S.verts[vs + k + 1];
-                double2 q2 = make_double2((cs * p2.x - sn * p2.y) + tx, (sn * p2.x + cs * p2.y) + ty);
-                double x1 = q.x + (-ncx), y1 = q.y + (-ncy), x2 = q2.x + (-ncx), y2 = q2.y + (-ncy);
-                double xd = x2 - x1, yd = y2 - y1;
-                double ra1 = sqrt(x1 * x1 + y1 * y1), ra2 = sqrt(x2 * x2 + y2 * y2);
-                double t1 = atan2(y1, x1), t2 = atan2(y2, x2);
-                double u1 = un - xin * ra1 * sin(t1), u2 = un - xin * ra2 * sin(t2);
-                double v1 = un + xin * ra1 * cos(t1), v2 = un + xin * ra2 * cos(t2);
-                double ud = u2 - u1, vd = v2 - v1;
-                e11 += ud * yd;
-                e12 += ud * xd + vd * yd;
-                e22 += vd * xd;
-            }
-            __syncwarp();
-            if (act) S.verts[vs + k] = q;
-            __syncwarp();
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            e11 += __shfl_xor_sync(FULLMASK, e11, o);
-            e12 += __shfl_xor_sync(FULLMASK, e12, o);
-            e22 += __shfl_xor_sync(FULLMASK, e22, o);
-        }
-        if (lane == 0) {
-            e12 *= 0.5;
-            double den = 2 * area;
-            S.strain[4 * i + 0] = e11 / den;
-            S.strain[4 * i + 1] = e12 / den;
-            S.strain[4 * i + 2] = e12 / den;
-            S.strain[4 * i + 3] = e22 / den;
-            S.height[i] = height;
-            S.mass[i] = mass;
-            S.moment[i] = moment;
-            S.alpha[i] = S.alpha[i] + Da;
-            S.cx[i] = ncx;
-            S.cy[i] = ncy;
-            S.p_dxdt[i] = u0;  // :509-511
-            S.p_dydt[i] = v0;
-            S.p_dalphadt[i] = xi0;
-            S.u[i] = un;
-            S.v[i] = vn;
-            S.p_dudt[i] = dudt;
-            S.p_dvdt[i] = dvdt;
-            S.xi[i] = xin;
-            S.p_dxidt[i] = dxidt;
-            S.warn[i] = warn;
-        }
-    }
-}
-
-void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P) {
-    if (S.n_init > 0) {
-        k_update<<<grid_for(L, S.n_init, 8), 256, 0, L.stream>>>(S, B, P);
-        g_launch_count += 1;
-    }
 }
 
 // ---- geometry service / test hook -------------------------------------------------------------------------------------------

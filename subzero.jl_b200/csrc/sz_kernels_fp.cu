@@ -1,0 +1,325 @@
+// sz_kernels_fp.cu — K6 (ocean/atmosphere coupling) and K7 (state update).
+//
+// These two kernels carry no discrete geometric decision that must match the reference bit for
+// bit: their parity bar is 1e-9 relative (BASELINE.json north_star).  They are therefore compiled
+// with FMA contraction ON (unlike sz_kernels.cu) and use algebraic identities the tolerance covers.
+#include "sz_common.cuh"
+
+#define FULLMASK 0xffffffffu
+void szk_count_launches(int n);
+
+// ---- field packing ---------------------------------------------------------------------------------
+// The five coupling fields are interleaved per grid node: (atm_u, atm_v, ocn_u, ocn_v, hflx, 0, 0, 0)
+// = 64 B, so one bilinear corner is three vector loads from one cache line instead of five scattered
+// 8-byte loads from five arrays.
+__global__ void k_pack_fields(const double *__restrict__ au, const double *__restrict__ av,
+                              const double *__restrict__ ou, const double *__restrict__ ov,
+                              const double *__restrict__ oh, double *__restrict__ out, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double *o = out + (size_t)i * 8;
+        o[0] = au[i];
+        o[1] = av[i];
+        o[2] = ou[i];
+        o[3] = ov[i];
+        o[4] = oh[i];
+        o[5] = o[6] = o[7] = 0.0;
+    }
+}
+void szk_pack_fields(const Launch &L, const Store &S, int n) {
+    k_pack_fields<<<(n + 255) / 256, 256, 0, L.stream>>>(S.atm_u, S.atm_v, S.ocn_u, S.ocn_v, S.ocn_hflx, S.fields8, n);
+}
+
+// ---- K6: one-way ocean/atmosphere coupling (coupling.jl:1486-1589) ---------------------------------------
+// One warp per floe.  Lanes read the floe's body-frame Monte-Carlo points as consecutive double2
+// (512 B per warp load, streaming: they are read once per step and must not evict the fields),
+// rotate/translate them (calc_subfloe_values!, :627-657), drop points outside a non-periodic grid
+// extent (in_bounds, :494-597), gather the five fields bilinearly (mc_interpolation :845-902 ==
+// bilinear on the lattice; periodic axes wrap on lines 1..N) and reduce stress and torque with
+// shuffles in a fixed order.  With r = (xc, yc), theta = atan(yc, xc): rad sin(theta) = yc and
+// rad cos(theta) = xc, so the reference's u - xi rad sin(theta) (:1534-1537) and
+// (-tx sin + ty cos) rad (:1562) need no transcendental call.
+struct CpConst {
+    double x0, y0, xf, yf, inv_dx, inv_dy, ct, sn, ka, ko, f;
+    int Nx, Ny, per_x, per_y;
+};
+
+struct CpAcc {
+    double tx, ty, trq, hf;
+    int n;
+};
+
+__device__ __forceinline__ void cp_point(const CpConst &c, const double *__restrict__ F, double2 b, double ca,
+                                         double sa, double cx, double cy, double u, double v, double xi, double mf,
+                                         CpAcc &acc) {
+    double xc = ca * b.x - sa * b.y, yc = sa * b.x + ca * b.y;  // body frame -> world, about the centroid
+    double x = xc + cx, y = yc + cy;
+    bool inb = (c.per_x || (c.x0 <= x && x <= c.xf)) && (c.per_y || (c.y0 <= y && y <= c.yf));
+    if (!inb) return;
+    acc.n++;
+    // the reference recomputes (x - cx, y - cy) from the translated point; the difference to (xc, yc) is
+    // one rounding of a ~1e5 coordinate, i.e. ~1e-11 m on a ~1e3 m lever arm (1e-14 relative)
+    double xr = x - cx, yr = y - cy;
+    double up = u - xi * yr, vp = v + xi * xr;
+    double gx = (x - c.x0) * c.inv_dx, gy = (y - c.y0) * c.inv_dy;
+    double fx = floor(gx), fy = floor(gy);
+    int ci = (int)fx, cj = (int)fy;
+    double wx = gx - fx, wy = gy - fy;
+    int i0, i1, j0, j1;
+    if (c.per_x) {
+        i0 = ci % c.Nx;
+        if (i0 < 0) i0 += c.Nx;
+        i1 = i0 + 1 == c.Nx ? 0 : i0 + 1;
+    } else {
+        if (ci >= c.Nx) { ci = c.Nx - 1; wx = 1.0; }
+        if (ci < 0) { ci = 0; wx = 0.0; }
+        i0 = ci;
+        i1 = ci + 1;
+    }
+    if (c.per_y) {
+        j0 = cj % c.Ny;
+        if (j0 < 0) j0 += c.Ny;
+        j1 = j0 + 1 == c.Ny ? 0 : j0 + 1;
+    } else {
+        if (cj >= c.Ny) { cj = c.Ny - 1; wy = 1.0; }
+        if (cj < 0) { cj = 0; wy = 0.0; }
+        j0 = cj;
+        j1 = cj + 1;
+    }
+    const int s = c.Nx + 1;
+    const double2 *n00 = (const double2 *)(F + (size_t)(i0 + s * j0) * 8);
+    const double2 *n10 = (const double2 *)(F + (size_t)(i1 + s * j0) * 8);
+    const double2 *n01 = (const double2 *)(F + (size_t)(i0 + s * j1) * 8);
+    const double2 *n11 = (const double2 *)(F + (size_t)(i1 + s * j1) * 8);
+    double w00 = (1 - wx) * (1 - wy), w10 = wx * (1 - wy), w01 = (1 - wx) * wy, w11 = wx * wy;
+    double2 a00 = __ldg(n00), a10 = __ldg(n10), a01 = __ldg(n01), a11 = __ldg(n11);          // atm u, v
+    double2 o00 = __ldg(n00 + 1), o10 = __ldg(n10 + 1), o01 = __ldg(n01 + 1), o11 = __ldg(n11 + 1);  // ocn u, v
+    double h00 = __ldg(F + (size_t)(i0 + s * j0) * 8 + 4), h10 = __ldg(F + (size_t)(i1 + s * j0) * 8 + 4),
+           h01 = __ldg(F + (size_t)(i0 + s * j1) * 8 + 4), h11 = __ldg(F + (size_t)(i1 + s * j1) * 8 + 4);
+    double uatm = w00 * a00.x + w10 * a10.x + w01 * a01.x + w11 * a11.x;
+    double vatm = w00 * a00.y + w10 * a10.y + w01 * a01.y + w11 * a11.y;
+    double uocn = w00 * o00.x + w10 * o10.x + w01 * o01.x + w11 * o11.x;
+    double vocn = w00 * o00.y + w10 * o10.y + w01 * o01.y + w11 * o11.y;
+    double hfl = w00 * h00 + w10 * h10 + w01 * h01 + w11 * h11;
+    double dua = uatm - up, dva = vatm - vp;  // calc_atmosphere_forcing, coupling.jl:1212-1232
+    double na = sqrt(dua * dua + dva * dva);
+    double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
+    double no = sqrt(duo * duo + dvo * dvo);
+    double tx = c.ka * na * dua - mf * vocn + c.ko * no * (c.ct * duo - c.sn * dvo);
+    double ty = c.ka * na * dva + mf * uocn + c.ko * no * (c.sn * duo + c.ct * dvo);
+    acc.tx += tx;
+    acc.ty += ty;
+    acc.trq += ty * xr - tx * yr;
+    acc.hf += hfl;
+}
+
+__global__ void __launch_bounds__(256, 3) k_coupling(Store S, CpConst c) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const double *__restrict__ F = S.fields8;
+    const int n = S.n_init;
+    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
+        const double a = S.alpha[i], cx = S.cx[i], cy = S.cy[i], u = S.u[i], v = S.v[i], xi = S.xi[i];
+        double sa, ca;
+        sincos(a, &sa, &ca);
+        const double ar = S.area[i];
+        const double mf = S.mass[i] / ar * c.f;
+        CpAcc acc = {0.0, 0.0, 0.0, 0.0, 0};
+        const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
+        long long k = m0 + lane;
+        for (; k + 32 < m1; k += 64) {  // two independent points per lane in flight
+            double2 b0 = __ldcs(S.mc + k), b1 = __ldcs(S.mc + k + 32);
+            cp_point(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc);
+            cp_point(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc);
+        }
+        if (k < m1) cp_point(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            acc.tx += __shfl_xor_sync(FULLMASK, acc.tx, o);
+            acc.ty += __shfl_xor_sync(FULLMASK, acc.ty, o);
+            acc.trq += __shfl_xor_sync(FULLMASK, acc.trq, o);
+            acc.hf += __shfl_xor_sync(FULLMASK, acc.hf, o);
+            acc.n += __shfl_xor_sync(FULLMASK, acc.n, o);
+        }
+        if (lane == 0) {
+            if (acc.n == 0) {
+                S.status[i] = SZ_STATUS_REMOVE;  // coupling.jl:1507-1508
+            } else {
+                double np_ = (double)acc.n;
+                double tot_x = np_ * (mf * v) + acc.tx, tot_y = -np_ * (mf * u) + acc.ty;  // Coriolis, :1522-1525
+                S.fxOA[i] = tot_x / np_ * ar;  // :1583-1586
+                S.fyOA[i] = tot_y / np_ * ar;
+                S.trqOA[i] = acc.trq / np_ * ar;
+                S.hflx[i] = acc.hf / np_;
+            }
+        }
+    }
+}
+
+void szk_coupling(const Launch &L, const Store &S, const Params &P) {
+    if (S.n_init <= 0) return;
+    CpConst c;
+    c.x0 = P.x0; c.y0 = P.y0; c.xf = P.xf; c.yf = P.yf;
+    c.inv_dx = 1.0 / P.dx; c.inv_dy = 1.0 / P.dy;
+    c.ct = cos(P.cfg.turn_theta); c.sn = sin(P.cfg.turn_theta);
+    c.ka = P.cfg.rho_a * P.cfg.Cd_ia; c.ko = P.cfg.rho_o * P.cfg.Cd_io; c.f = P.cfg.f;
+    c.Nx = P.Nx; c.Ny = P.Ny;
+    c.per_x = P.per_x; c.per_y = P.per_y;
+    long long blocks = ((long long)S.n_init + 7) / 8, cap = (long long)L.sms * 24;
+    k_coupling<<<(int)(blocks < cap ? blocks : cap), 256, 0, L.stream>>>(S, c);
+    szk_count_launches(1);
+}
+
+// ---- K7: state update (update_floe.jl:392-551) -------------------------------------------------------------
+// One warp per floe: scalars are computed by every lane (uniform), vertices and the strain sum are
+// spread over the lanes.  calc_strain! (:425-453) evaluates u - xi r sin(theta), u + xi r cos(theta)
+// at every vertex; with r sin(theta) = y and r cos(theta) = x those are u - xi y and u + xi x
+// (the v terms use floe.u exactly as the reference does, :441-442).
+__global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const double dt = (double)P.cfg.dt;
+    const int n = S.n_init;
+    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
+        uint32_t warn = 0;
+        double cfx = S.cfx[i], cfy = S.cfy[i], ctrq = S.ctrq[i];
+        const double cx = S.cx[i], cy = S.cy[i], area = S.area[i];
+        double height = S.height[i];
+        // calc_stress!, :392-414 (pre-move centroid)
+        double s11 = 0, s12 = 0, s22 = 0;
+        int r0 = B.row_off[i], r1 = B.row_off[i + 1];
+        if (r1 > r0) {
+            for (int k = r0; k < r1; ++k) {
+                const double *r = B.rows + (size_t)k * NCOL;
+                double fx = r[COL_FX], fy = r[COL_FY], px = r[COL_PX], py = r[COL_PY];
+                s11 += (px - cx) * fx;
+                s12 += (py - cy) * fx + (px - cx) * fy;
+                s22 += (py - cy) * fy;
+            }
+            s12 *= 0.5;
+            double inv = 1 / (area * height);
+            s11 *= inv;
+            s12 *= inv;
+            s22 *= inv;
+        }
+        double stv[4] = {s11, s12, s12, s22};
+        double lam = P.cfg.stress_lambda;  // stress_calculators.jl:118-122
+        if (lane < 4) {
+            double sv = lane == 0 ? stv[0] : (lane == 3 ? stv[3] : stv[1]);
+            S.stress_accum[4 * i + lane] = (1 - lam) * S.stress_accum[4 * i + lane] + lam * sv;
+            S.stress_instant[4 * i + lane] = sv;
+        }
+        if (height > P.cfg.max_floe_height) {  // :482-485
+            height = P.cfg.max_floe_height;
+            warn |= SZ_WARN_HEIGHT_CAPPED;
+        }
+        double mass = S.mass[i], moment = S.moment[i];
+        while (fmax(fabs(cfx), fabs(cfy)) > mass / (5 * dt)) {  // :487-491
+            cfx = cfx / 10;
+            cfy = cfy / 10;
+            ctrq = ctrq / 10;
+            warn |= SZ_WARN_FORCE_SCALED;
+        }
+        double hh = height;  // :494-500
+        double dh = S.hflx[i] / hh;
+        double hfrac = (hh + dh) / hh;
+        mass *= hfrac;
+        moment *= hfrac;
+        height -= dh;
+        hh = height;
+        const double u0 = S.u[i], v0 = S.v[i], xi0 = S.xi[i];
+        double Dx = 1.5 * dt * u0 - 0.5 * dt * S.p_dxdt[i];  // :503-506
+        double Dy = 1.5 * dt * v0 - 0.5 * dt * S.p_dydt[i];
+        double Da = 1.5 * dt * xi0 - 0.5 * dt * S.p_dalphadt[i];
+        // _move_floe! / _move_poly, floe_utils.jl:74-93: p -> R p + ((R(-c) + c) + D)
+        double sn, cs;
+        sincos(Da, &sn, &cs);
+        double tx = ((cs * (-cx) - sn * (-cy)) + cx) + Dx;
+        double ty = ((sn * (-cx) + cs * (-cy)) + cy) + Dy;
+        const double ncx = cx + Dx, ncy = cy + Dy;
+        double dudt = (S.fxOA[i] + cfx) / mass;  // :514-531
+        double dvdt = (S.fyOA[i] + cfy) / mass;
+        double frac = 1;
+        double au = fabs(dt * dudt), av = fabs(dt * dvdt), lim = hh / 2;
+        double sgu = (double)((dudt > 0) - (dudt < 0)), sgv = (double)((dvdt > 0) - (dvdt < 0));
+        if (au > lim && av > lim) {
+            double f1 = (sgu * hh / (2 * dt)) / dudt, f2 = (sgv * hh / (2 * dt)) / dvdt;
+            frac = f1 < f2 ? f1 : f2;
+        } else if (au > lim && av < lim) frac = (sgu * hh / (2 * dt)) / dudt;
+        else if (au < lim && av > lim) frac = (sgv * hh / (2 * dt)) / dvdt;
+        if (frac != 1) {
+            dudt = frac * dudt;
+            dvdt = frac * dvdt;
+            warn |= SZ_WARN_VELOCITY_LIMITED;
+        }
+        const double un = u0 + (1.5 * dt * dudt - 0.5 * dt * S.p_dudt[i]);  // :532-535
+        const double vn = v0 + (1.5 * dt * dvdt - 0.5 * dt * S.p_dvdt[i]);
+        double dxidt = (S.trqOA[i] + ctrq) / moment;  // :537-545
+        dxidt = frac * dxidt;
+        double xin = xi0 + 1.5 * dt * dxidt - 0.5 * dt * S.p_dxidt[i];
+        if (fabs(xin) > P.cfg.maximum_xi) {
+            xin = (double)((xin > 0) - (xin < 0)) * P.cfg.maximum_xi;
+            warn |= SZ_WARN_XI_CLAMPED;
+        }
+        // rigid move of the ring + calc_strain! on the moved ring with the updated u, xi
+        const int vs = S.vstart[i], nv = S.vcount[i];
+        double e11 = 0, e12 = 0, e22 = 0;
+        for (int base = 0; base < nv; base += 32) {
+            const int k = base + lane;
+            const bool act = k < nv;
+            double2 p = act ? S.verts[vs + k] : make_double2(0.0, 0.0);
+            double2 q = make_double2((cs * p.x - sn * p.y) + tx, (sn * p.x + cs * p.y) + ty);
+            if (k + 1 < nv) {
+                double2 p2 = S.verts[vs + k + 1];
+                double2 q2 = make_double2((cs * p2.x - sn * p2.y) + tx, (sn * p2.x + cs * p2.y) + ty);
+                double x1 = q.x - ncx, y1 = q.y - ncy, x2 = q2.x - ncx, y2 = q2.y - ncy;
+                double xd = x2 - x1, yd = y2 - y1;
+                double ud = (un - xin * y2) - (un - xin * y1), vd = (un + xin * x2) - (un + xin * x1);
+                e11 += ud * yd;
+                e12 += ud * xd + vd * yd;
+                e22 += vd * xd;
+            }
+            __syncwarp();
+            if (act) S.verts[vs + k] = q;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            e11 += __shfl_xor_sync(FULLMASK, e11, o);
+            e12 += __shfl_xor_sync(FULLMASK, e12, o);
+            e22 += __shfl_xor_sync(FULLMASK, e22, o);
+        }
+        if (lane == 0) {
+            e12 *= 0.5;
+            double den = 2 * area;
+            S.strain[4 * i + 0] = e11 / den;
+            S.strain[4 * i + 1] = e12 / den;
+            S.strain[4 * i + 2] = e12 / den;
+            S.strain[4 * i + 3] = e22 / den;
+            S.height[i] = height;
+            S.mass[i] = mass;
+            S.moment[i] = moment;
+            S.alpha[i] = S.alpha[i] + Da;
+            S.cx[i] = ncx;
+            S.cy[i] = ncy;
+            S.p_dxdt[i] = u0;  // :509-511
+            S.p_dydt[i] = v0;
+            S.p_dalphadt[i] = xi0;
+            S.u[i] = un;
+            S.v[i] = vn;
+            S.p_dudt[i] = dudt;
+            S.p_dvdt[i] = dvdt;
+            S.xi[i] = xin;
+            S.p_dxidt[i] = dxidt;
+            S.warn[i] = warn;
+        }
+    }
+}
+
+void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P) {
+    if (S.n_init <= 0) return;
+    long long blocks = ((long long)S.n_init + 7) / 8, cap = (long long)L.sms * 32;
+    k_update<<<(int)(blocks < cap ? blocks : cap), 256, 0, L.stream>>>(S, B, P);
+    szk_count_launches(1);
+}

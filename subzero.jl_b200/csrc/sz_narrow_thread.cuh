@@ -19,6 +19,7 @@
 #define TN_MAXREG 2  // regions per clip
 #define TN_RCAP 26   // points of all regions of one clip
 #define TN_MAXIP 8   // raw intersection points
+#define TN_MAXC 24   // edge pairs whose P edge straddles the Q edge's line
 
 enum { TN_OK = 0, TN_DEFER = 1 };
 
@@ -141,9 +142,20 @@ __device__ __noinline__ bool t_rings_intersect(const TRing &A, const TRing &B) {
 
 // intersect_polys for one thread; regions go to R ([point][thread]) as closed rings
 // [rs[r], re[r]), ordered by first crossing along P.
-__device__ __noinline__ int t_clip(const TRing &P, const TRing &Q, double2 *R, int *rs, int *re, int &status) {
+//
+// Crossing search: the side of every P vertex w.r.t. every Q edge is evaluated ONCE (np x nq
+// orientation values, kept as one bit mask per Q edge); an edge pair (e, f) can only cross where
+// the bit changes between vertex e and e+1, and only there the four orientations are evaluated
+// in full (identical expressions, hence identical bits, as the exhaustive (e, f) loop).
+// `xp_out` / `generic`: when no orientation value was exactly zero the crossing points ARE
+// GO.intersection_points(P, Q) (closed-segment intersection == proper crossing), in the same
+// (e, f) order; the caller then skips the separate 4 np nq pass.
+__device__ __noinline__ int t_clip(const TRing &P, const TRing &Q, double2 *R, int *rs, int *re, int &status,
+                                   double2 *xp_out, int *K_out, bool *generic) {
     const int np = P.n - 1, nq = Q.n - 1;
     status = TN_OK;
+    if (K_out) *K_out = 0;
+    if (generic) *generic = false;
     if (np < 3 || nq < 3) return 0;
     const bool q_ccw = t_area2(Q) > 0.0;
     const bool same = (t_area2(P) > 0.0) == q_ccw;
@@ -151,35 +163,81 @@ __device__ __noinline__ int t_clip(const TRing &P, const TRing &Q, double2 *R, i
     double xt[TN_MAXX], xs[TN_MAXX];
     double2 xp[TN_MAXX];
     bool xent[TN_MAXX], xvis[TN_MAXX];
-    int K = 0;
-    for (int e = 0; e < np; ++e) {
-        double2 a = tget(P, e), b = tget(P, e + 1);
-        double2 c = tget(Q, 0);
-        for (int f = 0; f < nq; ++f) {
-            double2 d = tget(Q, f + 1);
-            double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
-            bool sa = side_q(o1, c, d), sb = side_q(o2, c, d);
-            if (sa != sb) {
-                double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
-                bool sc = side_p(o3, a, b), sd = side_p(o4, a, b);
-                if (sc != sd) {
-                    if (K == TN_MAXX) {
+    // pass 1 (uniform across the warp): one orientation per (P vertex, Q edge); the (e, f) pairs whose
+    // side bit changes from vertex e to e+1 are appended to a short candidate list in (e, f) order
+    unsigned char ce[TN_MAXC], cf[TN_MAXC];
+    int nc = 0;
+    bool anyzero = false;
+    {
+        unsigned first = 0, prev = 0;
+        for (int v = 0; v <= np; ++v) {
+            unsigned cur;
+            if (v < np) {
+                double2 pv = tget(P, v);
+                double2 c = tget(Q, 0);
+                cur = 0;
+                for (int f = 0; f < nq; ++f) {
+                    double2 d = tget(Q, f + 1);
+                    double o = orient2d(c, d, pv);
+                    anyzero |= (o == 0.0);
+                    cur |= (unsigned)side_q(o, c, d) << f;
+                    c = d;
+                }
+                if (v == 0) first = cur;
+            } else {
+                cur = first;  // the closing point is vertex 0
+            }
+            if (v > 0) {
+                unsigned chg = prev ^ cur;
+                while (chg) {
+                    int f = __ffs(chg) - 1;
+                    chg &= chg - 1;
+                    if (nc == TN_MAXC) {
                         status = TN_DEFER;
                         return 0;
                     }
-                    double t = o1 / (o1 - o2);
-                    xe[K] = e;
-                    xf[K] = f;
-                    xt[K] = t;
-                    xs[K] = o3 / (o3 - o4);
-                    xp[K] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
-                    xent[K] = (sb == q_ccw);
-                    xvis[K] = false;
-                    K++;
+                    ce[nc] = (unsigned char)(v - 1);
+                    cf[nc] = (unsigned char)f;
+                    nc++;
                 }
             }
-            c = d;
+            prev = cur;
         }
+    }
+    // pass 2: the full four-orientation test only on the candidates
+    int K = 0;
+    for (int k = 0; k < nc; ++k) {
+        const int e = ce[k], f = cf[k];
+        double2 a = tget(P, e), b = tget(P, e + 1);
+        double2 c = tget(Q, f), d = tget(Q, f + 1);
+        double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
+        anyzero |= (o3 == 0.0) | (o4 == 0.0);
+        bool sc = side_p(o3, a, b), sd = side_p(o4, a, b);
+        if (sc == sd) continue;
+        if (K == TN_MAXX) {
+            status = TN_DEFER;
+            return 0;
+        }
+        double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
+        bool sb = side_q(o2, c, d);
+        double t = o1 / (o1 - o2);
+        xe[K] = e;
+        xf[K] = f;
+        xt[K] = t;
+        xs[K] = o3 / (o3 - o4);
+        xp[K] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
+        xent[K] = (sb == q_ccw);
+        xvis[K] = false;
+        K++;
+    }
+    if (K_out) {
+        bool dup = false;
+        for (int k = 0; k < K; ++k) {
+            xp_out[k * TN_NT] = xp[k];
+            for (int m = 0; m < k; ++m) dup |= (xp[m].x == xp[k].x && xp[m].y == xp[k].y);
+        }
+        *K_out = K;
+        *generic = !anyzero && !dup;
     }
     if (K == 0) {
         bool pin = t_point_in_ring_q(tget(P, 0), Q);
@@ -428,7 +486,7 @@ __device__ __noinline__ double t_normal_force(const TWs &w, const TRing &P, cons
         P2.sx = dir[0];
         P2.sy = dir[1];
         int rs2[TN_MAXREG], re2[TN_MAXREG];
-        int nreg2 = t_clip(P2, Q, w.R2, rs2, re2, status);
+        int nreg2 = t_clip(P2, Q, w.R2, rs2, re2, status, nullptr, nullptr, nullptr);
         if (status != TN_OK) return 0.0;
         for (int r = 0; r < nreg2; ++r) {
             TRing nr = tring(w.R2 + rs2[r] * TN_NT, re2[r] - rs2[r]);
@@ -490,7 +548,9 @@ __device__ bool thread_item(const TWs &w, const Store &S, const StepBuf &B, cons
     uint32_t flags = 0;
     int rs1[TN_MAXREG], re1[TN_MAXREG];
     double area1[TN_MAXREG];
-    int nreg = t_clip(Pr, Qr, w.R1, rs1, re1, status);
+    int K1 = 0;
+    bool generic = false;
+    int nreg = t_clip(Pr, Qr, w.R1, rs1, re1, status, w.ip, &K1, &generic);
     if (status != TN_OK) return false;
     double total = 0.0, max_area = 0.0;
     for (int r = 0; r < nreg; ++r) {
@@ -538,7 +598,8 @@ __device__ bool thread_item(const TWs &w, const Store &S, const StepBuf &B, cons
     int nrows = 0;
     if (forces) {
         // calc_elastic_forces, collisions.jl:149-188
-        int nip = t_intersection_points(Pr, Qr, w.ip, status);
+        // GO.intersection_points: the crossing points of clip #1 when the configuration is generic
+        int nip = generic ? K1 : t_intersection_points(Pr, Qr, w.ip, status);
         if (status != TN_OK) return false;
         if (nip >= 2) {
             int n1 = npp - 1, n2 = nqp - 1;
