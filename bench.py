@@ -34,8 +34,8 @@ METRIC = "sim timesteps/sec (collisions + one-way ocean/atmosphere coupling + st
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--floes", type=int, default=100000, help="floes per GPU")
     ap.add_argument("--npoints", type=int, default=1000, help="Monte-Carlo draws per floe (about 59 % are kept)")
@@ -48,51 +48,48 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, 5 ms period)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.bits, self.run, self.t, self.smax = index, [], 0, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        if self.nv is None:
+            return
+        self.run = True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            p = [x.strip() for x in r.split(",")]
-            if len(p) < 6:
-                continue
-            try:
-                sm.append(float(p[0]))
-                smax = float(p[1])
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if p[2 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.run = False
+        self.t.join(timeout=2)
+        reasons = sorted(n for b, n in self.REASONS.items() if self.bits & b)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                "samples": len(self.sm)}
 
 
 def pin_floe_arrays(fa):
@@ -194,10 +191,30 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prod = capi.product()
 
-    f = synth.make_field(args.floes, scale=args.scale, walls=args.walls, npoints=args.npoints, seed=args.floes + rank)
-    h = synth.setup_handle(f, prod, device=local_rank)
-    fa0 = f.floes
+    me = None
+    if world == 1:
+        f = synth.make_field(args.floes, scale=args.scale, walls=args.walls, npoints=args.npoints, seed=args.floes)
+        h = synth.setup_handle(f, prod, device=local_rank)
+        fa0 = f.floes
+    else:
+        # weak scaling: rank r generates the tile [r L, (r+1) L) x [0, L) and owns it; the neighbours' boundary
+        # floes become halo copies whose state is refreshed every step (slab.py)
+        from subzero_jl_b200 import slab
+        tile = synth.make_field(args.floes, scale=args.scale, walls="collision", npoints=args.npoints, seed=args.floes + rank)
+        slab.shift_x(tile.floes, rank * tile.L)
+        ew = "shear" if args.walls in ("shear", "periodic") else "collision"
+        f = synth.tiled_model(tile, world, ew)
+        me = slab.partition_tiles(tile.floes, rank, world, tile.L, world * tile.L if ew == "shear" else None, skin=500.0)
+        h = synth.setup_handle(f, prod, device=local_rank)
+        me.attach(h)
+        me.make_buffers(torch.device("cuda", local_rank))
+        fa0 = tile.floes
     N, M, V = fa0.n, int(fa0.mc_offsets[-1]), int(fa0.vert_offsets[-1])
+
+    def do_step(t):
+        if me is not None:
+            me.exchange()
+        h.step(t, True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -206,7 +223,7 @@ def main():
 
     # ---- device-resident throughput ---------------------------------------------------------------
     for t in range(args.warmup):
-        h.step(t, True)
+        do_step(t)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -215,7 +232,7 @@ def main():
     launches = 0
     t0 = time.perf_counter()
     for t in range(args.steps):
-        h.step(args.warmup + t, True)
+        do_step(args.warmup + t)
         ms = h.timings_raw()
         phase += ms
         launches += int(ms[7])
@@ -238,14 +255,14 @@ def main():
         h2d = dyn_bytes(host_fa)
         for t in range(2):
             h.upload_state(host_fa)
-            h.step(t, True)
+            do_step(t)
             h.download_floes(into=host_fa, mc=False)
         barrier()
         t0 = time.perf_counter()
         ne = max(3, min(args.steps, 10))
         for t in range(ne):
             h.upload_state(host_fa)          # H2D: every per-floe scalar + ring coordinates
-            h.step(t, True)
+            do_step(t)
             h.download_floes(into=host_fa, mc=False)   # D2H: the same state back
             _ = float(host_fa.collision_force[0, 0])
         torch.cuda.synchronize()
@@ -256,6 +273,13 @@ def main():
         e2e = {"value": ne / float(te[0]), "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "call": "sz_upload_state + sz_step + sz_download_floes on pinned host arrays"}
 
+    stale = bool(me.stale()) if me is not None else False
+    halo = None
+    if me is not None:
+        hs = torch.tensor([me.local.n - int(me.owned.sum()), sum(me.nbytes[0::2]), int(stale)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(hs, op=dist.ReduceOp.MAX)
+        halo = {"halo_floes_max": int(hs[0]), "send_bytes_per_step_max": int(hs[1]), "lists_stale": bool(hs[2]),
+                "exchange": "sz_halo_pack -> NCCL isend/irecv (torch.distributed) -> sz_halo_unpack, every step"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -304,7 +328,7 @@ def main():
         "mc_points_per_s": value * M * world,
         "device_ms_per_step": 1e3 * dev_max / args.steps,
         "counts": {k: c[k] for k in ("n_init", "n_candidates", "n_pairs", "n_overlap", "n_rows", "n_mc", "n_vertices")},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "halo": halo, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:

@@ -200,6 +200,21 @@ int32_t SZ_FN(get_warnings)(sz_handle *h, uint32_t *bits); /* [n_init] */
  * [5] floe properties [6] total [7] kernels launched by the last sz_step */
 int32_t SZ_FN(get_timings)(sz_handle *h, double ms[8]);
 
+/* ---- slab decomposition: halo exchange of floe state (new, the reference is single-process) ----
+ * One handle per GPU owns the floes of one spatial slab plus copies ("halo floes") of the neighbours'
+ * floes that can touch them.  The floe LIST of a handle is fixed between rebuilds; every step the owner of a
+ * floe sends its DYNAMIC state to the ranks that hold a copy.  A halo list is a set of local floe indices in
+ * an order both sides agree on (ascending global index).  sz_halo_pack gathers, for the floes of one list,
+ * 8 doubles per floe (centroid x, y, u, v, xi, height, status tag, alpha) followed by all their ring points
+ * (x, y interleaved) into a caller-provided buffer in the memory space the handle computes in (a CUDA device
+ * pointer for the product, host memory for the oracle build); the caller moves it (ncclSend/ncclRecv,
+ * torch.distributed) and sz_halo_unpack scatters it into the floes of the matching list on the other side. */
+int32_t SZ_FN(halo_configure)(sz_handle *h, int32_t n_lists, const int64_t *list_offsets,
+                              const int64_t *floe_index /* 1-based local indices */);
+int32_t SZ_FN(halo_bytes)(sz_handle *h, int32_t list, int64_t *bytes);
+int32_t SZ_FN(halo_pack)(sz_handle *h, int32_t list, void *dst, int64_t capacity_bytes);
+int32_t SZ_FN(halo_unpack)(sz_handle *h, int32_t list, const void *src, int64_t bytes);
+
 /* ---- geometry service (test hook; also what SURVEY §8(f) rank 2 reuses) ---------------------- */
 /* Clip two closed rings; regions are written as consecutive closed rings into out_xy
  * (capacity cap_points points), region r = points [out_offsets[r], out_offsets[r+1]).

@@ -76,6 +76,9 @@ struct sz_handle {
     int64_t *cand, *pairs, *overlap, *fuse;
     int64_t n_cand, n_pairs, n_overlap, n_fuse, n_domain_pairs, n_clip_fail;
     double ms[8];
+    /* halo lists (slab decomposition) */
+    int n_lists;
+    int64_t *hl_off, *hl_idx;
 };
 
 #define DFIELDS(X)                                                                               \
@@ -156,6 +159,7 @@ void szo_destroy(sz_handle *h) {
     for (int k = 0; k < h->n_topo; ++k) free(h->topo_ring[k]);
     free(h->topo_ring); free(h->topo_np); free(h->topo_cx); free(h->topo_cy); free(h->topo_rmax);
     free(h->cand); free(h->pairs); free(h->overlap); free(h->fuse);
+    free(h->hl_off); free(h->hl_idx);
     free(h);
 }
 
@@ -1259,6 +1263,65 @@ int32_t szo_get_warnings(sz_handle *h, uint32_t *bits) {
 int32_t szo_get_timings(sz_handle *h, double ms[8]) {
     if (!h || !ms) return SZ_ERR_INVALID;
     memcpy(ms, h->ms, sizeof(double) * 8);
+    return SZ_OK;
+}
+
+/* ---- halo exchange (same layout as the product: 8 doubles per floe, then the ring points) ------------- */
+int32_t szo_halo_configure(sz_handle *h, int32_t n_lists, const int64_t *off, const int64_t *idx) {
+    if (!h || n_lists < 0 || (n_lists > 0 && (!off || !idx))) return SZ_ERR_INVALID;
+    free(h->hl_off); free(h->hl_idx);
+    h->n_lists = n_lists;
+    int64_t tot = n_lists > 0 ? off[n_lists] : 0;
+    h->hl_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_lists + 1));
+    h->hl_idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(tot > 0 ? tot : 1));
+    h->hl_off[0] = 0;
+    for (int k = 0; k < n_lists; ++k) h->hl_off[k + 1] = off[k + 1];
+    for (int64_t k = 0; k < tot; ++k) {
+        if (idx[k] < 1 || idx[k] > h->n_init) return fail(h, SZ_ERR_INVALID, "halo_configure: index out of range");
+        h->hl_idx[k] = idx[k] - 1;
+    }
+    return SZ_OK;
+}
+
+int32_t szo_halo_bytes(sz_handle *h, int32_t list, int64_t *bytes) {
+    if (!h || !bytes || list < 0 || list >= h->n_lists) return SZ_ERR_INVALID;
+    int64_t b = 0;
+    for (int64_t k = h->hl_off[list]; k < h->hl_off[list + 1]; ++k) b += 64 + 16 * (int64_t)h->npts[h->hl_idx[k]];
+    *bytes = b;
+    return SZ_OK;
+}
+
+int32_t szo_halo_pack(sz_handle *h, int32_t list, void *dst, int64_t cap) {
+    int64_t need;
+    if (!h || !dst || szo_halo_bytes(h, list, &need) != SZ_OK) return SZ_ERR_INVALID;
+    if (need > cap) return fail(h, SZ_ERR_CAPACITY, "halo_pack: buffer too small");
+    int64_t n = h->hl_off[list + 1] - h->hl_off[list];
+    double *rec = (double *)dst, *vx = rec + 8 * n;
+    for (int64_t k = 0; k < n; ++k) {
+        int64_t i = h->hl_idx[h->hl_off[list] + k];
+        double *r = rec + 8 * k;
+        r[0] = h->cx[i]; r[1] = h->cy[i]; r[2] = h->u[i]; r[3] = h->v[i]; r[4] = h->xi[i];
+        r[5] = h->height[i]; r[6] = (double)h->status[i]; r[7] = h->alpha[i];
+        memcpy(vx, h->ring[i], sizeof(szo_pt) * (size_t)h->npts[i]);
+        vx += 2 * h->npts[i];
+    }
+    return SZ_OK;
+}
+
+int32_t szo_halo_unpack(sz_handle *h, int32_t list, const void *src, int64_t bytes) {
+    int64_t need;
+    if (!h || !src || szo_halo_bytes(h, list, &need) != SZ_OK) return SZ_ERR_INVALID;
+    if (need != bytes) return fail(h, SZ_ERR_INVALID, "halo_unpack: size differs from the configured list");
+    int64_t n = h->hl_off[list + 1] - h->hl_off[list];
+    const double *rec = (const double *)src, *vx = rec + 8 * n;
+    for (int64_t k = 0; k < n; ++k) {
+        int64_t i = h->hl_idx[h->hl_off[list] + k];
+        const double *r = rec + 8 * k;
+        h->cx[i] = r[0]; h->cy[i] = r[1]; h->u[i] = r[2]; h->v[i] = r[3]; h->xi[i] = r[4];
+        h->height[i] = r[5]; h->status[i] = (int32_t)r[6]; h->alpha[i] = r[7];
+        memcpy(h->ring[i], vx, sizeof(szo_pt) * (size_t)h->npts[i]);
+        vx += 2 * h->npts[i];
+    }
     return SZ_OK;
 }
 

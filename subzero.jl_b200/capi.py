@@ -105,6 +105,10 @@ class Library:
         "get_pairs": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
         "get_warnings": (C.c_int32, [C.c_void_p, c_u32_p]),
         "get_timings": (C.c_int32, [C.c_void_p, c_double_p]),
+        "halo_configure": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p]),
+        "halo_bytes": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
+        "halo_pack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+        "halo_unpack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
         "clip_polygons": (C.c_int32, [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                       C.c_int32, C.c_int32, c_i32_p, c_double_p, c_double_p]),
     }
@@ -362,6 +366,27 @@ class Handle:
         ms = np.zeros(8)
         self._ck(self.lib.get_timings(self.h, _dp(ms)))
         return dict(zip(("ghosts", "broad", "narrow", "reduce", "coupling", "update", "total"), ms[:7]))
+
+    # slab decomposition ---------------------------------------------------------------------------
+    def halo_configure(self, lists):
+        """lists: sequences of 0-based local floe indices (one per exchange partner and direction)."""
+        offs = np.zeros(len(lists) + 1, dtype=np.int64)
+        for k, l in enumerate(lists):
+            offs[k + 1] = offs[k] + len(l)
+        idx = (np.concatenate([np.asarray(l, dtype=np.int64) for l in lists]) + 1 if offs[-1] else np.zeros(1, dtype=np.int64))
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        self._ck(self.lib.halo_configure(self.h, len(lists), _ip(offs), _ip(idx)))
+
+    def halo_bytes(self, k):
+        b = C.c_int64(0)
+        self._ck(self.lib.halo_bytes(self.h, k, C.byref(b)))
+        return b.value
+
+    def halo_pack(self, k, ptr, capacity):
+        self._ck(self.lib.halo_pack(self.h, k, C.c_void_p(ptr), capacity))
+
+    def halo_unpack(self, k, ptr, nbytes):
+        self._ck(self.lib.halo_unpack(self.h, k, C.c_void_p(ptr), nbytes))
 
     def clip_polygons(self, p, q, cap_regions=64, cap_points=8192):
         p = np.ascontiguousarray(p, dtype=np.float64)

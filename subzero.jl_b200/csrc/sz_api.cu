@@ -38,6 +38,11 @@ struct sz_handle {
     int n_rows_host;
     cudaEvent_t ev[NEV];
     double ms[8];
+    // halo lists (slab decomposition)
+    int n_lists;
+    std::vector<long long> hl_off, hl_bytes;
+    int *d_hl_idx;
+    long long *d_hl_voff;
 };
 
 #define CK(expr)                                                                                         \
@@ -214,6 +219,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->P.cfg = *cfg;
     h->have_grid = h->have_fields = h->have_domain = h->have_floes = false;
     h->n_init = h->n_total = h->n_verts = h->n_verts_init = 0;
+    h->n_lists = 0; h->d_hl_idx = nullptr; h->d_hl_voff = nullptr;
     h->n_mc = 0; h->n_topo = 0; h->topo_verts_n = 0; h->field_n = 0; h->n_rows_host = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
@@ -247,6 +253,7 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(B.cell_count); dfree(B.cell_start); dfree(B.cell_fill); dfree(B.scan_block); dfree(B.cell_circ); dfree(B.pair_i); dfree(B.pair_j);
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
+    dfree(h->d_hl_idx); dfree(h->d_hl_voff);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int k = 0; k < NEV; ++k) cudaEventDestroy(h->ev[k]);
     cudaStreamDestroy(h->L.stream);
@@ -787,7 +794,6 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
     cudaSetDevice(h->cfg.device);
     cudaStream_t st = h->L.stream;
-    szk_launch_count(true);
     for (int attempt = 0;; ++attempt) {
         cudaEventRecord(h->ev[0], st);
         enqueue_ghosts(h);
@@ -827,7 +833,7 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     h->ms[4] = ev_ms(h, 5, 6);
     h->ms[5] = ev_ms(h, 6, 7);
     h->ms[6] = ev_ms(h, 0, 7);
-    h->ms[7] = (double)szk_launch_count(true);  // kernels launched by this call
+    h->ms[7] = (double)szk_launch_count(true);  // kernels launched since the previous sz_step returned (incl. halo pack/unpack)
     return SZ_OK;
 }
 
@@ -906,6 +912,58 @@ extern "C" int32_t sz_get_timings(sz_handle *h, double ms[8]) {
     memcpy(ms, h->ms, sizeof(double) * 8);
     return SZ_OK;
 }
+
+// ---- halo exchange ----------------------------------------------------------------------------------------
+extern "C" int32_t sz_halo_configure(sz_handle *h, int32_t n_lists, const int64_t *off, const int64_t *idx) {
+    if (!h || n_lists < 0 || (n_lists > 0 && (!off || !idx))) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "halo_configure before upload_floes");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    long long tot = n_lists > 0 ? off[n_lists] : 0;
+    std::vector<int> vcount(std::max(h->n_init, 1)), lidx((size_t)std::max<long long>(tot, 1));
+    std::vector<long long> voff((size_t)std::max<long long>(tot, 1));
+    if (h->n_init > 0) CK(cudaMemcpy(vcount.data(), h->S.vcount, sizeof(int) * h->n_init, cudaMemcpyDeviceToHost));
+    h->hl_off.assign(off, off + n_lists + 1);
+    h->hl_bytes.assign(n_lists, 0);
+    for (int l = 0; l < n_lists; ++l) {
+        long long v = 0;
+        for (long long k = off[l]; k < off[l + 1]; ++k) {
+            if (idx[k] < 1 || idx[k] > h->n_init) return fail(h, SZ_ERR_INVALID, "halo_configure: index out of range");
+            lidx[k] = (int)(idx[k] - 1);
+            voff[k] = v;
+            v += vcount[lidx[k]];
+        }
+        h->hl_bytes[l] = 64 * (off[l + 1] - off[l]) + 16 * v;
+    }
+    dfree(h->d_hl_idx); dfree(h->d_hl_voff);
+    CK(dalloc(&h->d_hl_idx, (size_t)tot)); CK(dalloc(&h->d_hl_voff, (size_t)tot));
+    if (tot > 0) {
+        CK(cudaMemcpy(h->d_hl_idx, lidx.data(), sizeof(int) * tot, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_hl_voff, voff.data(), sizeof(long long) * tot, cudaMemcpyHostToDevice));
+    }
+    h->n_lists = n_lists;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_halo_bytes(sz_handle *h, int32_t list, int64_t *bytes) {
+    if (!h || !bytes || list < 0 || list >= h->n_lists) return SZ_ERR_INVALID;
+    *bytes = h->hl_bytes[list];
+    return SZ_OK;
+}
+
+static int32_t halo_move(sz_handle *h, int32_t list, void *buf, int64_t bytes, bool pack) {
+    if (!h || !buf || list < 0 || list >= h->n_lists) return SZ_ERR_INVALID;
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "halo exchange with ghosts present");
+    if (pack ? bytes < h->hl_bytes[list] : bytes != h->hl_bytes[list]) return fail(h, pack ? SZ_ERR_CAPACITY : SZ_ERR_INVALID, "halo buffer size does not match the configured list");
+    cudaSetDevice(h->cfg.device);
+    long long a = h->hl_off[list], n = h->hl_off[list + 1] - a;
+    szk_halo(h->L, h->S, h->d_hl_idx + a, h->d_hl_voff + a, (int)n, (double *)buf, pack);
+    CK(cudaStreamSynchronize(h->L.stream));  // the caller's communication runs on its own stream
+    CK(cudaGetLastError());
+    return SZ_OK;
+}
+extern "C" int32_t sz_halo_pack(sz_handle *h, int32_t list, void *dst, int64_t cap) { return halo_move(h, list, dst, cap, true); }
+extern "C" int32_t sz_halo_unpack(sz_handle *h, int32_t list, const void *src, int64_t bytes) { return halo_move(h, list, (void *)src, bytes, false); }
 
 extern "C" int32_t sz_clip_polygons(sz_handle *h, const double *p_xy, int32_t np, const double *q_xy, int32_t nq,
                                     int32_t cap_regions, int32_t cap_points, int32_t *out_offsets, double *out_xy,

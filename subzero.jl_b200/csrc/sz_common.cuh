@@ -166,6 +166,7 @@ void szk_remove_ghosts(const Launch &L, const Store &S, int n_verts_init);
 void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_floes_hint,
                     int n_pairs_hint, cudaEvent_t *ev);
 int szk_configure(const Launch &L);
+void szk_halo(const Launch &L, const Store &S, const int *idx, const long long *voff, int n, double *buf, bool pack);
 void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);
 void szk_coupling(const Launch &L, const Store &S, const Params &P);
 void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P);

@@ -323,3 +323,32 @@ void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params 
     k_update<<<(int)(blocks < cap ? blocks : cap), 256, 0, L.stream>>>(S, B, P);
     szk_count_launches(1);
 }
+
+// ---- halo exchange (slab decomposition) ------------------------------------------------------
+// record k of a list: 8 doubles (cx, cy, u, v, xi, height, status, alpha); ring points follow the records
+template <bool PACK>
+__global__ void k_halo(Store S, const int *__restrict__ idx, const long long *__restrict__ voff, int n, double *buf) {
+    double2 *vx = (double2 *)(buf + 8 * (size_t)n);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int i = idx[k];
+        double *r = buf + 8 * (size_t)k;
+        const int vs = S.vstart[i], nv = S.vcount[i];
+        double2 *v = vx + voff[k];
+        if (PACK) {
+            r[0] = S.cx[i]; r[1] = S.cy[i]; r[2] = S.u[i]; r[3] = S.v[i]; r[4] = S.xi[i];
+            r[5] = S.height[i]; r[6] = (double)S.status[i]; r[7] = S.alpha[i];
+            for (int q = 0; q < nv; ++q) v[q] = S.verts[vs + q];
+        } else {
+            S.cx[i] = r[0]; S.cy[i] = r[1]; S.u[i] = r[2]; S.v[i] = r[3]; S.xi[i] = r[4];
+            S.height[i] = r[5]; S.status[i] = (int)r[6]; S.alpha[i] = r[7];
+            for (int q = 0; q < nv; ++q) S.verts[vs + q] = v[q];
+        }
+    }
+}
+void szk_halo(const Launch &L, const Store &S, const int *idx, const long long *voff, int n, double *buf, bool pack) {
+    if (n <= 0) return;
+    int blocks = (n + 127) / 128;
+    if (pack) k_halo<true><<<blocks, 128, 0, L.stream>>>(S, idx, voff, n, buf);
+    else k_halo<false><<<blocks, 128, 0, L.stream>>>(S, idx, voff, n, buf);
+    szk_count_launches(1);
+}

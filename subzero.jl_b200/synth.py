@@ -219,12 +219,34 @@ def make_field(n, scale=1.01, walls="collision", seed=None, npoints=1000, hmean=
     return f
 
 
-def setup_handle(field, lib=None, dt=10, **overrides):
-    """A handle with grid, fields, domain and the floes of `field` uploaded."""
+def tiled_model(tile, world, walls="collision"):
+    """Grid / ocean / atmosphere / domain / constants of `world` tiles side by side in x (weak scaling:
+    rank r owns the tile shifted by r L).  walls: 'collision' or 'shear' (periodic east/west)."""
+    f = Field()
+    L = tile.L
+    f.L, f.n, f.walls = L, tile.n * world, walls
+    f.grid = host.RegRectilinearGrid(0.0, world * L, 0.0, L, dx=1e4, dy=1e4)
+    g = f.grid
+    yl = np.linspace(g.y0, g.yf, g.Ny + 1)
+    prof = 0.5 * (1.0 - np.abs(2.0 * (yl - g.y0) / (g.yf - g.y0) - 1.0))
+    f.ocean = host.Ocean(g, np.repeat(prof[None, :], g.Nx + 1, axis=0), 0.0, 0.0)
+    f.atmos = host.Atmos(g, 0.0, 0.0, 0.0)
+    EW = host.PeriodicBoundary if walls == "shear" else host.CollisionBoundary
+    f.domain = host.Domain(host.CollisionBoundary(host.North, g), host.CollisionBoundary(host.South, g),
+                           EW(host.East, g), EW(host.West, g))
+    f.consts = tile.consts
+    f.floes = None
+    return f
+
+
+def setup_handle(field, lib=None, dt=10, floes=None, **overrides):
+    """A handle with grid, fields, domain and the floes of `field` (or `floes`) uploaded."""
     h = host._make_handle(lib, field.consts, dt, None, None, None, **overrides)
     g = field.grid
     h.set_grid(g.Nx, g.Ny, g.x0, g.xf, g.y0, g.yf)
     h.set_fields(field.ocean.u, field.ocean.v, field.ocean.hflx_factor, field.atmos.u, field.atmos.v)
     field.domain.push(h)
-    h.upload_floes(field.floes)
+    fl = field.floes if floes is None else floes
+    if fl is not None:
+        h.upload_floes(fl)
     return h
