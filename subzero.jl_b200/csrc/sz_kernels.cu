@@ -1125,7 +1125,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     const int maxv_s = 32, maxx_s = 16, wpb = 4;
     // thread-per-item fast path (small polygons), then warp-per-item for what it handed on, then the
     // large-polygon workspace for what that one handed on
-    k_narrow_thread<<<L.sms, TN_NT, TN_SMEM_BYTES, st>>>(S, B, P);
+    k_narrow_thread<<<2 * L.sms, TN_NT, TN_SMEM_BYTES, st>>>(S, B, P);
     k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
     k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
     k_pool_check<<<1, 1, 0, st>>>(S, B);

@@ -17,8 +17,8 @@
 #define TN_MAXV 11   // ring points incl. the closing point (<= 10 edges)
 #define TN_MAXX 4    // crossings per clip
 #define TN_MAXREG 2  // regions per clip
-#define TN_RCAP 26   // points of all regions of one clip
-#define TN_MAXIP 8   // raw intersection points
+#define TN_RCAP 24   // region points of clip #1 AND clip #2 together (they share one buffer)
+#define TN_MAXIP 6   // intersection points
 #define TN_MAXC 24   // edge pairs whose P edge straddles the Q edge's line
 
 enum { TN_OK = 0, TN_DEFER = 1 };
@@ -150,7 +150,7 @@ __device__ __noinline__ bool t_rings_intersect(const TRing A, const TRing B) {
 // `xp_out` / `generic`: when no orientation value was exactly zero the crossing points ARE
 // GO.intersection_points(P, Q) (closed-segment intersection == proper crossing), in the same
 // (e, f) order; the caller then skips the separate 4 np nq pass.
-__device__ __noinline__ int t_clip(const TRing P, const TRing Q, double2 *R, int *rs, int *re, int &status,
+__device__ __noinline__ int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, int *rs, int *re, int &status,
                                    double2 *xp_out, int *K_out, bool *generic) {
     const int np = P.n - 1, nq = Q.n - 1;
     status = TN_OK;
@@ -244,6 +244,10 @@ __device__ __noinline__ int t_clip(const TRing P, const TRing Q, double2 *R, int
         bool qin = pin ? false : t_point_in_ring_p(tget(Q, 0), P);
         if (!pin && !qin) return 0;
         const TRing src = pin ? P : Q;
+        if (src.n > rcap) {
+            status = TN_DEFER;
+            return 0;
+        }
         for (int k = 0; k < src.n; ++k) R[k * TN_NT] = tget(src, k);
         rs[0] = 0;
         re[0] = src.n;
@@ -273,7 +277,7 @@ __device__ __noinline__ int t_clip(const TRing P, const TRing Q, double2 *R, int
         double2 _p = (pt);                                                                           \
         double2 _l = npts > start ? R[(npts - 1) * TN_NT] : make_double2(0.0, 0.0);                  \
         if (!(npts > start && _l.x == _p.x && _l.y == _p.y)) {                                       \
-            if (npts >= TN_RCAP - 1) {                                                               \
+            if (npts >= rcap - 1) {                                                                  \
                 status = TN_DEFER;                                                                   \
                 return 0;                                                                            \
             }                                                                                        \
@@ -461,6 +465,7 @@ __device__ __noinline__ double t_many_intersect_normal(double dir[2], const TRin
 
 struct TWs {
     double2 *P, *Q, *R1, *R2, *ip;  // [cap][TN_NT], already offset by the thread index
+    int r2cap;                      // R2 = the part of the region buffer clip #1 left free
 };
 
 // calc_normal_force, collisions.jl:30-70
@@ -486,7 +491,7 @@ __device__ __noinline__ double t_normal_force(const TWs w, const TRing P, const 
         P2.sx = dir[0];
         P2.sy = dir[1];
         int rs2[TN_MAXREG], re2[TN_MAXREG];
-        int nreg2 = t_clip(P2, Q, w.R2, rs2, re2, status, nullptr, nullptr, nullptr);
+        int nreg2 = t_clip(P2, Q, w.R2, w.r2cap, rs2, re2, status, nullptr, nullptr, nullptr);
         if (status != TN_OK) return 0.0;
         for (int r = 0; r < nreg2; ++r) {
             TRing nr = tring(w.R2 + rs2[r] * TN_NT, re2[r] - rs2[r]);
@@ -502,7 +507,7 @@ __device__ __noinline__ double t_normal_force(const TWs w, const TRing P, const 
 }
 
 // One work item, one thread.  Returns false when the item must go to the warp kernel.
-__device__ bool thread_item(const TWs w, const Store &S, const StepBuf &B, const Params &P, int slot) {
+__device__ bool thread_item(TWs w, const Store &S, const StepBuf &B, const Params &P, int slot) {
     Counters *cnt = S.cnt;
     const DomainDev *D = S.dom;
     const bool is_pair = slot < B.cap_pairs;
@@ -550,8 +555,14 @@ __device__ bool thread_item(const TWs w, const Store &S, const StepBuf &B, const
     double area1[TN_MAXREG];
     int K1 = 0;
     bool generic = false;
-    int nreg = t_clip(Pr, Qr, w.R1, rs1, re1, status, w.ip, &K1, &generic);
+    int nreg = t_clip(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, w.ip, &K1, &generic);
     if (status != TN_OK) return false;
+    {
+        int used = 0;
+        for (int r = 0; r < nreg; ++r) used = max(used, re1[r]);
+        w.R2 = w.R1 + used * TN_NT;
+        w.r2cap = TN_RCAP - used;
+    }
     double total = 0.0, max_area = 0.0;
     for (int r = 0; r < nreg; ++r) {
         area1[r] = t_area(tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]));
@@ -663,9 +674,9 @@ __device__ bool thread_item(const TWs w, const Store &S, const StepBuf &B, const
     return true;
 }
 
-#define TN_SMEM_BYTES (sizeof(double2) * TN_NT * (2 * TN_MAXV + 2 * TN_RCAP + TN_MAXIP))
+#define TN_SMEM_BYTES (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))
 
-__global__ void __launch_bounds__(TN_NT, 1) k_narrow_thread(Store S, StepBuf B, Params P) {
+__global__ void __launch_bounds__(TN_NT, 2) k_narrow_thread(Store S, StepBuf B, Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -674,8 +685,9 @@ __global__ void __launch_bounds__(TN_NT, 1) k_narrow_thread(Store S, StepBuf B, 
     w.P = base;
     w.Q = w.P + TN_MAXV * TN_NT;
     w.R1 = w.Q + TN_MAXV * TN_NT;
-    w.R2 = w.R1 + TN_RCAP * TN_NT;
-    w.ip = w.R2 + TN_RCAP * TN_NT;
+    w.R2 = w.R1;
+    w.r2cap = 0;
+    w.ip = w.R1 + TN_RCAP * TN_NT;
     const int np = cnt->n_cand, total = np + cnt->n_dom;
     for (int it = blockIdx.x * TN_NT + threadIdx.x; it < total; it += gridDim.x * TN_NT) {
         int slot = it < np ? it : B.cap_pairs + (it - np);
