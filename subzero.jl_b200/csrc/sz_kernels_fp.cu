@@ -183,12 +183,22 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
     const int n = S.n_init;
     for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
         uint32_t warn = 0;
+        // every per-floe scalar is loaded up front: ~30 independent broadcast loads in flight instead of a
+        // chain of exposed latencies (ncu r1e: long_scoreboard on each first use)
         double cfx = S.cfx[i], cfy = S.cfy[i], ctrq = S.ctrq[i];
         const double cx = S.cx[i], cy = S.cy[i], area = S.area[i];
-        double height = S.height[i];
+        double height = S.height[i], mass = S.mass[i], moment = S.moment[i];
+        const double hflx = S.hflx[i], u0 = S.u[i], v0 = S.v[i], xi0 = S.xi[i], alpha0 = S.alpha[i];
+        const double pdx = S.p_dxdt[i], pdy = S.p_dydt[i], pda = S.p_dalphadt[i];
+        const double pdu = S.p_dudt[i], pdv = S.p_dvdt[i], pdxi = S.p_dxidt[i];
+        const double fxOA = S.fxOA[i], fyOA = S.fyOA[i], trqOA = S.trqOA[i];
+        const double acc_old = lane < 4 ? S.stress_accum[4 * i + lane] : 0.0;
+        const int r0 = B.row_off[i], r1 = B.row_off[i + 1];
+        const int vs = S.vstart[i], nv = S.vcount[i];
+        double2 pv0 = lane < nv ? S.verts[vs + lane] : make_double2(0.0, 0.0);
+        double2 pv1 = lane + 1 < nv ? S.verts[vs + lane + 1] : make_double2(0.0, 0.0);
         // calc_stress!, :392-414 (pre-move centroid)
         double s11 = 0, s12 = 0, s22 = 0;
-        int r0 = B.row_off[i], r1 = B.row_off[i + 1];
         if (r1 > r0) {
             for (int k = r0; k < r1; ++k) {
                 const double *r = B.rows + (size_t)k * NCOL;
@@ -203,18 +213,16 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
             s12 *= inv;
             s22 *= inv;
         }
-        double stv[4] = {s11, s12, s12, s22};
         double lam = P.cfg.stress_lambda;  // stress_calculators.jl:118-122
         if (lane < 4) {
-            double sv = lane == 0 ? stv[0] : (lane == 3 ? stv[3] : stv[1]);
-            S.stress_accum[4 * i + lane] = (1 - lam) * S.stress_accum[4 * i + lane] + lam * sv;
+            double sv = lane == 0 ? s11 : (lane == 3 ? s22 : s12);
+            S.stress_accum[4 * i + lane] = (1 - lam) * acc_old + lam * sv;
             S.stress_instant[4 * i + lane] = sv;
         }
         if (height > P.cfg.max_floe_height) {  // :482-485
             height = P.cfg.max_floe_height;
             warn |= SZ_WARN_HEIGHT_CAPPED;
         }
-        double mass = S.mass[i], moment = S.moment[i];
         while (fmax(fabs(cfx), fabs(cfy)) > mass / (5 * dt)) {  // :487-491
             cfx = cfx / 10;
             cfy = cfy / 10;
@@ -222,24 +230,23 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
             warn |= SZ_WARN_FORCE_SCALED;
         }
         double hh = height;  // :494-500
-        double dh = S.hflx[i] / hh;
+        double dh = hflx / hh;
         double hfrac = (hh + dh) / hh;
         mass *= hfrac;
         moment *= hfrac;
         height -= dh;
         hh = height;
-        const double u0 = S.u[i], v0 = S.v[i], xi0 = S.xi[i];
-        double Dx = 1.5 * dt * u0 - 0.5 * dt * S.p_dxdt[i];  // :503-506
-        double Dy = 1.5 * dt * v0 - 0.5 * dt * S.p_dydt[i];
-        double Da = 1.5 * dt * xi0 - 0.5 * dt * S.p_dalphadt[i];
+        double Dx = 1.5 * dt * u0 - 0.5 * dt * pdx;  // :503-506
+        double Dy = 1.5 * dt * v0 - 0.5 * dt * pdy;
+        double Da = 1.5 * dt * xi0 - 0.5 * dt * pda;
         // _move_floe! / _move_poly, floe_utils.jl:74-93: p -> R p + ((R(-c) + c) + D)
         double sn, cs;
         sincos(Da, &sn, &cs);
         double tx = ((cs * (-cx) - sn * (-cy)) + cx) + Dx;
         double ty = ((sn * (-cx) + cs * (-cy)) + cy) + Dy;
         const double ncx = cx + Dx, ncy = cy + Dy;
-        double dudt = (S.fxOA[i] + cfx) / mass;  // :514-531
-        double dvdt = (S.fyOA[i] + cfy) / mass;
+        double dudt = (fxOA + cfx) / mass;  // :514-531
+        double dvdt = (fyOA + cfy) / mass;
         double frac = 1;
         double au = fabs(dt * dudt), av = fabs(dt * dvdt), lim = hh / 2;
         double sgu = (double)((dudt > 0) - (dudt < 0)), sgv = (double)((dvdt > 0) - (dvdt < 0));
@@ -253,25 +260,24 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
             dvdt = frac * dvdt;
             warn |= SZ_WARN_VELOCITY_LIMITED;
         }
-        const double un = u0 + (1.5 * dt * dudt - 0.5 * dt * S.p_dudt[i]);  // :532-535
-        const double vn = v0 + (1.5 * dt * dvdt - 0.5 * dt * S.p_dvdt[i]);
-        double dxidt = (S.trqOA[i] + ctrq) / moment;  // :537-545
+        const double un = u0 + (1.5 * dt * dudt - 0.5 * dt * pdu);  // :532-535
+        const double vn = v0 + (1.5 * dt * dvdt - 0.5 * dt * pdv);
+        double dxidt = (trqOA + ctrq) / moment;  // :537-545
         dxidt = frac * dxidt;
-        double xin = xi0 + 1.5 * dt * dxidt - 0.5 * dt * S.p_dxidt[i];
+        double xin = xi0 + 1.5 * dt * dxidt - 0.5 * dt * pdxi;
         if (fabs(xin) > P.cfg.maximum_xi) {
             xin = (double)((xin > 0) - (xin < 0)) * P.cfg.maximum_xi;
             warn |= SZ_WARN_XI_CLAMPED;
         }
         // rigid move of the ring + calc_strain! on the moved ring with the updated u, xi
-        const int vs = S.vstart[i], nv = S.vcount[i];
         double e11 = 0, e12 = 0, e22 = 0;
         for (int base = 0; base < nv; base += 32) {
             const int k = base + lane;
             const bool act = k < nv;
-            double2 p = act ? S.verts[vs + k] : make_double2(0.0, 0.0);
+            double2 p = base == 0 ? pv0 : (act ? S.verts[vs + k] : make_double2(0.0, 0.0));
             double2 q = make_double2((cs * p.x - sn * p.y) + tx, (sn * p.x + cs * p.y) + ty);
             if (k + 1 < nv) {
-                double2 p2 = S.verts[vs + k + 1];
+                double2 p2 = base == 0 ? pv1 : S.verts[vs + k + 1];
                 double2 q2 = make_double2((cs * p2.x - sn * p2.y) + tx, (sn * p2.x + cs * p2.y) + ty);
                 double x1 = q.x - ncx, y1 = q.y - ncy, x2 = q2.x - ncx, y2 = q2.y - ncy;
                 double xd = x2 - x1, yd = y2 - y1;
@@ -292,15 +298,15 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
         }
         if (lane == 0) {
             e12 *= 0.5;
-            double den = 2 * area;
-            S.strain[4 * i + 0] = e11 / den;
-            S.strain[4 * i + 1] = e12 / den;
-            S.strain[4 * i + 2] = e12 / den;
-            S.strain[4 * i + 3] = e22 / den;
+            double iden = 1.0 / (2 * area);
+            S.strain[4 * i + 0] = e11 * iden;
+            S.strain[4 * i + 1] = e12 * iden;
+            S.strain[4 * i + 2] = e12 * iden;
+            S.strain[4 * i + 3] = e22 * iden;
             S.height[i] = height;
             S.mass[i] = mass;
             S.moment[i] = moment;
-            S.alpha[i] = S.alpha[i] + Da;
+            S.alpha[i] = alpha0 + Da;
             S.cx[i] = ncx;
             S.cy[i] = ncy;
             S.p_dxdt[i] = u0;  // :509-511
