@@ -58,6 +58,8 @@ struct Counters {
     int n_overlap;
     int n_large;   // work items deferred to the large-polygon kernel
     int n_mid;     // work items the thread-per-item kernel handed to the warp-per-item kernel
+    int n_order;   // work items of the thread-per-item kernels (class-sorted)
+    int n_force;   // ... of which need contact forces (phase 1)
     uint32_t error;
     int want_pairs, want_pool, want_rows, want_floes, want_verts, want_dom, want_fuse;  // sizes asked for on overflow
     int gnx, gny;
@@ -140,6 +142,9 @@ struct StepBuf {
     double *pool;        // [cap_pool][NPOOL] = fx, fy, px, py, overlap
     int *large_items;    // [cap_pairs + cap_dom] work list of the large-polygon kernel
     int *mid_items;      // [cap_pairs + cap_dom] work list of the warp-per-item kernel
+    int *order;          // [cap_pairs + cap_dom] items sorted by (edges of P, edges of Q)
+    int *force_items;    // [cap_pairs + cap_dom] items that need contact forces
+    int *class_count, *class_base, *class_cursor;  // [64] counting sort of the work items
     // per-floe rows
     int *row_pre, *row_count, *row_off;  // [cap_floes+1]
     double *rows;                        // [cap_rows][7]

@@ -1125,7 +1125,12 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     const int maxv_s = 32, maxx_s = 16, wpb = 4;
     // thread-per-item fast path (small polygons), then warp-per-item for what it handed on, then the
     // large-polygon workspace for what that one handed on
-    k_narrow_thread<<<2 * L.sms, TN_NT, TN_SMEM_BYTES, st>>>(S, B, P);
+    int gi = grid_for(L, (long long)pairs_hint + n_hint / 8 + 64, 256);
+    k_item_count<<<gi, 256, 0, st>>>(S, B);
+    k_class_scan<<<1, 1, 0, st>>>(S, B);
+    k_item_scatter<<<gi, 256, 0, st>>>(S, B);
+    k_narrow_ab<0><<<2 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, B, P);
+    k_narrow_ab<1><<<2 * L.sms, TN_NT, TN_SMEM_B, st>>>(S, B, P);
     k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
     k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
     k_pool_check<<<1, 1, 0, st>>>(S, B);
@@ -1139,7 +1144,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_row_write<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
     k_update_boundaries<<<1, 1, 0, st>>>(S, P);
     if (ev) cudaEventRecord(ev[2], st);
-    g_launch_count += 23;  // + 5 scans counted in scan_excl
+    g_launch_count += 27;  // + 5 scans counted in scan_excl
 }
 
 // ---- geometry service / test hook -------------------------------------------------------------------------------------------
@@ -1214,6 +1219,7 @@ int szk_configure(const Launch &L) {
     if (cudaFuncSetAttribute(k_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_ghost_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_debug_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(k_narrow_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_BYTES) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_narrow_ab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_narrow_ab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_B) != cudaSuccess) return -1;
     return 0;
 }

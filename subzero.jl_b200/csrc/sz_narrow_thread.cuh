@@ -509,8 +509,11 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
     return dl;
 }
 
-// One work item, one thread.  Returns false when the item must go to the warp kernel.
-__device__ bool thread_item(TWs w, const Store &S, const StepBuf &B, const Params &P, int slot) {
+// One work item, one thread.  phase 0 (k_narrow_a): clip #1, areas and the fuse / remove decisions; an
+// item that needs contact forces is handed to phase 1 (k_narrow_b), which repeats clip #1 (cheap next to the
+// force part) and computes the rows.  Returns TI_DONE, TI_WARP (the warp kernel must take it) or TI_FORCES.
+enum { TI_DONE = 0, TI_WARP = 1, TI_FORCES = 2 };
+__device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params &P, int slot, int phase) {
     Counters *cnt = S.cnt;
     const DomainDev *D = S.dom;
     const bool is_pair = slot < B.cap_pairs;
@@ -536,7 +539,7 @@ __device__ bool thread_item(TWs w, const Store &S, const StepBuf &B, const Param
         nqp = S.topo_vcount[elem - 4];
         gQ = S.topo_verts + S.topo_vstart[elem - 4];
     }
-    if (npp > TN_MAXV || nqp > TN_MAXV) return false;
+    if (npp > TN_MAXV || nqp > TN_MAXV) return TI_WARP;
     {
         const double2 *gP = S.verts + S.vstart[fi];
         for (int k = 0; k < npp; ++k) w.P[k * TN_NT] = gP[k];
@@ -558,8 +561,9 @@ __device__ bool thread_item(TWs w, const Store &S, const StepBuf &B, const Param
     double area1[TN_MAXREG];
     int K1 = 0;
     bool generic = false;
-    int nreg = t_clip(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, w.ip, &K1, &generic);
-    if (status != TN_OK) return false;
+    int nreg = phase == 0 ? t_clip(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, nullptr, nullptr, nullptr)
+                          : t_clip(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, w.ip, &K1, &generic);
+    if (status != TN_OK) return TI_WARP;
     {
         int used = 0;
         for (int r = 0; r < nreg; ++r) used = max(used, re1[r]);
@@ -608,13 +612,14 @@ __device__ bool thread_item(TWs w, const Store &S, const StepBuf &B, const Param
             }
         }
     }
+    if (forces && phase == 0) return TI_FORCES;
     double rows[TN_MAXREG][NPOOL];
     int nrows = 0;
     if (forces) {
         // calc_elastic_forces, collisions.jl:149-188
         // GO.intersection_points: the crossing points of clip #1 when the configuration is generic
         int nip = generic ? K1 : t_intersection_points(Pr, Qr, w.ip, status);
-        if (status != TN_OK) return false;
+        if (status != TN_OK) return TI_WARP;
         if (nip >= 2) {
             int n1 = npp - 1, n2 = nqp - 1;
             double min_area = (double)((n1 < n2 ? n1 : n2) * 100) / 1.75;
@@ -629,7 +634,7 @@ __device__ bool thread_item(TWs w, const Store &S, const StepBuf &B, const Param
                     c[3] = ce.y;
                     double force[2];
                     c[5] = t_normal_force(w, Pr, Qr, reg, area1[r], nip, ff, force, status);
-                    if (status != TN_OK) return false;
+                    if (status != TN_OK) return TI_WARP;
                     c[0] = force[0];
                     c[1] = force[1];
                 }
@@ -674,12 +679,98 @@ __device__ bool thread_item(TWs w, const Store &S, const StepBuf &B, const Param
         if (s < B.cap_fuse) B.fuse_pairs[s] = make_int2(fi, fj);
         else atomicOr(&cnt->error, ERR_FUSE_CAP);
     }
-    return true;
+    return TI_DONE;
 }
 
-#define TN_SMEM_BYTES (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))
+#define TN_SMEM_A (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP))
+#define TN_SMEM_B (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))
+#define TN_NCLASS 64  // (edges of P - 3) * 8 + (edges of Q - 3), rings of 3..10 edges
 
-__global__ void __launch_bounds__(TN_NT, 2) k_narrow_thread(Store S, StepBuf B, Params P) {
+// ---- work-item ordering -----------------------------------------------------------------------------
+// A warp of the thread-per-item kernels runs 32 items in lockstep, so its speed is set by the LARGEST
+// rings among them (ncu r1e: 10 of 32 lanes active).  Items are therefore counting-sorted by the pair
+// (edge count of P, edge count of Q): all lanes of a warp then walk identical loop trip counts.
+__device__ __forceinline__ int item_slot(const StepBuf &B, int it, int np) { return it < np ? it : B.cap_pairs + (it - np); }
+// -1: nothing to do (filtered pair), TN_NCLASS: too large for the thread kernels, else the class
+__device__ __forceinline__ int item_class(const Store &S, const StepBuf &B, int it, int np) {
+    int ep, eq;
+    if (it < np) {
+        if (!B.keep[it]) return -1;
+        ep = S.vcount[B.pair_i[it]] - 1;
+        eq = S.vcount[B.pair_j[it]] - 1;
+    } else {
+        int q = it - np, elem = B.dom_elem[q];
+        ep = S.vcount[B.dom_floe[q]] - 1;
+        eq = elem < 4 ? 4 : S.topo_vcount[elem - 4] - 1;
+    }
+    if (ep + 1 > TN_MAXV || eq + 1 > TN_MAXV) return TN_NCLASS;
+    return (ep - 3) * 8 + (eq - 3);
+}
+
+__global__ void __launch_bounds__(256) k_item_count(Store S, StepBuf B) {
+    __shared__ int hist[TN_NCLASS];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    for (int k = threadIdx.x; k < TN_NCLASS; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    const int np = cnt->n_cand, total = np + cnt->n_dom;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+        int c = item_class(S, B, it, np), slot = item_slot(B, it, np);
+        if (c < 0) {
+            B.item_nrows[slot] = 0;
+            B.item_flags[slot] = 0;
+        } else if (c == TN_NCLASS) {
+            B.mid_items[atomicAdd(&cnt->n_mid, 1)] = slot;
+            B.item_nrows[slot] = 0;
+            B.item_flags[slot] = IT_NEEDLARGE;
+        } else {
+            atomicAdd(&hist[c], 1);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < TN_NCLASS; k += blockDim.x)
+        if (hist[k]) atomicAdd(&B.class_count[k], hist[k]);
+}
+
+__global__ void k_class_scan(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int run = 0;
+    for (int k = 0; k < TN_NCLASS; ++k) {
+        B.class_base[k] = run;
+        B.class_cursor[k] = run;
+        run += B.class_count[k];
+        B.class_count[k] = 0;  // ready for the next step
+    }
+    cnt->n_order = run;
+    cnt->n_force = 0;
+}
+
+__global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
+    __shared__ int hist[TN_NCLASS], base[TN_NCLASS];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int np = cnt->n_cand, total = np + cnt->n_dom;
+    // block-strided chunks: rank inside the block first, then one global reservation per class and block
+    for (int start = blockIdx.x * blockDim.x; start < total; start += gridDim.x * blockDim.x) {
+        for (int k = threadIdx.x; k < TN_NCLASS; k += blockDim.x) hist[k] = 0;
+        __syncthreads();
+        int it = start + threadIdx.x, c = -1, rank = 0;
+        if (it < total) {
+            c = item_class(S, B, it, np);
+            if (c >= 0 && c < TN_NCLASS) rank = atomicAdd(&hist[c], 1);
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < TN_NCLASS; k += blockDim.x)
+            if (hist[k]) base[k] = atomicAdd(&B.class_cursor[k], hist[k]);
+        __syncthreads();
+        if (c >= 0 && c < TN_NCLASS) B.order[base[c] + rank] = item_slot(B, it, np);
+        __syncthreads();
+    }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(TN_NT, 2) k_narrow_ab(Store S, StepBuf B, Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -690,20 +781,31 @@ __global__ void __launch_bounds__(TN_NT, 2) k_narrow_thread(Store S, StepBuf B, 
     w.R1 = w.Q + TN_MAXV * TN_NT;
     w.R2 = w.R1;
     w.r2cap = 0;
-    w.ip = w.R1 + TN_RCAP * TN_NT;
-    const int np = cnt->n_cand, total = np + cnt->n_dom;
-    for (int it = blockIdx.x * TN_NT + threadIdx.x; it < total; it += gridDim.x * TN_NT) {
-        int slot = it < np ? it : B.cap_pairs + (it - np);
-        if (it < np && !B.keep[it]) {
-            B.item_nrows[slot] = 0;
-            B.item_flags[slot] = 0;
-            continue;
+    w.ip = w.R1 + TN_RCAP * TN_NT;  // phase 1 only
+    const int total = PHASE == 0 ? cnt->n_order : cnt->n_force;
+    const int *list = PHASE == 0 ? B.order : B.force_items;
+    const int lane = threadIdx.x & 31;
+    for (int base_it = blockIdx.x * TN_NT + (threadIdx.x & ~31); base_it < total; base_it += gridDim.x * TN_NT) {
+        const int it = base_it + lane;
+        int rc = TI_DONE, slot = -1;
+        if (it < total) {
+            slot = list[it];
+            rc = thread_item(w, S, B, P, slot, PHASE);
         }
-        if (!thread_item(w, S, B, P, slot)) {
-            int s = atomicAdd(&cnt->n_mid, 1);
-            B.mid_items[s] = slot;
+        if (rc == TI_WARP) {
+            B.mid_items[atomicAdd(&cnt->n_mid, 1)] = slot;
             B.item_nrows[slot] = 0;
             B.item_flags[slot] = IT_NEEDLARGE;
+        }
+        if (PHASE == 0) {
+            // warp-aggregated append: the force list keeps the (class-sorted) order warp by warp
+            unsigned m = __ballot_sync(0xffffffffu, rc == TI_FORCES);
+            if (m) {
+                int b0 = 0;
+                if (lane == 0) b0 = atomicAdd(&cnt->n_force, __popc(m));
+                b0 = __shfl_sync(0xffffffffu, b0, 0);
+                if (rc == TI_FORCES) B.force_items[b0 + __popc(m & ((1u << lane) - 1))] = slot;
+            }
         }
     }
 }
