@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=25000, help="floes of the cpu_baseline sample field")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--skin", type=float, default=3000.0, help="halo-list skin in metres (N > 1): lists stay valid while floes moved < skin/2")
     return ap.parse_args()
 
 
@@ -205,7 +206,7 @@ def main():
         slab.shift_x(tile.floes, rank * tile.L)
         ew = "shear" if args.walls in ("shear", "periodic") else "collision"
         f = synth.tiled_model(tile, world, ew)
-        me = slab.partition_tiles(tile.floes, rank, world, tile.L, world * tile.L if ew == "shear" else None, skin=500.0)
+        me = slab.partition_tiles(tile.floes, rank, world, tile.L, world * tile.L if ew == "shear" else None, skin=args.skin)
         h = synth.setup_handle(f, prod, device=local_rank)
         me.attach(h)
         me.make_buffers(torch.device("cuda", local_rank))
@@ -274,12 +275,13 @@ def main():
         e2e = {"value": ne / float(te[0]), "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "call": "sz_upload_state + sz_step + sz_download_floes on pinned host arrays"}
 
-    stale = bool(me.stale()) if me is not None else False
     halo = None
     if me is not None:
-        hs = torch.tensor([me.local.n - int(me.owned.sum()), sum(me.nbytes[0::2]), int(stale)], dtype=torch.float64, device="cuda")
+        disp = me.max_displacement()
+        hs = torch.tensor([me.local.n - int(me.owned.sum()), sum(me.nbytes[0::2]), disp], dtype=torch.float64, device="cuda")
         dist.all_reduce(hs, op=dist.ReduceOp.MAX)
-        halo = {"halo_floes_max": int(hs[0]), "send_bytes_per_step_max": int(hs[1]), "lists_stale": bool(hs[2]),
+        halo = {"halo_floes_max": int(hs[0]), "send_bytes_per_step_max": int(hs[1]), "skin_m": args.skin,
+                "max_displacement_m": float(hs[2]), "lists_stale": bool(hs[2] > 0.5 * args.skin),
                 "exchange": "sz_halo_pack -> NCCL isend/irecv (torch.distributed) -> sz_halo_unpack, every step"}
     if rank != 0:
         if world > 1:

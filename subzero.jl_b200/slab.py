@@ -176,6 +176,9 @@ class SlabRank:
 
     def stale(self):
         """True when an owned floe travelled more than skin / 2 since the lists were built."""
+        return self.max_displacement() > 0.5 * self.skin
+
+    def max_displacement(self):
         fa = self.h.download_floes(mc=False)
         dx = np.abs(fa.centroid_x[:self.local.n] - self.x0)
         dy = np.abs(fa.centroid_y[:self.local.n] - self.y0)
@@ -183,7 +186,8 @@ class SlabRank:
             dx = np.minimum(dx, np.abs(dx - self.period_x))
         if self.period_y:
             dy = np.minimum(dy, np.abs(dy - self.period_y))
-        return bool(np.any(np.hypot(dx, dy)[self.owned] > 0.5 * self.skin))
+        d = np.hypot(dx, dy)[self.owned]
+        return float(d.max()) if len(d) else 0.0
 
 
 def exchange_local(ranks):

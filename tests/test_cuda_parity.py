@@ -77,6 +77,65 @@ def test_fused_step_matches_phases(walls, product_lib, oracle_lib):
     assert rel_err(a.centroid_x, b.centroid_x) < 1e-6 and rel_err(a.u, b.u) < 1e-4
 
 
+def special_domain_field(n=900):
+    """Moving north/south walls, an open west wall, two topography elements cut out of the floe
+    field, plus floes that trigger every guard of the state update (height cap, force scaling,
+    velocity limiter, xi clamp: update_floe.jl:482-543)."""
+    from subzero_jl_b200 import host, slab
+    f = synth.make_field(n, scale=1.02, walls="collision", npoints=60, cache=False)
+    fields.perturb_state(f.floes)
+    c = np.hypot(f.floes.centroid_x - 0.5 * f.L, f.floes.centroid_y - 0.5 * f.L)
+    topo_idx = np.argsort(c)[[3, 40]]
+    topo = host.initialize_topography_field([[f.floes.ring(i).tolist()] for i in topo_idx])
+    keep = np.setdiff1d(np.arange(n), topo_idx)
+    f.floes = slab.extract(f.floes, keep)
+    f.floes.id = np.arange(1, f.floes.n + 1, dtype=np.int64)
+    g = f.grid
+    f.domain = host.Domain(host.MovingBoundary(host.North, g, u=0.0, v=-0.3), host.MovingBoundary(host.South, g, u=0.05, v=0.2),
+                           host.CollisionBoundary(host.East, g), host.OpenBoundary(host.West, g), topography=topo)
+    fa = f.floes
+    fa.height[5] = 12.0          # capped to max_floe_height
+    fa.xi[7] = 9.9e-6            # clamped after the update
+    fa.p_dxidt[7] = -1e-6
+    fa.fxOA[11], fa.fyOA[11] = 5e9, -7e9   # velocity limiter (only kept when coupling is skipped)
+    return f
+
+
+@pytest.mark.parametrize("coupling", [True, False])
+def test_moving_walls_topography_open_wall_and_guards(coupling, product_lib, oracle_lib):
+    f = special_domain_field()
+    hg, ho = handles(f, product_lib, oracle_lib)
+    for h in (hg, ho):
+        h.add_ghosts()
+        h.step_collisions()
+    assert_ok(compare_collision_outputs(hg, ho))
+    offs, rows = ho.interactions()
+    ids = set(rows[rows[:, 0] < 0, 0].astype(int).tolist())
+    assert {-1, -2, -3, -5, -6} <= ids, ids  # moving walls, collision wall, both topography elements
+    vg, rg = hg.get_domain()
+    vo, ro = ho.get_domain()
+    assert np.array_equal(vg, vo) and np.array_equal(rg, ro) and vo[0] != f.L  # walls moved (collisions.jl:565-571)
+    a, b = hg.download_floes(), ho.download_floes()
+    assert np.array_equal(a.status_tag, b.status_tag) and (b.status_tag == capi.STATUS_REMOVE).any()  # open wall
+    for h in (hg, ho):
+        h.remove_ghosts()
+        if coupling:
+            h.step_coupling()
+        h.step_floe_properties(0)
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes()))
+    wg, wo = hg.warnings(), ho.warnings()
+    assert np.array_equal(wg, wo)
+    assert wo[5] & capi.WARN_HEIGHT_CAPPED and wo[7] & capi.WARN_XI_CLAMPED
+    assert (wo & capi.WARN_FORCE_SCALED).any()
+    if not coupling:
+        assert wo[11] & capi.WARN_VELOCITY_LIMITED
+    # a second full step from the moved state (moving walls advanced, floes moved); identical start state
+    hg.upload_floes(ho.download_floes())
+    hg.step(1, True)
+    ho.step(1, True)
+    assert_ok(compare_state(hg.download_floes(), ho.download_floes()))
+
+
 def test_nonconvex_fixture_shapes(product_lib, oracle_lib):
     """The reference's own 462 floe shapes (7-591 vertices, non-convex): multi-region clips,
     the large-polygon kernel, wall contacts."""
