@@ -130,17 +130,23 @@ __device__ TN_FN double t_point_ring_distance(double2 p, const TRing r) {
     }
     return best;
 }
+// NOTE on control flow in this file: no `return` / `break` out of nested loops.  ncu (profiles/r1f)
+// showed 4-5 active lanes in the region trace: a divergent lane that leaves through an early return only
+// reconverges at the function exit.  Failures set a flag, loops run to a structured exit.
 __device__ TN_FN bool t_rings_intersect(const TRing A, const TRing B) {
-    for (int e = 0; e + 1 < A.n; ++e) {
+    bool hit = false;
+    for (int e = 0; e + 1 < A.n && !hit; ++e) {
         double2 a = tget(A, e), b = tget(A, e + 1);
+        double2 c = tget(B, 0);
         for (int f = 0; f + 1 < B.n; ++f) {
-            double2 p0, p1;
-            if (segment_intersection(a, b, tget(B, f), tget(B, f + 1), p0, p1) > 0) return true;
+            double2 d = tget(B, f + 1), p0, p1;
+            hit |= segment_intersection(a, b, c, d, p0, p1) > 0;
+            c = d;
         }
     }
-    if (t_point_coveredby(tget(A, 0), B)) return true;
-    if (t_point_coveredby(tget(B, 0), A)) return true;
-    return false;
+    if (!hit) hit = t_point_coveredby(tget(A, 0), B);
+    if (!hit) hit = t_point_coveredby(tget(B, 0), A);
+    return hit;
 }
 
 // intersect_polys for one thread; regions go to R ([point][thread]) as closed rings
@@ -170,7 +176,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     // side bit changes from vertex e to e+1 are appended to a short candidate list in (e, f) order
     unsigned char ce[TN_MAXC], cf[TN_MAXC];
     int nc = 0;
-    bool anyzero = false;
+    bool anyzero = false, fail = false;
     {
         unsigned first = 0, prev = 0;
         for (int v = 0; v <= np; ++v) {
@@ -196,12 +202,12 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                     int f = __ffs(chg) - 1;
                     chg &= chg - 1;
                     if (nc == TN_MAXC) {
-                        status = TN_DEFER;
-                        return 0;
+                        fail = true;
+                    } else {
+                        ce[nc] = (unsigned char)(v - 1);
+                        cf[nc] = (unsigned char)f;
+                        nc++;
                     }
-                    ce[nc] = (unsigned char)(v - 1);
-                    cf[nc] = (unsigned char)f;
-                    nc++;
                 }
             }
             prev = cur;
@@ -216,22 +222,27 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
         anyzero |= (o3 == 0.0) | (o4 == 0.0);
         bool sc = side_p(o3, a, b), sd = side_p(o4, a, b);
-        if (sc == sd) continue;
-        if (K == TN_MAXX) {
-            status = TN_DEFER;
-            return 0;
+        if (sc != sd) {
+            if (K == TN_MAXX) {
+                fail = true;
+            } else {
+                double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
+                bool sb = side_q(o2, c, d);
+                double t = o1 / (o1 - o2);
+                xe[K] = e;
+                xf[K] = f;
+                xt[K] = t;
+                xs[K] = o3 / (o3 - o4);
+                xp[K] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
+                xent[K] = (sb == q_ccw);
+                xvis[K] = false;
+                K++;
+            }
         }
-        double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
-        bool sb = side_q(o2, c, d);
-        double t = o1 / (o1 - o2);
-        xe[K] = e;
-        xf[K] = f;
-        xt[K] = t;
-        xs[K] = o3 / (o3 - o4);
-        xp[K] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
-        xent[K] = (sb == q_ccw);
-        xvis[K] = false;
-        K++;
+    }
+    if (fail) {
+        status = TN_DEFER;
+        return 0;
     }
     if (K_out) {
         bool dup = false;
@@ -280,84 +291,93 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         double2 _p = (pt);                                                                           \
         double2 _l = npts > start ? R[(npts - 1) * TN_NT] : make_double2(0.0, 0.0);                  \
         if (!(npts > start && _l.x == _p.x && _l.y == _p.y)) {                                       \
-            if (npts >= rcap - 1) {                                                                  \
-                status = TN_DEFER;                                                                   \
-                return 0;                                                                            \
-            }                                                                                        \
-            R[(npts++) * TN_NT] = _p;                                                                \
+            if (npts >= rcap - 1) fail = true;                                                       \
+            else R[(npts++) * TN_NT] = _p;                                                           \
         }                                                                                            \
     } while (0)
-    for (int r = 0; r < K; ++r) {
-        int startk = ordP[r];
-        if (!xent[startk] || xvis[startk]) continue;
-        int start = npts, cur = startk, mr = K, guard = 0;
-        while (true) {
-            if (xvis[cur]) { status = TN_DEFER; return 0; }
-            xvis[cur] = true;
-            if (rankP[cur] < mr) mr = rankP[cur];
-            TN_PUSH(xp[cur]);
-            int rn = rankP[cur] + 1 == K ? 0 : rankP[cur] + 1, nx = ordP[rn];
-            int cnt = xe[nx] - xe[cur] + (rn == 0 ? np : 0);
-            for (int k = 0, v = xe[cur] + 1; k < cnt; ++k, ++v) {
-                if (v >= np) v -= np;
-                TN_PUSH(tget(P, v));
-            }
-            if (xent[nx] || xvis[nx]) { status = TN_DEFER; return 0; }
-            xvis[nx] = true;
-            if (rankP[nx] < mr) mr = rankP[nx];
-            TN_PUSH(xp[nx]);
-            int nn;
-            if (same) {
-                int rq = rankQ[nx] + 1 == K ? 0 : rankQ[nx] + 1;
-                nn = ordQ[rq];
-                cnt = xf[nn] - xf[nx] + (rq == 0 ? nq : 0);
-                for (int k = 0, v = xf[nx] + 1; k < cnt; ++k, ++v) {
-                    if (v >= nq) v -= nq;
-                    TN_PUSH(tget(Q, v));
+    for (int r = 0; r < K && !fail; ++r) {
+        const int startk = ordP[r];
+        if (xent[startk] && !xvis[startk]) {
+            int start = npts, cur = startk, mr = K, guard = 0;
+            bool closed = false;
+            while (!closed && !fail) {
+                if (xvis[cur]) {
+                    fail = true;
+                } else {
+                    xvis[cur] = true;
+                    if (rankP[cur] < mr) mr = rankP[cur];
+                    TN_PUSH(xp[cur]);
+                    int rn = rankP[cur] + 1 == K ? 0 : rankP[cur] + 1, nx = ordP[rn];
+                    int cnt = xe[nx] - xe[cur] + (rn == 0 ? np : 0);
+                    for (int k = 0, v = xe[cur] + 1; k < cnt; ++k, ++v) {
+                        if (v >= np) v -= np;
+                        TN_PUSH(tget(P, v));
+                    }
+                    if (xent[nx] || xvis[nx]) {
+                        fail = true;
+                    } else {
+                        xvis[nx] = true;
+                        if (rankP[nx] < mr) mr = rankP[nx];
+                        TN_PUSH(xp[nx]);
+                        int nn;
+                        if (same) {
+                            int rq = rankQ[nx] + 1 == K ? 0 : rankQ[nx] + 1;
+                            nn = ordQ[rq];
+                            cnt = xf[nn] - xf[nx] + (rq == 0 ? nq : 0);
+                            for (int k = 0, v = xf[nx] + 1; k < cnt; ++k, ++v) {
+                                if (v >= nq) v -= nq;
+                                TN_PUSH(tget(Q, v));
+                            }
+                        } else {
+                            int rq = rankQ[nx] == 0 ? K - 1 : rankQ[nx] - 1;
+                            nn = ordQ[rq];
+                            cnt = xf[nx] - xf[nn] + (rankQ[nx] == 0 ? nq : 0);
+                            for (int k = 0, v = xf[nx]; k < cnt; ++k, --v) {
+                                if (v < 0) v += nq;
+                                TN_PUSH(tget(Q, v));
+                            }
+                        }
+                        if (!xent[nn]) fail = true;
+                        else if (nn == startk) closed = true;
+                        else {
+                            cur = nn;
+                            if (++guard > K) fail = true;
+                        }
+                    }
                 }
-            } else {
-                int rq = rankQ[nx] == 0 ? K - 1 : rankQ[nx] - 1;
-                nn = ordQ[rq];
-                cnt = xf[nx] - xf[nn] + (rankQ[nx] == 0 ? nq : 0);
-                for (int k = 0, v = xf[nx]; k < cnt; ++k, --v) {
-                    if (v < 0) v += nq;
-                    TN_PUSH(tget(Q, v));
+            }
+            if (!fail) {
+                double2 f0 = R[start * TN_NT], l0 = R[(npts - 1) * TN_NT];
+                if (npts - start > 1 && l0.x == f0.x && l0.y == f0.y) npts--;
+                bool keep = npts - start >= 3;
+                if (keep) {
+                    R[npts * TN_NT] = f0;
+                    npts++;
+                    keep = t_area2(tring(R + start * TN_NT, npts - start)) != 0.0;
+                }
+                if (!keep) {
+                    npts = start;
+                } else if (nreg >= TN_MAXREG) {
+                    fail = true;
+                } else {
+                    int pos = nreg;
+                    while (pos > 0 && minrank[pos - 1] > mr) {
+                        minrank[pos] = minrank[pos - 1];
+                        rs[pos] = rs[pos - 1];
+                        re[pos] = re[pos - 1];
+                        --pos;
+                    }
+                    minrank[pos] = mr;
+                    rs[pos] = start;
+                    re[pos] = npts;
+                    nreg++;
                 }
             }
-            if (!xent[nn]) { status = TN_DEFER; return 0; }
-            if (nn == startk) break;
-            cur = nn;
-            if (++guard > K) { status = TN_DEFER; return 0; }
         }
-        {
-            double2 f0 = R[start * TN_NT], l0 = R[(npts - 1) * TN_NT];
-            if (npts - start > 1 && l0.x == f0.x && l0.y == f0.y) npts--;
-        }
-        if (npts - start < 3) {
-            npts = start;
-            continue;
-        }
-        R[npts * TN_NT] = R[start * TN_NT];
-        npts++;
-        if (t_area2(tring(R + start * TN_NT, npts - start)) == 0.0) {
-            npts = start;
-            continue;
-        }
-        if (nreg >= TN_MAXREG) {
-            status = TN_DEFER;
-            return 0;
-        }
-        int pos = nreg;
-        while (pos > 0 && minrank[pos - 1] > mr) {
-            minrank[pos] = minrank[pos - 1];
-            rs[pos] = rs[pos - 1];
-            re[pos] = re[pos - 1];
-            --pos;
-        }
-        minrank[pos] = mr;
-        rs[pos] = start;
-        re[pos] = npts;
-        nreg++;
+    }
+    if (fail) {
+        status = TN_DEFER;
+        nreg = 0;
     }
 #undef TN_PUSH
     return nreg;
@@ -366,6 +386,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
 // GO.intersection_points, de-duplicated in discovery order; ip is [point][thread]
 __device__ TN_FN int t_intersection_points(const TRing P, const TRing Q, double2 *ip, int &status) {
     int n = 0;
+    bool fail = false;
     for (int e = 0; e + 1 < P.n; ++e) {
         double2 a = tget(P, e), b = tget(P, e + 1);
         double2 c = tget(Q, 0);
@@ -376,19 +397,21 @@ __device__ TN_FN int t_intersection_points(const TRing P, const TRing Q, double2
             for (int k = 0; k < cnt; ++k) {
                 double2 t = k == 0 ? t0 : t1;
                 bool dup = false;
-                for (int m = 0; m < n && !dup; ++m) {
+                for (int m = 0; m < n; ++m) {
                     double2 v = ip[m * TN_NT];
-                    dup = (v.x == t.x && v.y == t.y);
+                    dup |= (v.x == t.x && v.y == t.y);
                 }
-                if (dup) continue;
-                if (n == TN_MAXIP) {
-                    status = TN_DEFER;
-                    return 0;
+                if (!dup) {
+                    if (n == TN_MAXIP) fail = true;
+                    else ip[(n++) * TN_NT] = t;
                 }
-                ip[(n++) * TN_NT] = t;
             }
             c = d;
         }
+    }
+    if (fail) {
+        status = TN_DEFER;
+        n = 0;
     }
     return n;
 }
