@@ -164,7 +164,7 @@ static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
     StepBuf &B = h->B;
     dfree(B.pair_i); dfree(B.pair_j); dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem);
     dfree(B.item_nrows); dfree(B.item_row0); dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items);
-    dfree(B.order); dfree(B.force_items);
+    dfree(B.order);
     CK(dalloc(&B.pair_i, (size_t)cap_pairs));
     CK(dalloc(&B.pair_j, (size_t)cap_pairs));
     CK(dalloc(&B.low_pair, (size_t)cap_pairs));
@@ -178,7 +178,6 @@ static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
     CK(dalloc(&B.large_items, items));
     CK(dalloc(&B.mid_items, items));
     CK(dalloc(&B.order, items));
-    CK(dalloc(&B.force_items, items));
     if (!B.class_count) {
         CK(dalloc(&B.class_count, 3 * 64));
         CK(cudaMemset(B.class_count, 0, sizeof(int) * 3 * 64));
@@ -190,9 +189,13 @@ static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
     return SZ_OK;
 }
 static int32_t set_pool_cap(sz_handle *h, int cap) {
-    dfree(h->B.pool);
+    dfree(h->B.pool); dfree(h->B.force_items); dfree(h->B.force_meta); dfree(h->B.force_pts);
     CK(dalloc(&h->B.pool, (size_t)cap * NPOOL));
+    CK(dalloc(&h->B.force_items, (size_t)cap));
+    CK(dalloc(&h->B.force_meta, (size_t)cap));
+    CK(dalloc(&h->B.force_pts, (size_t)cap * 28));  // TN_PRE_PTS records, see sz_narrow_thread.cuh
     h->B.cap_pool = cap;
+    h->B.cap_force = cap;
     return SZ_OK;
 }
 static int32_t set_row_cap(sz_handle *h, int cap) {
@@ -261,7 +264,7 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(S.atm_u); dfree(S.atm_v); dfree(S.fields8); dfree(S.cnt); dfree(S.dom);
     dfree(B.cell_count); dfree(B.cell_start); dfree(B.cell_fill); dfree(B.scan_block); dfree(B.cell_circ); dfree(B.pair_i); dfree(B.pair_j);
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
-    dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.force_items); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
+    dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
     dfree(h->d_hl_idx); dfree(h->d_hl_voff);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int k = 0; k < NEV; ++k) cudaEventDestroy(h->ev[k]);

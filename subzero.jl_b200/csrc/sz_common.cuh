@@ -118,7 +118,7 @@ struct Store {
 
 // Work buffers of one collision step.
 struct StepBuf {
-    int cap_pairs, cap_dom, cap_rows, cap_fuse, cap_pool, cap_cells;
+    int cap_pairs, cap_dom, cap_rows, cap_fuse, cap_pool, cap_cells, cap_force;
     // uniform grid
     int *cell_of;     // [cap_floes]
     int *cell_count;  // [cap_cells+1]
@@ -143,7 +143,9 @@ struct StepBuf {
     int *large_items;    // [cap_pairs + cap_dom] work list of the large-polygon kernel
     int *mid_items;      // [cap_pairs + cap_dom] work list of the warp-per-item kernel
     int *order;          // [cap_pairs + cap_dom] items sorted by (edges of P, edges of Q)
-    int *force_items;    // [cap_pairs + cap_dom] items that need contact forces
+    int *force_items;    // [cap_force] items that need contact forces (cap_force == cap_pool)
+    int4 *force_meta;    // [cap_force] region table of clip #1
+    double2 *force_pts;  // [TN_PRE_PTS][cap_force] regions and crossing points of clip #1
     int *class_count, *class_base, *class_cursor;  // [64] counting sort of the work items
     // per-floe rows
     int *row_pre, *row_count, *row_off;  // [cap_floes+1]

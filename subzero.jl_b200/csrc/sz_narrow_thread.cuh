@@ -34,9 +34,12 @@ struct TRing {
     double sx, sy;
     bool shifted;
 };
-__device__ __forceinline__ double2 tget(const TRing r, int k) {
+__device__ __forceinline__ double2 tget(const TRing r, int k) { return r.b[k * TN_NT]; }
+// the translated ring P2 = P + dir of calc_normal_force's second clip (collisions.jl:59-61)
+template <bool SHIFT>
+__device__ __forceinline__ double2 tgets(const TRing r, int k) {
     double2 v = r.b[k * TN_NT];
-    if (r.shifted) {
+    if (SHIFT) {
         v.x = v.x + r.sx;
         v.y = v.y + r.sy;
     }
@@ -56,6 +59,16 @@ __device__ TN_FN double t_area2(const TRing r) {
     double2 p = tget(r, 0);
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 q = tget(r, k + 1);
+        a += p.x * q.y - p.y * q.x;
+        p = q;
+    }
+    return a;
+}
+__device__ TN_FN double t_area2s(const TRing r) {
+    double a = 0.0;
+    double2 p = tgets<true>(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 q = tgets<true>(r, k + 1);
         a += p.x * q.y - p.y * q.x;
         p = q;
     }
@@ -95,6 +108,20 @@ __device__ TN_FN bool t_point_in_ring_p(double2 q, const TRing r) {
     double2 a = tget(r, 0);
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 b = tget(r, k + 1);
+        if (a.y <= q.y && q.y < b.y) {
+            if (side_p(orient2d(a, b, q), a, b)) in = !in;
+        } else if (b.y <= q.y && q.y < a.y) {
+            if (!side_p(orient2d(a, b, q), a, b)) in = !in;
+        }
+        a = b;
+    }
+    return in;
+}
+__device__ TN_FN bool t_point_in_ring_ps(double2 q, const TRing r) {
+    bool in = false;
+    double2 a = tgets<true>(r, 0);
+    for (int k = 0; k + 1 < r.n; ++k) {
+        double2 b = tgets<true>(r, k + 1);
         if (a.y <= q.y && q.y < b.y) {
             if (side_p(orient2d(a, b, q), a, b)) in = !in;
         } else if (b.y <= q.y && q.y < a.y) {
@@ -159,6 +186,7 @@ __device__ TN_FN bool t_rings_intersect(const TRing A, const TRing B) {
 // `xp_out` / `generic`: when no orientation value was exactly zero the crossing points ARE
 // GO.intersection_points(P, Q) (closed-segment intersection == proper crossing), in the same
 // (e, f) order; the caller then skips the separate 4 np nq pass.
+template <bool SHIFT>
 __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, int *rs, int *re, int &status,
                                    double2 *xp_out, int *K_out, bool *generic) {
     const int np = P.n - 1, nq = Q.n - 1;
@@ -167,7 +195,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     if (generic) *generic = false;
     if (np < 3 || nq < 3) return 0;
     const bool q_ccw = t_area2(Q) > 0.0;
-    const bool same = (t_area2(P) > 0.0) == q_ccw;
+    const bool same = (SHIFT ? t_area2s(P) : t_area2(P)) > 0.0 == q_ccw;
     int xe[TN_MAXX], xf[TN_MAXX], rankP[TN_MAXX], rankQ[TN_MAXX], ordP[TN_MAXX], ordQ[TN_MAXX];
     double xt[TN_MAXX], xs[TN_MAXX];
     double2 xp[TN_MAXX];
@@ -182,7 +210,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         for (int v = 0; v <= np; ++v) {
             unsigned cur;
             if (v < np) {
-                double2 pv = tget(P, v);
+                double2 pv = tgets<SHIFT>(P, v);
                 double2 c = tget(Q, 0);
                 cur = 0;
                 for (int f = 0; f < nq; ++f) {
@@ -213,32 +241,36 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
             prev = cur;
         }
     }
-    // pass 2: the full four-orientation test only on the candidates
+    // pass 2a: which candidates are crossings (the Q edge must straddle the P edge's line as well)
     int K = 0;
     for (int k = 0; k < nc; ++k) {
         const int e = ce[k], f = cf[k];
-        double2 a = tget(P, e), b = tget(P, e + 1);
-        double2 c = tget(Q, f), d = tget(Q, f + 1);
-        double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
+        double2 a = tgets<SHIFT>(P, e), b = tgets<SHIFT>(P, e + 1);
+        double o3 = orient2d(a, b, tget(Q, f)), o4 = orient2d(a, b, tget(Q, f + 1));
         anyzero |= (o3 == 0.0) | (o4 == 0.0);
-        bool sc = side_p(o3, a, b), sd = side_p(o4, a, b);
-        if (sc != sd) {
+        if (side_p(o3, a, b) != side_p(o4, a, b)) {
             if (K == TN_MAXX) {
                 fail = true;
             } else {
-                double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
-                bool sb = side_q(o2, c, d);
-                double t = o1 / (o1 - o2);
                 xe[K] = e;
                 xf[K] = f;
-                xt[K] = t;
-                xs[K] = o3 / (o3 - o4);
-                xp[K] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
-                xent[K] = (sb == q_ccw);
-                xvis[K] = false;
                 K++;
             }
         }
+    }
+    // pass 2b (lanes in step again): parameters and point of every crossing
+    for (int k = 0; k < K; ++k) {
+        const int e = xe[k], f = xf[k];
+        double2 a = tgets<SHIFT>(P, e), b = tgets<SHIFT>(P, e + 1);
+        double2 c = tget(Q, f), d = tget(Q, f + 1);
+        double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
+        double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
+        double t = o1 / (o1 - o2);
+        xt[k] = t;
+        xs[k] = o3 / (o3 - o4);
+        xp[k] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
+        xent[k] = (side_q(o2, c, d) == q_ccw);
+        xvis[k] = false;
     }
     if (fail) {
         status = TN_DEFER;
@@ -254,15 +286,15 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         *generic = !anyzero && !dup;
     }
     if (K == 0) {
-        bool pin = t_point_in_ring_q(tget(P, 0), Q);
-        bool qin = pin ? false : t_point_in_ring_p(tget(Q, 0), P);
+        bool pin = t_point_in_ring_q(tgets<SHIFT>(P, 0), Q);
+        bool qin = pin ? false : (SHIFT ? t_point_in_ring_ps(tget(Q, 0), P) : t_point_in_ring_p(tget(Q, 0), P));
         if (!pin && !qin) return 0;
         const TRing src = pin ? P : Q;
         if (src.n > rcap) {
             status = TN_DEFER;
             return 0;
         }
-        for (int k = 0; k < src.n; ++k) R[k * TN_NT] = tget(src, k);
+        for (int k = 0; k < src.n; ++k) R[k * TN_NT] = pin ? tgets<SHIFT>(src, k) : tget(src, k);
         rs[0] = 0;
         re[0] = src.n;
         return 1;
@@ -311,7 +343,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                     int cnt = xe[nx] - xe[cur] + (rn == 0 ? np : 0);
                     for (int k = 0, v = xe[cur] + 1; k < cnt; ++k, ++v) {
                         if (v >= np) v -= np;
-                        TN_PUSH(tget(P, v));
+                        TN_PUSH(tgets<SHIFT>(P, v));
                     }
                     if (xent[nx] || xvis[nx]) {
                         fail = true;
@@ -425,15 +457,28 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
     }
     for (int i = 0; i < npoints; ++i) {
         double2 p = ip[i * TN_NT];
+        // the reference takes the first vertex with the smallest sqrt(sqrt(d2)) (floe_utils.jl:339-345).  sqrt is
+        // monotone, so that vertex has d2 within rounding of the smallest d2: the two square roots are only
+        // evaluated for those few candidates — same index, same threshold decision.
+        double m2 = INFINITY;
+        for (int j = 0; j < reg.n; ++j) {
+            double2 v = tget(reg, j);
+            double dx = v.x - p.x, dy = v.y - p.y;
+            m2 = fmin(m2, dx * dx + dy * dy);
+        }
+        const double lim = m2 * (1.0 + 1e-12);
         double min_dist = INFINITY;
         int min_vert = 0;
         for (int j = 0; j < reg.n; ++j) {
             double2 v = tget(reg, j);
             double dx = v.x - p.x, dy = v.y - p.y;
-            double dist = sqrt(sqrt(dx * dx + dy * dy));
-            if (dist < min_dist) {
-                min_dist = dist;
-                min_vert = j;
+            double d2 = dx * dx + dy * dy;
+            if (d2 <= lim) {
+                double dist = sqrt(sqrt(d2));
+                if (dist < min_dist) {
+                    min_dist = dist;
+                    min_vert = j;
+                }
             }
         }
         if (min_dist < 1.0) idx[m++] = min_vert;
@@ -517,7 +562,7 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
         P2.sx = dir[0];
         P2.sy = dir[1];
         int rs2[TN_MAXREG], re2[TN_MAXREG];
-        int nreg2 = t_clip(P2, Q, w.R2, w.r2cap, rs2, re2, status, nullptr, nullptr, nullptr);
+        int nreg2 = t_clip<true>(P2, Q, w.R2, w.r2cap, rs2, re2, status, nullptr, nullptr, nullptr);
         if (status != TN_OK) return 0.0;
         for (int r = 0; r < nreg2; ++r) {
             TRing nr = tring(w.R2 + rs2[r] * TN_NT, re2[r] - rs2[r]);
@@ -536,7 +581,14 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
 // item that needs contact forces is handed to phase 1 (k_narrow_b), which repeats clip #1 (cheap next to the
 // force part) and computes the rows.  Returns TI_DONE, TI_WARP (the warp kernel must take it) or TI_FORCES.
 enum { TI_DONE = 0, TI_WARP = 1, TI_FORCES = 2 };
-__device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params &P, int slot, int phase) {
+// what phase 0 hands to phase 1 (through global memory, SoA over the force list): the regions of clip #1,
+// the crossing points and whether they are GO.intersection_points
+struct TPre {
+    int nreg, rs[TN_MAXREG], re[TN_MAXREG], K1, used;
+    bool generic;
+};
+template <int PHASE>
+__device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params &P, int slot, TPre &pre) {
     Counters *cnt = S.cnt;
     const DomainDev *D = S.dom;
     const bool is_pair = slot < B.cap_pairs;
@@ -582,17 +634,32 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     uint32_t flags = 0;
     int rs1[TN_MAXREG], re1[TN_MAXREG];
     double area1[TN_MAXREG];
-    int K1 = 0;
+    int K1 = 0, nreg, used = 0;
     bool generic = false;
-    int nreg = phase == 0 ? t_clip(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, nullptr, nullptr, nullptr)
-                          : t_clip(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, w.ip, &K1, &generic);
-    if (status != TN_OK) return TI_WARP;
-    {
-        int used = 0;
+    if (PHASE == 0) {
+        nreg = t_clip<false>(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, w.ip, &K1, &generic);
+        if (status != TN_OK) return TI_WARP;
         for (int r = 0; r < nreg; ++r) used = max(used, re1[r]);
-        w.R2 = w.R1 + used * TN_NT;
-        w.r2cap = TN_RCAP - used;
+        pre.nreg = nreg;
+        pre.K1 = K1;
+        pre.generic = generic;
+        pre.used = used;
+        for (int r = 0; r < TN_MAXREG; ++r) {
+            pre.rs[r] = r < nreg ? rs1[r] : 0;
+            pre.re[r] = r < nreg ? re1[r] : 0;
+        }
+    } else {  // the regions and crossing points were loaded into w.R1 / w.ip by the caller
+        nreg = pre.nreg;
+        K1 = pre.K1;
+        generic = pre.generic;
+        used = pre.used;
+        for (int r = 0; r < TN_MAXREG; ++r) {
+            rs1[r] = pre.rs[r];
+            re1[r] = pre.re[r];
+        }
     }
+    w.R2 = w.R1 + used * TN_NT;
+    w.r2cap = TN_RCAP - used;
     double total = 0.0, max_area = 0.0;
     for (int r = 0; r < nreg; ++r) {
         area1[r] = t_area(tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]));
@@ -635,7 +702,7 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
             }
         }
     }
-    if (forces && phase == 0) return TI_FORCES;
+    if (forces && PHASE == 0) return TI_FORCES;
     double rows[TN_MAXREG][NPOOL];
     int nrows = 0;
     if (forces) {
@@ -705,7 +772,7 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     return TI_DONE;
 }
 
-#define TN_SMEM_A (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP))
+#define TN_SMEM_A (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))
 #define TN_SMEM_B (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))
 #define TN_NCLASS 64  // (edges of P - 3) * 8 + (edges of Q - 3), rings of 3..10 edges
 
@@ -792,6 +859,9 @@ __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
     }
 }
 
+// pre-clip records of the force list, SoA: point k of record b at [k * cap_force + b]
+#define TN_PRE_PTS (TN_RCAP + TN_MAXX)
+
 template <int PHASE>
 __global__ void __launch_bounds__(TN_NT, 2) k_narrow_ab(Store S, StepBuf B, Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -804,16 +874,29 @@ __global__ void __launch_bounds__(TN_NT, 2) k_narrow_ab(Store S, StepBuf B, Para
     w.R1 = w.Q + TN_MAXV * TN_NT;
     w.R2 = w.R1;
     w.r2cap = 0;
-    w.ip = w.R1 + TN_RCAP * TN_NT;  // phase 1 only
-    const int total = PHASE == 0 ? cnt->n_order : cnt->n_force;
+    w.ip = w.R1 + TN_RCAP * TN_NT;
+    const int total = PHASE == 0 ? cnt->n_order : min(cnt->n_force, B.cap_force);
     const int *list = PHASE == 0 ? B.order : B.force_items;
     const int lane = threadIdx.x & 31;
+    const size_t cf = (size_t)B.cap_force;
     for (int base_it = blockIdx.x * TN_NT + (threadIdx.x & ~31); base_it < total; base_it += gridDim.x * TN_NT) {
         const int it = base_it + lane;
         int rc = TI_DONE, slot = -1;
+        TPre pre;
         if (it < total) {
             slot = list[it];
-            rc = thread_item(w, S, B, P, slot, PHASE);
+            if (PHASE == 1) {
+                const int4 m = B.force_meta[it];
+                pre.nreg = m.x & 0xff;
+                pre.generic = (m.x >> 8) & 1;
+                pre.K1 = (m.x >> 16) & 0xff;
+                pre.used = m.w;
+                pre.rs[0] = m.y & 0xffff; pre.re[0] = m.y >> 16;
+                pre.rs[1] = m.z & 0xffff; pre.re[1] = m.z >> 16;
+                for (int k = 0; k < pre.used; ++k) w.R1[k * TN_NT] = B.force_pts[k * cf + it];
+                for (int k = 0; k < pre.K1; ++k) w.ip[k * TN_NT] = B.force_pts[(TN_RCAP + k) * cf + it];
+            }
+            rc = thread_item<PHASE>(w, S, B, P, slot, pre);
         }
         if (rc == TI_WARP) {
             B.mid_items[atomicAdd(&cnt->n_mid, 1)] = slot;
@@ -827,7 +910,19 @@ __global__ void __launch_bounds__(TN_NT, 2) k_narrow_ab(Store S, StepBuf B, Para
                 int b0 = 0;
                 if (lane == 0) b0 = atomicAdd(&cnt->n_force, __popc(m));
                 b0 = __shfl_sync(0xffffffffu, b0, 0);
-                if (rc == TI_FORCES) B.force_items[b0 + __popc(m & ((1u << lane) - 1))] = slot;
+                if (rc == TI_FORCES) {
+                    const int b = b0 + __popc(m & ((1u << lane) - 1));
+                    if (b < B.cap_force) {
+                        B.force_items[b] = slot;
+                        B.force_meta[b] = make_int4(pre.nreg | ((int)pre.generic << 8) | (pre.K1 << 16), pre.rs[0] | (pre.re[0] << 16),
+                                                    pre.rs[1] | (pre.re[1] << 16), pre.used);
+                        for (int k = 0; k < pre.used; ++k) B.force_pts[k * cf + b] = w.R1[k * TN_NT];
+                        for (int k = 0; k < pre.K1; ++k) B.force_pts[(TN_RCAP + k) * cf + b] = w.ip[k * TN_NT];
+                    } else {
+                        atomicOr(&cnt->error, ERR_POOL_CAP);  // the force list shares the contact pool's capacity
+                        atomicMax(&cnt->n_pool, b + 1);
+                    }
+                }
             }
         }
     }
