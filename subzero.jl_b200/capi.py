@@ -165,6 +165,19 @@ class FloeArrays:
         self.mc_y = np.zeros(0, dtype=np.float64)
 
     def as_struct(self):
+        """ctypes view of the arrays.  Cached: rebuilt only when an array object was replaced."""
+        key = tuple(id(getattr(self, n)) for n in DOUBLE_FIELDS + ("vert_xy", "mc_x", "mc_y", "status_tag", "id", "ghost_id",
+                                                                   "ghost_offsets", "ghost_index", "vert_offsets", "mc_offsets"))
+        cached = getattr(self, "_struct_cache", None)
+        if cached is not None and cached[0] == key and cached[1].n == self.n and cached[1].n_init == self.n_init:
+            return cached[1]
+        s = self._build_struct()
+        key = tuple(id(getattr(self, n)) for n in DOUBLE_FIELDS + ("vert_xy", "mc_x", "mc_y", "status_tag", "id", "ghost_id",
+                                                                   "ghost_offsets", "ghost_index", "vert_offsets", "mc_offsets"))
+        self._struct_cache = (key, s)
+        return s
+
+    def _build_struct(self):
         s = FloeSoA()
         s.n, s.n_init = self.n, self.n_init
         keep = []
@@ -295,8 +308,11 @@ class Handle:
         else:
             fa = into
         s = fa.as_struct()
-        if not mc:
-            s.mc_x, s.mc_y = None, None
+        if not mc:  # a private copy of the (cached) struct with the Monte-Carlo pointers cleared
+            s2 = FloeSoA()
+            C.memmove(C.byref(s2), C.byref(s), C.sizeof(FloeSoA))
+            s2.mc_x, s2.mc_y = None, None
+            s = s2
         self._ck(self.lib.download_floes(self.h, C.byref(s)))
         return fa
 

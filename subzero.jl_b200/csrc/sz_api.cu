@@ -43,6 +43,10 @@ struct sz_handle {
     std::vector<long long> hl_off, hl_bytes;
     int *d_hl_idx;
     long long *d_hl_voff;
+    // host mirrors of the static tables of the last upload (fast download path)
+    std::vector<int> h_vstart, h_vcount;
+    std::vector<long long> h_mc_off;
+    bool ghosts_uploaded;
 };
 
 #define CK(expr)                                                                                         \
@@ -400,9 +404,9 @@ static int32_t upload_scalars(sz_handle *h, const sz_floe_soa *s, int n) {
     CK(up(S.p_dvdt, s->p_dvdt, 1)); CK(up(S.p_dxidt, s->p_dxidt, 1)); CK(up(S.p_dalphadt, s->p_dalphadt, 1));
     CK(up(S.stress_accum, s->stress_accum, 4)); CK(up(S.stress_instant, s->stress_instant, 4)); CK(up(S.strain, s->strain, 4));
     // collision_force is [n][2] on the host, two columns on the device
-    if (s->collision_force) {
-        CK(cudaMemcpy2DAsync(S.cfx, sizeof(double), s->collision_force, 2 * sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpy2DAsync(S.cfy, sizeof(double), s->collision_force + 1, 2 * sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice, st));
+    if (s->collision_force) {  // [n][2] on the host -> two device columns
+        CK(cudaMemcpyAsync(h->B.cell_circ, s->collision_force, sizeof(double2) * n, cudaMemcpyHostToDevice, st));
+        szk_deinterleave(h->L, h->B.cell_circ, S.cfx, S.cfy, n);
     } else {
         CK(cudaMemsetAsync(S.cfx, 0, sizeof(double) * n, st));
         CK(cudaMemsetAsync(S.cfy, 0, sizeof(double) * n, st));
@@ -523,6 +527,9 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     h->n_verts_init = n_init > 0 ? (int)s->vert_offsets[n_init] : 0;
     h->n_rows_host = 0;
     memset(&h->last, 0, sizeof(h->last));
+    h->h_vstart = vstart;
+    h->h_vcount = vcount;
+    h->h_mc_off = mo;
     h->have_floes = true;
     return SZ_OK;
 }
@@ -592,48 +599,58 @@ extern "C" int32_t sz_download_floes(sz_handle *h, sz_floe_soa *s) {
     CK(dn(s->p_dxdt, S.p_dxdt, 1)); CK(dn(s->p_dydt, S.p_dydt, 1)); CK(dn(s->p_dudt, S.p_dudt, 1));
     CK(dn(s->p_dvdt, S.p_dvdt, 1)); CK(dn(s->p_dxidt, S.p_dxidt, 1)); CK(dn(s->p_dalphadt, S.p_dalphadt, 1));
     CK(dn(s->stress_accum, S.stress_accum, 4)); CK(dn(s->stress_instant, S.stress_instant, 4)); CK(dn(s->strain, S.strain, 4));
-    std::vector<double> cf;
-    if (s->collision_force) {
-        cf.resize((size_t)2 * n);
-        CK(cudaMemcpyAsync(cf.data(), S.cfx, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(cf.data() + n, S.cfy, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (s->collision_force) {  // two device columns -> [n][2] on the host (cell_circ is scratch between steps)
+        szk_interleave(h->L, S.cfx, S.cfy, h->B.cell_circ, n);
+        CK(cudaMemcpyAsync(s->collision_force, h->B.cell_circ, sizeof(double2) * n, cudaMemcpyDeviceToHost, st));
     }
-    std::vector<int> status, vstart(n), vcount(n), nghost(n), gslot((size_t)n * SZ_MAX_GHOSTS);
     if (s->status_tag) CK(cudaMemcpyAsync(s->status_tag, S.status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     if (s->id) CK(cudaMemcpyAsync(s->id, S.id, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
     if (s->ghost_id) CK(cudaMemcpyAsync(s->ghost_id, S.ghost_id, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vstart.data(), S.vstart, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vcount.data(), S.vcount, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(nghost.data(), S.nghost, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(gslot.data(), S.ghost_slot, sizeof(int) * SZ_MAX_GHOSTS * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (s->collision_force)
-        for (int i = 0; i < n; ++i) { s->collision_force[2 * i] = cf[i]; s->collision_force[2 * i + 1] = cf[(size_t)n + i]; }
+    const bool no_ghosts = n == n_init && (int)h->h_vcount.size() == n;
+    std::vector<int> vstart_d, vcount_d, nghost, gslot;
+    const int *vstart = h->h_vstart.data(), *vcount = h->h_vcount.data();
+    if (!no_ghosts) {  // ghosts resident: ring table and ghost links live on the device
+        vstart_d.resize(n); vcount_d.resize(n); nghost.resize(n); gslot.resize((size_t)n * SZ_MAX_GHOSTS);
+        CK(cudaMemcpyAsync(vstart_d.data(), S.vstart, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(vcount_d.data(), S.vcount, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(nghost.data(), S.nghost, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(gslot.data(), S.ghost_slot, sizeof(int) * SZ_MAX_GHOSTS * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        vstart = vstart_d.data();
+        vcount = vcount_d.data();
+    }
     // rings: the device keeps them in floe order (ghost rings appended), so one contiguous copy
     long long vo = 0;
     bool contiguous = true;
-    for (int i = 0; i < n; ++i) {
-        if (vstart[i] != vo) contiguous = false;
-        if (s->vert_offsets) s->vert_offsets[i] = vo;
-        vo += vcount[i];
+    if (no_ghosts) {
+        vo = h->n_verts_init;
+        if (s->vert_offsets) {
+            long long o = 0;
+            for (int i = 0; i < n; ++i) { s->vert_offsets[i] = o; o += vcount[i]; }
+            s->vert_offsets[n] = o;
+        }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            if (vstart[i] != vo) contiguous = false;
+            if (s->vert_offsets) s->vert_offsets[i] = vo;
+            vo += vcount[i];
+        }
+        if (s->vert_offsets) s->vert_offsets[n] = vo;
     }
-    if (s->vert_offsets) s->vert_offsets[n] = vo;
     if (s->vert_xy) {
         if (contiguous) {
-            CK(cudaMemcpy(s->vert_xy, S.verts, sizeof(double2) * (size_t)vo, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpyAsync(s->vert_xy, S.verts, sizeof(double2) * (size_t)vo, cudaMemcpyDeviceToHost, st));
         } else {
             long long o = 0;
             for (int i = 0; i < n; ++i) {
-                CK(cudaMemcpy(s->vert_xy + 2 * o, S.verts + vstart[i], sizeof(double2) * vcount[i], cudaMemcpyDeviceToHost));
+                CK(cudaMemcpyAsync(s->vert_xy + 2 * o, S.verts + vstart[i], sizeof(double2) * vcount[i], cudaMemcpyDeviceToHost, st));
                 o += vcount[i];
             }
         }
     }
-    if (s->mc_offsets) {
-        std::vector<long long> mo((size_t)n_init + 1);
-        CK(cudaMemcpy(mo.data(), S.mc_off, sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyDeviceToHost));
-        for (int i = 0; i <= n; ++i) s->mc_offsets[i] = mo[std::min(i, n_init)];
-    }
+    if (s->mc_offsets)
+        for (int i = 0; i <= n; ++i) s->mc_offsets[i] = h->h_mc_off[std::min(i, n_init)];
+    CK(cudaStreamSynchronize(st));
     if ((s->mc_x || s->mc_y) && h->n_mc > 0) {
         double *tx = nullptr, *ty = nullptr;
         CK(dalloc(&tx, (size_t)h->n_mc)); CK(dalloc(&ty, (size_t)h->n_mc));
@@ -642,6 +659,10 @@ extern "C" int32_t sz_download_floes(sz_handle *h, sz_floe_soa *s) {
         if (s->mc_y) CK(cudaMemcpyAsync(s->mc_y, ty, sizeof(double) * h->n_mc, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         cudaFree(tx); cudaFree(ty);
+    }
+    if (no_ghosts) {
+        if (s->ghost_offsets) memset(s->ghost_offsets, 0, sizeof(int64_t) * ((size_t)n + 1));
+        return SZ_OK;
     }
     long long go = 0;
     for (int i = 0; i < n; ++i) {
