@@ -22,6 +22,8 @@ struct sz_handle {
     sz_config cfg;
     char err[512];
     Launch L;
+    cudaStream_t stream2;      // coupling runs here, concurrently with the collision kernels (sz_step)
+    cudaEvent_t ev_fork, ev_join, ev_c0, ev_c1;
     Params P;
     bool have_grid, have_fields, have_domain, have_floes;
     DomainDev hD;
@@ -111,6 +113,7 @@ static void register_arrays(sz_handle *h) {
     add((void **)&S.nghost, sizeof(int));
     add((void **)&S.ghost_slot, SZ_MAX_GHOSTS * sizeof(int));
     add((void **)&S.warn, sizeof(uint32_t));
+    add((void **)&S.cpl_remove, sizeof(unsigned char));
     add((void **)&S.vstart, sizeof(int));
     add((void **)&S.vcount, sizeof(int));
     void **scr[] = {(void **)&B.cell_of, (void **)&B.cell_items, (void **)&B.up_count, (void **)&B.up_off,
@@ -242,7 +245,14 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->L.sms = prop.multiProcessorCount;
     h->L.maxv_large = 1024;
     h->L.maxx_large = 256;
-    if (cudaStreamCreateWithFlags(&h->L.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->L.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    cudaEventCreate(&h->ev_c0);
+    cudaEventCreate(&h->ev_c1);
     for (int k = 0; k < NEV; ++k) cudaEventCreate(&h->ev[k]);
     if (cudaMallocHost((void **)&h->h_cnt, sizeof(Counters)) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
     memset(h->h_cnt, 0, sizeof(Counters));
@@ -273,6 +283,8 @@ extern "C" void sz_destroy(sz_handle *h) {
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int k = 0; k < NEV; ++k) cudaEventDestroy(h->ev[k]);
     cudaStreamDestroy(h->L.stream);
+    cudaStreamDestroy(h->stream2);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_c0); cudaEventDestroy(h->ev_c1);
     delete h;
 }
 
@@ -798,6 +810,7 @@ extern "C" int32_t sz_step_coupling(sz_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaEventRecord(h->ev[0], h->L.stream);
     szk_coupling(h->L, h->S, h->P);
+    szk_apply_coupling_tags(h->L, h->S);
     cudaEventRecord(h->ev[1], h->L.stream);
     CK(cudaStreamSynchronize(h->L.stream));
     CK(cudaGetLastError());
@@ -831,12 +844,28 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
         cudaEventRecord(h->ev[0], st);
         enqueue_ghosts(h);
         cudaEventRecord(h->ev[1], st);
+        if (do_coupling) {
+            // fork: coupling only needs the floe state after add_ghosts! wrapped parents into the domain; it
+            // reads nothing the collision kernels write, so it runs beside them on a low-priority stream and
+            // fills the issue slots the latency-bound narrow phase leaves idle
+            cudaEventRecord(h->ev_fork, st);
+            cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+            Launch L2 = h->L;
+            L2.stream = h->stream2;
+            cudaEventRecord(h->ev_c0, h->stream2);
+            szk_coupling(L2, h->S, h->P);
+            cudaEventRecord(h->ev_c1, h->stream2);
+            cudaEventRecord(h->ev_join, h->stream2);
+        }
         // the ghost count of this step is not known on the host: size grids from the capacity-bounded hint
         szk_collisions(h->L, h->S, h->B, h->P, floes_hint(h), pairs_hint(h), &h->ev[2]);
         CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         szk_remove_ghosts(h->L, h->S, h->n_verts_init);
         cudaEventRecord(h->ev[5], st);
-        if (do_coupling) szk_coupling(h->L, h->S, h->P);
+        if (do_coupling) {
+            cudaStreamWaitEvent(st, h->ev_join, 0);  // join
+            szk_apply_coupling_tags(h->L, h->S);
+        }
         cudaEventRecord(h->ev[6], st);
         szk_update(h->L, h->S, h->B, h->P);
         cudaEventRecord(h->ev[7], st);
@@ -863,7 +892,12 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     h->ms[1] = ev_ms(h, 1, 2);
     h->ms[2] = ev_ms(h, 2, 3);
     h->ms[3] = ev_ms(h, 3, 5);
-    h->ms[4] = ev_ms(h, 5, 6);
+    h->ms[4] = 0.0;  // coupling kernel time on its own stream (overlaps the collision phases)
+    if (do_coupling) {
+        float cms = 0.f;
+        cudaEventElapsedTime(&cms, h->ev_c0, h->ev_c1);
+        h->ms[4] = (double)cms;
+    }
     h->ms[5] = ev_ms(h, 6, 7);
     h->ms[6] = ev_ms(h, 0, 7);
     h->ms[7] = (double)szk_launch_count(true);  // kernels launched since the previous sz_step returned (incl. halo pack/unpack)

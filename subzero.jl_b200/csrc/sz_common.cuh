@@ -100,6 +100,7 @@ struct Store {
     int *nghost;      // number of ghosts of a parent
     int *ghost_slot;  // [cap][SZ_MAX_GHOSTS]
     uint32_t *warn;
+    unsigned char *cpl_remove;  // coupling found no in-bounds Monte-Carlo point (coupling.jl:1507)
     // CSR geometry
     int *vstart, *vcount;  // ring of floe f = verts[vstart[f] .. vstart[f]+vcount[f]), closed
     double2 *verts;
@@ -176,6 +177,7 @@ int szk_configure(const Launch &L);
 void szk_halo(const Launch &L, const Store &S, const int *idx, const long long *voff, int n, double *buf, bool pack);
 void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);
 void szk_coupling(const Launch &L, const Store &S, const Params &P);
+void szk_apply_coupling_tags(const Launch &L, const Store &S);
 void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P);
 void szk_interleave(const Launch &L, const double *x, const double *y, double2 *out, long long n);
 void szk_deinterleave(const Launch &L, const double2 *in, double *x, double *y, long long n);

@@ -112,7 +112,7 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     acc.hf += hfl;
 }
 
-__global__ void __launch_bounds__(256, 3) k_coupling(Store S, CpConst c) {
+__global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(256, 3) k_coupling(Store S, CpConst c) {
         }
         if (lane == 0) {
             if (acc.n == 0) {
-                S.status[i] = SZ_STATUS_REMOVE;  // coupling.jl:1507-1508
+                S.cpl_remove[i] = 1;  // coupling.jl:1507-1508; applied to status.tag by k_apply_coupling_tags
             } else {
+                S.cpl_remove[i] = 0;
                 double np_ = (double)acc.n;
                 double tot_x = np_ * (mf * v) + acc.tx, tot_y = -np_ * (mf * u) + acc.ty;  // Coriolis, :1522-1525
                 S.fxOA[i] = tot_x / np_ * ar;  // :1583-1586
@@ -165,8 +166,23 @@ void szk_coupling(const Launch &L, const Store &S, const Params &P) {
     c.ka = P.cfg.rho_a * P.cfg.Cd_ia; c.ko = P.cfg.rho_o * P.cfg.Cd_io; c.f = P.cfg.f;
     c.Nx = P.Nx; c.Ny = P.Ny;
     c.per_x = P.per_x; c.per_y = P.per_y;
-    long long blocks = ((long long)S.n_init + 7) / 8, cap = (long long)L.sms * 24;
-    k_coupling<<<(int)(blocks < cap ? blocks : cap), 256, 0, L.stream>>>(S, c);
+    // 128-thread blocks: small enough to share an SM with the narrow-phase blocks when the two run on
+    // different streams (sz_step overlaps coupling with the collision kernels)
+    long long blocks = ((long long)S.n_init + 3) / 4, cap = (long long)L.sms * 48;
+    k_coupling<<<(int)(blocks < cap ? blocks : cap), 128, 0, L.stream>>>(S, c);
+    szk_count_launches(1);
+}
+
+// status.tag = remove for floes without an in-bounds Monte-Carlo point (coupling.jl:1507-1508).  A separate
+// pass because coupling may run concurrently with the collision kernels, which also write status.tag.
+__global__ void k_apply_coupling_tags(Store S) {
+    if (S.cnt->error) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n_init; i += gridDim.x * blockDim.x)
+        if (S.cpl_remove[i]) S.status[i] = SZ_STATUS_REMOVE;
+}
+void szk_apply_coupling_tags(const Launch &L, const Store &S) {
+    if (S.n_init <= 0) return;
+    k_apply_coupling_tags<<<(S.n_init + 255) / 256, 256, 0, L.stream>>>(S);
     szk_count_launches(1);
 }
 
