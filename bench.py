@@ -313,11 +313,14 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    notes = {"k_narrow": "narrow phase = k_narrow_thread (+ k_narrow for large rings): FP64 issue/latency bound, not bandwidth bound "
-                         "(ncu: 0.2 % DRAM, 10 of 32 lanes active per instruction); the HBM fraction is reported because the "
-                         "contract asks for it, the optimisation target is lane efficiency (profiles/README.md)",
-             "k_coupling": "streams 16 B per Monte-Carlo point once; FP64 pipe ~52 % busy (ncu)", "k_update": ""}
-    roofline = {"kernel": dom if dom != "k_narrow" else "k_narrow_thread", "bound": "hbm", "achieved": achieved, "peak": hbm,
+    notes = {"k_narrow": "narrow phase = k_item_count/scatter + k_narrow_ab<0> (clip, decisions) + k_narrow_ab<1> (forces) + k_narrow "
+                         "(rings > 10 edges): FP64 latency bound, not bandwidth bound (ncu r1j: <1 % of DRAM peak, 16-18 % issue "
+                         "slots, 20 of 32 lanes active); the HBM fraction is reported because the contract asks for it, the lever "
+                         "is lane efficiency and occupancy (profiles/README.md)",
+             "k_coupling": "streams 16 B per Monte-Carlo point once (ncu: 956 MB read = the algorithmic bytes); FP64 pipe 52 % busy; "
+                           "inside sz_step it runs on a second stream beside the collision kernels",
+             "k_update": ""}
+    roofline = {"kernel": dom if dom != "k_narrow" else "k_narrow_ab", "bound": "hbm", "achieved": achieved, "peak": hbm,
                 "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "note": notes[dom],
                 "all_kernels": {k: {"ms": v[0], "algorithmic_bytes": v[1], "GB/s": (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0),
                                     "frac": (v[1] / (v[0] * 1e-3) / 1e9 / hbm if v[0] > 0 else 0.0)} for k, v in kernels.items()},

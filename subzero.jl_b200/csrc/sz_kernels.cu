@@ -1127,7 +1127,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     // large-polygon workspace for what that one handed on
     int gi = grid_for(L, (long long)pairs_hint + n_hint / 8 + 64, 256);
     k_item_count<<<gi, 256, 0, st>>>(S, B);
-    k_class_scan<<<1, 1, 0, st>>>(S, B);
+    k_class_scan<<<1, 32, 0, st>>>(S, B);
     k_item_scatter<<<gi, 256, 0, st>>>(S, B);
     k_narrow_ab<0><<<2 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, B, P);
     k_narrow_ab<1><<<2 * L.sms, TN_NT, TN_SMEM_B, st>>>(S, B, P);

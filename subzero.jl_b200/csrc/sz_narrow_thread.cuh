@@ -822,18 +822,28 @@ __global__ void __launch_bounds__(256) k_item_count(Store S, StepBuf B) {
         if (hist[k]) atomicAdd(&B.class_count[k], hist[k]);
 }
 
-__global__ void k_class_scan(Store S, StepBuf B) {
+__global__ void k_class_scan(Store S, StepBuf B) {  // one warp, two classes per lane
     Counters *cnt = S.cnt;
     if (cnt->error) return;
-    int run = 0;
-    for (int k = 0; k < TN_NCLASS; ++k) {
-        B.class_base[k] = run;
-        B.class_cursor[k] = run;
-        run += B.class_count[k];
-        B.class_count[k] = 0;  // ready for the next step
+    const int lane = threadIdx.x & 31;
+    const int c0 = B.class_count[2 * lane], c1 = B.class_count[2 * lane + 1];
+    int incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
     }
-    cnt->n_order = run;
-    cnt->n_force = 0;
+    const int ex = incl - (c0 + c1);
+    B.class_base[2 * lane] = ex;
+    B.class_cursor[2 * lane] = ex;
+    B.class_base[2 * lane + 1] = ex + c0;
+    B.class_cursor[2 * lane + 1] = ex + c0;
+    B.class_count[2 * lane] = 0;  // ready for the next step
+    B.class_count[2 * lane + 1] = 0;
+    if (lane == 31) {
+        cnt->n_order = incl;
+        cnt->n_force = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
