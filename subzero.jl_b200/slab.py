@@ -190,6 +190,93 @@ class SlabRank:
         return float(d.max()) if len(d) else 0.0
 
 
+# ---- rebuild: migration of ownership + fresh halo lists ------------------------------------------------
+# Two collective rounds (all_gather of python objects; set-up path, not per step):
+#   1. every rank downloads its owned floes, re-assigns them by centroid and hands migrants (full
+#      record incl. Monte-Carlo points) to their new owner;
+#   2. with the post-migration owned set, every rank sends the floes each other rank needs as halo.
+def _rebuild_round1(me):
+    fa = me.h.download_floes(mc=False)
+    idx = np.nonzero(me.owned)[0]
+    own = extract(fa, idx)
+    src = extract(me.local, idx)  # the static Monte-Carlo points live in the uploaded list
+    own.mc_offsets, own.mc_x, own.mc_y = src.mc_offsets, src.mc_x, src.mc_y
+    g = me.gidx[idx]
+    new_owner = me.owner_of(_wrap(own.centroid_x, me))
+    out = {}
+    for s_ in range(me.world):
+        if s_ != me.rank:
+            sel = np.nonzero(new_owner == s_)[0]
+            if len(sel):
+                out[s_] = (g[sel], extract(own, sel))
+    keep = np.nonzero(new_owner == me.rank)[0]
+    me._own, me._own_g = extract(own, keep), g[keep]
+    return out
+
+
+def _wrap(cx, me):
+    """Centroids of floes that left a periodic domain are owned by the slab of their wrapped image."""
+    if not me.period_x:
+        return cx
+    lo = me.edges[0]
+    return lo + np.mod(cx - lo, me.period_x)
+
+
+def _rebuild_round2(me, all1):
+    parts, gl = [me._own], [me._own_g]
+    for s_ in range(me.world):
+        if s_ != me.rank and me.rank in all1[s_]:
+            g, fa = all1[s_][me.rank]
+            parts.append(fa)
+            gl.append(g)
+    own, g = concat(parts), np.concatenate(gl)
+    order = np.argsort(g, kind="stable")
+    me._own, me._own_g = extract(own, order), g[order]
+    out, me._send_sel = {}, {}
+    for s_ in range(me.world):
+        if s_ == me.rank:
+            continue
+        sel = np.nonzero(me.needs(me._own.centroid_x, me._own.rmax, r=s_))[0]
+        if len(sel):
+            me._send_sel[s_] = sel
+            out[s_] = (me._own_g[sel], strip_mc(extract(me._own, sel)))
+    return out
+
+
+def _rebuild_finish(me, all2):
+    parts, gl, ow = [me._own], [me._own_g], [np.full(me._own.n, me.rank, dtype=np.int64)]
+    for s_ in range(me.world):
+        if s_ != me.rank and me.rank in all2[s_]:
+            g, fa = all2[s_][me.rank]
+            parts.append(fa)
+            gl.append(g)
+            ow.append(np.full(len(g), s_, dtype=np.int64))
+    me.build(concat(parts), np.concatenate(gl), np.concatenate(ow))
+    me.set_send_lists({s_: me._own_g[sel] for s_, sel in me._send_sel.items()})
+    device = me.sbuf[0].device if getattr(me, "sbuf", None) else "cpu"
+    me.attach(me.h)
+    me.make_buffers(device)
+    del me._own, me._own_g, me._send_sel
+
+
+def rebuild(me):
+    """Collective over torch.distributed: call on every rank (e.g. when any rank reports stale())."""
+    import torch.distributed as dist
+    all1 = [None] * me.world
+    dist.all_gather_object(all1, _rebuild_round1(me))
+    all2 = [None] * me.world
+    dist.all_gather_object(all2, _rebuild_round2(me, all1))
+    _rebuild_finish(me, all2)
+
+
+def rebuild_local(ranks):
+    """The same for ranks emulated in one process."""
+    all1 = [_rebuild_round1(r) for r in ranks]
+    all2 = [_rebuild_round2(r, all1) for r in ranks]
+    for r in ranks:
+        _rebuild_finish(r, all2)
+
+
 def exchange_local(ranks):
     """Single-process stand-in for the send/recv (tests: several ranks emulated on one device or
     on the CPU oracle): pack on the owner, hand the buffer over, unpack on the copy holder."""

@@ -27,6 +27,8 @@ def gloo_worker(rank, world, port, q):
         me.attach(synth.setup_handle(f, lib, threads=1))
         me.make_buffers(torch.device("cpu"))
         for t in range(3):
+            if t == 2:
+                slab.rebuild(me)  # collective: migration + fresh halo lists through all_gather_object
             me.exchange()
             me.h.step(t, True)
         h = synth.setup_handle(f, lib, threads=1)

@@ -64,6 +64,45 @@ def test_emulated_ranks_match_single_rank_oracle(walls, world, oracle_lib):
     check_against_single(f, oracle_lib, ranks, 3)
 
 
+@pytest.mark.parametrize("walls,world", [("periodic", 3), ("collision", 2)])
+def test_rebuild_migrates_ownership_and_keeps_results(walls, world, oracle_lib):
+    """Fast floes + a small skin: the halo lists go stale, every rank rebuilds (ownership migrates to the
+    slab the centroid moved into, halo lists are renewed) and the owned results still equal the single-rank run."""
+    import torch
+    f = synth.make_field(1200, scale=1.02, walls=walls, npoints=20, cache=False)
+    fields.perturb_state(f.floes)
+    f.floes.u = f.floes.u * 40.0  # up to 4 m/s: 40 m per step
+    f.floes.v = f.floes.v * 40.0
+    period = f.L if walls == "periodic" else None
+    ranks = slab.partition_global(f.floes, world, period, skin=60.0, period_y=period)
+    for r in ranks:
+        r.attach(make_handle(f, oracle_lib))
+        r.make_buffers(torch.device("cpu"))
+    owner0 = [r.gidx[r.owned].copy() for r in ranks]
+    rebuilds = 0
+    for t in range(8):
+        if any(r.stale() for r in ranks):
+            slab.rebuild_local(ranks)
+            rebuilds += 1
+        slab.exchange_local(ranks)
+        for r in ranks:
+            r.h.step(t, True)
+    assert rebuilds >= 2
+    assert any(not np.array_equal(o, r.gidx[r.owned]) for o, r in zip(owner0, ranks))  # something migrated
+    h = make_handle(f, oracle_lib)
+    for t in range(8):
+        h.step(t, True)
+    ref = h.download_floes(mc=False)
+    seen = np.zeros(f.floes.n, dtype=bool)
+    for r in ranks:
+        g, own = r.owned_state()
+        seen[g] = True
+        bad = compare_state(own, slab.extract(ref, g), exact=STATE_FIELDS)
+        bad = [b for b in bad if not b.startswith(("mc_offsets", "ghost_"))]
+        assert not bad, "rank %d: %s" % (r.rank, "\n".join(bad))
+    assert seen.all()
+
+
 def test_two_process_gloo_halo_exchange():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
