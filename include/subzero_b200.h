@@ -81,7 +81,7 @@ typedef struct sz_config {
     double rho_i, max_floe_height, maximum_xi, stress_lambda;
     /* CouplingSettings, process_settings.jl:133-167 */
     int32_t coupling_dd;         /* Δd knot buffer; does not change a bilinear result */
-    int32_t two_way_coupling_on; /* must be 0: two-way coupling is SURVEY §8(f) "next" */
+    int32_t two_way_coupling_on; /* coupling.jl:1617-1680: ice/atmosphere stress on the ocean per grid cell */
     /* Simulation.Δt (Int seconds), simulation.jl:49-81 */
     int32_t dt;
     /* execution */
@@ -149,6 +149,18 @@ int32_t SZ_FN(set_grid)(sz_handle *h, int32_t Nx, int32_t Ny, double x0, double 
 int32_t SZ_FN(set_fields)(sz_handle *h, const double *ocean_u, const double *ocean_v,
                           const double *ocean_hflx, const double *atmos_u,
                           const double *atmos_v);
+/* Ocean.temp and Atmos.temp (oceans.jl:74-99, atmos.jl:4-16), same layout; only read by two-way coupling
+ * (ocean.hflx_factor = dt k / (rho_i L) (T_ocean - T_atmos), coupling.jl:1676-1677).  NULL = zeros. */
+int32_t SZ_FN(set_temperatures)(sz_handle *h, const double *ocean_temp, const double *atmos_temp);
+/* Two-way coupling results (coupling.jl:1617-1680), each (Nx+1) x (Ny+1) like the inputs: ocean.tau_x,
+ * ocean.tau_y, ocean.si_frac and the updated ocean.hflx_factor (which the next coupling step interpolates).
+ * Any pointer may be NULL. */
+int32_t SZ_FN(get_ocean_fields)(sz_handle *h, double *tau_x, double *tau_y, double *si_frac, double *hflx_factor);
+/* The floe -> grid-cell registry of the last coupling step (grid.floe_locations + ocean.scells,
+ * coupling.jl:1329-1454), sorted by (cell y, cell x, floe): cell_xy [n][2] 1-based cell indices, floe [n]
+ * 1-based, vals [n][5] = sum of -tau_x_ocn, sum of -tau_y_ocn, npoints, dx, dy (the periodic shift that moves
+ * the floe into the cell).  Call with NULL arrays to get *n. */
+int32_t SZ_FN(get_cell_floes)(sz_handle *h, int64_t *n, int64_t *cell_xy, int64_t *floe, double *vals);
 /* Domain, domains.jl:4-34.  rect[w] = {xmin, xmax, ymin, ymax} of wall w's rectangle
  * (boundaries.jl:29-33,65-69,102-106,139-143); uv[w] = MovingBoundary velocity.  Topography:
  * closed rings in CSR form plus centroid / rmax per element (topography.jl:5-9). */

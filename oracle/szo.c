@@ -40,6 +40,13 @@ typedef struct {
     int n, cap;
 } intlist;
 
+typedef struct cellrec {
+    int ix, iy;          /* 0-based cell (grid line) indices after the periodic shift */
+    int64_t floe;
+    double tx, ty, dx, dy;
+    int64_t npts;
+} cellrec;
+
 struct sz_handle {
     sz_config cfg;
     char err[512];
@@ -76,6 +83,12 @@ struct sz_handle {
     int64_t *cand, *pairs, *overlap, *fuse;
     int64_t n_cand, n_pairs, n_overlap, n_fuse, n_domain_pairs, n_clip_fail;
     double ms[8];
+    /* two-way coupling */
+    double *ocn_temp, *atm_temp, *taux, *tauy, *sifrac;
+    struct cellrec *crec;      /* registry sorted by (cell, floe) after step_coupling */
+    int64_t n_crec;
+    struct cellrec **frec;     /* per-floe records of the running coupling step */
+    int *nfrec;
     /* halo lists (slab decomposition) */
     int n_lists;
     int64_t *hl_off, *hl_idx;
@@ -117,7 +130,6 @@ const char *szo_last_error(sz_handle *h) { return h ? h->err : "null handle"; }
 
 int32_t szo_create(const sz_config *cfg, sz_handle **out) {
     if (!cfg || !out) return SZ_ERR_INVALID;
-    if (cfg->two_way_coupling_on) return SZ_ERR_UNSUPPORTED;
     sz_handle *h = (sz_handle *)calloc(1, sizeof(sz_handle));
     if (!h) return SZ_ERR_NOMEM;
     h->cfg = *cfg;
@@ -156,6 +168,7 @@ void szo_destroy(sz_handle *h) {
     if (!h) return;
     free_floes(h);
     free(h->ocn_u); free(h->ocn_v); free(h->ocn_hflx); free(h->atm_u); free(h->atm_v);
+    free(h->ocn_temp); free(h->atm_temp); free(h->taux); free(h->tauy); free(h->sifrac); free(h->crec);
     for (int k = 0; k < h->n_topo; ++k) free(h->topo_ring[k]);
     free(h->topo_ring); free(h->topo_np); free(h->topo_cx); free(h->topo_cy); free(h->topo_rmax);
     free(h->cand); free(h->pairs); free(h->overlap); free(h->fuse);
@@ -217,6 +230,40 @@ int32_t szo_set_fields(sz_handle *h, const double *ou, const double *ov, const d
     free(h->ocn_u); free(h->ocn_v); free(h->ocn_hflx); free(h->atm_u); free(h->atm_v);
     h->ocn_u = dupfield(ou, n); h->ocn_v = dupfield(ov, n); h->ocn_hflx = dupfield(oh, n);
     h->atm_u = dupfield(au, n); h->atm_v = dupfield(av, n);
+    free(h->ocn_temp); free(h->atm_temp); free(h->taux); free(h->tauy); free(h->sifrac);
+    h->ocn_temp = dupfield(NULL, n); h->atm_temp = dupfield(NULL, n);
+    h->taux = dupfield(NULL, n); h->tauy = dupfield(NULL, n); h->sifrac = dupfield(NULL, n);
+    return SZ_OK;
+}
+
+int32_t szo_set_temperatures(sz_handle *h, const double *ot, const double *at) {
+    if (!h || !h->ocn_u) return fail(h, SZ_ERR_INVALID, "set_temperatures before set_fields");
+    size_t n = (size_t)(h->Nx + 1) * (size_t)(h->Ny + 1);
+    free(h->ocn_temp); free(h->atm_temp);
+    h->ocn_temp = dupfield(ot, n); h->atm_temp = dupfield(at, n);
+    return SZ_OK;
+}
+
+int32_t szo_get_ocean_fields(sz_handle *h, double *tx, double *ty, double *si, double *hf) {
+    if (!h || !h->ocn_u) return fail(h, SZ_ERR_INVALID, "get_ocean_fields before set_fields");
+    size_t n = (size_t)(h->Nx + 1) * (size_t)(h->Ny + 1);
+    if (tx) memcpy(tx, h->taux, sizeof(double) * n);
+    if (ty) memcpy(ty, h->tauy, sizeof(double) * n);
+    if (si) memcpy(si, h->sifrac, sizeof(double) * n);
+    if (hf) memcpy(hf, h->ocn_hflx, sizeof(double) * n);
+    return SZ_OK;
+}
+
+int32_t szo_get_cell_floes(sz_handle *h, int64_t *n, int64_t *cell_xy, int64_t *floe, double *vals) {
+    if (!h || !n) return SZ_ERR_INVALID;
+    *n = h->n_crec;
+    for (int64_t k = 0; k < h->n_crec && cell_xy && floe && vals; ++k) {
+        const cellrec *r = &h->crec[k];
+        cell_xy[2 * k] = r->ix + 1; cell_xy[2 * k + 1] = r->iy + 1;
+        floe[k] = r->floe + 1;
+        vals[5 * k] = r->tx; vals[5 * k + 1] = r->ty; vals[5 * k + 2] = (double)r->npts;
+        vals[5 * k + 3] = r->dx; vals[5 * k + 4] = r->dy;
+    }
     return SZ_OK;
 }
 
@@ -1023,8 +1070,38 @@ static inline double bilinear(const double *F, int Nx, int Ny, int i0, int i1, i
     return (1 - wy) * ((1 - wx) * f00 + wx * f10) + wy * ((1 - wx) * f01 + wx * f11);
 }
 
+/* shift_cell_idx, coupling.jl:1155-1182 (1-based idx, nlines = N + 1) */
+static int shift_cell_idx(int idx, int nlines, int periodic) {
+    if (!periodic) return idx;
+    int ncells = nlines - 1;
+    return idx < 1 ? (idx + ncells) : (ncells < idx ? (idx - ncells) : idx);
+}
+
+/* floe_to_grid_info! + add_point!, coupling.jl:1329-1454, on the per-floe record list (the reference merges
+ * into a cell's LAST entry when it belongs to the same floe; floes are visited one after the other, so that is
+ * "one entry per (cell, floe)") */
+static void floe_to_grid_info(sz_handle *h, cellrec **list, int *n, int *cap, int64_t floe, int xidx, int yidx, double tx,
+                              double ty) {
+    int per_x = h->kind[2] == SZ_BOUNDARY_PERIODIC, per_y = h->kind[0] == SZ_BOUNDARY_PERIODIC;
+    int sx = shift_cell_idx(xidx, h->Nx + 1, per_x), sy = shift_cell_idx(yidx, h->Ny + 1, per_y);
+    double ddx = (sx - xidx) * h->dx, ddy = (sy - yidx) * h->dy;
+    for (int k = 0; k < *n; ++k)
+        if ((*list)[k].ix == sx - 1 && (*list)[k].iy == sy - 1) {
+            (*list)[k].tx += -tx; (*list)[k].ty += -ty; (*list)[k].npts += 1;
+            return;
+        }
+    if (*n == *cap) {
+        *cap = *cap ? 2 * *cap : 4;
+        *list = (cellrec *)realloc(*list, sizeof(cellrec) * (size_t)*cap);
+    }
+    cellrec *r = &(*list)[(*n)++];
+    r->ix = sx - 1; r->iy = sy - 1; r->floe = floe; r->tx = -tx; r->ty = -ty; r->dx = ddx; r->dy = ddy; r->npts = 1;
+}
+
 static void coupling_one_floe(sz_handle *h, int64_t i) {
     const sz_config *c = &h->cfg;
+    cellrec *rl = NULL;
+    int nrl = 0, caprl = 0;
     int per_x = h->kind[2] == SZ_BOUNDARY_PERIODIC, per_y = h->kind[0] == SZ_BOUNDARY_PERIODIC;
     double a = h->alpha[i];
     double tot_x = 0, tot_y = 0, tot_trq = 0, tot_hflx = 0;
@@ -1041,6 +1118,8 @@ static void coupling_one_floe(sz_handle *h, int64_t i) {
     }
     if (npoints == 0) {
         h->status[i] = SZ_STATUS_REMOVE; /* coupling.jl:1507-1508 */
+        h->frec[i] = NULL;
+        h->nfrec[i] = 0;
         free(X);
         return;
     }
@@ -1081,7 +1160,13 @@ static void coupling_one_floe(sz_handle *h, int64_t i) {
         double tx = tax + tpx + tox, ty = tay + tpy + toy;
         double trq = (-tx * sin(th) + ty * cos(th)) * rad;
         tot_x += tx; tot_y += ty; tot_trq += trq; tot_hflx += hfl;
+        { /* find_center_cell_index, coupling.jl:466-470 */
+            int xidx = (int)floor((x - h->x0) / h->dx + 0.5) + 1, yidx = (int)floor((y - h->y0) / h->dy + 0.5) + 1;
+            floe_to_grid_info(h, &rl, &nrl, &caprl, i, xidx, yidx, tox, toy);
+        }
     }
+    h->frec[i] = rl;
+    h->nfrec[i] = nrl;
     h->fxOA[i] = tot_x / npoints * h->area[i]; /* :1583-1586 */
     h->fyOA[i] = tot_y / npoints * h->area[i];
     h->trqOA[i] = tot_trq / npoints * h->area[i];
@@ -1089,13 +1174,128 @@ static void coupling_one_floe(sz_handle *h, int64_t i) {
     free(X);
 }
 
+static int cmp_cellrec(const void *a, const void *b) {
+    const cellrec *x = (const cellrec *)a, *y = (const cellrec *)b;
+    if (x->iy != y->iy) return x->iy < y->iy ? -1 : 1;
+    if (x->ix != y->ix) return x->ix < y->ix ? -1 : 1;
+    return (x->floe > y->floe) - (x->floe < y->floe);
+}
+
+/* center_cell_coords + check_cell_bounds, coupling.jl:931-1140 (ix, iy 1-based): xmin, xmax, ymin, ymax */
+static void center_cell_coords(const sz_handle *h, int ix, int iy, double out[4]) {
+    int per_x = h->kind[2] == SZ_BOUNDARY_PERIODIC, per_y = h->kind[0] == SZ_BOUNDARY_PERIODIC;
+    double xmin = (ix - 1.5) * h->dx + h->x0, xmax = xmin + h->dx;
+    double ymin = (iy - 1.5) * h->dy + h->y0, ymax = ymin + h->dy;
+    if (!per_x) {
+        xmin = xmin < h->x0 ? h->x0 : (xmin > h->xf ? h->xf : xmin);
+        xmax = xmax > h->xf ? h->xf : (xmax < h->x0 ? h->x0 : xmax);
+    }
+    if (!per_y) {
+        ymin = ymin < h->y0 ? h->y0 : (ymin > h->yf ? h->yf : ymin);
+        ymax = ymax > h->yf ? h->yf : (ymax < h->y0 ? h->y0 : ymax);
+    }
+    out[0] = xmin; out[1] = xmax; out[2] = ymin; out[3] = ymax;
+}
+
+/* calc_two_way_coupling!, coupling.jl:1617-1680 */
+static void two_way_coupling(sz_handle *h) {
+    const sz_config *c = &h->cfg;
+    int nx1 = h->Nx + 1, ny1 = h->Ny + 1;
+    double cell_area = h->dx * h->dy;
+    /* first record of every cell in the (cell, floe)-sorted registry */
+    int64_t *first = (int64_t *)calloc((size_t)nx1 * ny1 + 1, sizeof(int64_t));
+    for (int64_t k = 0; k < h->n_crec; ++k) first[(size_t)h->crec[k].iy * nx1 + h->crec[k].ix + 1]++;
+    for (size_t q = 0; q < (size_t)nx1 * ny1; ++q) first[q + 1] += first[q];
+#pragma omp parallel
+    {
+        szo_regions R;
+        szo_regions_init(&R);
+        szo_pt *T = NULL;
+        int capT = 0;
+#pragma omp for schedule(dynamic, 16)
+        for (int q = 0; q < nx1 * ny1; ++q) {
+            int ix = q % nx1, iy = q / nx1;
+            double tx = 0, ty = 0, si = 0;
+            if (first[q + 1] > first[q]) {
+                double b[4];
+                szo_pt cell[5];
+                center_cell_coords(h, ix + 1, iy + 1, b);
+                make_wall_ring(cell, b);
+                for (int64_t k = first[q]; k < first[q + 1]; ++k) {
+                    const cellrec *r = &h->crec[k];
+                    int np = h->npts[r->floe];
+                    if (np > capT) { capT = 2 * np; T = (szo_pt *)realloc(T, sizeof(szo_pt) * (size_t)capT); }
+                    for (int v = 0; v < np; ++v) { T[v].x = h->ring[r->floe][v].x + r->dx; T[v].y = h->ring[r->floe][v].y + r->dy; }
+                    szo_clip(cell, 5, T, np, &R);
+                    double a = 0;
+                    for (int g = 0; g < R.nreg; ++g) a += szo_ring_area(R.pts + R.off[g], R.off[g + 1] - R.off[g]);
+                    if (a > 0) {
+                        tx += (r->tx / (double)r->npts) * a;
+                        ty += (r->ty / (double)r->npts) * a;
+                        si += a;
+                    }
+                }
+                if (si > 0) {
+                    tx /= si; ty /= si;
+                    si /= cell_area;
+                }
+            }
+            double du = h->atm_u[q] - h->ocn_u[q], dv = h->atm_v[q] - h->ocn_v[q];
+            double ocn_frac = 1 - si, norm = sqrt(du * du + dv * dv);
+            tx += c->rho_a * c->Cd_ao * ocn_frac * norm * du;
+            ty += c->rho_a * c->Cd_ao * ocn_frac * norm * dv;
+            h->taux[q] = tx; h->tauy[q] = ty; h->sifrac[q] = si;
+            h->ocn_hflx[q] = c->dt * c->k / (c->rho_i * c->L) * (h->ocn_temp[q] - h->atm_temp[q]);
+        }
+        szo_regions_free(&R);
+        free(T);
+    }
+    free(first);
+}
+
 int32_t szo_step_coupling(sz_handle *h) {
     if (!h || !h->have_domain || !h->ocn_u) return fail(h, SZ_ERR_INVALID, "step_coupling before set_domain/set_fields");
     if (h->n != h->n_init) return fail(h, SZ_ERR_INVALID, "step_coupling with ghosts present (call remove_ghosts)");
     double t0 = now_ms();
+    h->frec = (cellrec **)calloc((size_t)(h->n > 0 ? h->n : 1), sizeof(cellrec *));
+    h->nfrec = (int *)calloc((size_t)(h->n > 0 ? h->n : 1), sizeof(int));
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < h->n; ++i) coupling_one_floe(h, i);
+    /* grid.floe_locations / ocean.scells: gather the per-floe lists, sort by (cell, floe) */
+    int64_t tot = 0;
+    for (int64_t i = 0; i < h->n; ++i) tot += h->nfrec[i];
+    free(h->crec);
+    h->crec = (cellrec *)malloc(sizeof(cellrec) * (size_t)(tot > 0 ? tot : 1));
+    h->n_crec = 0;
+    for (int64_t i = 0; i < h->n; ++i) {
+        for (int k = 0; k < h->nfrec[i]; ++k) h->crec[h->n_crec++] = h->frec[i][k];
+        free(h->frec[i]);
+    }
+    free(h->frec); free(h->nfrec);
+    h->frec = NULL; h->nfrec = NULL;
+    qsort(h->crec, (size_t)h->n_crec, sizeof(cellrec), cmp_cellrec);
+    if (h->cfg.two_way_coupling_on) two_way_coupling(h);
     h->ms[4] = now_ms() - t0;
+    return SZ_OK;
+}
+
+/* ---- test hooks (oracle only; pin the index semantics against test_coupling.jl:276-462) ------------------- */
+int32_t szo_test_center_cell_coords(sz_handle *h, int32_t ix, int32_t iy, double out[4]) {
+    if (!h || !h->have_domain || h->Nx == 0) return SZ_ERR_INVALID;
+    center_cell_coords(h, ix, iy, out);
+    return SZ_OK;
+}
+/* feeds (xidx, yidx, tau) sequences of ONE floe through floe_to_grid_info! and leaves the result in the registry */
+int32_t szo_test_floe_to_grid(sz_handle *h, int64_t floe, int32_t n, const int32_t *xidx, const int32_t *yidx,
+                              const double *tx, const double *ty) {
+    if (!h || !h->have_domain || h->Nx == 0) return SZ_ERR_INVALID;
+    cellrec *rl = NULL;
+    int nrl = 0, cap = 0;
+    for (int k = 0; k < n; ++k) floe_to_grid_info(h, &rl, &nrl, &cap, floe - 1, xidx[k], yidx[k], tx[k], ty[k]);
+    free(h->crec);
+    h->crec = rl;
+    h->n_crec = nrl;
+    qsort(h->crec, (size_t)h->n_crec, sizeof(cellrec), cmp_cellrec);
     return SZ_OK;
 }
 

@@ -87,6 +87,9 @@ class Library:
         "version": (C.c_char_p, []),
         "set_grid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_double] * 4),
         "set_fields": (C.c_int32, [C.c_void_p] + [c_double_p] * 5),
+        "set_temperatures": (C.c_int32, [C.c_void_p, c_double_p, c_double_p]),
+        "get_ocean_fields": (C.c_int32, [C.c_void_p] + [c_double_p] * 4),
+        "get_cell_floes": (C.c_int32, [C.c_void_p, c_i64_p, c_i64_p, c_i64_p, c_double_p]),
         "set_domain": (C.c_int32, [C.c_void_p, c_i32_p, c_double_p, c_double_p, c_double_p,
                                    C.c_int32, c_i64_p, c_double_p, c_double_p, c_double_p]),
         "get_domain": (C.c_int32, [C.c_void_p, c_double_p, c_double_p]),
@@ -258,6 +261,30 @@ class Handle:
             assert a.shape == (self.Nx + 1, self.Ny + 1), (a.shape, self.Nx, self.Ny)
             arrs.append(np.asfortranarray(a).ravel(order="F"))  # element [ix + (Nx+1) iy]
         self._ck(self.lib.set_fields(self.h, *[_dp(a) for a in arrs]))
+
+    def set_temperatures(self, ocean_temp, atmos_temp):
+        arrs = []
+        for a in (ocean_temp, atmos_temp):
+            a = np.asarray(a, dtype=np.float64)
+            assert a.shape == (self.Nx + 1, self.Ny + 1), (a.shape, self.Nx, self.Ny)
+            arrs.append(np.asfortranarray(a).ravel(order="F"))
+        self._ck(self.lib.set_temperatures(self.h, *[_dp(a) for a in arrs]))
+
+    def ocean_fields(self):
+        """(tau_x, tau_y, si_frac, hflx_factor), each (Nx+1, Ny+1) indexed [x, y]."""
+        out = [np.zeros((self.Nx + 1) * (self.Ny + 1)) for _ in range(4)]
+        self._ck(self.lib.get_ocean_fields(self.h, *[_dp(a) for a in out]))
+        return [a.reshape((self.Nx + 1, self.Ny + 1), order="F") for a in out]
+
+    def cell_floes(self):
+        """The floe -> cell registry: (cell_xy [n,2] 1-based, floe [n] 1-based, vals [n,5])."""
+        n = C.c_int64(0)
+        self._ck(self.lib.get_cell_floes(self.h, C.byref(n), None, None, None))
+        cell = np.zeros((max(n.value, 1), 2), dtype=np.int64)
+        floe = np.zeros(max(n.value, 1), dtype=np.int64)
+        vals = np.zeros((max(n.value, 1), 5))
+        self._ck(self.lib.get_cell_floes(self.h, C.byref(n), _ip(cell), _ip(floe), _dp(vals)))
+        return cell[:n.value], floe[:n.value], vals[:n.value]
 
     def set_domain(self, kinds, vals, uv, rect, topo_rings=(), topo_centroid=None, topo_rmax=None):
         kinds = np.ascontiguousarray(kinds, dtype=np.int32)

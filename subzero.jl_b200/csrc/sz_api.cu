@@ -29,6 +29,8 @@ struct sz_handle {
     DomainDev hD;
     Store S;
     StepBuf B;
+    CouplingBuf CB;
+    int n_crec_host;
     std::vector<FloeArr> floe_arrays;   // persistent per-floe arrays (grown with a copy)
     std::vector<void **> floe_scratch;  // int [cap_floes+1] scratch arrays (grown without)
     int n_init, n_total, n_verts, n_verts_init;
@@ -211,6 +213,15 @@ static int32_t set_row_cap(sz_handle *h, int cap) {
     h->B.cap_rows = cap;
     return SZ_OK;
 }
+static int32_t set_crec_cap(sz_handle *h, int cap) {
+    CouplingBuf &C = h->CB;
+    dfree(C.rec_cell); dfree(C.rec_floe); dfree(C.rec_npts); dfree(C.rec_t); dfree(C.rec_d); dfree(C.rec_area); dfree(C.perm); dfree(C.big_recs);
+    CK(dalloc(&C.rec_cell, (size_t)cap)); CK(dalloc(&C.rec_floe, (size_t)cap)); CK(dalloc(&C.rec_npts, (size_t)cap));
+    CK(dalloc(&C.rec_t, (size_t)cap)); CK(dalloc(&C.rec_d, (size_t)cap)); CK(dalloc(&C.rec_area, (size_t)cap));
+    CK(dalloc(&C.perm, (size_t)cap)); CK(dalloc(&C.big_recs, (size_t)cap));
+    C.cap_crec = cap;
+    return SZ_OK;
+}
 static int32_t set_fuse_cap(sz_handle *h, int cap) {
     dfree(h->B.fuse_pairs);
     CK(dalloc(&h->B.fuse_pairs, (size_t)cap));
@@ -221,7 +232,6 @@ static int32_t set_fuse_cap(sz_handle *h, int cap) {
 extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     if (!cfg || !out) return SZ_ERR_INVALID;
     *out = nullptr;
-    if (cfg->two_way_coupling_on) return SZ_ERR_UNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) return SZ_ERR_CUDA;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return SZ_ERR_CUDA;
@@ -229,6 +239,8 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     if (!h) return SZ_ERR_NOMEM;
     memset(&h->S, 0, sizeof(h->S));
     memset(&h->B, 0, sizeof(h->B));
+    memset(&h->CB, 0, sizeof(h->CB));
+    h->n_crec_host = 0;
     memset(&h->hD, 0, sizeof(h->hD));
     memset(&h->P, 0, sizeof(h->P));
     memset(&h->last, 0, sizeof(h->last));
@@ -280,6 +292,12 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
     dfree(h->d_hl_idx); dfree(h->d_hl_voff);
+    {
+        CouplingBuf &C = h->CB;
+        dfree(C.rec_cell); dfree(C.rec_floe); dfree(C.rec_npts); dfree(C.rec_t); dfree(C.rec_d); dfree(C.rec_area);
+        dfree(C.cell_count); dfree(C.cell_start); dfree(C.cell_fill); dfree(C.perm); dfree(C.big_recs); dfree(C.scan_block);
+        dfree(S.ocn_temp); dfree(S.atm_temp); dfree(S.taux); dfree(S.tauy); dfree(S.sifrac);
+    }
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int k = 0; k < NEV; ++k) cudaEventDestroy(h->ev[k]);
     cudaStreamDestroy(h->L.stream);
@@ -311,6 +329,15 @@ extern "C" int32_t sz_set_fields(sz_handle *h, const double *ou, const double *o
         CK(dalloc(&S.atm_u, n)); CK(dalloc(&S.atm_v, n));
         dfree(S.fields8);
         CK(dalloc(&S.fields8, 8 * n));
+        dfree(S.ocn_temp); dfree(S.atm_temp); dfree(S.taux); dfree(S.tauy); dfree(S.sifrac);
+        CK(dalloc(&S.ocn_temp, n)); CK(dalloc(&S.atm_temp, n)); CK(dalloc(&S.taux, n)); CK(dalloc(&S.tauy, n)); CK(dalloc(&S.sifrac, n));
+        double *z[5] = {S.ocn_temp, S.atm_temp, S.taux, S.tauy, S.sifrac};
+        for (int k = 0; k < 5; ++k) CK(cudaMemsetAsync(z[k], 0, sizeof(double) * n, h->L.stream));
+        CouplingBuf &C = h->CB;
+        dfree(C.cell_count); dfree(C.cell_start); dfree(C.cell_fill); dfree(C.scan_block);
+        CK(dalloc(&C.cell_count, n + 2)); CK(dalloc(&C.cell_start, n + 2)); CK(dalloc(&C.cell_fill, n + 2));
+        CK(dalloc(&C.scan_block, n / 4096 + 8));
+        C.cap_cells = (int)n;
         h->field_n = n;
     }
     const double *src[5] = {ou, ov, oh, au, av};
@@ -323,6 +350,59 @@ extern "C" int32_t sz_set_fields(sz_handle *h, const double *ou, const double *o
     CK(cudaStreamSynchronize(h->L.stream));
     CK(cudaGetLastError());
     h->have_fields = true;
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_set_temperatures(sz_handle *h, const double *ot, const double *at) {
+    if (!h || !h->have_fields) return fail(h, SZ_ERR_INVALID, "set_temperatures before set_fields");
+    cudaSetDevice(h->cfg.device);
+    size_t n = h->field_n;
+    const double *src[2] = {ot, at};
+    double *dst[2] = {h->S.ocn_temp, h->S.atm_temp};
+    for (int k = 0; k < 2; ++k) {
+        if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], sizeof(double) * n, cudaMemcpyHostToDevice, h->L.stream));
+        else CK(cudaMemsetAsync(dst[k], 0, sizeof(double) * n, h->L.stream));
+    }
+    CK(cudaStreamSynchronize(h->L.stream));
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_get_ocean_fields(sz_handle *h, double *tx, double *ty, double *si, double *hf) {
+    if (!h || !h->have_fields) return fail(h, SZ_ERR_INVALID, "get_ocean_fields before set_fields");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    size_t n = h->field_n;
+    double *dst[4] = {tx, ty, si, hf};
+    const double *src[4] = {h->S.taux, h->S.tauy, h->S.sifrac, h->S.ocn_hflx};
+    for (int k = 0; k < 4; ++k)
+        if (dst[k]) CK(cudaMemcpy(dst[k], src[k], sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_get_cell_floes(sz_handle *h, int64_t *n, int64_t *cell_xy, int64_t *floe, double *vals) {
+    if (!h || !n) return SZ_ERR_INVALID;
+    *n = h->n_crec_host;
+    if (!cell_xy || !floe || !vals || h->n_crec_host == 0) return SZ_OK;
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    const int m = h->n_crec_host, nx1 = h->P.Nx + 1;
+    std::vector<int> perm(m), rc(m), rf(m), rn(m);
+    std::vector<double2> rt(m), rd(m);
+    CouplingBuf &C = h->CB;
+    CK(cudaMemcpy(perm.data(), C.perm, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rc.data(), C.rec_cell, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rf.data(), C.rec_floe, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rn.data(), C.rec_npts, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rt.data(), C.rec_t, sizeof(double2) * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rd.data(), C.rec_d, sizeof(double2) * m, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < m; ++k) {
+        int r = perm[k];
+        cell_xy[2 * k] = rc[r] % nx1 + 1;
+        cell_xy[2 * k + 1] = rc[r] / nx1 + 1;
+        floe[k] = rf[r] + 1;
+        vals[5 * k] = rt[r].x; vals[5 * k + 1] = rt[r].y; vals[5 * k + 2] = (double)rn[r];
+        vals[5 * k + 3] = rd[r].x; vals[5 * k + 4] = rd[r].y;
+    }
     return SZ_OK;
 }
 
@@ -496,6 +576,7 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     long long want_rows = 2 * want_pool;
     if (want_rows > B.cap_rows || !B.rows) { int32_t rc = set_row_cap(h, (int)std::min<long long>(want_rows, 1ll << 28)); if (rc) return rc; }
     if (!B.fuse_pairs) { int32_t rc = set_fuse_cap(h, std::max(1024, S.cap_floes)); if (rc) return rc; }
+    if (h->cfg.two_way_coupling_on && h->CB.cap_crec < 6 * n_init + 4096) { int32_t rc = set_crec_cap(h, 6 * n_init + 4096); if (rc) return rc; }
     // copies
     cudaStream_t st = h->L.stream;
     { int32_t rc = upload_scalars(h, s, n); if (rc) return rc; }
@@ -721,6 +802,10 @@ static int32_t handle_overflow(sz_handle *h, const Counters &c) {
     if (e & ERR_FUSE_CAP) {
         if ((rc = set_fuse_cap(h, std::max(c.n_fuse, h->B.cap_fuse) * 2 + 1024))) return rc;
     }
+    if (e & ERR_CELL_TABLE) return fail(h, SZ_ERR_UNSUPPORTED, "two-way coupling: a floe touches more than 16 grid cells");
+    if (e & ERR_CREC_CAP) {
+        if ((rc = set_crec_cap(h, std::max(c.n_crec, h->CB.cap_crec) * 2 + 1024))) return rc;
+    }
     if (e & ERR_GHOST_CAP) {
         if ((rc = grow_floes(h, c.want_floes * 5 / 4 + 64, h->n_total))) return rc;
     }
@@ -741,6 +826,18 @@ static void enqueue_ghosts(sz_handle *h) {
     // collisions.jl:1171-1172: east/west pass, then north/south pass
     if (h->hD.kind[2] == SZ_BOUNDARY_PERIODIC) szk_ghost_pass(h->L, h->S, h->B, 0, floes_hint(h));
     if (h->hD.kind[0] == SZ_BOUNDARY_PERIODIC) szk_ghost_pass(h->L, h->S, h->B, 1, floes_hint(h));
+}
+
+// one-way: the streaming kernel; two-way: the same integration with the floe -> cell registry, the registry
+// sort, the floe ∩ cell areas and the per-cell pass (coupling.jl:1705-1738)
+static void enqueue_coupling(sz_handle *h, const Launch &L) {
+    if (!h->cfg.two_way_coupling_on) {
+        szk_coupling(L, h->S, h->P);
+        return;
+    }
+    szk_coupling_reg(L, h->S, h->CB, h->P);
+    szk_cells_sort_and_clip(L, h->S, h->CB, h->P, h->CB.cap_crec);
+    szk_cells_final(L, h->S, h->CB, h->P);
 }
 
 static double ev_ms(sz_handle *h, int a, int b) {
@@ -808,12 +905,19 @@ extern "C" int32_t sz_step_coupling(sz_handle *h) {
     if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "step_coupling before upload_floes");
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step_coupling with ghosts present (call remove_ghosts)");
     cudaSetDevice(h->cfg.device);
-    cudaEventRecord(h->ev[0], h->L.stream);
-    szk_coupling(h->L, h->S, h->P);
-    szk_apply_coupling_tags(h->L, h->S);
-    cudaEventRecord(h->ev[1], h->L.stream);
-    CK(cudaStreamSynchronize(h->L.stream));
-    CK(cudaGetLastError());
+    for (int attempt = 0;; ++attempt) {
+        cudaEventRecord(h->ev[0], h->L.stream);
+        enqueue_coupling(h, h->L);
+        szk_apply_coupling_tags(h->L, h->S);
+        cudaEventRecord(h->ev[1], h->L.stream);
+        int32_t rc = sync_counters(h);
+        if (rc) return rc;
+        CK(cudaGetLastError());
+        if (!h->h_cnt->error) break;
+        if (attempt >= 4) return fail(h, SZ_ERR_CAPACITY, "step_coupling: capacity retry limit");
+        if ((rc = handle_overflow(h, *h->h_cnt))) return rc;
+    }
+    h->n_crec_host = h->cfg.two_way_coupling_on ? h->h_cnt->n_crec : 0;
     h->ms[4] = ev_ms(h, 0, 1);
     return SZ_OK;
 }
@@ -844,7 +948,8 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
         cudaEventRecord(h->ev[0], st);
         enqueue_ghosts(h);
         cudaEventRecord(h->ev[1], st);
-        if (do_coupling) {
+        const bool fork = do_coupling && !h->cfg.two_way_coupling_on;
+        if (fork) {
             // fork: coupling only needs the floe state after add_ghosts! wrapped parents into the domain; it
             // reads nothing the collision kernels write, so it runs beside them on a low-priority stream and
             // fills the issue slots the latency-bound narrow phase leaves idle
@@ -859,16 +964,23 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
         }
         // the ghost count of this step is not known on the host: size grids from the capacity-bounded hint
         szk_collisions(h->L, h->S, h->B, h->P, floes_hint(h), pairs_hint(h), &h->ev[2]);
-        CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         szk_remove_ghosts(h->L, h->S, h->n_verts_init);
         cudaEventRecord(h->ev[5], st);
-        if (do_coupling) {
+        if (fork) {
             cudaStreamWaitEvent(st, h->ev_join, 0);  // join
+            szk_apply_coupling_tags(h->L, h->S);
+        } else if (do_coupling) {
+            // two-way coupling writes ocean.hflx_factor for the NEXT step: it must not run ahead of a collision
+            // phase that may still overflow and be repeated, so it stays in order on this stream
+            cudaEventRecord(h->ev_c0, st);
+            enqueue_coupling(h, h->L);
+            cudaEventRecord(h->ev_c1, st);
             szk_apply_coupling_tags(h->L, h->S);
         }
         cudaEventRecord(h->ev[6], st);
         szk_update(h->L, h->S, h->B, h->P);
         cudaEventRecord(h->ev[7], st);
+        CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         if (!h->h_cnt->error) break;
@@ -888,6 +1000,7 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     h->last = *h->h_cnt;
     h->n_total = h->n_init;
     h->n_verts = h->n_verts_init;
+    if (do_coupling) h->n_crec_host = h->cfg.two_way_coupling_on ? h->h_cnt->n_crec : 0;
     h->ms[0] = ev_ms(h, 0, 1);
     h->ms[1] = ev_ms(h, 1, 2);
     h->ms[2] = ev_ms(h, 2, 3);

@@ -43,6 +43,8 @@ enum : uint32_t {
     ERR_POLY_TOO_LARGE = 64u,
     ERR_DOM_CAP = 128u,
     ERR_GHOST_SLOTS = 256u,
+    ERR_CREC_CAP = 512u,    // floe -> cell registry records
+    ERR_CELL_TABLE = 1024u, // one floe touches more than 32 grid cells
 };
 
 struct Counters {
@@ -58,6 +60,9 @@ struct Counters {
     int n_overlap;
     int n_large;   // work items deferred to the large-polygon kernel
     int n_mid;     // work items the thread-per-item kernel handed to the warp-per-item kernel
+    int n_crec;    // records of the floe -> cell registry (coupling)
+    int n_cbig;    // ... whose ring needs the warp clip kernel
+    int n_ccells;  // number of grid cells (scan length of the registry sort)
     int n_order;   // work items of the thread-per-item kernels (class-sorted)
     int n_force;   // ... of which need contact forces (phase 1)
     uint32_t error;
@@ -113,6 +118,7 @@ struct Store {
     // fields (Nx+1)x(Ny+1), [ix + (Nx+1) iy]
     double *ocn_u, *ocn_v, *ocn_hflx, *atm_u, *atm_v;
     double *fields8;  // the five fields interleaved per node (8 doubles, see sz_kernels_fp.cu)
+    double *ocn_temp, *atm_temp, *taux, *tauy, *sifrac;  // two-way coupling: inputs and per-cell outputs
     Counters *cnt;
     DomainDev *dom;
 };
@@ -158,6 +164,18 @@ struct StepBuf {
     int *scan_block;
 };
 
+// floe -> cell registry (grid.floe_locations / ocean.scells, coupling.jl:1329-1454) of one coupling step
+struct CouplingBuf {
+    int cap_crec, cap_cells;
+    int *rec_cell, *rec_floe, *rec_npts;  // [cap_crec] unsorted records
+    double2 *rec_t, *rec_d;               // sum of -tau_ocn, periodic shift (dx, dy)
+    double *rec_area;                     // area of floe ∩ cell box
+    int *cell_count, *cell_start, *cell_fill;  // [cells + 1] counting sort by cell
+    int *perm;                            // [cap_crec] record indices sorted by (cell, floe)
+    int *big_recs;                        // records whose ring needs the warp kernel
+    int *scan_block;
+};
+
 __host__ __device__ inline int sz_div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 struct Launch {
@@ -178,6 +196,9 @@ void szk_halo(const Launch &L, const Store &S, const int *idx, const long long *
 void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);
 void szk_coupling(const Launch &L, const Store &S, const Params &P);
 void szk_apply_coupling_tags(const Launch &L, const Store &S);
+void szk_coupling_reg(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P);
+void szk_cells_final(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P);
+void szk_cells_sort_and_clip(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P, int n_rec_hint);
 void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P);
 void szk_interleave(const Launch &L, const double *x, const double *y, double2 *out, long long n);
 void szk_deinterleave(const Launch &L, const double2 *in, double *x, double *y, long long n);

@@ -1147,6 +1147,157 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     g_launch_count += 27;  // + 5 scans counted in scan_excl
 }
 
+// ---- two-way coupling: sort the registry by (cell, floe), floe ∩ cell-box areas ------------------------------
+__global__ void k_crec_zero(Store S, CouplingBuf CB, int ncell) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= ncell; c += gridDim.x * blockDim.x) {
+        CB.cell_count[c] = 0;
+        CB.cell_fill[c] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt->n_ccells = ncell;
+        cnt->n_cbig = 0;
+        if (cnt->n_crec > CB.cap_crec) cnt->n_crec = CB.cap_crec;
+    }
+}
+__global__ void k_crec_count(Store S, CouplingBuf CB) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < cnt->n_crec; r += gridDim.x * blockDim.x)
+        atomicAdd(&CB.cell_count[CB.rec_cell[r]], 1);
+}
+__global__ void k_crec_fill(Store S, CouplingBuf CB) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < cnt->n_crec; r += gridDim.x * blockDim.x) {
+        int c = CB.rec_cell[r];
+        CB.perm[CB.cell_start[c] + atomicAdd(&CB.cell_fill[c], 1)] = r;
+    }
+}
+// ascending floe index inside every cell: the order in which the reference's serial floe loop filled the cell
+__global__ void k_crec_sort(Store S, CouplingBuf CB, int ncell) {
+    if (S.cnt->error) return;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) {
+        int a = CB.cell_start[c], b = CB.cell_start[c + 1];
+        for (int i = a + 1; i < b; ++i) {
+            int v = CB.perm[i], fv = CB.rec_floe[v], j = i - 1;
+            while (j >= a && CB.rec_floe[CB.perm[j]] > fv) {
+                CB.perm[j + 1] = CB.perm[j];
+                --j;
+            }
+            CB.perm[j + 1] = v;
+        }
+    }
+}
+
+// center_cell_coords + check_cell_bounds, coupling.jl:931-1140 (0-based cell index): xmin, xmax, ymin, ymax
+__device__ __forceinline__ void center_cell_box(const Params &P, int ix, int iy, double b[4]) {
+    double xmin = ((double)(ix + 1) - 1.5) * P.dx + P.x0, xmax = xmin + P.dx;
+    double ymin = ((double)(iy + 1) - 1.5) * P.dy + P.y0, ymax = ymin + P.dy;
+    if (!P.per_x) {
+        xmin = xmin < P.x0 ? P.x0 : (xmin > P.xf ? P.xf : xmin);
+        xmax = xmax > P.xf ? P.xf : (xmax < P.x0 ? P.x0 : xmax);
+    }
+    if (!P.per_y) {
+        ymin = ymin < P.y0 ? P.y0 : (ymin > P.yf ? P.yf : ymin);
+        ymax = ymax > P.yf ? P.yf : (ymax < P.y0 ? P.y0 : ymax);
+    }
+    b[0] = xmin; b[1] = xmax; b[2] = ymin; b[3] = ymax;
+}
+
+// floe_area_in_cell = sum(area.(intersect_polys(cell_poly, translated floe_poly))), coupling.jl:1652-1660.
+// One thread per record (rings of <= 10 edges); larger rings go to the warp kernel below.
+__global__ void __launch_bounds__(TN_NT, 2) k_crec_area(Store S, CouplingBuf CB, Params P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    double2 *base = (double2 *)smem + threadIdx.x;
+    double2 *sP = base, *sQ = sP + TN_MAXV * TN_NT, *sR = sQ + TN_MAXV * TN_NT;
+    for (int r = blockIdx.x * TN_NT + threadIdx.x; r < cnt->n_crec; r += gridDim.x * TN_NT) {
+        const int f = CB.rec_floe[r], cell = CB.rec_cell[r], nq = S.vcount[f];
+        bool big = nq > TN_MAXV;
+        double area = 0.0;
+        if (!big) {
+            double b[4];
+            center_cell_box(P, cell % (P.Nx + 1), cell / (P.Nx + 1), b);
+            sP[0 * TN_NT] = make_double2(b[0], b[2]);
+            sP[1 * TN_NT] = make_double2(b[0], b[3]);
+            sP[2 * TN_NT] = make_double2(b[1], b[3]);
+            sP[3 * TN_NT] = make_double2(b[1], b[2]);
+            sP[4 * TN_NT] = make_double2(b[0], b[2]);
+            const double2 d = CB.rec_d[r];
+            const double2 *gQ = S.verts + S.vstart[f];
+            for (int k = 0; k < nq; ++k) {  // _translate_poly, floe_utils.jl:60-64
+                double2 v = gQ[k];
+                sQ[k * TN_NT] = make_double2(v.x + d.x, v.y + d.y);
+            }
+            int rs[TN_MAXREG], re[TN_MAXREG], status;
+            int nreg = t_clip<false>(tring(sP, 5), tring(sQ, nq), sR, TN_RCAP, rs, re, status, nullptr, nullptr, nullptr);
+            if (status != TN_OK) big = true;
+            else
+                for (int g = 0; g < nreg; ++g) area += t_area(tring(sR + rs[g] * TN_NT, re[g] - rs[g]));
+        }
+        if (big) CB.big_recs[atomicAdd(&cnt->n_cbig, 1)] = r;
+        else CB.rec_area[r] = area;
+    }
+}
+
+__global__ void k_crec_area_warp(Store S, CouplingBuf CB, Params P, int maxv, int maxx) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    Ws w = ws_carve(smem + (size_t)wib * ws_bytes(maxv, maxx), maxv, maxx);
+    for (int it = blockIdx.x * wpb + wib; it < cnt->n_cbig; it += gridDim.x * wpb) {
+        const int r = CB.big_recs[it], f = CB.rec_floe[r], cell = CB.rec_cell[r], nq = S.vcount[f];
+        if (nq > w.maxv) {
+            if (lane == 0) atomicOr(&cnt->error, ERR_POLY_TOO_LARGE);
+            continue;
+        }
+        double b[4];
+        center_cell_box(P, cell % (P.Nx + 1), cell / (P.Nx + 1), b);
+        if (lane < 5) {
+            double2 p;
+            switch (lane) {
+            case 1: p = make_double2(b[0], b[3]); break;
+            case 2: p = make_double2(b[1], b[3]); break;
+            case 3: p = make_double2(b[1], b[2]); break;
+            default: p = make_double2(b[0], b[2]); break;
+            }
+            w.P[lane] = p;
+        }
+        const double2 d = CB.rec_d[r];
+        const double2 *gQ = S.verts + S.vstart[f];
+        for (int k = lane; k < nq; k += 32) w.Q[k] = make_double2(gQ[k].x + d.x, gQ[k].y + d.y);
+        __syncwarp();
+        int status;
+        int nreg = warp_clip(w, w.P, 5, w.Q, nq, w.R1, w.rs1, w.re1, status);
+        if (status == CLIP_OVERFLOW) {
+            if (lane == 0) atomicOr(&cnt->error, ERR_POLY_TOO_LARGE);
+            continue;
+        }
+        double area = 0.0;
+        for (int g = 0; g < nreg; ++g) area += ring_area_seq(w.R1 + w.rs1[g], w.re1[g] - w.rs1[g]);
+        if (lane == 0) CB.rec_area[r] = area;
+        __syncwarp();
+    }
+}
+
+void szk_cells_sort_and_clip(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P, int n_rec_hint) {
+    cudaStream_t st = L.stream;
+    const int ncell = (P.Nx + 1) * (P.Ny + 1);
+    int gr = grid_for(L, n_rec_hint, TPB), gc = grid_for(L, ncell + 1, TPB);
+    k_crec_zero<<<gc, TPB, 0, st>>>(S, CB, ncell);
+    k_crec_count<<<gr, TPB, 0, st>>>(S, CB);
+    scan_excl(L, S, CB.cell_count, CB.cell_start, &S.cnt->n_ccells, 0, CB.cap_cells, CB.scan_block, nullptr);
+    k_crec_fill<<<gr, TPB, 0, st>>>(S, CB);
+    k_crec_sort<<<gc, TPB, 0, st>>>(S, CB, ncell);
+    k_crec_area<<<2 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, CB, P);
+    k_crec_area_warp<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, CB, P, L.maxv_large, L.maxx_large);
+    g_launch_count += 6;
+}
+
 // ---- geometry service / test hook -------------------------------------------------------------------------------------------
 __global__ void k_debug_clip(const double2 *gP, int npp, const double2 *gQ, int nqp, int maxv, int maxx, int cap_regions,
                              int cap_points, int *out_offsets, double2 *out_xy, double *out_areas, int *out_n) {
@@ -1220,6 +1371,8 @@ int szk_configure(const Launch &L) {
     if (cudaFuncSetAttribute(k_ghost_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_debug_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_narrow_ab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_crec_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_crec_area_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_narrow_ab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_B) != cudaSuccess) return -1;
     return 0;
 }

@@ -39,7 +39,7 @@ void szk_pack_fields(const Launch &L, const Store &S, int n) {
 // rad cos(theta) = xc, so the reference's u - xi rad sin(theta) (:1534-1537) and
 // (-tx sin + ty cos) rad (:1562) need no transcendental call.
 struct CpConst {
-    double x0, y0, xf, yf, inv_dx, inv_dy, ct, sn, ka, ko, f;
+    double x0, y0, xf, yf, inv_dx, inv_dy, dx, dy, ct, sn, ka, ko, f;
     int Nx, Ny, per_x, per_y;
 };
 
@@ -48,12 +48,21 @@ struct CpAcc {
     int n;
 };
 
+// what one Monte-Carlo point contributes to the floe -> cell registry (floe_to_grid_info!, coupling.jl:1417-1454)
+struct CpReg {
+    int cell;        // shifted cell index ix + (Nx+1) iy, -1 = point not in bounds
+    int sdx, sdy;    // shifted - unshifted grid-line index (periodic wrap), in cells
+    double tox, toy; // ocean stress on the ice at the point
+};
+
+template <bool REG>
 __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restrict__ F, double2 b, double ca,
                                          double sa, double cx, double cy, double u, double v, double xi, double mf,
-                                         CpAcc &acc) {
+                                         CpAcc &acc, CpReg *reg) {
     double xc = ca * b.x - sa * b.y, yc = sa * b.x + ca * b.y;  // body frame -> world, about the centroid
     double x = xc + cx, y = yc + cy;
     bool inb = (c.per_x || (c.x0 <= x && x <= c.xf)) && (c.per_y || (c.y0 <= y && y <= c.yf));
+    if (REG) reg->cell = -1;
     if (!inb) return;
     acc.n++;
     // the reference recomputes (x - cx, y - cy) from the translated point; the difference to (xc, yc) is
@@ -104,8 +113,21 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     double na = sqrt(dua * dua + dva * dva);
     double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
     double no = sqrt(duo * duo + dvo * dvo);
-    double tx = c.ka * na * dua - mf * vocn + c.ko * no * (c.ct * duo - c.sn * dvo);
-    double ty = c.ka * na * dva + mf * uocn + c.ko * no * (c.sn * duo + c.ct * dvo);
+    double tox = c.ko * no * (c.ct * duo - c.sn * dvo), toy = c.ko * no * (c.sn * duo + c.ct * dvo);
+    double tx = c.ka * na * dua - mf * vocn + tox;
+    double ty = c.ka * na * dva + mf * uocn + toy;
+    if (REG) {
+        // find_center_cell_index (coupling.jl:466-470) and shift_cell_idx (:1155-1182), 0-based here
+        int xi0 = (int)floor(gx + 0.5), yi0 = (int)floor(gy + 0.5);
+        int sx = xi0, sy = yi0;
+        if (c.per_x) sx = xi0 < 0 ? xi0 + c.Nx : (xi0 >= c.Nx ? xi0 - c.Nx : xi0);
+        if (c.per_y) sy = yi0 < 0 ? yi0 + c.Ny : (yi0 >= c.Ny ? yi0 - c.Ny : yi0);
+        reg->cell = sx + (c.Nx + 1) * sy;
+        reg->sdx = sx - xi0;
+        reg->sdy = sy - yi0;
+        reg->tox = tox;
+        reg->toy = toy;
+    }
     acc.tx += tx;
     acc.ty += ty;
     acc.trq += ty * xr - tx * yr;
@@ -129,10 +151,10 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
         long long k = m0 + lane;
         for (; k + 32 < m1; k += 64) {  // two independent points per lane in flight
             double2 b0 = __ldcs(S.mc + k), b1 = __ldcs(S.mc + k + 32);
-            cp_point(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc);
-            cp_point(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc);
+            cp_point<false>(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            cp_point<false>(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
         }
-        if (k < m1) cp_point(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc);
+        if (k < m1) cp_point<false>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             acc.tx += __shfl_xor_sync(FULLMASK, acc.tx, o);
@@ -157,11 +179,187 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
     }
 }
 
+// The same integration plus the floe -> cell registry (grid.floe_locations / ocean.scells): the points of a
+// warp iteration are grouped by cell with ballots, each group is reduced and added to a small per-floe table in
+// shared memory; the table is appended to the global record list (sorted by (cell, floe) afterwards).
+#define CP_TABLE 32  // distinct cells one floe may touch
+__global__ void __launch_bounds__(128, 6) k_coupling_reg(Store S, CouplingBuf CB, CpConst c) {
+    __shared__ int t_cell[4][CP_TABLE], t_n[4][CP_TABLE], t_sd[4][CP_TABLE][2];
+    __shared__ double t_t[4][CP_TABLE][2];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const double *__restrict__ F = S.fields8;
+    const int n = S.n_init;
+    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
+        const double a = S.alpha[i], cx = S.cx[i], cy = S.cy[i], u = S.u[i], v = S.v[i], xi = S.xi[i];
+        double sa, ca;
+        sincos(a, &sa, &ca);
+        const double ar = S.area[i];
+        const double mf = S.mass[i] / ar * c.f;
+        CpAcc acc = {0.0, 0.0, 0.0, 0.0, 0};
+        const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
+        int ntab = 0;
+        bool overflow = false;
+        for (long long base = m0; base < m1; base += 32) {
+            const long long k = base + lane;
+            CpReg r;
+            r.cell = -1;
+            r.sdx = r.sdy = 0;
+            r.tox = r.toy = 0.0;
+            if (k < m1) cp_point<true>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, &r);
+            unsigned pending = __ballot_sync(FULLMASK, r.cell >= 0);
+            while (pending) {
+                const int leader = __ffs(pending) - 1;
+                const int cc = __shfl_sync(FULLMASK, r.cell, leader);
+                const int sdx = __shfl_sync(FULLMASK, r.sdx, leader), sdy = __shfl_sync(FULLMASK, r.sdy, leader);
+                const bool mine = r.cell == cc;
+                const unsigned m = __ballot_sync(FULLMASK, mine);
+                double sx_ = mine ? -r.tox : 0.0, sy_ = mine ? -r.toy : 0.0;  // add_point! stores the stress ON the ocean
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    sx_ += __shfl_xor_sync(FULLMASK, sx_, o);
+                    sy_ += __shfl_xor_sync(FULLMASK, sy_, o);
+                }
+                if (lane == 0) {
+                    int e = 0;
+                    while (e < ntab && t_cell[wib][e] != cc) ++e;
+                    if (e == ntab) {
+                        if (ntab < CP_TABLE) {
+                            t_cell[wib][e] = cc;
+                            t_n[wib][e] = 0;
+                            t_sd[wib][e][0] = sdx;
+                            t_sd[wib][e][1] = sdy;
+                            t_t[wib][e][0] = t_t[wib][e][1] = 0.0;
+                            ntab++;
+                        } else {
+                            overflow = true;
+                        }
+                    }
+                    if (e < CP_TABLE) {
+                        t_t[wib][e][0] += sx_;
+                        t_t[wib][e][1] += sy_;
+                        t_n[wib][e] += __popc(m);
+                    }
+                }
+                ntab = __shfl_sync(FULLMASK, ntab, 0);
+                pending &= ~m;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            acc.tx += __shfl_xor_sync(FULLMASK, acc.tx, o);
+            acc.ty += __shfl_xor_sync(FULLMASK, acc.ty, o);
+            acc.trq += __shfl_xor_sync(FULLMASK, acc.trq, o);
+            acc.hf += __shfl_xor_sync(FULLMASK, acc.hf, o);
+            acc.n += __shfl_xor_sync(FULLMASK, acc.n, o);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (overflow) atomicOr(&cnt->error, ERR_CELL_TABLE);
+            if (acc.n == 0) {
+                S.cpl_remove[i] = 1;
+            } else {
+                S.cpl_remove[i] = 0;
+                double np_ = (double)acc.n;
+                double tot_x = np_ * (mf * v) + acc.tx, tot_y = -np_ * (mf * u) + acc.ty;
+                S.fxOA[i] = tot_x / np_ * ar;
+                S.fyOA[i] = tot_y / np_ * ar;
+                S.trqOA[i] = acc.trq / np_ * ar;
+                S.hflx[i] = acc.hf / np_;
+            }
+        }
+        int slot = 0;
+        if (lane == 0 && ntab > 0) {
+            slot = atomicAdd(&cnt->n_crec, ntab);
+            if (slot + ntab > CB.cap_crec) {
+                atomicOr(&cnt->error, ERR_CREC_CAP);
+                slot = -1;
+            }
+        }
+        slot = __shfl_sync(FULLMASK, slot, 0);
+        if (slot >= 0 && lane < ntab) {
+            const int e = lane, q = slot + e;
+            CB.rec_cell[q] = t_cell[wib][e];
+            CB.rec_floe[q] = i;
+            CB.rec_npts[q] = t_n[wib][e];
+            CB.rec_t[q] = make_double2(t_t[wib][e][0], t_t[wib][e][1]);
+            CB.rec_d[q] = make_double2(t_sd[wib][e][0] * c.dx, t_sd[wib][e][1] * c.dy);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_crec_reset(Counters *cnt) {
+    if (!cnt->error) cnt->n_crec = 0;
+}
+
+void szk_coupling_reg(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P) {
+    k_crec_reset<<<1, 1, 0, L.stream>>>(S.cnt);
+    szk_count_launches(1);
+    if (S.n_init <= 0) return;
+    CpConst c;
+    c.x0 = P.x0; c.y0 = P.y0; c.xf = P.xf; c.yf = P.yf;
+    c.inv_dx = 1.0 / P.dx; c.inv_dy = 1.0 / P.dy;
+    c.dx = P.dx; c.dy = P.dy;
+    c.ct = cos(P.cfg.turn_theta); c.sn = sin(P.cfg.turn_theta);
+    c.ka = P.cfg.rho_a * P.cfg.Cd_ia; c.ko = P.cfg.rho_o * P.cfg.Cd_io; c.f = P.cfg.f;
+    c.Nx = P.Nx; c.Ny = P.Ny;
+    c.per_x = P.per_x; c.per_y = P.per_y;
+    long long blocks = ((long long)S.n_init + 3) / 4, cap = (long long)L.sms * 48;
+    k_coupling_reg<<<(int)(blocks < cap ? blocks : cap), 128, 0, L.stream>>>(S, CB, c);
+    szk_count_launches(1);
+}
+
+// two-way coupling, last pass (calc_two_way_coupling!, coupling.jl:1617-1680): one thread per grid cell walks its
+// records in ascending floe order (the reference's order), then adds the atmosphere's drag on the open water
+// and refreshes ocean.hflx_factor.
+__global__ void k_cells_final(Store S, CouplingBuf CB, Params P) {
+    if (S.cnt->error) return;
+    const int ncell = (P.Nx + 1) * (P.Ny + 1);
+    const double cell_area = P.dx * P.dy;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += gridDim.x * blockDim.x) {
+        double tx = 0, ty = 0, si = 0;
+        for (int k = CB.cell_start[q], ke = CB.cell_start[q + 1]; k < ke; ++k) {
+            const int r = CB.perm[k];
+            const double a = CB.rec_area[r];
+            if (a > 0) {
+                const double2 t = CB.rec_t[r];
+                const double np_ = (double)CB.rec_npts[r];
+                tx += (t.x / np_) * a;
+                ty += (t.y / np_) * a;
+                si += a;
+            }
+        }
+        if (si > 0) {
+            tx /= si;
+            ty /= si;
+            si /= cell_area;
+        }
+        double du = S.atm_u[q] - S.ocn_u[q], dv = S.atm_v[q] - S.ocn_v[q];
+        double ocn_frac = 1 - si, norm = sqrt(du * du + dv * dv);
+        tx += P.cfg.rho_a * P.cfg.Cd_ao * ocn_frac * norm * du;
+        ty += P.cfg.rho_a * P.cfg.Cd_ao * ocn_frac * norm * dv;
+        S.taux[q] = tx;
+        S.tauy[q] = ty;
+        S.sifrac[q] = si;
+        double hf = P.cfg.dt * P.cfg.k / (P.cfg.rho_i * P.cfg.L) * (S.ocn_temp[q] - S.atm_temp[q]);
+        S.ocn_hflx[q] = hf;
+        S.fields8[(size_t)q * 8 + 4] = hf;  // the packed copy the next coupling step interpolates
+    }
+}
+void szk_cells_final(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P) {
+    int ncell = (P.Nx + 1) * (P.Ny + 1);
+    k_cells_final<<<(ncell + 127) / 128, 128, 0, L.stream>>>(S, CB, P);
+    szk_count_launches(1);
+}
+
 void szk_coupling(const Launch &L, const Store &S, const Params &P) {
     if (S.n_init <= 0) return;
     CpConst c;
     c.x0 = P.x0; c.y0 = P.y0; c.xf = P.xf; c.yf = P.yf;
     c.inv_dx = 1.0 / P.dx; c.inv_dy = 1.0 / P.dy;
+    c.dx = P.dx; c.dy = P.dy;
     c.ct = cos(P.cfg.turn_theta); c.sn = sin(P.cfg.turn_theta);
     c.ka = P.cfg.rho_a * P.cfg.Cd_ia; c.ko = P.cfg.rho_o * P.cfg.Cd_io; c.f = P.cfg.f;
     c.Nx = P.Nx; c.Ny = P.Ny;

@@ -114,6 +114,8 @@ class Ocean:
     def __init__(self, grid, u=0.0, v=0.0, temp=0.0):
         self.u, self.v, self.temp = _field(grid, u), _field(grid, v), _field(grid, temp)
         self.hflx_factor = np.zeros_like(self.u)
+        # two-way coupling outputs (oceans.jl:74-99)
+        self.tau_x, self.tau_y, self.si_frac = np.zeros_like(self.u), np.zeros_like(self.u), np.zeros_like(self.u)
 
 
 class Atmos:
@@ -386,14 +388,12 @@ def _make_handle(backend, consts, dt, collision_settings=None, coupling_settings
     cs = collision_settings or CollisionSettings()
     cp = coupling_settings or CouplingSettings()
     fs = floe_settings or FloeSettings()
-    if cp.two_way_coupling_on:
-        raise capi.SubzeroError(-4, "two-way coupling is outside the hot-path scope (SURVEY.md §8(f))")
     cfg = lib.default_config_struct()
     for name in ("rho_o", "rho_a", "Cd_io", "Cd_ia", "Cd_ao", "f", "turn_theta", "L", "k", "nu", "mu", "E"):
         setattr(cfg, name, getattr(consts, name))
     cfg.floe_floe_max_overlap, cfg.floe_domain_max_overlap = cs.floe_floe_max_overlap, cs.floe_domain_max_overlap
     cfg.rho_i, cfg.max_floe_height, cfg.maximum_xi, cfg.stress_lambda = fs.rho_i, fs.max_floe_height, fs.maximum_xi, fs.stress_lambda
-    cfg.coupling_dd, cfg.two_way_coupling_on, cfg.dt = cp.dd, 0, int(dt)
+    cfg.coupling_dd, cfg.two_way_coupling_on, cfg.dt = cp.dd, int(cp.two_way_coupling_on), int(dt)
     return capi.Handle(lib, cfg, **overrides)
 
 
@@ -484,10 +484,15 @@ def timestep_coupling(model, dt, consts, coupling_settings=None, floe_settings=N
     g = model.grid
     h.set_grid(g.Nx, g.Ny, g.x0, g.xf, g.y0, g.yf)
     h.set_fields(model.ocean.u, model.ocean.v, model.ocean.hflx_factor, model.atmos.u, model.atmos.v)
+    h.set_temperatures(model.ocean.temp, model.atmos.temp)
     model.domain.push(h)
     h.upload_floes(model.floes)
     h.step_coupling()
     model.floes.adopt(h.download_floes())
+    if coupling_settings is not None and coupling_settings.two_way_coupling_on:
+        oc = model.ocean
+        oc.tau_x, oc.tau_y, oc.si_frac, oc.hflx_factor = h.ocean_fields()
+    model.cell_floes = h.cell_floes()  # grid.floe_locations / ocean.scells as (cell, floe, values)
     h.close()
     return model
 
@@ -530,6 +535,7 @@ class Simulation:
         g = model.grid
         self.h.set_grid(g.Nx, g.Ny, g.x0, g.xf, g.y0, g.yf)
         self.h.set_fields(model.ocean.u, model.ocean.v, model.ocean.hflx_factor, model.atmos.u, model.atmos.v)
+        self.h.set_temperatures(model.ocean.temp, model.atmos.temp)
         model.domain.push(self.h)
         self.h.upload_floes(model.floes)
         self._resident = True
@@ -540,6 +546,9 @@ class Simulation:
     def sync_host(self):
         self.model.floes.adopt(self.h.download_floes())
         self.model.domain.pull(self.h)
+        if self.coupling_settings.two_way_coupling_on:
+            oc = self.model.ocean
+            oc.tau_x, oc.tau_y, oc.si_frac, oc.hflx_factor = self.h.ocean_fields()
         return self.model.floes
 
     def close(self):

@@ -128,8 +128,6 @@ def test_settings_clamp_like_the_reference():
         cp = host.CouplingSettings(dd=-3)
         assert cs.floe_floe_max_overlap == 1.0 and cs.floe_domain_max_overlap == 0.0 and cp.dd == 0
         assert len(w) == 3
-    with pytest.raises(capi.SubzeroError):
-        host._make_handle(None, host.Constants(), 10, None, host.CouplingSettings(two_way_coupling_on=True), None)
 
 
 def test_domain_validation_like_the_reference(oracle_lib):

@@ -1,0 +1,182 @@
+"""Two-way coupling and the floe -> grid-cell registry.
+
+The oracle's index logic is pinned against the reference's own tests
+(/root/reference/test/test_physical_processes/test_coupling.jl:276-462: center_cell_coords,
+floe_to_grid_info!) through two oracle-only test hooks; the CUDA product is then compared with the
+oracle on real fields (`-m gpu`)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fields
+from parity_util import rel_err
+from subzero_jl_b200 import capi, host, synth
+
+c_i32_p = C.POINTER(C.c_int32)
+
+
+def small_grid_handle(oracle_lib, ns_periodic, ew_periodic):
+    """grid of test_coupling.jl:166-172: x in [-10, 10], y in [-8, 8], dx = 2, dy = 4 (Nx = 10, Ny = 4)"""
+    h = capi.Handle(oracle_lib)
+    h.set_grid(10, 4, -10.0, 10.0, -8.0, 8.0)
+    g = host.RegRectilinearGrid(-10.0, 10.0, -8.0, 8.0, Nx=10, Ny=4)
+    B = lambda per: host.PeriodicBoundary if per else host.OpenBoundary
+    dom = host.Domain(B(ns_periodic)(host.North, g), B(ns_periodic)(host.South, g), B(ew_periodic)(host.East, g),
+                      B(ew_periodic)(host.West, g))
+    dom.push(h)
+    return h
+
+
+def cell_coords(oracle_lib, h, ix, iy):
+    fn = oracle_lib.dll.szo_test_center_cell_coords
+    fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, capi.c_double_p]
+    out = np.zeros(4)
+    assert fn(h.h, ix, iy, out.ctypes.data_as(capi.c_double_p)) == 0
+    return tuple(out)  # xmin, xmax, ymin, ymax
+
+
+def test_center_cell_coords_reference_values(oracle_lib):  # test_coupling.jl:276-288
+    per = small_grid_handle(oracle_lib, True, True)
+    opn = small_grid_handle(oracle_lib, False, False)
+    ns_open_ew_per = small_grid_handle(oracle_lib, False, True)
+    ns_per_ew_open = small_grid_handle(oracle_lib, True, False)
+    assert cell_coords(oracle_lib, per, 2, 3) == (-9, -7, -2, 2)
+    assert cell_coords(oracle_lib, opn, 1, 1) == (-10, -9, -8, -6)
+    assert cell_coords(oracle_lib, per, 11, 6) == (9, 11, 10, 14)
+    assert cell_coords(oracle_lib, opn, 11, 6) == (9, 10, 8, 8)
+    assert cell_coords(oracle_lib, ns_open_ew_per, 11, 6) == (9, 11, 8, 8)
+    assert cell_coords(oracle_lib, ns_per_ew_open, 11, 6) == (9, 10, 10, 14)
+
+
+def run_floe_to_grid(oracle_lib, h, floe, xidx, yidx, taux, tauy):
+    fn = oracle_lib.dll.szo_test_floe_to_grid
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_int32, c_i32_p, c_i32_p, capi.c_double_p, capi.c_double_p]
+    xi, yi = np.asarray(xidx, dtype=np.int32), np.asarray(yidx, dtype=np.int32)
+    tx, ty = np.asarray(taux, dtype=np.float64), np.asarray(tauy, dtype=np.float64)
+    assert fn(h.h, floe, len(xi), xi.ctypes.data_as(c_i32_p), yi.ctypes.data_as(c_i32_p), tx.ctypes.data_as(capi.c_double_p),
+              ty.ctypes.data_as(capi.c_double_p)) == 0
+    cell, fl, vals = h.cell_floes()
+    return {(int(c[0]), int(c[1])): (int(f), *v) for c, f, v in zip(cell, fl, vals)}
+
+
+FLOE_TO_GRID = [
+    # ns periodic, ew periodic, floe, xidx, yidx, tau sign, {cell: (dx, dy, sum tau_x, sum tau_y, npoints)}   test_coupling.jl:
+    (False, False, 1, [7, 7, 6, 6, 7, 7], [4, 4, 3, 3, 4, 4], 1.0,
+     {(7, 4): (0.0, 0.0, -4, -8, 4), (6, 3): (0.0, 0.0, -2, -4, 2)}),  # :353-371
+    (True, True, 2, [7, 7, 8, 8, 9, 9], [2, 3, 3, 3, 2, 2], 1.0,
+     {(7, 2): (0.0, 0.0, -1, -2, 1), (7, 3): (0.0, 0.0, -1, -2, 1), (9, 2): (0.0, 0.0, -2, -4, 2), (8, 3): (0.0, 0.0, -2, -4, 2)}),  # :373-395
+    (True, False, 3, [10, 10, 10, 11, 11, 11, 11], [4, 5, 6, 5, 6, 5, 6], 1.0,
+     {(10, 1): (0.0, -16.0, -1, -2, 1), (11, 1): (0.0, -16.0, -2, -4, 2), (10, 2): (0.0, -16.0, -1, -2, 1),
+      (11, 2): (0.0, -16.0, -2, -4, 2), (10, 4): (0.0, 0.0, -1, -2, 1)}),  # :397-420
+    (False, True, 4, [11, 11, 12, 12, 11], [4, 5, 5, 5, 4], 1.0,
+     {(1, 4): (-20.0, 0.0, -2, -4, 2), (1, 5): (-20.0, 0.0, -1, -2, 1), (2, 5): (-20.0, 0.0, -2, -4, 2)}),  # :422-441
+    (True, True, 2, [0, -1, -1, 1, -1], [0, -1, -2, 1, -1], -1.0,
+     {(1, 1): (0.0, 0.0, 1, 2, 1), (10, 4): (20.0, 16.0, 1, 2, 1), (9, 3): (20.0, 16.0, 2, 4, 2), (9, 2): (20.0, 16.0, 1, 2, 1)}),  # :443-461
+]
+
+
+@pytest.mark.parametrize("case", range(len(FLOE_TO_GRID)))
+def test_floe_to_grid_info_reference_values(case, oracle_lib):
+    ns, ew, floe, xidx, yidx, sign, expect = FLOE_TO_GRID[case]
+    h = small_grid_handle(oracle_lib, ns, ew)
+    got = run_floe_to_grid(oracle_lib, h, floe, xidx, yidx, sign * np.ones(len(xidx)), 2 * sign * np.ones(len(xidx)))
+    assert set(got) == set(expect)  # every other cell is empty
+    for cell, (dx, dy, stx, sty, npts) in expect.items():
+        f, tx, ty, n, gdx, gdy = got[cell]
+        assert f == floe and (gdx, gdy) == (dx, dy) and (tx, ty, n) == (stx, sty, npts)
+
+
+def two_way_field(n=600, walls="periodic"):
+    f = synth.make_field(n, scale=0.97, walls=walls, npoints=120, cache=False)
+    fields.perturb_state(f.floes)
+    g = f.grid
+    rng = np.random.default_rng(4)
+    f.atmos = host.Atmos(g, 3.0 + rng.uniform(-1, 1, (g.Nx + 1, g.Ny + 1)), -2.0, -15.0)
+    f.ocean = host.Ocean(g, f.ocean.u, 0.05, 1.5)
+    return f
+
+
+def two_way_handle(f, lib):
+    h = host._make_handle(lib, f.consts, 10, None, host.CouplingSettings(two_way_coupling_on=True), None)
+    g = f.grid
+    h.set_grid(g.Nx, g.Ny, g.x0, g.xf, g.y0, g.yf)
+    h.set_fields(f.ocean.u, f.ocean.v, f.ocean.hflx_factor, f.atmos.u, f.atmos.v)
+    h.set_temperatures(f.ocean.temp, f.atmos.temp)
+    f.domain.push(h)
+    h.upload_floes(f.floes)
+    return h
+
+
+@pytest.mark.parametrize("walls", ["periodic", "collision"])
+def test_two_way_coupling_physics_on_oracle(walls, oracle_lib):
+    f = two_way_field(walls=walls)
+    h = two_way_handle(f, oracle_lib)
+    h.step_coupling()
+    taux, tauy, si, hf = h.ocean_fields()
+    cell, floe, vals = h.cell_floes()
+    g = f.grid
+    assert len(cell) >= f.floes.n and cell.min() >= 1 and cell[:, 0].max() <= g.Nx + 1 and cell[:, 1].max() <= g.Ny + 1
+    key = (cell[:, 1] * (g.Nx + 2) + cell[:, 0]) * (f.floes.n + 1) + floe
+    assert np.all(np.diff(key) > 0)  # sorted by (cell, floe), one record per (cell, floe)
+    # every in-bounds Monte-Carlo point is registered exactly once
+    tot = f.floes.mc_offsets[-1]  # points outside a non-periodic grid are dropped (coupling.jl:494-597)
+    assert vals[:, 2].sum() == tot if walls == "periodic" else 0.97 * tot < vals[:, 2].sum() <= tot
+    assert np.all(si >= 0) and si.max() <= 1 + 1e-9 and si.max() > 0.5
+    interior = si[1:-1, 1:-1] if walls == "collision" else si[:-1, :-1]  # periodic: line N+1 is line 1
+    assert abs(interior.mean() - 0.97 ** 2) < 0.03  # concentration of the scaled Voronoi field
+    # heat-flux factor, coupling.jl:1676-1677
+    c = f.consts
+    assert np.allclose(hf, 10 * c.k / (920.0 * c.L) * (1.5 + 15.0), rtol=1e-14)
+    # ice-free limit: only the atmosphere drags the ocean
+    ho = two_way_handle(f, oracle_lib)
+    e = capi.FloeArrays(0)
+    ho.upload_floes(e)
+    ho.step_coupling()
+    t0x, t0y, s0, _ = ho.ocean_fields()
+    du, dv = f.atmos.u - f.ocean.u, f.atmos.v - f.ocean.v
+    assert np.all(s0 == 0) and np.allclose(t0x, c.rho_a * c.Cd_ao * np.hypot(du, dv) * du, rtol=1e-13)
+    # the new hflx_factor feeds the next coupling step and thins / thickens the floes
+    h.step_coupling()
+    fa = h.download_floes(mc=False)
+    assert np.allclose(fa.hflx_factor[fa.status_tag == capi.STATUS_ACTIVE], hf[0, 0], rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("walls", ["periodic", "collision", "shear"])
+def test_two_way_coupling_cuda_matches_oracle(walls, product_lib, oracle_lib):
+    f = two_way_field(n=3000, walls=walls)
+    hg, ho = two_way_handle(f, product_lib), two_way_handle(f, oracle_lib)
+    for h in (hg, ho):
+        h.step(0, True)
+        h.step(1, True)
+    cg, fg, vg = hg.cell_floes()
+    co, fo, vo = ho.cell_floes()
+    assert np.array_equal(cg, co) and np.array_equal(fg, fo)
+    assert np.array_equal(vg[:, 2:], vo[:, 2:]) and rel_err(vg[:, :2], vo[:, :2]) < 1e-9
+    for a, b, name in zip(hg.ocean_fields(), ho.ocean_fields(), ("tau_x", "tau_y", "si_frac", "hflx_factor")):
+        assert rel_err(a, b) < 1e-9, name
+    from parity_util import compare_state
+    bad = compare_state(hg.download_floes(), ho.download_floes())
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.gpu
+def test_two_way_coupling_nonconvex_shapes_cuda_matches_oracle(product_lib, oracle_lib):
+    """The reference's fixture shapes (up to 591 vertices, up to 23 km wide on a 10 km grid): the warp clip
+    kernel computes floe ∩ cell areas, one floe registers in up to 16 cells."""
+    f = fields.fixture_shape_field(scale=1.0, walls="collision", npoints=300)
+    g = f.grid
+    f.atmos = host.Atmos(g, 4.0, 1.0, -10.0)
+    f.ocean = host.Ocean(g, f.ocean.u, f.ocean.v, 0.5)
+    hg, ho = two_way_handle(f, product_lib), two_way_handle(f, oracle_lib)
+    for h in (hg, ho):
+        h.step_coupling()
+    cg, fg, vg = hg.cell_floes()
+    co, fo, vo = ho.cell_floes()
+    assert np.array_equal(cg, co) and np.array_equal(fg, fo) and np.array_equal(vg[:, 2:], vo[:, 2:])
+    assert np.bincount(fo).max() >= 9  # a floe spread over many cells
+    for a, b, name in zip(hg.ocean_fields(), ho.ocean_fields(), ("tau_x", "tau_y", "si_frac", "hflx_factor")):
+        assert rel_err(a, b) < 1e-9, name
+    assert ho.ocean_fields()[2].max() > 0.3
