@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=25000, help="floes of the cpu_baseline sample field")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--two-way", action="store_true", help="also turn on two-way coupling (not part of the headline config)")
     ap.add_argument("--skin", type=float, default=3000.0, help="halo-list skin in metres (N > 1): lists stay valid while floes moved < skin/2")
     return ap.parse_args()
 
@@ -196,7 +197,7 @@ def main():
     me = None
     if world == 1:
         f = synth.make_field(args.floes, scale=args.scale, walls=args.walls, npoints=args.npoints, seed=args.floes)
-        h = synth.setup_handle(f, prod, device=local_rank)
+        h = synth.setup_handle(f, prod, device=local_rank, two_way_coupling_on=int(args.two_way))
         fa0 = f.floes
     else:
         # weak scaling: rank r generates the tile [r L, (r+1) L) x [0, L) and owns it; the neighbours' boundary
