@@ -257,6 +257,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->L.sms = prop.multiProcessorCount;
     h->L.maxv_large = 1024;
     h->L.maxx_large = 256;
+    h->L.coupling_blocks_per_sm = 0;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&h->L.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
@@ -957,6 +958,9 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
             cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
             Launch L2 = h->L;
             L2.stream = h->stream2;
+            // measured (profiles/README.md): capping coupling to 2-4 resident blocks per SM so that it runs beside the
+            // narrow phase slows the latter more than the overlap gains; it fills the GPU during the broad phase
+            L2.coupling_blocks_per_sm = 0;
             cudaEventRecord(h->ev_c0, h->stream2);
             szk_coupling(L2, h->S, h->P);
             cudaEventRecord(h->ev_c1, h->stream2);

@@ -182,6 +182,7 @@ struct Launch {
     cudaStream_t stream;
     int sms;  // multiprocessor count: persistent grids are sized in multiples of it
     int maxv_large, maxx_large;  // workspace of the large-polygon kernels
+    int coupling_blocks_per_sm;  // 0 = fill the GPU; > 0 = persistent grid of that many blocks per SM
 };
 
 // ---- host-callable launchers (sz_kernels.cu) -------------------------------------------------

@@ -366,7 +366,10 @@ void szk_coupling(const Launch &L, const Store &S, const Params &P) {
     c.per_x = P.per_x; c.per_y = P.per_y;
     // 128-thread blocks: small enough to share an SM with the narrow-phase blocks when the two run on
     // different streams (sz_step overlaps coupling with the collision kernels)
-    long long blocks = ((long long)S.n_init + 3) / 4, cap = (long long)L.sms * 48;
+    // L.coupling_blocks_per_sm > 0 (sz_step: coupling shares the SMs with the collision kernels): a persistent
+    // grid of that many blocks per SM leaves registers for the high-priority stream's blocks
+    long long blocks = ((long long)S.n_init + 3) / 4;
+    long long cap = (long long)L.sms * (L.coupling_blocks_per_sm > 0 ? L.coupling_blocks_per_sm : 48);
     k_coupling<<<(int)(blocks < cap ? blocks : cap), 128, 0, L.stream>>>(S, c);
     szk_count_launches(1);
 }
