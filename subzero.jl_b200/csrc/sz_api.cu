@@ -347,6 +347,11 @@ extern "C" int32_t sz_set_fields(sz_handle *h, const double *ou, const double *o
         if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], sizeof(double) * n, cudaMemcpyHostToDevice, h->L.stream));
         else CK(cudaMemsetAsync(dst[k], 0, sizeof(double) * n, h->L.stream));
     }
+    {
+        auto nonzero = [&](const double *p) { if (!p) return false; for (size_t k = 0; k < n; ++k) if (p[k] != 0.0) return true; return false; };
+        h->P.atm_nonzero = nonzero(au) || nonzero(av);
+        h->P.hflx_nonzero = nonzero(oh) || h->cfg.two_way_coupling_on;
+    }
     szk_pack_fields(h->L, S, (int)n);
     CK(cudaStreamSynchronize(h->L.stream));
     CK(cudaGetLastError());

@@ -88,6 +88,7 @@ struct Params {
     int Nx, Ny;
     double x0, xf, y0, yf, dx, dy;
     int per_x, per_y;  // periodic east/west, north/south (domain kinds)
+    int atm_nonzero, hflx_nonzero;  // false: the atmosphere / heat-flux fields are identically zero (coupling skips them)
 };
 
 // Everything a kernel needs, passed by value.

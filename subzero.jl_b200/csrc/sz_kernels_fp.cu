@@ -55,7 +55,9 @@ struct CpReg {
     double tox, toy; // ocean stress on the ice at the point
 };
 
-template <bool REG>
+// ATM / HFLX: false when the atmosphere / heat-flux fields are identically zero (sz_set_fields checks): the
+// loads and multiply-adds of a zero field are skipped, the result is the same
+template <bool REG, bool ATM, bool HFLX>
 __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restrict__ F, double2 b, double ca,
                                          double sa, double cx, double cy, double u, double v, double xi, double mf,
                                          CpAcc &acc, CpReg *reg) {
@@ -100,15 +102,20 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     const double2 *n01 = (const double2 *)(F + (size_t)(i0 + s * j1) * 8);
     const double2 *n11 = (const double2 *)(F + (size_t)(i1 + s * j1) * 8);
     double w00 = (1 - wx) * (1 - wy), w10 = wx * (1 - wy), w01 = (1 - wx) * wy, w11 = wx * wy;
-    double2 a00 = __ldg(n00), a10 = __ldg(n10), a01 = __ldg(n01), a11 = __ldg(n11);          // atm u, v
     double2 o00 = __ldg(n00 + 1), o10 = __ldg(n10 + 1), o01 = __ldg(n01 + 1), o11 = __ldg(n11 + 1);  // ocn u, v
-    double h00 = __ldg(F + (size_t)(i0 + s * j0) * 8 + 4), h10 = __ldg(F + (size_t)(i1 + s * j0) * 8 + 4),
-           h01 = __ldg(F + (size_t)(i0 + s * j1) * 8 + 4), h11 = __ldg(F + (size_t)(i1 + s * j1) * 8 + 4);
-    double uatm = w00 * a00.x + w10 * a10.x + w01 * a01.x + w11 * a11.x;
-    double vatm = w00 * a00.y + w10 * a10.y + w01 * a01.y + w11 * a11.y;
+    double uatm = 0.0, vatm = 0.0, hfl = 0.0;
+    if (ATM) {
+        double2 a00 = __ldg(n00), a10 = __ldg(n10), a01 = __ldg(n01), a11 = __ldg(n11);  // atm u, v
+        uatm = w00 * a00.x + w10 * a10.x + w01 * a01.x + w11 * a11.x;
+        vatm = w00 * a00.y + w10 * a10.y + w01 * a01.y + w11 * a11.y;
+    }
+    if (HFLX) {
+        double h00 = __ldg((const double *)(n00 + 2)), h10 = __ldg((const double *)(n10 + 2)),
+               h01 = __ldg((const double *)(n01 + 2)), h11 = __ldg((const double *)(n11 + 2));
+        hfl = w00 * h00 + w10 * h10 + w01 * h01 + w11 * h11;
+    }
     double uocn = w00 * o00.x + w10 * o10.x + w01 * o01.x + w11 * o11.x;
     double vocn = w00 * o00.y + w10 * o10.y + w01 * o01.y + w11 * o11.y;
-    double hfl = w00 * h00 + w10 * h10 + w01 * h01 + w11 * h11;
     double dua = uatm - up, dva = vatm - vp;  // calc_atmosphere_forcing, coupling.jl:1212-1232
     double na = sqrt(dua * dua + dva * dva);
     double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
@@ -134,6 +141,7 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     acc.hf += hfl;
 }
 
+template <bool ATM, bool HFLX>
 __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -142,19 +150,21 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
     const int n = S.n_init;
     for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
         const double a = S.alpha[i], cx = S.cx[i], cy = S.cy[i], u = S.u[i], v = S.v[i], xi = S.xi[i];
+        const double ar = S.area[i], mass = S.mass[i];
+        const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
         double sa, ca;
         sincos(a, &sa, &ca);
-        const double ar = S.area[i];
-        const double mf = S.mass[i] / ar * c.f;
+        const double mf = mass / ar * c.f;
         CpAcc acc = {0.0, 0.0, 0.0, 0.0, 0};
-        const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
         long long k = m0 + lane;
-        for (; k + 32 < m1; k += 64) {  // two independent points per lane in flight
-            double2 b0 = __ldcs(S.mc + k), b1 = __ldcs(S.mc + k + 32);
-            cp_point<false>(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-            cp_point<false>(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+        for (; k + 96 < m1; k += 128) {  // four independent 512-byte loads per warp in flight (HBM latency)
+            double2 b0 = __ldcs(S.mc + k), b1 = __ldcs(S.mc + k + 32), b2 = __ldcs(S.mc + k + 64), b3 = __ldcs(S.mc + k + 96);
+            cp_point<false, ATM, HFLX>(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            cp_point<false, ATM, HFLX>(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            cp_point<false, ATM, HFLX>(c, F, b2, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            cp_point<false, ATM, HFLX>(c, F, b3, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
         }
-        if (k < m1) cp_point<false>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+        for (; k < m1; k += 32) cp_point<false, ATM, HFLX>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             acc.tx += __shfl_xor_sync(FULLMASK, acc.tx, o);
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(128, 6) k_coupling_reg(Store S, CouplingBuf CB
             r.cell = -1;
             r.sdx = r.sdy = 0;
             r.tox = r.toy = 0.0;
-            if (k < m1) cp_point<true>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, &r);
+            if (k < m1) cp_point<true, true, true>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, &r);
             unsigned pending = __ballot_sync(FULLMASK, r.cell >= 0);
             while (pending) {
                 const int leader = __ffs(pending) - 1;
@@ -370,7 +380,12 @@ void szk_coupling(const Launch &L, const Store &S, const Params &P) {
     // grid of that many blocks per SM leaves registers for the high-priority stream's blocks
     long long blocks = ((long long)S.n_init + 3) / 4;
     long long cap = (long long)L.sms * (L.coupling_blocks_per_sm > 0 ? L.coupling_blocks_per_sm : 48);
-    k_coupling<<<(int)(blocks < cap ? blocks : cap), 128, 0, L.stream>>>(S, c);
+    const int g = (int)(blocks < cap ? blocks : cap);
+    const bool atm = P.atm_nonzero, hf = P.hflx_nonzero;
+    if (atm && hf) k_coupling<true, true><<<g, 128, 0, L.stream>>>(S, c);
+    else if (atm) k_coupling<true, false><<<g, 128, 0, L.stream>>>(S, c);
+    else if (hf) k_coupling<false, true><<<g, 128, 0, L.stream>>>(S, c);
+    else k_coupling<false, false><<<g, 128, 0, L.stream>>>(S, c);
     szk_count_launches(1);
 }
 

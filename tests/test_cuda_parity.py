@@ -37,6 +37,10 @@ def test_phase_by_phase(cfg, product_lib, oracle_lib):
     n, scale, walls, flow = cfg
     f = synth.make_field(n, scale=scale, walls=walls, flow=flow, npoints=150, cache=False)
     fields.perturb_state(f.floes)
+    if n == 300:  # a heat-flux field (thermodynamic growth in the state update), with and without wind
+        f.ocean.hflx_factor = np.random.default_rng(n).uniform(-2e-4, 2e-4, f.ocean.u.shape)
+        if walls == "periodic":
+            f.atmos.u[:] = 5.0
     hg, ho = handles(f, product_lib, oracle_lib)
     # add_ghosts!: ghost order, ids, translated rings — exact
     ng, no = hg.add_ghosts(), ho.add_ghosts()
