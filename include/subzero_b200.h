@@ -191,6 +191,15 @@ int32_t SZ_FN(step_floe_properties)(sz_handle *h, int64_t tstep); /* update_floe
 /* One fused timestep without intermediate host synchronisation: add_ghosts, collisions,
  * remove_ghosts, coupling (iff do_coupling != 0), floe properties. */
 int32_t SZ_FN(step)(sz_handle *h, int64_t tstep, int32_t do_coupling);
+/* The same timestep on HOST buffers: sz_upload_state(in) + sz_step + sz_download_floes(out) as one call.  This
+ * is what the Julia shim calls when host processes (fracture, ridging, welding, writers: simulation.jl:121-214)
+ * touch the floe state every step.  The product overlaps the copies with the kernels: uploads are ordered by
+ * first use (centroids and radii first, then rings, ...) and every kernel waits only for the arrays it reads;
+ * results are copied back as soon as the kernel producing them is done.  `in` and `out` may alias (in-place
+ * update of the host arrays); pinned host memory is needed for the overlap, pageable memory works but
+ * serialises.  Monte-Carlo points and ghost lists are not transferred (mc_x / mc_y / ghost_index untouched). */
+int32_t SZ_FN(step_host)(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in,
+                         sz_floe_soa *out);
 
 /* ---- results ------------------------------------------------------------------------------- */
 /* interactions: offsets[n_total+1] and rows[n_rows][7] =

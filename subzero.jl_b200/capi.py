@@ -103,6 +103,7 @@ class Library:
         "step_coupling": (C.c_int32, [C.c_void_p]),
         "step_floe_properties": (C.c_int32, [C.c_void_p, C.c_int64]),
         "step": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32]),
+        "step_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(FloeSoA), C.POINTER(FloeSoA)]),
         "get_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
         "set_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
         "get_pairs": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
@@ -363,6 +364,14 @@ class Handle:
 
     def step(self, tstep=0, do_coupling=True):
         self._ck(self.lib.step(self.h, tstep, 1 if do_coupling else 0))
+
+    def step_host(self, fa, tstep=0, do_coupling=True, out=None):
+        """One timestep on host arrays (upload_state + step + download in one call, copies overlapped with the
+        kernels).  `out` defaults to `fa` (in-place)."""
+        s = fa.as_struct()
+        o = s if out is None or out is fa else out.as_struct()
+        self._ck(self.lib.step_host(self.h, tstep, 1 if do_coupling else 0, C.byref(s), C.byref(o)))
+        return fa if out is None else out
 
     # results ----------------------------------------------------------------------------------
     def interactions(self):

@@ -24,6 +24,11 @@ struct sz_handle {
     Launch L;
     cudaStream_t stream2;      // coupling runs here, concurrently with the collision kernels (sz_step)
     cudaEvent_t ev_fork, ev_join, ev_c0, ev_c1;
+    // sz_step_host: host -> device copies on stream_up and device -> host copies on stream_dn overlap the kernels
+    cudaStream_t stream_up, stream_dn;
+    cudaEvent_t ev_up[4], ev_dn[3], ev_up_start, ev_dn_end;
+    double2 *d_cf_dn;  // [n][2] staging of collision_force in the host layout
+    int cf_cap;
     Params P;
     bool have_grid, have_fields, have_domain, have_floes;
     DomainDev hD;
@@ -266,6 +271,14 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     cudaEventCreate(&h->ev_c0);
     cudaEventCreate(&h->ev_c1);
+    h->d_cf_dn = nullptr;
+    h->cf_cap = 0;
+    if (cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream_dn, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
+    for (int k = 0; k < 4; ++k) cudaEventCreate(&h->ev_up[k]);
+    for (int k = 0; k < 3; ++k) cudaEventCreate(&h->ev_dn[k]);
+    cudaEventCreate(&h->ev_up_start);
+    cudaEventCreate(&h->ev_dn_end);
     for (int k = 0; k < NEV; ++k) cudaEventCreate(&h->ev[k]);
     if (cudaMallocHost((void **)&h->h_cnt, sizeof(Counters)) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
     memset(h->h_cnt, 0, sizeof(Counters));
@@ -303,6 +316,11 @@ extern "C" void sz_destroy(sz_handle *h) {
     for (int k = 0; k < NEV; ++k) cudaEventDestroy(h->ev[k]);
     cudaStreamDestroy(h->L.stream);
     cudaStreamDestroy(h->stream2);
+    cudaStreamDestroy(h->stream_up);
+    cudaStreamDestroy(h->stream_dn);
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(h->ev_up[k]);
+    for (int k = 0; k < 3; ++k) cudaEventDestroy(h->ev_dn[k]);
+    dfree(h->d_cf_dn);
     cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_c0); cudaEventDestroy(h->ev_c1);
     delete h;
 }
@@ -942,15 +960,103 @@ extern "C" int32_t sz_step_floe_properties(sz_handle *h, int64_t tstep) {
     return SZ_OK;
 }
 
+// ---- sz_step / sz_step_host ----------------------------------------------------------------------------
+// Host buffers of one sz_step_host call.  The uploads are enqueued on stream_up in the order the kernels first
+// need them and signal four events; the kernels wait for the group they read (or overwrite):
+//   group 0  alpha, centroid, u, v, xi, area, mass, fxOA, fyOA, trqOA, hflx_factor  -> coupling.  First, because the
+//            coupling kernel is forked at once: it must run beside the (cheap) broad phase, not beside the
+//            latency-bound narrow phase, where the two slow each other down by more than the overlap gains
+//   group 1  rmax, status                                                            -> broad phase
+//   group 2  ring coordinates, height                                                -> narrow phase
+//   group 3  moment, overarea, the AB2 history, stress / strain tensors               -> row assembly, update
+// collision_force / collision_trq are NOT uploaded: timestep_collisions! zeroes them before anything reads them
+// (collisions.jl:747-749, k_step_reset), they are outputs of every step.
+// The downloads go to stream_dn as soon as the producing kernel is done (collision totals after the row
+// assembly, coupling outputs after the join, the rest after the update).
+struct HostIO {
+    const sz_floe_soa *in;
+    sz_floe_soa *out;
+};
+
+static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s) {
+    Store &S = h->S;
+    const int n = h->n_total;
+    cudaStream_t st = h->stream_up;
+    auto up = [&](double *dst, const double *src, size_t w) -> cudaError_t {
+        if (src) return cudaMemcpyAsync(dst, src, sizeof(double) * w * n, cudaMemcpyHostToDevice, st);
+        return cudaMemsetAsync(dst, 0, sizeof(double) * w * n, st);
+    };
+    CK(cudaEventRecord(h->ev_up_start, st));
+    // group 0
+    CK(up(S.alpha, s->alpha, 1)); CK(up(S.cx, s->centroid_x, 1)); CK(up(S.cy, s->centroid_y, 1)); CK(up(S.u, s->u, 1));
+    CK(up(S.v, s->v, 1)); CK(up(S.xi, s->xi, 1)); CK(up(S.area, s->area, 1)); CK(up(S.mass, s->mass, 1));
+    CK(up(S.fxOA, s->fxOA, 1)); CK(up(S.fyOA, s->fyOA, 1)); CK(up(S.trqOA, s->trqOA, 1)); CK(up(S.hflx, s->hflx_factor, 1));
+    CK(cudaEventRecord(h->ev_up[0], st));
+    // group 1
+    CK(up(S.rmax, s->rmax, 1));
+    if (s->status_tag) CK(cudaMemcpyAsync(S.status, s->status_tag, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(h->ev_up[1], st));
+    // group 2
+    if (h->n_verts > 0) CK(cudaMemcpyAsync(S.verts, s->vert_xy, sizeof(double2) * (size_t)h->n_verts, cudaMemcpyHostToDevice, st));
+    CK(up(S.height, s->height, 1));
+    CK(cudaEventRecord(h->ev_up[2], st));
+    // group 3
+    CK(up(S.moment, s->moment, 1)); CK(up(S.overarea, s->overarea, 1));
+    CK(up(S.p_dxdt, s->p_dxdt, 1)); CK(up(S.p_dydt, s->p_dydt, 1)); CK(up(S.p_dudt, s->p_dudt, 1));
+    CK(up(S.p_dvdt, s->p_dvdt, 1)); CK(up(S.p_dxidt, s->p_dxidt, 1)); CK(up(S.p_dalphadt, s->p_dalphadt, 1));
+    CK(up(S.stress_accum, s->stress_accum, 4)); CK(up(S.stress_instant, s->stress_instant, 4)); CK(up(S.strain, s->strain, 4));
+    CK(cudaEventRecord(h->ev_up[3], st));
+    return SZ_OK;
+}
+
+// stage: 0 after the row assembly, 1 after the coupling join, 2 after the state update
+static int32_t enqueue_downloads(sz_handle *h, sz_floe_soa *s, int stage) {
+    Store &S = h->S;
+    const int n = h->n_init;
+    cudaStream_t st = h->stream_dn;
+    if (stage == 0 && s->collision_force) szk_interleave(h->L, S.cfx, S.cfy, h->d_cf_dn, n);  // [n][2] host layout
+    CK(cudaEventRecord(h->ev_dn[stage], h->L.stream));
+    CK(cudaStreamWaitEvent(st, h->ev_dn[stage], 0));
+    auto dn = [&](double *dst, const double *src, size_t w) -> cudaError_t {
+        if (!dst) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, sizeof(double) * w * n, cudaMemcpyDeviceToHost, st);
+    };
+    if (stage == 0) {
+        if (s->collision_force) CK(cudaMemcpyAsync(s->collision_force, h->d_cf_dn, sizeof(double2) * n, cudaMemcpyDeviceToHost, st));
+        CK(dn(s->collision_trq, S.ctrq, 1)); CK(dn(s->overarea, S.overarea, 1));
+        CK(dn(s->area, S.area, 1)); CK(dn(s->rmax, S.rmax, 1));  // not changed by a step
+        if (s->id) CK(cudaMemcpyAsync(s->id, S.id, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        if (s->ghost_id) CK(cudaMemcpyAsync(s->ghost_id, S.ghost_id, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    } else if (stage == 1) {
+        CK(dn(s->fxOA, S.fxOA, 1)); CK(dn(s->fyOA, S.fyOA, 1)); CK(dn(s->trqOA, S.trqOA, 1)); CK(dn(s->hflx_factor, S.hflx, 1));
+        if (s->status_tag) CK(cudaMemcpyAsync(s->status_tag, S.status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));  // final after the tags
+    } else {
+        if (s->vert_xy && h->n_verts_init > 0)
+            CK(cudaMemcpyAsync(s->vert_xy, S.verts, sizeof(double2) * (size_t)h->n_verts_init, cudaMemcpyDeviceToHost, st));
+        CK(dn(s->centroid_x, S.cx, 1)); CK(dn(s->centroid_y, S.cy, 1)); CK(dn(s->alpha, S.alpha, 1));
+        CK(dn(s->u, S.u, 1)); CK(dn(s->v, S.v, 1)); CK(dn(s->xi, S.xi, 1));
+        CK(dn(s->height, S.height, 1)); CK(dn(s->mass, S.mass, 1)); CK(dn(s->moment, S.moment, 1));
+        CK(dn(s->p_dxdt, S.p_dxdt, 1)); CK(dn(s->p_dydt, S.p_dydt, 1)); CK(dn(s->p_dudt, S.p_dudt, 1));
+        CK(dn(s->p_dvdt, S.p_dvdt, 1)); CK(dn(s->p_dxidt, S.p_dxidt, 1)); CK(dn(s->p_dalphadt, S.p_dalphadt, 1));
+        CK(dn(s->stress_accum, S.stress_accum, 4)); CK(dn(s->stress_instant, S.stress_instant, 4)); CK(dn(s->strain, S.strain, 4));
+    }
+    return SZ_OK;
+}
+
 // One whole timestep enqueued back to back; a single host synchronisation at the end.
-extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
-    (void)tstep;
-    if (!h || !h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step before set_domain/upload_floes");
-    if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step with coupling before set_fields");
-    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
-    cudaSetDevice(h->cfg.device);
+static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
     cudaStream_t st = h->L.stream;
+    const bool periodic = h->hD.kind[2] == SZ_BOUNDARY_PERIODIC || h->hD.kind[0] == SZ_BOUNDARY_PERIODIC;
+    if (io) {
+        int32_t rc = enqueue_uploads(h, io->in);
+        if (rc) return rc;
+    }
     for (int attempt = 0;; ++attempt) {
+        if (io) {
+            // add_ghosts! copies every scalar of a parent into its ghost (collisions.jl:1017-1047): with periodic
+            // walls the step starts when all uploads have landed
+            for (int g = 0; g < (periodic ? 4 : 1); ++g) CK(cudaStreamWaitEvent(st, h->ev_up[g], 0));  // non-periodic: group 0
+        }
         cudaEventRecord(h->ev[0], st);
         enqueue_ghosts(h);
         cudaEventRecord(h->ev[1], st);
@@ -972,9 +1078,12 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
             cudaEventRecord(h->ev_join, h->stream2);
         }
         // the ghost count of this step is not known on the host: size grids from the capacity-bounded hint
-        szk_collisions(h->L, h->S, h->B, h->P, floes_hint(h), pairs_hint(h), &h->ev[2]);
+        cudaEvent_t waits[2] = {h->ev_up[2], h->ev_up[3]};
+        if (io) CK(cudaStreamWaitEvent(st, h->ev_up[1], 0));
+        szk_collisions(h->L, h->S, h->B, h->P, floes_hint(h), pairs_hint(h), &h->ev[2], io ? waits : nullptr);
         szk_remove_ghosts(h->L, h->S, h->n_verts_init);
         cudaEventRecord(h->ev[5], st);
+        if (io) { int32_t rc = enqueue_downloads(h, io->out, 0); if (rc) return rc; }
         if (fork) {
             cudaStreamWaitEvent(st, h->ev_join, 0);  // join
             szk_apply_coupling_tags(h->L, h->S);
@@ -986,11 +1095,31 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
             cudaEventRecord(h->ev_c1, st);
             szk_apply_coupling_tags(h->L, h->S);
         }
+        if (io) { int32_t rc = enqueue_downloads(h, io->out, 1); if (rc) return rc; }
         cudaEventRecord(h->ev[6], st);
         szk_update(h->L, h->S, h->B, h->P);
         cudaEventRecord(h->ev[7], st);
+        if (io) { int32_t rc = enqueue_downloads(h, io->out, 2); if (rc) return rc; }
         CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (io) {
+            CK(cudaEventRecord(h->ev_dn_end, h->stream_dn));
+            CK(cudaStreamSynchronize(h->stream_dn));
+            if (getenv("SZ_DEBUG_HOSTIO")) {
+                float t[12] = {0};
+                for (int g = 0; g < 4; ++g) cudaEventElapsedTime(&t[g], h->ev_up_start, h->ev_up[g]);
+                cudaEventElapsedTime(&t[4], h->ev_up_start, h->ev[0]);
+                cudaEventElapsedTime(&t[5], h->ev_up_start, h->ev[2]);
+                cudaEventElapsedTime(&t[6], h->ev_up_start, h->ev[3]);
+                cudaEventElapsedTime(&t[7], h->ev_up_start, h->ev[5]);
+                cudaEventElapsedTime(&t[8], h->ev_up_start, h->ev[7]);
+                cudaEventElapsedTime(&t[9], h->ev_up_start, h->ev_dn_end);
+                cudaEventElapsedTime(&t[10], h->ev_up_start, h->ev_c0);
+                cudaEventElapsedTime(&t[11], h->ev_up_start, h->ev_c1);
+                fprintf(stderr, "hostio ms: up groups %.3f %.3f %.3f %.3f | step start %.3f broad end %.3f narrow end %.3f rows end %.3f update end %.3f | coupling %.3f..%.3f | last download %.3f\n",
+                        t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[10], t[11], t[9]);
+            }
+        }
         CK(cudaGetLastError());
         if (!h->h_cnt->error) break;
         // every kernel after the overflow returned at once; only ghosts (and parents wrapped into
@@ -1023,6 +1152,54 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     h->ms[5] = ev_ms(h, 6, 7);
     h->ms[6] = ev_ms(h, 0, 7);
     h->ms[7] = (double)szk_launch_count(true);  // kernels launched since the previous sz_step returned (incl. halo pack/unpack)
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
+    (void)tstep;
+    if (!h || !h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step before set_domain/upload_floes");
+    if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step with coupling before set_fields");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
+    cudaSetDevice(h->cfg.device);
+    return step_impl(h, do_coupling, nullptr);
+}
+
+// sz_upload_state + sz_step + sz_download_floes in ONE call: the host <-> device copies run on their own
+// streams beside the kernels (see HostIO).  `in` and `out` may point to the same arrays.
+extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
+    (void)tstep;
+    if (!h || !in || !out) return SZ_ERR_INVALID;
+    if (!h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step_host before set_domain/upload_floes");
+    if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step_host with coupling before set_fields");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host with ghosts present (call remove_ghosts)");
+    if (in->n != h->n_total || in->n_init != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host: floe count differs from the resident store");
+    if (!in->centroid_x || !in->centroid_y || !in->area || !in->rmax || !in->vert_xy) return fail(h, SZ_ERR_INVALID, "step_host: geometry arrays are required");
+    if (in->vert_offsets && in->vert_offsets[h->n_total] != h->n_verts) return fail(h, SZ_ERR_INVALID, "step_host: vertex count differs from the resident store");
+    if ((int)h->h_vcount.size() != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host: no ring table of the resident floes");
+    cudaSetDevice(h->cfg.device);
+    const int n = h->n_init;
+    if (h->cf_cap < n) {
+        dfree(h->d_cf_dn);
+        CK(dalloc(&h->d_cf_dn, (size_t)n));
+        h->cf_cap = n;
+    }
+    HostIO io = {in, out};
+    int32_t rc = step_impl(h, do_coupling, &io);
+    if (rc) {
+        cudaStreamSynchronize(h->stream_up);
+        cudaStreamSynchronize(h->stream_dn);
+        return rc;
+    }
+    // host-side tables of the download (same as sz_download_floes without ghosts)
+    out->n = n;
+    out->n_init = n;
+    if (out->vert_offsets) {
+        long long o = 0;
+        for (int i = 0; i < n; ++i) { out->vert_offsets[i] = o; o += h->h_vcount[i]; }
+        out->vert_offsets[n] = o;
+    }
+    if (out->mc_offsets) for (int i = 0; i <= n; ++i) out->mc_offsets[i] = h->h_mc_off[i];
+    if (out->ghost_offsets) memset(out->ghost_offsets, 0, sizeof(int64_t) * ((size_t)n + 1));
     return SZ_OK;
 }
 

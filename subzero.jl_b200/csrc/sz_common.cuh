@@ -191,8 +191,9 @@ struct Launch {
 void szk_ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_floes_hint);
 void szk_remove_ghosts(const Launch &L, const Store &S, int n_verts_init);
 // ev (optional, 3 events): recorded after the broad phase, the narrow phase and the row assembly
+// waits (optional, 2 events): the stream waits for [0] before the narrow phase and for [1] before the row assembly
 void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_floes_hint,
-                    int n_pairs_hint, cudaEvent_t *ev);
+                    int n_pairs_hint, cudaEvent_t *ev, const cudaEvent_t *waits = nullptr);
 int szk_configure(const Launch &L);
 void szk_halo(const Launch &L, const Store &S, const int *idx, const long long *voff, int n, double *buf, bool pack);
 void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);

@@ -1101,7 +1101,7 @@ __global__ void k_kept_count(Store S, StepBuf B) {
 }
 
 void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_hint, int pairs_hint,
-                    cudaEvent_t *ev) {
+                    cudaEvent_t *ev, const cudaEvent_t *waits) {
     cudaStream_t st = L.stream;
     int gf = grid_for(L, n_hint, TPB);
     k_step_reset<<<gf, TPB, 0, st>>>(S);
@@ -1122,6 +1122,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_filter<<<gp, TPB, 0, st>>>(S, B);
     k_kept_count<<<gp, TPB, 0, st>>>(S, B);
     if (ev) cudaEventRecord(ev[0], st);
+    if (waits) cudaStreamWaitEvent(st, waits[0], 0);  // sz_step_host: rings and height have landed
     const int maxv_s = 32, maxx_s = 16, wpb = 4;
     // thread-per-item fast path (small polygons), then warp-per-item for what it handed on, then the
     // large-polygon workspace for what that one handed on
@@ -1135,6 +1136,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
     k_pool_check<<<1, 1, 0, st>>>(S, B);
     if (ev) cudaEventRecord(ev[1], st);
+    if (waits) cudaStreamWaitEvent(st, waits[1], 0);  // sz_step_host: everything else (overarea is accumulated by k_row_write)
     k_status<<<gf, TPB, 0, st>>>(S, B);
     k_fuse_propagate<<<1, 1024, 0, st>>>(S, B);
     k_row_count<<<gf, TPB, 0, st>>>(S, B);

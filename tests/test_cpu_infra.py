@@ -120,6 +120,19 @@ def test_coupling_outputs_are_held_between_coupling_steps(oracle_lib):
     assert np.array_equal(a, b) and not np.array_equal(b, c)
 
 
+def test_oracle_step_host_equals_three_calls(oracle_lib):
+    f = synth.make_field(400, scale=1.01, walls="periodic", npoints=60, cache=False)
+    fields.perturb_state(f.floes)
+    ha, hb = synth.setup_handle(f, oracle_lib), synth.setup_handle(f, oracle_lib)
+    fa, fb = ha.download_floes(mc=False), hb.download_floes(mc=False)
+    for t in range(3):
+        ha.upload_state(fa)
+        ha.step(t, True)
+        ha.download_floes(into=fa, mc=False)
+        hb.step_host(fb, t, True)
+        assert not compare_state(fb, fa, exact=STATE_FIELDS)
+
+
 def test_settings_clamp_like_the_reference():
     # test_process_settings.jl:22-93
     with warnings.catch_warnings(record=True) as w:

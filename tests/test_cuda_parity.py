@@ -105,6 +105,41 @@ def special_domain_field(n=900):
     return f
 
 
+@pytest.mark.parametrize("walls", ["collision", "periodic", "shear"])
+def test_step_host_equals_upload_step_download(walls, product_lib, oracle_lib):
+    """sz_step_host (copies overlapped with the kernels) must give the BITS of the three separate calls,
+    in place and into a second set of arrays, over several steps, with and without coupling."""
+    f = synth.make_field(3000, scale=1.01, walls=walls, npoints=120, cache=False)
+    fields.perturb_state(f.floes)
+    ha = synth.setup_handle(f, product_lib)
+    hb = synth.setup_handle(f, product_lib)
+    ho = synth.setup_handle(f, oracle_lib)
+    fa = ha.download_floes(mc=False)
+    fb = hb.download_floes(mc=False)
+    fo = ho.download_floes(mc=False)
+    out = hb.download_floes(mc=False)
+    for t in range(4):
+        cpl = t != 2
+        ha.upload_state(fa)
+        ha.step(t, cpl)
+        ha.download_floes(into=fa, mc=False)
+        if t % 2 == 0:
+            hb.step_host(fb, t, cpl)              # in place
+        else:
+            hb.step_host(fb, t, cpl, out=out)     # separate output arrays
+            fb, out = out, fb
+        assert_ok(compare_state(fb, fa, exact=parity_all_fields()))
+        if t == 0:
+            ho.step_host(fo, t, cpl)
+            assert_ok(compare_state(fb, fo))
+    assert ha.counts()["n_overlap"] == hb.counts()["n_overlap"] > 0
+
+
+def parity_all_fields():
+    from parity_util import STATE_FIELDS
+    return STATE_FIELDS
+
+
 @pytest.mark.parametrize("coupling", [True, False])
 def test_moving_walls_topography_open_wall_and_guards(coupling, product_lib, oracle_lib):
     f = special_domain_field()
