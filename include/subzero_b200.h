@@ -244,6 +244,46 @@ int32_t SZ_FN(clip_polygons)(sz_handle *h, const double *p_xy, int32_t np, const
                              int32_t nq, int32_t cap_regions, int32_t cap_points,
                              int32_t *out_offsets, double *out_xy, double *out_areas);
 
+/* ---- services for the host-side processes ------------------------------------ */
+/* Rank 2 — batched overlap query.  For every ordered pair (i, j) of `pairs` ([n_pairs][2], 1-based indices into
+ * the resident floe list, ghosts included when present):
+ *   interacts[k] = potential_interaction(centroid_i, centroid_j, rmax_i, rmax_j)          collisions.jl:705-710
+ *   areas[k]     = sum(GO.area, intersect_polys(poly_i, poly_j); init = 0.0)  (0 when !interacts)
+ * which is what smooth_floes! (simplification.jl:98-116), timestep_welding! (welding.jl:119-150) and the ridge /
+ * raft validity test (ridge_raft.jl:706-753) evaluate pair by pair on the host.  The candidate list itself comes
+ * from sz_get_pairs(h, 0, ...).  `interacts` may be NULL. */
+int32_t SZ_FN(pair_overlap_areas)(sz_handle *h, int64_t n_pairs, const int64_t *pairs, double *areas,
+                                  uint8_t *interacts);
+
+/* Rank 3 — Eulerian gridded output, calc_eulerian_data! (output.jl:794-919): floe data averaged on the cells of
+ * a GridOutputWriter grid.  xg [nx+1] / yg [ny+1] are the writer's grid lines; `kinds` [n_out] selects the
+ * outputs (SZ_GRID_*, the symbols of output.jl:859-905); data is [nx][ny][n_out] in Julia's column-major order,
+ * data[j + nx*(i + ny*k)] == writer.data[j+1, i+1, k+1] (x index first).  All floes in the store take part
+ * (the reference calls it between add_ghosts! and timestep_collisions!, simulation.jl:102-105, so ghosts are
+ * included when present).  Topography (cell polygons minus topography, output.jl:826-829) is outside the scope:
+ * with n_topo > 0 the call returns SZ_ERR_UNSUPPORTED and the host keeps its own implementation. */
+#define SZ_GRID_U 0
+#define SZ_GRID_V 1
+#define SZ_GRID_DUDT 2
+#define SZ_GRID_DVDT 3
+#define SZ_GRID_SI_FRAC 4
+#define SZ_GRID_OVERAREA 5
+#define SZ_GRID_MASS 6
+#define SZ_GRID_AREA 7
+#define SZ_GRID_HEIGHT 8
+#define SZ_GRID_STRESS_XX 9
+#define SZ_GRID_STRESS_YX 10
+#define SZ_GRID_STRESS_XY 11
+#define SZ_GRID_STRESS_YY 12
+#define SZ_GRID_STRESS_EIG 13
+#define SZ_GRID_STRAIN_UX 14
+#define SZ_GRID_STRAIN_VX 15
+#define SZ_GRID_STRAIN_UY 16
+#define SZ_GRID_STRAIN_VY 17
+#define SZ_GRID_NKINDS 18
+int32_t SZ_FN(eulerian_data)(sz_handle *h, int32_t nx, int32_t ny, const double *xg, const double *yg,
+                             int32_t n_out, const int32_t *kinds, double *data);
+
 #ifdef __cplusplus
 }
 #endif

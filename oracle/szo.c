@@ -1429,6 +1429,128 @@ int32_t szo_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz
     return rc;
 }
 
+
+/* ---- services for the host-side processes ------------------------------ */
+/* simplification.jl:98-116, welding.jl:119-150: potential_interaction, then sum(GO.area, intersect_polys(pi, pj)) */
+int32_t szo_pair_overlap_areas(sz_handle *h, int64_t n_pairs, const int64_t *pairs, double *areas, uint8_t *interacts) {
+    if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !areas))) return SZ_ERR_INVALID;
+    for (int64_t k = 0; k < n_pairs; ++k)
+        if (pairs[2 * k] < 1 || pairs[2 * k] > h->n || pairs[2 * k + 1] < 1 || pairs[2 * k + 1] > h->n)
+            return fail(h, SZ_ERR_INVALID, "pair_overlap_areas: floe index out of range");
+#pragma omp parallel
+    {
+        szo_regions R;
+        szo_regions_init(&R);
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t k = 0; k < n_pairs; ++k) {
+            int64_t i = pairs[2 * k] - 1, j = pairs[2 * k + 1] - 1;
+            int pi = potential_interaction(h, i, j);
+            double a = 0.0;
+            if (pi) {
+                szo_clip(h->ring[i], h->npts[i], h->ring[j], h->npts[j], &R);
+                for (int g = 0; g < R.nreg; ++g) a += szo_ring_area(R.pts + R.off[g], R.off[g + 1] - R.off[g]);
+            }
+            areas[k] = a;
+            if (interacts) interacts[k] = (uint8_t)pi;
+        }
+        szo_regions_free(&R);
+    }
+    return SZ_OK;
+}
+
+/* calc_eulerian_data!, output.jl:794-919 (no topography: the cell polygon list is the cell box) */
+int32_t szo_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg, const double *yg, int32_t n_out,
+                          const int32_t *kinds, double *data) {
+    if (!h || nx < 1 || ny < 1 || !xg || !yg || n_out < 0 || (n_out > 0 && (!kinds || !data))) return SZ_ERR_INVALID;
+    for (int k = 0; k < n_out; ++k)
+        if (kinds[k] < 0 || kinds[k] >= SZ_GRID_NKINDS) return fail(h, SZ_ERR_INVALID, "eulerian_data: unknown output kind");
+    if (h->n_topo > 0) return fail(h, SZ_ERR_UNSUPPORTED, "eulerian_data: topography (diff_polys of the cell polygons) stays on the host");
+    const double dx = xg[1] - xg[0], dy = yg[1] - yg[0];      /* :796-797 */
+    const double cell_rmax = sqrt(dx * dx + dy * dy);         /* :798 */
+#pragma omp parallel
+    {
+        szo_regions R;
+        szo_regions_init(&R);
+        int capf = 64, nf;
+        int64_t *fidx = (int64_t *)malloc(sizeof(int64_t) * (size_t)capf);
+        double *pic = (double *)malloc(sizeof(double) * (size_t)capf);
+#pragma omp for schedule(dynamic, 4) collapse(2)
+        for (int i = 0; i < ny; ++i) {
+            for (int j = 0; j < nx; ++j) {
+                const double xc = xg[j] + 0.5 * dx, yc = yg[i] + 0.5 * dy; /* :799-802 */
+                double b[4] = {xg[j], xg[j + 1], yg[i], yg[i + 1]};
+                szo_pt cell[5];
+                make_wall_ring(cell, b);                      /* _make_bounding_box_polygon, :825 */
+                nf = 0;
+                for (int64_t f = 0; f < h->n; ++f) {          /* mask :808-818, areas :838-846 */
+                    double ddx = xc - h->cx[f], ddy = yc - h->cy[f];
+                    double pint = sqrt(ddx * ddx + ddy * ddy) - (h->rmax[f] + cell_rmax);
+                    if (!(pint < 0)) continue;
+                    szo_clip(h->ring[f], h->npts[f], cell, 5, &R);
+                    double a = 0.0;
+                    for (int g = 0; g < R.nreg; ++g) a += szo_ring_area(R.pts + R.off[g], R.off[g + 1] - R.off[g]);
+                    if (a > 0) {                              /* :848-849 */
+                        if (nf == capf) {
+                            capf *= 2;
+                            fidx = (int64_t *)realloc(fidx, sizeof(int64_t) * (size_t)capf);
+                            pic = (double *)realloc(pic, sizeof(double) * (size_t)capf);
+                        }
+                        fidx[nf] = f;
+                        pic[nf] = a;
+                        nf++;
+                    }
+                }
+                double area_tot = 0.0, mass_tot = 0.0;        /* :854-856 */
+                for (int q = 0; q < nf; ++q) {
+                    area_tot += pic[q];
+                    mass_tot += h->mass[fidx[q]] * (pic[q] / h->area[fidx[q]]);
+                }
+                double acc[SZ_GRID_NKINDS];
+                for (int k = 0; k < SZ_GRID_NKINDS; ++k) acc[k] = 0.0;
+                if (mass_tot > 0) {                           /* :858-905 */
+                    double over = 0.0;
+                    for (int q = 0; q < nf; ++q) {
+                        int64_t f = fidx[q];
+                        double ma = (pic[q] / h->area[f]) * (h->mass[f] / mass_tot);
+                        const double *sa = h->stress_accum + 4 * f, *st = h->strain + 4 * f;
+                        acc[SZ_GRID_U] += h->u[f] * ma;
+                        acc[SZ_GRID_V] += h->v[f] * ma;
+                        acc[SZ_GRID_DUDT] += h->p_dudt[f] * ma;
+                        acc[SZ_GRID_DVDT] += h->p_dvdt[f] * ma;
+                        acc[SZ_GRID_HEIGHT] += h->height[f] * ma;
+                        acc[SZ_GRID_STRESS_XX] += sa[0] * ma;  /* s[1,1] */
+                        acc[SZ_GRID_STRESS_YX] += sa[2] * ma;  /* s[1,2] */
+                        acc[SZ_GRID_STRESS_XY] += sa[1] * ma;  /* s[2,1] */
+                        acc[SZ_GRID_STRESS_YY] += sa[3] * ma;  /* s[2,2] */
+                        acc[SZ_GRID_STRAIN_UX] += st[0] * ma;
+                        acc[SZ_GRID_STRAIN_VX] += st[2] * ma;
+                        acc[SZ_GRID_STRAIN_UY] += st[1] * ma;
+                        acc[SZ_GRID_STRAIN_VY] += st[3] * ma;
+                        over += h->overarea[f];
+                    }
+                    acc[SZ_GRID_SI_FRAC] = area_tot / szo_ring_area(cell, 5);
+                    acc[SZ_GRID_OVERAREA] = over / (double)nf;
+                    acc[SZ_GRID_MASS] = mass_tot;
+                    acc[SZ_GRID_AREA] = area_tot;
+                    {   /* maximum(eigvals([xx yx; xy yy])), zeroed when |.| > 1e8 (:884-893) */
+                        double xx = acc[SZ_GRID_STRESS_XX], yx = acc[SZ_GRID_STRESS_YX], xy = acc[SZ_GRID_STRESS_XY],
+                               yy = acc[SZ_GRID_STRESS_YY];
+                        double hm = 0.5 * (xx + yy), hd = 0.5 * (xx - yy), disc = hd * hd + yx * xy;
+                        double e = disc > 0 ? hm + sqrt(disc) : hm;
+                        if (fabs(e) > 1e8) e = 0.0;
+                        acc[SZ_GRID_STRESS_EIG] = e;
+                    }
+                }
+                for (int k = 0; k < n_out; ++k) data[(size_t)j + (size_t)nx * ((size_t)i + (size_t)ny * (size_t)k)] = acc[kinds[k]];
+            }
+        }
+        free(fidx);
+        free(pic);
+        szo_regions_free(&R);
+    }
+    return SZ_OK;
+}
+
 /* ---- results ----------------------------------------------------------------------------------- */
 int32_t szo_get_interactions(sz_handle *h, int64_t *offsets, double *rows) {
     if (!h || !offsets) return SZ_ERR_INVALID;

@@ -20,8 +20,13 @@ c_double_p = C.POINTER(C.c_double)
 c_i64_p = C.POINTER(C.c_int64)
 c_i32_p = C.POINTER(C.c_int32)
 c_u32_p = C.POINTER(C.c_uint32)
+c_u8_p = C.POINTER(C.c_uint8)
 
 STATUS_ACTIVE, STATUS_REMOVE, STATUS_FUSE = 1, 2, 3
+# outputs of calc_eulerian_data! (output.jl:859-905) in SZ_GRID_* order
+GRID_OUTPUTS = ("u_grid", "v_grid", "dudt_grid", "dvdt_grid", "si_frac_grid", "overarea_grid", "mass_grid", "area_grid",
+                "height_grid", "stress_xx_grid", "stress_yx_grid", "stress_xy_grid", "stress_yy_grid", "stress_eig_grid",
+                "strain_ux_grid", "strain_vx_grid", "strain_uy_grid", "strain_vy_grid")
 BOUNDARY_OPEN, BOUNDARY_PERIODIC, BOUNDARY_COLLISION, BOUNDARY_MOVING = 0, 1, 2, 3
 WARN_HEIGHT_CAPPED, WARN_FORCE_SCALED, WARN_VELOCITY_LIMITED, WARN_XI_CLAMPED = 1, 2, 4, 8
 
@@ -113,6 +118,8 @@ class Library:
         "halo_bytes": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
         "halo_pack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
         "halo_unpack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+        "pair_overlap_areas": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_double_p, c_u8_p]),
+        "eulerian_data": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int32, c_i32_p, c_double_p]),
         "clip_polygons": (C.c_int32, [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                       C.c_int32, C.c_int32, c_i32_p, c_double_p, c_double_p]),
     }
@@ -439,6 +446,27 @@ class Handle:
 
     def halo_unpack(self, k, ptr, nbytes):
         self._ck(self.lib.halo_unpack(self.h, k, C.c_void_p(ptr), nbytes))
+
+    # services for the host-side processes -------------------------------------------------------------
+    def pair_overlap_areas(self, pairs):
+        """pairs: [n, 2] 1-based ordered floe pairs -> (areas [n], interacts [n] bool):
+        potential_interaction and sum(GO.area, intersect_polys(poly_i, poly_j))."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        n = len(pairs)
+        areas = np.zeros(n)
+        inter = np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.pair_overlap_areas(self.h, n, _ip(pairs), _dp(areas), inter.ctypes.data_as(c_u8_p)))
+        return areas, inter.astype(bool)
+
+    def eulerian_data(self, xg, yg, kinds):
+        """calc_eulerian_data! on the grid lines xg, yg -> data [nx, ny, n_out] (writer.data layout)."""
+        xg = np.ascontiguousarray(xg, dtype=np.float64)
+        yg = np.ascontiguousarray(yg, dtype=np.float64)
+        kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+        nx, ny = len(xg) - 1, len(yg) - 1
+        data = np.zeros(nx * ny * len(kinds))
+        self._ck(self.lib.eulerian_data(self.h, nx, ny, _dp(xg), _dp(yg), len(kinds), kinds.ctypes.data_as(c_i32_p), _dp(data)))
+        return data.reshape((nx, ny, len(kinds)), order="F")
 
     def clip_polygons(self, p, q, cap_regions=64, cap_points=8192):
         p = np.ascontiguousarray(p, dtype=np.float64)

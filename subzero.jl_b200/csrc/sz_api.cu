@@ -18,8 +18,20 @@ struct FloeArr {
     size_t elem;  // bytes per floe
 };
 
+// grow-only device scratch of the service calls (sz_pair_overlap_areas, sz_eulerian_data)
+struct SvcBuf {
+    int2 *pairs; double *area; unsigned char *inter; int *big;
+    double *xg, *yg, *data, *rec_area;
+    int *rec_count, *rec_off, *cell_start, *rec_floe, *rec_cell, *val_in, *val_out;
+    unsigned long long *key_in, *key_out;
+    unsigned char *sort_tmp;
+    size_t cap_pairs, cap_area, cap_inter, cap_big, cap_xg, cap_yg, cap_data, cap_ra, cap_rc, cap_ro, cap_cs, cap_rf, cap_rcell,
+        cap_vi, cap_vo, cap_ki, cap_ko, cap_sort;
+};
+
 struct sz_handle {
     sz_config cfg;
+    SvcBuf svc;
     char err[512];
     Launch L;
     cudaStream_t stream2;      // coupling runs here, concurrently with the collision kernels (sz_step)
@@ -245,6 +257,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     memset(&h->S, 0, sizeof(h->S));
     memset(&h->B, 0, sizeof(h->B));
     memset(&h->CB, 0, sizeof(h->CB));
+    memset(&h->svc, 0, sizeof(h->svc));
     h->n_crec_host = 0;
     memset(&h->hD, 0, sizeof(h->hD));
     memset(&h->P, 0, sizeof(h->P));
@@ -285,7 +298,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     if (dalloc(&h->S.cnt, 1) != cudaSuccess || dalloc(&h->S.dom, 1) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
     cudaMemset(h->S.cnt, 0, sizeof(Counters));
     cudaMemset(h->S.dom, 0, sizeof(DomainDev));
-    if (szk_configure(h->L) != 0) { delete h; return SZ_ERR_CUDA; }
+    if (szk_configure(h->L) != 0 || szk_services_configure(h->L) != 0) { delete h; return SZ_ERR_CUDA; }
     register_arrays(h);
     *out = h;
     return SZ_OK;
@@ -306,6 +319,12 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
     dfree(h->d_hl_idx); dfree(h->d_hl_voff);
+    {
+        SvcBuf &V = h->svc;
+        dfree(V.pairs); dfree(V.area); dfree(V.inter); dfree(V.big); dfree(V.xg); dfree(V.yg); dfree(V.data); dfree(V.rec_area);
+        dfree(V.rec_count); dfree(V.rec_off); dfree(V.cell_start); dfree(V.rec_floe); dfree(V.rec_cell); dfree(V.val_in);
+        dfree(V.val_out); dfree(V.key_in); dfree(V.key_out); dfree(V.sort_tmp);
+    }
     {
         CouplingBuf &C = h->CB;
         dfree(C.rec_cell); dfree(C.rec_floe); dfree(C.rec_npts); dfree(C.rec_t); dfree(C.rec_d); dfree(C.rec_area);
@@ -1330,6 +1349,107 @@ static int32_t halo_move(sz_handle *h, int32_t list, void *buf, int64_t bytes, b
 }
 extern "C" int32_t sz_halo_pack(sz_handle *h, int32_t list, void *dst, int64_t cap) { return halo_move(h, list, dst, cap, true); }
 extern "C" int32_t sz_halo_unpack(sz_handle *h, int32_t list, const void *src, int64_t bytes) { return halo_move(h, list, (void *)src, bytes, false); }
+
+// ---- services for the host-side processes ------------------------------------------------
+// grow-only device scratch of the service calls
+template <typename T>
+static cudaError_t ensure(T *&p, size_t &cap, size_t need) {
+    if (need <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void **)&p, sizeof(T) * std::max<size_t>(need + need / 4, 64));
+    if (e == cudaSuccess) cap = std::max<size_t>(need + need / 4, 64);
+    return e;
+}
+
+extern "C" int32_t sz_pair_overlap_areas(sz_handle *h, int64_t n_pairs, const int64_t *pairs, double *areas, uint8_t *interacts) {
+    if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !areas))) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "pair_overlap_areas before upload_floes");
+    if (n_pairs > (1ll << 30)) return fail(h, SZ_ERR_UNSUPPORTED, "pair_overlap_areas: too many pairs");
+    if (n_pairs == 0) return SZ_OK;
+    cudaSetDevice(h->cfg.device);
+    const int n = (int)n_pairs;
+    std::vector<int2> hp((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        int64_t i = pairs[2 * k], j = pairs[2 * k + 1];
+        if (i < 1 || i > h->n_total || j < 1 || j > h->n_total) return fail(h, SZ_ERR_INVALID, "pair_overlap_areas: floe index out of range");
+        hp[k] = make_int2((int)(i - 1), (int)(j - 1));
+    }
+    SvcBuf &V = h->svc;
+    CK(ensure(V.pairs, V.cap_pairs, (size_t)n)); CK(ensure(V.area, V.cap_area, (size_t)n)); CK(ensure(V.inter, V.cap_inter, (size_t)n));
+    CK(ensure(V.big, V.cap_big, (size_t)n + 1));
+    cudaStream_t st = h->L.stream;
+    CK(cudaMemcpyAsync(V.pairs, hp.data(), sizeof(int2) * n, cudaMemcpyHostToDevice, st));
+    szk_pair_areas(h->L, h->S, V.pairs, n, V.area, V.inter, V.big + 1, V.big);
+    CK(cudaMemcpyAsync(areas, V.area, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (interacts) CK(cudaMemcpyAsync(interacts, V.inter, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h->h_cnt->error) {
+        char buf[256];
+        uint32_t e = h->h_cnt->error;
+        szk_clear_error(h->L, h->S);
+        return fail(h, SZ_ERR_UNSUPPORTED, errbits(e, buf, sizeof(buf)));
+    }
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg, const double *yg, int32_t n_out,
+                                    const int32_t *kinds, double *data) {
+    if (!h || nx < 1 || ny < 1 || !xg || !yg || n_out < 0 || (n_out > 0 && (!kinds || !data))) return SZ_ERR_INVALID;
+    if (!h->have_floes || !h->have_domain) return fail(h, SZ_ERR_INVALID, "eulerian_data before set_domain/upload_floes");
+    if (n_out > SZ_GRID_NKINDS) return fail(h, SZ_ERR_INVALID, "eulerian_data: more outputs than kinds");
+    for (int k = 0; k < n_out; ++k)
+        if (kinds[k] < 0 || kinds[k] >= SZ_GRID_NKINDS) return fail(h, SZ_ERR_INVALID, "eulerian_data: unknown output kind");
+    if (h->n_topo > 0) return fail(h, SZ_ERR_UNSUPPORTED, "eulerian_data: topography (diff_polys of the cell polygons) stays on the host");
+    if ((long long)nx * ny > (1ll << 28)) return fail(h, SZ_ERR_UNSUPPORTED, "eulerian_data: too many cells");
+    if (n_out == 0) return SZ_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaStream_t st = h->L.stream;
+    SvcBuf &V = h->svc;
+    const int nf = h->n_total, ncell = nx * ny;
+    CK(ensure(V.xg, V.cap_xg, (size_t)nx + 1)); CK(ensure(V.yg, V.cap_yg, (size_t)ny + 1));
+    CK(ensure(V.rec_count, V.cap_rc, (size_t)nf + 2)); CK(ensure(V.rec_off, V.cap_ro, (size_t)nf + 2));
+    CK(ensure(V.cell_start, V.cap_cs, (size_t)ncell + 2)); CK(ensure(V.data, V.cap_data, (size_t)ncell * n_out));
+    CK(ensure(V.big, V.cap_big, 2));
+    CK(cudaMemcpyAsync(V.xg, xg, sizeof(double) * (nx + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(V.yg, yg, sizeof(double) * (ny + 1), cudaMemcpyHostToDevice, st));
+    const double dx = xg[1] - xg[0], dy = yg[1] - yg[0];  // output.jl:796-797
+    int n_rec = 0;
+    if (nf > 0) {
+        szk_eul_count(h->L, h->S, nf, nx, ny, V.xg, V.yg, dx, dy, V.rec_count, V.rec_off);
+        CK(cudaMemcpyAsync(&n_rec, V.rec_off + nf, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    SzkEulArgs A;
+    memset(&A, 0, sizeof(A));
+    if (n_rec > 0) {
+        size_t nr = (size_t)n_rec;
+        CK(ensure(V.rec_floe, V.cap_rf, nr)); CK(ensure(V.rec_cell, V.cap_rcell, nr)); CK(ensure(V.rec_area, V.cap_ra, nr));
+        CK(ensure(V.key_in, V.cap_ki, nr)); CK(ensure(V.key_out, V.cap_ko, nr)); CK(ensure(V.val_in, V.cap_vi, nr));
+        CK(ensure(V.val_out, V.cap_vo, nr)); CK(ensure(V.big, V.cap_big, nr + 1));
+        A.sort_bytes = szk_eul_sort_bytes(n_rec);
+        CK(ensure(V.sort_tmp, V.cap_sort, A.sort_bytes));
+    }
+    A.n_floes = nf; A.nx = nx; A.ny = ny; A.n_rec = n_rec; A.n_out = n_out; A.d_xg = V.xg; A.d_yg = V.yg; A.dx = dx; A.dy = dy;
+    A.rec_count = V.rec_count; A.rec_off = V.rec_off; A.rec_floe = V.rec_floe; A.rec_cell = V.rec_cell; A.val_in = V.val_in;
+    A.val_out = V.val_out; A.cell_start = V.cell_start; A.big = V.big + 1; A.n_big = V.big; A.rec_area = V.rec_area;
+    A.key_in = V.key_in; A.key_out = V.key_out; A.sort_tmp = V.sort_tmp; A.kinds = kinds; A.d_data = V.data;
+    if (szk_eul_run(h->L, h->S, A) != 0) return fail(h, SZ_ERR_CUDA, "eulerian_data: sort failed");
+    CK(cudaMemcpyAsync(data, V.data, sizeof(double) * (size_t)ncell * n_out, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h->h_cnt->error) {
+        char buf[256];
+        uint32_t e = h->h_cnt->error;
+        szk_clear_error(h->L, h->S);
+        return fail(h, SZ_ERR_UNSUPPORTED, errbits(e, buf, sizeof(buf)));
+    }
+    return SZ_OK;
+}
 
 extern "C" int32_t sz_clip_polygons(sz_handle *h, const double *p_xy, int32_t np, const double *q_xy, int32_t nq,
                                     int32_t cap_regions, int32_t cap_points, int32_t *out_offsets, double *out_xy,

@@ -210,5 +210,26 @@ void szk_clear_error(const Launch &L, const Store &S);
 int szk_debug_clip(const Launch &L, const double *p_xy, int np, const double *q_xy, int nq, int cap_regions,
                    int cap_points, int *out_offsets, double *out_xy, double *out_areas);
 size_t szk_large_smem(int maxv, int maxx);
+// ---- services (sz_services.cu) ------------------------------------------------------------------
+int szk_services_configure(const Launch &L);
+void szk_pair_areas(const Launch &L, const Store &S, const int2 *pairs, int n, double *area, unsigned char *inter, int *big,
+                    int *n_big);
+void szk_eul_count(const Launch &L, const Store &S, int n_floes, int nx, int ny, const double *d_xg, const double *d_yg, double dx,
+                   double dy, int *rec_count, int *rec_off);
+size_t szk_eul_sort_bytes(int n_rec);
+struct SzkEulArgs {
+    int n_floes, nx, ny, n_rec, n_out;
+    const double *d_xg, *d_yg;
+    double dx, dy;
+    int *rec_count, *rec_off, *rec_floe, *rec_cell, *val_in, *val_out, *cell_start, *big, *n_big;
+    double *rec_area;
+    unsigned long long *key_in, *key_out;
+    void *sort_tmp;
+    size_t sort_bytes;
+    const int *kinds;  // host
+    double *d_data;
+};
+
+int szk_eul_run(const Launch &L, const Store &S, const SzkEulArgs &A);
 long long szk_launch_count(bool reset);
 void szk_count_launches(int n);

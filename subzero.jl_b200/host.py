@@ -517,6 +517,41 @@ def timestep_floe_properties(floes, tstep, dt, floe_settings=None, consts=None, 
 # ---------------------------------------------------------------------------------------
 
 
+class GridOutputWriter:
+    """GridOutputWriter(Δtout, grid, dims; outputs) of output.jl:560-640: the averaging grid (xg, yg: dims[1] x
+    dims[2] cells over the model grid's extent) and the list of outputs; `data` is [dims[1], dims[2], n_outputs]."""
+
+    def __init__(self, dtout, grid, dims, outputs=None):
+        self.dtout = int(dtout)
+        self.outputs = list(outputs) if outputs is not None else list(capi.GRID_OUTPUTS)
+        for o in self.outputs:
+            if o not in capi.GRID_OUTPUTS:
+                raise ValueError("unknown grid output %r" % (o,))
+        self.xg = np.linspace(grid.x0, grid.xf, int(dims[0]) + 1)
+        self.yg = np.linspace(grid.y0, grid.yf, int(dims[1]) + 1)
+        self.data = np.zeros((int(dims[0]), int(dims[1]), len(self.outputs)))
+
+
+def calc_eulerian_data(floes, topography, writer, domain=None, backend=None):
+    """calc_eulerian_data!(floes, topography, writer), output.jl:794-919: floe data averaged on the writer's grid.
+    Topography (cell polygons minus topography) is outside the device path's scope."""
+    if topography is not None and len(topography) > 0:
+        raise capi.SubzeroError(-4, "calc_eulerian_data with topography stays on the host")
+    h = _make_handle(backend, Constants(), 10)
+    if domain is None:
+        pad = 1e6
+        x0, xf, y0, yf = writer.xg[0] - pad, writer.xg[-1] + pad, writer.yg[0] - pad, writer.yg[-1] + pad
+        domain = Domain(*[OpenBoundary(d, x0=x0, xf=xf, y0=y0, yf=yf) for d in (North, South, East, West)])
+    g = _default_grid_for(domain)
+    h.set_grid(g.Nx, g.Ny, g.x0, g.xf, g.y0, g.yf)
+    domain.push(h)
+    h.upload_floes(floes)
+    kinds = [capi.GRID_OUTPUTS.index(o) for o in writer.outputs]
+    writer.data[...] = h.eulerian_data(writer.xg, writer.yg, kinds)
+    h.close()
+    return writer.data
+
+
 class Simulation:
     """simulation.jl:49-81.  Only the fields the hot path reads are kept; the host processes
     (fracture, ridging, welding, simplification, writers) are out of scope and therefore OFF.
