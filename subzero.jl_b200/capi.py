@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(HERE, "csrc", "libsubzero_b200.so")
+# SZ_B200_LIB: another build of the SAME CUDA library (A/B kernel experiments); never a fallback
+PRODUCT_LIB = os.environ.get("SZ_B200_LIB") or os.path.join(HERE, "csrc", "libsubzero_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_i64_p = C.POINTER(C.c_int64)

@@ -1157,6 +1157,10 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
     h->last = *h->h_cnt;
     h->n_total = h->n_init;
     h->n_verts = h->n_verts_init;
+    if (getenv("SZ_DEBUG_COUNTS"))
+        fprintf(stderr, "counts: cand %d kept %d dom %d order %d force %d mid %d large %d overlap %d rows %d\n", h->last.n_cand,
+                h->last.n_kept, h->last.n_dom, h->last.n_order, h->last.n_force, h->last.n_mid, h->last.n_large, h->last.n_overlap,
+                h->last.n_rows);
     if (do_coupling) h->n_crec_host = h->cfg.two_way_coupling_on ? h->h_cnt->n_crec : 0;
     h->ms[0] = ev_ms(h, 0, 1);
     h->ms[1] = ev_ms(h, 1, 2);

@@ -26,6 +26,18 @@
 
 enum { TN_OK = 0, TN_DEFER = 1 };
 
+// Instruction-cache pressure (profiles/README.md, r1k): the L1.5 instruction cache holds 32 KB; with the compiler's
+// default 4x unrolling of these runtime-trip-count loops k_narrow_ab<1> was 165 KB of SASS and 25 % of its stall
+// samples were `no_instructions`.  The loops below are kept rolled (measured one by one: match-vertices -5 %,
+// clip trace / ranking -7 %; the ring gather of thread_item and the pass-1 orientation loop are better unrolled),
+// and the rare paths (degenerate crossings, many-intersect normals, containment in the flip test) are not
+// instantiated here at all: those items go to the warp kernel.  Together: narrow phase 1.17 -> 0.81 ms.
+#define TN_ROLLED _Pragma("unroll 1")
+#define U_MATCH TN_ROLLED
+#define U_RINGS TN_ROLLED
+#define U_CLIP TN_ROLLED
+#define U_SMALL TN_ROLLED
+
 // a ring in [point][thread] shared memory, optionally translated on the fly (P2 = P + dir is
 // never stored: reading P[k] + dir yields the same bits every time)
 struct TRing {
@@ -57,6 +69,7 @@ __device__ __forceinline__ TRing tring(const double2 *b, int n) {
 __device__ TN_FN double t_area2(const TRing r) {
     double a = 0.0;
     double2 p = tget(r, 0);
+    U_SMALL
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 q = tget(r, k + 1);
         a += p.x * q.y - p.y * q.x;
@@ -67,6 +80,7 @@ __device__ TN_FN double t_area2(const TRing r) {
 __device__ TN_FN double t_area2s(const TRing r) {
     double a = 0.0;
     double2 p = tgets<true>(r, 0);
+    U_SMALL
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 q = tgets<true>(r, k + 1);
         a += p.x * q.y - p.y * q.x;
@@ -78,6 +92,7 @@ __device__ __forceinline__ double t_area(const TRing r) { return fabs(t_area2(r)
 __device__ TN_FN double2 t_centroid(const TRing r) {
     double a = 0.0, cx = 0.0, cy = 0.0;
     double2 p = tget(r, 0);
+    U_SMALL
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 q = tget(r, k + 1);
         double c = p.x * q.y - p.y * q.x;
@@ -92,6 +107,7 @@ __device__ TN_FN double2 t_centroid(const TRing r) {
 __device__ TN_FN bool t_point_in_ring_q(double2 p, const TRing r) {
     bool in = false;
     double2 c = tget(r, 0);
+    U_SMALL
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 d = tget(r, k + 1);
         if (c.y < p.y && p.y <= d.y) {
@@ -106,6 +122,7 @@ __device__ TN_FN bool t_point_in_ring_q(double2 p, const TRing r) {
 __device__ TN_FN bool t_point_in_ring_p(double2 q, const TRing r) {
     bool in = false;
     double2 a = tget(r, 0);
+    U_SMALL
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 b = tget(r, k + 1);
         if (a.y <= q.y && q.y < b.y) {
@@ -120,6 +137,7 @@ __device__ TN_FN bool t_point_in_ring_p(double2 q, const TRing r) {
 __device__ TN_FN bool t_point_in_ring_ps(double2 q, const TRing r) {
     bool in = false;
     double2 a = tgets<true>(r, 0);
+    U_SMALL
     for (int k = 0; k + 1 < r.n; ++k) {
         double2 b = tgets<true>(r, k + 1);
         if (a.y <= q.y && q.y < b.y) {
@@ -131,48 +149,23 @@ __device__ TN_FN bool t_point_in_ring_ps(double2 q, const TRing r) {
     }
     return in;
 }
-__device__ TN_FN bool t_point_coveredby(double2 p, const TRing r) {
-    bool onb = false, in = false;
-    double2 a = tget(r, 0);
-    for (int k = 0; k + 1 < r.n; ++k) {
-        double2 b = tget(r, k + 1);
-        if (orient2d(a, b, p) == 0.0 && p.x >= fmin(a.x, b.x) && p.x <= fmax(a.x, b.x) && p.y >= fmin(a.y, b.y) &&
-            p.y <= fmax(a.y, b.y))
-            onb = true;
-        if ((a.y > p.y) != (b.y > p.y)) {
-            double xi = a.x + (p.y - a.y) / (b.y - a.y) * (b.x - a.x);
-            if (p.x < xi) in = !in;
-        }
-        a = b;
-    }
-    return onb || in;
-}
-__device__ TN_FN double t_point_ring_distance(double2 p, const TRing r) {
-    double best = INFINITY;
-    double2 a = tget(r, 0);
-    for (int k = 0; k + 1 < r.n; ++k) {
-        double2 b = tget(r, k + 1);
-        best = fmin(best, point_segment_distance(p, a, b));
-        a = b;
-    }
-    return best;
-}
 // NOTE on control flow in this file: no `return` / `break` out of nested loops.  ncu (profiles/r1f)
 // showed 4-5 active lanes in the region trace: a divergent lane that leaves through an early return only
 // reconverges at the function exit.  Failures set a flag, loops run to a structured exit.
-__device__ TN_FN bool t_rings_intersect(const TRing A, const TRing B) {
+__device__ TN_FN bool t_rings_intersect(const TRing A, const TRing B, bool &nohit) {
     bool hit = false;
+    U_RINGS
     for (int e = 0; e + 1 < A.n && !hit; ++e) {
         double2 a = tget(A, e), b = tget(A, e + 1);
         double2 c = tget(B, 0);
+        U_RINGS
         for (int f = 0; f + 1 < B.n; ++f) {
             double2 d = tget(B, f + 1), p0, p1;
             hit |= segment_intersection(a, b, c, d, p0, p1) > 0;
             c = d;
         }
     }
-    if (!hit) hit = t_point_coveredby(tget(A, 0), B);
-    if (!hit) hit = t_point_coveredby(tget(B, 0), A);
+    if (!hit) nohit = true;  // containment or disjoint (GO.intersects then tests coveredby): rare, warp kernel
     return hit;
 }
 
@@ -213,7 +206,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                 double2 pv = tgets<SHIFT>(P, v);
                 double2 c = tget(Q, 0);
                 cur = 0;
-                for (int f = 0; f < nq; ++f) {
+                        for (int f = 0; f < nq; ++f) {
                     double2 d = tget(Q, f + 1);
                     double o = orient2d(c, d, pv);
                     anyzero |= (o == 0.0);
@@ -243,6 +236,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     }
     // pass 2a: which candidates are crossings (the Q edge must straddle the P edge's line as well)
     int K = 0;
+    U_CLIP
     for (int k = 0; k < nc; ++k) {
         const int e = ce[k], f = cf[k];
         double2 a = tgets<SHIFT>(P, e), b = tgets<SHIFT>(P, e + 1);
@@ -259,6 +253,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         }
     }
     // pass 2b (lanes in step again): parameters and point of every crossing
+    U_CLIP
     for (int k = 0; k < K; ++k) {
         const int e = xe[k], f = xf[k];
         double2 a = tgets<SHIFT>(P, e), b = tgets<SHIFT>(P, e + 1);
@@ -278,8 +273,10 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     }
     if (K_out) {
         bool dup = false;
+        U_CLIP
         for (int k = 0; k < K; ++k) {
             xp_out[k * TN_NT] = xp[k];
+            U_CLIP
             for (int m = 0; m < k; ++m) dup |= (xp[m].x == xp[k].x && xp[m].y == xp[k].y);
         }
         *K_out = K;
@@ -294,14 +291,17 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
             status = TN_DEFER;
             return 0;
         }
+        U_CLIP
         for (int k = 0; k < src.n; ++k) R[k * TN_NT] = pin ? tgets<SHIFT>(src, k) : tget(src, k);
         rs[0] = 0;
         re[0] = src.n;
         return 1;
     }
     int nentry = 0;
+    U_CLIP
     for (int k = 0; k < K; ++k) {
         int rp = 0, rq = 0;
+        U_CLIP
         for (int m = 0; m < K; ++m) {
             if (m == k) continue;
             if (xe[m] < xe[k] || (xe[m] == xe[k] && (xt[m] < xt[k] || (xt[m] == xt[k] && m < k)))) rp++;
@@ -327,6 +327,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
             else R[(npts++) * TN_NT] = _p;                                                           \
         }                                                                                            \
     } while (0)
+    U_CLIP
     for (int r = 0; r < K && !fail; ++r) {
         const int startk = ordP[r];
         if (xent[startk] && !xvis[startk]) {
@@ -341,6 +342,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                     TN_PUSH(xp[cur]);
                     int rn = rankP[cur] + 1 == K ? 0 : rankP[cur] + 1, nx = ordP[rn];
                     int cnt = xe[nx] - xe[cur] + (rn == 0 ? np : 0);
+                    U_CLIP
                     for (int k = 0, v = xe[cur] + 1; k < cnt; ++k, ++v) {
                         if (v >= np) v -= np;
                         TN_PUSH(tgets<SHIFT>(P, v));
@@ -356,6 +358,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                             int rq = rankQ[nx] + 1 == K ? 0 : rankQ[nx] + 1;
                             nn = ordQ[rq];
                             cnt = xf[nn] - xf[nx] + (rq == 0 ? nq : 0);
+                            U_CLIP
                             for (int k = 0, v = xf[nx] + 1; k < cnt; ++k, ++v) {
                                 if (v >= nq) v -= nq;
                                 TN_PUSH(tget(Q, v));
@@ -364,6 +367,7 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                             int rq = rankQ[nx] == 0 ? K - 1 : rankQ[nx] - 1;
                             nn = ordQ[rq];
                             cnt = xf[nx] - xf[nn] + (rankQ[nx] == 0 ? nq : 0);
+                            U_CLIP
                             for (int k = 0, v = xf[nx]; k < cnt; ++k, --v) {
                                 if (v < 0) v += nq;
                                 TN_PUSH(tget(Q, v));
@@ -415,39 +419,6 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     return nreg;
 }
 
-// GO.intersection_points, de-duplicated in discovery order; ip is [point][thread]
-__device__ TN_FN int t_intersection_points(const TRing P, const TRing Q, double2 *ip, int &status) {
-    int n = 0;
-    bool fail = false;
-    for (int e = 0; e + 1 < P.n; ++e) {
-        double2 a = tget(P, e), b = tget(P, e + 1);
-        double2 c = tget(Q, 0);
-        for (int f = 0; f + 1 < Q.n; ++f) {
-            double2 d = tget(Q, f + 1);
-            double2 t0, t1;
-            int cnt = segment_intersection(a, b, c, d, t0, t1);
-            for (int k = 0; k < cnt; ++k) {
-                double2 t = k == 0 ? t0 : t1;
-                bool dup = false;
-                for (int m = 0; m < n; ++m) {
-                    double2 v = ip[m * TN_NT];
-                    dup |= (v.x == t.x && v.y == t.y);
-                }
-                if (!dup) {
-                    if (n == TN_MAXIP) fail = true;
-                    else ip[(n++) * TN_NT] = t;
-                }
-            }
-            c = d;
-        }
-    }
-    if (fail) {
-        status = TN_DEFER;
-        n = 0;
-    }
-    return n;
-}
-
 // which_vertices_match_points, floe_utils.jl:331-352
 __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing reg, int *idx) {
     int m = 0, npoints = nip;
@@ -455,12 +426,14 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
         double2 f = ip[0], l = ip[(nip - 1) * TN_NT];
         if (f.x == l.x && f.y == l.y) npoints -= 1;
     }
+    U_MATCH
     for (int i = 0; i < npoints; ++i) {
         double2 p = ip[i * TN_NT];
         // the reference takes the first vertex with the smallest sqrt(sqrt(d2)) (floe_utils.jl:339-345).  sqrt is
         // monotone, so that vertex has d2 within rounding of the smallest d2: the two square roots are only
         // evaluated for those few candidates — same index, same threshold decision.
         double m2 = INFINITY;
+        U_MATCH
         for (int j = 0; j < reg.n; ++j) {
             double2 v = tget(reg, j);
             double dx = v.x - p.x, dy = v.y - p.y;
@@ -469,6 +442,7 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
         const double lim = m2 * (1.0 + 1e-12);
         double min_dist = INFINITY;
         int min_vert = 0;
+        U_MATCH
         for (int j = 0; j < reg.n; ++j) {
             double2 v = tget(reg, j);
             double dx = v.x - p.x, dy = v.y - p.y;
@@ -483,6 +457,7 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
         }
         if (min_dist < 1.0) idx[m++] = min_vert;
     }
+    U_MATCH
     for (int a = 1; a < m; ++a) {
         int v = idx[a], b = a - 1;
         while (b >= 0 && idx[b] > v) {
@@ -492,46 +467,6 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
         idx[b + 1] = v;
     }
     return m;
-}
-
-// _many_intersect_normal_force!, collisions.jl:78-119
-__device__ TN_FN double t_many_intersect_normal(double dir[2], const TRing reg, const TRing P, double ff) {
-    double x1 = 0, y1 = 0, dl = 0, Fx = 0, Fy = 0;
-    int n_pts = 0;
-    for (int i = 0; i < reg.n; ++i) {
-        double2 v = tget(reg, i);
-        double x2 = v.x, y2 = v.y;
-        if (i == 0) {
-            x1 = x2;
-            y1 = y2;
-            continue;
-        }
-        double xmid = 0.5 * (x2 + x1), ymid = 0.5 * (y2 + y1);
-        double dist = t_point_ring_distance(make_double2(xmid, ymid), P);
-        if (dist < 1e-8) {
-            double dx = x2 - x1, dy = y2 - y1;
-            double mag = sqrt(dx * dx + dy * dy);
-            double xt = xmid + (-dy / (100 * mag));
-            double yt = ymid + (dx / (100 * mag));
-            bool in_region = t_point_coveredby(make_double2(xt, yt), reg);
-            double fs = (in_region ? 1.0 : -1.0) * ff;
-            Fx = Fx + fs * (-dy);
-            Fy = Fy + fs * dx;
-            dl += mag;
-            n_pts += 1;
-        }
-        x1 = x2;
-        y1 = y2;
-    }
-    if (0 < n_pts && n_pts < reg.n - 1) {
-        dl /= n_pts;
-        if (dl > 0.1) {
-            double nf = sqrt(Fx * Fx + Fy * Fy);
-            dir[0] = Fx / nf;
-            dir[1] = Fy / nf;
-        }
-    }
-    return dl;
 }
 
 struct TWs {
@@ -553,8 +488,9 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
             dir[0] = -dy / dl;
             dir[1] = dx / dl;
         }
-    } else if (m != 0) {
-        dl = t_many_intersect_normal(dir, reg, P, ff);
+    } else if (m != 0) {  // _many_intersect_normal_force! (collisions.jl:78-119): rare, warp kernel
+        status = TN_DEFER;
+        return 0.0;
     }
     if (dl > 0.1) {
         TRing P2 = P;
@@ -564,13 +500,17 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
         int rs2[TN_MAXREG], re2[TN_MAXREG];
         int nreg2 = t_clip<true>(P2, Q, w.R2, w.r2cap, rs2, re2, status, nullptr, nullptr, nullptr);
         if (status != TN_OK) return 0.0;
+        bool defer = false;
         for (int r = 0; r < nreg2; ++r) {
             TRing nr = tring(w.R2 + rs2[r] * TN_NT, re2[r] - rs2[r]);
-            if (t_rings_intersect(nr, reg) && t_area(nr) / area > 1) {
+            bool nohit = false;
+            if (t_rings_intersect(nr, reg, nohit) && t_area(nr) / area > 1) {
                 dir[0] *= -1;
                 dir[1] *= -1;
             }
+            defer |= nohit;
         }
+        if (defer) status = TN_DEFER;
     }
     force[0] = dir[0] * area * ff;
     force[1] = dir[1] * area * ff;
@@ -619,7 +559,7 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
         const double2 *gP = S.verts + S.vstart[fi];
         for (int k = 0; k < npp; ++k) w.P[k * TN_NT] = gP[k];
         if (gQ) {
-            for (int k = 0; k < nqp; ++k) w.Q[k * TN_NT] = gQ[k];
+                for (int k = 0; k < nqp; ++k) w.Q[k * TN_NT] = gQ[k];
         } else {  // _make_bounding_box_polygon, floe_utils.jl:104-108
             double xmin = D->rect[elem][0], xmax = D->rect[elem][1], ymin = D->rect[elem][2], ymax = D->rect[elem][3];
             w.Q[0 * TN_NT] = make_double2(xmin, ymin);
@@ -708,13 +648,15 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     if (forces) {
         // calc_elastic_forces, collisions.jl:149-188
         // GO.intersection_points: the crossing points of clip #1 when the configuration is generic
-        int nip = generic ? K1 : t_intersection_points(Pr, Qr, w.ip, status);
-        if (status != TN_OK) return TI_WARP;
+        // GO.intersection_points are the crossing points of clip #1 when the configuration is generic; the rare
+        // degenerate configurations (an orientation exactly zero, duplicate points) go to the warp kernel
+        if (!generic) return TI_WARP;
+        const int nip = K1;
         if (nip >= 2) {
             int n1 = npp - 1, n2 = nqp - 1;
             double min_area = (double)((n1 < n2 ? n1 : n2) * 100) / 1.75;
             const double iu = S.u[fi], iv = S.v[fi], ixi = S.xi[fi], icx = S.cx[fi], icy = S.cy[fi];
-            for (int r = 0; r < nreg; ++r) {
+                for (int r = 0; r < nreg; ++r) {
                 if (area1[r] < min_area) continue;
                 double c[6] = {0.0, 0.0, 0.0, 0.0, area1[r], 0.0};
                 if (area1[r] != 0) {
