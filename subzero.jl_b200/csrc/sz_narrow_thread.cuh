@@ -419,8 +419,15 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     return nreg;
 }
 
-// which_vertices_match_points, floe_utils.jl:331-352
-__device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing reg, int *idx) {
+// which_vertices_match_points, floe_utils.jl:331-352.
+// The reference takes, for every intersection point, the FIRST vertex with the smallest dist = sqrt(sqrt(d2)) and
+// keeps it if dist < 1.  No square root is needed for that: sqrt is monotone and correctly rounded, so
+//   * dist < 1  <=>  d2 < 1  (the largest double below 1 has a square root below 1), and
+//   * the first vertex with the smallest dist is the first vertex with the smallest d2 unless another vertex has
+//     a d2 within a few ulp above the minimum (then the two roots may tie and the earlier index wins).  That
+//     near-tie (never seen on the bench fields) sets `rare`: the item is left to the warp kernel, which evaluates
+//     the roots.  ncu r1k: the two divergent DSQRT expansions were 7 % of the instructions of k_narrow_ab<1>.
+__device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing reg, int *idx, bool &rare) {
     int m = 0, npoints = nip;
     if (nip > 0) {
         double2 f = ip[0], l = ip[(nip - 1) * TN_NT];
@@ -429,33 +436,23 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
     U_MATCH
     for (int i = 0; i < npoints; ++i) {
         double2 p = ip[i * TN_NT];
-        // the reference takes the first vertex with the smallest sqrt(sqrt(d2)) (floe_utils.jl:339-345).  sqrt is
-        // monotone, so that vertex has d2 within rounding of the smallest d2: the two square roots are only
-        // evaluated for those few candidates — same index, same threshold decision.
-        double m2 = INFINITY;
-        U_MATCH
-        for (int j = 0; j < reg.n; ++j) {
-            double2 v = tget(reg, j);
-            double dx = v.x - p.x, dy = v.y - p.y;
-            m2 = fmin(m2, dx * dx + dy * dy);
-        }
-        const double lim = m2 * (1.0 + 1e-12);
-        double min_dist = INFINITY;
+        double m2 = INFINITY, s2 = INFINITY;  // smallest and second smallest DISTINCT squared distance
         int min_vert = 0;
         U_MATCH
         for (int j = 0; j < reg.n; ++j) {
             double2 v = tget(reg, j);
             double dx = v.x - p.x, dy = v.y - p.y;
             double d2 = dx * dx + dy * dy;
-            if (d2 <= lim) {
-                double dist = sqrt(sqrt(d2));
-                if (dist < min_dist) {
-                    min_dist = dist;
-                    min_vert = j;
-                }
+            if (d2 < m2) {
+                s2 = m2;
+                m2 = d2;
+                min_vert = j;
+            } else if (d2 > m2 && d2 < s2) {
+                s2 = d2;
             }
         }
-        if (min_dist < 1.0) idx[m++] = min_vert;
+        rare |= s2 <= m2 * (1.0 + 1e-12);
+        if (m2 < 1.0) idx[m++] = min_vert;
     }
     U_MATCH
     for (int a = 1; a < m; ++a) {
@@ -479,8 +476,12 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
                                               double area, int nip, double ff, double force[2], int &status) {
     double dir[2] = {0.0, 0.0}, dl = 0.0;
     int idx[TN_MAXIP];
-    int m = t_match_vertices(w.ip, nip, reg, idx);
-    if (m == 2) {
+    bool rare = false;
+    int m = t_match_vertices(w.ip, nip, reg, idx, rare);
+    // m not in {0, 2}: _many_intersect_normal_force! (collisions.jl:78-119) — rare, like a near-tie above: the item
+    // goes to the warp kernel (no early return: a divergent return only reconverges at the function exit)
+    bool defer = rare || (m != 2 && m != 0);
+    if (m == 2 && !defer) {
         double2 v0 = tget(reg, idx[0]), v1 = tget(reg, idx[1]);
         double dx = v1.x - v0.x, dy = v1.y - v0.y;
         dl = sqrt(dx * dx + dy * dy);
@@ -488,9 +489,6 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
             dir[0] = -dy / dl;
             dir[1] = dx / dl;
         }
-    } else if (m != 0) {  // _many_intersect_normal_force! (collisions.jl:78-119): rare, warp kernel
-        status = TN_DEFER;
-        return 0.0;
     }
     if (dl > 0.1) {
         TRing P2 = P;
@@ -499,8 +497,8 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
         P2.sy = dir[1];
         int rs2[TN_MAXREG], re2[TN_MAXREG];
         int nreg2 = t_clip<true>(P2, Q, w.R2, w.r2cap, rs2, re2, status, nullptr, nullptr, nullptr);
-        if (status != TN_OK) return 0.0;
-        bool defer = false;
+        defer |= status != TN_OK;
+        if (defer) nreg2 = 0;
         for (int r = 0; r < nreg2; ++r) {
             TRing nr = tring(w.R2 + rs2[r] * TN_NT, re2[r] - rs2[r]);
             bool nohit = false;
@@ -510,8 +508,8 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
             }
             defer |= nohit;
         }
-        if (defer) status = TN_DEFER;
     }
+    if (defer) status = TN_DEFER;
     force[0] = dir[0] * area * ff;
     force[1] = dir[1] * area * ff;
     return dl;
