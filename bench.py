@@ -191,6 +191,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prod = capi.product()
 
@@ -299,7 +300,7 @@ def main():
         dist.all_reduce(hs, op=dist.ReduceOp.MAX)
         halo = {"halo_floes_max": int(hs[0]), "send_bytes_per_step_max": int(hs[1]), "skin_m": args.skin,
                 "max_displacement_m": float(hs[2]), "lists_stale": bool(hs[2] > 0.5 * args.skin),
-                "exchange": "sz_halo_pack -> NCCL isend/irecv (torch.distributed) -> sz_halo_unpack, every step"}
+                "exchange": "sz_halo_pack_on -> NCCL isend/irecv (torch.distributed) -> sz_halo_unpack_on, stream-ordered, every step"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

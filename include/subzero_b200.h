@@ -235,6 +235,13 @@ int32_t SZ_FN(halo_configure)(sz_handle *h, int32_t n_lists, const int64_t *list
 int32_t SZ_FN(halo_bytes)(sz_handle *h, int32_t list, int64_t *bytes);
 int32_t SZ_FN(halo_pack)(sz_handle *h, int32_t list, void *dst, int64_t capacity_bytes);
 int32_t SZ_FN(halo_unpack)(sz_handle *h, int32_t list, const void *src, int64_t bytes);
+/* The same two calls ordered on the CALLER's stream instead of returning after a host synchronisation:
+ * `stream` is the cudaStream_t the caller's communication is enqueued on (ncclSend/ncclRecv, torch.distributed's
+ * current stream).  pack -> send/recv -> unpack -> sz_step then run back to back on the device: sz_halo_unpack_on
+ * makes the handle's own stream wait for the unpack kernel, nothing blocks the host.  The caller must not touch
+ * the buffers from another stream in between.  The oracle build (host buffers) ignores `stream`. */
+int32_t SZ_FN(halo_pack_on)(sz_handle *h, int32_t list, void *dst, int64_t capacity_bytes, void *stream);
+int32_t SZ_FN(halo_unpack_on)(sz_handle *h, int32_t list, const void *src, int64_t bytes, void *stream);
 
 /* ---- geometry service (test hook; also what SURVEY §8(f) rank 2 reuses) ---------------------- */
 /* Clip two closed rings; regions are written as consecutive closed rings into out_xy

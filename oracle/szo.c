@@ -1661,6 +1661,16 @@ int32_t szo_halo_unpack(sz_handle *h, int32_t list, const void *src, int64_t byt
     return SZ_OK;
 }
 
+/* host buffers: nothing to order, `stream` is ignored */
+int32_t szo_halo_pack_on(sz_handle *h, int32_t list, void *dst, int64_t cap, void *stream) {
+    (void)stream;
+    return szo_halo_pack(h, list, dst, cap);
+}
+int32_t szo_halo_unpack_on(sz_handle *h, int32_t list, const void *src, int64_t bytes, void *stream) {
+    (void)stream;
+    return szo_halo_unpack(h, list, src, bytes);
+}
+
 int32_t szo_clip_polygons(sz_handle *h, const double *p_xy, int32_t np, const double *q_xy, int32_t nq,
                           int32_t cap_regions, int32_t cap_points, int32_t *out_offsets, double *out_xy,
                           double *out_areas) {

@@ -119,6 +119,8 @@ class Library:
         "halo_bytes": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
         "halo_pack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
         "halo_unpack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+        "halo_pack_on": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+        "halo_unpack_on": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
         "pair_overlap_areas": (C.c_int32, [C.c_void_p, C.c_int64, c_i64_p, c_double_p, c_u8_p]),
         "eulerian_data": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int32, c_i32_p, c_double_p]),
         "clip_polygons": (C.c_int32, [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
@@ -447,6 +449,13 @@ class Handle:
 
     def halo_unpack(self, k, ptr, nbytes):
         self._ck(self.lib.halo_unpack(self.h, k, C.c_void_p(ptr), nbytes))
+
+    def halo_pack_on(self, k, ptr, capacity, stream):
+        """Stream-ordered pack (no host synchronisation); stream: cudaStream_t as an integer."""
+        self._ck(self.lib.halo_pack_on(self.h, k, C.c_void_p(ptr), capacity, C.c_void_p(stream)))
+
+    def halo_unpack_on(self, k, ptr, nbytes, stream):
+        self._ck(self.lib.halo_unpack_on(self.h, k, C.c_void_p(ptr), nbytes, C.c_void_p(stream)))
 
     # services for the host-side processes -------------------------------------------------------------
     def pair_overlap_areas(self, pairs):

@@ -38,7 +38,7 @@ struct sz_handle {
     cudaEvent_t ev_fork, ev_join, ev_c0, ev_c1;
     // sz_step_host: host -> device copies on stream_up and device -> host copies on stream_dn overlap the kernels
     cudaStream_t stream_up, stream_dn;
-    cudaEvent_t ev_up[4], ev_dn[3], ev_up_start, ev_dn_end;
+    cudaEvent_t ev_up[4], ev_dn[3], ev_up_start, ev_dn_end, ev_halo;
     double2 *d_cf_dn;  // [n][2] staging of collision_force in the host layout
     int cf_cap;
     Params P;
@@ -292,6 +292,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     for (int k = 0; k < 3; ++k) cudaEventCreate(&h->ev_dn[k]);
     cudaEventCreate(&h->ev_up_start);
     cudaEventCreate(&h->ev_dn_end);
+    cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming);
     for (int k = 0; k < NEV; ++k) cudaEventCreate(&h->ev[k]);
     if (cudaMallocHost((void **)&h->h_cnt, sizeof(Counters)) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
     memset(h->h_cnt, 0, sizeof(Counters));
@@ -1340,16 +1341,37 @@ extern "C" int32_t sz_halo_bytes(sz_handle *h, int32_t list, int64_t *bytes) {
     return SZ_OK;
 }
 
-static int32_t halo_move(sz_handle *h, int32_t list, void *buf, int64_t bytes, bool pack) {
+static int32_t halo_move(sz_handle *h, int32_t list, void *buf, int64_t bytes, bool pack, bool on_stream = false,
+                         cudaStream_t user = nullptr) {
     if (!h || !buf || list < 0 || list >= h->n_lists) return SZ_ERR_INVALID;
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "halo exchange with ghosts present");
     if (pack ? bytes < h->hl_bytes[list] : bytes != h->hl_bytes[list]) return fail(h, pack ? SZ_ERR_CAPACITY : SZ_ERR_INVALID, "halo buffer size does not match the configured list");
     cudaSetDevice(h->cfg.device);
     long long a = h->hl_off[list], n = h->hl_off[list + 1] - a;
+    if (on_stream) {
+        // every earlier call on this handle has synchronised: the store is complete.  The kernel runs on the
+        // caller's stream; after an unpack the handle's stream waits for it (device-side), so the next sz_step is
+        // ordered behind the halo update without a host synchronisation
+        Launch Lu = h->L;
+        Lu.stream = user;
+        szk_halo(Lu, h->S, h->d_hl_idx + a, h->d_hl_voff + a, (int)n, (double *)buf, pack);
+        if (!pack) {
+            CK(cudaEventRecord(h->ev_halo, user));
+            CK(cudaStreamWaitEvent(h->L.stream, h->ev_halo, 0));
+        }
+        CK(cudaGetLastError());
+        return SZ_OK;
+    }
     szk_halo(h->L, h->S, h->d_hl_idx + a, h->d_hl_voff + a, (int)n, (double *)buf, pack);
     CK(cudaStreamSynchronize(h->L.stream));  // the caller's communication runs on its own stream
     CK(cudaGetLastError());
     return SZ_OK;
+}
+extern "C" int32_t sz_halo_pack_on(sz_handle *h, int32_t list, void *dst, int64_t cap, void *stream) {
+    return halo_move(h, list, dst, cap, true, true, (cudaStream_t)stream);
+}
+extern "C" int32_t sz_halo_unpack_on(sz_handle *h, int32_t list, const void *src, int64_t bytes, void *stream) {
+    return halo_move(h, list, (void *)src, bytes, false, true, (cudaStream_t)stream);
 }
 extern "C" int32_t sz_halo_pack(sz_handle *h, int32_t list, void *dst, int64_t cap) { return halo_move(h, list, dst, cap, true); }
 extern "C" int32_t sz_halo_unpack(sz_handle *h, int32_t list, const void *src, int64_t bytes) { return halo_move(h, list, (void *)src, bytes, false); }

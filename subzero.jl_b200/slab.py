@@ -149,24 +149,35 @@ class SlabRank:
         self.rbuf = [torch.empty(max(self.nbytes[2 * k + 1], 8), dtype=torch.uint8, device=device) for k in range(len(self.partners))]
 
     def exchange(self):
-        """pack -> send/recv (torch.distributed: NCCL for CUDA buffers, gloo for host buffers) -> unpack"""
+        """pack -> send/recv (torch.distributed: NCCL for CUDA buffers, gloo for host buffers) -> unpack.
+        CUDA buffers: everything is ordered on torch's current stream (sz_halo_*_on): the pack kernels, the NCCL
+        send/recv pairs, the unpack kernels and the following sz_step run back to back on the device, the host
+        does not wait anywhere."""
         import torch.distributed as dist
+        cuda = bool(self.sbuf) and self.sbuf[0].is_cuda
+        stream = None
+        if cuda:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
         ops = []
         for k, s in enumerate(self.partners):
             if self.nbytes[2 * k]:
-                self.h.halo_pack(2 * k, self.sbuf[k].data_ptr(), self.nbytes[2 * k])
+                if cuda:
+                    self.h.halo_pack_on(2 * k, self.sbuf[k].data_ptr(), self.nbytes[2 * k], stream)
+                else:
+                    self.h.halo_pack(2 * k, self.sbuf[k].data_ptr(), self.nbytes[2 * k])
                 ops.append(dist.P2POp(dist.isend, self.sbuf[k][:self.nbytes[2 * k]], s))
             if self.nbytes[2 * k + 1]:
                 ops.append(dist.P2POp(dist.irecv, self.rbuf[k][:self.nbytes[2 * k + 1]], s))
         if ops:
             for r in dist.batch_isend_irecv(ops):
-                r.wait()
-            if self.sbuf[0].is_cuda:
-                import torch
-                torch.cuda.current_stream().synchronize()
+                r.wait()  # NCCL: the current stream waits for the transfer, the host does not
         for k, s in enumerate(self.partners):
             if self.nbytes[2 * k + 1]:
-                self.h.halo_unpack(2 * k + 1, self.rbuf[k].data_ptr(), self.nbytes[2 * k + 1])
+                if cuda:
+                    self.h.halo_unpack_on(2 * k + 1, self.rbuf[k].data_ptr(), self.nbytes[2 * k + 1], stream)
+                else:
+                    self.h.halo_unpack(2 * k + 1, self.rbuf[k].data_ptr(), self.nbytes[2 * k + 1])
 
     def owned_state(self):
         """(global indices, FloeArrays) of the owned floes, downloaded from the handle."""
@@ -279,25 +290,32 @@ def rebuild_local(ranks):
 
 def exchange_local(ranks):
     """Single-process stand-in for the send/recv (tests: several ranks emulated on one device or
-    on the CPU oracle): pack on the owner, hand the buffer over, unpack on the copy holder."""
+    on the CPU oracle): pack on the owner, hand the buffer over, unpack on the copy holder.  On a CUDA
+    device it takes the stream-ordered path of `exchange` (sz_halo_*_on on torch's current stream)."""
     import torch
+    cuda = bool(ranks) and bool(ranks[0].sbuf) and ranks[0].sbuf[0].is_cuda
+    stream = torch.cuda.current_stream().cuda_stream if cuda else None
     for a in ranks:
         for k, s in enumerate(a.partners):
             nb = a.nbytes[2 * k]
             if not nb:
                 continue
-            a.h.halo_pack(2 * k, a.sbuf[k].data_ptr(), nb)
+            if cuda:
+                a.h.halo_pack_on(2 * k, a.sbuf[k].data_ptr(), nb, stream)
+            else:
+                a.h.halo_pack(2 * k, a.sbuf[k].data_ptr(), nb)
             b = ranks[s]
             kb = b.partners.index(a.rank)
             assert b.nbytes[2 * kb + 1] == nb, (a.rank, s, nb, b.nbytes[2 * kb + 1])
             b.rbuf[kb][:nb].copy_(a.sbuf[k][:nb])
-    if ranks and ranks[0].sbuf and ranks[0].sbuf[0].is_cuda:
-        torch.cuda.synchronize()
     for b in ranks:
         for k, s in enumerate(b.partners):
             nb = b.nbytes[2 * k + 1]
             if nb:
-                b.h.halo_unpack(2 * k + 1, b.rbuf[k].data_ptr(), nb)
+                if cuda:
+                    b.h.halo_unpack_on(2 * k + 1, b.rbuf[k].data_ptr(), nb, stream)
+                else:
+                    b.h.halo_unpack(2 * k + 1, b.rbuf[k].data_ptr(), nb)
 
 
 def equal_count_edges(cx, world, period_x=None, x_west=0.0):
