@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--npoints", type=int, default=1000, help="Monte-Carlo draws per floe (about 59 %% are kept)")
     ap.add_argument("--walls", default="collision", choices=["collision", "periodic", "shear"])
     ap.add_argument("--scale", type=float, default=1.01)
+    ap.add_argument("--flow", default="random", choices=["random", "converging"],
+                    help="initial floe velocities: U(-0.1, 0.1) m/s or a flow converging on the domain centre (BASELINE config 5)")
     ap.add_argument("--cpu-sample", type=int, default=25000, help="floes of the cpu_baseline sample field")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -124,7 +126,7 @@ def oracle_steps_per_s(args, n_sample, steps, warmup, threads=0):
     from subzero_jl_b200 import synth
     from oracle import szo
     lib = szo.oracle()
-    f = synth.make_field(n_sample, scale=args.scale, walls=args.walls, npoints=args.npoints)
+    f = synth.make_field(n_sample, scale=args.scale, walls=args.walls, npoints=args.npoints, flow=args.flow)
     threads = threads or os.cpu_count()  # explicit: torchrun exports OMP_NUM_THREADS=1
     h = synth.setup_handle(f, lib, threads=threads)
     for t in range(warmup):
@@ -168,8 +170,8 @@ def run_reference(args, rank):
 
 def workload_config(args, world):
     return {"workload": "synthetic Voronoi-packed %d floes per GPU (BASELINE config 3), scale %.2f dense contacts, "
-                        "%s walls, collisions + one-way ocean/atmosphere coupling every step + state update"
-                        % (args.floes, args.scale, args.walls),
+                        "%s walls, %s initial flow, collisions + one-way ocean/atmosphere coupling every step + state update"
+                        % (args.floes, args.scale, args.walls, args.flow),
             "floes_per_gpu": args.floes, "mc_draws_per_floe": args.npoints, "coupling_every": 1, "dt_s": 10,
             "parallelism": "1 GPU" if world == 1 else "%d spatial slabs, one rank per GPU" % world,
             "l2": "Monte-Carlo points (%.2f GB per GPU at 100k floes) exceed the 126 MB L2; no explicit flush" % 0.95}
@@ -197,7 +199,7 @@ def main():
 
     me = None
     if world == 1:
-        f = synth.make_field(args.floes, scale=args.scale, walls=args.walls, npoints=args.npoints, seed=args.floes)
+        f = synth.make_field(args.floes, scale=args.scale, walls=args.walls, npoints=args.npoints, seed=args.floes, flow=args.flow)
         h = synth.setup_handle(f, prod, device=local_rank, two_way_coupling_on=int(args.two_way))
         fa0 = f.floes
     else:
@@ -206,6 +208,9 @@ def main():
         from subzero_jl_b200 import slab
         tile = synth.make_field(args.floes, scale=args.scale, walls="collision", npoints=args.npoints, seed=args.floes + rank)
         slab.shift_x(tile.floes, rank * tile.L)
+        if args.flow == "converging":  # towards the centre of the whole (world x 1 tiles) domain
+            tile.floes.u = -0.2 * (tile.floes.centroid_x - 0.5 * world * tile.L) / (world * tile.L)
+            tile.floes.v = -0.2 * (tile.floes.centroid_y - 0.5 * tile.L) / tile.L
         ew = "shear" if args.walls in ("shear", "periodic") else "collision"
         f = synth.tiled_model(tile, world, ew)
         me = slab.partition_tiles(tile.floes, rank, world, tile.L, world * tile.L if ew == "shear" else None, skin=args.skin)

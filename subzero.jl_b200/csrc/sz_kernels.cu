@@ -969,23 +969,41 @@ __global__ void k_row_check(Store S, StepBuf B) {
 
 // rows of floe f in the reference's order: own pairs (j ascending, regions in clip order), walls
 // N,S,E,W, topography (collisions.jl:776-794), mirrored rows (i ascending, :808-827).  (sx, sy)
-// is the ghost->parent shift of the contact points (:835-838).
-__device__ int emit_base_rows(const Store &S, const StepBuf &B, int f, double *dst, double sx, double sy, bool shift) {
+// is the ghost->parent shift of the contact points (:835-838).  The per-floe totals (collisions.jl:830-862,
+// 673-686) are accumulated while the rows are written, in row order: the same bits as a second pass over the
+// rows, without reading them back.
+struct RowAcc {
+    double oa, sx, sy, st;
+};
+__device__ __forceinline__ void emit_row(double *r, double idx, double fx, double fy, double px, double py, double ov, bool sums,
+                                         double cx, double cy, RowAcc &acc) {
+    double trq = 0.0;
+    acc.oa += ov;
+    if (sums) {
+        double xp = px - cx, yp = py - cy;
+        trq = xp * fy - yp * fx;
+        acc.sx += fx;
+        acc.sy += fy;
+        acc.st += trq;
+    }
+    r[COL_IDX] = idx;
+    r[COL_FX] = fx;
+    r[COL_FY] = fy;
+    r[COL_PX] = px;
+    r[COL_PY] = py;
+    r[COL_TRQ] = trq;
+    r[COL_OV] = ov;
+}
+__device__ int emit_base_rows(const Store &S, const StepBuf &B, int f, double *dst, double sx, double sy, bool shift, bool sums,
+                              double cx, double cy, RowAcc &acc) {
     int n = 0;
     for (int p = B.up_off[f], pe = B.up_off[f + 1]; p < pe; ++p) {
         if (!B.keep[p]) continue;
         const double *src = B.pool + (size_t)B.item_row0[p] * NPOOL;
         double idx = (double)(B.pair_j[p] + 1);
         for (int k = 0, nk = B.item_nrows[p]; k < nk; ++k, ++n) {
-            double *r = dst + (size_t)n * NCOL;
             const double *c = src + k * NPOOL;
-            r[COL_IDX] = idx;
-            r[COL_FX] = c[0];
-            r[COL_FY] = c[1];
-            r[COL_PX] = shift ? c[2] - sx : c[2];
-            r[COL_PY] = shift ? c[3] - sy : c[3];
-            r[COL_TRQ] = 0.0;
-            r[COL_OV] = c[4];
+            emit_row(dst + (size_t)n * NCOL, idx, c[0], c[1], shift ? c[2] - sx : c[2], shift ? c[3] - sy : c[3], c[4], sums, cx, cy, acc);
         }
     }
     for (int q = B.dom_off[f], qe = B.dom_off[f + 1]; q < qe; ++q) {
@@ -993,15 +1011,8 @@ __device__ int emit_base_rows(const Store &S, const StepBuf &B, int f, double *d
         const double *src = B.pool + (size_t)B.item_row0[slot] * NPOOL;
         double idx = (double)(-(B.dom_elem[q] + 1));
         for (int k = 0, nk = B.item_nrows[slot]; k < nk; ++k, ++n) {
-            double *r = dst + (size_t)n * NCOL;
             const double *c = src + k * NPOOL;
-            r[COL_IDX] = idx;
-            r[COL_FX] = c[0];
-            r[COL_FY] = c[1];
-            r[COL_PX] = shift ? c[2] - sx : c[2];
-            r[COL_PY] = shift ? c[3] - sy : c[3];
-            r[COL_TRQ] = 0.0;
-            r[COL_OV] = c[4];
+            emit_row(dst + (size_t)n * NCOL, idx, c[0], c[1], shift ? c[2] - sx : c[2], shift ? c[3] - sy : c[3], c[4], sums, cx, cy, acc);
         }
     }
     for (int t = B.low_off[f], te = B.low_off[f + 1]; t < te; ++t) {
@@ -1010,15 +1021,8 @@ __device__ int emit_base_rows(const Store &S, const StepBuf &B, int f, double *d
         const double *src = B.pool + (size_t)B.item_row0[p] * NPOOL;
         double idx = (double)(B.pair_i[p] + 1);
         for (int k = 0, nk = B.item_nrows[p]; k < nk; ++k, ++n) {
-            double *r = dst + (size_t)n * NCOL;
             const double *c = src + k * NPOOL;
-            r[COL_IDX] = idx;
-            r[COL_FX] = -c[0];
-            r[COL_FY] = -c[1];
-            r[COL_PX] = shift ? c[2] - sx : c[2];
-            r[COL_PY] = shift ? c[3] - sy : c[3];
-            r[COL_TRQ] = 0.0;
-            r[COL_OV] = c[4];
+            emit_row(dst + (size_t)n * NCOL, idx, -c[0], -c[1], shift ? c[2] - sx : c[2], shift ? c[3] - sy : c[3], c[4], sums, cx, cy, acc);
         }
     }
     return n;
@@ -1032,39 +1036,27 @@ __global__ void k_row_write(Store S, StepBuf B) {
     int n = cnt->n_total;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
         double *dst = B.rows + (size_t)B.row_off[f] * NCOL;
-        int par = S.parent[f];
+        const int par = S.parent[f];
+        const bool sums = f < S.n_init;
+        const double cx = S.cx[f], cy = S.cy[f];
+        RowAcc acc = {S.overarea[f], 0.0, 0.0, 0.0};
         int nr;
         if (f >= S.n_init && par >= 0) {
-            nr = emit_base_rows(S, B, f, dst, S.cx[f] - S.cx[par], S.cy[f] - S.cy[par], true);
+            nr = emit_base_rows(S, B, f, dst, cx - S.cx[par], cy - S.cy[par], true, sums, cx, cy, acc);
         } else {
-            nr = emit_base_rows(S, B, f, dst, 0.0, 0.0, false);
+            nr = emit_base_rows(S, B, f, dst, 0.0, 0.0, false, sums, cx, cy, acc);
         }
-        if (f < S.n_init) {
+        if (sums) {
             for (int g = 0, ng = S.nghost[f]; g < ng; ++g) {
                 int gi = S.ghost_slot[f * SZ_MAX_GHOSTS + g];
-                nr += emit_base_rows(S, B, gi, dst + (size_t)nr * NCOL, S.cx[gi] - S.cx[f], S.cy[gi] - S.cy[f], true);
+                nr += emit_base_rows(S, B, gi, dst + (size_t)nr * NCOL, S.cx[gi] - cx, S.cy[gi] - cy, true, sums, cx, cy, acc);
             }
         }
-        double oa = S.overarea[f];
-        double sx = 0.0, sy = 0.0, st = 0.0;
-        const double cx = S.cx[f], cy = S.cy[f];
-        for (int k = 0; k < nr; ++k) {
-            double *r = dst + (size_t)k * NCOL;
-            oa += r[COL_OV];
-            if (f < S.n_init) {
-                double xp = r[COL_PX] - cx, yp = r[COL_PY] - cy;
-                double trq = xp * r[COL_FY] - yp * r[COL_FX];
-                r[COL_TRQ] = trq;
-                sx += r[COL_FX];
-                sy += r[COL_FY];
-                st += trq;
-            }
-        }
-        S.overarea[f] = oa;
-        if (f < S.n_init) {
-            S.cfx[f] += sx;
-            S.cfy[f] += sy;
-            S.ctrq[f] += st;
+        S.overarea[f] = acc.oa;
+        if (sums) {
+            S.cfx[f] += acc.sx;
+            S.cfy[f] += acc.sy;
+            S.ctrq[f] += acc.st;
         }
     }
 }
