@@ -55,17 +55,35 @@ struct CpReg {
     double tox, toy; // ocean stress on the ice at the point
 };
 
+// |v| for the quadratic drag laws: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps on the
+// reciprocal root (relative error ~1e-16 before the final multiply) instead of the IEEE-rounded sqrt() expansion with
+// its slow-path call: ncu r1k had the two sqrt() of a point at 23 % of the kernel's instructions.  The parity bar of
+// this kernel is 1e-9 relative (sz_kernels_fp.cu header); measured agreement with the oracle stays ~1e-15.
+__device__ __forceinline__ double cp_norm(double s) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    const double hs = 0.5 * s;
+    r = r * (1.5 - hs * r * r);
+    r = r * (1.5 - hs * r * r);
+    return s > 0.0 ? s * r : 0.0;
+}
+
 // ATM / HFLX: false when the atmosphere / heat-flux fields are identically zero (sz_set_fields checks): the
 // loads and multiply-adds of a zero field are skipped, the result is the same
-template <bool REG, bool ATM, bool HFLX>
+// INTERIOR: the floe's bounding circle lies strictly inside the grid extent (warp-uniform, decided per floe): every
+// point is in bounds and 0 <= ci < Nx, 0 <= cj < Ny, so the in-bounds test, the clamps and the periodic modulo are
+// no-ops and are not executed (15 % of the instructions of a point in ncu r1k); the arithmetic is unchanged
+template <bool REG, bool ATM, bool HFLX, bool INTERIOR = false>
 __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restrict__ F, double2 b, double ca,
                                          double sa, double cx, double cy, double u, double v, double xi, double mf,
                                          CpAcc &acc, CpReg *reg) {
     double xc = ca * b.x - sa * b.y, yc = sa * b.x + ca * b.y;  // body frame -> world, about the centroid
     double x = xc + cx, y = yc + cy;
-    bool inb = (c.per_x || (c.x0 <= x && x <= c.xf)) && (c.per_y || (c.y0 <= y && y <= c.yf));
-    if (REG) reg->cell = -1;
-    if (!inb) return;
+    if (!INTERIOR) {
+        bool inb = (c.per_x || (c.x0 <= x && x <= c.xf)) && (c.per_y || (c.y0 <= y && y <= c.yf));
+        if (REG) reg->cell = -1;
+        if (!inb) return;
+    }
     acc.n++;
     // the reference recomputes (x - cx, y - cy) from the translated point; the difference to (xc, yc) is
     // one rounding of a ~1e5 coordinate, i.e. ~1e-11 m on a ~1e3 m lever arm (1e-14 relative)
@@ -76,7 +94,10 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     int ci = (int)fx, cj = (int)fy;
     double wx = gx - fx, wy = gy - fy;
     int i0, i1, j0, j1;
-    if (c.per_x) {
+    if (INTERIOR) {
+        i0 = ci;
+        i1 = (c.per_x && ci + 1 == c.Nx) ? 0 : ci + 1;  // periodic axes: line N+1 is line 1 (coupling.jl:722-745)
+    } else if (c.per_x) {
         i0 = ci % c.Nx;
         if (i0 < 0) i0 += c.Nx;
         i1 = i0 + 1 == c.Nx ? 0 : i0 + 1;
@@ -86,7 +107,10 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
         i0 = ci;
         i1 = ci + 1;
     }
-    if (c.per_y) {
+    if (INTERIOR) {
+        j0 = cj;
+        j1 = (c.per_y && cj + 1 == c.Ny) ? 0 : cj + 1;
+    } else if (c.per_y) {
         j0 = cj % c.Ny;
         if (j0 < 0) j0 += c.Ny;
         j1 = j0 + 1 == c.Ny ? 0 : j0 + 1;
@@ -117,9 +141,9 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     double uocn = w00 * o00.x + w10 * o10.x + w01 * o01.x + w11 * o11.x;
     double vocn = w00 * o00.y + w10 * o10.y + w01 * o01.y + w11 * o11.y;
     double dua = uatm - up, dva = vatm - vp;  // calc_atmosphere_forcing, coupling.jl:1212-1232
-    double na = sqrt(dua * dua + dva * dva);
+    double na = cp_norm(dua * dua + dva * dva);
     double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
-    double no = sqrt(duo * duo + dvo * dvo);
+    double no = cp_norm(duo * duo + dvo * dvo);
     double tox = c.ko * no * (c.ct * duo - c.sn * dvo), toy = c.ko * no * (c.sn * duo + c.ct * dvo);
     double tx = c.ka * na * dua - mf * vocn + tox;
     double ty = c.ka * na * dva + mf * uocn + toy;
@@ -157,14 +181,22 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
         const double mf = mass / ar * c.f;
         CpAcc acc = {0.0, 0.0, 0.0, 0.0, 0};
         long long k = m0 + lane;
-        for (; k + 96 < m1; k += 128) {  // four independent 512-byte loads per warp in flight (HBM latency)
-            double2 b0 = __ldcs(S.mc + k), b1 = __ldcs(S.mc + k + 32), b2 = __ldcs(S.mc + k + 64), b3 = __ldcs(S.mc + k + 96);
-            cp_point<false, ATM, HFLX>(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-            cp_point<false, ATM, HFLX>(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-            cp_point<false, ATM, HFLX>(c, F, b2, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-            cp_point<false, ATM, HFLX>(c, F, b3, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+        // Monte-Carlo points lie inside the ring, i.e. within rmax of the centroid (a small margin covers rounding)
+        const double rm = S.rmax[i] * (1.0 + 1e-9) + 1e-6;
+        const bool interior = cx - rm > c.x0 && cx + rm < c.xf && cy - rm > c.y0 && cy + rm < c.yf;
+        if (interior) {
+            for (; k + 96 < m1; k += 128) {  // four independent 512-byte loads per warp in flight (HBM latency)
+                double2 b0 = __ldcs(S.mc + k), b1 = __ldcs(S.mc + k + 32), b2 = __ldcs(S.mc + k + 64), b3 = __ldcs(S.mc + k + 96);
+                cp_point<false, ATM, HFLX, true>(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, b2, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, b3, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            }
+            for (; k < m1; k += 32) cp_point<false, ATM, HFLX, true>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+        } else {  // floes at the edge of the grid (about 1 % of a large field): the general path, not unrolled
+#pragma unroll 1
+            for (; k < m1; k += 32) cp_point<false, ATM, HFLX, false>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
         }
-        for (; k < m1; k += 32) cp_point<false, ATM, HFLX>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             acc.tx += __shfl_xor_sync(FULLMASK, acc.tx, o);
