@@ -435,20 +435,21 @@ void szk_apply_coupling_tags(const Launch &L, const Store &S) {
 }
 
 // ---- K7: state update (update_floe.jl:392-551) -------------------------------------------------------------
-// One warp per floe: scalars are computed by every lane (uniform), vertices and the strain sum are
-// spread over the lanes.  calc_strain! (:425-453) evaluates u - xi r sin(theta), u + xi r cos(theta)
+// calc_strain! (:425-453) evaluates u - xi r sin(theta), u + xi r cos(theta)
 // at every vertex; with r sin(theta) = y and r cos(theta) = x those are u - xi y and u + xi x
 // (the v terms use floe.u exactly as the reference does, :441-442).
-__global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
+// One THREAD per floe.  The update is ~25 scalars and a handful of divisions per floe plus a loop over ~7 ring points
+// and ~6 rows: as a warp per floe (r1e-r1k) every one of the ~840 scalar instructions was issued once per FLOE
+// (83.7 M warp instructions per step at 100 k floes, 42 % issue slots); per thread they are issued once per 32
+// floes and the SoA loads are coalesced across the warp.  Rings of consecutive floes are contiguous, so the ring
+// loop of a warp still walks one compact region.
+__global__ void __launch_bounds__(128) k_update(Store S, StepBuf B, Params P) {
     Counters *cnt = S.cnt;
     if (cnt->error) return;
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
     const double dt = (double)P.cfg.dt;
     const int n = S.n_init;
-    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t warn = 0;
-        // every per-floe scalar is loaded up front: ~30 independent broadcast loads in flight instead of a
-        // chain of exposed latencies (ncu r1e: long_scoreboard on each first use)
         double cfx = S.cfx[i], cfy = S.cfy[i], ctrq = S.ctrq[i];
         const double cx = S.cx[i], cy = S.cy[i], area = S.area[i];
         double height = S.height[i], mass = S.mass[i], moment = S.moment[i];
@@ -456,11 +457,9 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
         const double pdx = S.p_dxdt[i], pdy = S.p_dydt[i], pda = S.p_dalphadt[i];
         const double pdu = S.p_dudt[i], pdv = S.p_dvdt[i], pdxi = S.p_dxidt[i];
         const double fxOA = S.fxOA[i], fyOA = S.fyOA[i], trqOA = S.trqOA[i];
-        const double acc_old = lane < 4 ? S.stress_accum[4 * i + lane] : 0.0;
+        const double2 acc01 = ((const double2 *)S.stress_accum)[2 * (size_t)i], acc23 = ((const double2 *)S.stress_accum)[2 * (size_t)i + 1];
         const int r0 = B.row_off[i], r1 = B.row_off[i + 1];
         const int vs = S.vstart[i], nv = S.vcount[i];
-        double2 pv0 = lane < nv ? S.verts[vs + lane] : make_double2(0.0, 0.0);
-        double2 pv1 = lane + 1 < nv ? S.verts[vs + lane + 1] : make_double2(0.0, 0.0);
         // calc_stress!, :392-414 (pre-move centroid)
         double s11 = 0, s12 = 0, s22 = 0;
         if (r1 > r0) {
@@ -477,12 +476,11 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
             s12 *= inv;
             s22 *= inv;
         }
-        double lam = P.cfg.stress_lambda;  // stress_calculators.jl:118-122
-        if (lane < 4) {
-            double sv = lane == 0 ? s11 : (lane == 3 ? s22 : s12);
-            S.stress_accum[4 * i + lane] = (1 - lam) * acc_old + lam * sv;
-            S.stress_instant[4 * i + lane] = sv;
-        }
+        const double lam = P.cfg.stress_lambda;  // stress_calculators.jl:118-122
+        ((double2 *)S.stress_accum)[2 * (size_t)i] = make_double2((1 - lam) * acc01.x + lam * s11, (1 - lam) * acc01.y + lam * s12);
+        ((double2 *)S.stress_accum)[2 * (size_t)i + 1] = make_double2((1 - lam) * acc23.x + lam * s12, (1 - lam) * acc23.y + lam * s22);
+        ((double2 *)S.stress_instant)[2 * (size_t)i] = make_double2(s11, s12);
+        ((double2 *)S.stress_instant)[2 * (size_t)i + 1] = make_double2(s12, s22);
         if (height > P.cfg.max_floe_height) {  // :482-485
             height = P.cfg.max_floe_height;
             warn |= SZ_WARN_HEIGHT_CAPPED;
@@ -535,62 +533,50 @@ __global__ void __launch_bounds__(256) k_update(Store S, StepBuf B, Params P) {
         }
         // rigid move of the ring + calc_strain! on the moved ring with the updated u, xi
         double e11 = 0, e12 = 0, e22 = 0;
-        for (int base = 0; base < nv; base += 32) {
-            const int k = base + lane;
-            const bool act = k < nv;
-            double2 p = base == 0 ? pv0 : (act ? S.verts[vs + k] : make_double2(0.0, 0.0));
+        if (nv > 0) {
+            double2 p = S.verts[vs];
             double2 q = make_double2((cs * p.x - sn * p.y) + tx, (sn * p.x + cs * p.y) + ty);
-            if (k + 1 < nv) {
-                double2 p2 = base == 0 ? pv1 : S.verts[vs + k + 1];
-                double2 q2 = make_double2((cs * p2.x - sn * p2.y) + tx, (sn * p2.x + cs * p2.y) + ty);
+            for (int k = 0; k + 1 < nv; ++k) {
+                const double2 p2 = S.verts[vs + k + 1];
+                const double2 q2 = make_double2((cs * p2.x - sn * p2.y) + tx, (sn * p2.x + cs * p2.y) + ty);
                 double x1 = q.x - ncx, y1 = q.y - ncy, x2 = q2.x - ncx, y2 = q2.y - ncy;
                 double xd = x2 - x1, yd = y2 - y1;
                 double ud = (un - xin * y2) - (un - xin * y1), vd = (un + xin * x2) - (un + xin * x1);
                 e11 += ud * yd;
                 e12 += ud * xd + vd * yd;
                 e22 += vd * xd;
+                S.verts[vs + k] = q;
+                q = q2;
             }
-            __syncwarp();
-            if (act) S.verts[vs + k] = q;
-            __syncwarp();
+            S.verts[vs + nv - 1] = q;
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            e11 += __shfl_xor_sync(FULLMASK, e11, o);
-            e12 += __shfl_xor_sync(FULLMASK, e12, o);
-            e22 += __shfl_xor_sync(FULLMASK, e22, o);
-        }
-        if (lane == 0) {
-            e12 *= 0.5;
-            double iden = 1.0 / (2 * area);
-            S.strain[4 * i + 0] = e11 * iden;
-            S.strain[4 * i + 1] = e12 * iden;
-            S.strain[4 * i + 2] = e12 * iden;
-            S.strain[4 * i + 3] = e22 * iden;
-            S.height[i] = height;
-            S.mass[i] = mass;
-            S.moment[i] = moment;
-            S.alpha[i] = alpha0 + Da;
-            S.cx[i] = ncx;
-            S.cy[i] = ncy;
-            S.p_dxdt[i] = u0;  // :509-511
-            S.p_dydt[i] = v0;
-            S.p_dalphadt[i] = xi0;
-            S.u[i] = un;
-            S.v[i] = vn;
-            S.p_dudt[i] = dudt;
-            S.p_dvdt[i] = dvdt;
-            S.xi[i] = xin;
-            S.p_dxidt[i] = dxidt;
-            S.warn[i] = warn;
-        }
+        e12 *= 0.5;
+        const double iden = 1.0 / (2 * area);
+        ((double2 *)S.strain)[2 * (size_t)i] = make_double2(e11 * iden, e12 * iden);
+        ((double2 *)S.strain)[2 * (size_t)i + 1] = make_double2(e12 * iden, e22 * iden);
+        S.height[i] = height;
+        S.mass[i] = mass;
+        S.moment[i] = moment;
+        S.alpha[i] = alpha0 + Da;
+        S.cx[i] = ncx;
+        S.cy[i] = ncy;
+        S.p_dxdt[i] = u0;  // :509-511
+        S.p_dydt[i] = v0;
+        S.p_dalphadt[i] = xi0;
+        S.u[i] = un;
+        S.v[i] = vn;
+        S.p_dudt[i] = dudt;
+        S.p_dvdt[i] = dvdt;
+        S.xi[i] = xin;
+        S.p_dxidt[i] = dxidt;
+        S.warn[i] = warn;
     }
 }
 
 void szk_update(const Launch &L, const Store &S, const StepBuf &B, const Params &P) {
     if (S.n_init <= 0) return;
-    long long blocks = ((long long)S.n_init + 7) / 8, cap = (long long)L.sms * 32;
-    k_update<<<(int)(blocks < cap ? blocks : cap), 256, 0, L.stream>>>(S, B, P);
+    long long blocks = ((long long)S.n_init + 127) / 128, cap = (long long)L.sms * 32;
+    k_update<<<(int)(blocks < cap ? blocks : cap), 128, 0, L.stream>>>(S, B, P);
     szk_count_launches(1);
 }
 
