@@ -1122,7 +1122,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_item_count<<<gi, 256, 0, st>>>(S, B);
     k_class_scan<<<1, 32, 0, st>>>(S, B);
     k_item_scatter<<<gi, 256, 0, st>>>(S, B);
-    k_narrow_ab<0><<<2 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, B, P);
+    k_narrow_ab<0><<<3 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, B, P);
     k_narrow_ab<1><<<2 * L.sms, TN_NT, TN_SMEM_B, st>>>(S, B, P);
     k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
     k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
@@ -1287,7 +1287,7 @@ void szk_cells_sort_and_clip(const Launch &L, const Store &S, const CouplingBuf 
     scan_excl(L, S, CB.cell_count, CB.cell_start, &S.cnt->n_ccells, 0, CB.cap_cells, CB.scan_block, nullptr);
     k_crec_fill<<<gr, TPB, 0, st>>>(S, CB);
     k_crec_sort<<<gc, TPB, 0, st>>>(S, CB, ncell);
-    k_crec_area<<<2 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, CB, P);
+    k_crec_area<<<2 * L.sms, TN_NT, TN_SMEM_C, st>>>(S, CB, P);
     k_crec_area_warp<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, CB, P, L.maxv_large, L.maxx_large);
     g_launch_count += 6;
 }
@@ -1365,7 +1365,7 @@ int szk_configure(const Launch &L) {
     if (cudaFuncSetAttribute(k_ghost_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_debug_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_narrow_ab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(k_crec_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_crec_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_C) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_crec_area_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_narrow_ab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_B) != cudaSuccess) return -1;
     return 0;

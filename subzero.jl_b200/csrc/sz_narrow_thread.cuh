@@ -21,7 +21,9 @@
 #define TN_MAXX 4    // crossings per clip
 #define TN_MAXREG 2  // regions per clip
 #define TN_RCAP 24   // region points of clip #1 AND clip #2 together (they share one buffer)
-#define TN_MAXIP 6   // intersection points
+#define TN_RCAP_A 10 // phase 0 (clip #1 only): 36 double2 per thread = 72 KB per block, THREE blocks per SM; the few
+                     // regions with more points (and containment of a ring of > 9 points) go to the warp kernel
+#define TN_MAXIP 4   // intersection points = the crossing points of clip #1 (<= TN_MAXX)
 #define TN_MAXC 24   // edge pairs whose P edge straddles the Q edge's line
 
 enum { TN_OK = 0, TN_DEFER = 1 };
@@ -575,7 +577,7 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     int K1 = 0, nreg, used = 0;
     bool generic = false;
     if (PHASE == 0) {
-        nreg = t_clip<false>(Pr, Qr, w.R1, TN_RCAP, rs1, re1, status, w.ip, &K1, &generic);
+        nreg = t_clip<false>(Pr, Qr, w.R1, TN_RCAP_A, rs1, re1, status, w.ip, &K1, &generic);
         if (status != TN_OK) return TI_WARP;
         for (int r = 0; r < nreg; ++r) used = max(used, re1[r]);
         pre.nreg = nreg;
@@ -712,8 +714,9 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     return TI_DONE;
 }
 
-#define TN_SMEM_A (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))
-#define TN_SMEM_B (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))
+#define TN_SMEM_A (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP_A + TN_MAXIP))  // k_narrow_ab<0>
+#define TN_SMEM_B (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))    // k_narrow_ab<1>
+#define TN_SMEM_C (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP))               // single-clip kernels (P, Q, R)
 #define TN_NCLASS 64  // (edges of P - 3) * 8 + (edges of Q - 3), rings of 3..10 edges
 
 // ---- work-item ordering -----------------------------------------------------------------------------
@@ -813,7 +816,7 @@ __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
 #define TN_PRE_PTS (TN_RCAP + TN_MAXX)
 
 template <int PHASE>
-__global__ void __launch_bounds__(TN_NT, 2) k_narrow_ab(Store S, StepBuf B, Params P) {
+__global__ void __launch_bounds__(TN_NT, PHASE == 0 ? 3 : 2) k_narrow_ab(Store S, StepBuf B, Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(TN_NT, 2) k_narrow_ab(Store S, StepBuf B, Para
     w.R1 = w.Q + TN_MAXV * TN_NT;
     w.R2 = w.R1;
     w.r2cap = 0;
-    w.ip = w.R1 + TN_RCAP * TN_NT;
+    w.ip = w.R1 + (PHASE == 0 ? TN_RCAP_A : TN_RCAP) * TN_NT;
     const int total = PHASE == 0 ? cnt->n_order : min(cnt->n_force, B.cap_force);
     const int *list = PHASE == 0 ? B.order : B.force_items;
     const int lane = threadIdx.x & 31;

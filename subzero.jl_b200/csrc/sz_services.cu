@@ -99,7 +99,7 @@ void szk_pair_areas(const Launch &L, const Store &S, const int2 *pairs, int n, d
                     int *n_big) {
     PairQuery Q = {pairs, n, area, inter, big, n_big};
     cudaMemsetAsync(n_big, 0, sizeof(int), L.stream);
-    k_pair_area<<<2 * L.sms, TN_NT, TN_SMEM_A, L.stream>>>(S, Q);
+    k_pair_area<<<2 * L.sms, TN_NT, TN_SMEM_C, L.stream>>>(S, Q);
     k_pair_area_warp<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), L.stream>>>(S, Q, L.maxv_large, L.maxx_large);
     szk_count_launches(2);
 }
@@ -400,7 +400,7 @@ int szk_eul_run(const Launch &L, const Store &S, const SzkEulArgs &A) {
     if (A.n_rec > 0) {
         cudaMemsetAsync(A.n_big, 0, sizeof(int), st);
         k_eul_records<true><<<sv_grid(L, A.n_floes, 128), 128, 0, st>>>(S, G, B);
-        k_eul_area<<<2 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, G, B);
+        k_eul_area<<<2 * L.sms, TN_NT, TN_SMEM_C, st>>>(S, G, B);
         k_eul_area_warp<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, G, B, L.maxv_large, L.maxx_large);
         size_t bytes = A.sort_bytes;
         int bits = 32;
@@ -418,8 +418,8 @@ int szk_eul_run(const Launch &L, const Store &S, const SzkEulArgs &A) {
 
 int szk_services_configure(const Launch &L) {
     size_t lb = ws_bytes(L.maxv_large, L.maxx_large);
-    if (cudaFuncSetAttribute(k_pair_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(k_eul_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_pair_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_C) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_eul_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_C) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_pair_area_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_eul_area_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     return 0;
