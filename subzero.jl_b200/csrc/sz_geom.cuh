@@ -15,6 +15,11 @@
 #pragma once
 #include "sz_common.cuh"
 
+// keep the warp kernels small: see the instruction-cache note in sz_narrow_thread.cuh
+#ifndef SZ_ROLLED
+#define SZ_ROLLED _Pragma("unroll 1")
+#endif
+
 #define FULLMASK 0xffffffffu
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -43,12 +48,14 @@ __device__ __forceinline__ bool side_p(double o, double2 a, double2 b) {
 // Twice the signed shoelace area, canonical sequential order (every lane computes the same).
 __device__ __forceinline__ double ring_area2_seq(const double2 *r, int n) {
     double a = 0.0;
+    SZ_ROLLED
     for (int k = 0; k + 1 < n; ++k) a += r[k].x * r[k + 1].y - r[k].y * r[k + 1].x;
     return a;
 }
 __device__ __forceinline__ double ring_area_seq(const double2 *r, int n) { return fabs(ring_area2_seq(r, n) / 2.0); }
 __device__ __forceinline__ double2 ring_centroid_seq(const double2 *r, int n) {
     double a = 0.0, cx = 0.0, cy = 0.0;
+    SZ_ROLLED
     for (int k = 0; k + 1 < n; ++k) {
         double c = r[k].x * r[k + 1].y - r[k].y * r[k + 1].x;
         a += c;
@@ -61,6 +68,7 @@ __device__ __forceinline__ double2 ring_centroid_seq(const double2 *r, int n) {
 // orientation only (sign of the shoelace sum): lane-strided partial sums are enough
 __device__ __forceinline__ bool warp_ring_is_ccw(const double2 *r, int n) {
     double a = 0.0;
+    SZ_ROLLED
     for (int k = lane_id(); k + 1 < n; k += 32) a += r[k].x * r[k + 1].y - r[k].y * r[k + 1].x;
 #pragma unroll
     for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(FULLMASK, a, o);
@@ -119,6 +127,7 @@ __device__ __forceinline__ int segment_intersection(double2 a, double2 b, double
 // |GO.signed_distance(point, ring)|, collisions.jl:91
 __device__ __forceinline__ double warp_point_ring_distance(double2 p, const double2 *r, int n) {
     double best = INFINITY;
+    SZ_ROLLED
     for (int k = lane_id(); k + 1 < n; k += 32) best = fmin(best, point_segment_distance(p, r[k], r[k + 1]));
 #pragma unroll
     for (int o = 16; o; o >>= 1) best = fmin(best, __shfl_xor_sync(FULLMASK, best, o));
@@ -127,6 +136,7 @@ __device__ __forceinline__ double warp_point_ring_distance(double2 p, const doub
 // GO.coveredby(point, ring): interior or boundary, collisions.jl:99
 __device__ __forceinline__ bool warp_point_coveredby(double2 p, const double2 *r, int n) {
     bool onb = false, in = false;
+    SZ_ROLLED
     for (int k = lane_id(); k + 1 < n; k += 32) {
         double2 a = r[k], b = r[k + 1];
         if (orient2d(a, b, p) == 0.0 && p.x >= fmin(a.x, b.x) && p.x <= fmax(a.x, b.x) && p.y >= fmin(a.y, b.y) &&
@@ -144,6 +154,7 @@ __device__ __forceinline__ bool warp_point_coveredby(double2 p, const double2 *r
 // P point inside perturbed ring Q
 __device__ __forceinline__ bool warp_point_in_ring_q(double2 p, const double2 *r, int n) {
     bool in = false;
+    SZ_ROLLED
     for (int k = lane_id(); k + 1 < n; k += 32) {
         double2 c = r[k], d = r[k + 1];
         if (c.y < p.y && p.y <= d.y) {
@@ -157,6 +168,7 @@ __device__ __forceinline__ bool warp_point_in_ring_q(double2 p, const double2 *r
 // perturbed Q point inside ring P
 __device__ __forceinline__ bool warp_point_in_ring_p(double2 q, const double2 *r, int n) {
     bool in = false;
+    SZ_ROLLED
     for (int k = lane_id(); k + 1 < n; k += 32) {
         double2 a = r[k], b = r[k + 1];
         if (a.y <= q.y && q.y < b.y) {
@@ -171,6 +183,7 @@ __device__ __forceinline__ bool warp_point_in_ring_p(double2 q, const double2 *r
 __device__ __forceinline__ bool warp_rings_intersect(const double2 *A, int na, const double2 *B, int nb) {
     int ea = na - 1, eb = nb - 1, tot = ea * eb;
     bool hit = false;
+    SZ_ROLLED
     for (int idx = lane_id(); idx < tot; idx += 32) {
         int e = idx / eb, f = idx - e * eb;
         double2 p0, p1;
@@ -268,6 +281,7 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
     // 1. crossings, one edge pair per lane, compacted in (e, f) order
     int K = 0;
     const int tot = np * nq;
+    SZ_ROLLED
     for (int base = 0; base < tot; base += 32) {
         int idx = base + lane;
         bool hit = false;
@@ -326,6 +340,7 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
             status = CLIP_OVERFLOW;
             return 0;
         }
+        SZ_ROLLED
         for (int k = lane; k < ns; k += 32) R[k] = src[k];
         if (lane == 0) {
             rs[0] = 0;
@@ -336,10 +351,12 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
     }
     // 2. ranks along P (e, t, index) and along Q (f, s, index)
     int nentry = 0;
+    SZ_ROLLED
     for (int k = lane; k < K; k += 32) {
         int rp = 0, rq = 0;
         int ek = w.xe[k], fk = w.xf[k];
         double tk = w.xt[k], sk = w.xs[k];
+        SZ_ROLLED
         for (int m = 0; m < K; ++m) {
             if (m == k) continue;
             int em = w.xe[m], fm = w.xf[m];
@@ -361,6 +378,7 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
     // 3. trace (sequential, lane 0)
     if (lane == 0 && ok) {
         int npts = 0;
+        SZ_ROLLED
         for (int r = 0; ok && r < K; ++r) {
             int startk = w.ordP[r];
             if (!w.xentry[startk] || w.xvis[startk]) continue;
@@ -376,6 +394,7 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
                 R[npts++] = _p;                                                     \
         }                                                                           \
     } while (0)
+            SZ_ROLLED
             while (ok) {
                 if (w.xvis[cur]) { ok = 0; break; }
                 w.xvis[cur] = 1;
@@ -383,6 +402,7 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
                 SZ_PUSH(w.xp[cur]);
                 int rn = (w.rankP[cur] + 1) % K, nx = w.ordP[rn];
                 int cnt = w.xe[nx] - w.xe[cur] + (rn == 0 ? np : 0);
+                SZ_ROLLED
                 for (int k = 0; k < cnt && ok; ++k) SZ_PUSH(P[(w.xe[cur] + 1 + k) % np]);
                 if (!ok) break;
                 if (w.xentry[nx] || w.xvis[nx]) { ok = 0; break; }
@@ -394,11 +414,13 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
                     int rq = (w.rankQ[nx] + 1) % K;
                     nn = w.ordQ[rq];
                     cnt = w.xf[nn] - w.xf[nx] + (rq == 0 ? nq : 0);
+                    SZ_ROLLED
                     for (int k = 0; k < cnt && ok; ++k) SZ_PUSH(Q[(w.xf[nx] + 1 + k) % nq]);
                 } else {
                     int rq = (w.rankQ[nx] - 1 + K) % K;
                     nn = w.ordQ[rq];
                     cnt = w.xf[nx] - w.xf[nn] + (w.rankQ[nx] == 0 ? nq : 0);
+                    SZ_ROLLED
                     for (int k = 0; k < cnt && ok; ++k) SZ_PUSH(Q[(w.xf[nx] - k + nq) % nq]);
                 }
                 if (!ok) break;
@@ -417,6 +439,7 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
             if (nreg >= MAXREG) { ok = 0; status = CLIP_OVERFLOW; break; }
             // stable insertion by first-crossing rank
             int pos = nreg;
+            SZ_ROLLED
             while (pos > 0 && w.minrank[pos - 1] > mr) {
                 w.minrank[pos] = w.minrank[pos - 1];
                 rs[pos] = rs[pos - 1];
@@ -448,6 +471,7 @@ __device__ int warp_intersection_points(const Ws &w, const double2 *P, int npp, 
     const int lane = lane_id();
     const int np = npp - 1, nq = nqp - 1, tot = np * nq;
     int n = 0;
+    SZ_ROLLED
     for (int base = 0; base < tot; base += 32) {
         int idx = base + lane, c = 0;
         double2 p0 = make_double2(0.0, 0.0), p1 = p0;
@@ -466,14 +490,17 @@ __device__ int warp_intersection_points(const Ws &w, const double2 *P, int npp, 
         return 0;
     }
     __syncwarp();
+    SZ_ROLLED
     for (int k = lane; k < n; k += 32) {
         double2 p = w.ip[k];
         bool dup = false;
+        SZ_ROLLED
         for (int m = 0; m < k && !dup; ++m) dup = (w.ip[m].x == p.x && w.ip[m].y == p.y);
         w.ipdup[k] = dup;
     }
     __syncwarp();
     int out = 0;
+    SZ_ROLLED
     for (int base = 0; base < n; base += 32) {
         int k = base + lane;
         bool keep = k < n && !w.ipdup[k];
@@ -493,6 +520,7 @@ __device__ int warp_match_vertices(const Ws &w, int nip, const double2 *reg, int
     int npoints = nip;
     if (nip > 0 && w.ip[0].x == w.ip[nip - 1].x && w.ip[0].y == w.ip[nip - 1].y) npoints -= 1;
     int m = 0;
+    SZ_ROLLED
     for (int base = 0; base < npoints; base += 32) {
         int i = base + lane;
         bool hit = false;
@@ -500,6 +528,7 @@ __device__ int warp_match_vertices(const Ws &w, int nip, const double2 *reg, int
         if (i < npoints) {
             double2 p = w.ip[i];
             double min_dist = INFINITY;
+            SZ_ROLLED
             for (int j = 0; j < nr; ++j) {
                 double dx = reg[j].x - p.x, dy = reg[j].y - p.y;
                 double dist = sqrt(sqrt(dx * dx + dy * dy));  // sqrt(GO.distance(..)), floe_utils.jl:341
@@ -516,9 +545,11 @@ __device__ int warp_match_vertices(const Ws &w, int nip, const double2 *reg, int
     }
     __syncwarp();
     if (lane == 0) {
+        SZ_ROLLED
         for (int a = 1; a < m; ++a) {
             short v = w.ipidx[a];
             int b = a - 1;
+            SZ_ROLLED
             while (b >= 0 && w.ipidx[b] > v) {
                 w.ipidx[b + 1] = w.ipidx[b];
                 --b;
@@ -536,6 +567,7 @@ __device__ double warp_many_intersect_normal(double dir[2], const double2 *reg, 
                                              double ff) {
     double x1 = 0, y1 = 0, dl = 0, Fx = 0, Fy = 0;
     int n_pts = 0;
+    SZ_ROLLED
     for (int i = 0; i < nr; ++i) {
         double x2 = reg[i].x, y2 = reg[i].y;
         if (i == 0) {
@@ -589,6 +621,7 @@ __device__ double warp_normal_force(const Ws &w, const double2 *P, int npp, cons
         dl = warp_many_intersect_normal(dir, reg, nr, P, npp, ff);
     }
     if (dl > 0.1) {
+        SZ_ROLLED
         for (int k = lane_id(); k < npp; k += 32) w.P2[k] = make_double2(P[k].x + dir[0], P[k].y + dir[1]);
         __syncwarp();
         int st2;
@@ -598,6 +631,7 @@ __device__ double warp_normal_force(const Ws &w, const double2 *P, int npp, cons
             return 0.0;
         }
         if (st2 == CLIP_FAIL) flags |= IT_CLIPFAIL;
+        SZ_ROLLED
         for (int r = 0; r < nreg2; ++r) {
             const double2 *nr_ = w.R2 + w.rs2[r];
             int nn = w.re2[r] - w.rs2[r];
@@ -624,6 +658,7 @@ __device__ int warp_elastic_forces(const Ws &w, const double2 *P, int npp, const
     if (nip >= 2) {
         int n1 = npp - 1, n2 = nqp - 1;
         double min_area = (double)((n1 < n2 ? n1 : n2) * 100) / 1.75;
+        SZ_ROLLED
         for (int r = 0; r < nreg; ++r)
             if (!(w.area1[r] < min_area)) {
                 if (lane == 0) w.keepr[ncontact] = (short)r;
@@ -631,6 +666,7 @@ __device__ int warp_elastic_forces(const Ws &w, const double2 *P, int npp, const
             }
     }
     __syncwarp();
+    SZ_ROLLED
     for (int k = 0; k < ncontact; ++k) {
         int r = w.keepr[k];
         double ov = w.area1[r];
