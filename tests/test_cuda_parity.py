@@ -272,3 +272,43 @@ def test_full_size_properties(product_lib):
     fx = np.bincount(floe_of_row, weights=rows[:, 1], minlength=c["n_total"])
     assert rel_err(fa.collision_force[:, 0], fx) < 1e-9
     assert c["n_overlap"] > 2 * c["n_init"] and c["n_clip_fail"] == 0
+
+
+def test_full_size_periodic_shear_properties(product_lib):
+    """BASELINE config 4 scale (250k floes, periodic east/west as examples/shear_flow.jl): ghosts + image-pair filter
+    at full size through size-independent properties — every ghost is a translate of its parent by the period,
+    the filtered pair list is sorted and free of self-image pairs, floe-floe forces cancel over the parents
+    (ghost rows merged into their parents), and a full step keeps every floe's area and vertex count."""
+    n = 250000
+    f = synth.make_field(n, scale=1.01, walls="shear", npoints=20)
+    h = synth.setup_handle(f, product_lib)
+    fa0 = h.download_floes(mc=False)
+    nt = h.add_ghosts()
+    assert nt > n
+    fa = h.download_floes(mc=False)
+    g = np.arange(n, nt)
+    par = np.zeros(nt, dtype=np.int64)
+    for i in np.nonzero(np.diff(fa.ghost_offsets) > 0)[0]:
+        par[fa.ghost_index[fa.ghost_offsets[i]:fa.ghost_offsets[i + 1]] - 1] = i
+    assert np.array_equal(fa.id[g], fa.id[par[g]]) and np.all(fa.ghost_id[g] > 0)
+    assert np.allclose(np.abs(fa.centroid_x[g] - fa.centroid_x[par[g]]), f.L, rtol=0, atol=1e-6)
+    assert np.array_equal(fa.centroid_y[g], fa.centroid_y[par[g]])
+    h.step_collisions()
+    c = h.counts()
+    p = h.pairs(1)
+    assert np.all(p[:, 0] < p[:, 1]) and np.all(fa.id[p[:, 0] - 1] != fa.id[p[:, 1] - 1])
+    assert np.all(np.diff(p[:, 0] * (nt + 1) + p[:, 1]) > 0)
+    offs, rows = h.interactions()
+    own = np.repeat(np.arange(nt), np.diff(offs)) < n
+    ff = (rows[:, 0] > 0) & own
+    tot = np.abs(rows[ff, 1]).sum()
+    assert tot > 0 and abs(rows[ff, 1].sum()) <= 1e-9 * tot and abs(rows[ff, 2].sum()) <= 1e-9 * tot
+    assert c["n_clip_fail"] == 0 and c["n_overlap"] > 2 * n
+    h.remove_ghosts()
+    h.step_coupling()
+    h.step_floe_properties(0)
+    fb = h.download_floes(mc=False)
+    assert fb.n == n and np.array_equal(fb.vert_offsets, fa0.vert_offsets) and np.array_equal(fb.area, fa0.area)
+    assert np.all(np.isfinite(fb.u)) and np.all(np.isfinite(fb.vert_xy))
+    # the parents stay inside the periodic extent (add_ghosts! wraps them, collisions.jl:943-949)
+    assert fb.centroid_x.min() >= -1.0 and fb.centroid_x.max() <= f.L + 1.0
