@@ -58,7 +58,8 @@ struct CpReg {
 // |v| for the quadratic drag laws: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps on the
 // reciprocal root (relative error ~1e-16 before the final multiply) instead of the IEEE-rounded sqrt() expansion with
 // its slow-path call: ncu r1k had the two sqrt() of a point at 23 % of the kernel's instructions.  The parity bar of
-// this kernel is 1e-9 relative (sz_kernels_fp.cu header); measured agreement with the oracle stays ~1e-15.
+// this kernel is 1e-9 relative (sz_kernels_fp.cu header); measured agreement with the oracle stays ~1e-15.  (One
+// Newton step, ~1e-13, would also do; the second costs 3 of ~75 FP64 instructions per point and keeps the margin.)
 __device__ __forceinline__ double cp_norm(double s) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
