@@ -1123,7 +1123,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_class_scan<<<1, 32, 0, st>>>(S, B);
     k_item_scatter<<<gi, 256, 0, st>>>(S, B);
     k_narrow_ab<0><<<3 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, B, P);
-    k_narrow_ab<1><<<2 * L.sms, TN_NT, TN_SMEM_B, st>>>(S, B, P);
+    k_narrow_ab<1><<<3 * L.sms, TN_NT, TN_SMEM_B, st>>>(S, B, P);
     k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
     k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
     k_pool_check<<<1, 1, 0, st>>>(S, B);

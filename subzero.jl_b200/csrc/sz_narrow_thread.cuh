@@ -470,21 +470,21 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
 
 struct TWs {
     double2 *P, *Q, *R1, *R2, *ip;  // [cap][TN_NT], already offset by the thread index
+    int rcap;                       // rows of the region buffer (clip #1 and clip #2 share it)
     int r2cap;                      // R2 = the part of the region buffer clip #1 left free
 };
 
 // calc_normal_force, collisions.jl:30-70
+// (m, i0, i1, rare): the result of t_match_vertices for this region — evaluated for ALL regions before the first
+// second clip, because in k_narrow_ab<1> the crossing points share their rows with the regions of clip #2
 __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q, const TRing reg,
-                                              double area, int nip, double ff, double force[2], int &status) {
+                                              double area, int m, int i0, int i1, bool rare, double ff, double force[2], int &status) {
     double dir[2] = {0.0, 0.0}, dl = 0.0;
-    int idx[TN_MAXIP];
-    bool rare = false;
-    int m = t_match_vertices(w.ip, nip, reg, idx, rare);
     // m not in {0, 2}: _many_intersect_normal_force! (collisions.jl:78-119) — rare, like a near-tie above: the item
     // goes to the warp kernel (no early return: a divergent return only reconverges at the function exit)
     bool defer = rare || (m != 2 && m != 0);
     if (m == 2 && !defer) {
-        double2 v0 = tget(reg, idx[0]), v1 = tget(reg, idx[1]);
+        double2 v0 = tget(reg, i0), v1 = tget(reg, i1);
         double dx = v1.x - v0.x, dy = v1.y - v0.y;
         dl = sqrt(dx * dx + dy * dy);
         if (dl > 0.1) {
@@ -524,7 +524,7 @@ enum { TI_DONE = 0, TI_WARP = 1, TI_FORCES = 2 };
 // what phase 0 hands to phase 1 (through global memory, SoA over the force list): the regions of clip #1,
 // the crossing points and whether they are GO.intersection_points
 struct TPre {
-    int nreg, rs[TN_MAXREG], re[TN_MAXREG], K1, used;
+    int nreg, rs[TN_MAXREG], re[TN_MAXREG], K1, used, np, nq;
     bool generic;
 };
 template <int PHASE>
@@ -581,6 +581,8 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
         if (status != TN_OK) return TI_WARP;
         for (int r = 0; r < nreg; ++r) used = max(used, re1[r]);
         pre.nreg = nreg;
+        pre.np = npp;
+        pre.nq = nqp;
         pre.K1 = K1;
         pre.generic = generic;
         pre.used = used;
@@ -599,7 +601,7 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
         }
     }
     w.R2 = w.R1 + used * TN_NT;
-    w.r2cap = TN_RCAP - used;
+    w.r2cap = w.rcap - used;
     double total = 0.0, max_area = 0.0;
     for (int r = 0; r < nreg; ++r) {
         area1[r] = t_area(tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]));
@@ -656,7 +658,22 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
             int n1 = npp - 1, n2 = nqp - 1;
             double min_area = (double)((n1 < n2 ? n1 : n2) * 100) / 1.75;
             const double iu = S.u[fi], iv = S.v[fi], ixi = S.xi[fi], icx = S.cx[fi], icy = S.cy[fi];
-                for (int r = 0; r < nreg; ++r) {
+            // which_vertices_match_points for every region first (the crossing points are dead afterwards)
+            int mm[TN_MAXREG], mi0[TN_MAXREG], mi1[TN_MAXREG];
+            bool rare = false;
+#pragma unroll
+            for (int r = 0; r < TN_MAXREG; ++r) {
+                mm[r] = mi0[r] = mi1[r] = 0;
+                if (r < nreg && !(area1[r] < min_area) && area1[r] != 0) {
+                    int idx[TN_MAXIP];
+                    mm[r] = t_match_vertices(w.ip, nip, tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]), idx, rare);
+                    mi0[r] = idx[0];
+                    mi1[r] = idx[1];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < TN_MAXREG; ++r) {
+                if (r >= nreg) continue;
                 if (area1[r] < min_area) continue;
                 double c[6] = {0.0, 0.0, 0.0, 0.0, area1[r], 0.0};
                 if (area1[r] != 0) {
@@ -665,7 +682,7 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
                     c[2] = ce.x;
                     c[3] = ce.y;
                     double force[2];
-                    c[5] = t_normal_force(w, Pr, Qr, reg, area1[r], nip, ff, force, status);
+                    c[5] = t_normal_force(w, Pr, Qr, reg, area1[r], mm[r], mi0[r], mi1[r], rare, ff, force, status);
                     if (status != TN_OK) return TI_WARP;
                     c[0] = force[0];
                     c[1] = force[1];
@@ -715,7 +732,8 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
 }
 
 #define TN_SMEM_A (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP_A + TN_MAXIP))  // k_narrow_ab<0>
-#define TN_SMEM_B (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP + TN_MAXIP))    // k_narrow_ab<1>
+#define TN_ROWS_B 36  // rows per thread of k_narrow_ab<1>: three blocks per SM, split per warp (see the kernel)
+#define TN_SMEM_B (sizeof(double2) * TN_NT * TN_ROWS_B)                             // k_narrow_ab<1>
 #define TN_SMEM_C (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP))               // single-clip kernels (P, Q, R)
 #define TN_NCLASS 64  // (edges of P - 3) * 8 + (edges of Q - 3), rings of 3..10 edges
 
@@ -816,7 +834,7 @@ __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
 #define TN_PRE_PTS (TN_RCAP + TN_MAXX)
 
 template <int PHASE>
-__global__ void __launch_bounds__(TN_NT, PHASE == 0 ? 3 : 2) k_narrow_ab(Store S, StepBuf B, Params P) {
+__global__ void __launch_bounds__(TN_NT, 3) k_narrow_ab(Store S, StepBuf B, Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -826,8 +844,14 @@ __global__ void __launch_bounds__(TN_NT, PHASE == 0 ? 3 : 2) k_narrow_ab(Store S
     w.Q = w.P + TN_MAXV * TN_NT;
     w.R1 = w.Q + TN_MAXV * TN_NT;
     w.R2 = w.R1;
+    w.rcap = TN_RCAP_A;
     w.r2cap = 0;
-    w.ip = w.R1 + (PHASE == 0 ? TN_RCAP_A : TN_RCAP) * TN_NT;
+    w.ip = w.R1 + TN_RCAP_A * TN_NT;
+    // phase 1 needs P, Q, the regions of clip #1 AND of clip #2: with worst-case capacities (11 + 11 + 24 + 4 rows)
+    // only two blocks fit on an SM.  The items are sorted by ring size, so every WARP lays out its 32 columns of the
+    // 36 rows for the largest rings among its own items: P | Q | regions (what is left: 22 rows for two hexagons).  The
+    // 4 crossing points sit in the last region rows; they are consumed (which_vertices_match_points of every region)
+    // before the first second clip may write there.  A second clip that does not fit goes to the warp kernel.
     const int total = PHASE == 0 ? cnt->n_order : min(cnt->n_force, B.cap_force);
     const int *list = PHASE == 0 ? B.order : B.force_items;
     const int lane = threadIdx.x & 31;
@@ -843,9 +867,28 @@ __global__ void __launch_bounds__(TN_NT, PHASE == 0 ? 3 : 2) k_narrow_ab(Store S
                 pre.nreg = m.x & 0xff;
                 pre.generic = (m.x >> 8) & 1;
                 pre.K1 = (m.x >> 16) & 0xff;
-                pre.used = m.w;
+                pre.used = m.w & 0xff;
+                pre.np = (m.w >> 8) & 0xff;
+                pre.nq = (m.w >> 16) & 0xff;
                 pre.rs[0] = m.y & 0xffff; pre.re[0] = m.y >> 16;
                 pre.rs[1] = m.z & 0xffff; pre.re[1] = m.z >> 16;
+            }
+        }
+        if (PHASE == 1) {
+            int npm = it < total ? pre.np : 0, nqm = it < total ? pre.nq : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                npm = max(npm, __shfl_xor_sync(0xffffffffu, npm, o));
+                nqm = max(nqm, __shfl_xor_sync(0xffffffffu, nqm, o));
+            }
+            w.Q = w.P + npm * TN_NT;
+            w.R1 = w.Q + nqm * TN_NT;
+            w.R2 = w.R1;
+            w.rcap = TN_ROWS_B - npm - nqm;  // >= TN_RCAP_A + TN_MAXIP: clip #1's regions and the crossing points always fit
+            w.ip = w.P + (TN_ROWS_B - TN_MAXIP) * TN_NT;  // the last rows of the region buffer: read before clip #2 writes there
+        }
+        if (it < total) {
+            if (PHASE == 1) {
                 for (int k = 0; k < pre.used; ++k) w.R1[k * TN_NT] = B.force_pts[k * cf + it];
                 for (int k = 0; k < pre.K1; ++k) w.ip[k * TN_NT] = B.force_pts[(TN_RCAP + k) * cf + it];
             }
@@ -868,7 +911,7 @@ __global__ void __launch_bounds__(TN_NT, PHASE == 0 ? 3 : 2) k_narrow_ab(Store S
                     if (b < B.cap_force) {
                         B.force_items[b] = slot;
                         B.force_meta[b] = make_int4(pre.nreg | ((int)pre.generic << 8) | (pre.K1 << 16), pre.rs[0] | (pre.re[0] << 16),
-                                                    pre.rs[1] | (pre.re[1] << 16), pre.used);
+                                                    pre.rs[1] | (pre.re[1] << 16), pre.used | (pre.np << 8) | (pre.nq << 16));
                         for (int k = 0; k < pre.used; ++k) B.force_pts[k * cf + b] = w.R1[k * TN_NT];
                         for (int k = 0; k < pre.K1; ++k) B.force_pts[(TN_RCAP + k) * cf + b] = w.ip[k * TN_NT];
                     } else {
