@@ -55,17 +55,14 @@ struct CpReg {
     double tox, toy; // ocean stress on the ice at the point
 };
 
-// |v| for the quadratic drag laws: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps on the
-// reciprocal root (relative error ~1e-16 before the final multiply) instead of the IEEE-rounded sqrt() expansion with
-// its slow-path call: ncu r1k had the two sqrt() of a point at 23 % of the kernel's instructions.  The parity bar of
-// this kernel is 1e-9 relative (sz_kernels_fp.cu header); measured agreement with the oracle stays ~1e-15.  (One
-// Newton step, ~1e-13, would also do; the second costs 3 of ~75 FP64 instructions per point and keeps the margin.)
+// |v| for the quadratic drag laws: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, relative error ~2^-22) + ONE Newton step
+// on the reciprocal root (-> ~1e-13) instead of the IEEE-rounded sqrt() expansion with its slow-path call: ncu r1k had
+// the two sqrt() of a point at 23 % of the kernel's instructions, and the kernel is bound by the FP64 pipe.  The
+// parity bar of this kernel is 1e-9 relative (sz_kernels_fp.cu header); the tests see ~1e-13.
 __device__ __forceinline__ double cp_norm(double s) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
-    const double hs = 0.5 * s;
-    r = r * (1.5 - hs * r * r);
-    r = r * (1.5 - hs * r * r);
+    r = r * (1.5 - (0.5 * s) * r * r);
     return s > 0.0 ? s * r : 0.0;
 }
 
@@ -126,21 +123,24 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     const double2 *n10 = (const double2 *)(F + (size_t)(i1 + s * j0) * 8);
     const double2 *n01 = (const double2 *)(F + (size_t)(i0 + s * j1) * 8);
     const double2 *n11 = (const double2 *)(F + (size_t)(i1 + s * j1) * 8);
-    double w00 = (1 - wx) * (1 - wy), w10 = wx * (1 - wy), w01 = (1 - wx) * wy, w11 = wx * wy;
+    // bilinear as three lerps per field (6 FP64 instructions instead of 4 + the four shared weights)
+#define CP_LERP2(f00, f10, f01, f11) \
+    ((f00 + wx * (f10 - f00)) + wy * ((f01 + wx * (f11 - f01)) - (f00 + wx * (f10 - f00))))
     double2 o00 = __ldg(n00 + 1), o10 = __ldg(n10 + 1), o01 = __ldg(n01 + 1), o11 = __ldg(n11 + 1);  // ocn u, v
     double uatm = 0.0, vatm = 0.0, hfl = 0.0;
     if (ATM) {
         double2 a00 = __ldg(n00), a10 = __ldg(n10), a01 = __ldg(n01), a11 = __ldg(n11);  // atm u, v
-        uatm = w00 * a00.x + w10 * a10.x + w01 * a01.x + w11 * a11.x;
-        vatm = w00 * a00.y + w10 * a10.y + w01 * a01.y + w11 * a11.y;
+        uatm = CP_LERP2(a00.x, a10.x, a01.x, a11.x);
+        vatm = CP_LERP2(a00.y, a10.y, a01.y, a11.y);
     }
     if (HFLX) {
         double h00 = __ldg((const double *)(n00 + 2)), h10 = __ldg((const double *)(n10 + 2)),
                h01 = __ldg((const double *)(n01 + 2)), h11 = __ldg((const double *)(n11 + 2));
-        hfl = w00 * h00 + w10 * h10 + w01 * h01 + w11 * h11;
+        hfl = CP_LERP2(h00, h10, h01, h11);
     }
-    double uocn = w00 * o00.x + w10 * o10.x + w01 * o01.x + w11 * o11.x;
-    double vocn = w00 * o00.y + w10 * o10.y + w01 * o01.y + w11 * o11.y;
+    double uocn = CP_LERP2(o00.x, o10.x, o01.x, o11.x);
+    double vocn = CP_LERP2(o00.y, o10.y, o01.y, o11.y);
+#undef CP_LERP2
     double dua = uatm - up, dva = vatm - vp;  // calc_atmosphere_forcing, coupling.jl:1212-1232
     double na = cp_norm(dua * dua + dva * dva);
     double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
