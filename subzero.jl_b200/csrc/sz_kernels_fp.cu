@@ -3,6 +3,8 @@
 // These two kernels carry no discrete geometric decision that must match the reference bit for
 // bit: their parity bar is 1e-9 relative (BASELINE.json north_star).  They are therefore compiled
 // with FMA contraction ON (unlike sz_kernels.cu) and use algebraic identities the tolerance covers.
+#include <cuda_pipeline.h>
+
 #include "sz_common.cuh"
 
 #define FULLMASK 0xffffffffu
@@ -173,10 +175,30 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
     const double *__restrict__ F = S.fields8;
     const int n = S.n_init;
-    for (int i = blockIdx.x * wpb + wib; i < n; i += gridDim.x * wpb) {
+    // The Monte-Carlo points stream through a two-stage shared-memory ring filled with cp.async (LDGSTS, 16 B per lane):
+    // the loads of the next 128 points — of this floe or, behind its last chunk, of the warp's NEXT floe — are in
+    // flight while the current 128 are integrated.  ncu r1m: with four plain loads per lane issued and then consumed,
+    // 46 % of the stall samples sat on the first use of a loaded point (2.1 TB/s).  Every lane reads back what it
+    // copied itself, so no barrier is needed.
+    __shared__ double2 sbuf[2][4][128];  // [stage][load][thread]: 16 KB per block
+    const int tid = threadIdx.x, stride = gridDim.x * wpb;
+    int stage = 0;
+    bool have = false;  // chunk 0 of the current floe is already in flight in `stage`
+    int i = blockIdx.x * wpb + wib;
+    long long m0 = 0, m1 = 0;
+    if (i < n) {
+        m0 = S.mc_off[i];
+        m1 = S.mc_off[i + 1];
+    }
+    for (; i < n; i += stride) {
         const double a = S.alpha[i], cx = S.cx[i], cy = S.cy[i], u = S.u[i], v = S.v[i], xi = S.xi[i];
         const double ar = S.area[i], mass = S.mass[i];
-        const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
+        const int inext = i + stride;
+        long long m0n = 0, m1n = 0;
+        if (inext < n) {
+            m0n = S.mc_off[inext];
+            m1n = S.mc_off[inext + 1];
+        }
         double sa, ca;
         sincos(a, &sa, &ca);
         const double mf = mass / ar * c.f;
@@ -185,19 +207,48 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
         // Monte-Carlo points lie inside the ring, i.e. within rmax of the centroid (a small margin covers rounding)
         const double rm = S.rmax[i] * (1.0 + 1e-9) + 1e-6;
         const bool interior = cx - rm > c.x0 && cx + rm < c.xf && cy - rm > c.y0 && cy + rm < c.yf;
-        if (interior) {
-            for (; k + 96 < m1; k += 128) {  // four independent 512-byte loads per warp in flight (HBM latency)
-                double2 b0 = __ldcs(S.mc + k), b1 = __ldcs(S.mc + k + 32), b2 = __ldcs(S.mc + k + 64), b3 = __ldcs(S.mc + k + 96);
-                cp_point<false, ATM, HFLX, true>(c, F, b0, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-                cp_point<false, ATM, HFLX, true>(c, F, b1, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-                cp_point<false, ATM, HFLX, true>(c, F, b2, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-                cp_point<false, ATM, HFLX, true>(c, F, b3, ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-            }
-            for (; k < m1; k += 32) cp_point<false, ATM, HFLX, true>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
-        } else {  // floes at the edge of the grid (about 1 % of a large field): the general path, not unrolled
-#pragma unroll 1
-            for (; k < m1; k += 32) cp_point<false, ATM, HFLX, false>(c, F, __ldcs(S.mc + k), ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+        const int nchunk = (int)((m1 - m0 + 127) >> 7);
+        if (!have && nchunk > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + 32 * j < m1) __pipeline_memcpy_async(&sbuf[stage][j][tid], S.mc + k + 32 * j, sizeof(double2));
+            __pipeline_commit();
         }
+        have = false;
+        for (int cch = 0; cch < nchunk; ++cch, k += 128) {
+            const int nxt = stage ^ 1;
+            if (cch + 1 < nchunk) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k + 128 + 32 * j < m1) __pipeline_memcpy_async(&sbuf[nxt][j][tid], S.mc + k + 128 + 32 * j, sizeof(double2));
+            } else if (m1n > m0n) {  // behind the last chunk: the first chunk of the warp's next floe
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (m0n + lane + 32 * j < m1n) __pipeline_memcpy_async(&sbuf[nxt][j][tid], S.mc + m0n + lane + 32 * j, sizeof(double2));
+                have = true;
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(1);
+            if (interior && k + 96 < m1) {
+                cp_point<false, ATM, HFLX, true>(c, F, sbuf[stage][0][tid], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, sbuf[stage][1][tid], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, sbuf[stage][2][tid], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, sbuf[stage][3][tid], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            } else if (interior) {
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j)
+                    if (k + 32 * j < m1)
+                        cp_point<false, ATM, HFLX, true>(c, F, sbuf[stage][j][tid], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            } else {  // floes at the edge of the grid (about 1 % of a large field): the general path, not unrolled
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j)
+                    if (k + 32 * j < m1)
+                        cp_point<false, ATM, HFLX, false>(c, F, sbuf[stage][j][tid], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            }
+            stage = nxt;
+        }
+        m0 = m0n;
+        m1 = m1n;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             acc.tx += __shfl_xor_sync(FULLMASK, acc.tx, o);
@@ -220,6 +271,7 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
             }
         }
     }
+    __pipeline_wait_prior(0);
 }
 
 // The same integration plus the floe -> cell registry (grid.floe_locations / ocean.scells): the points of a
