@@ -337,11 +337,11 @@ def main():
     except Exception:
         pass
     notes = {"k_narrow": "narrow phase = k_item_count/scatter + k_narrow_ab<0> (clip, decisions) + k_narrow_ab<1> (forces) + k_narrow "
-                         "(rings > 10 edges): FP64 latency bound, not bandwidth bound (ncu r1j: <1 % of DRAM peak, 16-18 % issue "
-                         "slots, 20 of 32 lanes active); the HBM fraction is reported because the contract asks for it, the lever "
-                         "is lane efficiency and occupancy (profiles/README.md)",
-             "k_coupling": "streams 16 B per Monte-Carlo point once (ncu: 956 MB read = the algorithmic bytes); FP64 pipe 52 % busy; "
-                           "inside sz_step it runs on a second stream beside the collision kernels",
+                         "(warp kernel: large rings and every rare path): FP64 latency bound, not bandwidth bound (ncu r1m: 4 % of DRAM "
+                         "peak, 25 % issue slots, 12 warps per SM, 23 of 32 lanes active); the HBM fraction is reported because the "
+                         "contract asks for it, roofline.fp64 gives the FP64 view (profiles/README.md)",
+             "k_coupling": "streams 16 B per Monte-Carlo point once (ncu: 962 MB = the algorithmic bytes) through a cp.async ring; FP64 pipe "
+                           "54 % busy; inside sz_step it runs on a second stream beside the broad phase",
              "k_update": ""}
     roofline = {"kernel": dom if dom != "k_narrow" else "k_narrow_ab", "bound": "hbm", "achieved": achieved, "peak": hbm,
                 "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "note": notes[dom],
