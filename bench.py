@@ -288,8 +288,10 @@ def main():
         d2h = h2d + host_fa.id.nbytes + host_fa.ghost_id.nbytes
         sep = time_e2e(False)
         if world == 1:
-            # sz_step_host does not upload collision_force / collision_trq (zeroed by the step before any read)
-            h2d_fused = h2d - host_fa.collision_force.nbytes - host_fa.collision_trq.nbytes
+            # sz_step_host does not upload what the step overwrites before any read: collision_force / collision_trq
+            # (zeroed by timestep_collisions!) and, on a step that runs the coupling, fxOA / fyOA / trqOA / hflx_factor
+            h2d_fused = (h2d - host_fa.collision_force.nbytes - host_fa.collision_trq.nbytes - host_fa.fxOA.nbytes
+                         - host_fa.fyOA.nbytes - host_fa.trqOA.nbytes - host_fa.hflx_factor.nbytes)
             e2e = {"value": time_e2e(True), "unit": "steps/s", "h2d_bytes_per_step": int(h2d_fused), "d2h_bytes_per_step": int(d2h),
                    "call": "sz_step_host on pinned host arrays (upload of every per-floe input scalar + rings, step, download "
                            "of the whole state; copies overlap the kernels)",

@@ -197,7 +197,9 @@ int32_t SZ_FN(step)(sz_handle *h, int64_t tstep, int32_t do_coupling);
  * first use (centroids and radii first, then rings, ...) and every kernel waits only for the arrays it reads;
  * results are copied back as soon as the kernel producing them is done.  `in` and `out` may alias (in-place
  * update of the host arrays); pinned host memory is needed for the overlap, pageable memory works but
- * serialises.  Monte-Carlo points and ghost lists are not transferred (mc_x / mc_y / ghost_index untouched). */
+ * serialises.  Monte-Carlo points and ghost lists are not transferred (mc_x / mc_y / ghost_index untouched), nor
+ * are the fields the step overwrites before reading them: collision_force / collision_trq (collisions.jl:747-749)
+ * and, when do_coupling != 0, fxOA / fyOA / trqOA / hflx_factor (coupling.jl:1583-1586). */
 int32_t SZ_FN(step_host)(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in,
                          sz_floe_soa *out);
 

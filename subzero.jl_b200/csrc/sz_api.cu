@@ -983,14 +983,15 @@ extern "C" int32_t sz_step_floe_properties(sz_handle *h, int64_t tstep) {
 // ---- sz_step / sz_step_host ----------------------------------------------------------------------------
 // Host buffers of one sz_step_host call.  The uploads are enqueued on stream_up in the order the kernels first
 // need them and signal four events; the kernels wait for the group they read (or overwrite):
-//   group 0  alpha, centroid, u, v, xi, area, mass, fxOA, fyOA, trqOA, hflx_factor  -> coupling.  First, because the
+//   group 0  alpha, centroid, u, v, xi, area, mass  -> coupling.  First, because the
 //            coupling kernel is forked at once: it must run beside the (cheap) broad phase, not beside the
 //            latency-bound narrow phase, where the two slow each other down by more than the overlap gains
 //   group 1  rmax, status                                                            -> broad phase
 //   group 2  ring coordinates, height                                                -> narrow phase
 //   group 3  moment, overarea, the AB2 history, stress / strain tensors               -> row assembly, update
 // collision_force / collision_trq are NOT uploaded: timestep_collisions! zeroes them before anything reads them
-// (collisions.jl:747-749, k_step_reset), they are outputs of every step.
+// (collisions.jl:747-749, k_step_reset), they are outputs of every step.  fxOA, fyOA, trqOA, hflx_factor are outputs of
+// a step that runs the coupling (coupling.jl:1583-1586) and are uploaded (group 3) only when it does not.
 // The downloads go to stream_dn as soon as the producing kernel is done (collision totals after the row
 // assembly, coupling outputs after the join, the rest after the update).
 struct HostIO {
@@ -998,7 +999,7 @@ struct HostIO {
     sz_floe_soa *out;
 };
 
-static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s) {
+static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s, bool coupling_runs) {
     Store &S = h->S;
     const int n = h->n_total;
     cudaStream_t st = h->stream_up;
@@ -1010,7 +1011,6 @@ static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s) {
     // group 0
     CK(up(S.alpha, s->alpha, 1)); CK(up(S.cx, s->centroid_x, 1)); CK(up(S.cy, s->centroid_y, 1)); CK(up(S.u, s->u, 1));
     CK(up(S.v, s->v, 1)); CK(up(S.xi, s->xi, 1)); CK(up(S.area, s->area, 1)); CK(up(S.mass, s->mass, 1));
-    CK(up(S.fxOA, s->fxOA, 1)); CK(up(S.fyOA, s->fyOA, 1)); CK(up(S.trqOA, s->trqOA, 1)); CK(up(S.hflx, s->hflx_factor, 1));
     CK(cudaEventRecord(h->ev_up[0], st));
     // group 1
     CK(up(S.rmax, s->rmax, 1));
@@ -1021,6 +1021,9 @@ static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s) {
     CK(up(S.height, s->height, 1));
     CK(cudaEventRecord(h->ev_up[2], st));
     // group 3
+    if (!coupling_runs) {  // held between coupling steps (simulation.jl:151-154): inputs of the state update
+        CK(up(S.fxOA, s->fxOA, 1)); CK(up(S.fyOA, s->fyOA, 1)); CK(up(S.trqOA, s->trqOA, 1)); CK(up(S.hflx, s->hflx_factor, 1));
+    }
     CK(up(S.moment, s->moment, 1)); CK(up(S.overarea, s->overarea, 1));
     CK(up(S.p_dxdt, s->p_dxdt, 1)); CK(up(S.p_dydt, s->p_dydt, 1)); CK(up(S.p_dudt, s->p_dudt, 1));
     CK(up(S.p_dvdt, s->p_dvdt, 1)); CK(up(S.p_dxidt, s->p_dxidt, 1)); CK(up(S.p_dalphadt, s->p_dalphadt, 1));
@@ -1068,7 +1071,7 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
     cudaStream_t st = h->L.stream;
     const bool periodic = h->hD.kind[2] == SZ_BOUNDARY_PERIODIC || h->hD.kind[0] == SZ_BOUNDARY_PERIODIC;
     if (io) {
-        int32_t rc = enqueue_uploads(h, io->in);
+        int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
         if (rc) return rc;
     }
     for (int attempt = 0;; ++attempt) {
