@@ -171,7 +171,7 @@ static int32_t grow_floes(sz_handle *h, int new_cap, int keep) {
     CK(dalloc(&h->B.cell_count, (size_t)cells + 2));
     CK(dalloc(&h->B.cell_start, (size_t)cells + 2));
     CK(dalloc(&h->B.cell_fill, (size_t)cells + 2));
-    CK(dalloc(&h->B.scan_block, (size_t)cells / 4096 + 8));
+    CK(dalloc(&h->B.scan_block, (size_t)cells / 4096 + 64));  // also holds three floe-length scans side by side (scan_excl3)
     h->B.cap_cells = cells;
     return SZ_OK;
 }

@@ -146,6 +146,77 @@ static void scan_excl(const Launch &L, const Store &S, const int *in, int *out, 
     g_launch_count += 3;
 }
 
+// three scans of equal length in one set of launches (blockIdx.y selects the array): the neighbour counts of the
+// broad phase (own pairs, mirrored pairs, domain items) — 3 launches instead of 9 on the critical chain of small kernels
+struct Scan3 {
+    const int *in[3];
+    int *out[3];
+    int *total_out[3];
+};
+__global__ void __launch_bounds__(SCAN_T) k_scan3_tiles(Scan3 a, const int *len_ptr, int len_add, int *block_sums, int stride,
+                                                        const Counters *cnt) {
+    if (cnt->error) return;
+    const int y = blockIdx.y, len = *len_ptr + len_add, base = blockIdx.x * SCAN_TILE;
+    if (base >= len) return;
+    const int *in = a.in[y];
+    int *out = a.out[y];
+    int v[SCAN_ITEMS], s = 0;
+    const int i0 = base + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (i0 + k < len) ? in[i0 + k] : 0;
+        s += v[k];
+    }
+    int tot;
+    int pre = block_excl_scan_512(s, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (i0 + k < len) out[i0 + k] = pre;
+        pre += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[y * stride + blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan3_sums(int *block_sums, int stride, const int *len_ptr, int len_add, const Counters *cnt) {
+    if (cnt->error) return;
+    int *bs = block_sums + blockIdx.x * stride;
+    const int len = *len_ptr + len_add, ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+    int carry = 0;
+    for (int base = 0; base < ntiles; base += SCAN_T) {
+        int i = base + threadIdx.x;
+        int v = i < ntiles ? bs[i] : 0;
+        int tot;
+        int pre = block_excl_scan_512(v, &tot);
+        if (i < ntiles) bs[i] = carry + pre;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) bs[ntiles] = carry;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan3_add(Scan3 a, const int *len_ptr, int len_add, const int *block_sums, int stride,
+                                                      const Counters *cnt) {
+    if (cnt->error) return;
+    const int y = blockIdx.y, len = *len_ptr + len_add, ntiles = (len + SCAN_TILE - 1) / SCAN_TILE, base = blockIdx.x * SCAN_TILE;
+    const int *bs = block_sums + y * stride;
+    int *out = a.out[y];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[len] = bs[ntiles];
+        if (a.total_out[y]) *a.total_out[y] = bs[ntiles];
+    }
+    if (base >= len) return;
+    const int off = bs[blockIdx.x], i0 = base + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (i0 + k < len) out[i0 + k] += off;
+}
+static void scan_excl3(const Launch &L, const Store &S, const Scan3 &a, const int *len_ptr, int len_add, int max_len, int *scratch) {
+    int tiles = sz_div_up((long long)max_len, SCAN_TILE);
+    if (tiles < 1) tiles = 1;
+    const int stride = tiles + 2;
+    k_scan3_tiles<<<dim3(tiles, 3), SCAN_T, 0, L.stream>>>(a, len_ptr, len_add, scratch, stride, S.cnt);
+    k_scan3_sums<<<3, SCAN_T, 0, L.stream>>>(scratch, stride, len_ptr, len_add, S.cnt);
+    k_scan3_add<<<dim3(tiles, 3), SCAN_T, 0, L.stream>>>(a, len_ptr, len_add, scratch, stride, S.cnt);
+    g_launch_count += 3;
+}
+
 static inline int grid_for(const Launch &L, long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
     long long cap = (long long)L.sms * 32;
@@ -681,7 +752,7 @@ __global__ void k_low_link(Store S, StepBuf B) {
 __global__ void k_filter(Store S, StepBuf B) {
     Counters *cnt = S.cnt;
     if (cnt->error) return;
-    int np = cnt->n_cand;
+    int np = cnt->n_cand, nkept = 0;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
         int i = B.pair_i[p], j = B.pair_j[p];
         long long idi = S.id[i], idj = S.id[j];
@@ -711,7 +782,12 @@ __global__ void k_filter(Store S, StepBuf B) {
             }
         }
         B.keep[p] = keep;
+        nkept += keep;
     }
+    // n_kept (a diagnostic count): one atomic per warp (the loop above is not warp-uniform in its trip count)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nkept += __shfl_xor_sync(FULLMASK, nkept, o);
+    if (lane_id() == 0 && nkept) atomicAdd(&cnt->n_kept, nkept);
 }
 
 // ---- K3/K4: narrow phase -------------------------------------------------------------------------------------
@@ -1082,16 +1158,6 @@ __global__ void k_update_boundaries(Store S, Params P) {
     }
 }
 
-__global__ void k_kept_count(Store S, StepBuf B) {
-    Counters *cnt = S.cnt;
-    if (cnt->error) return;
-    int np = cnt->n_cand, c = 0;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) c += B.keep[p];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULLMASK, c, o);
-    if (lane_id() == 0 && c) atomicAdd(&cnt->n_kept, c);
-}
-
 void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_hint, int pairs_hint,
                     cudaEvent_t *ev, const cudaEvent_t *waits) {
     cudaStream_t st = L.stream;
@@ -1104,15 +1170,15 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     scan_excl(L, S, B.cell_count, B.cell_start, &S.cnt->n_cells, 0, B.cap_cells, B.scan_block, nullptr);
     k_cell_fill<<<gf, TPB, 0, st>>>(S, B);
     k_neighbours<false><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
-    scan_excl(L, S, B.up_count, B.up_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, &S.cnt->n_cand);
-    scan_excl(L, S, B.low_count, B.low_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, nullptr);
-    scan_excl(L, S, B.dom_count, B.dom_off, &S.cnt->n_total, 0, S.cap_floes, B.scan_block, &S.cnt->n_dom);
+    {
+        Scan3 a = {{B.up_count, B.low_count, B.dom_count}, {B.up_off, B.low_off, B.dom_off}, {&S.cnt->n_cand, nullptr, &S.cnt->n_dom}};
+        scan_excl3(L, S, a, &S.cnt->n_total, 0, S.cap_floes, B.scan_block);
+    }
     k_pair_check<<<1, 1, 0, st>>>(S, B);
     k_neighbours<true><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
     k_low_link<<<gf, TPB, 0, st>>>(S, B);
     int gp = grid_for(L, pairs_hint, TPB);
     k_filter<<<gp, TPB, 0, st>>>(S, B);
-    k_kept_count<<<gp, TPB, 0, st>>>(S, B);
     if (ev) cudaEventRecord(ev[0], st);
     if (waits) cudaStreamWaitEvent(st, waits[0], 0);  // sz_step_host: rings and height have landed
     const int maxv_s = 32, maxx_s = 16, wpb = 4;
@@ -1138,7 +1204,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_row_write<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
     k_update_boundaries<<<1, 1, 0, st>>>(S, P);
     if (ev) cudaEventRecord(ev[2], st);
-    g_launch_count += 27;  // + 5 scans counted in scan_excl
+    g_launch_count += 26;  // + the scans counted in scan_excl / scan_excl3
 }
 
 // ---- two-way coupling: sort the registry by (cell, floe), floe ∩ cell-box areas ------------------------------
