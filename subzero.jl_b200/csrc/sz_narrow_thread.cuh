@@ -191,10 +191,16 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     if (np < 3 || nq < 3) return 0;
     const bool q_ccw = t_area2(Q) > 0.0;
     const bool same = (SHIFT ? t_area2s(P) : t_area2(P)) > 0.0 == q_ccw;
-    int xe[TN_MAXX], xf[TN_MAXX], rankP[TN_MAXX], rankQ[TN_MAXX], ordP[TN_MAXX], ordQ[TN_MAXX];
+    // The tables of the (at most TN_MAXX = 4) crossings live in REGISTERS: small integers packed 8 bits per crossing,
+    // flags as bit masks, the doubles in arrays that are only ever indexed by unrolled compile-time constants (a
+    // dynamic index goes through X4D below).  As dynamically indexed local arrays they cost a ~30-cycle local-memory
+    // load per access in the divergent trace loop: 22 % of the stall samples of k_narrow_ab<0> in ncu r1n.
+    static_assert(TN_MAXX == 4, "the packed crossing tables hold 4 entries");
+    unsigned xe_p = 0, xf_p = 0, rankP_p = 0, rankQ_p = 0, ordP_p = 0, ordQ_p = 0, xent_m = 0, xvis_m = 0;
     double xt[TN_MAXX], xs[TN_MAXX];
     double2 xp[TN_MAXX];
-    bool xent[TN_MAXX], xvis[TN_MAXX];
+#define X8(pack, k) (((pack) >> (8 * (k))) & 0xffu)
+#define X4D(arr, k) ((k) == 0 ? arr[0] : ((k) == 1 ? arr[1] : ((k) == 2 ? arr[2] : arr[3])))
     // pass 1 (uniform across the warp): one orientation per (P vertex, Q edge); the (e, f) pairs whose
     // side bit changes from vertex e to e+1 are appended to a short candidate list in (e, f) order
     unsigned char ce[TN_MAXC], cf[TN_MAXC];
@@ -248,26 +254,29 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
             if (K == TN_MAXX) {
                 fail = true;
             } else {
-                xe[K] = e;
-                xf[K] = f;
+                xe_p |= (unsigned)e << (8 * K);
+                xf_p |= (unsigned)f << (8 * K);
                 K++;
             }
         }
     }
     // pass 2b (lanes in step again): parameters and point of every crossing
-    U_CLIP
-    for (int k = 0; k < K; ++k) {
-        const int e = xe[k], f = xf[k];
-        double2 a = tgets<SHIFT>(P, e), b = tgets<SHIFT>(P, e + 1);
-        double2 c = tget(Q, f), d = tget(Q, f + 1);
-        double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
-        double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
-        double t = o1 / (o1 - o2);
-        xt[k] = t;
-        xs[k] = o3 / (o3 - o4);
-        xp[k] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
-        xent[k] = (side_q(o2, c, d) == q_ccw);
-        xvis[k] = false;
+#pragma unroll
+    for (int k = 0; k < TN_MAXX; ++k) {
+        xt[k] = xs[k] = 0.0;
+        xp[k] = make_double2(0.0, 0.0);
+        if (k < K) {
+            const int e = X8(xe_p, k), f = X8(xf_p, k);
+            double2 a = tgets<SHIFT>(P, e), b = tgets<SHIFT>(P, e + 1);
+            double2 c = tget(Q, f), d = tget(Q, f + 1);
+            double o1 = orient2d(c, d, a), o2 = orient2d(c, d, b);
+            double o3 = orient2d(a, b, c), o4 = orient2d(a, b, d);
+            double t = o1 / (o1 - o2);
+            xt[k] = t;
+            xs[k] = o3 / (o3 - o4);
+            xp[k] = make_double2(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y));
+            xent_m |= (unsigned)(side_q(o2, c, d) == q_ccw) << k;
+        }
     }
     if (fail) {
         status = TN_DEFER;
@@ -275,11 +284,13 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     }
     if (K_out) {
         bool dup = false;
-        U_CLIP
-        for (int k = 0; k < K; ++k) {
-            xp_out[k * TN_NT] = xp[k];
-            U_CLIP
-            for (int m = 0; m < k; ++m) dup |= (xp[m].x == xp[k].x && xp[m].y == xp[k].y);
+#pragma unroll
+        for (int k = 0; k < TN_MAXX; ++k) {
+            if (k < K) {
+                xp_out[k * TN_NT] = xp[k];
+#pragma unroll
+                for (int m = 0; m < k; ++m) dup |= (xp[m].x == xp[k].x && xp[m].y == xp[k].y);
+            }
         }
         *K_out = K;
         *generic = !anyzero && !dup;
@@ -299,22 +310,25 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         re[0] = src.n;
         return 1;
     }
-    int nentry = 0;
-    U_CLIP
-    for (int k = 0; k < K; ++k) {
-        int rp = 0, rq = 0;
-        U_CLIP
-        for (int m = 0; m < K; ++m) {
-            if (m == k) continue;
-            if (xe[m] < xe[k] || (xe[m] == xe[k] && (xt[m] < xt[k] || (xt[m] == xt[k] && m < k)))) rp++;
-            if (xf[m] < xf[k] || (xf[m] == xf[k] && (xs[m] < xs[k] || (xs[m] == xs[k] && m < k)))) rq++;
+#pragma unroll
+    for (int k = 0; k < TN_MAXX; ++k) {
+        if (k < K) {
+            int rp = 0, rq = 0;
+            const int ek = X8(xe_p, k), fk = X8(xf_p, k);
+#pragma unroll
+            for (int m = 0; m < TN_MAXX; ++m) {
+                if (m == k || m >= K) continue;
+                const int em = X8(xe_p, m), fm = X8(xf_p, m);
+                if (em < ek || (em == ek && (xt[m] < xt[k] || (xt[m] == xt[k] && m < k)))) rp++;
+                if (fm < fk || (fm == fk && (xs[m] < xs[k] || (xs[m] == xs[k] && m < k)))) rq++;
+            }
+            rankP_p |= (unsigned)rp << (8 * k);
+            rankQ_p |= (unsigned)rq << (8 * k);
+            ordP_p |= (unsigned)k << (8 * rp);
+            ordQ_p |= (unsigned)k << (8 * rq);
         }
-        rankP[k] = rp;
-        rankQ[k] = rq;
-        ordP[rp] = k;
-        ordQ[rq] = k;
-        nentry += xent[k];
     }
+    const int nentry = __popc(xent_m);
     if ((K & 1) || 2 * nentry != K) {
         status = TN_DEFER;  // the warp kernel records the degenerate trace
         return 0;
@@ -331,51 +345,53 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
     } while (0)
     U_CLIP
     for (int r = 0; r < K && !fail; ++r) {
-        const int startk = ordP[r];
-        if (xent[startk] && !xvis[startk]) {
+        const int startk = X8(ordP_p, r);
+        if (((xent_m & ~xvis_m) >> startk) & 1u) {
             int start = npts, cur = startk, mr = K, guard = 0;
             bool closed = false;
             while (!closed && !fail) {
-                if (xvis[cur]) {
+                if ((xvis_m >> cur) & 1u) {
                     fail = true;
                 } else {
-                    xvis[cur] = true;
-                    if (rankP[cur] < mr) mr = rankP[cur];
-                    TN_PUSH(xp[cur]);
-                    int rn = rankP[cur] + 1 == K ? 0 : rankP[cur] + 1, nx = ordP[rn];
-                    int cnt = xe[nx] - xe[cur] + (rn == 0 ? np : 0);
+                    xvis_m |= 1u << cur;
+                    const int rpc = X8(rankP_p, cur), xec = X8(xe_p, cur);
+                    if (rpc < mr) mr = rpc;
+                    TN_PUSH(X4D(xp, cur));
+                    const int rn = rpc + 1 == K ? 0 : rpc + 1, nx = X8(ordP_p, rn);
+                    int cnt = (int)X8(xe_p, nx) - xec + (rn == 0 ? np : 0);
                     U_CLIP
-                    for (int k = 0, v = xe[cur] + 1; k < cnt; ++k, ++v) {
+                    for (int k = 0, v = xec + 1; k < cnt; ++k, ++v) {
                         if (v >= np) v -= np;
                         TN_PUSH(tgets<SHIFT>(P, v));
                     }
-                    if (xent[nx] || xvis[nx]) {
+                    if (((xent_m | xvis_m) >> nx) & 1u) {
                         fail = true;
                     } else {
-                        xvis[nx] = true;
-                        if (rankP[nx] < mr) mr = rankP[nx];
-                        TN_PUSH(xp[nx]);
+                        xvis_m |= 1u << nx;
+                        const int rpn = X8(rankP_p, nx), rqn = X8(rankQ_p, nx), xfn = X8(xf_p, nx);
+                        if (rpn < mr) mr = rpn;
+                        TN_PUSH(X4D(xp, nx));
                         int nn;
                         if (same) {
-                            int rq = rankQ[nx] + 1 == K ? 0 : rankQ[nx] + 1;
-                            nn = ordQ[rq];
-                            cnt = xf[nn] - xf[nx] + (rq == 0 ? nq : 0);
+                            int rq = rqn + 1 == K ? 0 : rqn + 1;
+                            nn = X8(ordQ_p, rq);
+                            cnt = (int)X8(xf_p, nn) - xfn + (rq == 0 ? nq : 0);
                             U_CLIP
-                            for (int k = 0, v = xf[nx] + 1; k < cnt; ++k, ++v) {
+                            for (int k = 0, v = xfn + 1; k < cnt; ++k, ++v) {
                                 if (v >= nq) v -= nq;
                                 TN_PUSH(tget(Q, v));
                             }
                         } else {
-                            int rq = rankQ[nx] == 0 ? K - 1 : rankQ[nx] - 1;
-                            nn = ordQ[rq];
-                            cnt = xf[nx] - xf[nn] + (rankQ[nx] == 0 ? nq : 0);
+                            int rq = rqn == 0 ? K - 1 : rqn - 1;
+                            nn = X8(ordQ_p, rq);
+                            cnt = xfn - (int)X8(xf_p, nn) + (rqn == 0 ? nq : 0);
                             U_CLIP
-                            for (int k = 0, v = xf[nx]; k < cnt; ++k, --v) {
+                            for (int k = 0, v = xfn; k < cnt; ++k, --v) {
                                 if (v < 0) v += nq;
                                 TN_PUSH(tget(Q, v));
                             }
                         }
-                        if (!xent[nn]) fail = true;
+                        if (!((xent_m >> nn) & 1u)) fail = true;
                         else if (nn == startk) closed = true;
                         else {
                             cur = nn;
@@ -418,6 +434,8 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         nreg = 0;
     }
 #undef TN_PUSH
+#undef X8
+#undef X4D
     return nreg;
 }
 
