@@ -1292,11 +1292,10 @@ __global__ void __launch_bounds__(TN_NT, 2) k_crec_area(Store S, CouplingBuf CB,
                 double2 v = gQ[k];
                 sQ[k * TN_NT] = make_double2(v.x + d.x, v.y + d.y);
             }
-            int rs[TN_MAXREG], re[TN_MAXREG], status;
-            int nreg = t_clip<false>(tring(sP, 5), tring(sQ, nq), sR, TN_RCAP, rs, re, status, nullptr, nullptr, nullptr);
-            if (status != TN_OK) big = true;
+            const unsigned long long cr = t_clip<false>(tring(sP, 5), tring(sQ, nq), sR, TN_RCAP, nullptr);
+            if (TC_STATUS(cr) != TN_OK) big = true;
             else
-                for (int g = 0; g < nreg; ++g) area += t_area(tring(sR + rs[g] * TN_NT, re[g] - rs[g]));
+                for (int g = 0; g < TC_NREG(cr); ++g) area += t_area(tring(sR + TC_RS(cr, g) * TN_NT, TC_RE(cr, g) - TC_RS(cr, g)));
         }
         if (big) CB.big_recs[atomicAdd(&cnt->n_cbig, 1)] = r;
         else CB.rec_area[r] = area;

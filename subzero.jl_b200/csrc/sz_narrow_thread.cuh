@@ -181,14 +181,24 @@ __device__ TN_FN bool t_rings_intersect(const TRing A, const TRing B, bool &nohi
 // `xp_out` / `generic`: when no orientation value was exactly zero the crossing points ARE
 // GO.intersection_points(P, Q) (closed-segment intersection == proper crossing), in the same
 // (e, f) order; the caller then skips the separate 4 np nq pass.
+// The result comes back PACKED in one 64-bit value (a __noinline__ function returns it in registers; reference or
+// pointer outputs would live in local memory): number of regions, status, the two region ranges, the number of
+// crossings and whether they are GO.intersection_points.
+#define TC_PACK(nreg, status, rs0, re0, rs1, re1, K, gen)                                                          \
+    ((unsigned long long)(nreg) | ((unsigned long long)(status) << 8) | ((unsigned long long)(rs0) << 16) |          \
+     ((unsigned long long)(re0) << 24) | ((unsigned long long)(rs1) << 32) | ((unsigned long long)(re1) << 40) |     \
+     ((unsigned long long)(K) << 48) | ((unsigned long long)(gen) << 56))
+#define TC_NREG(v) ((int)((v)&0xffu))
+#define TC_STATUS(v) ((int)(((v) >> 8) & 0xffu))
+#define TC_RS(v, r) ((int)(((v) >> (16 + 16 * (r))) & 0xffu))
+#define TC_RE(v, r) ((int)(((v) >> (24 + 16 * (r))) & 0xffu))
+#define TC_K(v) ((int)(((v) >> 48) & 0xffu))
+#define TC_GENERIC(v) ((bool)(((v) >> 56) & 1u))
 template <bool SHIFT>
-__device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, int *rs, int *re, int &status,
-                                   double2 *xp_out, int *K_out, bool *generic) {
+__device__ TN_FN unsigned long long t_clip(const TRing P, const TRing Q, double2 *R, int rcap, double2 *xp_out) {
+    static_assert(TN_MAXREG == 2, "the packed result holds two regions");
     const int np = P.n - 1, nq = Q.n - 1;
-    status = TN_OK;
-    if (K_out) *K_out = 0;
-    if (generic) *generic = false;
-    if (np < 3 || nq < 3) return 0;
+    if (np < 3 || nq < 3) return TC_PACK(0, TN_OK, 0, 0, 0, 0, 0, 0);
     const bool q_ccw = t_area2(Q) > 0.0;
     const bool same = (SHIFT ? t_area2s(P) : t_area2(P)) > 0.0 == q_ccw;
     // The tables of the (at most TN_MAXX = 4) crossings live in REGISTERS: small integers packed 8 bits per crossing,
@@ -278,11 +288,9 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
             xent_m |= (unsigned)(side_q(o2, c, d) == q_ccw) << k;
         }
     }
-    if (fail) {
-        status = TN_DEFER;
-        return 0;
-    }
-    if (K_out) {
+    if (fail) return TC_PACK(0, TN_DEFER, 0, 0, 0, 0, 0, 0);
+    bool gen = false;
+    if (xp_out) {
         bool dup = false;
 #pragma unroll
         for (int k = 0; k < TN_MAXX; ++k) {
@@ -292,23 +300,17 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                 for (int m = 0; m < k; ++m) dup |= (xp[m].x == xp[k].x && xp[m].y == xp[k].y);
             }
         }
-        *K_out = K;
-        *generic = !anyzero && !dup;
+        gen = !anyzero && !dup;
     }
     if (K == 0) {
         bool pin = t_point_in_ring_q(tgets<SHIFT>(P, 0), Q);
         bool qin = pin ? false : (SHIFT ? t_point_in_ring_ps(tget(Q, 0), P) : t_point_in_ring_p(tget(Q, 0), P));
-        if (!pin && !qin) return 0;
+        if (!pin && !qin) return TC_PACK(0, TN_OK, 0, 0, 0, 0, 0, gen);
         const TRing src = pin ? P : Q;
-        if (src.n > rcap) {
-            status = TN_DEFER;
-            return 0;
-        }
+        if (src.n > rcap) return TC_PACK(0, TN_DEFER, 0, 0, 0, 0, 0, 0);
         U_CLIP
         for (int k = 0; k < src.n; ++k) R[k * TN_NT] = pin ? tgets<SHIFT>(src, k) : tget(src, k);
-        rs[0] = 0;
-        re[0] = src.n;
-        return 1;
+        return TC_PACK(1, TN_OK, 0, src.n, 0, 0, 0, gen);
     }
 #pragma unroll
     for (int k = 0; k < TN_MAXX; ++k) {
@@ -329,11 +331,8 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
         }
     }
     const int nentry = __popc(xent_m);
-    if ((K & 1) || 2 * nentry != K) {
-        status = TN_DEFER;  // the warp kernel records the degenerate trace
-        return 0;
-    }
-    int nreg = 0, npts = 0, minrank[TN_MAXREG];
+    if ((K & 1) || 2 * nentry != K) return TC_PACK(0, TN_DEFER, 0, 0, 0, 0, 0, 0);  // the warp kernel records the degenerate trace
+    int nreg = 0, npts = 0, rs0 = 0, re0 = 0, rs1 = 0, re1 = 0, mr0 = 0;
 #define TN_PUSH(pt)                                                                                  \
     do {                                                                                             \
         double2 _p = (pt);                                                                           \
@@ -413,30 +412,25 @@ __device__ TN_FN int t_clip(const TRing P, const TRing Q, double2 *R, int rcap, 
                     npts = start;
                 } else if (nreg >= TN_MAXREG) {
                     fail = true;
-                } else {
-                    int pos = nreg;
-                    while (pos > 0 && minrank[pos - 1] > mr) {
-                        minrank[pos] = minrank[pos - 1];
-                        rs[pos] = rs[pos - 1];
-                        re[pos] = re[pos - 1];
-                        --pos;
+                } else {  // regions ordered by their first crossing along P (two at most here)
+                    if (nreg == 0) {
+                        rs0 = start; re0 = npts; mr0 = mr;
+                    } else if (mr0 > mr) {
+                        rs1 = rs0; re1 = re0;
+                        rs0 = start; re0 = npts; mr0 = mr;
+                    } else {
+                        rs1 = start; re1 = npts;
                     }
-                    minrank[pos] = mr;
-                    rs[pos] = start;
-                    re[pos] = npts;
                     nreg++;
                 }
             }
         }
     }
-    if (fail) {
-        status = TN_DEFER;
-        nreg = 0;
-    }
 #undef TN_PUSH
 #undef X8
 #undef X4D
-    return nreg;
+    if (fail) return TC_PACK(0, TN_DEFER, 0, 0, 0, 0, 0, 0);
+    return TC_PACK(nreg, TN_OK, rs0, re0, rs1, re1, K, gen);
 }
 
 // which_vertices_match_points, floe_utils.jl:331-352.
@@ -515,12 +509,13 @@ __device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q
         P2.shifted = true;
         P2.sx = dir[0];
         P2.sy = dir[1];
-        int rs2[TN_MAXREG], re2[TN_MAXREG];
-        int nreg2 = t_clip<true>(P2, Q, w.R2, w.r2cap, rs2, re2, status, nullptr, nullptr, nullptr);
-        defer |= status != TN_OK;
-        if (defer) nreg2 = 0;
-        for (int r = 0; r < nreg2; ++r) {
-            TRing nr = tring(w.R2 + rs2[r] * TN_NT, re2[r] - rs2[r]);
+        const unsigned long long c2 = t_clip<true>(P2, Q, w.R2, w.r2cap, nullptr);
+        defer |= TC_STATUS(c2) != TN_OK;
+        const int nreg2 = defer ? 0 : TC_NREG(c2);
+#pragma unroll
+        for (int r = 0; r < TN_MAXREG; ++r) {
+            if (r >= nreg2) continue;
+            TRing nr = tring(w.R2 + TC_RS(c2, r) * TN_NT, TC_RE(c2, r) - TC_RS(c2, r));
             bool nohit = false;
             if (t_rings_intersect(nr, reg, nohit) && t_area(nr) / area > 1) {
                 dir[0] *= -1;
@@ -595,8 +590,16 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     int K1 = 0, nreg, used = 0;
     bool generic = false;
     if (PHASE == 0) {
-        nreg = t_clip<false>(Pr, Qr, w.R1, TN_RCAP_A, rs1, re1, status, w.ip, &K1, &generic);
-        if (status != TN_OK) return TI_WARP;
+        const unsigned long long c1 = t_clip<false>(Pr, Qr, w.R1, TN_RCAP_A, w.ip);
+        if (TC_STATUS(c1) != TN_OK) return TI_WARP;
+        nreg = TC_NREG(c1);
+        K1 = TC_K(c1);
+        generic = TC_GENERIC(c1);
+#pragma unroll
+        for (int r = 0; r < TN_MAXREG; ++r) {
+            rs1[r] = TC_RS(c1, r);
+            re1[r] = TC_RE(c1, r);
+        }
         for (int r = 0; r < nreg; ++r) used = max(used, re1[r]);
         pre.nreg = nreg;
         pre.np = npp;

@@ -56,11 +56,10 @@ __global__ void __launch_bounds__(TN_NT, 2) k_pair_area(Store S, PairQuery Q) {
                 const double2 *gP = S.verts + S.vstart[pr.x], *gQ = S.verts + S.vstart[pr.y];
                 for (int v = 0; v < np; ++v) sP[v * TN_NT] = gP[v];
                 for (int v = 0; v < nq; ++v) sQ[v * TN_NT] = gQ[v];
-                int rs[TN_MAXREG], re[TN_MAXREG], status;
-                int nreg = t_clip<false>(tring(sP, np), tring(sQ, nq), sR, TN_RCAP, rs, re, status, nullptr, nullptr, nullptr);
-                if (status != TN_OK) big = true;
+                const unsigned long long cr = t_clip<false>(tring(sP, np), tring(sQ, nq), sR, TN_RCAP, nullptr);
+                if (TC_STATUS(cr) != TN_OK) big = true;
                 else
-                    for (int g = 0; g < nreg; ++g) area += t_area(tring(sR + rs[g] * TN_NT, re[g] - rs[g]));
+                    for (int g = 0; g < TC_NREG(cr); ++g) area += t_area(tring(sR + TC_RS(cr, g) * TN_NT, TC_RE(cr, g) - TC_RS(cr, g)));
             }
         }
         if (big) Q.big[atomicAdd(Q.n_big, 1)] = k;
@@ -205,11 +204,10 @@ __global__ void __launch_bounds__(TN_NT, 2) k_eul_area(Store S, EulGrid G, EulBu
             sQ[2 * TN_NT] = make_double2(b[1], b[3]);
             sQ[3 * TN_NT] = make_double2(b[1], b[2]);
             sQ[4 * TN_NT] = make_double2(b[0], b[2]);
-            int rs[TN_MAXREG], re[TN_MAXREG], status;
-            int nreg = t_clip<false>(tring(sP, np), tring(sQ, 5), sR, TN_RCAP, rs, re, status, nullptr, nullptr, nullptr);
-            if (status != TN_OK) big = true;
+            const unsigned long long cr = t_clip<false>(tring(sP, np), tring(sQ, 5), sR, TN_RCAP, nullptr);
+            if (TC_STATUS(cr) != TN_OK) big = true;
             else
-                for (int g = 0; g < nreg; ++g) area += t_area(tring(sR + rs[g] * TN_NT, re[g] - rs[g]));
+                for (int g = 0; g < TC_NREG(cr); ++g) area += t_area(tring(sR + TC_RS(cr, g) * TN_NT, TC_RE(cr, g) - TC_RS(cr, g)));
         }
         if (big) B.big[atomicAdd(B.n_big, 1)] = r;
         else B.rec_area[r] = area;
