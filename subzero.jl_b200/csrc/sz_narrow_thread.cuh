@@ -489,7 +489,8 @@ struct TWs {
 // calc_normal_force, collisions.jl:30-70
 // (m, i0, i1, rare): the result of t_match_vertices for this region — evaluated for ALL regions before the first
 // second clip, because in k_narrow_ab<1> the crossing points share their rows with the regions of clip #2
-__device__ TN_FN double t_normal_force(const TWs w, const TRing P, const TRing Q, const TRing reg,
+// (one call site: inlined, so that `force` and `status` stay in registers)
+__device__ __forceinline__ double t_normal_force(const TWs w, const TRing P, const TRing Q, const TRing reg,
                                               double area, int m, int i0, int i1, bool rare, double ff, double force[2], int &status) {
     double dir[2] = {0.0, 0.0}, dl = 0.0;
     // m not in {0, 2}: _many_intersect_normal_force! (collisions.jl:78-119) — rare, like a near-tie above: the item
@@ -600,7 +601,9 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
             rs1[r] = TC_RS(c1, r);
             re1[r] = TC_RE(c1, r);
         }
-        for (int r = 0; r < nreg; ++r) used = max(used, re1[r]);
+#pragma unroll
+        for (int r = 0; r < TN_MAXREG; ++r)
+            if (r < nreg) used = max(used, re1[r]);
         pre.nreg = nreg;
         pre.np = npp;
         pre.nq = nqp;
@@ -624,10 +627,14 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     w.R2 = w.R1 + used * TN_NT;
     w.r2cap = w.rcap - used;
     double total = 0.0, max_area = 0.0;
-    for (int r = 0; r < nreg; ++r) {
-        area1[r] = t_area(tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]));
-        total += area1[r];
-        if (area1[r] > max_area) max_area = area1[r];
+#pragma unroll
+    for (int r = 0; r < TN_MAXREG; ++r) {  // constant indices: rs1 / re1 / area1 stay in registers
+        area1[r] = 0.0;
+        if (r < nreg) {
+            area1[r] = t_area(tring(w.R1 + rs1[r] * TN_NT, re1[r] - rs1[r]));
+            total += area1[r];
+            if (area1[r] > max_area) max_area = area1[r];
+        }
     }
     const double ai = S.area[fi], hi = S.height[fi];
     bool forces = false;
@@ -719,11 +726,12 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
                                fr);
                 double fx = c[0] + fr[0], fy = c[1] + fr[1];
                 if (fx != 0 || fy != 0) {  // add_interactions!, collisions.jl:288
-                    rows[nrows][0] = fx;
-                    rows[nrows][1] = fy;
-                    rows[nrows][2] = c[2];
-                    rows[nrows][3] = c[3];
-                    rows[nrows][4] = c[4];
+                    // (constant first index: the two staged rows stay in registers)
+                    if (nrows == 0) {
+                        rows[0][0] = fx; rows[0][1] = fy; rows[0][2] = c[2]; rows[0][3] = c[3]; rows[0][4] = c[4];
+                    } else {
+                        rows[1][0] = fx; rows[1][1] = fy; rows[1][2] = c[2]; rows[1][3] = c[3]; rows[1][4] = c[4];
+                    }
                     nrows++;
                 }
             }
@@ -736,8 +744,12 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
             atomicOr(&cnt->error, ERR_POOL_CAP);
             nrows = 0;
         } else {
-            for (int k = 0; k < nrows; ++k)
-                for (int q = 0; q < NPOOL; ++q) B.pool[(size_t)(row0 + k) * NPOOL + q] = rows[k][q];
+#pragma unroll
+            for (int k = 0; k < TN_MAXREG; ++k)
+                if (k < nrows) {
+#pragma unroll
+                    for (int q = 0; q < NPOOL; ++q) B.pool[(size_t)(row0 + k) * NPOOL + q] = rows[k][q];
+                }
         }
     }
     B.item_nrows[slot] = nrows;
