@@ -12,6 +12,7 @@
 #include "sz_common.cuh"
 
 #define NEV 8
+#define SZ_GRAPH_MAX_FLOES 32768  // sz_step replays a CUDA graph up to this field size (see step_impl)
 
 struct FloeArr {
     void **ptr;
@@ -40,6 +41,12 @@ struct sz_handle {
     cudaStream_t stream_up, stream_dn;
     cudaEvent_t ev_up[4], ev_dn[3], ev_up_start, ev_dn_end, ev_halo;
     double2 *d_cf_dn;  // [n][2] staging of collision_force in the host layout
+    // sz_step replays a captured CUDA graph of the whole timestep (39 launches, two streams); `gen` counts every
+    // change of a device pointer / parameter baked into the kernel nodes and forces a new capture
+    cudaGraphExec_t gexec;
+    unsigned long long gen, gkey_gen;
+    int gkey_coupling, gkey_floes, gkey_pairs, graph_launches;
+    bool graph_off;
     int cf_cap;
     Params P;
     bool have_grid, have_fields, have_domain, have_floes;
@@ -144,6 +151,7 @@ static void register_arrays(sz_handle *h) {
 
 // grow every per-floe array to new_cap floes, keeping the first `keep` entries
 static int32_t grow_floes(sz_handle *h, int new_cap, int keep) {
+    h->gen++;
     for (FloeArr &a : h->floe_arrays) {
         void *np = nullptr;
         CK(cudaMalloc(&np, a.elem * (size_t)std::max(new_cap, 1)));
@@ -177,6 +185,7 @@ static int32_t grow_floes(sz_handle *h, int new_cap, int keep) {
 }
 
 static int32_t grow_verts(sz_handle *h, int new_cap, int keep) {
+    h->gen++;
     double2 *np = nullptr;
     CK(dalloc(&np, (size_t)new_cap));
     if (keep > 0 && h->S.verts) CK(cudaMemcpy(np, h->S.verts, sizeof(double2) * (size_t)keep, cudaMemcpyDeviceToDevice));
@@ -187,6 +196,7 @@ static int32_t grow_verts(sz_handle *h, int new_cap, int keep) {
 }
 
 static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
+    h->gen++;
     StepBuf &B = h->B;
     dfree(B.pair_i); dfree(B.pair_j); dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem);
     dfree(B.item_nrows); dfree(B.item_row0); dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items);
@@ -215,6 +225,7 @@ static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
     return SZ_OK;
 }
 static int32_t set_pool_cap(sz_handle *h, int cap) {
+    h->gen++;
     dfree(h->B.pool); dfree(h->B.force_items); dfree(h->B.force_meta); dfree(h->B.force_pts);
     CK(dalloc(&h->B.pool, (size_t)cap * NPOOL));
     CK(dalloc(&h->B.force_items, (size_t)cap));
@@ -225,12 +236,14 @@ static int32_t set_pool_cap(sz_handle *h, int cap) {
     return SZ_OK;
 }
 static int32_t set_row_cap(sz_handle *h, int cap) {
+    h->gen++;
     dfree(h->B.rows);
     CK(dalloc(&h->B.rows, (size_t)cap * NCOL));
     h->B.cap_rows = cap;
     return SZ_OK;
 }
 static int32_t set_crec_cap(sz_handle *h, int cap) {
+    h->gen++;
     CouplingBuf &C = h->CB;
     dfree(C.rec_cell); dfree(C.rec_floe); dfree(C.rec_npts); dfree(C.rec_t); dfree(C.rec_d); dfree(C.rec_area); dfree(C.perm); dfree(C.big_recs);
     CK(dalloc(&C.rec_cell, (size_t)cap)); CK(dalloc(&C.rec_floe, (size_t)cap)); CK(dalloc(&C.rec_npts, (size_t)cap));
@@ -240,6 +253,7 @@ static int32_t set_crec_cap(sz_handle *h, int cap) {
     return SZ_OK;
 }
 static int32_t set_fuse_cap(sz_handle *h, int cap) {
+    h->gen++;
     dfree(h->B.fuse_pairs);
     CK(dalloc(&h->B.fuse_pairs, (size_t)cap));
     h->B.cap_fuse = cap;
@@ -285,6 +299,13 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     cudaEventCreate(&h->ev_c0);
     cudaEventCreate(&h->ev_c1);
     h->d_cf_dn = nullptr;
+    h->gexec = nullptr;
+    h->gen = 1;
+    h->gkey_gen = 0;
+    h->gkey_coupling = h->gkey_floes = h->gkey_pairs = -1;
+    h->graph_launches = 0;
+    h->graph_off = getenv("SZ_NO_GRAPH") != nullptr;
+    h->L.capturing = false;
     h->cf_cap = 0;
     if (cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream_dn, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SZ_ERR_CUDA; }
@@ -334,6 +355,7 @@ extern "C" void sz_destroy(sz_handle *h) {
     }
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int k = 0; k < NEV; ++k) cudaEventDestroy(h->ev[k]);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     cudaStreamDestroy(h->L.stream);
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream_up);
@@ -353,6 +375,7 @@ extern "C" int32_t sz_set_grid(sz_handle *h, int32_t Nx, int32_t Ny, double x0, 
     h->P.dy = (yf - y0) / Ny;
     h->have_grid = true;
     h->have_fields = false;
+    h->gen++;
     return SZ_OK;
 }
 
@@ -390,6 +413,7 @@ extern "C" int32_t sz_set_fields(sz_handle *h, const double *ou, const double *o
         h->P.atm_nonzero = nonzero(au) || nonzero(av);
         h->P.hflx_nonzero = nonzero(oh) || h->cfg.two_way_coupling_on;
     }
+    h->gen++;
     szk_pack_fields(h->L, S, (int)n);
     CK(cudaStreamSynchronize(h->L.stream));
     CK(cudaGetLastError());
@@ -498,6 +522,7 @@ extern "C" int32_t sz_set_domain(sz_handle *h, const int32_t kinds[4], const dou
     CK(cudaMemcpy(S.dom, &D, sizeof(DomainDev), cudaMemcpyHostToDevice));
     h->n_topo = n_topo;
     h->have_domain = true;
+    h->gen++;
     return SZ_OK;
 }
 
@@ -668,6 +693,7 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     h->h_vcount = vcount;
     h->h_mc_off = mo;
     h->have_floes = true;
+    h->gen++;
     return SZ_OK;
 }
 
@@ -862,7 +888,9 @@ static int32_t handle_overflow(sz_handle *h, const Counters &c) {
 
 static int pairs_hint(sz_handle *h) {
     long long g = h->last.n_cand > 0 ? (long long)h->last.n_cand * 2 : 8ll * h->n_total;
-    return (int)std::min<long long>(std::max<long long>(g, 1024), h->B.cap_pairs);
+    long long q = 1024;  // a power of two: the grid sizes baked into the captured graph change rarely
+    while (q < g) q <<= 1;
+    return (int)std::min<long long>(q, h->B.cap_pairs);
 }
 static int floes_hint(sz_handle *h) { return std::min(h->S.cap_floes, h->n_total + h->n_total / 4 + 64); }
 
@@ -1074,15 +1102,16 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
         if (rc) return rc;
     }
-    for (int attempt = 0;; ++attempt) {
+    // everything a timestep enqueues, from add_ghosts! to the read-back of the counters (no host synchronisation)
+    auto enqueue = [&]() -> int32_t {
         if (io) {
             // add_ghosts! copies every scalar of a parent into its ghost (collisions.jl:1017-1047): with periodic
             // walls the step starts when all uploads have landed
             for (int g = 0; g < (periodic ? 4 : 1); ++g) CK(cudaStreamWaitEvent(st, h->ev_up[g], 0));  // non-periodic: group 0
         }
-        cudaEventRecord(h->ev[0], st);
+        sz_record(h->L, h->ev[0], st);
         enqueue_ghosts(h);
-        cudaEventRecord(h->ev[1], st);
+        sz_record(h->L, h->ev[1], st);
         const bool fork = do_coupling && !h->cfg.two_way_coupling_on;
         if (fork) {
             // fork: coupling only needs the floe state after add_ghosts! wrapped parents into the domain; it
@@ -1095,9 +1124,9 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
             // measured (profiles/README.md): capping coupling to 2-4 resident blocks per SM so that it runs beside the
             // narrow phase slows the latter more than the overlap gains; it fills the GPU during the broad phase
             L2.coupling_blocks_per_sm = 0;
-            cudaEventRecord(h->ev_c0, h->stream2);
+            sz_record(L2, h->ev_c0, h->stream2);
             szk_coupling(L2, h->S, h->P);
-            cudaEventRecord(h->ev_c1, h->stream2);
+            sz_record(L2, h->ev_c1, h->stream2);
             cudaEventRecord(h->ev_join, h->stream2);
         }
         // the ghost count of this step is not known on the host: size grids from the capacity-bounded hint
@@ -1105,25 +1134,71 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         if (io) CK(cudaStreamWaitEvent(st, h->ev_up[1], 0));
         szk_collisions(h->L, h->S, h->B, h->P, floes_hint(h), pairs_hint(h), &h->ev[2], io ? waits : nullptr);
         szk_remove_ghosts(h->L, h->S, h->n_verts_init);
-        cudaEventRecord(h->ev[5], st);
-        if (io) { int32_t rc = enqueue_downloads(h, io->out, 0); if (rc) return rc; }
+        sz_record(h->L, h->ev[5], st);
+        if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 0); if (rc2) return rc2; }
         if (fork) {
             cudaStreamWaitEvent(st, h->ev_join, 0);  // join
             szk_apply_coupling_tags(h->L, h->S);
         } else if (do_coupling) {
             // two-way coupling writes ocean.hflx_factor for the NEXT step: it must not run ahead of a collision
             // phase that may still overflow and be repeated, so it stays in order on this stream
-            cudaEventRecord(h->ev_c0, st);
+            sz_record(h->L, h->ev_c0, st);
             enqueue_coupling(h, h->L);
-            cudaEventRecord(h->ev_c1, st);
+            sz_record(h->L, h->ev_c1, st);
             szk_apply_coupling_tags(h->L, h->S);
         }
-        if (io) { int32_t rc = enqueue_downloads(h, io->out, 1); if (rc) return rc; }
-        cudaEventRecord(h->ev[6], st);
+        if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 1); if (rc2) return rc2; }
+        sz_record(h->L, h->ev[6], st);
         szk_update(h->L, h->S, h->B, h->P);
-        cudaEventRecord(h->ev[7], st);
-        if (io) { int32_t rc = enqueue_downloads(h, io->out, 2); if (rc) return rc; }
+        sz_record(h->L, h->ev[7], st);
+        if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 2); if (rc2) return rc2; }
         CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        return SZ_OK;
+    };
+    for (int attempt = 0;; ++attempt) {
+        // Device-resident steps replay a captured CUDA graph of the ~39 launches on two streams: most of them are
+        // small dependent kernels (scans, checks, the broad phase) whose launch gaps then shrink; the graph is
+        // captured again whenever a pointer or parameter baked into its nodes changed (h->gen) or a grid-size hint
+        // moved to another bucket.  sz_step_host (host copies with caller pointers) enqueues directly, and so do LARGE
+        // fields: measured (tools/ab_small.sh) the graph gives +22 % at 1 k floes and +12 % at 10 k, but -7 % at 100 k,
+        // where the step is bound by three long kernels and the coupling branch, which loses its low stream priority
+        // inside the graph, gets in the way of the broad phase.
+        bool replay = false;
+        if (!io && !h->graph_off && h->n_init <= SZ_GRAPH_MAX_FLOES) {
+            const int fh = floes_hint(h), ph = pairs_hint(h);
+            const bool fresh = h->gexec && h->gkey_gen == h->gen && h->gkey_coupling == do_coupling && h->gkey_floes == fh && h->gkey_pairs == ph;
+            if (!fresh) {
+                if (h->gexec) cudaGraphExecDestroy(h->gexec);
+                h->gexec = nullptr;
+                const long long before = szk_launch_count(false);
+                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                h->L.capturing = true;
+                const int32_t crc = enqueue();
+                h->L.capturing = false;
+                cudaGraph_t g = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(st, &g);
+                const long long captured = szk_launch_count(false) - before;
+                szk_count_launches((int)-captured);  // nothing has run yet
+                if (crc == SZ_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&h->gexec, g, 0) == cudaSuccess) {
+                    h->gkey_gen = h->gen; h->gkey_coupling = do_coupling; h->gkey_floes = fh; h->gkey_pairs = ph;
+                    h->graph_launches = (int)captured;
+                } else {
+                    h->gexec = nullptr;
+                    h->graph_off = true;  // fall back to direct launches for the life of the handle
+                    cudaGetLastError();
+                }
+                if (g) cudaGraphDestroy(g);
+            }
+            if (h->gexec) {
+                CK(cudaGraphLaunch(h->gexec, st));
+                szk_count_launches(h->graph_launches);
+                replay = true;
+            }
+        }
+        if (!replay) {
+            int32_t erc = enqueue();
+            if (erc) return erc;
+        }
         CK(cudaStreamSynchronize(st));
         if (io) {
             CK(cudaEventRecord(h->ev_dn_end, h->stream_dn));

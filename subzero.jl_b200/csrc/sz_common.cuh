@@ -184,7 +184,14 @@ struct Launch {
     int sms;  // multiprocessor count: persistent grids are sized in multiples of it
     int maxv_large, maxx_large;  // workspace of the large-polygon kernels
     int coupling_blocks_per_sm;  // 0 = fill the GPU; > 0 = persistent grid of that many blocks per SM
+    bool capturing;              // the stream is being captured into a CUDA graph (sz_step)
 };
+
+// Timing events: inside a stream capture they must be recorded as EXTERNAL event nodes to stay usable with
+// cudaEventElapsedTime after the graph has run.
+inline void sz_record(const Launch &L, cudaEvent_t e, cudaStream_t s) {
+    cudaEventRecordWithFlags(e, s, L.capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 
 // ---- host-callable launchers (sz_kernels.cu) -------------------------------------------------
 // one periodic axis of add_ghosts! (0 = east/west, 1 = north/south)

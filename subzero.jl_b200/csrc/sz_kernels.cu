@@ -1179,7 +1179,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_low_link<<<gf, TPB, 0, st>>>(S, B);
     int gp = grid_for(L, pairs_hint, TPB);
     k_filter<<<gp, TPB, 0, st>>>(S, B);
-    if (ev) cudaEventRecord(ev[0], st);
+    if (ev) sz_record(L, ev[0], st);
     if (waits) cudaStreamWaitEvent(st, waits[0], 0);  // sz_step_host: rings and height have landed
     const int maxv_s = 32, maxx_s = 16, wpb = 4;
     // thread-per-item fast path (small polygons), then warp-per-item for what it handed on, then the
@@ -1193,7 +1193,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
     k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
     k_pool_check<<<1, 1, 0, st>>>(S, B);
-    if (ev) cudaEventRecord(ev[1], st);
+    if (ev) sz_record(L, ev[1], st);
     if (waits) cudaStreamWaitEvent(st, waits[1], 0);  // sz_step_host: everything else (overarea is accumulated by k_row_write)
     k_status<<<gf, TPB, 0, st>>>(S, B);
     k_fuse_propagate<<<1, 1024, 0, st>>>(S, B);
@@ -1203,7 +1203,7 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
     k_row_check<<<1, 1, 0, st>>>(S, B);
     k_row_write<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
     k_update_boundaries<<<1, 1, 0, st>>>(S, P);
-    if (ev) cudaEventRecord(ev[2], st);
+    if (ev) sz_record(L, ev[2], st);
     g_launch_count += 26;  // + the scans counted in scan_excl / scan_excl3
 }
 
