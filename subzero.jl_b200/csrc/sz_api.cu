@@ -1161,8 +1161,8 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         // captured again whenever a pointer or parameter baked into its nodes changed (h->gen) or a grid-size hint
         // moved to another bucket.  sz_step_host (host copies with caller pointers) enqueues directly, and so do LARGE
         // fields: measured (tools/ab_small.sh) the graph gives +22 % at 1 k floes and +12 % at 10 k, but -7 % at 100 k,
-        // where the step is bound by three long kernels and the coupling branch, which loses its low stream priority
-        // inside the graph, gets in the way of the broad phase.
+        // where the step is bound by three long kernels (the captured nodes keep their stream priorities: checked with
+        // cudaGraphKernelNodeGetAttribute; the external timing-event nodes in the chain are the suspected cost).
         bool replay = false;
         if (!io && !h->graph_off && h->n_init <= SZ_GRAPH_MAX_FLOES) {
             const int fh = floes_hint(h), ph = pairs_hint(h);
