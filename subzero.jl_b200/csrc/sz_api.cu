@@ -1102,6 +1102,12 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
         if (rc) return rc;
     }
+    // A collision-phase buffer overflow is repaired and the step repeated FROM THE COLLISIONS: the ghosts of the failed
+    // attempt are complete and stay (every kernel after the overflow returned at once, including the ghost removal).
+    // Running add_ghosts! again would start from parents the first pass has already wrapped into the domain and can
+    // number the images of a corner floe in another order than a clean step does (rows and totals then differ from the
+    // reference in their last bit).
+    bool keep_ghosts = false;
     // everything a timestep enqueues, from add_ghosts! to the read-back of the counters (no host synchronisation)
     auto enqueue = [&]() -> int32_t {
         if (io) {
@@ -1110,7 +1116,7 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
             for (int g = 0; g < (periodic ? 4 : 1); ++g) CK(cudaStreamWaitEvent(st, h->ev_up[g], 0));  // non-periodic: group 0
         }
         sz_record(h->L, h->ev[0], st);
-        enqueue_ghosts(h);
+        if (!keep_ghosts) enqueue_ghosts(h);
         sz_record(h->L, h->ev[1], st);
         const bool fork = do_coupling && !h->cfg.two_way_coupling_on;
         if (fork) {
@@ -1166,7 +1172,8 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         bool replay = false;
         if (!io && !h->graph_off && h->n_init <= SZ_GRAPH_MAX_FLOES) {
             const int fh = floes_hint(h), ph = pairs_hint(h);
-            const bool fresh = h->gexec && h->gkey_gen == h->gen && h->gkey_coupling == do_coupling && h->gkey_floes == fh && h->gkey_pairs == ph;
+            const bool fresh = !keep_ghosts && h->gexec && h->gkey_gen == h->gen && h->gkey_coupling == do_coupling && h->gkey_floes == fh &&
+                               h->gkey_pairs == ph;
             if (!fresh) {
                 if (h->gexec) cudaGraphExecDestroy(h->gexec);
                 h->gexec = nullptr;
@@ -1180,7 +1187,8 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
                 const long long captured = szk_launch_count(false) - before;
                 szk_count_launches((int)-captured);  // nothing has run yet
                 if (crc == SZ_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&h->gexec, g, 0) == cudaSuccess) {
-                    h->gkey_gen = h->gen; h->gkey_coupling = do_coupling; h->gkey_floes = fh; h->gkey_pairs = ph;
+                    h->gkey_gen = keep_ghosts ? 0 : h->gen;  // a repair attempt's graph (no ghost pass) is not reused
+                    h->gkey_coupling = do_coupling; h->gkey_floes = fh; h->gkey_pairs = ph;
                     h->graph_launches = (int)captured;
                 } else {
                     h->gexec = nullptr;
@@ -1220,15 +1228,22 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         }
         CK(cudaGetLastError());
         if (!h->h_cnt->error) break;
-        // every kernel after the overflow returned at once; only ghosts (and parents wrapped into
-        // the domain) may have been written, which a fresh add_ghosts! reproduces
+        // every kernel after the overflow returned at once: the floe state is untouched except for the ghosts (and the
+        // parents add_ghosts! wrapped into the domain), which stay for the repeated attempt (see keep_ghosts above)
         Counters c = *h->h_cnt;
         h->n_total = c.n_total;
         h->n_verts = c.n_verts;
         if (attempt >= 6) return fail(h, SZ_ERR_CAPACITY, "step: capacity retry limit");
         int32_t rc = handle_overflow(h, c);
         if (rc) return rc;
-        szk_remove_ghosts(h->L, h->S, h->n_verts_init);
+        const uint32_t ghost_bits = ERR_GHOST_CAP | ERR_VERT_CAP | ERR_GHOST_SLOTS;
+        if (c.error & ghost_bits) {
+            // the ghost pass itself overflowed: nothing of it was committed for that axis; start over
+            szk_remove_ghosts(h->L, h->S, h->n_verts_init);
+            keep_ghosts = false;
+        } else {
+            keep_ghosts = true;
+        }
         CK(cudaStreamSynchronize(st));
         h->n_total = h->n_init;
         h->n_verts = h->n_verts_init;

@@ -407,3 +407,29 @@ def test_exactly_packed_voronoi_field(walls, product_lib, oracle_lib):
         h.add_ghosts()
         h.step_collisions()
     same_outputs()
+
+
+@pytest.mark.parametrize("walls", ["collision", "periodic"])
+def test_graph_replay_equals_direct_launches(walls, product_lib, monkeypatch):
+    """sz_step replays a captured CUDA graph for fields of up to 32k floes: same bits as direct launches, over several
+    steps, with and without coupling (two graphs), across a re-upload (new capture) and a capacity overflow.  The
+    periodic field starts with 18 centroids outside the domain (add_ghosts! wraps those parents): the overflow repair
+    must not run add_ghosts! a second time from the wrapped state, or a corner floe's images change their order."""
+    f = synth.make_field(4000, scale=1.02, walls=walls, npoints=60, cache=False)
+    fields.perturb_state(f.floes)
+    hg = synth.setup_handle(f, product_lib, max_pairs_per_floe=1)   # tiny pair capacity: the first step overflows and retries
+    monkeypatch.setenv("SZ_NO_GRAPH", "1")
+    hd = synth.setup_handle(f, product_lib)
+    monkeypatch.delenv("SZ_NO_GRAPH")
+    for t in range(6):
+        cpl = t % 3 != 1
+        hg.step(t, cpl)
+        hd.step(t, cpl)
+        a, b = hg.download_floes(mc=False), hd.download_floes(mc=False)
+        assert_ok(compare_state(a, b, exact=parity_all_fields()))
+        assert hg.counts() == hd.counts()
+        if t == 3:   # a new floe list: the graph is captured again
+            hg.upload_floes(hd.download_floes())
+            hd.upload_floes(hd.download_floes())
+    tg, td = hg.timings(), hd.timings()
+    assert tg["narrow"] > 0 and td["narrow"] > 0   # the external timing events of the graph work
