@@ -200,7 +200,7 @@ static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
     StepBuf &B = h->B;
     dfree(B.pair_i); dfree(B.pair_j); dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem);
     dfree(B.item_nrows); dfree(B.item_row0); dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items);
-    dfree(B.order);
+    dfree(B.order); dfree(B.order_cls);
     CK(dalloc(&B.pair_i, (size_t)cap_pairs));
     CK(dalloc(&B.pair_j, (size_t)cap_pairs));
     CK(dalloc(&B.low_pair, (size_t)cap_pairs));
@@ -214,11 +214,12 @@ static int32_t set_pair_cap(sz_handle *h, int cap_pairs, int cap_dom) {
     CK(dalloc(&B.large_items, items));
     CK(dalloc(&B.mid_items, items));
     CK(dalloc(&B.order, items));
+    CK(dalloc(&B.order_cls, items));
     if (!B.class_count) {
-        CK(dalloc(&B.class_count, 3 * 64));
-        CK(cudaMemset(B.class_count, 0, sizeof(int) * 3 * 64));
-        B.class_base = B.class_count + 64;
-        B.class_cursor = B.class_count + 128;
+        CK(dalloc(&B.class_count, 3 * 128));
+        CK(cudaMemset(B.class_count, 0, sizeof(int) * 3 * 128));
+        B.class_base = B.class_count + 128;
+        B.class_cursor = B.class_count + 256;
     }
     B.cap_pairs = cap_pairs;
     B.cap_dom = cap_dom;
@@ -339,7 +340,7 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(S.atm_u); dfree(S.atm_v); dfree(S.fields8); dfree(S.cnt); dfree(S.dom);
     dfree(B.cell_count); dfree(B.cell_start); dfree(B.cell_fill); dfree(B.scan_block); dfree(B.cell_circ); dfree(B.pair_i); dfree(B.pair_j);
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
-    dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
+    dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.order_cls); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
     dfree(h->d_hl_idx); dfree(h->d_hl_voff);
     {
         SvcBuf &V = h->svc;

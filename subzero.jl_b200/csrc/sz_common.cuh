@@ -151,10 +151,11 @@ struct StepBuf {
     int *large_items;    // [cap_pairs + cap_dom] work list of the large-polygon kernel
     int *mid_items;      // [cap_pairs + cap_dom] work list of the warp-per-item kernel
     int *order;          // [cap_pairs + cap_dom] items sorted by (edges of P, edges of Q)
+    unsigned char *order_cls;  // ... and their class (the ring sizes the warp lays its shared memory out for)
     int *force_items;    // [cap_force] items that need contact forces (cap_force == cap_pool)
     int4 *force_meta;    // [cap_force] region table of clip #1
     double2 *force_pts;  // [TN_PRE_PTS][cap_force] regions and crossing points of clip #1
-    int *class_count, *class_base, *class_cursor;  // [64] counting sort of the work items
+    int *class_count, *class_base, *class_cursor;  // [128] counting sort of the work items
     // per-floe rows
     int *row_pre, *row_count, *row_off;  // [cap_floes+1]
     double *rows;                        // [cap_rows][7]

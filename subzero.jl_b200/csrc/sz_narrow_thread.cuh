@@ -17,12 +17,12 @@
 #define TN_FN __noinline__  // measured: forcing these inline triples the kernel time (3.4 active lanes per instruction instead of 10)
 #endif
 #define TN_NT 128    // threads per block
-#define TN_MAXV 11   // ring points incl. the closing point (<= 10 edges)
+#define TN_MAXV 14   // ring points incl. the closing point (<= 13 edges)
 #define TN_MAXX 4    // crossings per clip
 #define TN_MAXREG 2  // regions per clip
 #define TN_RCAP 24   // region points of clip #1 AND clip #2 together (they share one buffer)
-#define TN_RCAP_A 10 // phase 0 (clip #1 only): 36 double2 per thread = 72 KB per block, THREE blocks per SM; the few
-                     // regions with more points (and containment of a ring of > 9 points) go to the warp kernel
+#define TN_RCAP_A 16 // phase 0 (clip #1 only): at most this many region rows (what phase 1 can take over); the few
+                     // regions with more points go to the warp kernel
 #define TN_MAXIP 4   // intersection points = the crossing points of clip #1 (<= TN_MAXX)
 #define TN_MAXC 24   // edge pairs whose P edge straddles the Q edge's line
 
@@ -591,7 +591,7 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     int K1 = 0, nreg, used = 0;
     bool generic = false;
     if (PHASE == 0) {
-        const unsigned long long c1 = t_clip<false>(Pr, Qr, w.R1, TN_RCAP_A, w.ip);
+        const unsigned long long c1 = t_clip<false>(Pr, Qr, w.R1, w.rcap, w.ip);
         if (TC_STATUS(c1) != TN_OK) return TI_WARP;
         nreg = TC_NREG(c1);
         K1 = TC_K(c1);
@@ -764,11 +764,13 @@ __device__ int thread_item(TWs w, const Store &S, const StepBuf &B, const Params
     return TI_DONE;
 }
 
-#define TN_SMEM_A (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP_A + TN_MAXIP))  // k_narrow_ab<0>
-#define TN_ROWS_B 36  // rows per thread of k_narrow_ab<1>: three blocks per SM, split per warp (see the kernel)
+#define TN_ROWS_B 36  // rows per thread of k_narrow_ab<0/1>: three blocks per SM, split per warp (see the kernel)
+#define TN_SMEM_A (sizeof(double2) * TN_NT * TN_ROWS_B)                             // k_narrow_ab<0>
 #define TN_SMEM_B (sizeof(double2) * TN_NT * TN_ROWS_B)                             // k_narrow_ab<1>
 #define TN_SMEM_C (sizeof(double2) * TN_NT * (2 * TN_MAXV + TN_RCAP))               // single-clip kernels (P, Q, R)
-#define TN_NCLASS 64  // (edges of P - 3) * 8 + (edges of Q - 3), rings of 3..10 edges
+#define TN_NCE (TN_MAXV - 3)      // edge counts 3 .. TN_MAXV - 1
+#define TN_NCLASS 128             // >= TN_NCE^2 classes: (edges of P - 3) * TN_NCE + (edges of Q - 3)
+static_assert(TN_NCE * TN_NCE <= TN_NCLASS, "class table too small");
 
 // ---- work-item ordering -----------------------------------------------------------------------------
 // A warp of the thread-per-item kernels runs 32 items in lockstep, so its speed is set by the LARGEST
@@ -788,7 +790,7 @@ __device__ __forceinline__ int item_class(const Store &S, const StepBuf &B, int 
         eq = elem < 4 ? 4 : S.topo_vcount[elem - 4] - 1;
     }
     if (ep + 1 > TN_MAXV || eq + 1 > TN_MAXV) return TN_NCLASS;
-    return (ep - 3) * 8 + (eq - 3);
+    return (ep - 3) * TN_NCE + (eq - 3);
 }
 
 __global__ void __launch_bounds__(256) k_item_count(Store S, StepBuf B) {
@@ -816,24 +818,30 @@ __global__ void __launch_bounds__(256) k_item_count(Store S, StepBuf B) {
         if (hist[k]) atomicAdd(&B.class_count[k], hist[k]);
 }
 
-__global__ void k_class_scan(Store S, StepBuf B) {  // one warp, two classes per lane
+__global__ void k_class_scan(Store S, StepBuf B) {  // one warp, four classes per lane
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const int lane = threadIdx.x & 31;
-    const int c0 = B.class_count[2 * lane], c1 = B.class_count[2 * lane + 1];
-    int incl = c0 + c1;
+    int c[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c[k] = B.class_count[4 * lane + k];
+        tot += c[k];
+    }
+    int incl = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         int y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
     }
-    const int ex = incl - (c0 + c1);
-    B.class_base[2 * lane] = ex;
-    B.class_cursor[2 * lane] = ex;
-    B.class_base[2 * lane + 1] = ex + c0;
-    B.class_cursor[2 * lane + 1] = ex + c0;
-    B.class_count[2 * lane] = 0;  // ready for the next step
-    B.class_count[2 * lane + 1] = 0;
+    int ex = incl - tot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        B.class_base[4 * lane + k] = ex;
+        B.class_cursor[4 * lane + k] = ex;
+        B.class_count[4 * lane + k] = 0;  // ready for the next step
+        ex += c[k];
+    }
     if (lane == 31) {
         cnt->n_order = incl;
         cnt->n_force = 0;
@@ -858,7 +866,10 @@ __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
         for (int k = threadIdx.x; k < TN_NCLASS; k += blockDim.x)
             if (hist[k]) base[k] = atomicAdd(&B.class_cursor[k], hist[k]);
         __syncthreads();
-        if (c >= 0 && c < TN_NCLASS) B.order[base[c] + rank] = item_slot(B, it, np);
+        if (c >= 0 && c < TN_NCLASS) {
+            B.order[base[c] + rank] = item_slot(B, it, np);
+            B.order_cls[base[c] + rank] = (unsigned char)c;
+        }
         __syncthreads();
     }
 }
@@ -874,17 +885,15 @@ __global__ void __launch_bounds__(TN_NT, 3) k_narrow_ab(Store S, StepBuf B, Para
     double2 *base = (double2 *)smem + threadIdx.x;
     TWs w;
     w.P = base;
-    w.Q = w.P + TN_MAXV * TN_NT;
-    w.R1 = w.Q + TN_MAXV * TN_NT;
-    w.R2 = w.R1;
-    w.rcap = TN_RCAP_A;
+    w.Q = w.R1 = w.R2 = w.ip = base;
+    w.rcap = 0;
     w.r2cap = 0;
-    w.ip = w.R1 + TN_RCAP_A * TN_NT;
-    // phase 1 needs P, Q, the regions of clip #1 AND of clip #2: with worst-case capacities (11 + 11 + 24 + 4 rows)
-    // only two blocks fit on an SM.  The items are sorted by ring size, so every WARP lays out its 32 columns of the
-    // 36 rows for the largest rings among its own items: P | Q | regions (what is left: 22 rows for two hexagons).  The
-    // 4 crossing points sit in the last region rows; they are consumed (which_vertices_match_points of every region)
-    // before the first second clip may write there.  A second clip that does not fit goes to the warp kernel.
+    // With worst-case capacities (14 + 14 ring rows, 24 region rows, 4 crossing points) only two blocks would fit on
+    // an SM.  The items are sorted by ring size, so every WARP lays out its 32 columns of the 36 rows for the largest
+    // rings among its own items: P | Q | regions (what is left: 22 rows for two hexagons in phase 1).  Phase 0 keeps the
+    // 4 crossing points in the last rows; in phase 1 they alias the last region rows and are consumed
+    // (which_vertices_match_points of every region) before the first second clip may write there.  Regions that do not
+    // fit go to the warp kernel.
     const int total = PHASE == 0 ? cnt->n_order : min(cnt->n_force, B.cap_force);
     const int *list = PHASE == 0 ? B.order : B.force_items;
     const int lane = threadIdx.x & 31;
@@ -907,6 +916,20 @@ __global__ void __launch_bounds__(TN_NT, 3) k_narrow_ab(Store S, StepBuf B, Para
                 pre.rs[1] = m.z & 0xffff; pre.re[1] = m.z >> 16;
             }
         }
+        if (PHASE == 0) {
+            const int cls = it < total ? (int)B.order_cls[it] : -1;
+            int npm = cls >= 0 ? cls / TN_NCE + 4 : 0, nqm = cls >= 0 ? cls % TN_NCE + 4 : 0;  // ring points = edges + 1
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                npm = max(npm, __shfl_xor_sync(0xffffffffu, npm, o));
+                nqm = max(nqm, __shfl_xor_sync(0xffffffffu, nqm, o));
+            }
+            w.Q = w.P + npm * TN_NT;
+            w.R1 = w.Q + nqm * TN_NT;
+            w.R2 = w.R1;
+            w.rcap = min(TN_ROWS_B - TN_MAXIP - npm - nqm, TN_RCAP_A);
+            w.ip = w.P + (TN_ROWS_B - TN_MAXIP) * TN_NT;
+        }
         if (PHASE == 1) {
             int npm = it < total ? pre.np : 0, nqm = it < total ? pre.nq : 0;
 #pragma unroll
@@ -917,15 +940,19 @@ __global__ void __launch_bounds__(TN_NT, 3) k_narrow_ab(Store S, StepBuf B, Para
             w.Q = w.P + npm * TN_NT;
             w.R1 = w.Q + nqm * TN_NT;
             w.R2 = w.R1;
-            w.rcap = TN_ROWS_B - npm - nqm;  // >= TN_RCAP_A + TN_MAXIP: clip #1's regions and the crossing points always fit
+            w.rcap = TN_ROWS_B - npm - nqm;  // clip #1's regions + the crossing points must fit: checked per item below
             w.ip = w.P + (TN_ROWS_B - TN_MAXIP) * TN_NT;  // the last rows of the region buffer: read before clip #2 writes there
         }
         if (it < total) {
+            bool fits = true;
             if (PHASE == 1) {
-                for (int k = 0; k < pre.used; ++k) w.R1[k * TN_NT] = B.force_pts[k * cf + it];
-                for (int k = 0; k < pre.K1; ++k) w.ip[k * TN_NT] = B.force_pts[(TN_RCAP + k) * cf + it];
+                fits = pre.used + TN_MAXIP <= w.rcap;  // (a warp of 13-gons leaves 8 region rows)
+                if (fits) {
+                    for (int k = 0; k < pre.used; ++k) w.R1[k * TN_NT] = B.force_pts[k * cf + it];
+                    for (int k = 0; k < pre.K1; ++k) w.ip[k * TN_NT] = B.force_pts[(TN_RCAP + k) * cf + it];
+                }
             }
-            rc = thread_item<PHASE>(w, S, B, P, slot, pre);
+            rc = fits ? thread_item<PHASE>(w, S, B, P, slot, pre) : TI_WARP;
         }
         if (rc == TI_WARP) {
             B.mid_items[atomicAdd(&cnt->n_mid, 1)] = slot;
