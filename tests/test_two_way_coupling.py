@@ -157,9 +157,18 @@ def test_two_way_coupling_cuda_matches_oracle(walls, product_lib, oracle_lib):
     assert np.array_equal(vg[:, 2:], vo[:, 2:]) and rel_err(vg[:, :2], vo[:, :2]) < 1e-9
     for a, b, name in zip(hg.ocean_fields(), ho.ocean_fields(), ("tau_x", "tau_y", "si_frac", "hflx_factor")):
         assert rel_err(a, b) < 1e-9, name
-    from parity_util import compare_state
+    from parity_util import STATE_FIELDS, compare_state
     bad = compare_state(hg.download_floes(), ho.download_floes())
     assert not bad, "\n".join(bad)
+    # the host-buffer form of the step (two-way coupling stays in order on the main stream there): same bits
+    hh = two_way_handle(f, product_lib)
+    fa = hh.download_floes(mc=False)
+    hh.step_host(fa, 0, True)
+    hh.step_host(fa, 1, True)
+    bad = compare_state(fa, hg.download_floes(mc=False), exact=STATE_FIELDS)
+    assert not bad, "\n".join(bad)
+    for a, b in zip(hh.ocean_fields(), hg.ocean_fields()):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.gpu
