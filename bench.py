@@ -275,7 +275,11 @@ def main():
         host_fa = pin_floe_arrays(h.download_floes(mc=False))
         h2d = dyn_bytes(host_fa)
         def e2e_step(t, fused):
-            if fused:
+            if fused and me is not None:
+                h.upload_state_begin(host_fa, True)      # H2D enqueued; the halo exchange waits for it on the device
+                me.exchange()
+                h.step_host(None, t, True, out=host_fa)  # kernels + overlapped D2H
+            elif fused:
                 h.step_host(host_fa, t, True)            # one C-ABI call: H2D + kernels + D2H, overlapped
             else:
                 h.upload_state(host_fa)                  # H2D: every per-floe scalar + ring coordinates
@@ -299,18 +303,15 @@ def main():
 
         d2h = h2d + host_fa.id.nbytes + host_fa.ghost_id.nbytes
         sep = time_e2e(False)
-        if world == 1:
-            # sz_step_host does not upload what the step overwrites before any read: collision_force / collision_trq
-            # (zeroed by timestep_collisions!) and, on a step that runs the coupling, fxOA / fyOA / trqOA / hflx_factor
-            h2d_fused = (h2d - host_fa.collision_force.nbytes - host_fa.collision_trq.nbytes - host_fa.fxOA.nbytes
-                         - host_fa.fyOA.nbytes - host_fa.trqOA.nbytes - host_fa.hflx_factor.nbytes)
-            e2e = {"value": time_e2e(True), "unit": "steps/s", "h2d_bytes_per_step": int(h2d_fused), "d2h_bytes_per_step": int(d2h),
-                   "call": "sz_step_host on pinned host arrays (upload of every per-floe input scalar + rings, step, download "
-                           "of the whole state; copies overlap the kernels)",
-                   "separate_calls_steps_per_s": sep}
-        else:
-            e2e = {"value": sep, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "call": "sz_upload_state + halo exchange + sz_step + sz_download_floes on pinned host arrays"}
+        # sz_step_host does not upload what the step overwrites before any read: collision_force / collision_trq
+        # (zeroed by timestep_collisions!) and, on a step that runs the coupling, fxOA / fyOA / trqOA / hflx_factor
+        h2d_fused = (h2d - host_fa.collision_force.nbytes - host_fa.collision_trq.nbytes - host_fa.fxOA.nbytes
+                     - host_fa.fyOA.nbytes - host_fa.trqOA.nbytes - host_fa.hflx_factor.nbytes)
+        e2e = {"value": time_e2e(True), "unit": "steps/s", "h2d_bytes_per_step": int(h2d_fused), "d2h_bytes_per_step": int(d2h),
+               "call": ("sz_step_host on pinned host arrays (upload of every per-floe input scalar + rings, step, download "
+                        "of the whole state; copies overlap the kernels)" if world == 1 else
+                        "sz_upload_state_begin + halo exchange + sz_step_host(in = NULL) on pinned host arrays, every rank"),
+               "separate_calls_steps_per_s": sep}
 
     halo = None
     if me is not None:

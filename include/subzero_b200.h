@@ -202,6 +202,11 @@ int32_t SZ_FN(step)(sz_handle *h, int64_t tstep, int32_t do_coupling);
  * and, when do_coupling != 0, fxOA / fyOA / trqOA / hflx_factor (coupling.jl:1583-1586). */
 int32_t SZ_FN(step_host)(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in,
                          sz_floe_soa *out);
+/* The upload half of sz_step_host on its own, for a slab rank: sz_upload_state_begin(in) enqueues the uploads and
+ * returns at once, the halo exchange follows (sz_halo_pack_on waits on the device for the uploads, so the halo
+ * update lands on top of the uploaded copies), then sz_step_host(h, tstep, do_coupling, NULL, out) runs the step
+ * and the overlapped downloads.  `in` must stay valid until that call returns; do_coupling must be the same. */
+int32_t SZ_FN(upload_state_begin)(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in);
 
 /* ---- results ------------------------------------------------------------------------------- */
 /* interactions: offsets[n_total+1] and rows[n_rows][7] =

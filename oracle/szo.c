@@ -1416,10 +1416,14 @@ int32_t szo_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
 }
 
 /* the host-buffer form of the timestep: no overlap to exploit on the CPU, the three calls back to back */
+int32_t szo_upload_state_begin(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in) {
+    (void)do_coupling;
+    return szo_upload_state(h, in);
+}
 int32_t szo_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
     int32_t rc;
-    if (!h || !in || !out) return SZ_ERR_INVALID;
-    if ((rc = szo_upload_state(h, in)) != SZ_OK) return rc;
+    if (!h || !out) return SZ_ERR_INVALID;
+    if (in && (rc = szo_upload_state(h, in)) != SZ_OK) return rc; /* in == NULL: szo_upload_state_begin did it */
     if ((rc = szo_step(h, tstep, do_coupling)) != SZ_OK) return rc;
     double *mx = out->mc_x, *my = out->mc_y;
     out->mc_x = out->mc_y = NULL; /* Monte-Carlo points are not transferred */

@@ -110,6 +110,7 @@ class Library:
         "step_floe_properties": (C.c_int32, [C.c_void_p, C.c_int64]),
         "step": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32]),
         "step_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(FloeSoA), C.POINTER(FloeSoA)]),
+        "upload_state_begin": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FloeSoA)]),
         "get_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
         "set_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
         "get_pairs": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
@@ -378,10 +379,19 @@ class Handle:
     def step_host(self, fa, tstep=0, do_coupling=True, out=None):
         """One timestep on host arrays (upload_state + step + download in one call, copies overlapped with the
         kernels).  `out` defaults to `fa` (in-place)."""
+        if fa is None:  # the uploads were enqueued by upload_state_begin
+            o = out.as_struct()
+            self._ck(self.lib.step_host(self.h, tstep, 1 if do_coupling else 0, None, C.byref(o)))
+            return out
         s = fa.as_struct()
         o = s if out is None or out is fa else out.as_struct()
         self._ck(self.lib.step_host(self.h, tstep, 1 if do_coupling else 0, C.byref(s), C.byref(o)))
         return fa if out is None else out
+
+    def upload_state_begin(self, fa, do_coupling=True):
+        """The upload half of step_host (returns at once); follow with the halo exchange and step_host(None, ..., out=fa)."""
+        s = fa.as_struct()
+        self._ck(self.lib.upload_state_begin(self.h, 1 if do_coupling else 0, C.byref(s)))
 
     # results ----------------------------------------------------------------------------------
     def interactions(self):

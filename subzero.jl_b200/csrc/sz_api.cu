@@ -47,6 +47,7 @@ struct sz_handle {
     unsigned long long gen, gkey_gen;
     int gkey_coupling, gkey_floes, gkey_pairs, graph_launches;
     bool graph_off;
+    int up_pending;  // sz_upload_state_begin ran: 1 + do_coupling, 0 = none
     int cf_cap;
     Params P;
     bool have_grid, have_fields, have_domain, have_floes;
@@ -301,6 +302,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     cudaEventCreate(&h->ev_c1);
     h->d_cf_dn = nullptr;
     h->gexec = nullptr;
+    h->up_pending = 0;
     h->gen = 1;
     h->gkey_gen = 0;
     h->gkey_coupling = h->gkey_floes = h->gkey_pairs = -1;
@@ -1099,7 +1101,7 @@ static int32_t enqueue_downloads(sz_handle *h, sz_floe_soa *s, int stage) {
 static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
     cudaStream_t st = h->L.stream;
     const bool periodic = h->hD.kind[2] == SZ_BOUNDARY_PERIODIC || h->hD.kind[0] == SZ_BOUNDARY_PERIODIC;
-    if (io) {
+    if (io && io->in) {
         int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
         if (rc) return rc;
     }
@@ -1284,15 +1286,47 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
 
 // sz_upload_state + sz_step + sz_download_floes in ONE call: the host <-> device copies run on their own
 // streams beside the kernels (see HostIO).  `in` and `out` may point to the same arrays.
+static int32_t check_host_state(sz_handle *h, const char *who, int32_t do_coupling, const sz_floe_soa *in) {
+    char msg[160];
+    if (!h->have_domain || !h->have_floes) { snprintf(msg, sizeof(msg), "%s before set_domain/upload_floes", who); return fail(h, SZ_ERR_INVALID, msg); }
+    if (do_coupling && !h->have_fields) { snprintf(msg, sizeof(msg), "%s with coupling before set_fields", who); return fail(h, SZ_ERR_INVALID, msg); }
+    if (h->n_total != h->n_init) { snprintf(msg, sizeof(msg), "%s with ghosts present (call remove_ghosts)", who); return fail(h, SZ_ERR_INVALID, msg); }
+    if (in) {
+        if (in->n != h->n_total || in->n_init != h->n_init) { snprintf(msg, sizeof(msg), "%s: floe count differs from the resident store", who); return fail(h, SZ_ERR_INVALID, msg); }
+        if (!in->centroid_x || !in->centroid_y || !in->area || !in->rmax || !in->vert_xy) { snprintf(msg, sizeof(msg), "%s: geometry arrays are required", who); return fail(h, SZ_ERR_INVALID, msg); }
+        if (in->vert_offsets && in->vert_offsets[h->n_total] != h->n_verts) { snprintf(msg, sizeof(msg), "%s: vertex count differs from the resident store", who); return fail(h, SZ_ERR_INVALID, msg); }
+    }
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_upload_state_begin(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in) {
+    if (!h || !in) return SZ_ERR_INVALID;
+    int32_t rc = check_host_state(h, "upload_state_begin", do_coupling, in);
+    if (rc) return rc;
+    if (h->up_pending) return fail(h, SZ_ERR_INVALID, "upload_state_begin: an upload is already pending");
+    cudaSetDevice(h->cfg.device);
+    rc = enqueue_uploads(h, in, do_coupling != 0);
+    if (rc) {
+        cudaStreamSynchronize(h->stream_up);
+        return rc;
+    }
+    h->up_pending = 1 + (do_coupling != 0);
+    return SZ_OK;
+}
+
+// sz_upload_state + sz_step + sz_download_floes in ONE call: the host <-> device copies run on their own
+// streams beside the kernels (see HostIO).  `in` and `out` may point to the same arrays; in == NULL: the uploads were
+// enqueued by sz_upload_state_begin.
 extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
     (void)tstep;
-    if (!h || !in || !out) return SZ_ERR_INVALID;
-    if (!h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step_host before set_domain/upload_floes");
-    if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step_host with coupling before set_fields");
-    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host with ghosts present (call remove_ghosts)");
-    if (in->n != h->n_total || in->n_init != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host: floe count differs from the resident store");
-    if (!in->centroid_x || !in->centroid_y || !in->area || !in->rmax || !in->vert_xy) return fail(h, SZ_ERR_INVALID, "step_host: geometry arrays are required");
-    if (in->vert_offsets && in->vert_offsets[h->n_total] != h->n_verts) return fail(h, SZ_ERR_INVALID, "step_host: vertex count differs from the resident store");
+    if (!h || !out) return SZ_ERR_INVALID;
+    {
+        int32_t rc = check_host_state(h, "step_host", do_coupling, in);
+        if (rc) return rc;
+    }
+    if (!in && h->up_pending != 1 + (do_coupling != 0)) return fail(h, SZ_ERR_INVALID, "step_host without input arrays needs sz_upload_state_begin with the same do_coupling");
+    if (in && h->up_pending) return fail(h, SZ_ERR_INVALID, "step_host: an upload of sz_upload_state_begin is pending (pass in = NULL)");
+    h->up_pending = 0;
     if ((int)h->h_vcount.size() != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host: no ring table of the resident floes");
     cudaSetDevice(h->cfg.device);
     const int n = h->n_init;
@@ -1448,6 +1482,7 @@ static int32_t halo_move(sz_handle *h, int32_t list, void *buf, int64_t bytes, b
         // ordered behind the halo update without a host synchronisation
         Launch Lu = h->L;
         Lu.stream = user;
+        if (h->up_pending) CK(cudaStreamWaitEvent(user, h->ev_up[3], 0));  // sz_upload_state_begin: the uploads land first
         szk_halo(Lu, h->S, h->d_hl_idx + a, h->d_hl_voff + a, (int)n, (double *)buf, pack);
         if (!pack) {
             CK(cudaEventRecord(h->ev_halo, user));

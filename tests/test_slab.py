@@ -36,6 +36,26 @@ def run_decomposed(f, lib, world, steps, device="cpu", walls_period=None, coupli
     return ranks
 
 
+def run_decomposed_host(f, lib, world, steps, device="cpu", walls_period=None):
+    """The same decomposition driven through HOST arrays every step: sz_upload_state_begin -> halo exchange ->
+    sz_step_host(in = NULL): the halo update must land on top of the (stale) uploaded halo copies."""
+    import torch
+    period = f.L if walls_period else None
+    ranks = slab.partition_global(f.floes, world, period, skin=200.0, period_y=f.L if f.walls == "periodic" else None)
+    host = []
+    for r in ranks:
+        r.attach(make_handle(f, lib))
+        r.make_buffers(torch.device(device))
+        host.append(r.h.download_floes(mc=False))
+    for t in range(steps):
+        for r, fa in zip(ranks, host):
+            r.h.upload_state_begin(fa, True)
+        slab.exchange_local(ranks)
+        for r, fa in zip(ranks, host):
+            r.h.step_host(None, t, True, out=fa)
+    return ranks
+
+
 def check_against_single(f, lib, ranks, steps, coupling=True):
     h = make_handle(f, lib)
     for t in range(steps):
@@ -61,6 +81,14 @@ def test_emulated_ranks_match_single_rank_oracle(walls, world, oracle_lib):
     ranks = run_decomposed(f, oracle_lib, world, 3, walls_period=walls in ("periodic", "shear"))
     assert sum(int(r.owned.sum()) for r in ranks) == f.floes.n
     assert all(r.local.n < f.floes.n for r in ranks)
+    check_against_single(f, oracle_lib, ranks, 3)
+
+
+@pytest.mark.parametrize("walls,world", [("periodic", 2), ("collision", 3)])
+def test_emulated_ranks_through_host_arrays_oracle(walls, world, oracle_lib):
+    f = synth.make_field(1200, scale=1.02, walls=walls, npoints=30, cache=False)
+    fields.perturb_state(f.floes)
+    ranks = run_decomposed_host(f, oracle_lib, world, 3, walls_period=walls in ("periodic", "shear"))
     check_against_single(f, oracle_lib, ranks, 3)
 
 
@@ -136,6 +164,16 @@ def test_two_process_gloo_weak_scaling_tiles(walls):
         p.join(timeout=60)
     for rank, bad in res:
         assert not bad, "rank %d: %s" % (rank, "\n".join(bad))
+
+
+@pytest.mark.gpu
+def test_emulated_ranks_through_host_arrays_on_one_gpu(product_lib):
+    """sz_upload_state_begin -> stream-ordered halo exchange -> sz_step_host(in = NULL) on CUDA: bit-identical to the
+    single-handle device-resident run."""
+    f = synth.make_field(3000, scale=1.01, walls="periodic", npoints=40, cache=False)
+    fields.perturb_state(f.floes)
+    ranks = run_decomposed_host(f, product_lib, 3, 3, device="cuda", walls_period=True)
+    check_against_single(f, product_lib, ranks, 3)
 
 
 @pytest.mark.gpu
