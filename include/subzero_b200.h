@@ -46,7 +46,7 @@ extern "C" {
 #define SZ_ERR_INVALID (-1)     /* bad argument / call order */
 #define SZ_ERR_CUDA (-2)        /* CUDA runtime failure */
 #define SZ_ERR_CAPACITY (-3)    /* a device buffer overflowed (pairs, regions, rows, ghosts) */
-#define SZ_ERR_UNSUPPORTED (-4) /* feature outside the hot-path scope (e.g. two-way coupling) */
+#define SZ_ERR_UNSUPPORTED (-4) /* outside the scope or the workspace (a ring of > 1024 points, gridded output with topography) */
 #define SZ_ERR_NOMEM (-5)
 
 /* Status tags, src/simulation_components/floe.jl:8-12 */

@@ -8,7 +8,7 @@
  * Parity status: the reference is 100 % Julia and cannot run in this environment (no julia
  * binary), and its polygon clipping lives in GeometryOps.jl 0.1.x which is not vendored.
  * The oracle is pinned against every golden value the reference's own tests hold for this
- * path (tests/test_oracle_golden.py: test_collisions.jl:50-150,190-363,
+ * path (tests/test_reference_golden.py: test_collisions.jl:50-150,190-363,
  * test_coupling.jl:464-640, test_update_floe.jl:2-42).  Below the digits those tests print,
  * and for exactly degenerate polygon configurations, parity is UNPINNED (see szo_geom.h).
  *
