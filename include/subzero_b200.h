@@ -247,6 +247,12 @@ int32_t SZ_FN(halo_unpack)(sz_handle *h, int32_t list, const void *src, int64_t 
  * current stream).  pack -> send/recv -> unpack -> sz_step then run back to back on the device: sz_halo_unpack_on
  * makes the handle's own stream wait for the unpack kernel, nothing blocks the host.  The caller must not touch
  * the buffers from another stream in between.  The oracle build (host buffers) ignores `stream`. */
+/* A slab rank may start the one-way coupling of the coming sz_step BEFORE the halo exchange: the coupling of an owned
+ * floe reads only that floe's own state, so it runs beside pack / send / recv / unpack instead of after them
+ * (the results of the halo copies are never used).  No-op (returns SZ_OK) where the order matters: with a periodic
+ * boundary on this handle (add_ghosts! wraps parents first) or with two-way coupling.  The next sz_step /
+ * sz_step_host(do_coupling != 0) joins it instead of launching its own. */
+int32_t SZ_FN(coupling_begin)(sz_handle *h);
 int32_t SZ_FN(halo_pack_on)(sz_handle *h, int32_t list, void *dst, int64_t capacity_bytes, void *stream);
 int32_t SZ_FN(halo_unpack_on)(sz_handle *h, int32_t list, const void *src, int64_t bytes, void *stream);
 

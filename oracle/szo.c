@@ -1416,6 +1416,8 @@ int32_t szo_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
 }
 
 /* the host-buffer form of the timestep: no overlap to exploit on the CPU, the three calls back to back */
+/* an overlap hint for the CUDA product; the oracle's step does its coupling in order */
+int32_t szo_coupling_begin(sz_handle *h) { return h ? SZ_OK : SZ_ERR_INVALID; }
 int32_t szo_upload_state_begin(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in) {
     (void)do_coupling;
     return szo_upload_state(h, in);

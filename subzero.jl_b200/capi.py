@@ -111,6 +111,7 @@ class Library:
         "step": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32]),
         "step_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(FloeSoA), C.POINTER(FloeSoA)]),
         "upload_state_begin": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FloeSoA)]),
+        "coupling_begin": (C.c_int32, [C.c_void_p]),
         "get_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
         "set_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
         "get_pairs": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p]),
@@ -387,6 +388,10 @@ class Handle:
         o = s if out is None or out is fa else out.as_struct()
         self._ck(self.lib.step_host(self.h, tstep, 1 if do_coupling else 0, C.byref(s), C.byref(o)))
         return fa if out is None else out
+
+    def coupling_begin(self):
+        """Slab ranks: start the coming step's one-way coupling before the halo exchange (no-op where the order matters)."""
+        self._ck(self.lib.coupling_begin(self.h))
 
     def upload_state_begin(self, fa, do_coupling=True):
         """The upload half of step_host (returns at once); follow with the halo exchange and step_host(None, ..., out=fa)."""

@@ -48,6 +48,7 @@ struct sz_handle {
     int gkey_coupling, gkey_floes, gkey_pairs, graph_launches;
     bool graph_off;
     int up_pending;  // sz_upload_state_begin ran: 1 + do_coupling, 0 = none
+    bool cpl_prelaunched;  // sz_coupling_begin started this step's coupling kernel on stream2
     int cf_cap;
     Params P;
     bool have_grid, have_fields, have_domain, have_floes;
@@ -303,6 +304,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->d_cf_dn = nullptr;
     h->gexec = nullptr;
     h->up_pending = 0;
+    h->cpl_prelaunched = false;
     h->gen = 1;
     h->gkey_gen = 0;
     h->gkey_coupling = h->gkey_floes = h->gkey_pairs = -1;
@@ -1122,7 +1124,7 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         if (!keep_ghosts) enqueue_ghosts(h);
         sz_record(h->L, h->ev[1], st);
         const bool fork = do_coupling && !h->cfg.two_way_coupling_on;
-        if (fork) {
+        if (fork && !h->cpl_prelaunched) {
             // fork: coupling only needs the floe state after add_ghosts! wrapped parents into the domain; it
             // reads nothing the collision kernels write, so it runs beside them on a low-priority stream and
             // fills the issue slots the latency-bound narrow phase leaves idle
@@ -1173,7 +1175,7 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         // where the step is bound by three long kernels (the captured nodes keep their stream priorities: checked with
         // cudaGraphKernelNodeGetAttribute; the external timing-event nodes in the chain are the suspected cost).
         bool replay = false;
-        if (!io && !h->graph_off && h->n_init <= SZ_GRAPH_MAX_FLOES) {
+        if (!io && !h->graph_off && !h->cpl_prelaunched && h->n_init <= SZ_GRAPH_MAX_FLOES) {
             const int fh = floes_hint(h), ph = pairs_hint(h);
             const bool fresh = !keep_ghosts && h->gexec && h->gkey_gen == h->gen && h->gkey_coupling == do_coupling && h->gkey_floes == fh &&
                                h->gkey_pairs == ph;
@@ -1254,6 +1256,7 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
     h->last = *h->h_cnt;
     h->n_total = h->n_init;
     h->n_verts = h->n_verts_init;
+    h->cpl_prelaunched = false;
     if (getenv("SZ_DEBUG_COUNTS"))
         fprintf(stderr, "counts: cand %d kept %d dom %d order %d force %d mid %d large %d overlap %d rows %d\n", h->last.n_cand,
                 h->last.n_kept, h->last.n_dom, h->last.n_order, h->last.n_force, h->last.n_mid, h->last.n_large, h->last.n_overlap,
@@ -1275,11 +1278,36 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
     return SZ_OK;
 }
 
+extern "C" int32_t sz_coupling_begin(sz_handle *h) {
+    if (!h) return SZ_ERR_INVALID;
+    if (!h->have_domain || !h->have_floes || !h->have_fields) return fail(h, SZ_ERR_INVALID, "coupling_begin before set_domain/set_fields/upload_floes");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "coupling_begin with ghosts present");
+    if (h->cfg.two_way_coupling_on || h->P.per_x || h->P.per_y || h->cpl_prelaunched) return SZ_OK;  // the order matters there
+    cudaSetDevice(h->cfg.device);
+    cudaStream_t st = h->L.stream;
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    if (h->up_pending) {  // sz_upload_state_begin: the coupling inputs are upload group 0
+        CK(cudaStreamWaitEvent(h->stream2, h->ev_up[0], 0));
+    }
+    Launch L2 = h->L;
+    L2.stream = h->stream2;
+    L2.coupling_blocks_per_sm = 0;
+    sz_record(L2, h->ev_c0, h->stream2);
+    szk_coupling(L2, h->S, h->P);
+    sz_record(L2, h->ev_c1, h->stream2);
+    CK(cudaEventRecord(h->ev_join, h->stream2));
+    CK(cudaGetLastError());
+    h->cpl_prelaunched = true;
+    return SZ_OK;
+}
+
 extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     (void)tstep;
     if (!h || !h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step before set_domain/upload_floes");
     if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step with coupling before set_fields");
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
+    if (h->cpl_prelaunched && !do_coupling) return fail(h, SZ_ERR_INVALID, "step without coupling after sz_coupling_begin");
     cudaSetDevice(h->cfg.device);
     return step_impl(h, do_coupling, nullptr);
 }
@@ -1327,6 +1355,7 @@ extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling
     if (!in && h->up_pending != 1 + (do_coupling != 0)) return fail(h, SZ_ERR_INVALID, "step_host without input arrays needs sz_upload_state_begin with the same do_coupling");
     if (in && h->up_pending) return fail(h, SZ_ERR_INVALID, "step_host: an upload of sz_upload_state_begin is pending (pass in = NULL)");
     h->up_pending = 0;
+    if (h->cpl_prelaunched && !do_coupling) return fail(h, SZ_ERR_INVALID, "step_host without coupling after sz_coupling_begin");
     if ((int)h->h_vcount.size() != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host: no ring table of the resident floes");
     cudaSetDevice(h->cfg.device);
     const int n = h->n_init;

@@ -145,6 +145,7 @@ class SlabRank:
     # ---- per-step exchange ----------------------------------------------------------------------
     def make_buffers(self, device):
         import torch
+        self._plan = None
         self.sbuf = [torch.empty(max(self.nbytes[2 * k], 8), dtype=torch.uint8, device=device) for k in range(len(self.partners))]
         self.rbuf = [torch.empty(max(self.nbytes[2 * k + 1], 8), dtype=torch.uint8, device=device) for k in range(len(self.partners))]
 
@@ -155,29 +156,35 @@ class SlabRank:
         does not wait anywhere."""
         import torch.distributed as dist
         cuda = bool(self.sbuf) and self.sbuf[0].is_cuda
-        stream = None
+        plan = getattr(self, "_plan", None)
+        if plan is None:  # the lists are fixed between rebuilds: slices, pointers and P2P descriptors are built once
+            sends = [(2 * k, self.sbuf[k].data_ptr(), self.nbytes[2 * k]) for k in range(len(self.partners)) if self.nbytes[2 * k]]
+            recvs = [(2 * k + 1, self.rbuf[k].data_ptr(), self.nbytes[2 * k + 1]) for k in range(len(self.partners)) if self.nbytes[2 * k + 1]]
+            ops = []
+            for k, s in enumerate(self.partners):
+                if self.nbytes[2 * k]:
+                    ops.append(dist.P2POp(dist.isend, self.sbuf[k][:self.nbytes[2 * k]], s))
+                if self.nbytes[2 * k + 1]:
+                    ops.append(dist.P2POp(dist.irecv, self.rbuf[k][:self.nbytes[2 * k + 1]], s))
+            plan = self._plan = (sends, recvs, ops)
+        sends, recvs, ops = plan
         if cuda:
             import torch
             stream = torch.cuda.current_stream().cuda_stream
-        ops = []
-        for k, s in enumerate(self.partners):
-            if self.nbytes[2 * k]:
-                if cuda:
-                    self.h.halo_pack_on(2 * k, self.sbuf[k].data_ptr(), self.nbytes[2 * k], stream)
-                else:
-                    self.h.halo_pack(2 * k, self.sbuf[k].data_ptr(), self.nbytes[2 * k])
-                ops.append(dist.P2POp(dist.isend, self.sbuf[k][:self.nbytes[2 * k]], s))
-            if self.nbytes[2 * k + 1]:
-                ops.append(dist.P2POp(dist.irecv, self.rbuf[k][:self.nbytes[2 * k + 1]], s))
+            for lst, ptr, nb in sends:
+                self.h.halo_pack_on(lst, ptr, nb, stream)
+        else:
+            for lst, ptr, nb in sends:
+                self.h.halo_pack(lst, ptr, nb)
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()  # NCCL: the current stream waits for the transfer, the host does not
-        for k, s in enumerate(self.partners):
-            if self.nbytes[2 * k + 1]:
-                if cuda:
-                    self.h.halo_unpack_on(2 * k + 1, self.rbuf[k].data_ptr(), self.nbytes[2 * k + 1], stream)
-                else:
-                    self.h.halo_unpack(2 * k + 1, self.rbuf[k].data_ptr(), self.nbytes[2 * k + 1])
+        if cuda:
+            for lst, ptr, nb in recvs:
+                self.h.halo_unpack_on(lst, ptr, nb, stream)
+        else:
+            for lst, ptr, nb in recvs:
+                self.h.halo_unpack(lst, ptr, nb)
 
     def owned_state(self):
         """(global indices, FloeArrays) of the owned floes, downloaded from the handle."""

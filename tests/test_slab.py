@@ -30,6 +30,9 @@ def run_decomposed(f, lib, world, steps, device="cpu", walls_period=None, coupli
         r.attach(h)
         r.make_buffers(torch.device(device))
     for t in range(steps):
+        if coupling:
+            for r in ranks:
+                r.h.coupling_begin()   # CUDA, no periodic wall on the rank: the coupling runs beside the exchange
         slab.exchange_local(ranks)
         for r in ranks:
             r.h.step(t, coupling)
@@ -50,6 +53,7 @@ def run_decomposed_host(f, lib, world, steps, device="cpu", walls_period=None):
     for t in range(steps):
         for r, fa in zip(ranks, host):
             r.h.upload_state_begin(fa, True)
+            r.h.coupling_begin()
         slab.exchange_local(ranks)
         for r, fa in zip(ranks, host):
             r.h.step_host(None, t, True, out=fa)
