@@ -580,6 +580,17 @@ static int match_vertices(const szo_pt *ip, int nip, const szo_pt *reg, int nr, 
     return m;
 }
 
+/* test hook: which_vertices_match_points on caller data (golden values of test_floe_utils.jl:76-137); indices
+ * come back 1-based like the reference's */
+int32_t szo_test_match_vertices(const double *pts_xy, int32_t npts, const double *ring_xy, int32_t nring, int32_t *idx_out) {
+    if (!pts_xy || !ring_xy || !idx_out || npts < 1 || nring < 1) return SZ_ERR_INVALID;
+    int *idx = (int *)malloc(sizeof(int) * (size_t)npts);
+    int m = match_vertices((const szo_pt *)pts_xy, npts, (const szo_pt *)ring_xy, nring, idx);
+    for (int k = 0; k < m; ++k) idx_out[k] = idx[k] + 1;
+    free(idx);
+    return m;
+}
+
 /* _many_intersect_normal_force!, collisions.jl:78-119 */
 static double many_intersect_normal(double dir[2], const szo_pt *reg, int nr, const szo_pt *P, int npp, double ff) {
     double x1 = 0, y1 = 0, dl = 0, Fx = 0, Fy = 0;

@@ -443,3 +443,33 @@ def test_stress_strain(lib):
 def test_moment_of_inertia_helper():
     tri = np.array([[0, 1], [0, 0], [1, 0], [0, 1]], dtype=np.float64) * 6.67
     assert host.calc_moment_inertia(tri, host.ring_centroid(tri), 0.5) == pytest.approx(50581.145, abs=1e-3)
+
+
+# ---- which_vertices_match_points (floe_utils.jl:331-352), test_floe_utils.jl:76-137 ------------------------------
+MATCH_CASES = [
+    # (points = ring of polygon 1, ring of polygon 2, expected 1-based vertex indices of polygon 2)
+    ([[0.0, 0.0], [0.0, 20.0], [20.0, 20.0], [20.0, 0.0], [0.0, 0.0]],
+     [[20.0, 0.0], [20.0, 20.0], [40.0, 20.0], [40.0, 0.0], [20.0, 0.0]], [1, 2]),                               # :76-83
+    ([[0.0, 0.0], [0.0, 20.0], [20.0, 20.0], [20.0, 10.0], [20.0, 0.0], [0.0, 0.0]],
+     [[40.0, 20.0], [40.0, 0.0], [20.0, 0.0], [20.0, 10.0], [20.0, 20.0], [40.0, 20.0]], [3, 4, 5]),             # :90-97
+    ([[0.0, 0.0], [0.0, 20.0], [20.0, 20.0], [20.0, 18.0], [20.0, 15.0], [20.0, 0.0], [0.0, 0.0]],
+     [[20.0, 18.0], [20.0, 20.0], [40.0, 20.0], [40.0, 0.0], [20.0, 0.0], [20.0, 15.0], [20.0, 18.0]], [1, 2, 5, 6]),  # :110-117
+    ([[0.0, 0.0], [0.0, 20.0], [20.0, 20.0], [5.0, 5.0], [0.0, 0.0]],
+     [[0.0, 0.0], [5.0, 5.0], [20.0, 20.0], [20.0, 0.0], [0.0, 0.0]], [1, 2, 3]),                                # :129-136
+]
+
+
+@pytest.mark.parametrize("case", MATCH_CASES, ids=["two_shared", "three_shared", "four_shared", "triangle_shared"])
+def test_which_vertices_match_points(oracle_lib, case):
+    """Pins the oracle's restatement (the CUDA kernels are held to the oracle bit for bit on the rows these indices feed)."""
+    import ctypes as C
+    pts, ring, want = case
+    fn = oracle_lib.dll.szo_test_match_vertices
+    fn.restype = C.c_int32
+    fn.argtypes = [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_int32)]
+    p = np.ascontiguousarray(pts, dtype=np.float64)
+    r = np.ascontiguousarray(ring, dtype=np.float64)
+    out = np.zeros(len(p), dtype=np.int32)
+    m = fn(p.ctypes.data_as(C.POINTER(C.c_double)), len(p), r.ctypes.data_as(C.POINTER(C.c_double)), len(r),
+           out.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert out[:m].tolist() == want
