@@ -1109,6 +1109,28 @@ static void floe_to_grid_info(sz_handle *h, cellrec **list, int *n, int *cap, in
     r->ix = sx - 1; r->iy = sy - 1; r->floe = floe; r->tx = -tx; r->ty = -ty; r->dx = ddx; r->dy = ddy; r->npts = 1;
 }
 
+/* in_bounds, coupling.jl:494-597: a periodic axis accepts every coordinate, a non-periodic one the closed grid extent */
+static inline int in_bounds(const sz_handle *h, double x, double y, int per_x, int per_y) {
+    return (per_x || (h->x0 <= x && x <= h->xf)) && (per_y || (h->y0 <= y && y <= h->yf));
+}
+/* find_center_cell_index, coupling.jl:466-470 (1-based like the reference; may lie outside 1..N+1) */
+static inline void center_cell_index(const sz_handle *h, double x, double y, int *xidx, int *yidx) {
+    *xidx = (int)floor((x - h->x0) / h->dx + 0.5) + 1;
+    *yidx = (int)floor((y - h->y0) / h->dy + 0.5) + 1;
+}
+/* test hooks for the truth tables of test_coupling.jl:165-195 */
+int32_t szo_test_in_bounds(sz_handle *h, double x, double y, int32_t per_x, int32_t per_y) {
+    return h ? in_bounds(h, x, y, per_x, per_y) : SZ_ERR_INVALID;
+}
+int32_t szo_test_find_center_cell_index(sz_handle *h, double x, double y, int32_t out[2]) {
+    if (!h || !out) return SZ_ERR_INVALID;
+    int xi, yi;
+    center_cell_index(h, x, y, &xi, &yi);
+    out[0] = xi;
+    out[1] = yi;
+    return SZ_OK;
+}
+
 static void coupling_one_floe(sz_handle *h, int64_t i) {
     const sz_config *c = &h->cfg;
     cellrec *rl = NULL;
@@ -1124,8 +1146,7 @@ static void coupling_one_floe(sz_handle *h, int64_t i) {
         double px = cos(a) * h->mcx[i][k] - sin(a) * h->mcy[i][k];
         double py = sin(a) * h->mcx[i][k] + cos(a) * h->mcy[i][k];
         double x = px + h->cx[i], y = py + h->cy[i];
-        int inb = (per_x || (h->x0 <= x && x <= h->xf)) && (per_y || (h->y0 <= y && y <= h->yf));
-        if (inb) { X[npoints] = x; Y[npoints] = y; npoints++; }
+        if (in_bounds(h, x, y, per_x, per_y)) { X[npoints] = x; Y[npoints] = y; npoints++; }
     }
     if (npoints == 0) {
         h->status[i] = SZ_STATUS_REMOVE; /* coupling.jl:1507-1508 */
@@ -1171,8 +1192,9 @@ static void coupling_one_floe(sz_handle *h, int64_t i) {
         double tx = tax + tpx + tox, ty = tay + tpy + toy;
         double trq = (-tx * sin(th) + ty * cos(th)) * rad;
         tot_x += tx; tot_y += ty; tot_trq += trq; tot_hflx += hfl;
-        { /* find_center_cell_index, coupling.jl:466-470 */
-            int xidx = (int)floor((x - h->x0) / h->dx + 0.5) + 1, yidx = (int)floor((y - h->y0) / h->dy + 0.5) + 1;
+        {
+            int xidx, yidx;
+            center_cell_index(h, x, y, &xidx, &yidx);
             floe_to_grid_info(h, &rl, &nrl, &caprl, i, xidx, yidx, tox, toy);
         }
     }

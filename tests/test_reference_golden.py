@@ -473,3 +473,44 @@ def test_which_vertices_match_points(oracle_lib, case):
     m = fn(p.ctypes.data_as(C.POINTER(C.c_double)), len(p), r.ctypes.data_as(C.POINTER(C.c_double)), len(r),
            out.ctypes.data_as(C.POINTER(C.c_int32)))
     assert out[:m].tolist() == want
+
+
+# ---- coupling helper truth tables, test_coupling.jl:165-195 (grid x in [-10, 10] dx 2, y in [-8, 8] dy 4) ------------
+def _helper_handle(oracle_lib):
+    h = capi.Handle(oracle_lib)
+    h.set_grid(10, 4, -10.0, 10.0, -8.0, 8.0)
+    return h
+
+
+def test_find_center_cell_index_table(oracle_lib):  # :167-178
+    import ctypes as C
+    h = _helper_handle(oracle_lib)
+    fn = oracle_lib.dll.szo_test_find_center_cell_index
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_int32)]
+    xpoints = [-10.5, -10, -10, -6.5, -6, -4, 10, 10.5, 12]
+    ypoints = [0.0, 6.0, -8.0, 4.5, 0.0, 5.0, -8.0, 0.0, 0.0]
+    xidx = [1, 1, 1, 3, 3, 4, 11, 11, 12]
+    yidx = [3, 5, 1, 4, 3, 4, 1, 3, 3]
+    out = (C.c_int32 * 2)()
+    for x, y, ix, iy in zip(xpoints, ypoints, xidx, yidx):
+        assert fn(h.h, x, y, out) == 0
+        assert (out[0], out[1]) == (ix, iy), (x, y)
+
+
+def test_in_bounds_truth_tables(oracle_lib):  # :180-195; in_bounds(x, y, grid, north/south kind, east/west kind)
+    import ctypes as C
+    h = _helper_handle(oracle_lib)
+    fn = oracle_lib.dll.szo_test_in_bounds
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32]
+    x = [-12, -10, -8, -6, 0, 4, 4, 10, 12, 12]
+    y = [5, -6, 4, 10, -10, 8, -8, -6, 4, 10]
+    open_open = [False, True, True, False, False, True, True, True, False, False]
+    periodic_open = [False, True, True, True, True, True, True, True, False, False]   # N-S periodic, E-W open
+    open_periodic = [True, True, True, False, False, True, True, True, True, False]   # N-S open, E-W periodic
+    for k in range(len(x)):
+        assert bool(fn(h.h, x[k], y[k], 0, 0)) == open_open[k]
+        assert bool(fn(h.h, x[k], y[k], 1, 0)) == open_periodic[k]   # per_x = E-W periodic
+        assert bool(fn(h.h, x[k], y[k], 0, 1)) == periodic_open[k]   # per_y = N-S periodic
+        assert bool(fn(h.h, x[k], y[k], 1, 1))
