@@ -49,13 +49,11 @@ def test_linear_momentum_is_conserved_through_collisions(name, oracle_lib):
     sim = host.Simulation(model, consts=consts, dt=10, n_dt=5000, coupling_settings=host.CouplingSettings(coupling_on=False),
                           backend=oracle_lib)
     q0 = quantities(sim.sync_host())
-    touched = False
     for t in range(5001):
         host.timestep_sim(sim, t)
-        if t % 500 == 0:
-            touched |= sim.h.counts()["n_overlap"] > 0
-    q1 = quantities(sim.sync_host())
-    assert touched, "the floes never collided"
+    final = sim.sync_host()
+    q1 = quantities(final)
+    assert final.overarea.sum() > 0, "the floes never collided"   # overarea only ever grows (collisions.jl:304)
     drift = 100.0 * np.abs(q1 - q0) / np.maximum(np.abs(q0), 1e-300)
     named = dict(zip(("energy", "x momentum", "y momentum", "angular momentum"), drift))
     assert drift[1] < 1e-6 and drift[2] < 1e-6, named
