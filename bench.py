@@ -10,7 +10,8 @@ reference default is every 10th), so the number is a lower bound for default set
                     [--floes 100000] [--npoints 1000] [--walls collision|periodic|shear]
 
 N = 1: BASELINE config 3 (100k floes, collisions + ocean/atmosphere coupling) on one B200.
-N > 1 (torchrun, one rank per GPU): weak scaling, every rank owns a slab of `--floes` floes.
+N > 1 (torchrun, one rank per GPU): weak scaling, every rank owns a slab of `--floes` floes; the slab data plane
+(partition, per-step halo update over peer memory, staleness test, rebuild) is the library's sz_slab_* API.
 --impl reference: the CPU oracle (the reference is pure Julia and cannot run in this image, so the
 reference arm is the oracle "port") on the host cores of rank 0, on a bounded sample of the workload.
 """
@@ -28,7 +29,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import szload  # noqa: E402,F401  (registers the package directory `subzero.jl_b200` as subzero_jl_b200)
 
-METRIC = "sim timesteps/sec (collisions + one-way ocean/atmosphere coupling + state update)"
+# `value` is FLOE-NORMALISED: simulated timesteps/s x floes_total / 100 000, i.e. timesteps/s of a 100k-floe field
+# (BASELINE config 3).  At N = 1 with the default 100k floes it IS timesteps/s; under weak scaling (100k floes per
+# GPU, N GPUs) it is the whole-job aggregate that grows with N, so value_N / (N value_1) is the parallel efficiency.
+METRIC = "sim timesteps/sec per 100k floes (collisions + one-way ocean/atmosphere coupling + state update; steps/s x floes_total/100000)"
+NORM_FLOES = 100000.0
 
 
 def parse():
@@ -46,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=25000, help="floes of the cpu_baseline sample field")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the one-step CUDA-vs-oracle comparison on the benchmark field")
     ap.add_argument("--two-way", action="store_true", help="also turn on two-way coupling (not part of the headline config)")
     ap.add_argument("--skin", type=float, default=3000.0, help="halo-list skin in metres (N > 1): lists stay valid while floes moved < skin/2")
     return ap.parse_args()
@@ -140,6 +146,50 @@ def oracle_steps_per_s(args, n_sample, steps, warmup, threads=0):
     return steps / dt, threads, c
 
 
+def parity_vs_oracle(args, prod, device, world):
+    """One timestep of the benchmark field (this rank's tile at N > 1) on the CUDA library and on the CPU oracle, phase by
+    phase, from the same initial state: pair sets and interaction rows bit-exact, state within 1e-9 (BASELINE north_star).
+    Runs AFTER the timed region; the oracle is the checker, not the thing measured."""
+    from subzero_jl_b200 import synth
+    from oracle import szo
+    try:
+        f = synth.make_field(args.floes, scale=args.scale, walls=args.walls if world == 1 else "collision", npoints=args.npoints,
+                             seed=args.floes, flow=args.flow)
+        hg = synth.setup_handle(f, prod, device=device)
+        ho = synth.setup_handle(f, szo.oracle(), threads=os.cpu_count())
+        for h in (hg, ho):
+            h.add_ghosts()
+            h.step_collisions()
+        pairs_equal = all(np.array_equal(hg.pairs(w), ho.pairs(w)) for w in range(4))
+        og, rg = hg.interactions()
+        oo, ro = ho.interactions()
+        rows_equal = bool(np.array_equal(og, oo) and np.array_equal(rg, ro))
+        for h in (hg, ho):
+            h.remove_ghosts()
+            h.step_coupling()
+            h.step_floe_properties(0)
+        a, b = hg.download_floes(mc=False), ho.download_floes(mc=False)
+        worst, worst_name = 0.0, ""
+        for name in ("centroid_x", "centroid_y", "alpha", "u", "v", "xi", "fxOA", "fyOA", "trqOA", "collision_force", "collision_trq",
+                     "overarea", "stress_accum", "stress_instant", "strain", "vert_xy", "mass", "moment", "height"):
+            x, y = np.asarray(getattr(a, name)), np.asarray(getattr(b, name))
+            scale = max(float(np.sqrt(np.mean(y * y))), 1e-300)
+            err = float(np.max(np.abs(x - y) / np.maximum(np.abs(y), scale))) if x.size else 0.0
+            if err > worst:
+                worst, worst_name = err, name
+        c = hg.counts()
+        out = {"pairs_equal": bool(pairs_equal), "rows_equal": rows_equal, "max_rel_err": worst, "max_rel_err_field": worst_name,
+               "tolerance": 1e-9, "ok": bool(pairs_equal and rows_equal and worst < 1e-9),
+               "n_floes": int(f.floes.n), "n_candidates": c["n_candidates"], "n_overlap": c["n_overlap"], "n_rows": c["n_rows"],
+               "how": "one timestep phase by phase on the benchmark field, CUDA library vs CPU oracle (candidate / filtered / overlap / "
+                      "fuse pair lists and interaction rows compared bit for bit, state fields relative to max(|ref|, rms))"}
+        hg.close()
+        ho.close()
+        return out
+    except Exception as e:  # evidence, not part of the measurement
+        return {"error": repr(e)}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -151,14 +201,18 @@ def run_reference(args, rank):
     n_sample = int(min(args.floes, max(n0, budget / ((args.steps + args.warmup) * per_floe))))
     n_sample = max(1000, (n_sample // 1000) * 1000)
     sps, cores, c = oracle_steps_per_s(args, n_sample, args.steps, args.warmup)
-    value = sps * n_sample / args.floes  # O(N) path: steps/s scale inversely with the floe count
+    world = max(1, args.gpus)
+    total = args.floes * world
+    steps_per_s = sps * n_sample / total  # O(N) path: steps/s scale inversely with the floe count
+    value = steps_per_s * total / NORM_FLOES  # the same floe-normalised unit as the GPU arm
     sample = ("oracle port (OpenMP, %d threads) on a %d-floe field of the same generator; steps/s scaled by %d/%d "
-              "to the %d-floe workload" % (cores, n_sample, n_sample, args.floes, args.floes))
+              "to the %d-floe workload (%d GPUs x %d floes), then floe-normalised like the GPU arm"
+              % (cores, n_sample, n_sample, total, total, world, args.floes))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, world), "floes_total": total, "steps_per_s": steps_per_s,
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -209,35 +263,52 @@ def main():
             os.close(saved_fd)
     prod = capi.product()
 
-    me = None
+    sl = None
+    gloo = None
     if world == 1:
         f = synth.make_field(args.floes, scale=args.scale, walls=args.walls, npoints=args.npoints, seed=args.floes, flow=args.flow)
         h = synth.setup_handle(f, prod, device=local_rank, two_way_coupling_on=int(args.two_way))
         fa0 = f.floes
     else:
-        # weak scaling: rank r generates the tile [r L, (r+1) L) x [0, L) and owns it; the neighbours' boundary
-        # floes become halo copies whose state is refreshed every step (slab.py)
+        # weak scaling: rank r generates the tile [r L, (r+1) L) x [0, L) and hands it to sz_slab_build; the library
+        # finds the neighbours' boundary floes (halo copies), wires the peer-memory arenas (cudaIpc) and from then on
+        # every sz_slab_step pushes this rank's boundary floes straight into its neighbours' stores
         from subzero_jl_b200 import slab
+        gloo = dist.new_group(backend="gloo")  # byte transport of the library's set-up / rebuild messages
         tile = synth.make_field(args.floes, scale=args.scale, walls="collision", npoints=args.npoints, seed=args.floes + rank)
         slab.shift_x(tile.floes, rank * tile.L)
+        tile.floes.id = rank * args.floes + np.arange(1, args.floes + 1, dtype=np.int64)  # unique over all tiles (collisions.jl:751-758)
         if args.flow == "converging":  # towards the centre of the whole (world x 1 tiles) domain
             tile.floes.u = -0.2 * (tile.floes.centroid_x - 0.5 * world * tile.L) / (world * tile.L)
             tile.floes.v = -0.2 * (tile.floes.centroid_y - 0.5 * tile.L) / tile.L
         ew = "shear" if args.walls in ("shear", "periodic") else "collision"
         f = synth.tiled_model(tile, world, ew)
-        me = slab.partition_tiles(tile.floes, rank, world, tile.L, world * tile.L if ew == "shear" else None, skin=args.skin)
-        h = synth.setup_handle(f, prod, device=local_rank)
-        me.attach(h)
-        me.make_buffers(torch.device("cuda", local_rank))
+        sl = slab.Slab(prod, f, world, rank=rank, group=gloo, devices=[local_rank], skin=args.skin, device=local_rank)
+        sl.set_edges(slab.tile_edges(world, tile.L, ew == "shear"))
+        sl.build([tile.floes], [rank * args.floes + np.arange(args.floes, dtype=np.int64)])
+        h = sl.handles[0]
         fa0 = tile.floes
     N, M, V = fa0.n, int(fa0.mc_offsets[-1]), int(fa0.vert_offsets[-1])
+    rebuild_s = []
+
+    def maybe_rebuild(t):
+        # the lists are valid while no owned floe travelled more than skin / 2; polled every 50 steps against skin / 4
+        # (one 8-byte all-reduce), so floes may move another skin / 4 in between
+        if sl is None or t % 50 != 49:
+            return
+        d = torch.tensor([sl.max_displacement()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        if float(d[0]) > 0.25 * args.skin:
+            t0 = time.perf_counter()
+            sl.rebuild()
+            rebuild_s.append(time.perf_counter() - t0)
 
     def do_step(t):
-        if me is not None:
-            # (measured at N = 2: starting the coupling before the exchange with sz_coupling_begin makes the small pack /
-            # NCCL / unpack kernels queue behind its blocks, 737 -> 689 steps/s; it pays only when uploads come first)
-            me.exchange()
-        h.step(t, True)
+        if sl is not None:
+            sl.step(t, True)  # unpack the neighbours' records, step, push mine: one C call, no NCCL on the data path
+            maybe_rebuild(t)
+        else:
+            h.step(t, True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,7 +340,9 @@ def main():
     if world > 1:
         dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
     wall_max, dev_max = float(t_rank[0]), float(t_rank[1])
-    value = args.steps / wall_max
+    steps_per_s = args.steps / wall_max
+    norm = N * world / NORM_FLOES
+    value = steps_per_s * norm
 
     # ---- end to end through the C ABI with pinned host buffers ------------------------------------------
     e2e = None
@@ -277,21 +350,18 @@ def main():
         host_fa = pin_floe_arrays(h.download_floes(mc=False))
         h2d = dyn_bytes(host_fa)
         def e2e_step(t, fused):
-            if fused and me is not None:
-                h.upload_state_begin(host_fa, True)      # H2D enqueued; the halo exchange waits for it on the device
-                h.coupling_begin()
-                me.exchange()
-                h.step_host(None, t, True, out=host_fa)  # kernels + overlapped D2H
+            if sl is not None:
+                sl.step_host([host_fa], t, True)         # uploads, publication to the neighbours, step, overlapped D2H
             elif fused:
                 h.step_host(host_fa, t, True)            # one C-ABI call: H2D + kernels + D2H, overlapped
             else:
                 h.upload_state(host_fa)                  # H2D: every per-floe scalar + ring coordinates
-                do_step(t)
+                h.step(t, True)
                 h.download_floes(into=host_fa, mc=False)  # D2H: the same state back
             return float(host_fa.collision_force[0, 0])
 
         def time_e2e(fused):
-            for t in range(2):
+            for t in range(3):
                 e2e_step(t, fused)
             barrier()
             t0 = time.perf_counter()
@@ -305,25 +375,63 @@ def main():
             return ne / float(te[0])
 
         d2h = h2d + host_fa.id.nbytes + host_fa.ghost_id.nbytes
-        sep = time_e2e(False)
+        sep = time_e2e(False) if sl is None else None
         # sz_step_host does not upload what the step overwrites before any read: collision_force / collision_trq
         # (zeroed by timestep_collisions!) and, on a step that runs the coupling, fxOA / fyOA / trqOA / hflx_factor
         h2d_fused = (h2d - host_fa.collision_force.nbytes - host_fa.collision_trq.nbytes - host_fa.fxOA.nbytes
                      - host_fa.fyOA.nbytes - host_fa.trqOA.nbytes - host_fa.hflx_factor.nbytes)
-        e2e = {"value": time_e2e(True), "unit": "steps/s", "h2d_bytes_per_step": int(h2d_fused), "d2h_bytes_per_step": int(d2h),
+        e2e_sps = time_e2e(True)
+        e2e = {"value": e2e_sps * norm, "unit": "steps/s", "steps_per_s": e2e_sps,
+               "h2d_bytes_per_step": int(h2d_fused), "d2h_bytes_per_step": int(d2h),
                "call": ("sz_step_host on pinned host arrays (upload of every per-floe input scalar + rings, step, download "
                         "of the whole state; copies overlap the kernels)" if world == 1 else
-                        "sz_upload_state_begin + halo exchange + sz_step_host(in = NULL) on pinned host arrays, every rank"),
+                        "sz_slab_step_host on pinned host arrays of every rank's local list (uploads, publication of the "
+                        "uploaded boundary floes to the neighbours, step, overlapped downloads)"),
                "separate_calls_steps_per_s": sep}
 
+    # ---- parity of the benchmark field against the oracle (one step, after the timed region) --------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_vs_oracle(args, prod, local_rank, world)
+
     halo = None
-    if me is not None:
-        disp = me.max_displacement()
-        hs = torch.tensor([me.local.n - int(me.owned.sum()), sum(me.nbytes[0::2]), disp], dtype=torch.float64, device="cuda")
-        dist.all_reduce(hs, op=dist.ReduceOp.MAX)
-        halo = {"halo_floes_max": int(hs[0]), "send_bytes_per_step_max": int(hs[1]), "skin_m": args.skin,
-                "max_displacement_m": float(hs[2]), "lists_stale": bool(hs[2] > 0.5 * args.skin),
-                "exchange": "sz_halo_pack_on -> NCCL isend/irecv (torch.distributed) -> sz_halo_unpack_on, stream-ordered, every step"}
+    if sl is not None:
+        # transport check: every halo copy must carry its owner's state bit for bit.  Each rank publishes a checksum per
+        # owned boundary floe, the holders of copies compare (outside the timed region, gloo).
+        st = sl.stats()
+        g, o = sl.local_index(0)
+        sl.refresh_halo()  # collective: halo copies := their owners' current state
+        fa = h.download_floes(mc=False)
+        key = np.stack([fa.centroid_x, fa.centroid_y, fa.u, fa.v, fa.xi, fa.alpha, fa.height], axis=1).view(np.uint64)
+        chk = np.bitwise_xor.reduce(key * np.arange(1, 8, dtype=np.uint64)[None, :], axis=1)
+        mine = {int(a): int(b) for a, b in zip(g[o == rank], chk[o == rank])} if False else None
+        tables = [None] * world
+        own_mask = o == rank
+        dist.all_gather_object(tables, (g[own_mask], chk[own_mask]), group=gloo)
+        bad = 0
+        for src in range(world):
+            if src == rank:
+                continue
+            sel = np.nonzero(o == src)[0]
+            if len(sel) == 0:
+                continue
+            gs, cs = tables[src]
+            pos = np.searchsorted(gs, g[sel])
+            ok = (pos < len(gs)) & (gs[np.minimum(pos, len(gs) - 1)] == g[sel])
+            bad += int((~ok).sum()) + int((cs[pos[ok]] != chk[sel[ok]]).sum())
+        hs = torch.tensor([st["halo_floes"], st["send_bytes_per_step"], sl.max_displacement(), bad, st["rebuilds"],
+                           sum(rebuild_s)], dtype=torch.float64, device="cuda")
+        hmax = hs.clone()
+        dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hs, op=dist.ReduceOp.SUM)
+        assert int(hs[3]) == 0, "halo copies differ from their owners' state on %d floes" % int(hs[3])
+        halo = {"halo_floes_max": int(hmax[0]), "send_bytes_per_step_max": int(hmax[1]), "skin_m": args.skin,
+                "max_displacement_m": float(hmax[2]), "lists_stale": bool(hmax[2] > 0.5 * args.skin),
+                "rebuilds": int(hmax[4]), "rebuild_seconds_total_max": float(hmax[5]),
+                "halo_copies_equal_owner_state": True,
+                "exchange": "sz_slab_step: k_slab_unpack (wait for the neighbours' flag, scatter) -> step -> k_slab_push (8 doubles + "
+                            "ring per boundary floe straight into the neighbours' arenas over NVLink, cudaIpc-mapped) — no NCCL "
+                            "call, no pack / unpack round trip; NCCL only for this script's barrier / all-reduce of the timings"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -340,10 +448,13 @@ def main():
     per = phase / args.steps
     P, C = c["n_pairs"], c["n_rows"]
     nbar = V / max(N, 1)
+    Pc = c["n_candidates"]
     kernels = {
         "k_coupling": (per[4], 16.0 * M + 120.0 * N + 40.0 * (g.Nx + 1) * (g.Ny + 1)),
         "k_narrow": (per[2], P * (16.0 * (2 * nbar) + 128.0) + 112.0 * C),
         "k_update": (per[5], 440.0 * N + 32.0 * V + 56.0 * C),
+        "broad": (per[1], 56.0 * N + 8.0 * Pc),   # SURVEY §8(d) K1 + K2
+        "rows": (per[3], 112.0 * C + 24.0 * N),
     }
     dom = max(kernels, key=lambda k: kernels[k][0])
     kms, kbytes = kernels[dom]
@@ -360,7 +471,8 @@ def main():
                          "contract asks for it, roofline.fp64 gives the FP64 view (profiles/README.md)",
              "k_coupling": "streams 16 B per Monte-Carlo point once (ncu: 962 MB = the algorithmic bytes) through a cp.async ring; FP64 pipe "
                            "54 % busy; inside sz_step it runs on a second stream beside the broad phase",
-             "k_update": ""}
+             "k_update": "", "broad": "chain of small dependent kernels (uniform grid, neighbour lists, image filter): latency bound",
+             "rows": "per-floe row assembly + sequential sums in the reference's row order (deterministic, no float atomics)"}
     roofline = {"kernel": dom if dom != "k_narrow" else "k_narrow_ab", "bound": "hbm", "achieved": achieved, "peak": hbm,
                 "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "note": notes[dom],
                 "all_kernels": {k: {"ms": v[0], "algorithmic_bytes": v[1], "GB/s": (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0),
@@ -399,9 +511,9 @@ def main():
         "metric": METRIC, "value": value * 1.0, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-        "floes_total": N * world, "floe_steps_per_s": value * N * world,
-        "contacts_per_s": value * c["n_overlap"] * world, "candidate_pairs_per_s": value * c["n_candidates"] * world,
-        "mc_points_per_s": value * M * world,
+        "steps_per_s": steps_per_s, "floes_total": N * world, "floe_steps_per_s": steps_per_s * N * world,
+        "contacts_per_s": steps_per_s * c["n_overlap"] * world, "candidate_pairs_per_s": steps_per_s * c["n_candidates"] * world,
+        "mc_points_per_s": steps_per_s * M * world, "parity": parity,
         "device_ms_per_step": 1e3 * dev_max / args.steps,
         "counts": {k: c[k] for k in ("n_init", "n_candidates", "n_pairs", "n_overlap", "n_rows", "n_mc", "n_vertices")},
         "halo": halo, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -256,6 +256,76 @@ int32_t SZ_FN(coupling_begin)(sz_handle *h);
 int32_t SZ_FN(halo_pack_on)(sz_handle *h, int32_t list, void *dst, int64_t capacity_bytes, void *stream);
 int32_t SZ_FN(halo_unpack_on)(sz_handle *h, int32_t list, const void *src, int64_t bytes, void *stream);
 
+/* ---- slab decomposition INSIDE the library ("multi-GPU is internal to one handle"; §8(e)) -------
+ * A sz_slab drives the `n_local` of `world` slab ranks that live in this process:
+ *   n_local == world  one host process (the Julia shim) drives every GPU of the box;
+ *   n_local == 1      one process per GPU (torchrun / MPI): `alltoallv` moves the set-up / rebuild messages.
+ * Each rank is a sz_handle on its own device holding its owned floes plus halo copies of the neighbours' floes,
+ * sorted by GLOBAL floe index, so pair orientation, row order and the canonical image pair are those of one handle
+ * and owned results are bit-identical to the single-GPU run (the reference is single-process: collisions.jl:734-864
+ * sees one floe list).  The library does the partition (sz_slab_build), the per-step halo update, the staleness
+ * test and the rebuild with migration of ownership (sz_slab_rebuild).
+ *
+ * Per-step data plane (CUDA build): no NCCL call and no pack / unpack round trip.  After the state update ONE
+ * kernel per rank writes the 8 doubles + ring points of its boundary floes straight into the neighbours' receive
+ * arenas over NVLink (peer-mapped memory in one process, cudaIpc handles between processes) and raises a flag
+ * there; the neighbour's next step begins with a kernel that waits for the flag and scatters the records into its
+ * store.  Arenas are double-buffered by step parity, so no rank waits for a neighbour's acknowledgement on the
+ * critical path.  The oracle build moves the same records through host memory / `alltoallv`.
+ *
+ * alltoallv (MPI_Alltoallv semantics on bytes, collective over all `world` processes; only used when
+ * n_local == 1): send block d = bytes [send_off[d], send_off[d+1]) of `send` goes to rank d, the block from rank s
+ * arrives at [recv_off[s], recv_off[s+1]) of `recv`.  Return 0 on success. */
+typedef struct sz_slab sz_slab;
+typedef int32_t (*sz_alltoallv_fn)(void *ctx, const void *send, const int64_t *send_off, void *recv,
+                                   const int64_t *recv_off);
+#define SZ_SLAB_MAX_PARTNERS 16
+int32_t SZ_FN(slab_create)(const sz_config *cfg, int32_t world, int32_t rank_first, int32_t n_local,
+                           const int32_t *devices /* [n_local] CUDA ordinals */, double skin,
+                           sz_alltoallv_fn alltoallv, void *ctx, sz_slab **out);
+void SZ_FN(slab_destroy)(sz_slab *s);
+const char *SZ_FN(slab_last_error)(sz_slab *s);
+/* The handle of local rank k (0 <= k < n_local) for every per-handle call of this header (timings, counts,
+ * downloads, interactions ...).  Owned by the slab. */
+int32_t SZ_FN(slab_handle)(sz_slab *s, int32_t k, sz_handle **out);
+/* Model description, replicated on every rank (same arguments as the per-handle calls). */
+int32_t SZ_FN(slab_set_grid)(sz_slab *s, int32_t Nx, int32_t Ny, double x0, double xf, double y0, double yf);
+int32_t SZ_FN(slab_set_fields)(sz_slab *s, const double *ocean_u, const double *ocean_v, const double *ocean_hflx,
+                               const double *atmos_u, const double *atmos_v);
+int32_t SZ_FN(slab_set_domain)(sz_slab *s, const int32_t kinds[4], const double vals[4], const double uv[8],
+                               const double rect[16], int32_t n_topo, const int64_t *topo_offsets,
+                               const double *topo_xy, const double *topo_centroid, const double *topo_rmax);
+/* Slab boundaries in x, edges[world+1] ascending; slab r = [edges[r], edges[r+1]).  Without this call
+ * sz_slab_build takes equal-count quantiles of the centroids it is given (n_local == world only). */
+int32_t SZ_FN(slab_set_edges)(sz_slab *s, const double *edges);
+/* Collective.  floes[k] / gidx[k]: the floes local rank k brings (full records incl. Monte-Carlo points) and their
+ * 0-based global indices (unique over all ranks; ids must be unique too, NULL id = gidx + 1).  ANY initial
+ * distribution works: a single-process host hands its whole list to local rank 0 and n = 0 to the others; every
+ * floe migrates to the slab its centroid lies in, then the halo lists are built. */
+int32_t SZ_FN(slab_build)(sz_slab *s, const sz_floe_soa *const *floes, const int64_t *const *gidx);
+/* Local list of rank k after a build / rebuild: n floes (owned + halo, ascending global index). */
+int32_t SZ_FN(slab_local_count)(sz_slab *s, int32_t k, int64_t *n, int64_t *n_owned);
+int32_t SZ_FN(slab_local_index)(sz_slab *s, int32_t k, int64_t *gidx /* [n] */, int32_t *owner /* [n] */);
+/* One timestep on every local rank (halo update + sz_step).  All ranks of the decomposition must make the same
+ * sequence of sz_slab_step / sz_slab_step_host / sz_slab_rebuild calls. */
+int32_t SZ_FN(slab_step)(sz_slab *s, int64_t tstep, int32_t do_coupling);
+/* The same on host arrays of each rank's LOCAL list (layout of sz_slab_local_index): upload, halo update on top
+ * of the uploaded (stale) halo copies, step, download.  in[k] == out[k] is allowed. */
+int32_t SZ_FN(slab_step_host)(sz_slab *s, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in,
+                              sz_floe_soa *const *out);
+/* Largest distance an owned floe of the local ranks travelled since the lists were built (periodic wrap taken out);
+ * the lists are valid while it stays below skin / 2.  No device synchronisation (the step reads it back). */
+int32_t SZ_FN(slab_max_displacement)(sz_slab *s, double *metres);
+/* Collective: migrate floes whose centroid left their slab (full record incl. Monte-Carlo points) and renew the
+ * halo lists.  With n_local == world sz_slab_step calls it by itself when the displacement exceeds skin / 2. */
+int32_t SZ_FN(slab_rebuild)(sz_slab *s);
+/* Collective: bring every halo copy up to date with its owner's CURRENT state without stepping (between steps a copy
+ * holds what its holder's own update made of it; only owned floes are results).  For host-side consumers of whole
+ * local lists and for transport checks. */
+int32_t SZ_FN(slab_refresh_halo)(sz_slab *s);
+/* bytes pushed to the neighbours per step by local rank k, number of halo copies it holds, rebuilds so far */
+int32_t SZ_FN(slab_stats)(sz_slab *s, int32_t k, int64_t *send_bytes, int64_t *halo_floes, int64_t *rebuilds);
+
 /* ---- geometry service (test hook; also what SURVEY §8(f) rank 2 reuses) ---------------------- */
 /* Clip two closed rings; regions are written as consecutive closed rings into out_xy
  * (capacity cap_points points), region r = points [out_offsets[r], out_offsets[r+1]).

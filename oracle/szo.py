@@ -17,8 +17,11 @@ _oracle = None
 
 
 def build(force=False):
-    src = [os.path.join(HERE, f) for f in ("szo.c", "szo_geom.h")] + [
-        os.path.join(os.path.dirname(HERE), "include", "subzero_b200.h")]
+    root = os.path.dirname(HERE)
+    src = [os.path.join(HERE, f) for f in ("szo.c", "szo_geom.h", "Makefile")] + [
+        os.path.join(root, "include", "subzero_b200.h"),
+        os.path.join(root, "subzero.jl_b200", "csrc", "sz_slab.cpp"),  # the product's slab host logic on the oracle's ABI
+        os.path.join(root, "subzero.jl_b200", "csrc", "sz_slab_backend.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB

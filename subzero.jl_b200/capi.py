@@ -127,6 +127,27 @@ class Library:
         "eulerian_data": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int32, c_i32_p, c_double_p]),
         "clip_polygons": (C.c_int32, [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                       C.c_int32, C.c_int32, c_i32_p, c_double_p, c_double_p]),
+        # slab decomposition inside the library
+        "slab_create": (C.c_int32, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, c_i32_p, C.c_double, C.c_void_p,
+                                    C.c_void_p, C.POINTER(C.c_void_p)]),
+        "slab_destroy": (None, [C.c_void_p]),
+        "slab_last_error": (C.c_char_p, [C.c_void_p]),
+        "slab_handle": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+        "slab_set_grid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_double] * 4),
+        "slab_set_fields": (C.c_int32, [C.c_void_p] + [c_double_p] * 5),
+        "slab_set_domain": (C.c_int32, [C.c_void_p, c_i32_p, c_double_p, c_double_p, c_double_p,
+                                        C.c_int32, c_i64_p, c_double_p, c_double_p, c_double_p]),
+        "slab_set_edges": (C.c_int32, [C.c_void_p, c_double_p]),
+        "slab_build": (C.c_int32, [C.c_void_p, C.POINTER(C.POINTER(FloeSoA)), C.POINTER(c_i64_p)]),
+        "slab_local_count": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p]),
+        "slab_local_index": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i32_p]),
+        "slab_step": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32]),
+        "slab_step_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.POINTER(FloeSoA)),
+                                       C.POINTER(C.POINTER(FloeSoA))]),
+        "slab_max_displacement": (C.c_int32, [C.c_void_p, c_double_p]),
+        "slab_rebuild": (C.c_int32, [C.c_void_p]),
+        "slab_refresh_halo": (C.c_int32, [C.c_void_p]),
+        "slab_stats": (C.c_int32, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p, c_i64_p]),
     }
 
     def __init__(self, path, prefix="sz_"):
@@ -231,8 +252,46 @@ class FloeArrays:
         return list(self.ghost_index[self.ghost_offsets[i]:self.ghost_offsets[i + 1]])
 
 
+def marshal_fields(Nx, Ny, arrays):
+    """Five (Nx+1, Ny+1) arrays indexed [x, y] -> flat arrays with element [ix + (Nx+1) iy]."""
+    out = []
+    for a in arrays:
+        a = np.asarray(a, dtype=np.float64)
+        assert a.shape == (Nx + 1, Ny + 1), (a.shape, Nx, Ny)
+        out.append(np.asfortranarray(a).ravel(order="F"))
+    return out
+
+
+def marshal_domain(kinds, vals, uv, rect, topo_rings=(), topo_centroid=None, topo_rmax=None):
+    """Arguments of sz_set_domain / sz_slab_set_domain behind the handle pointer (arrays are kept alive by the tuple)."""
+    kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(8)
+    rect = np.ascontiguousarray(rect, dtype=np.float64).reshape(16)
+    nt = len(topo_rings)
+    offs = np.zeros(nt + 1, dtype=np.int64)
+    for k, r in enumerate(topo_rings):
+        offs[k + 1] = offs[k] + len(r)
+    xy = (np.concatenate([np.asarray(r, dtype=np.float64) for r in topo_rings])
+          if nt else np.zeros((0, 2)))
+    xy = np.ascontiguousarray(xy, dtype=np.float64)
+    cen = np.ascontiguousarray(topo_centroid if nt else np.zeros((0, 2)), dtype=np.float64)
+    rm = np.ascontiguousarray(topo_rmax if nt else np.zeros(0), dtype=np.float64)
+    keep = (kinds, vals, uv, rect, offs, xy, cen, rm)
+    return (kinds.ctypes.data_as(c_i32_p), _dp(vals), _dp(uv), _dp(rect), nt, _ip(offs), _dp(xy), _dp(cen), _dp(rm)), keep
+
+
 class Handle:
     """RAII wrapper of sz_handle for one Library."""
+
+    @classmethod
+    def borrow(cls, lib, ptr, Nx=None, Ny=None):
+        """A non-owning wrapper of a handle that belongs to a sz_slab."""
+        self = cls.__new__(cls)
+        self.lib, self.cfg, self.h, self.borrowed = lib, None, C.c_void_p(ptr), True
+        if Nx is not None:
+            self.Nx, self.Ny = Nx, Ny
+        return self
 
     def __init__(self, lib, cfg=None, **overrides):
         self.lib = lib
@@ -247,9 +306,9 @@ class Handle:
             raise SubzeroError(rc, "sz_create failed (library %s)" % lib.path)
 
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "borrowed", False):
             self.lib.destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -268,11 +327,7 @@ class Handle:
         self.Nx, self.Ny = Nx, Ny
 
     def set_fields(self, ocean_u, ocean_v, ocean_hflx, atmos_u, atmos_v):
-        arrs = []
-        for a in (ocean_u, ocean_v, ocean_hflx, atmos_u, atmos_v):
-            a = np.asarray(a, dtype=np.float64)
-            assert a.shape == (self.Nx + 1, self.Ny + 1), (a.shape, self.Nx, self.Ny)
-            arrs.append(np.asfortranarray(a).ravel(order="F"))  # element [ix + (Nx+1) iy]
+        arrs = marshal_fields(self.Nx, self.Ny, (ocean_u, ocean_v, ocean_hflx, atmos_u, atmos_v))
         self._ck(self.lib.set_fields(self.h, *[_dp(a) for a in arrs]))
 
     def set_temperatures(self, ocean_temp, atmos_temp):
@@ -300,21 +355,9 @@ class Handle:
         return cell[:n.value], floe[:n.value], vals[:n.value]
 
     def set_domain(self, kinds, vals, uv, rect, topo_rings=(), topo_centroid=None, topo_rmax=None):
-        kinds = np.ascontiguousarray(kinds, dtype=np.int32)
-        vals = np.ascontiguousarray(vals, dtype=np.float64)
-        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(8)
-        rect = np.ascontiguousarray(rect, dtype=np.float64).reshape(16)
-        nt = len(topo_rings)
-        offs = np.zeros(nt + 1, dtype=np.int64)
-        for k, r in enumerate(topo_rings):
-            offs[k + 1] = offs[k] + len(r)
-        xy = (np.concatenate([np.asarray(r, dtype=np.float64) for r in topo_rings])
-              if nt else np.zeros((0, 2)))
-        xy = np.ascontiguousarray(xy, dtype=np.float64)
-        cen = np.ascontiguousarray(topo_centroid if nt else np.zeros((0, 2)), dtype=np.float64)
-        rm = np.ascontiguousarray(topo_rmax if nt else np.zeros(0), dtype=np.float64)
-        self._ck(self.lib.set_domain(self.h, kinds.ctypes.data_as(c_i32_p), _dp(vals), _dp(uv),
-                                     _dp(rect), nt, _ip(offs), _dp(xy), _dp(cen), _dp(rm)))
+        args, keep = marshal_domain(kinds, vals, uv, rect, topo_rings, topo_centroid, topo_rmax)
+        self._ck(self.lib.set_domain(self.h, *args))
+        del keep
 
     def get_domain(self):
         vals, rect = np.zeros(4), np.zeros(16)

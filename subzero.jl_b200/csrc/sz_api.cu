@@ -9,7 +9,10 @@
 #include <cstring>
 #include <vector>
 
+#include <unistd.h>
+
 #include "sz_common.cuh"
+#include "sz_slab_backend.h"
 
 #define NEV 8
 #define SZ_GRAPH_MAX_FLOES 32768  // sz_step replays a CUDA graph up to this field size (see step_impl)
@@ -30,8 +33,46 @@ struct SvcBuf {
         cap_vi, cap_vo, cap_ki, cap_ko, cap_sort;
 };
 
+// Host buffers of one sz_step_host call (see enqueue_uploads / enqueue_downloads below).
+struct HostIO {
+    const sz_floe_soa *in;
+    sz_floe_soa *out;
+};
+
+// slab decomposition (sz_slab_*): this rank's exchange lists, its receive arena and the partners' arenas
+struct SlabState {
+    bool on;
+    int rank, n_partners;
+    SlabDev dev;
+    int *d_send_idx, *d_recv_idx;
+    long long *d_send_voff, *d_recv_voff;
+    unsigned char *d_owned;
+    double *d_refx, *d_refy;
+    unsigned char *arena;      // flags + double-buffered staging, written by the partners
+    size_t arena_bytes;
+    std::vector<void *> ipc_open;  // partners' arenas mapped from other processes
+    std::vector<long long> send_bytes;  // per partner
+    int epoch;      // epoch the next step consumes
+    int pushed;     // last epoch published to the partners
+    int max_send, max_recv;
+    long long send_bytes_total;
+};
+
+// the step in flight between step_enqueue and step_finish
+struct StepCur {
+    int32_t do_coupling;
+    HostIO io;
+    bool has_io;
+    bool keep_ghosts;       // repeat from the collisions, the ghosts of the failed attempt stay
+    bool coupling_only;     // repeat from the (two-way) coupling: the collisions of this step are complete
+    bool slab_host_mode;    // slab rank stepping on host arrays: publish at the start, not behind the update
+    int attempt;
+};
+
 struct sz_handle {
     sz_config cfg;
+    SlabState slab;
+    StepCur cur;
     SvcBuf svc;
     char err[512];
     Launch L;
@@ -65,6 +106,7 @@ struct sz_handle {
     size_t field_n;
     Counters *h_cnt;  // pinned mirror
     Counters last;    // counters of the last collision step
+    Counters last_ok_collisions;  // ... kept while a coupling-only repair repeats the rest of the step
     int n_rows_host;
     cudaEvent_t ev[NEV];
     double ms[8];
@@ -276,6 +318,12 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     memset(&h->CB, 0, sizeof(h->CB));
     memset(&h->svc, 0, sizeof(h->svc));
     h->n_crec_host = 0;
+    h->slab.on = false; h->slab.rank = 0; h->slab.n_partners = 0;
+    memset(&h->slab.dev, 0, sizeof(h->slab.dev));
+    h->slab.d_send_idx = h->slab.d_recv_idx = nullptr; h->slab.d_send_voff = h->slab.d_recv_voff = nullptr;
+    h->slab.d_owned = nullptr; h->slab.d_refx = h->slab.d_refy = nullptr; h->slab.arena = nullptr; h->slab.arena_bytes = 0;
+    h->slab.epoch = 1; h->slab.pushed = 0; h->slab.max_send = h->slab.max_recv = 0; h->slab.send_bytes_total = 0;
+    memset(&h->cur, 0, sizeof(h->cur));
     memset(&h->hD, 0, sizeof(h->hD));
     memset(&h->P, 0, sizeof(h->P));
     memset(&h->last, 0, sizeof(h->last));
@@ -346,6 +394,13 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.order_cls); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
     dfree(h->d_hl_idx); dfree(h->d_hl_voff);
+    for (void *p : h->slab.ipc_open) cudaIpcCloseMemHandle(p);
+    h->slab.ipc_open.clear();
+    {
+        SlabState &Bs = h->slab;
+        dfree(Bs.d_send_idx); dfree(Bs.d_recv_idx); dfree(Bs.d_send_voff); dfree(Bs.d_recv_voff); dfree(Bs.d_owned);
+        dfree(Bs.d_refx); dfree(Bs.d_refy); dfree(Bs.arena);
+    }
     {
         SvcBuf &V = h->svc;
         dfree(V.pairs); dfree(V.area); dfree(V.inter); dfree(V.big); dfree(V.xg); dfree(V.yg); dfree(V.data); dfree(V.rec_area);
@@ -581,7 +636,11 @@ static int32_t upload_scalars(sz_handle *h, const sz_floe_soa *s, int n) {
     return SZ_OK;
 }
 
-extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
+// mc_src == NULL: Monte-Carlo points come from s->mc_x / s->mc_y (layout s->mc_offsets).
+// mc_src != NULL (sz_slab_rebuild): the points of floe i are already on the device — at offset mc_src[i] of the resident
+// array when mc_src[i] >= 0 — or arrive in the COMPACT host arrays s->mc_x / s->mc_y at offset -1 - mc_src[i]
+// (n_extra points in total: migrants); the new array is gathered on the device.
+static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64_t *mc_src, int64_t n_extra) {
     if (!h || !s || s->n < 0 || s->n_init < 0 || s->n_init > s->n) return fail(h, SZ_ERR_INVALID, "upload_floes: bad sizes");
     if (s->n > 0 && (!s->centroid_x || !s->centroid_y || !s->area || !s->rmax || !s->vert_offsets || !s->vert_xy))
         return fail(h, SZ_ERR_INVALID, "upload_floes: geometry arrays are required");
@@ -628,7 +687,14 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
         if (rc) return rc;
     }
     Store &S = h->S;
-    if (M > S.cap_mc || !S.mc) {
+    double2 *old_mc = nullptr;
+    if (mc_src) {  // keep the resident points until the new array is gathered
+        old_mc = S.mc;
+        S.mc = nullptr;
+        CK(dalloc(&S.mc, (size_t)M));
+        S.cap_mc = M;
+        h->gen++;
+    } else if (M > S.cap_mc || !S.mc) {
         dfree(S.mc);
         CK(dalloc(&S.mc, (size_t)M));
         S.cap_mc = M;
@@ -676,7 +742,26 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     if (s->mc_offsets) for (int i = 0; i <= n_init; ++i) mo[i] = s->mc_offsets[i];
     CK(cudaMemcpyAsync(S.mc_off, mo.data(), sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyHostToDevice, st));
     long long Mi = mo[n_init];
-    if (Mi > 0) {
+    if (mc_src) {
+        double2 *extra = nullptr;
+        long long *dsrc = nullptr;
+        double *tx = nullptr, *ty = nullptr;
+        if (n_extra > 0) {
+            CK(dalloc(&tx, (size_t)n_extra)); CK(dalloc(&ty, (size_t)n_extra)); CK(dalloc(&extra, (size_t)n_extra));
+            CK(cudaMemcpyAsync(tx, s->mc_x, sizeof(double) * n_extra, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ty, s->mc_y, sizeof(double) * n_extra, cudaMemcpyHostToDevice, st));
+            szk_interleave(h->L, tx, ty, extra, n_extra);
+        }
+        CK(dalloc(&dsrc, (size_t)n_init + 1));
+        std::vector<long long> hs((size_t)n_init + 1, 0);
+        for (int i = 0; i < n_init; ++i) hs[i] = mc_src[i];
+        CK(cudaMemcpyAsync(dsrc, hs.data(), sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyHostToDevice, st));
+        szk_mc_regather(h->L, S.mc, S.mc_off, old_mc, extra, dsrc, n_init);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        cudaFree(tx); cudaFree(ty); cudaFree(extra); cudaFree(dsrc);
+        if (old_mc) cudaFree(old_mc);
+    } else if (Mi > 0) {
         double *tx = nullptr, *ty = nullptr;
         CK(dalloc(&tx, (size_t)Mi)); CK(dalloc(&ty, (size_t)Mi));
         CK(cudaMemcpyAsync(tx, s->mc_x, sizeof(double) * Mi, cudaMemcpyHostToDevice, st));
@@ -698,9 +783,12 @@ extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) {
     h->h_vcount = vcount;
     h->h_mc_off = mo;
     h->have_floes = true;
+    h->slab.on = false;  // a new floe list: the halo lists must be configured again
     h->gen++;
     return SZ_OK;
 }
+
+extern "C" int32_t sz_upload_floes(sz_handle *h, const sz_floe_soa *s) { return upload_floes_impl(h, s, nullptr, 0); }
 
 // Refresh the dynamic state of the resident floes (same floe list and ring sizes as the last
 // sz_upload_floes); Monte-Carlo points, ids and ghost links stay resident.
@@ -1027,10 +1115,6 @@ extern "C" int32_t sz_step_floe_properties(sz_handle *h, int64_t tstep) {
 // a step that runs the coupling (coupling.jl:1583-1586) and are uploaded (group 3) only when it does not.
 // The downloads go to stream_dn as soon as the producing kernel is done (collision totals after the row
 // assembly, coupling outputs after the join, the rest after the update).
-struct HostIO {
-    const sz_floe_soa *in;
-    sz_floe_soa *out;
-};
 
 static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s, bool coupling_runs) {
     Store &S = h->S;
@@ -1099,47 +1183,69 @@ static int32_t enqueue_downloads(sz_handle *h, sz_floe_soa *s, int stage) {
     return SZ_OK;
 }
 
-// One whole timestep enqueued back to back; a single host synchronisation at the end.
-static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
+// ---- slab hooks (sz_slab_*): what a slab rank adds to a timestep -----------------------------------------------------
+// before the first kernel that reads a halo copy: wait for the partners' records of this epoch and scatter them
+static void slab_unpack(sz_handle *h) {
+    if (!h->slab.on) return;
+    szk_slab_unpack(h->L, h->S, h->slab.dev, h->slab.epoch, h->slab.max_recv);
+}
+// publish my boundary floes as epoch `e` (and measure the displacement of the owned floes)
+static void slab_push(sz_handle *h, int e) {
+    if (!h->slab.on) return;
+    szk_slab_push(h->L, h->S, h->slab.dev, e, h->slab.max_send);
+}
+
+// One whole timestep enqueued back to back; a single host synchronisation at the end (step_finish).
+// everything a timestep enqueues, from add_ghosts! to the read-back of the counters (no host synchronisation)
+static int32_t step_enqueue_direct(sz_handle *h) {
     cudaStream_t st = h->L.stream;
+    const StepCur &cur = h->cur;
+    const int32_t do_coupling = cur.do_coupling;
+    const HostIO *io = cur.has_io ? &cur.io : nullptr;
     const bool periodic = h->hD.kind[2] == SZ_BOUNDARY_PERIODIC || h->hD.kind[0] == SZ_BOUNDARY_PERIODIC;
-    if (io && io->in) {
-        int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
-        if (rc) return rc;
-    }
-    // A collision-phase buffer overflow is repaired and the step repeated FROM THE COLLISIONS: the ghosts of the failed
-    // attempt are complete and stay (every kernel after the overflow returned at once, including the ghost removal).
-    // Running add_ghosts! again would start from parents the first pass has already wrapped into the domain and can
-    // number the images of a corner floe in another order than a clean step does (rows and totals then differ from the
-    // reference in their last bit).
-    bool keep_ghosts = false;
-    // everything a timestep enqueues, from add_ghosts! to the read-back of the counters (no host synchronisation)
-    auto enqueue = [&]() -> int32_t {
+    const bool fork = do_coupling && !h->cfg.two_way_coupling_on;
+    auto fork_coupling = [&]() {
+        // fork: coupling only needs the floe state after add_ghosts! wrapped parents into the domain; it
+        // reads nothing the collision kernels write, so it runs beside them on a low-priority stream and
+        // fills the issue slots the latency-bound narrow phase leaves idle
+        cudaEventRecord(h->ev_fork, st);
+        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+        Launch L2 = h->L;
+        L2.stream = h->stream2;
+        // measured (profiles/README.md): capping coupling to 2-4 resident blocks per SM so that it runs beside the
+        // narrow phase slows the latter more than the overlap gains; it fills the GPU during the broad phase
+        L2.coupling_blocks_per_sm = 0;
+        sz_record(L2, h->ev_c0, h->stream2);
+        szk_coupling(L2, h->S, h->P);
+        sz_record(L2, h->ev_c1, h->stream2);
+        cudaEventRecord(h->ev_join, h->stream2);
+    };
+    if (!cur.coupling_only) {
         if (io) {
             // add_ghosts! copies every scalar of a parent into its ghost (collisions.jl:1017-1047): with periodic
             // walls the step starts when all uploads have landed
             for (int g = 0; g < (periodic ? 4 : 1); ++g) CK(cudaStreamWaitEvent(st, h->ev_up[g], 0));  // non-periodic: group 0
         }
         sz_record(h->L, h->ev[0], st);
-        if (!keep_ghosts) enqueue_ghosts(h);
-        sz_record(h->L, h->ev[1], st);
-        const bool fork = do_coupling && !h->cfg.two_way_coupling_on;
-        if (fork && !h->cpl_prelaunched) {
-            // fork: coupling only needs the floe state after add_ghosts! wrapped parents into the domain; it
-            // reads nothing the collision kernels write, so it runs beside them on a low-priority stream and
-            // fills the issue slots the latency-bound narrow phase leaves idle
-            cudaEventRecord(h->ev_fork, st);
-            cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-            Launch L2 = h->L;
-            L2.stream = h->stream2;
-            // measured (profiles/README.md): capping coupling to 2-4 resident blocks per SM so that it runs beside the
-            // narrow phase slows the latter more than the overlap gains; it fills the GPU during the broad phase
-            L2.coupling_blocks_per_sm = 0;
-            sz_record(L2, h->ev_c0, h->stream2);
-            szk_coupling(L2, h->S, h->P);
-            sz_record(L2, h->ev_c1, h->stream2);
-            cudaEventRecord(h->ev_join, h->stream2);
+        bool forked = h->cpl_prelaunched;
+        if (h->slab.on) {
+            // the coupling of an owned floe reads only that floe's own state: without a periodic wall (add_ghosts! wraps
+            // parents first) it starts before this rank waits for its neighbours' records
+            if (fork && !forked && !periodic) {
+                fork_coupling();
+                forked = true;
+            }
+            if (cur.slab_host_mode && cur.attempt == 0) {
+                // host arrays every step: what the host uploaded is what the neighbours must see
+                if (io) CK(cudaStreamWaitEvent(st, h->ev_up[3], 0));
+                slab_push(h, h->slab.epoch);
+            }
+            if (io) CK(cudaStreamWaitEvent(st, h->ev_up[3], 0));  // the halo update lands on top of the uploaded (stale) copies
+            slab_unpack(h);
         }
+        if (!cur.keep_ghosts) enqueue_ghosts(h);
+        sz_record(h->L, h->ev[1], st);
+        if (fork && !forked) fork_coupling();
         // the ghost count of this step is not known on the host: size grids from the capacity-bounded hint
         cudaEvent_t waits[2] = {h->ev_up[2], h->ev_up[3]};
         if (io) CK(cudaStreamWaitEvent(st, h->ev_up[1], 0));
@@ -1147,71 +1253,88 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         szk_remove_ghosts(h->L, h->S, h->n_verts_init);
         sz_record(h->L, h->ev[5], st);
         if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 0); if (rc2) return rc2; }
-        if (fork) {
-            cudaStreamWaitEvent(st, h->ev_join, 0);  // join
-            szk_apply_coupling_tags(h->L, h->S);
-        } else if (do_coupling) {
-            // two-way coupling writes ocean.hflx_factor for the NEXT step: it must not run ahead of a collision
-            // phase that may still overflow and be repeated, so it stays in order on this stream
-            sz_record(h->L, h->ev_c0, st);
-            enqueue_coupling(h, h->L);
-            sz_record(h->L, h->ev_c1, st);
-            szk_apply_coupling_tags(h->L, h->S);
-        }
-        if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 1); if (rc2) return rc2; }
-        sz_record(h->L, h->ev[6], st);
-        szk_update(h->L, h->S, h->B, h->P);
-        sz_record(h->L, h->ev[7], st);
-        if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 2); if (rc2) return rc2; }
-        CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        return SZ_OK;
-    };
-    for (int attempt = 0;; ++attempt) {
-        // Device-resident steps replay a captured CUDA graph of the ~39 launches on two streams: most of them are
-        // small dependent kernels (scans, checks, the broad phase) whose launch gaps then shrink; the graph is
-        // captured again whenever a pointer or parameter baked into its nodes changed (h->gen) or a grid-size hint
-        // moved to another bucket.  sz_step_host (host copies with caller pointers) enqueues directly, and so do LARGE
-        // fields: measured (tools/ab_small.sh) the graph gives +22 % at 1 k floes and +12 % at 10 k, but -7 % at 100 k,
-        // where the step is bound by three long kernels (the captured nodes keep their stream priorities: checked with
-        // cudaGraphKernelNodeGetAttribute; the external timing-event nodes in the chain are the suspected cost).
-        bool replay = false;
-        if (!io && !h->graph_off && !h->cpl_prelaunched && h->n_init <= SZ_GRAPH_MAX_FLOES) {
-            const int fh = floes_hint(h), ph = pairs_hint(h);
-            const bool fresh = !keep_ghosts && h->gexec && h->gkey_gen == h->gen && h->gkey_coupling == do_coupling && h->gkey_floes == fh &&
-                               h->gkey_pairs == ph;
-            if (!fresh) {
-                if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    }
+    if (fork) {
+        cudaStreamWaitEvent(st, h->ev_join, 0);  // join
+        szk_apply_coupling_tags(h->L, h->S);
+    } else if (do_coupling) {
+        // two-way coupling writes ocean.hflx_factor for the NEXT step: it must not run ahead of a collision
+        // phase that may still overflow and be repeated, so it stays in order on this stream
+        sz_record(h->L, h->ev_c0, st);
+        enqueue_coupling(h, h->L);
+        sz_record(h->L, h->ev_c1, st);
+        szk_apply_coupling_tags(h->L, h->S);
+    }
+    if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 1); if (rc2) return rc2; }
+    sz_record(h->L, h->ev[6], st);
+    szk_update(h->L, h->S, h->B, h->P);
+    sz_record(h->L, h->ev[7], st);
+    if (io) { int32_t rc2 = enqueue_downloads(h, io->out, 2); if (rc2) return rc2; }
+    if (h->slab.on && !cur.slab_host_mode) slab_push(h, h->slab.epoch + 1);  // device-resident: publish behind the update
+    CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    return SZ_OK;
+}
+
+static int32_t step_enqueue(sz_handle *h) {
+    cudaStream_t st = h->L.stream;
+    const StepCur &cur = h->cur;
+    // Device-resident steps replay a captured CUDA graph of the ~39 launches on two streams: most of them are
+    // small dependent kernels (scans, checks, the broad phase) whose launch gaps then shrink; the graph is
+    // captured again whenever a pointer or parameter baked into its nodes changed (h->gen) or a grid-size hint
+    // moved to another bucket.  sz_step_host (host copies with caller pointers) enqueues directly, and so do LARGE
+    // fields: measured (tools/ab_small.sh) the graph gives +22 % at 1 k floes and +12 % at 10 k, but -7 % at 100 k,
+    // where the step is bound by three long kernels (the captured nodes keep their stream priorities: checked with
+    // cudaGraphKernelNodeGetAttribute; the external timing-event nodes in the chain are the suspected cost).
+    // Slab ranks (epoch-numbered push / unpack kernels) and coupling-only repairs launch directly.
+    if (!cur.has_io && !h->graph_off && !h->cpl_prelaunched && !h->slab.on && !cur.coupling_only && h->n_init <= SZ_GRAPH_MAX_FLOES) {
+        const int fh = floes_hint(h), ph = pairs_hint(h);
+        const bool fresh = !cur.keep_ghosts && h->gexec && h->gkey_gen == h->gen && h->gkey_coupling == cur.do_coupling &&
+                           h->gkey_floes == fh && h->gkey_pairs == ph;
+        if (!fresh) {
+            if (h->gexec) cudaGraphExecDestroy(h->gexec);
+            h->gexec = nullptr;
+            const long long before = szk_launch_count(false);
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            h->L.capturing = true;
+            const int32_t crc = step_enqueue_direct(h);
+            h->L.capturing = false;
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            const long long captured = szk_launch_count(false) - before;
+            szk_count_launches((int)-captured);  // nothing has run yet
+            if (crc == SZ_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&h->gexec, g, 0) == cudaSuccess) {
+                h->gkey_gen = cur.keep_ghosts ? 0 : h->gen;  // a repair attempt's graph (no ghost pass) is not reused
+                h->gkey_coupling = cur.do_coupling; h->gkey_floes = fh; h->gkey_pairs = ph;
+                h->graph_launches = (int)captured;
+            } else {
                 h->gexec = nullptr;
-                const long long before = szk_launch_count(false);
-                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                h->L.capturing = true;
-                const int32_t crc = enqueue();
-                h->L.capturing = false;
-                cudaGraph_t g = nullptr;
-                const cudaError_t ce = cudaStreamEndCapture(st, &g);
-                const long long captured = szk_launch_count(false) - before;
-                szk_count_launches((int)-captured);  // nothing has run yet
-                if (crc == SZ_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&h->gexec, g, 0) == cudaSuccess) {
-                    h->gkey_gen = keep_ghosts ? 0 : h->gen;  // a repair attempt's graph (no ghost pass) is not reused
-                    h->gkey_coupling = do_coupling; h->gkey_floes = fh; h->gkey_pairs = ph;
-                    h->graph_launches = (int)captured;
-                } else {
-                    h->gexec = nullptr;
-                    h->graph_off = true;  // fall back to direct launches for the life of the handle
-                    cudaGetLastError();
-                }
-                if (g) cudaGraphDestroy(g);
+                h->graph_off = true;  // fall back to direct launches for the life of the handle
+                cudaGetLastError();
             }
-            if (h->gexec) {
-                CK(cudaGraphLaunch(h->gexec, st));
-                szk_count_launches(h->graph_launches);
-                replay = true;
-            }
+            if (g) cudaGraphDestroy(g);
         }
-        if (!replay) {
-            int32_t erc = enqueue();
-            if (erc) return erc;
+        if (h->gexec) {
+            CK(cudaGraphLaunch(h->gexec, st));
+            szk_count_launches(h->graph_launches);
+            return SZ_OK;
         }
+    }
+    return step_enqueue_direct(h);
+}
+
+// Wait for the step in flight; a buffer overflow is repaired and the step repeated:
+//  * collision-phase overflow: FROM THE COLLISIONS — the ghosts of the failed attempt are complete and stay (every
+//    kernel after the overflow returned at once, including the ghost removal).  Running add_ghosts! again would start
+//    from parents the first pass has already wrapped into the domain and can number the images of a corner floe in
+//    another order than a clean step does (rows and totals then differ from the reference in their last bit);
+//  * the ghost pass itself overflowed: nothing of it was committed for that axis; start over;
+//  * the floe -> cell registry of the two-way coupling overflowed: the collisions of this step are COMPLETE (rows
+//    added to overarea, moving walls advanced, ghosts removed): only coupling, tags and update are repeated.
+static int32_t step_finish(sz_handle *h) {
+    cudaStream_t st = h->L.stream;
+    StepCur &cur = h->cur;
+    const bool io = cur.has_io;
+    for (;;) {
         CK(cudaStreamSynchronize(st));
         if (io) {
             CK(cudaEventRecord(h->ev_dn_end, h->stream_dn));
@@ -1233,30 +1356,46 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
         }
         CK(cudaGetLastError());
         if (!h->h_cnt->error) break;
-        // every kernel after the overflow returned at once: the floe state is untouched except for the ghosts (and the
-        // parents add_ghosts! wrapped into the domain), which stay for the repeated attempt (see keep_ghosts above)
+        // every kernel after the overflow returned at once
         Counters c = *h->h_cnt;
         h->n_total = c.n_total;
         h->n_verts = c.n_verts;
-        if (attempt >= 6) return fail(h, SZ_ERR_CAPACITY, "step: capacity retry limit");
+        if (cur.attempt >= 6) return fail(h, SZ_ERR_CAPACITY, "step: capacity retry limit");
         int32_t rc = handle_overflow(h, c);
         if (rc) return rc;
         const uint32_t ghost_bits = ERR_GHOST_CAP | ERR_VERT_CAP | ERR_GHOST_SLOTS;
-        if (c.error & ghost_bits) {
-            // the ghost pass itself overflowed: nothing of it was committed for that axis; start over
+        const uint32_t coupling_bits = ERR_CREC_CAP | ERR_CELL_TABLE;
+        if (cur.coupling_only || (c.error & ~coupling_bits) == 0) {
+            if (!cur.coupling_only) h->last_ok_collisions = c;
+            cur.coupling_only = true;
+        } else if (c.error & ghost_bits) {
             szk_remove_ghosts(h->L, h->S, h->n_verts_init);
-            keep_ghosts = false;
+            cur.keep_ghosts = false;
         } else {
-            keep_ghosts = true;
+            cur.keep_ghosts = true;
         }
         CK(cudaStreamSynchronize(st));
         h->n_total = h->n_init;
         h->n_verts = h->n_verts_init;
+        cur.attempt++;
+        if ((rc = step_enqueue(h))) return rc;
     }
-    h->last = *h->h_cnt;
+    const int32_t do_coupling = cur.do_coupling;
+    if (!cur.coupling_only) h->last = *h->h_cnt;
+    else {  // the collision counters of the first attempt stand; take the registry size of the repeated coupling
+        Counters keep = h->last_ok_collisions;
+        keep.n_crec = h->h_cnt->n_crec;
+        keep.slab_disp = h->h_cnt->slab_disp;
+        h->last = keep;
+    }
     h->n_total = h->n_init;
     h->n_verts = h->n_verts_init;
     h->cpl_prelaunched = false;
+    if (h->slab.on) {
+        if (cur.slab_host_mode) h->slab.pushed = h->slab.epoch;
+        else h->slab.pushed = h->slab.epoch + 1;
+        h->slab.epoch += 1;
+    }
     if (getenv("SZ_DEBUG_COUNTS"))
         fprintf(stderr, "counts: cand %d kept %d dom %d order %d force %d mid %d large %d overlap %d rows %d\n", h->last.n_cand,
                 h->last.n_kept, h->last.n_dom, h->last.n_order, h->last.n_force, h->last.n_mid, h->last.n_large, h->last.n_overlap,
@@ -1276,6 +1415,28 @@ static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
     h->ms[6] = ev_ms(h, 0, 7);
     h->ms[7] = (double)szk_launch_count(true);  // kernels launched since the previous sz_step returned (incl. halo pack/unpack)
     return SZ_OK;
+}
+
+static int32_t step_begin(sz_handle *h, int32_t do_coupling, const HostIO *io, bool slab_host_mode) {
+    StepCur &cur = h->cur;
+    cur.do_coupling = do_coupling;
+    cur.has_io = io != nullptr;
+    if (io) cur.io = *io;
+    cur.keep_ghosts = cur.coupling_only = false;
+    cur.slab_host_mode = slab_host_mode;
+    cur.attempt = 0;
+    if (h->slab.on && slab_host_mode && h->slab.pushed >= h->slab.epoch) h->slab.epoch = h->slab.pushed + 1;  // a fresh epoch for the re-publication
+    if (io && io->in) {
+        int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
+        if (rc) return rc;
+    }
+    return step_enqueue(h);
+}
+
+static int32_t step_impl(sz_handle *h, int32_t do_coupling, const HostIO *io) {
+    int32_t rc = step_begin(h, do_coupling, io, false);
+    if (rc) return rc;
+    return step_finish(h);
 }
 
 extern "C" int32_t sz_coupling_begin(sz_handle *h) {
@@ -1308,6 +1469,7 @@ extern "C" int32_t sz_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
     if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step with coupling before set_fields");
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
     if (h->cpl_prelaunched && !do_coupling) return fail(h, SZ_ERR_INVALID, "step without coupling after sz_coupling_begin");
+    if (h->slab.on) return fail(h, SZ_ERR_INVALID, "this handle is a slab rank: step it with sz_slab_step");
     cudaSetDevice(h->cfg.device);
     return step_impl(h, do_coupling, nullptr);
 }
@@ -1345,8 +1507,7 @@ extern "C" int32_t sz_upload_state_begin(sz_handle *h, int32_t do_coupling, cons
 // sz_upload_state + sz_step + sz_download_floes in ONE call: the host <-> device copies run on their own
 // streams beside the kernels (see HostIO).  `in` and `out` may point to the same arrays; in == NULL: the uploads were
 // enqueued by sz_upload_state_begin.
-extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
-    (void)tstep;
+static int32_t prepare_step_host(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
     if (!h || !out) return SZ_ERR_INVALID;
     {
         int32_t rc = check_host_state(h, "step_host", do_coupling, in);
@@ -1364,14 +1525,12 @@ extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling
         CK(dalloc(&h->d_cf_dn, (size_t)n));
         h->cf_cap = n;
     }
-    HostIO io = {in, out};
-    int32_t rc = step_impl(h, do_coupling, &io);
-    if (rc) {
-        cudaStreamSynchronize(h->stream_up);
-        cudaStreamSynchronize(h->stream_dn);
-        return rc;
-    }
-    // host-side tables of the download (same as sz_download_floes without ghosts)
+    return SZ_OK;
+}
+
+// host-side tables of the download (same as sz_download_floes without ghosts)
+static void finish_host_tables(sz_handle *h, sz_floe_soa *out) {
+    const int n = h->n_init;
     out->n = n;
     out->n_init = n;
     if (out->vert_offsets) {
@@ -1381,6 +1540,284 @@ extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling
     }
     if (out->mc_offsets) for (int i = 0; i <= n; ++i) out->mc_offsets[i] = h->h_mc_off[i];
     if (out->ghost_offsets) memset(out->ghost_offsets, 0, sizeof(int64_t) * ((size_t)n + 1));
+}
+
+extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
+    (void)tstep;
+    if (h && h->slab.on) return fail(h, SZ_ERR_INVALID, "this handle is a slab rank: step it with sz_slab_step_host");
+    int32_t rc = prepare_step_host(h, do_coupling, in, out);
+    if (rc) return rc;
+    HostIO io = {in, out};
+    rc = step_impl(h, do_coupling, &io);
+    if (rc) {
+        cudaStreamSynchronize(h->stream_up);
+        cudaStreamSynchronize(h->stream_dn);
+        return rc;
+    }
+    finish_host_tables(h, out);
+    return SZ_OK;
+}
+
+// ---- slab backend (sz_slab_backend.h): a rank's side of the peer-memory halo update ---------------------------------
+struct WireData {
+    int32_t pid, device, rank, pad;
+    unsigned long long base;
+    cudaIpcMemHandle_t ipc;
+    long long off_ready, off_ack, off_stage[2], bytes;
+};
+static_assert(sizeof(WireData) <= sizeof(SlabWire), "SlabWire too small");
+
+int32_t szb_release_peers(sz_handle *h) {
+    if (!h) return SZ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->L.stream);
+    for (void *p : h->slab.ipc_open) cudaIpcCloseMemHandle(p);
+    h->slab.ipc_open.clear();
+    for (int k = 0; k < SZ_SLAB_MAX_PARTNERS; ++k) {
+        h->slab.dev.p[k].r_stage[0] = h->slab.dev.p[k].r_stage[1] = nullptr;
+        h->slab.dev.p[k].r_ready = h->slab.dev.p[k].r_ack = nullptr;
+    }
+    return SZ_OK;
+}
+
+static void slab_free(sz_handle *h) {
+    SlabState &B = h->slab;
+    dfree(B.d_send_idx); dfree(B.d_recv_idx); dfree(B.d_send_voff); dfree(B.d_recv_voff); dfree(B.d_owned); dfree(B.d_refx);
+    dfree(B.d_refy); dfree(B.arena);
+    B.arena_bytes = 0;
+    B.on = false;
+}
+
+int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
+    if (!h || !l || l->n_partners < 0 || (l->n_partners > 0 && !wire_out)) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "slab: configure before upload_floes");
+    if (l->n_partners > SZ_SLAB_MAX_PARTNERS) return fail(h, SZ_ERR_UNSUPPORTED, "slab: more than 16 exchange partners");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "slab: configure with ghosts present");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaStreamSynchronize(h->L.stream));
+    szb_release_peers(h);
+    slab_free(h);
+    SlabState &B = h->slab;
+    const int np = l->n_partners, n = h->n_init;
+    const long long ns = np ? l->send_off[np] : 0, nr = np ? l->recv_off[np] : 0;
+    std::vector<int> sidx((size_t)std::max<long long>(ns, 1)), ridx((size_t)std::max<long long>(nr, 1));
+    std::vector<long long> svoff((size_t)std::max<long long>(ns, 1)), rvoff((size_t)std::max<long long>(nr, 1));
+    std::vector<long long> sbytes(np, 0), rbytes(np, 0);
+    memset(&B.dev, 0, sizeof(B.dev));
+    B.max_send = B.max_recv = 0;
+    B.send_bytes_total = 0;
+    for (int p = 0; p < np; ++p) {
+        long long v = 0;
+        for (long long k = l->send_off[p]; k < l->send_off[p + 1]; ++k) {
+            if (l->send_idx[k] < 0 || l->send_idx[k] >= n) return fail(h, SZ_ERR_INVALID, "slab: send index out of range");
+            sidx[k] = (int)l->send_idx[k];
+            svoff[k] = v;
+            v += h->h_vcount[sidx[k]];
+        }
+        sbytes[p] = 64 * (l->send_off[p + 1] - l->send_off[p]) + 16 * v;
+        v = 0;
+        for (long long k = l->recv_off[p]; k < l->recv_off[p + 1]; ++k) {
+            if (l->recv_idx[k] < 0 || l->recv_idx[k] >= n) return fail(h, SZ_ERR_INVALID, "slab: receive index out of range");
+            ridx[k] = (int)l->recv_idx[k];
+            rvoff[k] = v;
+            v += h->h_vcount[ridx[k]];
+        }
+        rbytes[p] = 64 * (l->recv_off[p + 1] - l->recv_off[p]) + 16 * v;
+        SlabPartnerDev &d = B.dev.p[p];
+        d.send_off = (int)l->send_off[p]; d.send_n = (int)(l->send_off[p + 1] - l->send_off[p]);
+        d.recv_off = (int)l->recv_off[p]; d.recv_n = (int)(l->recv_off[p + 1] - l->recv_off[p]);
+        B.max_send = std::max(B.max_send, d.send_n);
+        B.max_recv = std::max(B.max_recv, d.recv_n);
+        B.send_bytes_total += sbytes[p];
+    }
+    B.send_bytes = sbytes;
+    // arena: [0, 4096) flags — ready[16] | ack[16] | push_count[16] | unpack_count[16] — then two halves per partner
+    const size_t FLAGS = 4096;
+    std::vector<size_t> off0(np), off1(np);
+    size_t total = FLAGS;
+    for (int p = 0; p < np; ++p) {
+        size_t b = ((size_t)rbytes[p] + 255) / 256 * 256 + 256;
+        off0[p] = total; total += b;
+        off1[p] = total; total += b;
+    }
+    CK(cudaMalloc((void **)&B.arena, total));
+    B.arena_bytes = total;
+    CK(cudaMemset(B.arena, 0, total));
+    CK(dalloc(&B.d_send_idx, (size_t)ns)); CK(dalloc(&B.d_recv_idx, (size_t)nr));
+    CK(dalloc(&B.d_send_voff, (size_t)ns)); CK(dalloc(&B.d_recv_voff, (size_t)nr));
+    CK(dalloc(&B.d_owned, (size_t)n)); CK(dalloc(&B.d_refx, (size_t)n)); CK(dalloc(&B.d_refy, (size_t)n));
+    if (ns > 0) {
+        CK(cudaMemcpy(B.d_send_idx, sidx.data(), sizeof(int) * ns, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B.d_send_voff, svoff.data(), sizeof(long long) * ns, cudaMemcpyHostToDevice));
+    }
+    if (nr > 0) {
+        CK(cudaMemcpy(B.d_recv_idx, ridx.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B.d_recv_voff, rvoff.data(), sizeof(long long) * nr, cudaMemcpyHostToDevice));
+    }
+    if (n > 0) {
+        CK(cudaMemcpy(B.d_owned, l->owned, (size_t)n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B.d_refx, h->S.cx, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(B.d_refy, h->S.cy, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+    }
+    szk_slab_reset_disp(h->L, h->S);
+    CK(cudaStreamSynchronize(h->L.stream));
+    h->h_cnt->slab_disp = 0ull;
+    int *flags = (int *)B.arena;
+    B.dev.n_partners = np;
+    B.dev.send_idx = B.d_send_idx; B.dev.recv_idx = B.d_recv_idx; B.dev.send_voff = B.d_send_voff; B.dev.recv_voff = B.d_recv_voff;
+    B.dev.push_count = flags + 32; B.dev.unpack_count = flags + 48;
+    B.dev.owned = B.d_owned; B.dev.refx = B.d_refx; B.dev.refy = B.d_refy;
+    B.dev.period_x = l->period_x; B.dev.period_y = l->period_y;
+    cudaIpcMemHandle_t ipc;
+    memset(&ipc, 0, sizeof(ipc));
+    if (cudaIpcGetMemHandle(&ipc, B.arena) != cudaSuccess) {  // same-process partners do not need it
+        cudaGetLastError();
+        memset(&ipc, 0, sizeof(ipc));
+    }
+    for (int p = 0; p < np; ++p) {
+        SlabPartnerDev &d = B.dev.p[p];
+        d.l_stage[0] = (const double *)(B.arena + off0[p]);
+        d.l_stage[1] = (const double *)(B.arena + off1[p]);
+        d.l_ready = flags + p;
+        d.l_ack = flags + 16 + p;
+        WireData w;
+        memset(&w, 0, sizeof(w));
+        w.pid = (int32_t)getpid(); w.device = h->cfg.device; w.rank = l->rank;
+        w.base = (unsigned long long)(uintptr_t)B.arena;
+        w.ipc = ipc;
+        w.off_ready = (long long)(sizeof(int) * p); w.off_ack = (long long)(sizeof(int) * (16 + p));
+        w.off_stage[0] = (long long)off0[p]; w.off_stage[1] = (long long)off1[p];
+        w.bytes = rbytes[p];
+        memset(&wire_out[p], 0, sizeof(SlabWire));
+        memcpy(&wire_out[p], &w, sizeof(w));
+    }
+    B.rank = l->rank;
+    B.n_partners = np;
+    B.epoch = 1;
+    B.pushed = 0;
+    B.on = true;
+    h->gen++;
+    return SZ_OK;
+}
+
+int32_t szb_connect(sz_handle *h, const SlabWire *peer_wire) {
+    if (!h || !h->slab.on) return SZ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    SlabState &B = h->slab;
+    std::vector<std::pair<unsigned long long, unsigned char *>> mapped;  // one mapping per partner process arena
+    for (int p = 0; p < B.n_partners; ++p) {
+        WireData w;
+        memcpy(&w, &peer_wire[p], sizeof(w));
+        if (w.bytes != B.send_bytes[p]) return fail(h, SZ_ERR_INVALID, "slab: a partner expects a different message size (lists disagree)");
+        unsigned char *base = nullptr;
+        if (w.pid == (int32_t)getpid()) {
+            base = (unsigned char *)(uintptr_t)w.base;
+            if (w.device != h->cfg.device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, h->cfg.device, w.device));
+                if (!can) return fail(h, SZ_ERR_UNSUPPORTED, "slab: no peer access between two devices of the decomposition");
+                cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                cudaGetLastError();
+            }
+        } else {
+            void *m = nullptr;
+            CK(cudaIpcOpenMemHandle(&m, w.ipc, cudaIpcMemLazyEnablePeerAccess));
+            B.ipc_open.push_back(m);
+            base = (unsigned char *)m;
+        }
+        SlabPartnerDev &d = B.dev.p[p];
+        d.r_stage[0] = (double *)(base + w.off_stage[0]);
+        d.r_stage[1] = (double *)(base + w.off_stage[1]);
+        d.r_ready = (int *)(base + w.off_ready);
+        d.r_ack = (int *)(base + w.off_ack);
+    }
+    // first publication: the partners' first step consumes epoch 1
+    szk_slab_push(h->L, h->S, B.dev, 1, B.max_send);
+    CK(cudaStreamSynchronize(h->L.stream));
+    CK(cudaGetLastError());
+    szk_launch_count(true);
+    B.pushed = 1;
+    B.epoch = 1;
+    return SZ_OK;
+}
+
+int32_t szb_step_begin(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out, int32_t host_mode) {
+    (void)tstep;
+    if (!h || !h->slab.on) return fail(h, SZ_ERR_INVALID, "slab step on a handle without halo lists");
+    if (!h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step before set_domain/upload_floes");
+    if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step with coupling before set_fields");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
+    cudaSetDevice(h->cfg.device);
+    if (host_mode) {
+        int32_t rc = prepare_step_host(h, do_coupling, in, out);
+        if (rc) return rc;
+        HostIO io = {in, out};
+        return step_begin(h, do_coupling, &io, true);
+    }
+    return step_begin(h, do_coupling, nullptr, false);
+}
+
+int32_t szb_step_end(sz_handle *h, int32_t host_mode) {
+    if (!h) return SZ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = step_finish(h);
+    if (host_mode) {
+        if (rc) {
+            cudaStreamSynchronize(h->stream_up);
+            cudaStreamSynchronize(h->stream_dn);
+            return rc;
+        }
+        finish_host_tables(h, h->cur.io.out);
+    }
+    return rc;
+}
+
+int32_t szb_refresh_publish(sz_handle *h) {
+    if (!h || !h->slab.on) return SZ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    if (h->slab.pushed < h->slab.epoch) {
+        slab_push(h, h->slab.epoch);
+        h->slab.pushed = h->slab.epoch;
+    }
+    CK(cudaGetLastError());
+    return SZ_OK;
+}
+
+int32_t szb_refresh_consume(sz_handle *h) {
+    if (!h || !h->slab.on) return SZ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    slab_unpack(h);  // the next step consumes the same epoch again: idempotent
+    CK(cudaStreamSynchronize(h->L.stream));
+    CK(cudaGetLastError());
+    return SZ_OK;
+}
+
+double szb_max_displacement(sz_handle *h) {
+    if (!h) return 0.0;
+    double d;
+    unsigned long long e = h->h_cnt->slab_disp;
+    memcpy(&d, &e, sizeof(d));
+    return d;
+}
+
+int32_t szb_upload_floes_resident_mc(sz_handle *h, const sz_floe_soa *s, const int64_t *mc_src, int64_t n_extra) {
+    return upload_floes_impl(h, s, mc_src, n_extra);
+}
+
+int32_t szb_fetch_mc(sz_handle *h, int64_t off, int64_t n, double *x, double *y) {
+    if (!h || n < 0 || off < 0 || off + n > h->n_mc) return SZ_ERR_INVALID;
+    if (n == 0) return SZ_OK;
+    cudaSetDevice(h->cfg.device);
+    std::vector<double2> t((size_t)n);
+    CK(cudaMemcpy(t.data(), h->S.mc + off, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < n; ++k) { x[k] = t[k].x; y[k] = t[k].y; }
+    return SZ_OK;
+}
+
+int32_t szb_mc_offsets(sz_handle *h, int64_t *off) {
+    if (!h || !off) return SZ_ERR_INVALID;
+    for (size_t i = 0; i < h->h_mc_off.size(); ++i) off[i] = h->h_mc_off[i];
     return SZ_OK;
 }
 

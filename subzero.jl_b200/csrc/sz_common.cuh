@@ -73,6 +73,9 @@ struct Counters {
     // broad-phase bounding box, order-preserving uint64 encodings (k_bbox)
     unsigned long long bb[5];  // min x, min y, max x, max y, max rmax
     double gx0, gy0, cell;
+    // slab decomposition: largest distance an owned floe travelled since the halo lists were built (order-preserving
+    // encoding of a double, atomicMax in k_slab_push); never reset by a step
+    unsigned long long slab_disp;
 };
 
 struct DomainDev {
@@ -178,6 +181,29 @@ struct CouplingBuf {
     int *scan_block;
 };
 
+// ---- slab decomposition: per-step halo update over peer memory (sz_slab_*) ---------------------------
+// One entry per exchange partner.  "r_" pointers live in the PARTNER's receive arena (peer-mapped: same process, or
+// a cudaIpc mapping), "l_" pointers in this rank's own arena.  A message is n records of 8 doubles (cx, cy, u, v, xi,
+// height, status, alpha) followed by the ring points of those floes; arenas are double-buffered by epoch parity.
+struct SlabPartnerDev {
+    int send_off, send_n, recv_off, recv_n;  // segments of the send / receive lists
+    double *r_stage[2];        // where my records for this partner go
+    int *r_ready;              // partner's flag: my records of epoch e are complete
+    int *r_ack;                // partner's flag: I have consumed its records of epoch e
+    const double *l_stage[2];  // where the partner's records arrive
+    int *l_ready, *l_ack;      // written by the partner
+};
+struct SlabDev {
+    int n_partners;
+    SlabPartnerDev p[SZ_SLAB_MAX_PARTNERS];
+    const int *send_idx, *recv_idx;          // local floe indices, per partner segment
+    const long long *send_voff, *recv_voff;  // first ring point of each listed floe inside its message
+    int *push_count, *unpack_count;          // [n_partners] block counters (last block raises the flag)
+    const unsigned char *owned;              // [n_init] 1 = this rank owns the floe
+    const double *refx, *refy;               // centroids when the lists were built
+    double period_x, period_y;               // 0 = not periodic
+};
+
 __host__ __device__ inline int sz_div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 struct Launch {
@@ -204,6 +230,15 @@ void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Par
                     int n_pairs_hint, cudaEvent_t *ev, const cudaEvent_t *waits = nullptr);
 int szk_configure(const Launch &L);
 void szk_halo(const Launch &L, const Store &S, const int *idx, const long long *voff, int n, double *buf, bool pack);
+// slab data plane: push my boundary floes into the partners' arenas (+ displacement of the owned floes) / wait for
+// the partners' records of `epoch` and scatter them into the store
+void szk_slab_push(const Launch &L, const Store &S, const SlabDev &D, int epoch, int max_send);
+void szk_slab_unpack(const Launch &L, const Store &S, const SlabDev &D, int epoch, int max_recv);
+void szk_slab_reset_disp(const Launch &L, const Store &S);
+// Monte-Carlo points of a re-built floe list: segment i comes from the old device array (src[i] >= 0: offset) or from
+// `extra` (src[i] < 0: offset -1 - src[i])
+void szk_mc_regather(const Launch &L, double2 *dst, const long long *dst_off, const double2 *old_mc, const double2 *extra,
+                     const long long *src, int n);
 void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);
 void szk_coupling(const Launch &L, const Store &S, const Params &P);
 void szk_apply_coupling_tags(const Launch &L, const Store &S);

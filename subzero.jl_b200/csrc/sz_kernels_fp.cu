@@ -661,3 +661,138 @@ void szk_halo(const Launch &L, const Store &S, const int *idx, const long long *
     else k_halo<false><<<blocks, 128, 0, L.stream>>>(S, idx, voff, n, buf);
     szk_count_launches(1);
 }
+
+// ---- slab data plane: one push kernel over peer memory instead of pack -> ncclSend/ncclRecv -> unpack ----------------
+// The reference is single-process (collisions.jl:734-864 sees one floe list); this is the per-step halo update of
+// SURVEY §8(e).  k_slab_push runs right behind k_update: blockIdx.y = partner; every thread copies one boundary floe
+// (8 doubles + its ring) with plain stores into the partner's receive arena — peer-mapped device memory, NVLink —
+// fences, and the last block of a partner raises `ready = epoch` there.  The extra y-slice measures how far the owned
+// floes travelled since the lists were built.  k_slab_unpack opens the partner's next step: spin on `ready`, scatter
+// the records into the store, last block writes `ack = epoch` back.  Arenas alternate with the epoch's parity, so a
+// sender only has to see the ack of epoch - 2 (one whole step old: never waited for in practice).
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long enc_disp(double x) {  // x >= 0: the bit pattern is order-preserving
+    return (unsigned long long)__double_as_longlong(x);
+}
+
+__global__ void __launch_bounds__(128) k_slab_push(Store S, SlabDev D, int epoch) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;  // an overflowing step is repeated: nothing is published
+    const int y = blockIdx.y;
+    if (y == D.n_partners) {  // displacement of the owned floes (periodic wrap taken out, collisions.jl:943-949)
+        double m = 0.0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n_init; i += gridDim.x * blockDim.x) {
+            if (!D.owned[i]) continue;
+            double dx = fabs(S.cx[i] - D.refx[i]), dy = fabs(S.cy[i] - D.refy[i]);
+            if (D.period_x > 0.0) dx = fmin(dx, fabs(dx - D.period_x));
+            if (D.period_y > 0.0) dy = fmin(dy, fabs(dy - D.period_y));
+            m = fmax(m, sqrt(dx * dx + dy * dy));
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(FULLMASK, m, o));
+        if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(&cnt->slab_disp, enc_disp(m));
+        return;
+    }
+    const SlabPartnerDev &p = D.p[y];
+    const int nb = (p.send_n + blockDim.x - 1) / blockDim.x;
+    if ((int)blockIdx.x >= nb) return;
+    if (threadIdx.x == 0)
+        while (ld_acquire_sys(p.l_ack) < epoch - 2) __nanosleep(64);  // the partner is done with this half of its arena
+    __syncthreads();
+    double *buf = p.r_stage[epoch & 1];
+    double2 *vx = (double2 *)(buf + 8 * (size_t)p.send_n);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < p.send_n) {
+        const int i = D.send_idx[p.send_off + k];
+        double2 *r = (double2 *)(buf + 8 * (size_t)k);
+        r[0] = make_double2(S.cx[i], S.cy[i]);
+        r[1] = make_double2(S.u[i], S.v[i]);
+        r[2] = make_double2(S.xi[i], S.height[i]);
+        r[3] = make_double2((double)S.status[i], S.alpha[i]);
+        const int vs = S.vstart[i], nv = S.vcount[i];
+        double2 *v = vx + D.send_voff[p.send_off + k];
+        for (int q = 0; q < nv; ++q) v[q] = S.verts[vs + q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(&D.push_count[y], 1);
+        if (done == nb - 1) {
+            D.push_count[y] = 0;
+            __threadfence_system();
+            st_release_sys(p.r_ready, epoch);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_slab_unpack(Store S, SlabDev D, int epoch) {
+    const int y = blockIdx.y;
+    const SlabPartnerDev &p = D.p[y];
+    const int nb = (p.recv_n + blockDim.x - 1) / blockDim.x;
+    if ((int)blockIdx.x >= nb) return;
+    if (threadIdx.x == 0)
+        while (ld_acquire_sys(p.l_ready) < epoch) __nanosleep(64);
+    __syncthreads();
+    const double *buf = p.l_stage[epoch & 1];
+    const double2 *vx = (const double2 *)(buf + 8 * (size_t)p.recv_n);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < p.recv_n) {
+        const int i = D.recv_idx[p.recv_off + k];
+        const double2 *r = (const double2 *)(buf + 8 * (size_t)k);
+        // written by another GPU: read through L2 (ld.cg), never from a stale L1 line
+        const double2 a = __ldcg(r), b = __ldcg(r + 1), c = __ldcg(r + 2), d = __ldcg(r + 3);
+        S.cx[i] = a.x; S.cy[i] = a.y; S.u[i] = b.x; S.v[i] = b.y; S.xi[i] = c.x; S.height[i] = c.y;
+        S.status[i] = (int)d.x; S.alpha[i] = d.y;
+        const int vs = S.vstart[i], nv = S.vcount[i];
+        const double2 *v = vx + D.recv_voff[p.recv_off + k];
+        for (int q = 0; q < nv; ++q) S.verts[vs + q] = __ldcg(v + q);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(&D.unpack_count[y], 1);
+        if (done == nb - 1) {
+            D.unpack_count[y] = 0;
+            st_release_sys(p.r_ack, epoch);
+        }
+    }
+}
+
+void szk_slab_push(const Launch &L, const Store &S, const SlabDev &D, int epoch, int max_send) {
+    int bx = (max_send + 127) / 128, bd = (S.n_init + 127) / 128;
+    if (bd > 4 * L.sms) bd = 4 * L.sms;
+    if (bx < bd) bx = bd;
+    if (bx < 1) bx = 1;
+    k_slab_push<<<dim3(bx, D.n_partners + 1), 128, 0, L.stream>>>(S, D, epoch);
+    szk_count_launches(1);
+}
+void szk_slab_unpack(const Launch &L, const Store &S, const SlabDev &D, int epoch, int max_recv) {
+    if (D.n_partners <= 0 || max_recv <= 0) return;
+    k_slab_unpack<<<dim3((max_recv + 127) / 128, D.n_partners), 128, 0, L.stream>>>(S, D, epoch);
+    szk_count_launches(1);
+}
+__global__ void k_slab_reset_disp(Counters *cnt) { cnt->slab_disp = 0ull; }
+void szk_slab_reset_disp(const Launch &L, const Store &S) { k_slab_reset_disp<<<1, 1, 0, L.stream>>>(S.cnt); }
+
+// Monte-Carlo points of a re-built local list (sz_slab_rebuild): warp per floe, segment copy
+__global__ void k_mc_regather(double2 *__restrict__ dst, const long long *__restrict__ dst_off, const double2 *__restrict__ old_mc,
+                              const double2 *__restrict__ extra, const long long *__restrict__ src, int n) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+        const long long a = dst_off[i], m = dst_off[i + 1] - a, s = src[i];
+        const double2 *from = s >= 0 ? old_mc + s : extra + (-1 - s);
+        for (long long k = lane; k < m; k += 32) dst[a + k] = from[k];
+    }
+}
+void szk_mc_regather(const Launch &L, double2 *dst, const long long *dst_off, const double2 *old_mc, const double2 *extra,
+                     const long long *src, int n) {
+    if (n <= 0) return;
+    long long blocks = ((long long)n + 7) / 8, cap = (long long)L.sms * 16;
+    k_mc_regather<<<(int)(blocks < cap ? blocks : cap), 256, 0, L.stream>>>(dst, dst_off, old_mc, extra, src, n);
+}

@@ -1,0 +1,900 @@
+// sz_slab.cpp — slab decomposition inside the library (include/subzero_b200.h, sz_slab_*).
+//
+// Host logic only: which rank owns which floe, which floes a neighbour needs copies of, the local floe list of every
+// rank (sorted by GLOBAL index, so pair orientation, candidate order, row order and the canonical image pair of
+// collisions.jl:745-775 are those of the single-list run and owned results are bit-identical to one GPU), migration
+// of ownership and renewal of the halo lists.  The reference is single-process; nothing here restates reference code.
+//
+// Compiled twice from this one source:
+//   * into libsubzero_b200.so (prefix sz_): the per-step halo update is the peer-memory push / unpack kernel pair of
+//     sz_kernels_fp.cu, reached through sz_slab_backend.h; Monte-Carlo points never leave the device on a rebuild
+//     (only those of migrating floes do);
+//   * with -DSZ_ORACLE_BUILD into the oracle's test library (prefix szo_): the same lists, the records move through
+//     szo_halo_pack / host memory / the alltoallv callback (gloo in the CPU tests).
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "sz_slab_backend.h"
+
+#define FN(name) SZ_FN(name)
+
+namespace {
+
+constexpr int W = 40;  // doubles per floe record
+constexpr int C_CX = 0, C_CY = 1, C_RMAX = 5, C_STATUS = 37, C_ID = 38, C_GID = 39;
+
+struct DField {
+    size_t off;
+    int width, col;
+};
+#define DF(name, w, c) {offsetof(sz_floe_soa, name), w, c}
+const DField DFIELDS[] = {DF(centroid_x, 1, 0), DF(centroid_y, 1, 1), DF(height, 1, 2), DF(area, 1, 3), DF(mass, 1, 4),
+                          DF(rmax, 1, 5), DF(moment, 1, 6), DF(alpha, 1, 7), DF(u, 1, 8), DF(v, 1, 9), DF(xi, 1, 10),
+                          DF(fxOA, 1, 11), DF(fyOA, 1, 12), DF(trqOA, 1, 13), DF(hflx_factor, 1, 14), DF(overarea, 1, 15),
+                          DF(collision_force, 2, 16), DF(collision_trq, 1, 18), DF(stress_accum, 4, 19),
+                          DF(stress_instant, 4, 23), DF(strain, 4, 27), DF(p_dxdt, 1, 31), DF(p_dydt, 1, 32),
+                          DF(p_dudt, 1, 33), DF(p_dvdt, 1, 34), DF(p_dxidt, 1, 35), DF(p_dalphadt, 1, 36)};
+#undef DF
+constexpr int NDF = sizeof(DFIELDS) / sizeof(DFIELDS[0]);
+
+inline double *&dptr(sz_floe_soa &s, const DField &f) { return *(double **)((char *)&s + f.off); }
+inline const double *cdptr(const sz_floe_soa &s, const DField &f) { return *(double *const *)((const char *)&s + f.off); }
+inline double i64_as_double(int64_t v) { double d; memcpy(&d, &v, 8); return d; }
+inline int64_t double_as_i64(double d) { int64_t v; memcpy(&v, &d, 8); return v; }
+
+// Full floe records on the host.  Monte-Carlo points of a floe are either held here (msrc = -1, at [mhoff, mhoff + mcnt)
+// of mx / my) or resident in the owning rank's device array at offset msrc (CUDA build).
+struct FloeList {
+    int64_t n = 0;
+    std::vector<double> rec;  // [n][W]
+    std::vector<int64_t> gidx, vcnt, voff, mcnt, msrc, mhoff;
+    std::vector<double> vxy, mx, my;
+
+    void push_from(const FloeList &s, int64_t i, bool with_mc) {
+        rec.insert(rec.end(), s.rec.begin() + i * W, s.rec.begin() + (i + 1) * W);
+        gidx.push_back(s.gidx[i]);
+        vcnt.push_back(s.vcnt[i]);
+        voff.push_back((int64_t)vxy.size() / 2);
+        vxy.insert(vxy.end(), s.vxy.begin() + 2 * s.voff[i], s.vxy.begin() + 2 * (s.voff[i] + s.vcnt[i]));
+        if (!with_mc) {
+            mcnt.push_back(0); msrc.push_back(-1); mhoff.push_back((int64_t)mx.size());
+        } else {
+            mcnt.push_back(s.mcnt[i]);
+            msrc.push_back(s.msrc[i]);
+            mhoff.push_back((int64_t)mx.size());
+            if (s.msrc[i] < 0) {
+                mx.insert(mx.end(), s.mx.begin() + s.mhoff[i], s.mx.begin() + s.mhoff[i] + s.mcnt[i]);
+                my.insert(my.end(), s.my.begin() + s.mhoff[i], s.my.begin() + s.mhoff[i] + s.mcnt[i]);
+            }
+        }
+        n++;
+    }
+    double cx(int64_t i) const { return rec[i * W + C_CX]; }
+    double rmax(int64_t i) const { return rec[i * W + C_RMAX]; }
+};
+
+// arrays behind a sz_floe_soa (download target / upload source)
+struct SoaBuf {
+    sz_floe_soa s;
+    std::vector<std::vector<double>> d;
+    std::vector<int32_t> status;
+    std::vector<int64_t> id, gid, goff, gindex, voff, moff;
+    std::vector<double> vxy, mx, my;
+    void alloc(int64_t n, int64_t V, int64_t M) {
+        memset(&s, 0, sizeof(s));
+        s.n = s.n_init = n;
+        d.assign(NDF, std::vector<double>());
+        for (int f = 0; f < NDF; ++f) {
+            d[f].assign((size_t)std::max<int64_t>(n * DFIELDS[f].width, 1), 0.0);
+            dptr(s, DFIELDS[f]) = d[f].data();
+        }
+        status.assign((size_t)std::max<int64_t>(n, 1), SZ_STATUS_ACTIVE);
+        id.assign((size_t)std::max<int64_t>(n, 1), 0);
+        gid.assign((size_t)std::max<int64_t>(n, 1), 0);
+        goff.assign((size_t)n + 1, 0);
+        gindex.assign(1, 0);
+        voff.assign((size_t)n + 1, 0);
+        moff.assign((size_t)n + 1, 0);
+        vxy.assign((size_t)std::max<int64_t>(2 * V, 2), 0.0);
+        mx.assign((size_t)std::max<int64_t>(M, 1), 0.0);
+        my.assign((size_t)std::max<int64_t>(M, 1), 0.0);
+        s.status_tag = status.data(); s.id = id.data(); s.ghost_id = gid.data();
+        s.ghost_offsets = goff.data(); s.ghost_index = gindex.data();
+        s.vert_offsets = voff.data(); s.vert_xy = vxy.data();
+        s.mc_offsets = moff.data(); s.mc_x = mx.data(); s.mc_y = my.data();
+    }
+};
+
+// record i of a caller's SoA
+void record_from_soa(const sz_floe_soa &s, int64_t i, int64_t g, double *r) {
+    for (int f = 0; f < NDF; ++f) {
+        const double *p = cdptr(s, DFIELDS[f]);
+        for (int w = 0; w < DFIELDS[f].width; ++w) r[DFIELDS[f].col + w] = p ? p[i * DFIELDS[f].width + w] : 0.0;
+    }
+    r[C_STATUS] = (double)(s.status_tag ? s.status_tag[i] : SZ_STATUS_ACTIVE);
+    r[C_ID] = i64_as_double(s.id ? s.id[i] : g + 1);
+    r[C_GID] = i64_as_double(s.ghost_id ? s.ghost_id[i] : 0);
+}
+
+typedef std::vector<char> Blob;
+template <typename T>
+void put(Blob &b, const T *p, size_t count) {
+    const char *c = (const char *)p;
+    b.insert(b.end(), c, c + sizeof(T) * count);
+}
+template <typename T>
+void get(const Blob &b, size_t &pos, T *p, size_t count) {
+    memcpy(p, b.data() + pos, sizeof(T) * count);
+    pos += sizeof(T) * count;
+}
+
+struct Rank {
+    int rank = 0, device = 0;
+    sz_handle *h = nullptr;
+    std::vector<int64_t> gidx;
+    std::vector<int32_t> owner;
+    int64_t n_owned = 0;
+    std::vector<int32_t> partners;
+    std::vector<int64_t> send_off, send_idx, recv_off, recv_idx;
+    int64_t send_bytes = 0;
+    bool built = false;
+    FloeList pending;
+#ifdef SZ_ORACLE_BUILD
+    std::vector<double> refx, refy;
+    std::vector<int64_t> sbytes, rbytes;  // per partner
+    double disp = 0.0;
+#endif
+};
+
+}  // namespace
+
+struct sz_slab {
+    sz_config cfg;
+    int world = 1, rank_first = 0, n_local = 1;
+    double skin = 0.0;
+    sz_alltoallv_fn cb = nullptr;
+    void *ctx = nullptr;
+    std::vector<double> edges;
+    bool have_edges = false, have_domain = false;
+    int32_t kinds[4] = {0, 0, 0, 0};
+    double vals[4] = {0, 0, 0, 0};
+    double period_x = 0.0, period_y = 0.0, x_west = 0.0;
+    double rmax_max = 0.0;
+    std::vector<Rank> ranks;
+    int64_t rebuilds = 0;
+    char err[512] = {0};
+};
+
+namespace {
+
+int32_t sfail(sz_slab *s, int32_t code, const char *msg) {
+    if (s) snprintf(s->err, sizeof(s->err), "%s", msg);
+    return code;
+}
+int32_t hfail(sz_slab *s, Rank &r, int32_t code, const char *what) {
+    const char *m = FN(last_error)(r.h);
+    snprintf(s->err, sizeof(s->err), "rank %d: %s: %s", r.rank, what, m ? m : "");
+    return code;
+}
+#define HCK(call, what)                                   \
+    do {                                                  \
+        int32_t _rc = (call);                             \
+        if (_rc != SZ_OK) return hfail(S, R, _rc, what); \
+    } while (0)
+
+// out[k][d]: from local rank k to global rank d  ->  in[k][s]: for local rank k from global rank s
+int32_t exchange(sz_slab *S, std::vector<std::vector<Blob>> &out, std::vector<std::vector<Blob>> &in) {
+    const int Wd = S->world;
+    in.assign(S->n_local, std::vector<Blob>(Wd));
+    if (S->n_local == Wd) {
+        for (int k = 0; k < Wd; ++k)
+            for (int d = 0; d < Wd; ++d) in[d][k] = std::move(out[k][d]);
+        return SZ_OK;
+    }
+    // one rank per process: sizes first, then the payload (MPI_Alltoallv semantics)
+    std::vector<int64_t> ssz(Wd), rsz(Wd, 0), o8(Wd + 1), so(Wd + 1, 0), ro(Wd + 1, 0);
+    for (int d = 0; d <= Wd; ++d) o8[d] = 8 * (int64_t)d;
+    for (int d = 0; d < Wd; ++d) ssz[d] = (int64_t)out[0][d].size();
+    if (S->cb(S->ctx, ssz.data(), o8.data(), rsz.data(), o8.data()) != 0) return sfail(S, SZ_ERR_INVALID, "slab: alltoallv callback failed (sizes)");
+    for (int d = 0; d < Wd; ++d) {
+        so[d + 1] = so[d] + ssz[d];
+        ro[d + 1] = ro[d] + rsz[d];
+    }
+    Blob sb((size_t)std::max<int64_t>(so[Wd], 1)), rb((size_t)std::max<int64_t>(ro[Wd], 1));
+    for (int d = 0; d < Wd; ++d)
+        if (ssz[d]) memcpy(sb.data() + so[d], out[0][d].data(), (size_t)ssz[d]);
+    if (S->cb(S->ctx, sb.data(), so.data(), rb.data(), ro.data()) != 0) return sfail(S, SZ_ERR_INVALID, "slab: alltoallv callback failed (payload)");
+    for (int s = 0; s < Wd; ++s) in[0][s].assign(rb.begin() + ro[s], rb.begin() + ro[s + 1]);
+    return SZ_OK;
+}
+
+int owner_of(const sz_slab *S, double cx) {
+    if (S->period_x > 0.0) {  // a floe that left a periodic domain belongs to the slab of its wrapped image
+        double t = fmod(cx - S->x_west, S->period_x);
+        if (t < 0) t += S->period_x;
+        cx = S->x_west + t;
+    }
+    // number of edges <= cx, minus one (searchsorted side = right)
+    int r = (int)(std::upper_bound(S->edges.begin(), S->edges.end(), cx) - S->edges.begin()) - 1;
+    return std::min(std::max(r, 0), S->world - 1);
+}
+
+// does rank r need a copy of a floe at cx with bounding radius rmax?  |x - slab_r| < rmax + rmax_max + skin, minimised
+// over the east/west period: the reference's periodic ghosts (collisions.jl:925-952) then appear on the rank that
+// needs them simply because add_ghosts! runs on its local list
+bool needs(const sz_slab *S, int r, double cx, double rmax) {
+    const double xa = S->edges[r], xb = S->edges[r + 1];
+    auto dist = [&](double x) { return std::max(std::max(xa - x, x - xb), 0.0); };
+    double d = dist(cx);
+    if (S->period_x > 0.0) d = std::min(d, std::min(dist(cx + S->period_x), dist(cx - S->period_x)));
+    return d < rmax + S->rmax_max + S->skin;
+}
+
+// Monte-Carlo points of floe i of a list owned by rank R, wherever they are
+int32_t fetch_mc(sz_slab *S, Rank &R, const FloeList &L, int64_t i, double *x, double *y) {
+    if (L.mcnt[i] == 0) return SZ_OK;
+    if (L.msrc[i] < 0) {
+        memcpy(x, L.mx.data() + L.mhoff[i], sizeof(double) * L.mcnt[i]);
+        memcpy(y, L.my.data() + L.mhoff[i], sizeof(double) * L.mcnt[i]);
+        return SZ_OK;
+    }
+#ifndef SZ_ORACLE_BUILD
+    HCK(szb_fetch_mc(R.h, L.msrc[i], L.mcnt[i], x, y), "fetch Monte-Carlo points");
+    return SZ_OK;
+#else
+    (void)S; (void)R;
+    return SZ_ERR_INVALID;
+#endif
+}
+
+int32_t serialize(sz_slab *S, Rank &R, const FloeList &L, const std::vector<int64_t> &sel, bool with_mc, Blob &b) {
+    int64_t cnt = (int64_t)sel.size();
+    put(b, &cnt, 1);
+    std::vector<double> tx, ty;
+    for (int64_t i : sel) {
+        int64_t hdr[3] = {L.gidx[i], L.vcnt[i], with_mc ? L.mcnt[i] : 0};
+        put(b, hdr, 3);
+        put(b, L.rec.data() + i * W, W);
+        put(b, L.vxy.data() + 2 * L.voff[i], (size_t)(2 * L.vcnt[i]));
+        if (with_mc && L.mcnt[i] > 0) {
+            tx.resize((size_t)L.mcnt[i]); ty.resize((size_t)L.mcnt[i]);
+            int32_t rc = fetch_mc(S, R, L, i, tx.data(), ty.data());
+            if (rc) return rc;
+            put(b, tx.data(), tx.size());
+            put(b, ty.data(), ty.size());
+        }
+    }
+    return SZ_OK;
+}
+
+void deserialize(const Blob &b, FloeList &L) {
+    if (b.size() < 8) return;
+    size_t pos = 0;
+    int64_t cnt = 0;
+    get(b, pos, &cnt, 1);
+    for (int64_t k = 0; k < cnt; ++k) {
+        int64_t hdr[3];
+        get(b, pos, hdr, 3);
+        L.gidx.push_back(hdr[0]);
+        L.vcnt.push_back(hdr[1]);
+        L.mcnt.push_back(hdr[2]);
+        L.msrc.push_back(-1);
+        L.rec.resize(L.rec.size() + W);
+        get(b, pos, L.rec.data() + L.n * W, W);
+        L.voff.push_back((int64_t)L.vxy.size() / 2);
+        L.vxy.resize(L.vxy.size() + 2 * hdr[1]);
+        get(b, pos, L.vxy.data() + 2 * L.voff.back(), (size_t)(2 * hdr[1]));
+        L.mhoff.push_back((int64_t)L.mx.size());
+        if (hdr[2] > 0) {
+            L.mx.resize(L.mx.size() + hdr[2]); L.my.resize(L.my.size() + hdr[2]);
+            get(b, pos, L.mx.data() + L.mhoff.back(), (size_t)hdr[2]);
+            get(b, pos, L.my.data() + L.mhoff.back(), (size_t)hdr[2]);
+        }
+        L.n++;
+    }
+}
+
+// the floes of `parts` merged in ascending global index; origin[k] = which part record k came from
+void merge_sorted(const std::vector<const FloeList *> &parts, const std::vector<bool> &with_mc, FloeList &out, std::vector<int> *origin) {
+    struct Ref { int64_t g; int part; int64_t i; };
+    std::vector<Ref> refs;
+    for (size_t p = 0; p < parts.size(); ++p)
+        for (int64_t i = 0; i < parts[p]->n; ++i) refs.push_back({parts[p]->gidx[i], (int)p, i});
+    std::stable_sort(refs.begin(), refs.end(), [](const Ref &a, const Ref &b) { return a.g < b.g; });
+    for (const Ref &r : refs) {
+        out.push_from(*parts[r.part], r.i, with_mc[r.part]);
+        if (origin) origin->push_back(r.part);
+    }
+}
+
+// every floe rank R holds, as full records (owned ones only); Monte-Carlo points stay resident in the CUDA build
+int32_t download_owned(sz_slab *S, Rank &R, FloeList &L) {
+    sz_counts c;
+    HCK(FN(get_counts)(R.h, &c), "get_counts");
+    const int64_t n = c.n_total;
+    SoaBuf B;
+#ifdef SZ_ORACLE_BUILD
+    B.alloc(n, c.n_vertices, c.n_mc);
+#else
+    B.alloc(n, c.n_vertices, 0);
+    B.s.mc_x = B.s.mc_y = nullptr;
+#endif
+    HCK(FN(download_floes)(R.h, &B.s), "download_floes");
+#ifndef SZ_ORACLE_BUILD
+    HCK(szb_mc_offsets(R.h, B.moff.data()), "mc offsets");
+#endif
+    FloeList all;
+    all.n = n;
+    all.rec.assign((size_t)n * W, 0.0);
+    all.gidx = R.gidx;
+    all.vcnt.resize(n); all.voff.resize(n); all.mcnt.resize(n); all.msrc.resize(n); all.mhoff.resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        record_from_soa(B.s, i, R.gidx[i], all.rec.data() + i * W);
+        all.voff[i] = B.voff[i];
+        all.vcnt[i] = B.voff[i + 1] - B.voff[i];
+        all.mcnt[i] = B.moff[i + 1] - B.moff[i];
+#ifdef SZ_ORACLE_BUILD
+        all.msrc[i] = -1;
+        all.mhoff[i] = B.moff[i];
+#else
+        all.msrc[i] = B.moff[i];
+        all.mhoff[i] = 0;
+#endif
+    }
+    all.vxy.swap(B.vxy);
+#ifdef SZ_ORACLE_BUILD
+    all.mx.swap(B.mx); all.my.swap(B.my);
+#endif
+    for (int64_t i = 0; i < n; ++i)
+        if (R.owner[i] == R.rank) L.push_from(all, i, true);
+    return SZ_OK;
+}
+
+// upload the local list of rank R (owned + halo, ascending global index)
+int32_t upload_local(sz_slab *S, Rank &R, const FloeList &L) {
+    const int64_t n = L.n;
+    int64_t V = 0, M = 0, n_extra = 0;
+    bool any_resident = false;
+    for (int64_t i = 0; i < n; ++i) {
+        V += L.vcnt[i];
+        M += L.mcnt[i];
+        if (L.mcnt[i] > 0 && L.msrc[i] >= 0) any_resident = true;
+        else n_extra += L.mcnt[i];
+    }
+    SoaBuf B;
+    B.alloc(n, V, any_resident ? n_extra : M);
+    std::vector<int64_t> mc_src((size_t)std::max<int64_t>(n, 1), 0);
+    int64_t vo = 0, mo = 0, eo = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *r = L.rec.data() + i * W;
+        for (int f = 0; f < NDF; ++f)
+            for (int w = 0; w < DFIELDS[f].width; ++w) B.d[f][(size_t)(i * DFIELDS[f].width + w)] = r[DFIELDS[f].col + w];
+        B.status[i] = (int32_t)r[C_STATUS];
+        B.id[i] = double_as_i64(r[C_ID]);
+        B.gid[i] = double_as_i64(r[C_GID]);
+        B.voff[i] = vo;
+        memcpy(B.vxy.data() + 2 * vo, L.vxy.data() + 2 * L.voff[i], sizeof(double) * 2 * L.vcnt[i]);
+        vo += L.vcnt[i];
+        B.moff[i] = mo;
+        if (L.mcnt[i] > 0) {
+            if (L.msrc[i] >= 0) {
+                mc_src[i] = L.msrc[i];
+            } else {
+                const int64_t at = any_resident ? eo : mo;
+                memcpy(B.mx.data() + at, L.mx.data() + L.mhoff[i], sizeof(double) * L.mcnt[i]);
+                memcpy(B.my.data() + at, L.my.data() + L.mhoff[i], sizeof(double) * L.mcnt[i]);
+                mc_src[i] = -1 - eo;
+                eo += L.mcnt[i];
+            }
+        }
+        mo += L.mcnt[i];
+    }
+    B.voff[n] = vo;
+    B.moff[n] = mo;
+#ifndef SZ_ORACLE_BUILD
+    if (any_resident) {
+        HCK(szb_upload_floes_resident_mc(R.h, &B.s, mc_src.data(), n_extra), "upload_floes (resident Monte-Carlo points)");
+        return SZ_OK;
+    }
+#endif
+    HCK(FN(upload_floes)(R.h, &B.s), "upload_floes");
+    return SZ_OK;
+}
+
+// Collective.  own[k]: the floes local rank k currently holds as owner (any distribution).  Migrates every floe to
+// the slab of its centroid, builds the halo lists, uploads the local lists and wires the per-step exchange.
+int32_t repartition(sz_slab *S, std::vector<FloeList> &own) {
+    const int Wd = S->world, NL = S->n_local;
+    if (!S->have_domain) return sfail(S, SZ_ERR_INVALID, "slab: build before sz_slab_set_domain");
+    // ---- global bounding radius (and equal-count edges when none were given) ----------------------------------------
+    {
+        std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
+        for (int k = 0; k < NL; ++k) {
+            double m = 0.0;
+            for (int64_t i = 0; i < own[k].n; ++i) m = std::max(m, own[k].rmax(i));
+            for (int d = 0; d < Wd; ++d) put(out[k][d], &m, 1);
+        }
+        int32_t rc = exchange(S, out, in);
+        if (rc) return rc;
+        S->rmax_max = 0.0;
+        for (int s = 0; s < Wd; ++s) {
+            double m = 0.0;
+            size_t pos = 0;
+            if (in[0][s].size() >= 8) get(in[0][s], pos, &m, 1);
+            S->rmax_max = std::max(S->rmax_max, m);
+        }
+    }
+    if (!S->have_edges) {
+        if (NL != Wd) return sfail(S, SZ_ERR_INVALID, "slab: one rank per process needs sz_slab_set_edges");
+        std::vector<double> cx;
+        for (int k = 0; k < NL; ++k)
+            for (int64_t i = 0; i < own[k].n; ++i) cx.push_back(own[k].cx(i));
+        std::sort(cx.begin(), cx.end());
+        S->edges.assign(Wd + 1, 0.0);
+        const double inf = std::numeric_limits<double>::infinity();
+        S->edges[0] = S->period_x > 0.0 ? S->x_west : -inf;
+        S->edges[Wd] = S->period_x > 0.0 ? S->x_west + S->period_x : inf;
+        for (int r = 1; r < Wd; ++r) {  // linear-interpolated quantile r / world
+            if (cx.empty()) { S->edges[r] = 0.0; continue; }
+            double pos = (double)(cx.size() - 1) * r / Wd;
+            size_t lo = (size_t)floor(pos), hi = std::min(lo + 1, cx.size() - 1);
+            S->edges[r] = cx[lo] + (pos - (double)lo) * (cx[hi] - cx[lo]);
+        }
+        S->have_edges = true;
+    }
+    // ---- 1. migration of ownership (full records incl. Monte-Carlo points) -----------------------------------------------
+    std::vector<FloeList> mine(NL);
+    {
+        std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
+        std::vector<FloeList> keep(NL);
+        for (int k = 0; k < NL; ++k) {
+            Rank &R = S->ranks[k];
+            std::vector<std::vector<int64_t>> sel(Wd);
+            for (int64_t i = 0; i < own[k].n; ++i) sel[owner_of(S, own[k].cx(i))].push_back(i);
+            for (int d = 0; d < Wd; ++d) {
+                if (d == R.rank) {
+                    for (int64_t i : sel[d]) keep[k].push_from(own[k], i, true);
+                } else if (!sel[d].empty()) {
+                    int32_t rc = serialize(S, R, own[k], sel[d], true, out[k][d]);
+                    if (rc) return rc;
+                }
+            }
+        }
+        int32_t rc = exchange(S, out, in);
+        if (rc) return rc;
+        for (int k = 0; k < NL; ++k) {
+            FloeList got;
+            for (int s = 0; s < Wd; ++s) deserialize(in[k][s], got);
+            std::vector<const FloeList *> parts = {&keep[k], &got};
+            merge_sorted(parts, {true, true}, mine[k], nullptr);
+        }
+        own.clear();
+    }
+    // ---- 2. halo copies: the OWNER applies the receiver's criterion (no second round needed) --------------------------------
+    std::vector<std::vector<std::vector<int64_t>>> send_sel(NL, std::vector<std::vector<int64_t>>(Wd));
+    std::vector<FloeList> local(NL);
+    std::vector<std::vector<int>> origin(NL);
+    {
+        std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
+        for (int k = 0; k < NL; ++k) {
+            Rank &R = S->ranks[k];
+            for (int d = 0; d < Wd; ++d) {
+                if (d == R.rank) continue;
+                for (int64_t i = 0; i < mine[k].n; ++i)
+                    if (needs(S, d, mine[k].cx(i), mine[k].rmax(i))) send_sel[k][d].push_back(i);
+                if (!send_sel[k][d].empty()) {
+                    int32_t rc = serialize(S, R, mine[k], send_sel[k][d], false, out[k][d]);
+                    if (rc) return rc;
+                }
+            }
+        }
+        int32_t rc = exchange(S, out, in);
+        if (rc) return rc;
+        for (int k = 0; k < NL; ++k) {
+            std::vector<FloeList> halo(Wd);
+            std::vector<const FloeList *> parts;
+            std::vector<bool> with_mc;
+            std::vector<int> part_owner;
+            parts.push_back(&mine[k]); with_mc.push_back(true); part_owner.push_back(S->ranks[k].rank);
+            for (int s = 0; s < Wd; ++s) {
+                deserialize(in[k][s], halo[s]);
+                if (halo[s].n) { parts.push_back(&halo[s]); with_mc.push_back(false); part_owner.push_back(s); }
+            }
+            std::vector<int> org;
+            merge_sorted(parts, with_mc, local[k], &org);
+            origin[k].resize(org.size());
+            for (size_t i = 0; i < org.size(); ++i) origin[k][i] = part_owner[org[i]];
+        }
+    }
+    // ---- 3. local lists, exchange lists, upload, wiring ----------------------------------------------------------------------------
+    std::vector<std::vector<SlabWire>> wires(NL);
+    for (int k = 0; k < NL; ++k) {
+        Rank &R = S->ranks[k];
+        const FloeList &L = local[k];
+        for (int64_t i = 1; i < L.n; ++i)
+            if (L.gidx[i] == L.gidx[i - 1]) return sfail(S, SZ_ERR_INVALID, "slab: duplicate global floe index");
+        R.gidx = L.gidx;
+        R.owner.assign(origin[k].begin(), origin[k].end());
+        R.n_owned = mine[k].n;
+        // position of every owned floe in the local list (both ascending in the global index)
+        std::vector<int64_t> pos_owned((size_t)mine[k].n);
+        {
+            int64_t q = 0;
+            for (int64_t i = 0; i < L.n; ++i)
+                if (R.owner[i] == R.rank) pos_owned[q++] = i;
+        }
+        R.partners.clear();
+        for (int d = 0; d < Wd; ++d) {
+            if (d == R.rank) continue;
+            bool recv_any = false;
+            for (int64_t i = 0; i < L.n && !recv_any; ++i) recv_any = R.owner[i] == d;
+            if (!send_sel[k][d].empty() || recv_any) R.partners.push_back(d);
+        }
+        const int np = (int)R.partners.size();
+        if (np > SZ_SLAB_MAX_PARTNERS) return sfail(S, SZ_ERR_UNSUPPORTED, "slab: a rank has more than 16 exchange partners (slabs thinner than the interaction range)");
+        R.send_off.assign(np + 1, 0); R.recv_off.assign(np + 1, 0);
+        R.send_idx.clear(); R.recv_idx.clear();
+        for (int p = 0; p < np; ++p) {
+            const int d = R.partners[p];
+            for (int64_t i : send_sel[k][d]) R.send_idx.push_back(pos_owned[(size_t)i]);
+            for (int64_t i = 0; i < L.n; ++i)
+                if (R.owner[i] == d) R.recv_idx.push_back(i);
+            R.send_off[p + 1] = (int64_t)R.send_idx.size();
+            R.recv_off[p + 1] = (int64_t)R.recv_idx.size();
+        }
+        int32_t rc = upload_local(S, R, L);
+        if (rc) return rc;
+        std::vector<uint8_t> owned((size_t)std::max<int64_t>(L.n, 1), 0);
+        for (int64_t i = 0; i < L.n; ++i) owned[i] = R.owner[i] == R.rank;
+        R.send_bytes = 0;
+        for (int p = 0; p < np; ++p)
+            for (int64_t q = R.send_off[p]; q < R.send_off[p + 1]; ++q) R.send_bytes += 64 + 16 * L.vcnt[R.send_idx[q]];
+#ifndef SZ_ORACLE_BUILD
+        SlabLists ls;
+        ls.rank = R.rank; ls.n_partners = np; ls.partner_rank = R.partners.data();
+        ls.send_off = R.send_off.data(); ls.send_idx = R.send_idx.data(); ls.recv_off = R.recv_off.data(); ls.recv_idx = R.recv_idx.data();
+        ls.owned = owned.data(); ls.period_x = S->period_x; ls.period_y = S->period_y;
+        wires[k].resize((size_t)std::max(np, 1));
+        HCK(szb_configure(R.h, &ls, wires[k].data()), "configure halo lists");
+#else
+        // oracle build: the records move through szo_halo_pack / szo_halo_unpack; list 2p = send to partner p, 2p+1 = receive
+        std::vector<int64_t> off(2 * np + 1, 0), idx;
+        for (int p = 0; p < np; ++p) {
+            for (int64_t q = R.send_off[p]; q < R.send_off[p + 1]; ++q) idx.push_back(R.send_idx[q] + 1);
+            off[2 * p + 1] = (int64_t)idx.size();
+            for (int64_t q = R.recv_off[p]; q < R.recv_off[p + 1]; ++q) idx.push_back(R.recv_idx[q] + 1);
+            off[2 * p + 2] = (int64_t)idx.size();
+        }
+        if (idx.empty()) idx.push_back(1);
+        HCK(FN(halo_configure)(R.h, 2 * np, off.data(), idx.data()), "halo_configure");
+        R.sbytes.assign(np, 0); R.rbytes.assign(np, 0);
+        for (int p = 0; p < np; ++p) {
+            HCK(FN(halo_bytes)(R.h, 2 * p, &R.sbytes[p]), "halo_bytes");
+            HCK(FN(halo_bytes)(R.h, 2 * p + 1, &R.rbytes[p]), "halo_bytes");
+        }
+        R.refx.resize((size_t)L.n); R.refy.resize((size_t)L.n);
+        for (int64_t i = 0; i < L.n; ++i) { R.refx[i] = L.rec[i * W + C_CX]; R.refy[i] = L.rec[i * W + C_CY]; }
+        R.disp = 0.0;
+#endif
+        R.built = true;
+    }
+#ifndef SZ_ORACLE_BUILD
+    {   // tell every partner where to write (wire p of rank k is for partner p), then map and publish epoch 1
+        std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
+        for (int k = 0; k < NL; ++k) {
+            Rank &R = S->ranks[k];
+            for (size_t p = 0; p < R.partners.size(); ++p) put(out[k][R.partners[p]], &wires[k][p], 1);
+        }
+        int32_t rc = exchange(S, out, in);
+        if (rc) return rc;
+        for (int k = 0; k < NL; ++k) {
+            Rank &R = S->ranks[k];
+            std::vector<SlabWire> peer((size_t)std::max<size_t>(R.partners.size(), 1));
+            for (size_t p = 0; p < R.partners.size(); ++p) {
+                const Blob &b = in[k][R.partners[p]];
+                if (b.size() != sizeof(SlabWire)) return sfail(S, SZ_ERR_INVALID, "slab: partner lists are not symmetric");
+                memcpy(&peer[p], b.data(), sizeof(SlabWire));
+            }
+            HCK(szb_connect(R.h, peer.data()), "connect partners");
+        }
+    }
+#endif
+    return SZ_OK;
+}
+
+#ifdef SZ_ORACLE_BUILD
+// per-step exchange of the oracle build: pack -> host memory / alltoallv -> unpack
+int32_t host_exchange(sz_slab *S) {
+    const int Wd = S->world, NL = S->n_local;
+    std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
+    for (int k = 0; k < NL; ++k) {
+        Rank &R = S->ranks[k];
+        for (size_t p = 0; p < R.partners.size(); ++p) {
+            Blob &b = out[k][R.partners[p]];
+            b.resize((size_t)R.sbytes[p]);
+            if (R.sbytes[p]) HCK(FN(halo_pack)(R.h, 2 * (int)p, b.data(), R.sbytes[p]), "halo_pack");
+        }
+    }
+    int32_t rc = exchange(S, out, in);
+    if (rc) return rc;
+    for (int k = 0; k < NL; ++k) {
+        Rank &R = S->ranks[k];
+        for (size_t p = 0; p < R.partners.size(); ++p) {
+            const Blob &b = in[k][R.partners[p]];
+            if ((int64_t)b.size() != R.rbytes[p]) return sfail(S, SZ_ERR_INVALID, "slab: halo message size differs from the list");
+            if (R.rbytes[p]) HCK(FN(halo_unpack)(R.h, 2 * (int)p + 1, b.data(), R.rbytes[p]), "halo_unpack");
+        }
+    }
+    return SZ_OK;
+}
+
+int32_t host_displacement(sz_slab *S, Rank &R) {
+    const int64_t n = (int64_t)R.gidx.size();
+    if (n == 0) return SZ_OK;
+    std::vector<double> cx((size_t)n), cy((size_t)n);
+    sz_floe_soa q;
+    memset(&q, 0, sizeof(q));
+    q.centroid_x = cx.data(); q.centroid_y = cy.data();
+    HCK(FN(download_floes)(R.h, &q), "download centroids");
+    for (int64_t i = 0; i < n; ++i) {
+        if (R.owner[i] != R.rank) continue;
+        double dx = fabs(cx[i] - R.refx[i]), dy = fabs(cy[i] - R.refy[i]);
+        if (S->period_x > 0.0) dx = std::min(dx, fabs(dx - S->period_x));
+        if (S->period_y > 0.0) dy = std::min(dy, fabs(dy - S->period_y));
+        R.disp = std::max(R.disp, sqrt(dx * dx + dy * dy));
+    }
+    return SZ_OK;
+}
+#endif
+
+double local_max_disp(sz_slab *S) {
+    double m = 0.0;
+    for (Rank &R : S->ranks) {
+#ifdef SZ_ORACLE_BUILD
+        m = std::max(m, R.disp);
+#else
+        m = std::max(m, szb_max_displacement(R.h));
+#endif
+    }
+    return m;
+}
+
+int32_t do_rebuild(sz_slab *S) {
+    std::vector<FloeList> own(S->n_local);
+#ifndef SZ_ORACLE_BUILD
+    for (Rank &R : S->ranks) HCK(szb_release_peers(R.h), "release partners");
+#endif
+    for (int k = 0; k < S->n_local; ++k) {
+        int32_t rc = download_owned(S, S->ranks[k], own[k]);
+        if (rc) return rc;
+    }
+    int32_t rc = repartition(S, own);
+    if (rc == SZ_OK) S->rebuilds++;
+    return rc;
+}
+
+}  // namespace
+
+// ---- C ABI --------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t FN(slab_create)(const sz_config *cfg, int32_t world, int32_t rank_first, int32_t n_local, const int32_t *devices,
+                        double skin, sz_alltoallv_fn alltoallv, void *ctx, sz_slab **out) {
+    if (!cfg || !out || world < 1 || n_local < 1 || rank_first < 0 || rank_first + n_local > world || !(skin >= 0.0)) return SZ_ERR_INVALID;
+    *out = nullptr;
+    if (n_local != world && (n_local != 1 || !alltoallv)) return SZ_ERR_INVALID;  // all ranks here, or one rank per process + a transport
+    sz_slab *S = new (std::nothrow) sz_slab();
+    if (!S) return SZ_ERR_NOMEM;
+    S->cfg = *cfg;
+    S->world = world; S->rank_first = rank_first; S->n_local = n_local; S->skin = skin;
+    S->cb = alltoallv; S->ctx = ctx;
+    S->ranks.resize(n_local);
+    for (int k = 0; k < n_local; ++k) {
+        Rank &R = S->ranks[k];
+        R.rank = rank_first + k;
+        R.device = devices ? devices[k] : 0;
+        sz_config c = *cfg;
+        c.device = R.device;
+        int32_t rc = FN(create)(&c, &R.h);
+        if (rc != SZ_OK) {
+            for (int j = 0; j < k; ++j) FN(destroy)(S->ranks[j].h);
+            delete S;
+            return rc;
+        }
+    }
+    *out = S;
+    return SZ_OK;
+}
+
+void FN(slab_destroy)(sz_slab *S) {
+    if (!S) return;
+#ifndef SZ_ORACLE_BUILD
+    for (Rank &R : S->ranks) if (R.h) szb_release_peers(R.h);
+#endif
+    for (Rank &R : S->ranks) if (R.h) FN(destroy)(R.h);
+    delete S;
+}
+
+const char *FN(slab_last_error)(sz_slab *S) { return S ? S->err : "null slab"; }
+
+int32_t FN(slab_handle)(sz_slab *S, int32_t k, sz_handle **out) {
+    if (!S || !out || k < 0 || k >= S->n_local) return SZ_ERR_INVALID;
+    *out = S->ranks[k].h;
+    return SZ_OK;
+}
+
+int32_t FN(slab_set_grid)(sz_slab *S, int32_t Nx, int32_t Ny, double x0, double xf, double y0, double yf) {
+    if (!S) return SZ_ERR_INVALID;
+    for (Rank &R : S->ranks) HCK(FN(set_grid)(R.h, Nx, Ny, x0, xf, y0, yf), "set_grid");
+    return SZ_OK;
+}
+
+int32_t FN(slab_set_fields)(sz_slab *S, const double *ou, const double *ov, const double *oh, const double *au, const double *av) {
+    if (!S) return SZ_ERR_INVALID;
+    for (Rank &R : S->ranks) HCK(FN(set_fields)(R.h, ou, ov, oh, au, av), "set_fields");
+    return SZ_OK;
+}
+
+int32_t FN(slab_set_domain)(sz_slab *S, const int32_t kinds[4], const double vals[4], const double uv[8], const double rect[16],
+                            int32_t n_topo, const int64_t *toff, const double *txy, const double *tcent, const double *trmax) {
+    if (!S || !kinds || !vals) return SZ_ERR_INVALID;
+    for (Rank &R : S->ranks) HCK(FN(set_domain)(R.h, kinds, vals, uv, rect, n_topo, toff, txy, tcent, trmax), "set_domain");
+    for (int w = 0; w < 4; ++w) { S->kinds[w] = kinds[w]; S->vals[w] = vals[w]; }
+    S->period_x = kinds[2] == SZ_BOUNDARY_PERIODIC ? vals[2] - vals[3] : 0.0;
+    S->period_y = kinds[0] == SZ_BOUNDARY_PERIODIC ? vals[0] - vals[1] : 0.0;
+    S->x_west = vals[3];
+    S->have_domain = true;
+    return SZ_OK;
+}
+
+int32_t FN(slab_set_edges)(sz_slab *S, const double *edges) {
+    if (!S || !edges) return SZ_ERR_INVALID;
+    for (int r = 0; r < S->world; ++r)
+        if (!(edges[r] <= edges[r + 1])) return sfail(S, SZ_ERR_INVALID, "slab: edges must ascend");
+    S->edges.assign(edges, edges + S->world + 1);
+    S->have_edges = true;
+    return SZ_OK;
+}
+
+int32_t FN(slab_build)(sz_slab *S, const sz_floe_soa *const *floes, const int64_t *const *gidx) {
+    if (!S || !floes || !gidx) return SZ_ERR_INVALID;
+    std::vector<FloeList> own(S->n_local);
+    for (int k = 0; k < S->n_local; ++k) {
+        const sz_floe_soa *s = floes[k];
+        if (!s || s->n == 0) continue;
+        if (s->n != s->n_init) return sfail(S, SZ_ERR_INVALID, "slab_build: floe lists must not contain ghosts");
+        if (!gidx[k] || !s->centroid_x || !s->centroid_y || !s->rmax || !s->vert_offsets || !s->vert_xy)
+            return sfail(S, SZ_ERR_INVALID, "slab_build: global indices and geometry arrays are required");
+        FloeList &L = own[k];
+        L.n = s->n;
+        L.rec.assign((size_t)s->n * W, 0.0);
+        L.gidx.assign(gidx[k], gidx[k] + s->n);
+        L.vcnt.resize(s->n); L.voff.resize(s->n); L.mcnt.resize(s->n); L.msrc.assign(s->n, -1); L.mhoff.resize(s->n);
+        for (int64_t i = 0; i < s->n; ++i) {
+            record_from_soa(*s, i, gidx[k][i], L.rec.data() + i * W);
+            L.voff[i] = s->vert_offsets[i];
+            L.vcnt[i] = s->vert_offsets[i + 1] - s->vert_offsets[i];
+            L.mhoff[i] = s->mc_offsets ? s->mc_offsets[i] : 0;
+            L.mcnt[i] = s->mc_offsets ? s->mc_offsets[i + 1] - s->mc_offsets[i] : 0;
+        }
+        L.vxy.assign(s->vert_xy, s->vert_xy + 2 * s->vert_offsets[s->n]);
+        if (s->mc_offsets && s->mc_offsets[s->n] > 0) {
+            if (!s->mc_x || !s->mc_y) return sfail(S, SZ_ERR_INVALID, "slab_build: Monte-Carlo offsets without points");
+            L.mx.assign(s->mc_x, s->mc_x + s->mc_offsets[s->n]);
+            L.my.assign(s->mc_y, s->mc_y + s->mc_offsets[s->n]);
+        }
+    }
+#ifndef SZ_ORACLE_BUILD
+    for (Rank &R : S->ranks) if (R.built) HCK(szb_release_peers(R.h), "release partners");
+#endif
+    return repartition(S, own);
+}
+
+int32_t FN(slab_local_count)(sz_slab *S, int32_t k, int64_t *n, int64_t *n_owned) {
+    if (!S || k < 0 || k >= S->n_local) return SZ_ERR_INVALID;
+    if (n) *n = (int64_t)S->ranks[k].gidx.size();
+    if (n_owned) *n_owned = S->ranks[k].n_owned;
+    return SZ_OK;
+}
+
+int32_t FN(slab_local_index)(sz_slab *S, int32_t k, int64_t *gidx, int32_t *owner) {
+    if (!S || k < 0 || k >= S->n_local) return SZ_ERR_INVALID;
+    const Rank &R = S->ranks[k];
+    if (gidx) std::copy(R.gidx.begin(), R.gidx.end(), gidx);
+    if (owner) std::copy(R.owner.begin(), R.owner.end(), owner);
+    return SZ_OK;
+}
+
+static int32_t slab_step_common(sz_slab *S, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in, sz_floe_soa *const *out) {
+    if (!S) return SZ_ERR_INVALID;
+    for (Rank &R : S->ranks) if (!R.built) return sfail(S, SZ_ERR_INVALID, "slab: step before sz_slab_build");
+    const bool host_mode = out != nullptr;
+#ifndef SZ_ORACLE_BUILD
+    // one host thread drives every local device: enqueue the whole step everywhere, then wait everywhere
+    for (int k = 0; k < S->n_local; ++k) {
+        Rank &R = S->ranks[k];
+        HCK(szb_step_begin(R.h, tstep, do_coupling, host_mode ? in[k] : nullptr, host_mode ? out[k] : nullptr, host_mode), "step");
+    }
+    for (int k = 0; k < S->n_local; ++k) {
+        Rank &R = S->ranks[k];
+        HCK(szb_step_end(R.h, host_mode), "step");
+    }
+#else
+    if (host_mode)
+        for (int k = 0; k < S->n_local; ++k) {
+            Rank &R = S->ranks[k];
+            HCK(FN(upload_state)(R.h, in[k]), "upload_state");
+        }
+    {
+        int32_t rc = host_exchange(S);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < S->n_local; ++k) {
+        Rank &R = S->ranks[k];
+        HCK(FN(step)(R.h, tstep, do_coupling), "step");
+        if (host_mode) {  // like sz_step_host: Monte-Carlo points and ghost lists are not transferred
+            sz_floe_soa o = *out[k];
+            o.mc_x = o.mc_y = nullptr;
+            o.ghost_index = nullptr;
+            HCK(FN(download_floes)(R.h, &o), "download_floes");
+            out[k]->n = o.n;
+            out[k]->n_init = o.n_init;
+        }
+        int32_t rc = host_displacement(S, R);
+        if (rc) return rc;
+    }
+#endif
+    // every rank lives here: the library renews the lists by itself
+    if (S->n_local == S->world && S->world > 1 && local_max_disp(S) > 0.5 * S->skin) return do_rebuild(S);
+    return SZ_OK;
+}
+
+int32_t FN(slab_step)(sz_slab *S, int64_t tstep, int32_t do_coupling) { return slab_step_common(S, tstep, do_coupling, nullptr, nullptr); }
+
+int32_t FN(slab_step_host)(sz_slab *S, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in, sz_floe_soa *const *out) {
+    if (!S || !in || !out) return SZ_ERR_INVALID;
+    for (int k = 0; k < S->n_local; ++k)
+        if (!in[k] || !out[k]) return sfail(S, SZ_ERR_INVALID, "slab_step_host: arrays of every local rank are required");
+    return slab_step_common(S, tstep, do_coupling, in, out);
+}
+
+int32_t FN(slab_max_displacement)(sz_slab *S, double *metres) {
+    if (!S || !metres) return SZ_ERR_INVALID;
+    *metres = local_max_disp(S);
+    return SZ_OK;
+}
+
+int32_t FN(slab_rebuild)(sz_slab *S) {
+    if (!S) return SZ_ERR_INVALID;
+    for (Rank &R : S->ranks) if (!R.built) return sfail(S, SZ_ERR_INVALID, "slab: rebuild before sz_slab_build");
+    return do_rebuild(S);
+}
+
+int32_t FN(slab_refresh_halo)(sz_slab *S) {
+    if (!S) return SZ_ERR_INVALID;
+    for (Rank &R : S->ranks) if (!R.built) return sfail(S, SZ_ERR_INVALID, "slab: refresh before sz_slab_build");
+#ifndef SZ_ORACLE_BUILD
+    for (Rank &R : S->ranks) HCK(szb_refresh_publish(R.h), "publish");
+    for (Rank &R : S->ranks) HCK(szb_refresh_consume(R.h), "consume");
+    return SZ_OK;
+#else
+    return host_exchange(S);
+#endif
+}
+
+int32_t FN(slab_stats)(sz_slab *S, int32_t k, int64_t *send_bytes, int64_t *halo_floes, int64_t *rebuilds) {
+    if (!S || k < 0 || k >= S->n_local) return SZ_ERR_INVALID;
+    const Rank &R = S->ranks[k];
+    if (send_bytes) *send_bytes = R.send_bytes;
+    if (halo_floes) *halo_floes = (int64_t)R.gidx.size() - R.n_owned;
+    if (rebuilds) *rebuilds = S->rebuilds;
+    return SZ_OK;
+}
+
+}  // extern "C"

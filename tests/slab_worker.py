@@ -1,5 +1,6 @@
-"""Worker of tests/test_slab.py::test_two_process_gloo_halo_exchange (importable by a spawned
-process: sets up the import paths itself)."""
+"""Workers of tests/test_slab.py's multi-process tests (importable by a spawned process: sets up the import
+paths itself).  One rank per process: the library's set-up / rebuild messages go through its alltoallv callback
+(torch.distributed point-to-point on gloo, slab._make_transport)."""
 import os
 import sys
 
@@ -9,13 +10,22 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import szload  # noqa: E402,F401
 
 
+def _compare_owned(s, ref, extra_skip=()):
+    from parity_util import STATE_FIELDS, compare_state
+    from subzero_jl_b200 import slab
+    g, own = s.owned_state(0)
+    bad = compare_state(own, slab.extract(ref, g), exact=STATE_FIELDS, skip=())
+    return [b for b in bad if not b.startswith(("mc_offsets", "ghost_") + tuple(extra_skip))]
+
+
 def gloo_worker(rank, world, port, q):
+    """Global list known everywhere; rank r brings the floes with gidx % world == r (ANY distribution works).  A forced
+    rebuild in the middle migrates ownership through the callback."""
     try:
-        import torch
+        import numpy as np
         import torch.distributed as dist
         import fields
         from oracle import szo
-        from parity_util import STATE_FIELDS, compare_state
         from subzero_jl_b200 import slab, synth
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -23,22 +33,22 @@ def gloo_worker(rank, world, port, q):
         lib = szo.oracle()
         f = synth.make_field(700, scale=1.02, walls="periodic", npoints=20, cache=False)
         fields.perturb_state(f.floes)
-        me = slab.partition_global(f.floes, world, f.L, skin=200.0, period_y=f.L)[rank]
-        me.attach(synth.setup_handle(f, lib, threads=1))
-        me.make_buffers(torch.device("cpu"))
+        s = slab.Slab(lib, f, world, rank=rank, skin=200.0, threads=1)
+        s.set_edges(np.concatenate([[0.0], np.quantile(f.floes.centroid_x, np.arange(1, world) / world), [f.L]]))
+        mine = np.arange(rank, f.floes.n, world)
+        s.build([slab.extract(f.floes, mine)], [mine])
         for t in range(3):
             if t == 2:
-                slab.rebuild(me)  # collective: migration + fresh halo lists through all_gather_object
-            me.exchange()
-            me.h.step(t, True)
+                s.rebuild()  # collective: migration + fresh halo lists
+            s.step(t, True)
         h = synth.setup_handle(f, lib, threads=1)
         for t in range(3):
             h.step(t, True)
-        ref = h.download_floes(mc=False)
-        g, own = me.owned_state()
-        bad = compare_state(own, slab.extract(ref, g), exact=STATE_FIELDS)
-        bad = [b for b in bad if not b.startswith(("mc_offsets", "ghost_"))]
-        if me.stale():
+        bad = _compare_owned(s, h.download_floes(mc=False))
+        g, o = s.local_index(0)
+        if not (o != rank).any() or len(g) >= f.floes.n:
+            bad.append("no decomposition happened")
+        if s.stale():
             bad.append("halo lists went stale")
         dist.barrier()
         dist.destroy_process_group()
@@ -48,47 +58,83 @@ def gloo_worker(rank, world, port, q):
         q.put((rank, ["exception: %s\n%s" % (e, traceback.format_exc())]))
 
 
+def _tiles(world, n, walls):
+    import numpy as np
+    import fields
+    from subzero_jl_b200 import slab, synth
+    tiles = [synth.make_field(n, scale=1.02, walls="collision", npoints=20, cache=False, seed=1000 + r) for r in range(world)]
+    for r, t in enumerate(tiles):
+        fields.perturb_state(t.floes, seed=r)
+        slab.shift_x(t.floes, r * t.L)
+        t.floes.id = r * n + np.arange(1, n + 1, dtype=np.int64)  # ids must be unique over all tiles (collisions.jl:751-758)
+    gfield = synth.tiled_model(tiles[0], world, walls)
+    allf = slab.concat([t.floes for t in tiles])
+    return tiles, gfield, allf
+
+
 def tile_worker(rank, world, port, q, walls):
     """Weak-scaling tiles: every rank generates its own tile; compare with one rank holding all tiles."""
     try:
         import numpy as np
-        import torch
         import torch.distributed as dist
-        import fields
         from oracle import szo
-        from parity_util import STATE_FIELDS, compare_state
-        from subzero_jl_b200 import host, slab, synth
+        from subzero_jl_b200 import slab, synth
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
         lib = szo.oracle()
         n = 500
-        tiles = [synth.make_field(n, scale=1.02, walls="collision", npoints=20, cache=False, seed=1000 + r) for r in range(world)]
-        for r, t in enumerate(tiles):
-            fields.perturb_state(t.floes, seed=r)
-            slab.shift_x(t.floes, r * t.L)
-        L = tiles[0].L
-        gfield = synth.tiled_model(tiles[0], world, walls)
-        me = slab.partition_tiles(tiles[rank].floes, rank, world, L, world * L if walls == "shear" else None, skin=200.0)
-        h = synth.setup_handle(gfield, lib, threads=1, floes=me.local)
-        me.attach(h)
-        me.make_buffers(torch.device("cpu"))
+        tiles, gfield, allf = _tiles(world, n, walls)
+        s = slab.Slab(lib, gfield, world, rank=rank, skin=200.0, threads=1)
+        s.set_edges(slab.tile_edges(world, tiles[0].L, walls == "shear"))
+        s.build([tiles[rank].floes], [rank * n + np.arange(n, dtype=np.int64)])
         for t in range(3):
-            me.exchange()
-            me.h.step(t, True)
-        allf = slab.concat([t.floes for t in tiles])
-        allf.id = np.arange(1, allf.n + 1, dtype=np.int64)
+            s.step(t, True)
         hs = synth.setup_handle(gfield, lib, threads=1, floes=allf)
         for t in range(3):
             hs.step(t, True)
-        ref = hs.download_floes(mc=False)
-        g, own = me.owned_state()
-        bad = compare_state(own, slab.extract(ref, g), exact=STATE_FIELDS, skip=())
-        bad = [b for b in bad if not b.startswith(("mc_offsets", "ghost_", "id "))]
-        if me.stale():
+        bad = _compare_owned(s, hs.download_floes(mc=False))
+        g, o = s.local_index(0)
+        if s.stale():
             bad.append("halo lists went stale")
-        if me.local.n >= allf.n:
+        if len(g) >= allf.n or not (o != rank).any():
             bad.append("no decomposition happened")
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bad))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, ["exception: %s\n%s" % (e, traceback.format_exc())]))
+
+
+def cuda_worker(rank, world, port, q):
+    """One process per GPU on the CUDA library: arenas mapped with cudaIpc, flags over NVLink; a forced rebuild in the
+    middle.  Compared with a single-handle run on this rank's own device."""
+    try:
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        import fields
+        from subzero_jl_b200 import capi, slab, synth
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.cuda.set_device(rank)
+        lib = capi.product()
+        f = synth.make_field(20000, scale=1.01, walls="shear", npoints=60, cache=False)
+        fields.perturb_state(f.floes)
+        s = slab.Slab(lib, f, world, rank=rank, skin=500.0, devices=[rank], device=rank)
+        s.set_edges(np.concatenate([[0.0], np.quantile(f.floes.centroid_x, np.arange(1, world) / world), [f.L]]))
+        mine = np.arange(rank, f.floes.n, world)
+        s.build([slab.extract(f.floes, mine)], [mine])
+        for t in range(6):
+            if t == 3:
+                s.rebuild()
+            s.step(t, True)
+        h = synth.setup_handle(f, lib, device=rank)
+        for t in range(6):
+            h.step(t, True)
+        bad = _compare_owned(s, h.download_floes(mc=False))
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, bad))

@@ -1,4 +1,5 @@
-"""One emulated 3-rank slab step (periodic field, CUDA pack / unpack kernels) for compute-sanitizer."""
+"""A few emulated 3-rank slab steps (periodic field, the library's push / unpack kernels) for compute-sanitizer.
+NB: compute-sanitizer is closed on this pool (profiles/r2/r2a_compute_sanitizer_closed.txt); kept for other boxes."""
 import os
 import sys
 
@@ -13,6 +14,6 @@ from subzero_jl_b200 import capi, synth  # noqa: E402
 f = synth.make_field(600, scale=1.01, walls="periodic", npoints=30, cache=False)
 fields.perturb_state(f.floes)
 lib = capi.product()
-ranks = test_slab.run_decomposed(f, lib, 3, 2, device="cuda", walls_period=True)
-test_slab.check_against_single(f, lib, ranks, 2)
+s = test_slab.run_slab(f, lib, 3, 2)
+test_slab.check_against_single(f, lib, s, test_slab.single_rank_reference(f, lib, 2))
 print("slab step ok")
