@@ -946,6 +946,10 @@ static const char *errbits(uint32_t e, char *buf, size_t len) {
 static int32_t handle_overflow(sz_handle *h, const Counters &c) {
     uint32_t e = c.error;
     char buf[256];
+    if (e & ERR_SLAB_TIMEOUT) {
+        szk_clear_error(h->L, h->S);
+        return fail(h, SZ_ERR_INVALID, "slab: a neighbour rank did not publish (or acknowledge) its boundary floes in time — did every rank make the same sz_slab_* call?");
+    }
     if (e & (ERR_POLY_TOO_LARGE | ERR_GHOST_SLOTS)) return fail(h, (e & ERR_POLY_TOO_LARGE) ? SZ_ERR_UNSUPPORTED : SZ_ERR_CAPACITY, errbits(e, buf, sizeof(buf)));
     int32_t rc = SZ_OK;
     if (e & (ERR_PAIR_CAP | ERR_DOM_CAP)) {
@@ -1235,11 +1239,7 @@ static int32_t step_enqueue_direct(sz_handle *h) {
                 fork_coupling();
                 forked = true;
             }
-            if (cur.slab_host_mode && cur.attempt == 0) {
-                // host arrays every step: what the host uploaded is what the neighbours must see
-                if (io) CK(cudaStreamWaitEvent(st, h->ev_up[3], 0));
-                slab_push(h, h->slab.epoch);
-            }
+            // (host arrays every step: step_setup has already published what the host uploaded)
             if (io) CK(cudaStreamWaitEvent(st, h->ev_up[3], 0));  // the halo update lands on top of the uploaded (stale) copies
             slab_unpack(h);
         }
@@ -1417,7 +1417,11 @@ static int32_t step_finish(sz_handle *h) {
     return SZ_OK;
 }
 
-static int32_t step_begin(sz_handle *h, int32_t do_coupling, const HostIO *io, bool slab_host_mode) {
+// First half of a step: the uploads and — for a slab rank stepping on host arrays — the publication of the uploaded
+// boundary floes.  A process that drives several ranks runs this on ALL of them before any rank enqueues the kernel
+// that waits for its neighbours (step_enqueue): nothing that may synchronise the device (allocations, pageable copies)
+// then stands between a waiting kernel and the publication it waits for.
+static int32_t step_setup(sz_handle *h, int32_t do_coupling, const HostIO *io, bool slab_host_mode) {
     StepCur &cur = h->cur;
     cur.do_coupling = do_coupling;
     cur.has_io = io != nullptr;
@@ -1430,6 +1434,19 @@ static int32_t step_begin(sz_handle *h, int32_t do_coupling, const HostIO *io, b
         int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
         if (rc) return rc;
     }
+    // host arrays: what the host uploaded is what the neighbours must see.  Device-resident: the previous step published
+    // behind its update — unless that step ran on host arrays (or this is the first step after a refresh-less rebuild)
+    if (h->slab.on && (slab_host_mode || h->slab.pushed < h->slab.epoch)) {
+        if (io && io->in) CK(cudaStreamWaitEvent(h->L.stream, h->ev_up[3], 0));
+        slab_push(h, h->slab.epoch);
+        h->slab.pushed = h->slab.epoch;
+    }
+    return SZ_OK;
+}
+
+static int32_t step_begin(sz_handle *h, int32_t do_coupling, const HostIO *io, bool slab_host_mode) {
+    int32_t rc = step_setup(h, do_coupling, io, slab_host_mode);
+    if (rc) return rc;
     return step_enqueue(h);
 }
 
@@ -1668,6 +1685,12 @@ int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
     B.dev.push_count = flags + 32; B.dev.unpack_count = flags + 48;
     B.dev.owned = B.d_owned; B.dev.refx = B.d_refx; B.dev.refy = B.d_refy;
     B.dev.period_x = l->period_x; B.dev.period_y = l->period_y;
+    {
+        const char *ts = getenv("SZ_SLAB_TIMEOUT_S");
+        double sec = ts ? atof(ts) : 20.0;
+        if (!(sec > 0.0)) sec = 20.0;
+        B.dev.timeout_ns = (unsigned long long)(sec * 1e9);
+    }
     cudaIpcMemHandle_t ipc;
     memset(&ipc, 0, sizeof(ipc));
     if (cudaIpcGetMemHandle(&ipc, B.arena) != cudaSuccess) {  // same-process partners do not need it
@@ -1742,7 +1765,13 @@ int32_t szb_connect(sz_handle *h, const SlabWire *peer_wire) {
     return SZ_OK;
 }
 
-int32_t szb_step_begin(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out, int32_t host_mode) {
+int32_t szb_step_begin(sz_handle *h) {
+    if (!h || !h->slab.on) return SZ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    return step_enqueue(h);
+}
+
+int32_t szb_step_publish(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out, int32_t host_mode) {
     (void)tstep;
     if (!h || !h->slab.on) return fail(h, SZ_ERR_INVALID, "slab step on a handle without halo lists");
     if (!h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step before set_domain/upload_floes");
@@ -1753,9 +1782,9 @@ int32_t szb_step_begin(sz_handle *h, int64_t tstep, int32_t do_coupling, const s
         int32_t rc = prepare_step_host(h, do_coupling, in, out);
         if (rc) return rc;
         HostIO io = {in, out};
-        return step_begin(h, do_coupling, &io, true);
+        return step_setup(h, do_coupling, &io, true);
     }
-    return step_begin(h, do_coupling, nullptr, false);
+    return step_setup(h, do_coupling, nullptr, false);
 }
 
 int32_t szb_step_end(sz_handle *h, int32_t host_mode) {

@@ -45,6 +45,7 @@ enum : uint32_t {
     ERR_GHOST_SLOTS = 256u,
     ERR_CREC_CAP = 512u,    // floe -> cell registry records
     ERR_CELL_TABLE = 1024u, // one floe touches more than 32 grid cells
+    ERR_SLAB_TIMEOUT = 2048u,  // a slab neighbour did not publish / acknowledge its halo records in time
 };
 
 struct Counters {
@@ -202,6 +203,7 @@ struct SlabDev {
     const unsigned char *owned;              // [n_init] 1 = this rank owns the floe
     const double *refx, *refy;               // centroids when the lists were built
     double period_x, period_y;               // 0 = not periodic
+    unsigned long long timeout_ns;           // give up waiting for a neighbour's flag after this long (ERR_SLAB_TIMEOUT)
 };
 
 __host__ __device__ inline int sz_div_up(long long a, int b) { return (int)((a + b - 1) / b); }

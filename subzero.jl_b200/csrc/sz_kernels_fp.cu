@@ -678,12 +678,34 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
 __device__ __forceinline__ void st_release_sys(int *p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= want.  A neighbour that never publishes (its step failed, its process died) must not hang this GPU:
+// after timeout_ns the step is abandoned with ERR_SLAB_TIMEOUT (every later kernel of the step returns at once).
+__device__ __forceinline__ bool slab_wait(const int *flag, int want, unsigned long long timeout_ns, Counters *cnt) {
+    if (ld_acquire_sys(flag) >= want) return true;
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+        for (int k = 0; k < 64; ++k) {
+            if (ld_acquire_sys(flag) >= want) return true;
+            __nanosleep(100);
+        }
+        if (global_ns() - t0 > timeout_ns) {
+            atomicOr(&cnt->error, ERR_SLAB_TIMEOUT);
+            return false;
+        }
+    }
+}
 __device__ __forceinline__ unsigned long long enc_disp(double x) {  // x >= 0: the bit pattern is order-preserving
     return (unsigned long long)__double_as_longlong(x);
 }
 
 __global__ void __launch_bounds__(128) k_slab_push(Store S, SlabDev D, int epoch) {
     Counters *cnt = S.cnt;
+    __shared__ int ok;
     if (cnt->error) return;  // an overflowing step is repeated: nothing is published
     const int y = blockIdx.y;
     if (y == D.n_partners) {  // displacement of the owned floes (periodic wrap taken out, collisions.jl:943-949)
@@ -703,9 +725,9 @@ __global__ void __launch_bounds__(128) k_slab_push(Store S, SlabDev D, int epoch
     const SlabPartnerDev &p = D.p[y];
     const int nb = (p.send_n + blockDim.x - 1) / blockDim.x;
     if ((int)blockIdx.x >= nb) return;
-    if (threadIdx.x == 0)
-        while (ld_acquire_sys(p.l_ack) < epoch - 2) __nanosleep(64);  // the partner is done with this half of its arena
+    if (threadIdx.x == 0) ok = slab_wait(p.l_ack, epoch - 2, D.timeout_ns, cnt);  // the partner is done with this half of its arena
     __syncthreads();
+    if (!ok) return;
     double *buf = p.r_stage[epoch & 1];
     double2 *vx = (double2 *)(buf + 8 * (size_t)p.send_n);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -733,13 +755,14 @@ __global__ void __launch_bounds__(128) k_slab_push(Store S, SlabDev D, int epoch
 }
 
 __global__ void __launch_bounds__(128) k_slab_unpack(Store S, SlabDev D, int epoch) {
+    __shared__ int ok;
     const int y = blockIdx.y;
     const SlabPartnerDev &p = D.p[y];
     const int nb = (p.recv_n + blockDim.x - 1) / blockDim.x;
     if ((int)blockIdx.x >= nb) return;
-    if (threadIdx.x == 0)
-        while (ld_acquire_sys(p.l_ready) < epoch) __nanosleep(64);
+    if (threadIdx.x == 0) ok = slab_wait(p.l_ready, epoch, D.timeout_ns, S.cnt);
     __syncthreads();
+    if (!ok) return;
     const double *buf = p.l_stage[epoch & 1];
     const double2 *vx = (const double2 *)(buf + 8 * (size_t)p.recv_n);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -816,10 +816,14 @@ static int32_t slab_step_common(sz_slab *S, int64_t tstep, int32_t do_coupling, 
     for (Rank &R : S->ranks) if (!R.built) return sfail(S, SZ_ERR_INVALID, "slab: step before sz_slab_build");
     const bool host_mode = out != nullptr;
 #ifndef SZ_ORACLE_BUILD
-    // one host thread drives every local device: enqueue the whole step everywhere, then wait everywhere
+    // one host thread drives every local device: uploads + publication everywhere, kernels everywhere, wait everywhere
     for (int k = 0; k < S->n_local; ++k) {
         Rank &R = S->ranks[k];
-        HCK(szb_step_begin(R.h, tstep, do_coupling, host_mode ? in[k] : nullptr, host_mode ? out[k] : nullptr, host_mode), "step");
+        HCK(szb_step_publish(R.h, tstep, do_coupling, host_mode ? in[k] : nullptr, host_mode ? out[k] : nullptr, host_mode), "step");
+    }
+    for (int k = 0; k < S->n_local; ++k) {
+        Rank &R = S->ranks[k];
+        HCK(szb_step_begin(R.h), "step");
     }
     for (int k = 0; k < S->n_local; ++k) {
         Rank &R = S->ranks[k];

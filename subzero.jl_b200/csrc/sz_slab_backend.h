@@ -32,8 +32,11 @@ int32_t szb_release_peers(sz_handle *h);
 int32_t szb_configure(sz_handle *h, const SlabLists *lists, SlabWire *wire_out);
 // peer_wire[p] = what partner p exported for this rank; ends with the first publication (epoch 1)
 int32_t szb_connect(sz_handle *h, const SlabWire *peer_wire);
-// one timestep, split so that one host thread can drive several devices: enqueue on all ranks, then wait on all
-int32_t szb_step_begin(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out, int32_t host_mode);
+// One timestep in three phases, so that one host thread can drive several ranks: on ALL ranks the uploads and (host
+// arrays) the publication of the uploaded boundary floes, then on all ranks the kernels — the first of which waits for
+// the neighbours' records —, then wait on all ranks.
+int32_t szb_step_publish(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out, int32_t host_mode);
+int32_t szb_step_begin(sz_handle *h);
 int32_t szb_step_end(sz_handle *h, int32_t host_mode);
 double szb_max_displacement(sz_handle *h);
 // halo copies := owners' current state, without stepping: publish (if the current epoch is not out yet) on every rank,
