@@ -289,16 +289,18 @@ def main():
         h = sl.handles[0]
         fa0 = tile.floes
     N, M, V = fa0.n, int(fa0.mc_offsets[-1]), int(fa0.vert_offsets[-1])
-    rebuild_s = []
+    rebuild_s, polls = [], []
 
     def maybe_rebuild(t):
-        # the lists are valid while no owned floe travelled more than skin / 2; polled every 50 steps against skin / 4
-        # (one 8-byte all-reduce), so floes may move another skin / 4 in between
-        if sl is None or t % 50 != 49:
+        # the lists are valid while no owned floe travelled more than skin / 2; polled every 25 steps against 0.4 skin
+        # (one 8-byte all-reduce; the library keeps the displacement current without a synchronisation), so floes may
+        # move another skin / 10 in between (1.2 m/s at the default skin)
+        if sl is None or t % 25 != 24:
             return
         d = torch.tensor([sl.max_displacement()], dtype=torch.float64, device="cuda")
         dist.all_reduce(d, op=dist.ReduceOp.MAX)
-        if float(d[0]) > 0.25 * args.skin:
+        polls.append((t, float(d[0])))
+        if float(d[0]) > 0.4 * args.skin:
             t0 = time.perf_counter()
             sl.rebuild()
             rebuild_s.append(time.perf_counter() - t0)
@@ -427,7 +429,7 @@ def main():
         assert int(hs[3]) == 0, "halo copies differ from their owners' state on %d floes" % int(hs[3])
         halo = {"halo_floes_max": int(hmax[0]), "send_bytes_per_step_max": int(hmax[1]), "skin_m": args.skin,
                 "max_displacement_m": float(hmax[2]), "lists_stale": bool(hmax[2] > 0.5 * args.skin),
-                "rebuilds": int(hmax[4]), "rebuild_seconds_total_max": float(hmax[5]),
+                "rebuilds": int(hmax[4]), "rebuild_seconds_total_max": float(hmax[5]), "displacement_polls": polls[-12:],
                 "halo_copies_equal_owner_state": True,
                 "exchange": "sz_slab_step: k_slab_unpack (wait for the neighbours' flag, scatter) -> step -> k_slab_push (8 doubles + "
                             "ring per boundary floe straight into the neighbours' arenas over NVLink, cudaIpc-mapped) — no NCCL "

@@ -20,6 +20,9 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+#include <cstdlib>
+
 #include "sz_slab_backend.h"
 
 #define FN(name) SZ_FN(name)
@@ -56,28 +59,24 @@ struct FloeList {
     std::vector<int64_t> gidx, vcnt, voff, mcnt, msrc, mhoff;
     std::vector<double> vxy, mx, my;
 
-    void push_from(const FloeList &s, int64_t i, bool with_mc) {
-        rec.insert(rec.end(), s.rec.begin() + i * W, s.rec.begin() + (i + 1) * W);
-        gidx.push_back(s.gidx[i]);
-        vcnt.push_back(s.vcnt[i]);
-        voff.push_back((int64_t)vxy.size() / 2);
-        vxy.insert(vxy.end(), s.vxy.begin() + 2 * s.voff[i], s.vxy.begin() + 2 * (s.voff[i] + s.vcnt[i]));
-        if (!with_mc) {
-            mcnt.push_back(0); msrc.push_back(-1); mhoff.push_back((int64_t)mx.size());
-        } else {
-            mcnt.push_back(s.mcnt[i]);
-            msrc.push_back(s.msrc[i]);
-            mhoff.push_back((int64_t)mx.size());
-            if (s.msrc[i] < 0) {
-                mx.insert(mx.end(), s.mx.begin() + s.mhoff[i], s.mx.begin() + s.mhoff[i] + s.mcnt[i]);
-                my.insert(my.end(), s.my.begin() + s.mhoff[i], s.my.begin() + s.mhoff[i] + s.mcnt[i]);
-            }
-        }
-        n++;
-    }
     double cx(int64_t i) const { return rec[i * W + C_CX]; }
     double rmax(int64_t i) const { return rec[i * W + C_RMAX]; }
 };
+
+// A floe of some FloeList that stays alive: lists are merged, filtered and sorted as references and copied only twice
+// (device -> records, records -> upload arrays).  mc = false: a halo copy, its Monte-Carlo points are not needed.
+struct Ref {
+    const FloeList *L;
+    int64_t i;
+    bool mc;
+    int owner;
+    int64_t g() const { return L->gidx[i]; }
+};
+typedef std::vector<Ref> RefList;
+
+void sort_by_gidx(RefList &r) {
+    std::stable_sort(r.begin(), r.end(), [](const Ref &a, const Ref &b) { return a.g() < b.g(); });
+}
 
 // arrays behind a sz_floe_soa (download target / upload source)
 struct SoaBuf {
@@ -173,6 +172,19 @@ struct sz_slab {
 
 namespace {
 
+// SZ_SLAB_DEBUG=1: wall-clock of the phases of a (re)build on stderr
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(getenv("SZ_SLAB_DEBUG") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(int rank, const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[slab rank %d] %-28s %8.2f ms\n", rank, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int32_t sfail(sz_slab *s, int32_t code, const char *msg) {
     if (s) snprintf(s->err, sizeof(s->err), "%s", msg);
     return code;
@@ -253,11 +265,20 @@ int32_t fetch_mc(sz_slab *S, Rank &R, const FloeList &L, int64_t i, double *x, d
 #endif
 }
 
-int32_t serialize(sz_slab *S, Rank &R, const FloeList &L, const std::vector<int64_t> &sel, bool with_mc, Blob &b) {
+int32_t serialize(sz_slab *S, Rank &R, const RefList &refs, const std::vector<int64_t> &sel, bool with_mc, Blob &b) {
     int64_t cnt = (int64_t)sel.size();
+    size_t bytes = 8;
+    for (int64_t q : sel) {
+        const FloeList &L = *refs[q].L;
+        const int64_t i = refs[q].i;
+        bytes += 24 + 8 * W + 16 * (size_t)L.vcnt[i] + (with_mc ? 16 * (size_t)L.mcnt[i] : 0);
+    }
+    b.reserve(b.size() + bytes);
     put(b, &cnt, 1);
     std::vector<double> tx, ty;
-    for (int64_t i : sel) {
+    for (int64_t q : sel) {
+        const FloeList &L = *refs[q].L;
+        const int64_t i = refs[q].i;
         int64_t hdr[3] = {L.gidx[i], L.vcnt[i], with_mc ? L.mcnt[i] : 0};
         put(b, hdr, 3);
         put(b, L.rec.data() + i * W, W);
@@ -300,19 +321,6 @@ void deserialize(const Blob &b, FloeList &L) {
     }
 }
 
-// the floes of `parts` merged in ascending global index; origin[k] = which part record k came from
-void merge_sorted(const std::vector<const FloeList *> &parts, const std::vector<bool> &with_mc, FloeList &out, std::vector<int> *origin) {
-    struct Ref { int64_t g; int part; int64_t i; };
-    std::vector<Ref> refs;
-    for (size_t p = 0; p < parts.size(); ++p)
-        for (int64_t i = 0; i < parts[p]->n; ++i) refs.push_back({parts[p]->gidx[i], (int)p, i});
-    std::stable_sort(refs.begin(), refs.end(), [](const Ref &a, const Ref &b) { return a.g < b.g; });
-    for (const Ref &r : refs) {
-        out.push_from(*parts[r.part], r.i, with_mc[r.part]);
-        if (origin) origin->push_back(r.part);
-    }
-}
-
 // every floe rank R holds, as full records (owned ones only); Monte-Carlo points stay resident in the CUDA build
 int32_t download_owned(sz_slab *S, Rank &R, FloeList &L) {
     sz_counts c;
@@ -329,71 +337,89 @@ int32_t download_owned(sz_slab *S, Rank &R, FloeList &L) {
 #ifndef SZ_ORACLE_BUILD
     HCK(szb_mc_offsets(R.h, B.moff.data()), "mc offsets");
 #endif
-    FloeList all;
-    all.n = n;
-    all.rec.assign((size_t)n * W, 0.0);
-    all.gidx = R.gidx;
-    all.vcnt.resize(n); all.voff.resize(n); all.mcnt.resize(n); all.msrc.resize(n); all.mhoff.resize(n);
-    for (int64_t i = 0; i < n; ++i) {
-        record_from_soa(B.s, i, R.gidx[i], all.rec.data() + i * W);
-        all.voff[i] = B.voff[i];
-        all.vcnt[i] = B.voff[i + 1] - B.voff[i];
-        all.mcnt[i] = B.moff[i + 1] - B.moff[i];
-#ifdef SZ_ORACLE_BUILD
-        all.msrc[i] = -1;
-        all.mhoff[i] = B.moff[i];
-#else
-        all.msrc[i] = B.moff[i];
-        all.mhoff[i] = 0;
-#endif
-    }
-    all.vxy.swap(B.vxy);
-#ifdef SZ_ORACLE_BUILD
-    all.mx.swap(B.mx); all.my.swap(B.my);
-#endif
+    int64_t no = 0, Vo = 0, Mo = 0;
     for (int64_t i = 0; i < n; ++i)
-        if (R.owner[i] == R.rank) L.push_from(all, i, true);
+        if (R.owner[i] == R.rank) { no++; Vo += B.voff[i + 1] - B.voff[i]; Mo += B.moff[i + 1] - B.moff[i]; }
+    L.n = no;
+    L.rec.resize((size_t)no * W);
+    L.gidx.resize(no); L.vcnt.resize(no); L.voff.resize(no); L.mcnt.resize(no); L.msrc.resize(no); L.mhoff.resize(no);
+    L.vxy.resize((size_t)(2 * Vo));
+#ifdef SZ_ORACLE_BUILD
+    L.mx.resize((size_t)Mo); L.my.resize((size_t)Mo);
+#else
+    (void)Mo;
+#endif
+    int64_t q = 0, vo = 0, mo = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (R.owner[i] != R.rank) continue;
+        record_from_soa(B.s, i, R.gidx[i], L.rec.data() + q * W);
+        L.gidx[q] = R.gidx[i];
+        L.vcnt[q] = B.voff[i + 1] - B.voff[i];
+        L.voff[q] = vo;
+        memcpy(L.vxy.data() + 2 * vo, B.vxy.data() + 2 * B.voff[i], sizeof(double) * 2 * L.vcnt[q]);
+        vo += L.vcnt[q];
+        L.mcnt[q] = B.moff[i + 1] - B.moff[i];
+#ifdef SZ_ORACLE_BUILD
+        L.msrc[q] = -1;
+        L.mhoff[q] = mo;
+        if (L.mcnt[q] > 0) {
+            memcpy(L.mx.data() + mo, B.mx.data() + B.moff[i], sizeof(double) * L.mcnt[q]);
+            memcpy(L.my.data() + mo, B.my.data() + B.moff[i], sizeof(double) * L.mcnt[q]);
+        }
+        mo += L.mcnt[q];
+#else
+        L.msrc[q] = B.moff[i];  // resident: offset in the rank's device array
+        L.mhoff[q] = 0;
+#endif
+        q++;
+    }
+    (void)mo;
     return SZ_OK;
 }
 
 // upload the local list of rank R (owned + halo, ascending global index)
-int32_t upload_local(sz_slab *S, Rank &R, const FloeList &L) {
-    const int64_t n = L.n;
+int32_t upload_local(sz_slab *S, Rank &R, const RefList &refs) {
+    const int64_t n = (int64_t)refs.size();
     int64_t V = 0, M = 0, n_extra = 0;
     bool any_resident = false;
-    for (int64_t i = 0; i < n; ++i) {
-        V += L.vcnt[i];
-        M += L.mcnt[i];
-        if (L.mcnt[i] > 0 && L.msrc[i] >= 0) any_resident = true;
-        else n_extra += L.mcnt[i];
+    for (const Ref &r : refs) {
+        const FloeList &L = *r.L;
+        V += L.vcnt[r.i];
+        if (!r.mc) continue;
+        M += L.mcnt[r.i];
+        if (L.mcnt[r.i] > 0 && L.msrc[r.i] >= 0) any_resident = true;
+        else n_extra += L.mcnt[r.i];
     }
     SoaBuf B;
     B.alloc(n, V, any_resident ? n_extra : M);
     std::vector<int64_t> mc_src((size_t)std::max<int64_t>(n, 1), 0);
     int64_t vo = 0, mo = 0, eo = 0;
     for (int64_t i = 0; i < n; ++i) {
-        const double *r = L.rec.data() + i * W;
+        const FloeList &L = *refs[i].L;
+        const int64_t j = refs[i].i;
+        const double *r = L.rec.data() + j * W;
         for (int f = 0; f < NDF; ++f)
             for (int w = 0; w < DFIELDS[f].width; ++w) B.d[f][(size_t)(i * DFIELDS[f].width + w)] = r[DFIELDS[f].col + w];
         B.status[i] = (int32_t)r[C_STATUS];
         B.id[i] = double_as_i64(r[C_ID]);
         B.gid[i] = double_as_i64(r[C_GID]);
         B.voff[i] = vo;
-        memcpy(B.vxy.data() + 2 * vo, L.vxy.data() + 2 * L.voff[i], sizeof(double) * 2 * L.vcnt[i]);
-        vo += L.vcnt[i];
+        memcpy(B.vxy.data() + 2 * vo, L.vxy.data() + 2 * L.voff[j], sizeof(double) * 2 * L.vcnt[j]);
+        vo += L.vcnt[j];
         B.moff[i] = mo;
-        if (L.mcnt[i] > 0) {
-            if (L.msrc[i] >= 0) {
-                mc_src[i] = L.msrc[i];
+        const int64_t mc = refs[i].mc ? L.mcnt[j] : 0;
+        if (mc > 0) {
+            if (L.msrc[j] >= 0) {
+                mc_src[i] = L.msrc[j];
             } else {
                 const int64_t at = any_resident ? eo : mo;
-                memcpy(B.mx.data() + at, L.mx.data() + L.mhoff[i], sizeof(double) * L.mcnt[i]);
-                memcpy(B.my.data() + at, L.my.data() + L.mhoff[i], sizeof(double) * L.mcnt[i]);
+                memcpy(B.mx.data() + at, L.mx.data() + L.mhoff[j], sizeof(double) * mc);
+                memcpy(B.my.data() + at, L.my.data() + L.mhoff[j], sizeof(double) * mc);
                 mc_src[i] = -1 - eo;
-                eo += L.mcnt[i];
+                eo += mc;
             }
         }
-        mo += L.mcnt[i];
+        mo += mc;
     }
     B.voff[n] = vo;
     B.moff[n] = mo;
@@ -412,6 +438,8 @@ int32_t upload_local(sz_slab *S, Rank &R, const FloeList &L) {
 int32_t repartition(sz_slab *S, std::vector<FloeList> &own) {
     const int Wd = S->world, NL = S->n_local;
     if (!S->have_domain) return sfail(S, SZ_ERR_INVALID, "slab: build before sz_slab_set_domain");
+    PhaseTimer pt;
+    const int r0 = S->ranks[0].rank;
     // ---- global bounding radius (and equal-count edges when none were given) ----------------------------------------
     {
         std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
@@ -448,46 +476,51 @@ int32_t repartition(sz_slab *S, std::vector<FloeList> &own) {
         }
         S->have_edges = true;
     }
+    pt.lap(r0, "rmax / edges");
     // ---- 1. migration of ownership (full records incl. Monte-Carlo points) -----------------------------------------------
-    std::vector<FloeList> mine(NL);
+    std::vector<RefList> mine(NL);
+    std::vector<FloeList> got(NL);
     {
         std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
-        std::vector<FloeList> keep(NL);
         for (int k = 0; k < NL; ++k) {
             Rank &R = S->ranks[k];
+            RefList all((size_t)own[k].n);
             std::vector<std::vector<int64_t>> sel(Wd);
-            for (int64_t i = 0; i < own[k].n; ++i) sel[owner_of(S, own[k].cx(i))].push_back(i);
-            for (int d = 0; d < Wd; ++d) {
-                if (d == R.rank) {
-                    for (int64_t i : sel[d]) keep[k].push_from(own[k], i, true);
-                } else if (!sel[d].empty()) {
-                    int32_t rc = serialize(S, R, own[k], sel[d], true, out[k][d]);
+            for (int64_t i = 0; i < own[k].n; ++i) {
+                all[i] = {&own[k], i, true, 0};
+                const int d = owner_of(S, own[k].cx(i));
+                if (d == R.rank) mine[k].push_back({&own[k], i, true, R.rank});
+                else sel[d].push_back(i);
+            }
+            for (int d = 0; d < Wd; ++d)
+                if (d != R.rank && !sel[d].empty()) {
+                    int32_t rc = serialize(S, R, all, sel[d], true, out[k][d]);
                     if (rc) return rc;
                 }
-            }
         }
         int32_t rc = exchange(S, out, in);
         if (rc) return rc;
         for (int k = 0; k < NL; ++k) {
-            FloeList got;
-            for (int s = 0; s < Wd; ++s) deserialize(in[k][s], got);
-            std::vector<const FloeList *> parts = {&keep[k], &got};
-            merge_sorted(parts, {true, true}, mine[k], nullptr);
+            for (int s = 0; s < Wd; ++s) deserialize(in[k][s], got[k]);
+            for (int64_t i = 0; i < got[k].n; ++i) mine[k].push_back({&got[k], i, true, S->ranks[k].rank});
+            sort_by_gidx(mine[k]);
         }
-        own.clear();
     }
+    pt.lap(r0, "migration");
     // ---- 2. halo copies: the OWNER applies the receiver's criterion (no second round needed) --------------------------------
     std::vector<std::vector<std::vector<int64_t>>> send_sel(NL, std::vector<std::vector<int64_t>>(Wd));
-    std::vector<FloeList> local(NL);
-    std::vector<std::vector<int>> origin(NL);
+    std::vector<RefList> local(NL);
+    std::vector<std::vector<FloeList>> halo(NL, std::vector<FloeList>(Wd));
     {
         std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
         for (int k = 0; k < NL; ++k) {
             Rank &R = S->ranks[k];
             for (int d = 0; d < Wd; ++d) {
                 if (d == R.rank) continue;
-                for (int64_t i = 0; i < mine[k].n; ++i)
-                    if (needs(S, d, mine[k].cx(i), mine[k].rmax(i))) send_sel[k][d].push_back(i);
+                for (int64_t q = 0; q < (int64_t)mine[k].size(); ++q) {
+                    const Ref &r = mine[k][q];
+                    if (needs(S, d, r.L->cx(r.i), r.L->rmax(r.i))) send_sel[k][d].push_back(q);
+                }
                 if (!send_sel[k][d].empty()) {
                     int32_t rc = serialize(S, R, mine[k], send_sel[k][d], false, out[k][d]);
                     if (rc) return rc;
@@ -497,45 +530,42 @@ int32_t repartition(sz_slab *S, std::vector<FloeList> &own) {
         int32_t rc = exchange(S, out, in);
         if (rc) return rc;
         for (int k = 0; k < NL; ++k) {
-            std::vector<FloeList> halo(Wd);
-            std::vector<const FloeList *> parts;
-            std::vector<bool> with_mc;
-            std::vector<int> part_owner;
-            parts.push_back(&mine[k]); with_mc.push_back(true); part_owner.push_back(S->ranks[k].rank);
+            local[k] = mine[k];
             for (int s = 0; s < Wd; ++s) {
-                deserialize(in[k][s], halo[s]);
-                if (halo[s].n) { parts.push_back(&halo[s]); with_mc.push_back(false); part_owner.push_back(s); }
+                deserialize(in[k][s], halo[k][s]);
+                for (int64_t i = 0; i < halo[k][s].n; ++i) local[k].push_back({&halo[k][s], i, false, s});
             }
-            std::vector<int> org;
-            merge_sorted(parts, with_mc, local[k], &org);
-            origin[k].resize(org.size());
-            for (size_t i = 0; i < org.size(); ++i) origin[k][i] = part_owner[org[i]];
+            sort_by_gidx(local[k]);
         }
     }
+    pt.lap(r0, "halo selection + exchange");
     // ---- 3. local lists, exchange lists, upload, wiring ----------------------------------------------------------------------------
     std::vector<std::vector<SlabWire>> wires(NL);
     for (int k = 0; k < NL; ++k) {
         Rank &R = S->ranks[k];
-        const FloeList &L = local[k];
-        for (int64_t i = 1; i < L.n; ++i)
-            if (L.gidx[i] == L.gidx[i - 1]) return sfail(S, SZ_ERR_INVALID, "slab: duplicate global floe index");
-        R.gidx = L.gidx;
-        R.owner.assign(origin[k].begin(), origin[k].end());
-        R.n_owned = mine[k].n;
+        const RefList &L = local[k];
+        const int64_t Ln = (int64_t)L.size();
+        R.gidx.resize((size_t)Ln);
+        R.owner.resize((size_t)Ln);
+        for (int64_t i = 0; i < Ln; ++i) {
+            R.gidx[i] = L[i].g();
+            R.owner[i] = L[i].owner;
+            if (i > 0 && R.gidx[i] == R.gidx[i - 1]) return sfail(S, SZ_ERR_INVALID, "slab: duplicate global floe index");
+        }
+        R.n_owned = (int64_t)mine[k].size();
         // position of every owned floe in the local list (both ascending in the global index)
-        std::vector<int64_t> pos_owned((size_t)mine[k].n);
+        std::vector<int64_t> pos_owned((size_t)mine[k].size());
+        std::vector<std::vector<int64_t>> recv_by(Wd);
         {
             int64_t q = 0;
-            for (int64_t i = 0; i < L.n; ++i)
+            for (int64_t i = 0; i < Ln; ++i) {
                 if (R.owner[i] == R.rank) pos_owned[q++] = i;
+                else recv_by[R.owner[i]].push_back(i);
+            }
         }
         R.partners.clear();
-        for (int d = 0; d < Wd; ++d) {
-            if (d == R.rank) continue;
-            bool recv_any = false;
-            for (int64_t i = 0; i < L.n && !recv_any; ++i) recv_any = R.owner[i] == d;
-            if (!send_sel[k][d].empty() || recv_any) R.partners.push_back(d);
-        }
+        for (int d = 0; d < Wd; ++d)
+            if (d != R.rank && (!send_sel[k][d].empty() || !recv_by[d].empty())) R.partners.push_back(d);
         const int np = (int)R.partners.size();
         if (np > SZ_SLAB_MAX_PARTNERS) return sfail(S, SZ_ERR_UNSUPPORTED, "slab: a rank has more than 16 exchange partners (slabs thinner than the interaction range)");
         R.send_off.assign(np + 1, 0); R.recv_off.assign(np + 1, 0);
@@ -543,18 +573,22 @@ int32_t repartition(sz_slab *S, std::vector<FloeList> &own) {
         for (int p = 0; p < np; ++p) {
             const int d = R.partners[p];
             for (int64_t i : send_sel[k][d]) R.send_idx.push_back(pos_owned[(size_t)i]);
-            for (int64_t i = 0; i < L.n; ++i)
-                if (R.owner[i] == d) R.recv_idx.push_back(i);
+            R.recv_idx.insert(R.recv_idx.end(), recv_by[d].begin(), recv_by[d].end());
             R.send_off[p + 1] = (int64_t)R.send_idx.size();
             R.recv_off[p + 1] = (int64_t)R.recv_idx.size();
         }
+        pt.lap(R.rank, "exchange lists");
         int32_t rc = upload_local(S, R, L);
         if (rc) return rc;
-        std::vector<uint8_t> owned((size_t)std::max<int64_t>(L.n, 1), 0);
-        for (int64_t i = 0; i < L.n; ++i) owned[i] = R.owner[i] == R.rank;
+        pt.lap(R.rank, "upload local list");
+        std::vector<uint8_t> owned((size_t)std::max<int64_t>(Ln, 1), 0);
+        for (int64_t i = 0; i < Ln; ++i) owned[i] = R.owner[i] == R.rank;
         R.send_bytes = 0;
         for (int p = 0; p < np; ++p)
-            for (int64_t q = R.send_off[p]; q < R.send_off[p + 1]; ++q) R.send_bytes += 64 + 16 * L.vcnt[R.send_idx[q]];
+            for (int64_t q = R.send_off[p]; q < R.send_off[p + 1]; ++q) {
+                const Ref &r = L[(size_t)R.send_idx[q]];
+                R.send_bytes += 64 + 16 * r.L->vcnt[r.i];
+            }
 #ifndef SZ_ORACLE_BUILD
         SlabLists ls;
         ls.rank = R.rank; ls.n_partners = np; ls.partner_rank = R.partners.data();
@@ -578,12 +612,16 @@ int32_t repartition(sz_slab *S, std::vector<FloeList> &own) {
             HCK(FN(halo_bytes)(R.h, 2 * p, &R.sbytes[p]), "halo_bytes");
             HCK(FN(halo_bytes)(R.h, 2 * p + 1, &R.rbytes[p]), "halo_bytes");
         }
-        R.refx.resize((size_t)L.n); R.refy.resize((size_t)L.n);
-        for (int64_t i = 0; i < L.n; ++i) { R.refx[i] = L.rec[i * W + C_CX]; R.refy[i] = L.rec[i * W + C_CY]; }
+        R.refx.resize((size_t)Ln); R.refy.resize((size_t)Ln);
+        for (int64_t i = 0; i < Ln; ++i) {
+            R.refx[i] = L[i].L->rec[L[i].i * W + C_CX];
+            R.refy[i] = L[i].L->rec[L[i].i * W + C_CY];
+        }
         R.disp = 0.0;
 #endif
         R.built = true;
     }
+    pt.lap(r0, "configure");
 #ifndef SZ_ORACLE_BUILD
     {   // tell every partner where to write (wire p of rank k is for partner p), then map and publish epoch 1
         std::vector<std::vector<Blob>> out(NL, std::vector<Blob>(Wd)), in;
@@ -605,6 +643,7 @@ int32_t repartition(sz_slab *S, std::vector<FloeList> &own) {
         }
     }
 #endif
+    pt.lap(r0, "wiring + first publication");
     return SZ_OK;
 }
 
@@ -667,6 +706,7 @@ double local_max_disp(sz_slab *S) {
 
 int32_t do_rebuild(sz_slab *S) {
     std::vector<FloeList> own(S->n_local);
+    PhaseTimer pt;
 #ifndef SZ_ORACLE_BUILD
     for (Rank &R : S->ranks) HCK(szb_release_peers(R.h), "release partners");
 #endif
@@ -674,6 +714,7 @@ int32_t do_rebuild(sz_slab *S) {
         int32_t rc = download_owned(S, S->ranks[k], own[k]);
         if (rc) return rc;
     }
+    pt.lap(S->ranks[0].rank, "download owned floes");
     int32_t rc = repartition(S, own);
     if (rc == SZ_OK) S->rebuilds++;
     return rc;
