@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the one-step CUDA-vs-oracle comparison on the benchmark field")
     ap.add_argument("--two-way", action="store_true", help="also turn on two-way coupling (not part of the headline config)")
-    ap.add_argument("--skin", type=float, default=3000.0, help="halo-list skin in metres (N > 1): lists stay valid while floes moved < skin/2")
+    ap.add_argument("--skin", type=float, default=6000.0, help="halo-list skin in metres (N > 1): lists stay valid while floes moved < skin/2")
     return ap.parse_args()
 
 

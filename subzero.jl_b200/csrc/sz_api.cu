@@ -50,7 +50,13 @@ struct SlabState {
     double *d_refx, *d_refy;
     unsigned char *arena;      // flags + double-buffered staging, written by the partners
     size_t arena_bytes;
-    std::vector<void *> ipc_open;  // partners' arenas mapped from other processes
+    // partners' arenas mapped from other processes, kept across rebuilds: (pid, arena generation) -> mapping.  An arena
+    // lives until it is too small; the mapping of a replaced arena is closed when its successor is connected, and the
+    // owner frees a replaced arena only one rebuild later (cudaFree before the importers closed is undefined)
+    struct IpcMap { int pid; unsigned long long gen; void *ptr; };
+    std::vector<IpcMap> ipc_open;
+    unsigned long long arena_gen;
+    std::vector<unsigned char *> retired;
     std::vector<long long> send_bytes;  // per partner
     int epoch;      // epoch the next step consumes
     int pushed;     // last epoch published to the partners
@@ -323,6 +329,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->slab.d_send_idx = h->slab.d_recv_idx = nullptr; h->slab.d_send_voff = h->slab.d_recv_voff = nullptr;
     h->slab.d_owned = nullptr; h->slab.d_refx = h->slab.d_refy = nullptr; h->slab.arena = nullptr; h->slab.arena_bytes = 0;
     h->slab.epoch = 1; h->slab.pushed = 0; h->slab.max_send = h->slab.max_recv = 0; h->slab.send_bytes_total = 0;
+    h->slab.arena_gen = 0;
     memset(&h->cur, 0, sizeof(h->cur));
     memset(&h->hD, 0, sizeof(h->hD));
     memset(&h->P, 0, sizeof(h->P));
@@ -394,8 +401,10 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.order_cls); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
     dfree(h->d_hl_idx); dfree(h->d_hl_voff);
-    for (void *p : h->slab.ipc_open) cudaIpcCloseMemHandle(p);
+    for (auto &m : h->slab.ipc_open) cudaIpcCloseMemHandle(m.ptr);
     h->slab.ipc_open.clear();
+    for (unsigned char *p : h->slab.retired) cudaFree(p);
+    h->slab.retired.clear();
     {
         SlabState &Bs = h->slab;
         dfree(Bs.d_send_idx); dfree(Bs.d_recv_idx); dfree(Bs.d_send_voff); dfree(Bs.d_recv_voff); dfree(Bs.d_owned);
@@ -1578,18 +1587,21 @@ extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling
 // ---- slab backend (sz_slab_backend.h): a rank's side of the peer-memory halo update ---------------------------------
 struct WireData {
     int32_t pid, device, rank, pad;
-    unsigned long long base;
+    unsigned long long base, gen;
     cudaIpcMemHandle_t ipc;
     long long off_ready, off_ack, off_stage[2], bytes;
 };
 static_assert(sizeof(WireData) <= sizeof(SlabWire), "SlabWire too small");
 
-int32_t szb_release_peers(sz_handle *h) {
+// start of a (re)build or the end of the slab: nothing is in flight any more.  final: also unmap the partners' arenas.
+int32_t szb_release_peers(sz_handle *h, int32_t final) {
     if (!h) return SZ_ERR_INVALID;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->L.stream);
-    for (void *p : h->slab.ipc_open) cudaIpcCloseMemHandle(p);
-    h->slab.ipc_open.clear();
+    if (final) {
+        for (auto &m : h->slab.ipc_open) cudaIpcCloseMemHandle(m.ptr);
+        h->slab.ipc_open.clear();
+    }
     for (int k = 0; k < SZ_SLAB_MAX_PARTNERS; ++k) {
         h->slab.dev.p[k].r_stage[0] = h->slab.dev.p[k].r_stage[1] = nullptr;
         h->slab.dev.p[k].r_ready = h->slab.dev.p[k].r_ack = nullptr;
@@ -1600,9 +1612,8 @@ int32_t szb_release_peers(sz_handle *h) {
 static void slab_free(sz_handle *h) {
     SlabState &B = h->slab;
     dfree(B.d_send_idx); dfree(B.d_recv_idx); dfree(B.d_send_voff); dfree(B.d_recv_voff); dfree(B.d_owned); dfree(B.d_refx);
-    dfree(B.d_refy); dfree(B.arena);
-    B.arena_bytes = 0;
-    B.on = false;
+    dfree(B.d_refy);
+    B.on = false;  // the arena stays (see SlabState)
 }
 
 int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
@@ -1612,7 +1623,7 @@ int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "slab: configure with ghosts present");
     cudaSetDevice(h->cfg.device);
     CK(cudaStreamSynchronize(h->L.stream));
-    szb_release_peers(h);
+    szb_release_peers(h, 0);
     slab_free(h);
     SlabState &B = h->slab;
     const int np = l->n_partners, n = h->n_init;
@@ -1657,9 +1668,18 @@ int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
         off0[p] = total; total += b;
         off1[p] = total; total += b;
     }
-    CK(cudaMalloc((void **)&B.arena, total));
-    B.arena_bytes = total;
-    CK(cudaMemset(B.arena, 0, total));
+    // arenas replaced at the PREVIOUS rebuild: every importer has switched (and closed) since
+    for (unsigned char *p : B.retired) cudaFree(p);
+    B.retired.clear();
+    if (total > B.arena_bytes || !B.arena) {
+        if (B.arena) B.retired.push_back(B.arena);
+        B.arena = nullptr;
+        const size_t cap = total + total / 2 + (1u << 20);  // headroom: the lists change a little at every rebuild
+        CK(cudaMalloc((void **)&B.arena, cap));
+        B.arena_bytes = cap;
+        B.arena_gen++;
+    }
+    CK(cudaMemset(B.arena, 0, FLAGS));
     CK(dalloc(&B.d_send_idx, (size_t)ns)); CK(dalloc(&B.d_recv_idx, (size_t)nr));
     CK(dalloc(&B.d_send_voff, (size_t)ns)); CK(dalloc(&B.d_recv_voff, (size_t)nr));
     CK(dalloc(&B.d_owned, (size_t)n)); CK(dalloc(&B.d_refx, (size_t)n)); CK(dalloc(&B.d_refy, (size_t)n));
@@ -1707,6 +1727,7 @@ int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
         memset(&w, 0, sizeof(w));
         w.pid = (int32_t)getpid(); w.device = h->cfg.device; w.rank = l->rank;
         w.base = (unsigned long long)(uintptr_t)B.arena;
+        w.gen = B.arena_gen;
         w.ipc = ipc;
         w.off_ready = (long long)(sizeof(int) * p); w.off_ack = (long long)(sizeof(int) * (16 + p));
         w.off_stage[0] = (long long)off0[p]; w.off_stage[1] = (long long)off1[p];
@@ -1745,8 +1766,16 @@ int32_t szb_connect(sz_handle *h, const SlabWire *peer_wire) {
             }
         } else {
             void *m = nullptr;
-            CK(cudaIpcOpenMemHandle(&m, w.ipc, cudaIpcMemLazyEnablePeerAccess));
-            B.ipc_open.push_back(m);
+            for (size_t q = 0; q < B.ipc_open.size();) {
+                if (B.ipc_open[q].pid != w.pid) { ++q; continue; }
+                if (B.ipc_open[q].gen == w.gen) { m = B.ipc_open[q].ptr; ++q; continue; }
+                cudaIpcCloseMemHandle(B.ipc_open[q].ptr);  // that process replaced its arena
+                B.ipc_open.erase(B.ipc_open.begin() + q);
+            }
+            if (!m) {
+                CK(cudaIpcOpenMemHandle(&m, w.ipc, cudaIpcMemLazyEnablePeerAccess));
+                B.ipc_open.push_back({w.pid, w.gen, m});
+            }
             base = (unsigned char *)m;
         }
         SlabPartnerDev &d = B.dev.p[p];
@@ -1843,6 +1872,11 @@ int32_t szb_fetch_mc(sz_handle *h, int64_t off, int64_t n, double *x, double *y)
     for (int64_t k = 0; k < n; ++k) { x[k] = t[k].x; y[k] = t[k].y; }
     return SZ_OK;
 }
+
+int32_t szb_host_alloc(size_t bytes, void **out) {
+    return cudaHostAlloc(out, bytes, cudaHostAllocPortable) == cudaSuccess ? SZ_OK : SZ_ERR_NOMEM;
+}
+void szb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int32_t szb_mc_offsets(sz_handle *h, int64_t *off) {
     if (!h || !off) return SZ_ERR_INVALID;

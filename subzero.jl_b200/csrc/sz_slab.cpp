@@ -78,35 +78,83 @@ void sort_by_gidx(RefList &r) {
     std::stable_sort(r.begin(), r.end(), [](const Ref &a, const Ref &b) { return a.g() < b.g(); });
 }
 
-// arrays behind a sz_floe_soa (download target / upload source)
+// grow-only host staging of a rank (page-locked in the CUDA build: the copies of a rebuild run at PCIe speed)
+struct HostArena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    bool ensure(size_t bytes) {
+        used = 0;
+        if (bytes <= cap) return true;
+        release();
+        const size_t want = bytes + bytes / 4 + 4096;
+#ifndef SZ_ORACLE_BUILD
+        void *p = nullptr;
+        if (szb_host_alloc(want, &p) != SZ_OK) return false;
+        base = (char *)p;
+#else
+        base = (char *)malloc(want);
+        if (!base) return false;
+#endif
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (!base) return;
+#ifndef SZ_ORACLE_BUILD
+        szb_host_free(base);
+#else
+        free(base);
+#endif
+        base = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *take(size_t count) {
+        used = (used + 63) / 64 * 64;
+        T *p = (T *)(base + used);
+        used += sizeof(T) * std::max<size_t>(count, 1);
+        return p;
+    }
+};
+
+// arrays behind a sz_floe_soa (download target / upload source), carved from a rank's HostArena
 struct SoaBuf {
     sz_floe_soa s;
-    std::vector<std::vector<double>> d;
-    std::vector<int32_t> status;
-    std::vector<int64_t> id, gid, goff, gindex, voff, moff;
-    std::vector<double> vxy, mx, my;
-    void alloc(int64_t n, int64_t V, int64_t M) {
+    double *d[32];
+    int32_t *status;
+    int64_t *id, *gid, *goff, *gindex, *voff, *moff;
+    double *vxy, *mx, *my;
+    bool alloc(HostArena &A, int64_t n, int64_t V, int64_t M) {
+        size_t bytes = 64 * 48;
+        for (int f = 0; f < NDF; ++f) bytes += 8 * (size_t)std::max<int64_t>(n * DFIELDS[f].width, 1);
+        bytes += (size_t)std::max<int64_t>(n, 1) * (4 + 8 + 8) + ((size_t)n + 2) * 8 * 3 + 8;
+        bytes += 8 * (size_t)std::max<int64_t>(2 * V, 2) + 16 * (size_t)std::max<int64_t>(M, 1);
+        if (!A.ensure(bytes)) return false;
         memset(&s, 0, sizeof(s));
         s.n = s.n_init = n;
-        d.assign(NDF, std::vector<double>());
         for (int f = 0; f < NDF; ++f) {
-            d[f].assign((size_t)std::max<int64_t>(n * DFIELDS[f].width, 1), 0.0);
-            dptr(s, DFIELDS[f]) = d[f].data();
+            d[f] = A.take<double>((size_t)(n * DFIELDS[f].width));
+            dptr(s, DFIELDS[f]) = d[f];
         }
-        status.assign((size_t)std::max<int64_t>(n, 1), SZ_STATUS_ACTIVE);
-        id.assign((size_t)std::max<int64_t>(n, 1), 0);
-        gid.assign((size_t)std::max<int64_t>(n, 1), 0);
-        goff.assign((size_t)n + 1, 0);
-        gindex.assign(1, 0);
-        voff.assign((size_t)n + 1, 0);
-        moff.assign((size_t)n + 1, 0);
-        vxy.assign((size_t)std::max<int64_t>(2 * V, 2), 0.0);
-        mx.assign((size_t)std::max<int64_t>(M, 1), 0.0);
-        my.assign((size_t)std::max<int64_t>(M, 1), 0.0);
-        s.status_tag = status.data(); s.id = id.data(); s.ghost_id = gid.data();
-        s.ghost_offsets = goff.data(); s.ghost_index = gindex.data();
-        s.vert_offsets = voff.data(); s.vert_xy = vxy.data();
-        s.mc_offsets = moff.data(); s.mc_x = mx.data(); s.mc_y = my.data();
+        status = A.take<int32_t>((size_t)n);
+        id = A.take<int64_t>((size_t)n);
+        gid = A.take<int64_t>((size_t)n);
+        goff = A.take<int64_t>((size_t)n + 1);
+        gindex = A.take<int64_t>(1);
+        voff = A.take<int64_t>((size_t)n + 1);
+        moff = A.take<int64_t>((size_t)n + 1);
+        vxy = A.take<double>((size_t)(2 * V));
+        mx = A.take<double>((size_t)M);
+        my = A.take<double>((size_t)M);
+        memset(goff, 0, sizeof(int64_t) * ((size_t)n + 1));
+        gindex[0] = 0;
+        voff[0] = moff[0] = 0;
+        if (n > 0) { status[0] = SZ_STATUS_ACTIVE; }
+        s.status_tag = status; s.id = id; s.ghost_id = gid;
+        s.ghost_offsets = goff; s.ghost_index = gindex;
+        s.vert_offsets = voff; s.vert_xy = vxy;
+        s.mc_offsets = moff; s.mc_x = mx; s.mc_y = my;
+        return true;
     }
 };
 
@@ -143,7 +191,7 @@ struct Rank {
     std::vector<int64_t> send_off, send_idx, recv_off, recv_idx;
     int64_t send_bytes = 0;
     bool built = false;
-    FloeList pending;
+    HostArena stage;
 #ifdef SZ_ORACLE_BUILD
     std::vector<double> refx, refy;
     std::vector<int64_t> sbytes, rbytes;  // per partner
@@ -328,14 +376,14 @@ int32_t download_owned(sz_slab *S, Rank &R, FloeList &L) {
     const int64_t n = c.n_total;
     SoaBuf B;
 #ifdef SZ_ORACLE_BUILD
-    B.alloc(n, c.n_vertices, c.n_mc);
+    if (!B.alloc(R.stage, n, c.n_vertices, c.n_mc)) return sfail(S, SZ_ERR_NOMEM, "slab: host staging");
 #else
-    B.alloc(n, c.n_vertices, 0);
+    if (!B.alloc(R.stage, n, c.n_vertices, 0)) return sfail(S, SZ_ERR_NOMEM, "slab: host staging");
     B.s.mc_x = B.s.mc_y = nullptr;
 #endif
     HCK(FN(download_floes)(R.h, &B.s), "download_floes");
 #ifndef SZ_ORACLE_BUILD
-    HCK(szb_mc_offsets(R.h, B.moff.data()), "mc offsets");
+    HCK(szb_mc_offsets(R.h, B.moff), "mc offsets");
 #endif
     int64_t no = 0, Vo = 0, Mo = 0;
     for (int64_t i = 0; i < n; ++i)
@@ -356,15 +404,15 @@ int32_t download_owned(sz_slab *S, Rank &R, FloeList &L) {
         L.gidx[q] = R.gidx[i];
         L.vcnt[q] = B.voff[i + 1] - B.voff[i];
         L.voff[q] = vo;
-        memcpy(L.vxy.data() + 2 * vo, B.vxy.data() + 2 * B.voff[i], sizeof(double) * 2 * L.vcnt[q]);
+        memcpy(L.vxy.data() + 2 * vo, B.vxy + 2 * B.voff[i], sizeof(double) * 2 * L.vcnt[q]);
         vo += L.vcnt[q];
         L.mcnt[q] = B.moff[i + 1] - B.moff[i];
 #ifdef SZ_ORACLE_BUILD
         L.msrc[q] = -1;
         L.mhoff[q] = mo;
         if (L.mcnt[q] > 0) {
-            memcpy(L.mx.data() + mo, B.mx.data() + B.moff[i], sizeof(double) * L.mcnt[q]);
-            memcpy(L.my.data() + mo, B.my.data() + B.moff[i], sizeof(double) * L.mcnt[q]);
+            memcpy(L.mx.data() + mo, B.mx + B.moff[i], sizeof(double) * L.mcnt[q]);
+            memcpy(L.my.data() + mo, B.my + B.moff[i], sizeof(double) * L.mcnt[q]);
         }
         mo += L.mcnt[q];
 #else
@@ -391,7 +439,7 @@ int32_t upload_local(sz_slab *S, Rank &R, const RefList &refs) {
         else n_extra += L.mcnt[r.i];
     }
     SoaBuf B;
-    B.alloc(n, V, any_resident ? n_extra : M);
+    if (!B.alloc(R.stage, n, V, any_resident ? n_extra : M)) return sfail(S, SZ_ERR_NOMEM, "slab: host staging");
     std::vector<int64_t> mc_src((size_t)std::max<int64_t>(n, 1), 0);
     int64_t vo = 0, mo = 0, eo = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -404,7 +452,7 @@ int32_t upload_local(sz_slab *S, Rank &R, const RefList &refs) {
         B.id[i] = double_as_i64(r[C_ID]);
         B.gid[i] = double_as_i64(r[C_GID]);
         B.voff[i] = vo;
-        memcpy(B.vxy.data() + 2 * vo, L.vxy.data() + 2 * L.voff[j], sizeof(double) * 2 * L.vcnt[j]);
+        memcpy(B.vxy + 2 * vo, L.vxy.data() + 2 * L.voff[j], sizeof(double) * 2 * L.vcnt[j]);
         vo += L.vcnt[j];
         B.moff[i] = mo;
         const int64_t mc = refs[i].mc ? L.mcnt[j] : 0;
@@ -413,8 +461,8 @@ int32_t upload_local(sz_slab *S, Rank &R, const RefList &refs) {
                 mc_src[i] = L.msrc[j];
             } else {
                 const int64_t at = any_resident ? eo : mo;
-                memcpy(B.mx.data() + at, L.mx.data() + L.mhoff[j], sizeof(double) * mc);
-                memcpy(B.my.data() + at, L.my.data() + L.mhoff[j], sizeof(double) * mc);
+                memcpy(B.mx + at, L.mx.data() + L.mhoff[j], sizeof(double) * mc);
+                memcpy(B.my + at, L.my.data() + L.mhoff[j], sizeof(double) * mc);
                 mc_src[i] = -1 - eo;
                 eo += mc;
             }
@@ -708,7 +756,7 @@ int32_t do_rebuild(sz_slab *S) {
     std::vector<FloeList> own(S->n_local);
     PhaseTimer pt;
 #ifndef SZ_ORACLE_BUILD
-    for (Rank &R : S->ranks) HCK(szb_release_peers(R.h), "release partners");
+    for (Rank &R : S->ranks) HCK(szb_release_peers(R.h, 0), "release partners");
 #endif
     for (int k = 0; k < S->n_local; ++k) {
         int32_t rc = download_owned(S, S->ranks[k], own[k]);
@@ -756,9 +804,12 @@ int32_t FN(slab_create)(const sz_config *cfg, int32_t world, int32_t rank_first,
 void FN(slab_destroy)(sz_slab *S) {
     if (!S) return;
 #ifndef SZ_ORACLE_BUILD
-    for (Rank &R : S->ranks) if (R.h) szb_release_peers(R.h);
+    for (Rank &R : S->ranks) if (R.h) szb_release_peers(R.h, 1);
 #endif
-    for (Rank &R : S->ranks) if (R.h) FN(destroy)(R.h);
+    for (Rank &R : S->ranks) {
+        R.stage.release();
+        if (R.h) FN(destroy)(R.h);
+    }
     delete S;
 }
 
@@ -832,7 +883,7 @@ int32_t FN(slab_build)(sz_slab *S, const sz_floe_soa *const *floes, const int64_
         }
     }
 #ifndef SZ_ORACLE_BUILD
-    for (Rank &R : S->ranks) if (R.built) HCK(szb_release_peers(R.h), "release partners");
+    for (Rank &R : S->ranks) if (R.built) HCK(szb_release_peers(R.h, 0), "release partners");
 #endif
     return repartition(S, own);
 }

@@ -4,6 +4,7 @@
 // peer-memory push / unpack kernels (sz_kernels_fp.cu), and — with -DSZ_ORACLE_BUILD — into the oracle's test library,
 // where sz_slab.cpp itself implements them through szo_halo_pack / szo_halo_unpack and host memory.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/subzero_b200.h"
@@ -25,8 +26,8 @@ struct SlabLists {
 };
 
 #ifndef SZ_ORACLE_BUILD
-// unmap the partners' arenas (first thing of a rebuild, before any rank frees its own)
-int32_t szb_release_peers(sz_handle *h);
+// first thing of a (re)build: wait for the rank's stream; final != 0 (slab destroyed): also unmap the partners' arenas
+int32_t szb_release_peers(sz_handle *h, int32_t final);
 // after the local list was uploaded: register the lists, allocate this rank's receive arena; wire_out[p] tells partner
 // p where to write
 int32_t szb_configure(sz_handle *h, const SlabLists *lists, SlabWire *wire_out);
@@ -48,4 +49,7 @@ int32_t szb_upload_floes_resident_mc(sz_handle *h, const sz_floe_soa *s, const i
 // Monte-Carlo points [off, off + n) of the resident array -> host (migrants of a rebuild)
 int32_t szb_fetch_mc(sz_handle *h, int64_t off, int64_t n, double *x, double *y);
 int32_t szb_mc_offsets(sz_handle *h, int64_t *off /* [n_init + 1] */);
+// page-locked host staging of a rebuild
+int32_t szb_host_alloc(size_t bytes, void **out);
+void szb_host_free(void *p);
 #endif
