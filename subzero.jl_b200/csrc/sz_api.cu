@@ -303,6 +303,14 @@ static int32_t set_crec_cap(sz_handle *h, int cap) {
     C.cap_crec = cap;
     return SZ_OK;
 }
+static int32_t set_spill_cap(sz_handle *h, int cap) {
+    h->gen++;
+    CouplingBuf &C = h->CB;
+    dfree(C.sp_cell); dfree(C.sp_n); dfree(C.sp_sd); dfree(C.sp_t);
+    CK(dalloc(&C.sp_cell, (size_t)cap)); CK(dalloc(&C.sp_n, (size_t)cap)); CK(dalloc(&C.sp_sd, (size_t)cap)); CK(dalloc(&C.sp_t, (size_t)cap));
+    C.cap_spill = cap;
+    return SZ_OK;
+}
 static int32_t set_fuse_cap(sz_handle *h, int cap) {
     h->gen++;
     dfree(h->B.fuse_pairs);
@@ -420,6 +428,7 @@ extern "C" void sz_destroy(sz_handle *h) {
         CouplingBuf &C = h->CB;
         dfree(C.rec_cell); dfree(C.rec_floe); dfree(C.rec_npts); dfree(C.rec_t); dfree(C.rec_d); dfree(C.rec_area);
         dfree(C.cell_count); dfree(C.cell_start); dfree(C.cell_fill); dfree(C.perm); dfree(C.big_recs); dfree(C.scan_block);
+        dfree(C.sp_cell); dfree(C.sp_n); dfree(C.sp_sd); dfree(C.sp_t);
         dfree(S.ocn_temp); dfree(S.atm_temp); dfree(S.taux); dfree(S.tauy); dfree(S.sifrac);
     }
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -978,7 +987,10 @@ static int32_t handle_overflow(sz_handle *h, const Counters &c) {
     if (e & ERR_FUSE_CAP) {
         if ((rc = set_fuse_cap(h, std::max(c.n_fuse, h->B.cap_fuse) * 2 + 1024))) return rc;
     }
-    if (e & ERR_CELL_TABLE) return fail(h, SZ_ERR_UNSUPPORTED, "two-way coupling: a floe touches more than 16 grid cells");
+    if (e & ERR_CELL_TABLE) return fail(h, SZ_ERR_UNSUPPORTED, "two-way coupling: a floe touches more than 2080 grid cells");
+    if (e & ERR_SPILL_CAP) {  // every floe wider than the shared-memory table claims a block of 2048 entries
+        if ((rc = set_spill_cap(h, std::max(c.n_spill, h->CB.cap_spill) + 8 * 2048))) return rc;
+    }
     if (e & ERR_CREC_CAP) {
         if ((rc = set_crec_cap(h, std::max(c.n_crec, h->CB.cap_crec) * 2 + 1024))) return rc;
     }
@@ -1373,7 +1385,7 @@ static int32_t step_finish(sz_handle *h) {
         int32_t rc = handle_overflow(h, c);
         if (rc) return rc;
         const uint32_t ghost_bits = ERR_GHOST_CAP | ERR_VERT_CAP | ERR_GHOST_SLOTS;
-        const uint32_t coupling_bits = ERR_CREC_CAP | ERR_CELL_TABLE;
+        const uint32_t coupling_bits = ERR_CREC_CAP | ERR_CELL_TABLE | ERR_SPILL_CAP;
         if (cur.coupling_only || (c.error & ~coupling_bits) == 0) {
             if (!cur.coupling_only) h->last_ok_collisions = c;
             cur.coupling_only = true;

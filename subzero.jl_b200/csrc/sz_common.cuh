@@ -44,7 +44,8 @@ enum : uint32_t {
     ERR_DOM_CAP = 128u,
     ERR_GHOST_SLOTS = 256u,
     ERR_CREC_CAP = 512u,    // floe -> cell registry records
-    ERR_CELL_TABLE = 1024u, // one floe touches more than 32 grid cells
+    ERR_CELL_TABLE = 1024u, // one floe touches more than 32 + 2048 grid cells
+    ERR_SPILL_CAP = 4096u,     // spill table of the floe -> cell registry (floes touching more than 32 cells)
     ERR_SLAB_TIMEOUT = 2048u,  // a slab neighbour did not publish / acknowledge its halo records in time
 };
 
@@ -62,6 +63,7 @@ struct Counters {
     int n_large;   // work items deferred to the large-polygon kernel
     int n_mid;     // work items the thread-per-item kernel handed to the warp-per-item kernel
     int n_crec;    // records of the floe -> cell registry (coupling)
+    int n_spill;   // entries claimed in the registry's spill table
     int n_cbig;    // ... whose ring needs the warp clip kernel
     int n_ccells;  // number of grid cells (scan length of the registry sort)
     int n_order;   // work items of the thread-per-item kernels (class-sorted)
@@ -172,7 +174,11 @@ struct StepBuf {
 
 // floe -> cell registry (grid.floe_locations / ocean.scells, coupling.jl:1329-1454) of one coupling step
 struct CouplingBuf {
-    int cap_crec, cap_cells;
+    int cap_crec, cap_cells, cap_spill;
+    // per-floe tables of floes touching more than 32 cells (blocks of 2048 entries claimed on demand)
+    int *sp_cell, *sp_n;
+    int2 *sp_sd;
+    double2 *sp_t;
     int *rec_cell, *rec_floe, *rec_npts;  // [cap_crec] unsorted records
     double2 *rec_t, *rec_d;               // sum of -tau_ocn, periodic shift (dx, dy)
     double *rec_area;                     // area of floe ∩ cell box

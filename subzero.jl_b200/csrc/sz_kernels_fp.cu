@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
 // The same integration plus the floe -> cell registry (grid.floe_locations / ocean.scells): the points of a
 // warp iteration are grouped by cell with ballots, each group is reduced and added to a small per-floe table in
 // shared memory; the table is appended to the global record list (sorted by (cell, floe) afterwards).
-#define CP_TABLE 32  // distinct cells one floe may touch
+#define CP_TABLE 32     // distinct cells of one floe held in shared memory ...
+#define CP_SPILL 2048   // ... and in a block of global memory claimed on demand (floes wider than ~5 grid cells)
 __global__ void __launch_bounds__(128, 6) k_coupling_reg(Store S, CouplingBuf CB, CpConst c) {
     __shared__ int t_cell[4][CP_TABLE], t_n[4][CP_TABLE], t_sd[4][CP_TABLE][2];
     __shared__ double t_t[4][CP_TABLE][2];
@@ -294,7 +295,8 @@ __global__ void __launch_bounds__(128, 6) k_coupling_reg(Store S, CouplingBuf CB
         const double mf = S.mass[i] / ar * c.f;
         CpAcc acc = {0.0, 0.0, 0.0, 0.0, 0};
         const long long m0 = S.mc_off[i], m1 = S.mc_off[i + 1];
-        int ntab = 0;
+        int ntab = 0, nsp = 0;   // entries in the shared table / in this floe's spill block (warp-uniform)
+        long long sp = -1;       // first entry of the spill block, -1 = none claimed yet, -2 = no room (step is repeated)
         bool overflow = false;
         for (long long base = m0; base < m1; base += 32) {
             const long long k = base + lane;
@@ -316,28 +318,67 @@ __global__ void __launch_bounds__(128, 6) k_coupling_reg(Store S, CouplingBuf CB
                     sx_ += __shfl_xor_sync(FULLMASK, sx_, o);
                     sy_ += __shfl_xor_sync(FULLMASK, sy_, o);
                 }
+                int e = -1;
                 if (lane == 0) {
-                    int e = 0;
-                    while (e < ntab && t_cell[wib][e] != cc) ++e;
-                    if (e == ntab) {
-                        if (ntab < CP_TABLE) {
-                            t_cell[wib][e] = cc;
-                            t_n[wib][e] = 0;
-                            t_sd[wib][e][0] = sdx;
-                            t_sd[wib][e][1] = sdy;
-                            t_t[wib][e][0] = t_t[wib][e][1] = 0.0;
-                            ntab++;
-                        } else {
-                            overflow = true;
-                        }
+                    int q = 0;
+                    while (q < ntab && t_cell[wib][q] != cc) ++q;
+                    if (q < ntab) e = q;
+                    else if (ntab < CP_TABLE) {
+                        t_cell[wib][q] = cc;
+                        t_n[wib][q] = 0;
+                        t_sd[wib][q][0] = sdx;
+                        t_sd[wib][q][1] = sdy;
+                        t_t[wib][q][0] = t_t[wib][q][1] = 0.0;
+                        e = q;
+                        ntab++;
                     }
-                    if (e < CP_TABLE) {
+                    if (e >= 0) {
                         t_t[wib][e][0] += sx_;
                         t_t[wib][e][1] += sy_;
                         t_n[wib][e] += __popc(m);
                     }
                 }
+                e = __shfl_sync(FULLMASK, e, 0);
                 ntab = __shfl_sync(FULLMASK, ntab, 0);
+                if (e < 0) {  // the shared table is full: this floe's block of the global spill table
+                    if (sp == -1) {
+                        if (lane == 0) {
+                            sp = (long long)atomicAdd(&cnt->n_spill, CP_SPILL);
+                            if (sp + CP_SPILL > CB.cap_spill) {
+                                atomicOr(&cnt->error, ERR_SPILL_CAP);
+                                sp = -2;
+                            }
+                        }
+                        sp = __shfl_sync(FULLMASK, sp, 0);
+                    }
+                    if (sp >= 0) {
+                        int f = -1;
+                        for (int b = 0; b < nsp && f < 0; b += 32) {  // the search is spread over the lanes
+                            const int idx = b + lane;
+                            const unsigned hit = __ballot_sync(FULLMASK, idx < nsp && CB.sp_cell[sp + idx] == cc);
+                            if (hit) f = b + __ffs(hit) - 1;
+                        }
+                        if (f < 0) {
+                            if (nsp < CP_SPILL) {
+                                f = nsp++;
+                                if (lane == 0) {
+                                    CB.sp_cell[sp + f] = cc;
+                                    CB.sp_n[sp + f] = 0;
+                                    CB.sp_sd[sp + f] = make_int2(sdx, sdy);
+                                    CB.sp_t[sp + f] = make_double2(0.0, 0.0);
+                                }
+                            } else {
+                                overflow = true;
+                            }
+                        }
+                        if (f >= 0 && lane == 0) {
+                            double2 t = CB.sp_t[sp + f];
+                            CB.sp_t[sp + f] = make_double2(t.x + sx_, t.y + sy_);
+                            CB.sp_n[sp + f] += __popc(m);
+                        }
+                        __syncwarp();
+                    }
+                }
                 pending &= ~m;
             }
         }
@@ -365,9 +406,10 @@ __global__ void __launch_bounds__(128, 6) k_coupling_reg(Store S, CouplingBuf CB
             }
         }
         int slot = 0;
-        if (lane == 0 && ntab > 0) {
-            slot = atomicAdd(&cnt->n_crec, ntab);
-            if (slot + ntab > CB.cap_crec) {
+        const int nrec = ntab + nsp;
+        if (lane == 0 && nrec > 0) {
+            slot = atomicAdd(&cnt->n_crec, nrec);
+            if (slot + nrec > CB.cap_crec) {
                 atomicOr(&cnt->error, ERR_CREC_CAP);
                 slot = -1;
             }
@@ -381,12 +423,25 @@ __global__ void __launch_bounds__(128, 6) k_coupling_reg(Store S, CouplingBuf CB
             CB.rec_t[q] = make_double2(t_t[wib][e][0], t_t[wib][e][1]);
             CB.rec_d[q] = make_double2(t_sd[wib][e][0] * c.dx, t_sd[wib][e][1] * c.dy);
         }
+        if (slot >= 0 && sp >= 0)
+            for (int e = lane; e < nsp; e += 32) {
+                const int q = slot + ntab + e;
+                const int2 sd = CB.sp_sd[sp + e];
+                CB.rec_cell[q] = CB.sp_cell[sp + e];
+                CB.rec_floe[q] = i;
+                CB.rec_npts[q] = CB.sp_n[sp + e];
+                CB.rec_t[q] = CB.sp_t[sp + e];
+                CB.rec_d[q] = make_double2(sd.x * c.dx, sd.y * c.dy);
+            }
         __syncwarp();
     }
 }
 
 __global__ void k_crec_reset(Counters *cnt) {
-    if (!cnt->error) cnt->n_crec = 0;
+    if (!cnt->error) {
+        cnt->n_crec = 0;
+        cnt->n_spill = 0;
+    }
 }
 
 void szk_coupling_reg(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P) {

@@ -601,6 +601,10 @@ def timestep_sim(sim, tstep, start_tstep=0):
     if sim.collision_settings.collisions_on:
         sim.h.step(tstep, do_cpl)
     else:
+        # add_ghosts! runs whether or not collisions are on (simulation.jl:100-102): it is what wraps a parent that
+        # drifted out of a periodic domain back inside (collisions.jl:943-949); the ghosts are deleted again at :138-144
+        sim.h.add_ghosts()
+        sim.h.remove_ghosts()
         if do_cpl:
             sim.h.step_coupling()
         sim.h.step_floe_properties(tstep)

@@ -11,6 +11,7 @@ import szload  # noqa: E402,F401
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: takes minutes (benchmark-size fields); still part of -m gpu")
 
 
 @pytest.fixture(scope="session")

@@ -314,6 +314,60 @@ def test_full_size_periodic_shear_properties(product_lib):
     assert fb.centroid_x.min() >= -1.0 and fb.centroid_x.max() <= f.L + 1.0
 
 
+# BASELINE.json configs 3, 4 and 5 at their OWN sizes against the oracle (round-1 verdict: the largest CUDA-vs-oracle
+# comparison was 10 000 floes, and above 32 768 floes sz_step takes the direct-launch path instead of the CUDA graph).
+BENCH_SIZE_CONFIGS = [
+    # name, floes, walls, flow, Monte-Carlo draws
+    ("config3_100k_collision_walls", 100000, "collision", "random", 1000),
+    ("config4_250k_periodic_shear", 250000, "shear", "random", 200),
+    ("config5_1M_converging", 1000000, "collision", "converging", 200),
+]
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("cfg", BENCH_SIZE_CONFIGS, ids=lambda c: c[0])
+def test_benchmark_size_parity(cfg, product_lib, oracle_lib):
+    """One timestep of the benchmark field on CUDA and on the oracle from the same state: (1) phase by phase — ghost
+    lists, candidate / filtered / overlap / fuse pair lists and interaction rows bit-exact, state to 1e-9 after every
+    phase; (2) the fused sz_step (direct-launch path at these sizes, coupling on its second stream) against the oracle's
+    step and, bit for bit, against the CUDA phases."""
+    import os
+    name, n, walls, flow, npoints = cfg
+    f = synth.make_field(n, scale=1.01, walls=walls, flow=flow, npoints=npoints)
+    hg = synth.setup_handle(f, product_lib)
+    ho = synth.setup_handle(f, oracle_lib, threads=os.cpu_count())
+    assert hg.add_ghosts() == ho.add_ghosts()
+    hg.step_collisions()
+    ho.step_collisions()
+    assert_ok(compare_collision_outputs(hg, ho))
+    c = hg.counts()
+    assert c["n_overlap"] > 2 * n and c["n_clip_fail"] == 0
+    for h in (hg, ho):
+        h.remove_ghosts()
+        h.step_coupling()
+    a, b = hg.download_floes(mc=False), ho.download_floes(mc=False)
+    assert_ok(compare_state(a, b, exact=("collision_force", "collision_trq", "overarea", "vert_xy")))
+    for h in (hg, ho):
+        h.step_floe_properties(0)
+    a, b = hg.download_floes(mc=False), ho.download_floes(mc=False)
+    assert_ok(compare_state(a, b))
+    assert np.array_equal(hg.warnings(), ho.warnings())
+    ho.close()
+    # the fused step from the same initial state
+    h2 = synth.setup_handle(f, product_lib)
+    h2.step(0, True)
+    a2 = h2.download_floes(mc=False)
+    assert_ok(compare_state(a2, b))
+    assert_ok(compare_state(a2, a, exact=("collision_force", "collision_trq", "overarea", "centroid_x", "centroid_y", "vert_xy",
+                                          "u", "v", "xi", "alpha", "stress_accum", "strain")))
+    c2 = h2.counts()
+    for k in ("n_candidates", "n_pairs", "n_overlap", "n_fuse", "n_domain_pairs"):
+        assert c2[k] == c[k], (k, c2[k], c[k])
+    og, rg = hg.interactions()
+    o2, r2 = h2.interactions()
+    assert np.array_equal(og[:n + 1], o2[:n + 1]) and np.array_equal(rg[:og[n]], r2[:o2[n]])
+
+
 def degenerate_square_field():
     """Axis-aligned squares on a lattice: exactly shared edges and corners, exact overlaps of half a cell, one square
     nested in another, two identical squares — every orientation predicate of these pairs is exactly zero somewhere."""

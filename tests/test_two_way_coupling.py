@@ -189,3 +189,65 @@ def test_two_way_coupling_nonconvex_shapes_cuda_matches_oracle(product_lib, orac
     for a, b, name in zip(hg.ocean_fields(), ho.ocean_fields(), ("tau_x", "tau_y", "si_frac", "hflx_factor")):
         assert rel_err(a, b) < 1e-9, name
     assert ho.ocean_fields()[2].max() > 0.3
+
+
+def fine_grid_field(n=1500, cell=400.0):
+    """A grid five times finer than the floes (each floe registers in ~30 cells, many in more than the 32 the
+    shared-memory table of k_coupling_reg holds), periodic east/west, MOVING north/south walls."""
+    f = synth.make_field(n, scale=0.98, walls="shear", npoints=400, cache=False)
+    fields.perturb_state(f.floes)
+    g = host.RegRectilinearGrid(0.0, f.L, 0.0, f.L, dx=cell, dy=cell)
+    f.grid = g
+    rng = np.random.default_rng(9)
+    yl = np.linspace(g.y0, g.yf, g.Ny + 1)
+    prof = 0.5 * (1.0 - np.abs(2.0 * (yl - g.y0) / (g.yf - g.y0) - 1.0))
+    f.ocean = host.Ocean(g, np.repeat(prof[None, :], g.Nx + 1, axis=0), 0.03, 1.0)
+    f.atmos = host.Atmos(g, 2.0 + rng.uniform(-1, 1, (g.Nx + 1, g.Ny + 1)), -1.0, -12.0)
+    f.domain = host.Domain(host.MovingBoundary(host.North, g, u=0.0, v=-0.2), host.MovingBoundary(host.South, g, u=0.0, v=0.1),
+                           host.PeriodicBoundary(host.East, g), host.PeriodicBoundary(host.West, g))
+    return f
+
+
+def test_fine_grid_registry_on_oracle(oracle_lib):
+    f = fine_grid_field(n=300)
+    h = two_way_handle(f, oracle_lib)
+    h.step(0, True)
+    cell, floe, vals = h.cell_floes()
+    per_floe = np.bincount(floe)
+    assert per_floe.max() > 32 and len(cell) > 6 * f.floes.n + 4096  # beyond the product's first-guess capacities
+    assert vals[:, 2].sum() <= f.floes.mc_offsets[-1]
+
+
+@pytest.mark.gpu
+def test_two_way_registry_overflow_repeats_only_the_coupling(product_lib, oracle_lib):
+    """Round-1 advisor findings: (1) ERR_CREC_CAP is raised AFTER the collisions of the step finished (rows added to
+    overarea, moving walls advanced, ghosts removed): the repair must repeat only coupling + update — a second run of
+    the collisions would double overarea and move the walls twice; (2) a floe in more than 32 cells must not abort
+    the step (spill table).  Fine grid: the registry needs ~30 records per floe (first guess: 6 n + 4096) and many
+    floes touch more than 32 cells; periodic east/west + moving north/south walls."""
+    f = fine_grid_field()
+    hg, ho = two_way_handle(f, product_lib), two_way_handle(f, oracle_lib)
+    for h in (hg, ho):
+        h.step(0, True)
+        h.step(1, True)
+    cg, fg, vg = hg.cell_floes()
+    co, fo, vo = ho.cell_floes()
+    assert np.bincount(fo).max() > 32 and len(co) > 6 * f.floes.n + 4096
+    assert np.array_equal(cg, co) and np.array_equal(fg, fo)
+    assert np.array_equal(vg[:, 2:], vo[:, 2:]) and rel_err(vg[:, :2], vo[:, :2]) < 1e-9
+    for a, b, name in zip(hg.ocean_fields(), ho.ocean_fields(), ("tau_x", "tau_y", "si_frac", "hflx_factor")):
+        assert rel_err(a, b) < 1e-9, name
+    vg_, rg_ = hg.get_domain()
+    vo_, ro_ = ho.get_domain()
+    assert np.array_equal(vg_, vo_) and np.array_equal(rg_, ro_)  # the moving walls advanced exactly twice
+    from parity_util import compare_state
+    bad = compare_state(hg.download_floes(), ho.download_floes(), exact=("overarea", "collision_force", "collision_trq"))
+    assert not bad, "\n".join(bad)
+    # the same through host arrays (coupling-only repair with downloads in flight)
+    hh = two_way_handle(f, product_lib)
+    fa = hh.download_floes(mc=False)
+    hh.step_host(fa, 0, True)
+    hh.step_host(fa, 1, True)
+    from parity_util import STATE_FIELDS
+    bad = compare_state(fa, hg.download_floes(mc=False), exact=STATE_FIELDS)
+    assert not bad, "\n".join(bad)
