@@ -374,6 +374,39 @@ int32_t SZ_FN(pair_overlap_areas)(sz_handle *h, int64_t n_pairs, const int64_t *
 int32_t SZ_FN(eulerian_data)(sz_handle *h, int32_t nx, int32_t ny, const double *xg, const double *yg,
                              int32_t n_out, const int32_t *kinds, double *data);
 
+/* Rank 4 — sub-floe point generation (generate_subfloe_points, coupling.jl:172-208 Monte Carlo, :235-321 sub-grid),
+ * what replace_floe! (update_floe.jl:55-66) calls for every floe a host process created.  For each listed floe of the
+ * resident list the points are generated in the body frame (ring translated by -centroid, coupling.jl:189 / :261):
+ *
+ * SZ_POINTS_MONTE_CARLO  up to 10 attempts of `npoints` uniform draws in the ring's bounding box, kept when
+ *     GO.coveredby(point, ring); an attempt is accepted when |kept / npoints * box area - area| / area <= err;
+ *     after 10 failures the 10th attempt's points are kept and the floe is tagged `remove` (:182-185), as it is when no
+ *     point was kept (:203-205).  Julia's Xoshiro stream cannot be reproduced, so the draws come from a counter-based
+ *     generator — u(seed, floe id, attempt, draw, axis), splitmix64 finaliser, 53 bits — identical in this library and
+ *     in the oracle: counts, `remove` semantics and point order are exact against the oracle, the DISTRIBUTION is what
+ *     is held against the reference (statistical parity).
+ * SZ_POINTS_SUB_GRID     deterministic: every vertex, edge points every <= delta_g (with the reference's shift of
+ *     delta_g / 2 along the edge, including its always-positive x shift), then the interior lattice points kept when
+ *     coveredby.  range(a, b, length = n) is restated as: endpoints exact, element i = a + i (b - a) / (n - 1)
+ *     evaluated in double-double and rounded once (Julia's TwicePrecision ranges give the same value to <= 1 ulp).
+ *
+ * floes: 1-based indices into the resident list (NULL = all n_floes = n_init floes in order).  offsets[n_floes + 1] and
+ * status[n_floes] (SZ_STATUS_ACTIVE / SZ_STATUS_REMOVE; may be NULL) are always written; x / y (capacity cap_points
+ * points) may be NULL to query the sizes first.  install != 0 (all floes only): the generated points also replace the
+ * resident Monte-Carlo points of the store, and `remove` tags are applied to status.tag. */
+#define SZ_POINTS_MONTE_CARLO 0
+#define SZ_POINTS_SUB_GRID 1
+typedef struct sz_points_generator {
+    int32_t kind;
+    int32_t npoints;  /* Monte Carlo: draws per attempt (MonteCarloPointsGenerator.npoints, default 1000) */
+    double err;       /* Monte Carlo: accepted relative area error (default 0.1) */
+    double delta_g;   /* sub-grid: point spacing (SubGridPointsGenerator.Δg) */
+    uint64_t seed;    /* Monte Carlo */
+} sz_points_generator;
+int32_t SZ_FN(generate_subfloe_points)(sz_handle *h, const sz_points_generator *gen, int64_t n_floes, const int64_t *floes,
+                                       int64_t *offsets, double *x, double *y, int64_t cap_points, int32_t *status,
+                                       int32_t install);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@
 #define SZ_ORACLE_BUILD 1
 #include "../include/subzero_b200.h"
 #include "szo_geom.h"
+#include "szo_points.h"
 
 #include <stdio.h>
 #include <time.h>
@@ -1495,6 +1496,143 @@ int32_t szo_pair_overlap_areas(sz_handle *h, int64_t n_pairs, const int64_t *pai
         szo_regions_free(&R);
     }
     return SZ_OK;
+}
+
+/* ---- generate_subfloe_points, coupling.jl:172-208 (Monte Carlo), :235-321 (sub-grid) ---------- */
+typedef struct { double *x, *y; int64_t n, cap; } ptlist;
+static void pt_push(ptlist *l, double x, double y) {
+    if (l->n == l->cap) {
+        l->cap = l->cap ? 2 * l->cap : 256;
+        l->x = (double *)realloc(l->x, sizeof(double) * (size_t)l->cap);
+        l->y = (double *)realloc(l->y, sizeof(double) * (size_t)l->cap);
+    }
+    l->x[l->n] = x; l->y[l->n] = y; l->n++;
+}
+
+/* points of floe f in the body frame; returns the status tag */
+static int generate_points_one(sz_handle *h, const sz_points_generator *g, int64_t f, ptlist *out) {
+    const int np = h->npts[f];
+    szo_pt *r = (szo_pt *)malloc(sizeof(szo_pt) * (size_t)np);
+    double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    for (int k = 0; k < np; ++k) { /* _translate_poly(poly, -cx, -cy), coupling.jl:189,261; GI.extent */
+        r[k].x = h->ring[f][k].x + (-h->cx[f]);
+        r[k].y = h->ring[f][k].y + (-h->cy[f]);
+        xmin = fmin(xmin, r[k].x); xmax = fmax(xmax, r[k].x);
+        ymin = fmin(ymin, r[k].y); ymax = fmax(ymax, r[k].y);
+    }
+    const double Dx = xmax - xmin, Dy = ymax - ymin;
+    int status = SZ_STATUS_ACTIVE;
+    out->n = 0;
+    if (g->kind == SZ_POINTS_MONTE_CARLO) { /* :172-208 */
+        const int n = g->npoints;
+        int count = 1, used = 0;
+        double err = 1.0;
+        while (err > g->err) {
+            if (count > 10) {
+                err = 0.0;
+                status = SZ_STATUS_REMOVE;
+            } else {
+                int64_t in = 0;
+                for (int j = 0; j < n; ++j) {
+                    szo_pt p = {xmin + Dx * szo_uniform(g->seed, h->id[f], count, j, 0), ymin + Dy * szo_uniform(g->seed, h->id[f], count, j, 1)};
+                    in += szo_point_coveredby(p, r, np);
+                }
+                err = fabs((double)in / (double)n * (Dx * Dy) - h->area[f]) / h->area[f];
+                used = count;
+                count += 1;
+            }
+        }
+        for (int j = 0; used > 0 && j < n; ++j) { /* mc_x[mc_in]: the draws of the last attempt, in draw order */
+            szo_pt p = {xmin + Dx * szo_uniform(g->seed, h->id[f], used, j, 0), ymin + Dy * szo_uniform(g->seed, h->id[f], used, j, 1)};
+            if (szo_point_coveredby(p, r, np)) pt_push(out, p.x, p.y);
+        }
+        if (out->n == 0) status = SZ_STATUS_REMOVE; /* :203-205 */
+    } else { /* :235-321 */
+        const double dg = g->delta_g;
+        double x1 = r[0].x, y1 = r[0].y;
+        for (int i = 1; i < np; ++i) {
+            double x2 = r[i].x, y2 = r[i].y;
+            double dx = x2 - x1, dy = y2 - y1;
+            double l = sqrt(dx * dx + dy * dy);
+            pt_push(out, x1, y1);
+            const double x2u = x2, y2u = y2;
+            if (l <= 2 * dg) {
+                if (l > dg) pt_push(out, x1 + dx / 2, y1 + dy / 2);
+            } else {
+                if (dx == 0) {
+                    double sg = (double)((dy > 0) - (dy < 0));
+                    y1 += dg / 2 * sg;
+                    y2 -= dg / 2 * sg;
+                } else if (dy == 0) {
+                    double sg = (double)((dx > 0) - (dx < 0));
+                    x1 += dg / 2 * sg;
+                    x2 -= dg / 2 * sg;
+                } else { /* "shift points to still be on the line": x_shift is positive whatever the edge's direction */
+                    double m = dy / dx;
+                    double xs = sqrt(dg * dg / (4 * (1 + m * m)));
+                    double ys = m * xs;
+                    x1 += xs; x2 -= xs; y1 += ys; y2 -= ys;
+                }
+                l = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+                int64_t ne = (int64_t)ceil(l / dg) + 1;
+                for (int64_t k = 0; k < ne; ++k) pt_push(out, szo_range_elem(x1, x2, k, ne), szo_range_elem(y1, y2, k, ne));
+            }
+            x1 = x2u; y1 = y2u;
+        }
+        int64_t nx = (int64_t)ceil((xmax - xmin) / dg), ny = (int64_t)ceil((ymax - ymin) / dg);
+        const int xs1 = nx < 3, ys1 = ny < 3;
+        if (xs1) nx = 1;
+        if (ys1) ny = 1;
+        for (int64_t k = 0; k < nx * ny; ++k) { /* repeat(x, ny), repeat(y, inner = nx) */
+            szo_pt p = {xs1 ? 0.0 : szo_range_elem(xmin + dg / 2, xmax - dg / 2, k % nx, nx),
+                        ys1 ? 0.0 : szo_range_elem(ymin + dg / 2, ymax - dg / 2, k / nx, ny)};
+            if (szo_point_coveredby(p, r, np)) pt_push(out, p.x, p.y);
+        }
+    }
+    free(r);
+    return status;
+}
+
+int32_t szo_generate_subfloe_points(sz_handle *h, const sz_points_generator *g, int64_t n_floes, const int64_t *floes,
+                                    int64_t *offsets, double *x, double *y, int64_t cap_points, int32_t *status, int32_t install) {
+    if (!h || !g || !offsets || n_floes < 0) return SZ_ERR_INVALID;
+    if (g->kind != SZ_POINTS_MONTE_CARLO && g->kind != SZ_POINTS_SUB_GRID) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: unknown generator");
+    if (g->kind == SZ_POINTS_MONTE_CARLO ? g->npoints < 1 : !(g->delta_g > 0)) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: bad generator parameters");
+    if (!floes && n_floes != h->n_init) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: floes == NULL means all n_init floes");
+    if (install && floes) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: install needs the whole list (floes == NULL)");
+    for (int64_t k = 0; floes && k < n_floes; ++k)
+        if (floes[k] < 1 || floes[k] > h->n) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: floe index out of range");
+    ptlist *lists = (ptlist *)calloc((size_t)(n_floes > 0 ? n_floes : 1), sizeof(ptlist));
+    int *st = (int *)malloc(sizeof(int) * (size_t)(n_floes > 0 ? n_floes : 1));
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t k = 0; k < n_floes; ++k) st[k] = generate_points_one(h, g, floes ? floes[k] - 1 : k, &lists[k]);
+    offsets[0] = 0;
+    for (int64_t k = 0; k < n_floes; ++k) offsets[k + 1] = offsets[k] + lists[k].n;
+    int32_t rc = SZ_OK;
+    if (x && y) {
+        if (offsets[n_floes] > cap_points) rc = fail(h, SZ_ERR_CAPACITY, "generate_subfloe_points: output arrays too small");
+        else
+            for (int64_t k = 0; k < n_floes; ++k) {
+                memcpy(x + offsets[k], lists[k].x, sizeof(double) * (size_t)lists[k].n);
+                memcpy(y + offsets[k], lists[k].y, sizeof(double) * (size_t)lists[k].n);
+            }
+    }
+    if (rc == SZ_OK && install)
+        for (int64_t k = 0; k < n_floes; ++k) {
+            free(h->mcx[k]); free(h->mcy[k]);
+            h->nmc[k] = lists[k].n;
+            h->mcx[k] = (double *)malloc(sizeof(double) * (size_t)(lists[k].n > 0 ? lists[k].n : 1));
+            h->mcy[k] = (double *)malloc(sizeof(double) * (size_t)(lists[k].n > 0 ? lists[k].n : 1));
+            memcpy(h->mcx[k], lists[k].x, sizeof(double) * (size_t)lists[k].n);
+            memcpy(h->mcy[k], lists[k].y, sizeof(double) * (size_t)lists[k].n);
+            if (st[k] == SZ_STATUS_REMOVE) h->status[k] = SZ_STATUS_REMOVE;
+        }
+    for (int64_t k = 0; k < n_floes; ++k) {
+        if (status) status[k] = st[k];
+        free(lists[k].x); free(lists[k].y);
+    }
+    free(lists); free(st);
+    return rc;
 }
 
 /* calc_eulerian_data!, output.jl:794-919 (no topography: the cell polygon list is the cell box) */

@@ -65,6 +65,13 @@ class FloeSoA(C.Structure):
                  ("mc_offsets", c_i64_p), ("mc_x", c_double_p), ("mc_y", c_double_p)])
 
 
+class PointsGenerator(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("npoints", C.c_int32), ("err", C.c_double), ("delta_g", C.c_double), ("seed", C.c_uint64)]
+
+
+POINTS_MONTE_CARLO, POINTS_SUB_GRID = 0, 1
+
+
 class Counts(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "n_init", "n_total", "n_vertices", "n_mc", "n_ghost_links", "n_candidates", "n_pairs",
@@ -127,6 +134,8 @@ class Library:
         "eulerian_data": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int32, c_i32_p, c_double_p]),
         "clip_polygons": (C.c_int32, [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                       C.c_int32, C.c_int32, c_i32_p, c_double_p, c_double_p]),
+        "generate_subfloe_points": (C.c_int32, [C.c_void_p, C.POINTER(PointsGenerator), C.c_int64, c_i64_p, c_i64_p, c_double_p,
+                                                c_double_p, C.c_int64, c_i32_p, C.c_int32]),
         # slab decomposition inside the library
         "slab_create": (C.c_int32, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, c_i32_p, C.c_double, C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -535,6 +544,24 @@ class Handle:
         data = np.zeros(nx * ny * len(kinds))
         self._ck(self.lib.eulerian_data(self.h, nx, ny, _dp(xg), _dp(yg), len(kinds), kinds.ctypes.data_as(c_i32_p), _dp(data)))
         return data.reshape((nx, ny, len(kinds)), order="F")
+
+    def generate_subfloe_points(self, kind, npoints=1000, err=0.1, delta_g=0.0, seed=0, floes=None, install=False):
+        """generate_subfloe_points (coupling.jl:172-321) for the resident floes (`floes`: 1-based indices, None = all)
+        -> (offsets [n+1], x, y, status [n]) in the body frame."""
+        g = PointsGenerator(kind, int(npoints), float(err), float(delta_g), int(seed))
+        if floes is None:
+            n, fp = self.counts()["n_init"], None
+        else:
+            fl = np.ascontiguousarray(floes, dtype=np.int64)
+            n, fp = len(fl), _ip(fl)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        sp = status.ctypes.data_as(c_i32_p)
+        self._ck(self.lib.generate_subfloe_points(self.h, C.byref(g), n, fp, _ip(offs), None, None, 0, sp, 0))  # sizes
+        m = int(offs[-1])
+        x, y = np.zeros(max(m, 1)), np.zeros(max(m, 1))
+        self._ck(self.lib.generate_subfloe_points(self.h, C.byref(g), n, fp, _ip(offs), _dp(x), _dp(y), m, sp, 1 if install else 0))
+        return offs, x[:m], y[:m], status[:n]
 
     def clip_polygons(self, p, q, cap_regions=64, cap_points=8192):
         p = np.ascontiguousarray(p, dtype=np.float64)

@@ -2147,6 +2147,104 @@ extern "C" int32_t sz_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const 
     return SZ_OK;
 }
 
+// generate_subfloe_points (coupling.jl:172-208, :235-321) for floes of the resident list
+extern "C" int32_t sz_generate_subfloe_points(sz_handle *h, const sz_points_generator *g, int64_t n_floes, const int64_t *floes,
+                                              int64_t *offsets, double *x, double *y, int64_t cap_points, int32_t *status,
+                                              int32_t install) {
+    if (!h || !g || !offsets || n_floes < 0) return SZ_ERR_INVALID;
+    if (!h->have_floes) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points before upload_floes");
+    if (g->kind != SZ_POINTS_MONTE_CARLO && g->kind != SZ_POINTS_SUB_GRID) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: unknown generator");
+    if (g->kind == SZ_POINTS_MONTE_CARLO ? g->npoints < 1 : !(g->delta_g > 0)) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: bad generator parameters");
+    if (!floes && n_floes != h->n_init) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: floes == NULL means all n_init floes");
+    if (install && floes) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: install needs the whole list (floes == NULL)");
+    if (install && h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: install with ghosts present");
+    if (n_floes > (1ll << 28)) return fail(h, SZ_ERR_UNSUPPORTED, "generate_subfloe_points: too many floes");
+    cudaSetDevice(h->cfg.device);
+    cudaStream_t st = h->L.stream;
+    const int n = (int)n_floes;
+    offsets[0] = 0;
+    if (n == 0) return SZ_OK;
+    int *d_floes = nullptr, *d_count = nullptr, *d_attempt = nullptr, *d_status = nullptr, *d_off = nullptr, *d_scan = nullptr;
+    double2 *d_out = nullptr;
+    double *d_x = nullptr, *d_y = nullptr;
+    long long *d_off64 = nullptr;
+    int32_t rc = SZ_OK;
+    std::vector<int> hidx, hcount((size_t)n), hstatus((size_t)n);
+    auto cleanup = [&]() {
+        cudaFree(d_floes); cudaFree(d_count); cudaFree(d_attempt); cudaFree(d_status); cudaFree(d_off); cudaFree(d_scan);
+        cudaFree(d_out); cudaFree(d_x); cudaFree(d_y); cudaFree(d_off64);
+    };
+#define PCK(expr)                                                                                                      \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess) {                                                                                       \
+            snprintf(h->err, sizeof(h->err), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            cleanup();                                                                                                 \
+            return SZ_ERR_CUDA;                                                                                        \
+        }                                                                                                              \
+    } while (0)
+    if (floes) {
+        hidx.resize((size_t)n);
+        for (int k = 0; k < n; ++k) {
+            if (floes[k] < 1 || floes[k] > h->n_total) return fail(h, SZ_ERR_INVALID, "generate_subfloe_points: floe index out of range");
+            hidx[k] = (int)(floes[k] - 1);
+        }
+        PCK(dalloc(&d_floes, (size_t)n));
+        PCK(cudaMemcpyAsync(d_floes, hidx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    }
+    PCK(dalloc(&d_count, (size_t)n)); PCK(dalloc(&d_attempt, (size_t)n)); PCK(dalloc(&d_status, (size_t)n));
+    szk_points_count(h->L, h->S, *g, d_floes, n, d_count, d_attempt, d_status);
+    PCK(cudaMemcpyAsync(hcount.data(), d_count, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    PCK(cudaMemcpyAsync(hstatus.data(), d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    PCK(cudaGetLastError());
+    std::vector<int> hoff((size_t)n + 1, 0);
+    for (int k = 0; k < n; ++k) {
+        offsets[k + 1] = offsets[k] + hcount[k];
+        if (offsets[k + 1] > (1ll << 30)) { cleanup(); return fail(h, SZ_ERR_UNSUPPORTED, "generate_subfloe_points: more than 2^30 points"); }
+        hoff[k + 1] = (int)offsets[k + 1];
+        if (status) status[k] = hstatus[k];
+    }
+    const long long M = offsets[n];
+    const bool want_points = x && y;
+    if (want_points && M > cap_points) { cleanup(); return fail(h, SZ_ERR_CAPACITY, "generate_subfloe_points: output arrays too small"); }
+    if ((want_points || install) && M > 0) {
+        PCK(dalloc(&d_off, (size_t)n + 1));
+        PCK(cudaMemcpyAsync(d_off, hoff.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+        PCK(dalloc(&d_out, (size_t)M));
+        szk_points_write(h->L, h->S, *g, d_floes, n, d_attempt, d_off, d_out);
+        if (want_points) {
+            PCK(dalloc(&d_x, (size_t)M)); PCK(dalloc(&d_y, (size_t)M));
+            szk_deinterleave(h->L, d_out, d_x, d_y, M);
+            PCK(cudaMemcpyAsync(x, d_x, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+            PCK(cudaMemcpyAsync(y, d_y, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+        }
+        PCK(cudaStreamSynchronize(st));
+        PCK(cudaGetLastError());
+    }
+    if (install) {  // the generated points become the store's Monte-Carlo points (floe.jl:37-38), `remove` tags are applied
+        Store &S = h->S;
+        std::vector<long long> mo((size_t)n + 1);
+        for (int k = 0; k <= n; ++k) mo[k] = offsets[k];
+        cudaFree(S.mc);
+        S.mc = d_out;
+        d_out = nullptr;
+        if (!S.mc) PCK(dalloc(&S.mc, 1));
+        S.cap_mc = M;
+        PCK(cudaMemcpy(S.mc_off, mo.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+        for (int k = 0; k < n; ++k) hstatus[k] = hstatus[k] == SZ_STATUS_REMOVE ? 1 : 0;
+        PCK(cudaMemcpy(d_status, hstatus.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        szk_apply_remove_flags(h->L, S, d_status, n);
+        PCK(cudaStreamSynchronize(st));
+        h->h_mc_off = mo;
+        h->n_mc = M;
+        h->gen++;
+    }
+#undef PCK
+    cleanup();
+    return rc;
+}
+
 extern "C" int32_t sz_clip_polygons(sz_handle *h, const double *p_xy, int32_t np, const double *q_xy, int32_t nq,
                                     int32_t cap_regions, int32_t cap_points, int32_t *out_offsets, double *out_xy,
                                     double *out_areas) {

@@ -250,6 +250,7 @@ void szk_mc_regather(const Launch &L, double2 *dst, const long long *dst_off, co
 void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);
 void szk_coupling(const Launch &L, const Store &S, const Params &P);
 void szk_apply_coupling_tags(const Launch &L, const Store &S);
+void szk_apply_remove_flags(const Launch &L, const Store &S, const int *flags, int n);  // status.tag = remove where flags[i] != 0
 void szk_coupling_reg(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P);
 void szk_cells_final(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P);
 void szk_cells_sort_and_clip(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P, int n_rec_hint);
@@ -282,5 +283,10 @@ struct SzkEulArgs {
 };
 
 int szk_eul_run(const Launch &L, const Store &S, const SzkEulArgs &A);
+// sub-floe point generation: count pass (points per floe, accepted Monte-Carlo attempt, status), write pass
+void szk_points_count(const Launch &L, const Store &S, const sz_points_generator &g, const int *floes, int n, int *count, int *attempt,
+                      int *status);
+void szk_points_write(const Launch &L, const Store &S, const sz_points_generator &g, const int *floes, int n, int *attempt, const int *off,
+                      double2 *out);
 long long szk_launch_count(bool reset);
 void szk_count_launches(int n);

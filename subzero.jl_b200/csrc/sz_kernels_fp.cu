@@ -542,6 +542,15 @@ void szk_apply_coupling_tags(const Launch &L, const Store &S) {
     szk_count_launches(1);
 }
 
+__global__ void k_apply_remove_flags(Store S, const int *__restrict__ flags, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flags[i]) S.status[i] = SZ_STATUS_REMOVE;
+}
+void szk_apply_remove_flags(const Launch &L, const Store &S, const int *flags, int n) {
+    if (n <= 0) return;
+    k_apply_remove_flags<<<(n + 255) / 256, 256, 0, L.stream>>>(S, flags, n);
+}
+
 // ---- K7: state update (update_floe.jl:392-551) -------------------------------------------------------------
 // calc_strain! (:425-453) evaluates u - xi r sin(theta), u + xi r cos(theta)
 // at every vertex; with r sin(theta) = y and r cos(theta) = x those are u - xi y and u + xi x

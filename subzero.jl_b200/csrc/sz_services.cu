@@ -422,3 +422,249 @@ int szk_services_configure(const Launch &L) {
     if (cudaFuncSetAttribute(k_eul_area_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     return 0;
 }
+
+// ---- rank 4: sub-floe point generation (generate_subfloe_points, coupling.jl:172-208, :235-321) ----------------------
+// One block per floe.  Two passes with the same arithmetic: COUNT (how many points, which Monte-Carlo attempt is
+// accepted, status) and WRITE (the points, compacted in the reference's order with block-wide prefix sums), with a
+// device scan of the counts in between, so the output is one contiguous CSR array.  The ring is read from global
+// memory and translated by -centroid on the fly (_translate_poly: x + (-cx), the same bits as the reference).
+#define PG_NT 128
+
+__device__ __forceinline__ unsigned long long pg_sm64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// u(seed, floe id, attempt, draw, axis) in [0, 1): the counter-based generator of include/subzero_b200.h
+__device__ __forceinline__ double pg_uniform(unsigned long long seed, long long id, int attempt, long long draw, int axis) {
+    unsigned long long z = pg_sm64(seed ^ ((unsigned long long)id * 0x9E3779B97F4A7C15ull));
+    z = pg_sm64(z ^ (((unsigned long long)attempt << 40) | (unsigned long long)draw));
+    z = pg_sm64(z ^ (unsigned long long)axis);
+    return (double)(z >> 11) * 0x1.0p-53;
+}
+// element i of range(a, b, length = n): endpoints exact, interior points in double-double, rounded once
+__device__ __forceinline__ double pg_range_elem(double a, double b, long long i, long long n) {
+    if (i == 0 || n < 2) return a;
+    if (i == n - 1) return b;
+    double dh = b - a, bb = dh - b, dl = (b - (dh - bb)) + (-a - bb);
+    const double c = (double)i, m = (double)(n - 1);
+    double ph = dh * c, pl = __fma_rn(dh, c, -ph) + dl * c;
+    double s = ph + pl;
+    pl = pl - (s - ph);
+    ph = s;
+    double qh = ph / m, th = qh * m, tl = __fma_rn(qh, m, -th);
+    double ql = (((ph - th) - tl) + pl) / m;
+    double sh = a + qh, t = sh - a, sl = (a - (sh - t)) + (qh - t);
+    return sh + (sl + ql);
+}
+// GO.coveredby(point, ring) on the translated ring: interior or boundary (one thread, edges in order)
+__device__ bool pg_coveredby(double2 p, const double2 *__restrict__ g, int n, double cx, double cy) {
+    bool in = false;
+    double2 a = make_double2(g[0].x + (-cx), g[0].y + (-cy));
+    for (int k = 0; k + 1 < n; ++k) {
+        const double2 b = make_double2(g[k + 1].x + (-cx), g[k + 1].y + (-cy));
+        if (orient2d(a, b, p) == 0.0 && p.x >= fmin(a.x, b.x) && p.x <= fmax(a.x, b.x) && p.y >= fmin(a.y, b.y) && p.y <= fmax(a.y, b.y))
+            return true;
+        if ((a.y > p.y) != (b.y > p.y)) {
+            const double xi = a.x + (p.y - a.y) / (b.y - a.y) * (b.x - a.x);
+            if (p.x < xi) in = !in;
+        }
+        a = b;
+    }
+    return in;
+}
+// block-wide exclusive prefix sum of one int per thread (PG_NT threads); *total = sum over the block
+__device__ int pg_block_scan(int v, int *total) {
+    __shared__ int ws[PG_NT / 32], tot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < w; ++k) off += ws[k];
+    if (threadIdx.x == PG_NT - 1) tot = off + x;
+    __syncthreads();
+    *total = tot;
+    return off + x - v;
+}
+
+struct PgArgs {
+    sz_points_generator g;
+    const int *floes;   // 0-based indices, nullptr = identity
+    int n;
+    int *count, *attempt, *status;  // [n]
+    const int *off;     // [n + 1] (write pass)
+    double2 *out;
+};
+
+// edge i (1 <= i < np) of the sub-grid generator: points it emits (coupling.jl:248-288); WRITE: store them at dst
+template <bool WRITE>
+__device__ int pg_edge(const double2 *__restrict__ g, int i, double cx, double cy, double dg, double2 *dst) {
+    double x1 = g[i - 1].x + (-cx), y1 = g[i - 1].y + (-cy), x2 = g[i].x + (-cx), y2 = g[i].y + (-cy);
+    double dx = x2 - x1, dy = y2 - y1;
+    double l = sqrt(dx * dx + dy * dy);
+    int n = 1;
+    if (WRITE) dst[0] = make_double2(x1, y1);
+    if (l <= 2 * dg) {
+        if (l > dg) {
+            if (WRITE) dst[1] = make_double2(x1 + dx / 2, y1 + dy / 2);
+            n = 2;
+        }
+        return n;
+    }
+    if (dx == 0) {
+        const double sg = (double)((dy > 0) - (dy < 0));
+        y1 += dg / 2 * sg;
+        y2 -= dg / 2 * sg;
+    } else if (dy == 0) {
+        const double sg = (double)((dx > 0) - (dx < 0));
+        x1 += dg / 2 * sg;
+        x2 -= dg / 2 * sg;
+    } else {  // the reference's x shift is positive whatever the direction of the edge
+        const double m = dy / dx;
+        const double xs = sqrt(dg * dg / (4 * (1 + m * m)));
+        const double ys = m * xs;
+        x1 += xs; x2 -= xs; y1 += ys; y2 -= ys;
+    }
+    l = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+    const long long ne = (long long)ceil(l / dg) + 1;
+    if (WRITE)
+        for (long long k = 0; k < ne; ++k) dst[1 + k] = make_double2(pg_range_elem(x1, x2, k, ne), pg_range_elem(y1, y2, k, ne));
+    return 1 + (int)ne;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(PG_NT) k_points(Store S, PgArgs A) {
+    __shared__ double red[4][PG_NT / 32];
+    __shared__ int s_in;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int q = blockIdx.x; q < A.n; q += gridDim.x) {
+        const int f = A.floes ? A.floes[q] : q;
+        const double2 *__restrict__ g = S.verts + S.vstart[f];
+        const int np = S.vcount[f];
+        const double cx = S.cx[f], cy = S.cy[f];
+        // GI.extent of the translated ring
+        double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+        for (int k = tid; k < np; k += PG_NT) {
+            const double x = g[k].x + (-cx), y = g[k].y + (-cy);
+            xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        __syncthreads();
+        if (lane == 0) { red[0][w] = xmin; red[1][w] = xmax; red[2][w] = ymin; red[3][w] = ymax; }
+        __syncthreads();
+        for (int k = 0; k < PG_NT / 32; ++k) {
+            xmin = fmin(xmin, red[0][k]); xmax = fmax(xmax, red[1][k]); ymin = fmin(ymin, red[2][k]); ymax = fmax(ymax, red[3][k]);
+        }
+        const double Dx = xmax - xmin, Dy = ymax - ymin;
+        double2 *dst = WRITE ? A.out + A.off[q] : nullptr;
+        if (A.g.kind == SZ_POINTS_MONTE_CARLO) {
+            const int n = A.g.npoints;
+            const long long id = S.id[f];
+            if (!WRITE) {
+                const double area = S.area[f];
+                int count = 1, used = 0, kept = 0, status = SZ_STATUS_ACTIVE;
+                double err = 1.0;
+                while (err > A.g.err) {  // warp- and block-uniform
+                    if (count > 10) {
+                        err = 0.0;
+                        status = SZ_STATUS_REMOVE;
+                    } else {
+                        int in = 0;
+                        for (int j = tid; j < n; j += PG_NT) {
+                            const double2 p = make_double2(xmin + Dx * pg_uniform(A.g.seed, id, count, j, 0),
+                                                           ymin + Dy * pg_uniform(A.g.seed, id, count, j, 1));
+                            in += pg_coveredby(p, g, np, cx, cy) ? 1 : 0;
+                        }
+                        int tot;
+                        pg_block_scan(in, &tot);
+                        kept = tot;
+                        err = fabs((double)tot / (double)n * (Dx * Dy) - area) / area;
+                        used = count;
+                        count += 1;
+                    }
+                }
+                if (kept == 0) status = SZ_STATUS_REMOVE;
+                if (tid == 0) { A.count[q] = kept; A.attempt[q] = used; A.status[q] = status; }
+            } else {
+                const int used = A.attempt[q];
+                int base = 0;
+                for (int j0 = 0; used > 0 && j0 < n; j0 += PG_NT) {  // draw order is kept: chunk by chunk, scan inside a chunk
+                    const int j = j0 + tid;
+                    double2 p = make_double2(0.0, 0.0);
+                    bool in = false;
+                    if (j < n) {
+                        p = make_double2(xmin + Dx * pg_uniform(A.g.seed, id, used, j, 0), ymin + Dy * pg_uniform(A.g.seed, id, used, j, 1));
+                        in = pg_coveredby(p, g, np, cx, cy);
+                    }
+                    int tot;
+                    const int pos = pg_block_scan(in ? 1 : 0, &tot);
+                    if (in) dst[base + pos] = p;
+                    base += tot;
+                }
+            }
+        } else {
+            const double dg = A.g.delta_g;
+            int base = 0;
+            // every vertex + the points on its edge, edges in ring order
+            for (int i0 = 1; i0 < np; i0 += PG_NT) {
+                const int i = i0 + tid;
+                const int ne = i < np ? pg_edge<false>(g, i, cx, cy, dg, nullptr) : 0;
+                int tot;
+                const int pos = pg_block_scan(ne, &tot);
+                if (WRITE && i < np) pg_edge<true>(g, i, cx, cy, dg, dst + base + pos);
+                base += tot;
+            }
+            // interior lattice (:289-318)
+            long long nx = (long long)ceil((xmax - xmin) / dg), ny = (long long)ceil((ymax - ymin) / dg);
+            const bool xs1 = nx < 3, ys1 = ny < 3;
+            if (xs1) nx = 1;
+            if (ys1) ny = 1;
+            const double xa = xmin + dg / 2, xb = xmax - dg / 2, ya = ymin + dg / 2, yb = ymax - dg / 2;
+            for (long long k0 = 0; k0 < nx * ny; k0 += PG_NT) {
+                const long long k = k0 + tid;
+                double2 p = make_double2(0.0, 0.0);
+                bool in = false;
+                if (k < nx * ny) {
+                    p = make_double2(xs1 ? 0.0 : pg_range_elem(xa, xb, k % nx, nx), ys1 ? 0.0 : pg_range_elem(ya, yb, k / nx, ny));
+                    in = pg_coveredby(p, g, np, cx, cy);
+                }
+                int tot;
+                const int pos = pg_block_scan(in ? 1 : 0, &tot);
+                if (WRITE && in) dst[base + pos] = p;
+                base += tot;
+            }
+            if (!WRITE && tid == 0) { A.count[q] = base; A.attempt[q] = 0; A.status[q] = SZ_STATUS_ACTIVE; }
+        }
+        __syncthreads();
+        (void)s_in;
+    }
+}
+
+void szk_points_count(const Launch &L, const Store &S, const sz_points_generator &g, const int *floes, int n, int *count, int *attempt,
+                      int *status) {
+    if (n <= 0) return;
+    PgArgs A = {g, floes, n, count, attempt, status, nullptr, nullptr};
+    k_points<false><<<sv_grid(L, n, 1), PG_NT, 0, L.stream>>>(S, A);
+    szk_count_launches(1);
+}
+void szk_points_write(const Launch &L, const Store &S, const sz_points_generator &g, const int *floes, int n, int *attempt, const int *off,
+                      double2 *out) {
+    if (n <= 0) return;
+    PgArgs A = {g, floes, n, nullptr, attempt, nullptr, off, out};
+    k_points<true><<<sv_grid(L, n, 1), PG_NT, 0, L.stream>>>(S, A);
+    szk_count_launches(1);
+}

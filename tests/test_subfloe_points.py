@@ -1,0 +1,175 @@
+"""Sub-floe point generation: generate_subfloe_points, coupling.jl:172-208 (Monte Carlo) and
+:235-321 (sub-grid), through sz_generate_subfloe_points.
+
+Sub-grid generator: deterministic — the oracle is pinned on the reference's own known answers
+(/root/reference/test/test_physical_processes/test_coupling.jl:60-162) and the CUDA kernels must reproduce the oracle bit
+for bit.  Monte-Carlo generator: Julia's Xoshiro stream cannot be reproduced, so the library and the oracle share a
+counter-based generator (bit-exact against each other), and what is held against the REFERENCE is what its test holds
+(:20-36: every point inside, the accepted area error, status) plus the distribution (two-sample KS test against an
+independent uniform sample of the polygon) and the `remove` semantics of :182-185,:203-205."""
+import numpy as np
+import pytest
+
+import fields
+from subzero_jl_b200 import capi, host, synth
+
+DG = 10 / np.sqrt(2)  # SubGridPointsGenerator{Float64}(10/sqrt(2)), test_coupling.jl:61
+
+
+def ring_handle(lib, rings, **kw):
+    """A handle holding the given closed rings as floes (centroid, area computed like the reference's constructor)."""
+    grid = host.RegRectilinearGrid(-1e5, 1e5, -1e5, 1e5, Nx=2, Ny=2)
+    dom = host.Domain(*[host.OpenBoundary(d, grid) for d in (host.North, host.South, host.East, host.West)])
+    floes = host.FloeField([host.Floe([r], 0.5, 0.0, rng=np.random.default_rng(1)) for r in rings])
+    h = capi.Handle(lib, **kw)
+    h.set_grid(grid.Nx, grid.Ny, grid.x0, grid.xf, grid.y0, grid.yf)
+    dom.push(h)
+    h.upload_floes(floes)
+    return h, floes
+
+
+SQUARE = [[-2.5, -2.5], [-2.5, 2.5], [2.5, 2.5], [2.5, -2.5], [-2.5, -2.5]]
+TALL = [[-2.0, -10.0], [-2.0, 10.0], [2.0, 10.0], [2.0, -10.0], [-2.0, -10.0]]
+WIDE = [[-10.0, -2.0], [-10.0, 2.0], [10.0, 2.0], [10.0, -2.0], [-10.0, -2.0]]
+TRAPEZOID = [[-8.0, -8.0], [-4.0, 8.0], [4.0, 8.0], [8.0, -8.0], [-8.0, -8.0]]
+
+
+def check_reference_sub_grid_answers(lib):
+    h, floes = ring_handle(lib, [SQUARE, TALL, WIDE, TRAPEZOID])
+    offs, x, y, status = h.generate_subfloe_points(capi.POINTS_SUB_GRID, delta_g=DG)
+    assert np.all(status == capi.STATUS_ACTIVE)
+    px = [x[offs[k]:offs[k + 1]] for k in range(4)]
+    py = [y[offs[k]:offs[k + 1]] for k in range(4)]
+    # test_coupling.jl:80-81
+    assert np.array_equal(px[0], [-2.5, -2.5, 2.5, 2.5, 0.0]) and np.array_equal(py[0], [-2.5, 2.5, 2.5, -2.5, 0.0])
+    # :99-105
+    assert np.array_equal(px[1], [-2.0] * 5 + [2.0] * 5 + [0.0] * 3)
+    assert np.allclose(py[1], [-10.0, -6.46447, 0.0, 6.46447, 10.0, 10.0, 6.46447, 0.0, -6.46447, -10, -6.46447, 0.0, 6.46447], rtol=0, atol=1e-5)
+    # :123-130
+    assert np.allclose(px[2], [-10, -10, -6.46447, 0.0, 6.46447, 10, 10, 6.46447, 0.0, -6.464466, -6.46447, 0, 6.46447], rtol=0, atol=1e-5)
+    assert np.array_equal(py[2], [-2.0] + [2.0] * 5 + [-2.0] * 4 + [0.0] * 3)
+    # :147-162 (the trapezoid's centroid is not on the origin in y)
+    cy = floes.centroid_y[3]
+    assert np.allclose(px[3], [-8, -7.14251, -6.0, -4.85749, -4.0, 0.0, 4.0, 4.85749, 6.0, 7.14251, 8.0, 4.46447, 0.0, -4.46447,
+                               -4.46447, 0.0, 4.46447, -4.46447, 0.0, 4.46447, -4.46447, 0.0, 4.46447], rtol=0, atol=1e-5)
+    assert np.allclose(py[3] + cy, [-8, -4.57003, 0.0, 4.57003, 8.0, 8.0, 8.0, 4.57003, 0.0, -4.57003, -8.0, -8.0, -8.0, -8.0,
+                                    -4.46447, -4.46447, -4.46447, 0.0, 0.0, 0.0, 4.46447, 4.46447, 4.46447], rtol=0, atol=1e-5)
+    h.close()
+
+
+def test_sub_grid_reference_answers_oracle(oracle_lib):
+    check_reference_sub_grid_answers(oracle_lib)
+
+
+def uniform_in_ring(ring, n, rng):
+    """An independent uniform sample of the polygon (numpy generator, rejection from the bounding box)."""
+    ring = np.asarray(ring)
+    lo, hi = ring.min(0), ring.max(0)
+    out = np.zeros((0, 2))
+    while len(out) < n:
+        p = lo + (hi - lo) * rng.random((4 * n, 2))
+        out = np.concatenate([out, p[host.points_in_ring(p[:, 0], p[:, 1], ring)]])
+    return out[:n]
+
+
+def check_monte_carlo(lib):
+    from scipy import stats
+    f = fields.fixture_shape_field(scale=1.0, walls="collision", npoints=10)  # the reference's floe_shapes.jld2 (non-convex rings)
+    h = synth.setup_handle(f, lib)
+    fa = f.floes
+    sel = np.arange(1, 41)
+    offs, x, y, status = h.generate_subfloe_points(capi.POINTS_MONTE_CARLO, npoints=1000, err=0.1, seed=1, floes=sel)
+    offs2, x2, y2, status2 = h.generate_subfloe_points(capi.POINTS_MONTE_CARLO, npoints=1000, err=0.1, seed=1, floes=sel)
+    assert np.array_equal(offs, offs2) and np.array_equal(x, x2) and np.array_equal(y, y2)  # test_coupling.jl:37-47
+    _, x3, _, _ = h.generate_subfloe_points(capi.POINTS_MONTE_CARLO, npoints=1000, err=0.1, seed=2, floes=sel)
+    assert len(x3) != len(x) or not np.array_equal(x3, x)
+    rng = np.random.default_rng(3)
+    pvals = []
+    for k, i in enumerate(sel - 1):
+        ring = fa.ring(i) - fa.centroid(i)
+        px, py = x[offs[k]:offs[k + 1]], y[offs[k]:offs[k + 1]]
+        assert len(px) > 0 and status[k] == capi.STATUS_ACTIVE                  # :28,:36
+        assert host.points_in_ring(px, py, ring).all()                          # :29-30
+        box = np.prod(ring.max(0) - ring.min(0))
+        assert abs(len(px) / 1000 * box - fa.area[i]) / fa.area[i] < 0.1       # :33-35
+        ref = uniform_in_ring(ring, 4000, rng)
+        pvals += [stats.ks_2samp(px, ref[:, 0]).pvalue, stats.ks_2samp(py, ref[:, 1]).pvalue]
+    pvals = np.array(pvals)
+    # 80 independent KS tests of true nulls: p-values are uniform — none absurdly small, and their own distribution is flat
+    assert pvals.min() > 1e-4 and stats.kstest(pvals, "uniform").pvalue > 1e-3, (pvals.min(), np.sort(pvals)[:5])
+    # an error bound that cannot be met: ten attempts, the last attempt's points are kept, the floe is tagged `remove` (:182-185)
+    offs, x, y, status = h.generate_subfloe_points(capi.POINTS_MONTE_CARLO, npoints=200, err=1e-9, seed=5, floes=sel[:5])
+    assert np.all(status == capi.STATUS_REMOVE) and np.all(np.diff(offs) > 0)
+    h.close()
+    # a sliver no draw can hit: no points, `remove` (:203-205)
+    sliver = [[0.0, 0.0], [1e4, 1e4], [1e4 + 1e-7, 1e4], [0.0, 0.0]]
+    hs, _ = ring_handle(lib, [sliver])
+    offs, x, y, status = hs.generate_subfloe_points(capi.POINTS_MONTE_CARLO, npoints=50, err=0.1, seed=1)
+    assert offs[-1] == 0 and status[0] == capi.STATUS_REMOVE
+    hs.close()
+
+
+def test_monte_carlo_reference_properties_oracle(oracle_lib):
+    check_monte_carlo(oracle_lib)
+
+
+def test_install_replaces_the_resident_points_oracle(oracle_lib):
+    check_install(oracle_lib)
+
+
+def check_install(lib):
+    """install: the generated points become the floes' x/y_subfloe_points (replace_floe!, update_floe.jl:55-66) and the
+    coupling integrates over them."""
+    f = synth.make_field(400, scale=0.98, walls="collision", npoints=30, cache=False)
+    h = synth.setup_handle(f, lib)
+    offs, x, y, status = h.generate_subfloe_points(capi.POINTS_SUB_GRID, delta_g=400.0, install=True)
+    fa = h.download_floes()
+    assert np.array_equal(fa.mc_offsets, offs) and np.array_equal(fa.mc_x, x) and np.array_equal(fa.mc_y, y)
+    h.step_coupling()
+    a = h.download_floes(mc=False)
+    f2 = synth.make_field(400, scale=0.98, walls="collision", npoints=30, cache=False)
+    f2.floes.mc_offsets, f2.floes.mc_x, f2.floes.mc_y = offs, x, y
+    h2 = synth.setup_handle(f2, lib)
+    h2.step_coupling()
+    b = h2.download_floes(mc=False)
+    assert np.array_equal(a.fxOA, b.fxOA) and np.array_equal(a.trqOA, b.trqOA) and np.abs(a.fxOA).max() > 0
+    h.close()
+    h2.close()
+
+
+# ---- CUDA ------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_sub_grid_reference_answers_cuda(product_lib):
+    check_reference_sub_grid_answers(product_lib)
+
+
+@pytest.mark.gpu
+def test_monte_carlo_reference_properties_cuda(product_lib):
+    check_monte_carlo(product_lib)
+
+
+@pytest.mark.gpu
+def test_install_replaces_the_resident_points_cuda(product_lib):
+    check_install(product_lib)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["monte_carlo", "sub_grid"])
+def test_points_cuda_equal_oracle_bit_for_bit(kind, product_lib, oracle_lib):
+    """Same generator, same arithmetic: point counts, order, coordinates and status tags are identical — on Voronoi
+    cells and on the reference's non-convex fixture shapes (rings of up to 591 points)."""
+    for f in (synth.make_field(3000, scale=1.0, walls="periodic", npoints=10, cache=False),
+              fields.fixture_shape_field(scale=1.0, walls="collision", npoints=10)):
+        hg, ho = synth.setup_handle(f, product_lib), synth.setup_handle(f, oracle_lib)
+        kw = dict(npoints=300, err=0.05, seed=11) if kind == "monte_carlo" else dict(delta_g=350.0)
+        k = capi.POINTS_MONTE_CARLO if kind == "monte_carlo" else capi.POINTS_SUB_GRID
+        a, b = hg.generate_subfloe_points(k, **kw), ho.generate_subfloe_points(k, **kw)
+        for u, v, name in zip(a, b, ("offsets", "x", "y", "status")):
+            assert np.array_equal(u, v), (kind, name)
+        assert a[0][-1] > 10 * f.floes.n
+        sub = np.arange(f.floes.n, 0, -7)  # an explicit (descending) floe list
+        a, b = hg.generate_subfloe_points(k, floes=sub, **kw), ho.generate_subfloe_points(k, floes=sub, **kw)
+        for u, v, name in zip(a, b, ("offsets", "x", "y", "status")):
+            assert np.array_equal(u, v), (kind, name, "subset")
+        hg.close()
+        ho.close()
