@@ -170,6 +170,11 @@ struct StepBuf {
     int *g_flag, *g_cnt, *g_off, *g_vcnt, *g_voff;  // [cap_floes+1]
     // scan scratch
     int *scan_block;
+    // single-pass scans (look-back descriptors / tickets of the step's three scans) and the parked neighbour indices
+    unsigned long long *lb_desc;
+    int *lb_ticket;
+    int lb_stride;
+    int *nb_scratch;  // [NB_K][cap_floes]
 };
 
 // floe -> cell registry (grid.floe_locations / ocean.scells, coupling.jl:1329-1454) of one coupling step
@@ -220,11 +225,14 @@ struct Launch {
     int maxv_large, maxx_large;  // workspace of the large-polygon kernels
     int coupling_blocks_per_sm;  // 0 = fill the GPU; > 0 = persistent grid of that many blocks per SM
     bool capturing;              // the stream is being captured into a CUDA graph (sz_step)
+    bool chain_v2;               // fused broad-phase / row chain with single-pass scans (SZ_CHAIN_V1 selects the old one)
+    bool no_phase_events;        // experiment (SZ_GRAPH_NO_EVENTS): no timing-event nodes inside a captured graph
 };
 
 // Timing events: inside a stream capture they must be recorded as EXTERNAL event nodes to stay usable with
 // cudaEventElapsedTime after the graph has run.
 inline void sz_record(const Launch &L, cudaEvent_t e, cudaStream_t s) {
+    if (L.capturing && L.no_phase_events) return;
     cudaEventRecordWithFlags(e, s, L.capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 

@@ -217,6 +217,98 @@ static void scan_excl3(const Launch &L, const Store &S, const Scan3 &a, const in
     g_launch_count += 3;
 }
 
+// ---- single-pass exclusive scan (decoupled look-back): ONE launch instead of three ------------------------------------
+// Tiles take a ticket (forward progress: a tile only ever waits for tiles that already run), publish
+// (flag << 62 | value) in one 64-bit word — flag 1 = the tile's own sum, 2 = inclusive prefix up to and including the
+// tile — and one thread walks back over its predecessors.  Up to three arrays of equal length per launch
+// (blockIdx.y).  The descriptors and tickets of all scans of a step are zeroed by k_grid_zero at its start.
+#define LB_AGG (1ull << 62)
+#define LB_INC (2ull << 62)
+#define LB_VAL ((1ull << 62) - 1)
+struct ScanLB {
+    const int *in[3];
+    int *out[3];
+    int *total_out[3];
+    unsigned long long *desc;  // [3][stride]
+    int *ticket;               // [3]
+    int stride;
+};
+__global__ void __launch_bounds__(SCAN_T) k_scan_lb(ScanLB a, const int *len_ptr, int len_add, const Counters *cnt) {
+    if (cnt->error) return;
+    __shared__ int s_tile, s_excl;
+    const int y = blockIdx.y;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.ticket[y], 1);
+    __syncthreads();
+    const int tile = s_tile, len = *len_ptr + len_add, ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+    const int *in = a.in[y];
+    int *out = a.out[y];
+    if (len == 0) {
+        if (tile == 0 && threadIdx.x == 0) {
+            out[0] = 0;
+            if (a.total_out[y]) *a.total_out[y] = 0;
+        }
+        return;
+    }
+    if (tile >= ntiles) return;
+    unsigned long long *desc = a.desc + (size_t)y * a.stride;
+    const int base = tile * SCAN_TILE, i0 = base + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (i0 + k < len) ? in[i0 + k] : 0;
+        sum += v[k];
+    }
+    int tot;
+    int pre = block_excl_scan_512(sum, &tot);
+    if (threadIdx.x == 0) {
+        int excl = 0;
+        if (tile == 0) {
+            atomicExch(&desc[0], LB_INC | (unsigned long long)tot);
+        } else {
+            atomicExch(&desc[tile], LB_AGG | (unsigned long long)tot);
+            for (int t = tile - 1; t >= 0; --t) {
+                unsigned long long d;
+                do {
+                    d = *(volatile unsigned long long *)&desc[t];
+                } while ((d >> 62) == 0);
+                excl += (int)(d & LB_VAL);
+                if ((d >> 62) == 2) break;
+            }
+            atomicExch(&desc[tile], LB_INC | (unsigned long long)(excl + tot));
+        }
+        s_excl = excl;
+        if (tile == ntiles - 1) {
+            out[len] = excl + tot;
+            if (a.total_out[y]) *a.total_out[y] = excl + tot;
+        }
+    }
+    __syncthreads();
+    pre += s_excl;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (i0 + k < len) out[i0 + k] = pre;
+        pre += v[k];
+    }
+}
+// slot: which of the step's scans (each has its own descriptors): 0 cells, 1 neighbour counts (3 arrays), 2 rows
+#define LB_SLOTS 3
+static void scan_lb(const Launch &L, const Store &S, const StepBuf &B, int slot, int narr, const int *const *in, int *const *out,
+                    int *const *total_out, const int *len_ptr, int len_add, int max_len) {
+    ScanLB a;
+    for (int k = 0; k < 3; ++k) {
+        a.in[k] = k < narr ? in[k] : nullptr;
+        a.out[k] = k < narr ? out[k] : nullptr;
+        a.total_out[k] = k < narr ? total_out[k] : nullptr;
+    }
+    a.stride = B.lb_stride;
+    a.desc = B.lb_desc + (size_t)slot * 3 * B.lb_stride;
+    a.ticket = B.lb_ticket + slot * 3;
+    int tiles = sz_div_up((long long)max_len, SCAN_TILE);
+    if (tiles < 1) tiles = 1;
+    k_scan_lb<<<dim3(tiles, narr), SCAN_T, 0, L.stream>>>(a, len_ptr, len_add, S.cnt);
+    g_launch_count += 1;
+}
+
 static inline int grid_for(const Launch &L, long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
     long long cap = (long long)L.sms * 32;
@@ -250,6 +342,8 @@ __global__ void k_set_counts(Counters *cnt, int n_total, int n_verts) {
     cnt->n_total = n_total;
     cnt->n_verts = n_verts;
     cnt->error = 0;
+    cnt->bb[0] = cnt->bb[1] = ~0ull;  // the fused chain only accumulates into the box (k_bbox2) and resets it behind its last reader
+    cnt->bb[2] = cnt->bb[3] = cnt->bb[4] = 0ull;
 }
 void szk_set_counts(const Launch &L, const Store &S, int n_total, int n_verts) {
     k_set_counts<<<1, 1, 0, L.stream>>>(S.cnt, n_total, n_verts);
@@ -1158,8 +1252,414 @@ __global__ void k_update_boundaries(Store S, Params P) {
     }
 }
 
+// ---- the fused chain (v2): 9 + 5 launches instead of 19 + 10 around the narrow phase ---------------------------------------
+// k_bbox2: k_step_reset's per-floe zeroing + k_bbox.  The bounding-box words and the step counters are reset by
+// k_cell_count2 (after the last reader of the box) for the NEXT collision step; k_set_counts initialises them.
+__global__ void k_bbox2(Store S) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    double xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY, rm = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        S.cfx[i] = 0.0;  // collisions.jl:747-749
+        S.cfy[i] = 0.0;
+        S.ctrq[i] = 0.0;
+        double x = S.cx[i], y = S.cy[i];
+        xmin = fmin(xmin, x);
+        xmax = fmax(xmax, x);
+        ymin = fmin(ymin, y);
+        ymax = fmax(ymax, y);
+        rm = fmax(rm, S.rmax[i]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(FULLMASK, xmin, o));
+        ymin = fmin(ymin, __shfl_xor_sync(FULLMASK, ymin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(FULLMASK, xmax, o));
+        ymax = fmax(ymax, __shfl_xor_sync(FULLMASK, ymax, o));
+        rm = fmax(rm, __shfl_xor_sync(FULLMASK, rm, o));
+    }
+    if (lane_id() == 0 && xmin <= xmax) {
+        atomicMin(&cnt->bb[0], enc_f64(xmin));
+        atomicMin(&cnt->bb[1], enc_f64(ymin));
+        atomicMax(&cnt->bb[2], enc_f64(xmax));
+        atomicMax(&cnt->bb[3], enc_f64(ymax));
+        atomicMax(&cnt->bb[4], enc_f64(rm));
+    }
+}
+
+struct GridGeom {
+    double gx0, gy0, cell;
+    int gnx, gny;
+};
+// k_grid_setup's arithmetic, evaluated redundantly by every thread that needs it (a handful of flops)
+__device__ __forceinline__ GridGeom grid_geom(const Counters *cnt, int cap_cells) {
+    GridGeom g;
+    if (cnt->n_total == 0) {
+        g.gx0 = g.gy0 = 0.0;
+        g.cell = 1.0;
+        g.gnx = g.gny = 1;
+        return g;
+    }
+    double xmin = dec_f64(cnt->bb[0]), ymin = dec_f64(cnt->bb[1]);
+    double xmax = dec_f64(cnt->bb[2]), ymax = dec_f64(cnt->bb[3]), rm = dec_f64(cnt->bb[4]);
+    double cs = 2.0 * rm * (1.0 + 1e-6) + 1e-6;
+    double ex = xmax - xmin, ey = ymax - ymin;
+    double fx = floor(ex / cs) + 1.0, fy = floor(ey / cs) + 1.0;
+    while (fx * fy > (double)cap_cells) {
+        cs *= 1.5;
+        fx = floor(ex / cs) + 1.0;
+        fy = floor(ey / cs) + 1.0;
+    }
+    g.gx0 = xmin;
+    g.gy0 = ymin;
+    g.cell = cs;
+    g.gnx = (int)fx;
+    g.gny = (int)fy;
+    return g;
+}
+
+// k_grid_setup + k_cell_zero + the reset of every look-back scan of this step
+__global__ void k_grid_zero(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const GridGeom g = grid_geom(cnt, B.cap_cells);
+    const int nc = g.gnx * g.gny;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int c = t0; c <= nc; c += nt) {
+        B.cell_count[c] = 0;
+        if (c < nc) B.cell_fill[c] = 0;
+    }
+    for (int k = t0; k < LB_SLOTS * 3 * B.lb_stride; k += nt) B.lb_desc[k] = 0ull;
+    if (t0 < LB_SLOTS * 3) B.lb_ticket[t0] = 0;
+    if (t0 == 0) {
+        cnt->gx0 = g.gx0;
+        cnt->gy0 = g.gy0;
+        cnt->cell = g.cell;
+        cnt->gnx = g.gnx;
+        cnt->gny = g.gny;
+        cnt->n_cells = nc;
+    }
+}
+
+// k_cell_count; thread 0 then resets what k_step_reset used to reset (the box has no reader left in this step)
+__global__ void k_cell_count2(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int n = cnt->n_total, gnx = cnt->gnx, gny = cnt->gny;
+    const double gx0 = cnt->gx0, gy0 = cnt->gy0, cs = cnt->cell;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int ix = (int)floor((S.cx[i] - gx0) / cs), iy = (int)floor((S.cy[i] - gy0) / cs);
+        ix = min(max(ix, 0), gnx - 1);
+        iy = min(max(iy, 0), gny - 1);
+        int c = iy * gnx + ix;
+        B.cell_of[i] = c;
+        atomicAdd(&B.cell_count[c], 1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt->n_cand = cnt->n_dom = cnt->n_rows = cnt->n_fuse = cnt->n_pool = 0;
+        cnt->n_clipfail = cnt->n_kept = cnt->n_overlap = cnt->n_large = cnt->n_mid = 0;
+        cnt->n_domchecks = 0;
+        cnt->bb[0] = cnt->bb[1] = ~0ull;  // for the next collision step (k_bbox2 only accumulates)
+        cnt->bb[2] = cnt->bb[3] = cnt->bb[4] = 0ull;
+    }
+}
+
+// ONE neighbour search: the count pass also parks the indices it finds (up to NB_K per floe, in the cell-sorted
+// slot order so that a warp writes 32 consecutive ints per k); the write pass only reads them back, splits them into
+// j > i / j < i, sorts and stores — floes with more than NB_K candidates search again.
+#define NB_K 20
+template <bool WRITE>
+__global__ void k_neighbours2(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    if (WRITE && (cnt->n_cand > B.cap_pairs || cnt->n_dom > B.cap_dom)) {  // k_pair_check: every thread backs off, one reports
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (cnt->n_cand > B.cap_pairs) { atomicOr(&cnt->error, ERR_PAIR_CAP); cnt->want_pairs = cnt->n_cand; }
+            if (cnt->n_dom > B.cap_dom) { atomicOr(&cnt->error, ERR_DOM_CAP); cnt->want_dom = cnt->n_dom; }
+        }
+        return;
+    }
+    const DomainDev *D = S.dom;
+    const int n = cnt->n_total, gnx = cnt->gnx, gny = cnt->gny, cap = S.cap_floes;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const double2 me0 = B.cell_circ[2 * t], me1 = B.cell_circ[2 * t + 1];
+        const int i = (int)__double_as_longlong(me1.y);
+        const double xi = me0.x, yi = me0.y, ri = me1.x;
+        int up = 0, low = 0, ub = 0, lb = 0, db = 0;
+        bool research = true;
+        if (WRITE) {
+            ub = B.up_off[i];
+            lb = B.low_off[i];
+            db = B.dom_off[i];
+            const int tot = (B.up_off[i + 1] - ub) + (B.low_off[i + 1] - lb);
+            if (tot <= NB_K) {
+                research = false;
+                for (int k = 0; k < tot; ++k) {
+                    const int j = B.nb_scratch[(size_t)k * cap + t];
+                    if (j > i) B.pair_j[ub + up++] = j;
+                    else B.low_pair[lb + low++] = j;
+                }
+            }
+        }
+        if (research) {
+            const int c = B.cell_of[i], ix = c % gnx, iy = c / gnx;
+            const int x_lo = max(ix - 1, 0), x_hi = min(ix + 1, gnx - 1);
+            int found = 0;
+            for (int yy = max(iy - 1, 0); yy <= min(iy + 1, gny - 1); ++yy) {
+                for (int k = B.cell_start[yy * gnx + x_lo], ke = B.cell_start[yy * gnx + x_hi + 1]; k < ke; ++k) {
+                    if (k == t) continue;
+                    const double2 o0 = B.cell_circ[2 * k], o1 = B.cell_circ[2 * k + 1];
+                    if (!potential_interaction(xi, yi, ri, o0.x, o0.y, o1.x)) continue;
+                    const int j = (int)__double_as_longlong(o1.y);
+                    if (!WRITE && found < NB_K) B.nb_scratch[(size_t)found * cap + t] = j;
+                    found++;
+                    if (j > i) {
+                        if (WRITE) B.pair_j[ub + up] = j;
+                        up++;
+                    } else {
+                        if (WRITE) B.low_pair[lb + low] = j;
+                        low++;
+                    }
+                }
+            }
+        }
+        const int wm = wall_mask(D, xi, yi, ri);
+        int dc = 0, checks = __popc(wm);
+        for (int wl = 0; wl < 4; ++wl)
+            if ((wm >> wl) & 1) {
+                if (D->kind[wl] != SZ_BOUNDARY_PERIODIC) {  // collisions.jl:459-468: periodic walls do nothing
+                    if (WRITE) {
+                        B.dom_floe[db + dc] = i;
+                        B.dom_elem[db + dc] = wl;
+                    }
+                    dc++;
+                }
+            }
+        for (int k = 0; k < D->n_topo; ++k)
+            if (potential_interaction(S.topo_cx[k], S.topo_cy[k], S.topo_rmax[k], xi, yi, ri)) {  // :650
+                if (WRITE) {
+                    B.dom_floe[db + dc] = i;
+                    B.dom_elem[db + dc] = 4 + k;
+                }
+                dc++;
+                checks++;
+            }
+        if (!WRITE) {
+            B.up_count[i] = up;
+            B.low_count[i] = low;
+            B.dom_count[i] = dc;
+            if (checks) atomicAdd(&cnt->n_domchecks, checks);
+        } else {
+            // ascending j (own pairs) and ascending i (mirrored rows): the reference's loop order
+            for (int a = 1; a < up; ++a) {
+                int v = B.pair_j[ub + a], b = a - 1;
+                while (b >= 0 && B.pair_j[ub + b] > v) {
+                    B.pair_j[ub + b + 1] = B.pair_j[ub + b];
+                    --b;
+                }
+                B.pair_j[ub + b + 1] = v;
+            }
+            for (int a = 0; a < up; ++a) B.pair_i[ub + a] = i;
+            for (int a = 1; a < low; ++a) {
+                int v = B.low_pair[lb + a], b = a - 1;
+                while (b >= 0 && B.low_pair[lb + b] > v) {
+                    B.low_pair[lb + b + 1] = B.low_pair[lb + b];
+                    --b;
+                }
+                B.low_pair[lb + b + 1] = v;
+            }
+        }
+    }
+}
+
+// k_low_link (blocks [0, nb_link)) and k_filter (the rest) in one launch: both only read the sorted own-pair lists
+__global__ void k_link_filter(Store S, StepBuf B, int nb_link) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    if ((int)blockIdx.x < nb_link) {
+        const int n = cnt->n_total;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nb_link * blockDim.x)
+            for (int t = B.low_off[j], te = B.low_off[j + 1]; t < te; ++t) B.low_pair[t] = find_pair(B, B.low_pair[t], j);
+        return;
+    }
+    const int np = cnt->n_cand, nb = gridDim.x - nb_link;
+    int nkept = 0;
+    for (int p = (blockIdx.x - nb_link) * blockDim.x + threadIdx.x; p < np; p += nb * blockDim.x) {
+        int i = B.pair_i[p], j = B.pair_j[p];
+        long long idi = S.id[i], idj = S.id[j];
+        unsigned char keep = 0;
+        if (idi != idj) {
+            int ri = S.parent[i] >= 0 ? S.parent[i] : i, rj = S.parent[j] >= 0 ? S.parent[j] : j;
+            int ngi = S.nghost[ri], ngj = S.nghost[rj];
+            if (ngi == 0 && ngj == 0) keep = 1;
+            else {
+                int pmin = p;
+                for (int a = -1; a < ngi; ++a) {
+                    int fa = a < 0 ? ri : S.ghost_slot[ri * SZ_MAX_GHOSTS + a];
+                    for (int b = -1; b < ngj; ++b) {
+                        int fb = b < 0 ? rj : S.ghost_slot[rj * SZ_MAX_GHOSTS + b];
+                        int q = find_pair(B, min(fa, fb), max(fa, fb));
+                        if (q >= 0 && q < pmin) pmin = q;
+                    }
+                }
+                int ci = B.pair_i[pmin], cj = B.pair_j[pmin];
+                long long g1, g2, G1, G2;
+                if (idi > idj) { g1 = S.ghost_id[i]; g2 = S.ghost_id[j]; }
+                else { g1 = S.ghost_id[j]; g2 = S.ghost_id[i]; }
+                if (S.id[ci] > S.id[cj]) { G1 = S.ghost_id[ci]; G2 = S.ghost_id[cj]; }
+                else { G1 = S.ghost_id[cj]; G2 = S.ghost_id[ci]; }
+                bool ma = g1 == G1, mb = g2 == G2;
+                keep = (ma && mb) || (ma != mb);
+            }
+        }
+        B.keep[p] = keep;
+        nkept += keep;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nkept += __shfl_xor_sync(FULLMASK, nkept, o);
+    if (lane_id() == 0 && nkept) atomicAdd(&cnt->n_kept, nkept);
+}
+
+// k_pool_check + k_status + k_row_count
+__global__ void k_status_rowcount(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (cnt->n_pool > B.cap_pool) cnt->want_pool = cnt->n_pool;
+        if (cnt->n_fuse > B.cap_fuse) cnt->want_fuse = cnt->n_fuse;
+    }
+    if (cnt->error) return;
+    int n = cnt->n_total;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int s = S.status[i], c = 0;
+        for (int p = B.up_off[i], pe = B.up_off[i + 1]; p < pe; ++p)
+            if (B.keep[p]) {
+                if (B.item_flags[p] & IT_FUSE) s = SZ_STATUS_FUSE;
+                c += B.item_nrows[p];
+            }
+        for (int q = B.dom_off[i], qe = B.dom_off[i + 1]; q < qe; ++q) {
+            if (B.item_flags[B.cap_pairs + q] & IT_REMOVE) s = SZ_STATUS_REMOVE;
+            c += B.item_nrows[B.cap_pairs + q];
+        }
+        for (int t = B.low_off[i], te = B.low_off[i + 1]; t < te; ++t) {
+            int p = B.low_pair[t];
+            if (B.keep[p]) c += B.item_nrows[p];
+        }
+        S.status[i] = s;
+        B.row_pre[i] = c;
+    }
+}
+
+// k_row_check + k_row_write + k_update_boundaries
+__global__ void k_row_write2(Store S, StepBuf B, Params P) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    if (cnt->n_rows > B.cap_rows) {  // every thread backs off, one reports
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicOr(&cnt->error, ERR_ROW_CAP);
+            cnt->want_rows = cnt->n_rows;
+        }
+        return;
+    }
+    int n = cnt->n_total;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+        double *dst = B.rows + (size_t)B.row_off[f] * NCOL;
+        const int par = S.parent[f];
+        const bool sums = f < S.n_init;
+        const double cx = S.cx[f], cy = S.cy[f];
+        RowAcc acc = {S.overarea[f], 0.0, 0.0, 0.0};
+        int nr;
+        if (f >= S.n_init && par >= 0) {
+            nr = emit_base_rows(S, B, f, dst, cx - S.cx[par], cy - S.cy[par], true, sums, cx, cy, acc);
+        } else {
+            nr = emit_base_rows(S, B, f, dst, 0.0, 0.0, false, sums, cx, cy, acc);
+        }
+        if (sums) {
+            for (int g = 0, ng = S.nghost[f]; g < ng; ++g) {
+                int gi = S.ghost_slot[f * SZ_MAX_GHOSTS + g];
+                nr += emit_base_rows(S, B, gi, dst + (size_t)nr * NCOL, S.cx[gi] - cx, S.cy[gi] - cy, true, sums, cx, cy, acc);
+            }
+        }
+        S.overarea[f] = acc.oa;
+        if (sums) {
+            S.cfx[f] += acc.sx;
+            S.cfy[f] += acc.sy;
+            S.ctrq[f] += acc.st;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // update_boundaries!, collisions.jl:565-571
+        DomainDev *D = S.dom;
+        for (int wl = 0; wl < 4; ++wl) {
+            if (D->kind[wl] != SZ_BOUNDARY_MOVING) continue;
+            if (wl < 2) {
+                double d = D->wv[wl] * P.cfg.dt;
+                D->rect[wl][2] += d;
+                D->rect[wl][3] += d;
+                D->val[wl] += d;
+            } else {
+                double d = D->wu[wl] * P.cfg.dt;
+                D->rect[wl][0] += d;
+                D->rect[wl][1] += d;
+                D->val[wl] += d;
+            }
+        }
+    }
+}
+
+static void collisions_v2(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_hint, int pairs_hint,
+                          cudaEvent_t *ev, const cudaEvent_t *waits) {
+    cudaStream_t st = L.stream;
+    const int gf = grid_for(L, n_hint, TPB);
+    k_bbox2<<<gf, TPB, 0, st>>>(S);
+    k_grid_zero<<<grid_for(L, B.cap_cells, TPB), TPB, 0, st>>>(S, B);
+    k_cell_count2<<<gf, TPB, 0, st>>>(S, B);
+    {
+        const int *in[1] = {B.cell_count};
+        int *out[1] = {B.cell_start}, *tot[1] = {nullptr};
+        scan_lb(L, S, B, 0, 1, in, out, tot, &S.cnt->n_cells, 0, B.cap_cells);
+    }
+    k_cell_fill<<<gf, TPB, 0, st>>>(S, B);
+    k_neighbours2<false><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
+    {
+        const int *in[3] = {B.up_count, B.low_count, B.dom_count};
+        int *out[3] = {B.up_off, B.low_off, B.dom_off}, *tot[3] = {&S.cnt->n_cand, nullptr, &S.cnt->n_dom};
+        scan_lb(L, S, B, 1, 3, in, out, tot, &S.cnt->n_total, 0, S.cap_floes);
+    }
+    k_neighbours2<true><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
+    const int gp = grid_for(L, pairs_hint, TPB);
+    k_link_filter<<<gf + gp, TPB, 0, st>>>(S, B, gf);
+    if (ev) sz_record(L, ev[0], st);
+    if (waits) cudaStreamWaitEvent(st, waits[0], 0);  // sz_step_host: rings and height have landed
+    const int maxv_s = 32, maxx_s = 16, wpb = 4;
+    int gi = grid_for(L, (long long)pairs_hint + n_hint / 8 + 64, 256);
+    k_item_count<<<gi, 256, 0, st>>>(S, B);
+    k_class_scan<<<1, 32, 0, st>>>(S, B);
+    k_item_scatter<<<gi, 256, 0, st>>>(S, B);
+    k_narrow_ab<0><<<3 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, B, P);
+    k_narrow_ab<1><<<3 * L.sms, TN_NT, TN_SMEM_B, st>>>(S, B, P);
+    k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
+    k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
+    if (ev) sz_record(L, ev[1], st);
+    if (waits) cudaStreamWaitEvent(st, waits[1], 0);  // sz_step_host: everything else (overarea is accumulated by k_row_write)
+    k_status_rowcount<<<gf, TPB, 0, st>>>(S, B);
+    k_fuse_propagate<<<1, 1024, 0, st>>>(S, B);
+    k_row_total<<<gf, TPB, 0, st>>>(S, B);
+    {
+        const int *in[1] = {B.row_count};
+        int *out[1] = {B.row_off}, *tot[1] = {&S.cnt->n_rows};
+        scan_lb(L, S, B, 2, 1, in, out, tot, &S.cnt->n_total, 0, S.cap_floes);
+    }
+    k_row_write2<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B, P);
+    if (ev) sz_record(L, ev[2], st);
+    g_launch_count += 18;  // + the three look-back scans counted in scan_lb
+}
+
 void szk_collisions(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_hint, int pairs_hint,
                     cudaEvent_t *ev, const cudaEvent_t *waits) {
+    if (L.chain_v2) {
+        collisions_v2(L, S, B, P, n_hint, pairs_hint, ev, waits);
+        return;
+    }
     cudaStream_t st = L.stream;
     int gf = grid_for(L, n_hint, TPB);
     k_step_reset<<<gf, TPB, 0, st>>>(S);
