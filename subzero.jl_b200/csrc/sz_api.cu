@@ -95,6 +95,8 @@ struct sz_handle {
     int gkey_coupling, gkey_floes, gkey_pairs, graph_launches;
     bool graph_off;
     int graph_max_floes;
+    double2 *mc_spare;              // second Monte-Carlo array of a slab rank (rebuilds gather into it and swap)
+    long long mc_spare_cap;
     unsigned long long tables_gen;  // finish_host_tables: the offset tables were last written for this floe list ...
     const void *tables_ptr[3];      // ... into these caller arrays
     long long tables_mid[2];
@@ -194,12 +196,13 @@ static void register_arrays(sz_handle *h) {
     add((void **)&S.ghost_slot, SZ_MAX_GHOSTS * sizeof(int));
     add((void **)&S.warn, sizeof(uint32_t));
     add((void **)&S.cpl_remove, sizeof(unsigned char));
+    add((void **)&S.mc_r, sizeof(double));
     add((void **)&S.vstart, sizeof(int));
     add((void **)&S.vcount, sizeof(int));
     void **scr[] = {(void **)&B.cell_of, (void **)&B.cell_items, (void **)&B.up_count, (void **)&B.up_off,
                     (void **)&B.low_count, (void **)&B.low_off, (void **)&B.dom_count, (void **)&B.dom_off,
                     (void **)&B.row_pre, (void **)&B.row_count, (void **)&B.row_off, (void **)&B.g_flag,
-                    (void **)&B.g_cnt, (void **)&B.g_off, (void **)&B.g_vcnt, (void **)&B.g_voff};
+                    (void **)&B.g_cnt, (void **)&B.g_off, (void **)&B.g_vcnt, (void **)&B.g_voff, (void **)&B.g_list};
     for (void **p : scr) h->floe_scratch.push_back(p);
 }
 
@@ -237,10 +240,10 @@ static int32_t grow_floes(sz_handle *h, int new_cap, int keep) {
     h->B.cap_cells = cells;
     dfree(h->B.lb_desc); dfree(h->B.lb_ticket); dfree(h->B.nb_scratch);
     h->B.lb_stride = cells / 4096 + 8;  // tiles of the longest scan (cells >= floes)
-    CK(dalloc(&h->B.lb_desc, (size_t)9 * h->B.lb_stride));
+    CK(dalloc(&h->B.lb_desc, (size_t)12 * h->B.lb_stride));  // 4 scan slots (cells, neighbour counts, rows, ghosts) x 3 arrays
     CK(dalloc(&h->B.lb_ticket, 16));
     CK(dalloc(&h->B.nb_scratch, (size_t)20 * new_cap));  // NB_K rows
-    CK(cudaMemset(h->B.lb_desc, 0, sizeof(unsigned long long) * 9 * h->B.lb_stride));
+    CK(cudaMemset(h->B.lb_desc, 0, sizeof(unsigned long long) * 12 * h->B.lb_stride));
     CK(cudaMemset(h->B.lb_ticket, 0, sizeof(int) * 16));
     return SZ_OK;
 }
@@ -387,6 +390,8 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->L.capturing = false;
     h->L.no_phase_events = getenv("SZ_GRAPH_NO_EVENTS") != nullptr;
     h->L.chain_v2 = getenv("SZ_CHAIN_V1") == nullptr;
+    h->mc_spare = nullptr;
+    h->mc_spare_cap = 0;
     h->tables_gen = 0;
     h->tables_ptr[0] = h->tables_ptr[1] = h->tables_ptr[2] = nullptr;
     h->graph_max_floes = getenv("SZ_GRAPH_MAX_FLOES") ? atoi(getenv("SZ_GRAPH_MAX_FLOES")) : SZ_GRAPH_MAX_FLOES;
@@ -425,7 +430,7 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(B.lb_desc); dfree(B.lb_ticket); dfree(B.nb_scratch);
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.order_cls); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
-    dfree(h->d_hl_idx); dfree(h->d_hl_voff);
+    dfree(h->d_hl_idx); dfree(h->d_hl_voff); dfree(h->mc_spare);
     for (auto &m : h->slab.ipc_open) cudaIpcCloseMemHandle(m.ptr);
     h->slab.ipc_open.clear();
     for (unsigned char *p : h->slab.retired) cudaFree(p);
@@ -712,22 +717,36 @@ static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64
     int want_cap = h->cfg.floe_capacity > 0 ? (int)h->cfg.floe_capacity
                                             : n + std::max(64, std::min(3 * n_init, n_init / 2 + 4096));
     if (want_cap < n) want_cap = n;
-    if (want_cap > h->S.cap_floes || !h->S.cx) {
+    // Hysteresis: a list that grew by a few floes (every slab rebuild changes the halo a little) keeps its buffers as long
+    // as half of the ghost headroom is left — re-allocating ~60 arrays costs tens of milliseconds (and far more while
+    // peers have this device's memory mapped); an overflowing ghost pass still grows them on demand.
+    const int min_cap = h->cfg.floe_capacity > 0 ? want_cap : n + (want_cap - n) / 2;
+    if (min_cap > h->S.cap_floes || !h->S.cx) {
         int32_t rc = grow_floes(h, want_cap, 0);
         if (rc) return rc;
     }
-    long long want_v = V + (long long)(n_init > 0 ? (V / std::max(n, 1) + 1) : 0) * (h->S.cap_floes - n) + 64;
-    if (want_v > h->S.cap_verts || !h->S.verts) {
-        int32_t rc = grow_verts(h, (int)std::min<long long>(want_v, 1ll << 30), 0);
+    const long long per_floe = n_init > 0 ? (V / std::max(n, 1) + 1) : 0;
+    long long want_v = V + per_floe * (h->S.cap_floes - n) + 64, min_v = V + per_floe * ((want_cap - n) / 2) + 64;
+    if (min_v > h->S.cap_verts || !h->S.verts) {
+        int32_t rc = grow_verts(h, (int)std::min<long long>(std::max(want_v, min_v), 1ll << 30), 0);
         if (rc) return rc;
     }
     Store &S = h->S;
     double2 *old_mc = nullptr;
-    if (mc_src) {  // keep the resident points until the new array is gathered
+    long long old_cap = 0;
+    if (mc_src) {  // gather into the spare array, then swap: no allocation per rebuild once both have their headroom
         old_mc = S.mc;
-        S.mc = nullptr;
-        CK(dalloc(&S.mc, (size_t)M));
-        S.cap_mc = M;
+        old_cap = S.cap_mc;
+        if (h->mc_spare_cap < M || !h->mc_spare) {
+            dfree(h->mc_spare);
+            const long long cap = M + M / 16 + 4096;
+            CK(dalloc(&h->mc_spare, (size_t)cap));
+            h->mc_spare_cap = cap;
+        }
+        S.mc = h->mc_spare;
+        S.cap_mc = h->mc_spare_cap;
+        h->mc_spare = nullptr;
+        h->mc_spare_cap = 0;
         h->gen++;
     } else if (M > S.cap_mc || !S.mc) {
         dfree(S.mc);
@@ -795,7 +814,8 @@ static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         cudaFree(tx); cudaFree(ty); cudaFree(extra); cudaFree(dsrc);
-        if (old_mc) cudaFree(old_mc);
+        h->mc_spare = old_mc;  // the next rebuild gathers into it
+        h->mc_spare_cap = old_cap;
     } else if (Mi > 0) {
         double *tx = nullptr, *ty = nullptr;
         CK(dalloc(&tx, (size_t)Mi)); CK(dalloc(&ty, (size_t)Mi));
@@ -807,6 +827,7 @@ static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64
     }
     CK(cudaMemsetAsync(B.row_off, 0, sizeof(int) * ((size_t)S.cap_floes + 2), st));
     S.n_init = n_init;
+    szk_mc_radius(h->L, S);
     szk_set_counts(h->L, S, n, (int)V);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
@@ -2271,6 +2292,7 @@ extern "C" int32_t sz_generate_subfloe_points(sz_handle *h, const sz_points_gene
         for (int k = 0; k < n; ++k) hstatus[k] = hstatus[k] == SZ_STATUS_REMOVE ? 1 : 0;
         PCK(cudaMemcpy(d_status, hstatus.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
         szk_apply_remove_flags(h->L, S, d_status, n);
+        szk_mc_radius(h->L, S);
         PCK(cudaStreamSynchronize(st));
         h->h_mc_off = mo;
         h->n_mc = M;

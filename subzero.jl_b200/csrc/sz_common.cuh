@@ -64,6 +64,7 @@ struct Counters {
     int n_mid;     // work items the thread-per-item kernel handed to the warp-per-item kernel
     int n_crec;    // records of the floe -> cell registry (coupling)
     int n_spill;   // entries claimed in the registry's spill table
+    int n_gflag;   // floes on the compact list of a ghost pass
     int n_cbig;    // ... whose ring needs the warp clip kernel
     int n_ccells;  // number of grid cells (scan length of the registry sort)
     int n_order;   // work items of the thread-per-item kernels (class-sorted)
@@ -113,6 +114,8 @@ struct Store {
     int *ghost_slot;  // [cap][SZ_MAX_GHOSTS]
     uint32_t *warn;
     unsigned char *cpl_remove;  // coupling found no in-bounds Monte-Carlo point (coupling.jl:1507)
+    double *mc_r;               // largest |p| over the floe's sub-floe points (the sub-grid generator's shifted edge points may
+                                // lie outside the ring): what the coupling's "strictly inside the grid" fast path must clear
     // CSR geometry
     int *vstart, *vcount;  // ring of floe f = verts[vstart[f] .. vstart[f]+vcount[f]), closed
     double2 *verts;
@@ -168,6 +171,7 @@ struct StepBuf {
     int2 *fuse_pairs;                    // [cap_fuse]
     // ghost scratch
     int *g_flag, *g_cnt, *g_off, *g_vcnt, *g_voff;  // [cap_floes+1]
+    int *g_list;                                    // [cap_floes+1] floes flagged by the current ghost pass (unordered)
     // scan scratch
     int *scan_block;
     // single-pass scans (look-back descriptors / tickets of the step's three scans) and the parked neighbour indices
@@ -258,6 +262,7 @@ void szk_mc_regather(const Launch &L, double2 *dst, const long long *dst_off, co
 void szk_pack_fields(const Launch &L, const Store &S, int n_nodes);
 void szk_coupling(const Launch &L, const Store &S, const Params &P);
 void szk_apply_coupling_tags(const Launch &L, const Store &S);
+void szk_mc_radius(const Launch &L, const Store &S);  // S.mc_r from the resident points (after every change of them)
 void szk_apply_remove_flags(const Launch &L, const Store &S, const int *flags, int n);  // status.tag = remove where flags[i] != 0
 void szk_coupling_reg(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P);
 void szk_cells_final(const Launch &L, const Store &S, const CouplingBuf &CB, const Params &P);

@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_lb(ScanLB a, const int *len_ptr
     }
 }
 // slot: which of the step's scans (each has its own descriptors): 0 cells, 1 neighbour counts (3 arrays), 2 rows
-#define LB_SLOTS 3
+#define LB_SLOTS 3       // zeroed by k_grid_zero
+#define LB_SLOT_GHOST 3  // zeroed by k_ghost_flag2
 static void scan_lb(const Launch &L, const Store &S, const StepBuf &B, int slot, int narr, const int *const *in, int *const *out,
                     int *const *total_out, const int *len_ptr, int len_add, int max_len) {
     ScanLB a;
@@ -344,11 +345,15 @@ __global__ void k_set_counts(Counters *cnt, int n_total, int n_verts) {
     cnt->error = 0;
     cnt->bb[0] = cnt->bb[1] = ~0ull;  // the fused chain only accumulates into the box (k_bbox2) and resets it behind its last reader
     cnt->bb[2] = cnt->bb[3] = cnt->bb[4] = 0ull;
+    cnt->n_gflag = 0;
 }
 void szk_set_counts(const Launch &L, const Store &S, int n_total, int n_verts) {
     k_set_counts<<<1, 1, 0, L.stream>>>(S.cnt, n_total, n_verts);
 }
-__global__ void k_clear_error(Counters *cnt) { cnt->error = 0; }
+__global__ void k_clear_error(Counters *cnt) {
+    cnt->error = 0;
+    cnt->n_gflag = 0;  // a ghost pass that was abandoned half-way leaves its list behind
+}
 void szk_clear_error(const Launch &L, const Store &S) { k_clear_error<<<1, 1, 0, L.stream>>>(S.cnt); }
 
 // ---- K8: ghosts (collisions.jl:881-1174) -------------------------------------------------------------
@@ -553,6 +558,192 @@ __global__ void k_ghost_commit(Store S, StepBuf B) {
     cnt->n_total = n0 + B.g_off[n0];
 }
 
+// ---- the ghost pass on a COMPACT list of the flagged floes (v2) -------------------------------------------------------
+// Only the floes near a periodic wall take part (a few thousand of 250 k): the flag kernel appends them to a list
+// (order irrelevant: every result is written at the floe's own index, the append positions come from prefix sums over
+// the floe index as before), the clip and write kernels walk that list instead of striding over every floe, and the two
+// prefix sums are one look-back launch.  6 launches per axis instead of 12.
+__global__ void k_ghost_flag2(Store S, StepBuf B, GhostAxis A) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const DomainDev *D = S.dom;
+    const int n0 = cnt->n_total;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int k = t0; k < 3 * B.lb_stride; k += nt) B.lb_desc[(size_t)LB_SLOT_GHOST * 3 * B.lb_stride + k] = 0ull;
+    if (t0 < 3) B.lb_ticket[LB_SLOT_GHOST * 3 + t0] = 0;
+    for (int i = t0; i < n0; i += nt) {
+        int flag = 0;
+        if (S.status[i] == SZ_STATUS_ACTIVE && S.ghost_id[i] == 0) {
+            double c = A.axis == 0 ? S.cx[i] : S.cy[i], r = S.rmax[i];
+            if (c - r < D->val[A.wmin]) flag = 1;
+            else if (c + r > D->val[A.wmax]) flag = 2;
+        }
+        B.g_flag[i] = flag;
+        B.g_cnt[i] = 0;
+        B.g_vcnt[i] = 0;
+        if (flag) B.g_list[atomicAdd(&cnt->n_gflag, 1)] = i;
+    }
+}
+
+__global__ void k_ghost_clip2(Store S, StepBuf B, GhostAxis A, int maxv, int maxx, int large) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    Ws w = ws_carve(smem + (size_t)wib * ws_bytes(maxv, maxx), maxv, maxx);
+    const int nl = cnt->n_gflag;
+    for (int e = blockIdx.x * wpb + wib; e < nl; e += gridDim.x * wpb) {
+        const int i = B.g_list[e];
+        int flag = B.g_flag[i];
+        if (flag == 0) continue;
+        if (large ? !(flag & 4) : (flag & 4)) continue;
+        int side = flag & 3;
+        int npp = S.vcount[i];
+        bool defer = npp > w.maxv;
+        int nreg = 0, status = CLIP_OK;
+        if (!defer) {
+            const double2 *gP = S.verts + S.vstart[i];
+            for (int k = lane; k < npp; k += 32) w.P[k] = gP[k];
+            stage_wall_ring(w.Q, S.dom, side == 1 ? A.wmin : A.wmax, lane);
+            __syncwarp();
+            nreg = warp_clip(w, w.P, npp, w.Q, 5, w.R1, w.rs1, w.re1, status);
+            defer = status == CLIP_OVERFLOW;
+        }
+        if (lane == 0) {
+            if (defer) {
+                if (large) atomicOr(&cnt->error, ERR_POLY_TOO_LARGE);
+                else B.g_flag[i] = side | 4;
+            } else if (nreg > 0) {
+                int ng = S.nghost[i], vc = npp;
+                for (int k = 0; k < ng; ++k) vc += S.vcount[S.ghost_slot[i * SZ_MAX_GHOSTS + k]];
+                B.g_flag[i] = side;
+                B.g_cnt[i] = ng + 1;
+                B.g_vcnt[i] = vc;
+                if (2 * ng + 1 > SZ_MAX_GHOSTS) atomicOr(&cnt->error, ERR_GHOST_SLOTS);
+            } else {
+                B.g_flag[i] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// k_ghost_check + k_ghost_write over the list
+__global__ void k_ghost_write2(Store S, StepBuf B, GhostAxis A) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const DomainDev *D = S.dom;
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const int n0 = cnt->n_total, v0 = cnt->n_verts;
+    {
+        const int add = B.g_off[n0], vadd = B.g_voff[n0];
+        if (n0 + add > S.cap_floes || v0 + vadd > S.cap_verts) {  // every thread backs off, one reports
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (n0 + add > S.cap_floes) { atomicOr(&cnt->error, ERR_GHOST_CAP); cnt->want_floes = n0 + add; }
+                if (v0 + vadd > S.cap_verts) { atomicOr(&cnt->error, ERR_VERT_CAP); cnt->want_verts = v0 + vadd; }
+            }
+            return;
+        }
+    }
+    const double Lp = D->val[A.wmax] - D->val[A.wmin];
+    const int nl = cnt->n_gflag;
+    for (int e = blockIdx.x * wpb + wib; e < nl; e += gridDim.x * wpb) {
+        const int i = B.g_list[e];
+        int cntg = B.g_cnt[i];
+        if (cntg == 0) continue;
+        int side = B.g_flag[i] & 3;
+        double t = side == 1 ? Lp : -Lp;
+        double tx = A.axis == 0 ? t : 0.0, ty = A.axis == 0 ? 0.0 : t;
+        int base = n0 + B.g_off[i], vbase = v0 + B.g_voff[i];
+        int ng = S.nghost[i];
+        for (int k = 0; k < cntg; ++k) {
+            int src = k < ng ? S.ghost_slot[i * SZ_MAX_GHOSTS + k] : i, dst = base + k;
+            int nv = S.vcount[src], vs = S.vstart[src];
+            if (lane == 0) {
+                copy_floe_scalars(S, src, dst);
+                S.cx[dst] += tx;  // _translate_floe!, floe_utils.jl:66-72
+                S.cy[dst] += ty;
+                S.ghost_id[dst] = (long long)((k + 1) + ng);  // collisions.jl:1036-1038
+                S.parent[dst] = i;
+                S.vstart[dst] = vbase;
+                S.vcount[dst] = nv;
+            }
+            for (int q = lane; q < nv; q += 32) {
+                double2 p = S.verts[vs + q];
+                p.x += tx;
+                p.y += ty;
+                S.verts[vbase + q] = p;
+            }
+            vbase += nv;
+        }
+        __syncwarp();
+        // parent / last-ghost swap, collisions.jl:943-949
+        double c = A.axis == 0 ? S.cx[i] : S.cy[i];
+        double sw = 0.0;
+        if (c < D->val[A.wmin]) sw = Lp;
+        else if (D->val[A.wmax] < c) sw = -Lp;
+        __syncwarp();
+        if (sw != 0.0) {
+            double sx = A.axis == 0 ? sw : 0.0, sy = A.axis == 0 ? 0.0 : sw;
+            int last = base + cntg - 1;
+            int vs = S.vstart[i], nv = S.vcount[i];
+            for (int q = lane; q < nv; q += 32) {
+                double2 p = S.verts[vs + q];
+                p.x += sx;
+                p.y += sy;
+                S.verts[vs + q] = p;
+            }
+            int vl = v0 + B.g_voff[i] + B.g_vcnt[i] - nv;  // the parent's copy is the last ring written
+            for (int q = lane; q < nv; q += 32) {
+                double2 p = S.verts[vl + q];
+                p.x += -sx;
+                p.y += -sy;
+                S.verts[vl + q] = p;
+            }
+            if (lane == 0) {
+                S.cx[i] += sx;
+                S.cy[i] += sy;
+                S.cx[last] += -sx;
+                S.cy[last] += -sy;
+            }
+        }
+        if (lane == 0) {
+            for (int k = 0; k < cntg; ++k) S.ghost_slot[i * SZ_MAX_GHOSTS + ng + k] = base + k;
+            S.nghost[i] = ng + cntg;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_ghost_commit2(Store S, StepBuf B) {
+    Counters *cnt = S.cnt;
+    cnt->n_gflag = 0;  // for the next pass, error or not
+    if (cnt->error) return;
+    int n0 = cnt->n_total;
+    cnt->n_verts += B.g_voff[n0];
+    cnt->n_total = n0 + B.g_off[n0];
+}
+
+static void ghost_pass_v2(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_hint) {
+    GhostAxis A;
+    A.axis = axis;
+    A.wmax = axis == 0 ? 2 : 0;
+    A.wmin = axis == 0 ? 3 : 1;
+    const int maxv_s = 32, maxx_s = 16, wpb = 4;
+    const int glist = grid_for(L, n_hint / 16 + 256, wpb);  // the list holds a small fraction of the floes; the loops stride anyway
+    k_ghost_flag2<<<grid_for(L, n_hint, TPB), TPB, 0, L.stream>>>(S, B, A);
+    k_ghost_clip2<<<glist, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), L.stream>>>(S, B, A, maxv_s, maxx_s, 0);
+    k_ghost_clip2<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), L.stream>>>(S, B, A, L.maxv_large, L.maxx_large, 1);
+    {
+        const int *in[2] = {B.g_cnt, B.g_vcnt};
+        int *out[2] = {B.g_off, B.g_voff}, *tot[2] = {nullptr, nullptr};
+        scan_lb(L, S, B, LB_SLOT_GHOST, 2, in, out, tot, &S.cnt->n_total, 0, S.cap_floes);
+    }
+    k_ghost_write2<<<grid_for(L, n_hint / 16 + 256, 8), 256, 0, L.stream>>>(S, B, A);
+    k_ghost_commit2<<<1, 1, 0, L.stream>>>(S, B);
+    g_launch_count += 5;
+}
+
 static void ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_hint) {
     GhostAxis A;
     A.axis = axis;
@@ -573,7 +764,8 @@ static void ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int ax
 }
 
 void szk_ghost_pass(const Launch &L, const Store &S, const StepBuf &B, int axis, int n_hint) {
-    ghost_pass(L, S, B, axis, n_hint);
+    if (L.chain_v2) ghost_pass_v2(L, S, B, axis, n_hint);
+    else ghost_pass(L, S, B, axis, n_hint);
 }
 
 // simulation.jl:138-144
@@ -1928,6 +2120,7 @@ int szk_configure(const Launch &L) {
     size_t lb = ws_bytes(L.maxv_large, L.maxx_large);
     if (cudaFuncSetAttribute(k_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_ghost_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_ghost_clip2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_debug_clip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_narrow_ab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_A) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_crec_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_C) != cudaSuccess) return -1;

@@ -4,6 +4,7 @@
 // bit: their parity bar is 1e-9 relative (BASELINE.json north_star).  They are therefore compiled
 // with FMA contraction ON (unlike sz_kernels.cu) and use algebraic identities the tolerance covers.
 #include <cuda_pipeline.h>
+#include <stdlib.h>
 
 #include "sz_common.cuh"
 
@@ -65,7 +66,27 @@ __device__ __forceinline__ double cp_norm(double s) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
     r = r * (1.5 - (0.5 * s) * r * r);
-    return s > 0.0 ? s * r : 0.0;
+    return s > 2.2250738585072014e-308 ? s * r : 0.0;  // ftz: a denormal argument gives +inf, its norm is 0 to 1e-154
+}
+
+// largest distance of a floe's sub-floe points from its centroid (body frame): warp per floe
+__global__ void k_mc_radius(Store S) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < S.n_init; i += gridDim.x * wpb) {
+        double m = 0.0;
+        for (long long k = S.mc_off[i] + lane, e = S.mc_off[i + 1]; k < e; k += 32) {
+            const double2 p = S.mc[k];
+            m = fmax(m, p.x * p.x + p.y * p.y);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(FULLMASK, m, o));
+        if (lane == 0) S.mc_r[i] = sqrt(m);
+    }
+}
+void szk_mc_radius(const Launch &L, const Store &S) {
+    if (S.n_init <= 0) return;
+    long long blocks = ((long long)S.n_init + 7) / 8, cap = (long long)L.sms * 16;
+    k_mc_radius<<<(int)(blocks < cap ? blocks : cap), 256, 0, L.stream>>>(S);
 }
 
 // ATM / HFLX: false when the atmosphere / heat-flux fields are identically zero (sz_set_fields checks): the
@@ -204,8 +225,8 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
         const double mf = mass / ar * c.f;
         CpAcc acc = {0.0, 0.0, 0.0, 0.0, 0};
         long long k = m0 + lane;
-        // Monte-Carlo points lie inside the ring, i.e. within rmax of the centroid (a small margin covers rounding)
-        const double rm = S.rmax[i] * (1.0 + 1e-9) + 1e-6;
+        // sub-floe points lie within max(rmax, mc_r) of the centroid (a small margin covers rounding)
+        const double rm = fmax(S.rmax[i], S.mc_r[i]) * (1.0 + 1e-9) + 1e-6;
         const bool interior = cx - rm > c.x0 && cx + rm < c.xf && cy - rm > c.y0 && cy + rm < c.yf;
         const int nchunk = (int)((m1 - m0 + 127) >> 7);
         if (!have && nchunk > 0) {
@@ -272,6 +293,141 @@ __global__ void __launch_bounds__(128, 6) k_coupling(Store S, CpConst c) {
         }
     }
     __pipeline_wait_prior(0);
+}
+
+// ---- the same kernel with the Monte-Carlo points brought in by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) ----
+// A floe's points are ONE contiguous block of the CSR array — the one perfectly contiguous stream of the step — so a
+// chunk of 128 points (2 KB) is a single 1-D bulk copy global -> shared issued by one lane and completed on an
+// mbarrier (complete_tx::bytes); the other 31 lanes issue nothing for the load at all (the LDGSTS version spends four
+// predicated 16-byte copies + their address arithmetic per lane and chunk in a kernel that is bound by its issue slots).
+// Two stages per warp, each with its own barrier; the copy of the next chunk — of this floe or, behind its last
+// chunk, of the warp's next floe — is in flight while the current one is integrated.
+__device__ __forceinline__ unsigned cp_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_bulk_load(double2 *dst, const double2 *src, unsigned bytes, unsigned long long *bar) {
+    const unsigned d = cp_smem_u32(dst), b = cp_smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_bar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned b = cp_smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(b), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+template <bool ATM, bool HFLX>
+__global__ void __launch_bounds__(128, 6) k_coupling_bulk(Store S, CpConst c) {
+    Counters *cnt = S.cnt;
+    if (cnt->error) return;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const double *__restrict__ F = S.fields8;
+    const int n = S.n_init;
+    __shared__ __align__(128) double2 sbuf[2][4][128];  // [stage][warp][point]: 16 KB per block
+    __shared__ __align__(8) unsigned long long mbar[2][4];
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cp_smem_u32(&mbar[0][wib])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cp_smem_u32(&mbar[1][wib])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const int stride = gridDim.x * wpb;
+    int stage = 0;
+    unsigned ph0 = 0, ph1 = 0;  // phase parity of the two barriers
+    bool have = false;          // chunk 0 of the current floe is already in flight in `stage`
+    int i = blockIdx.x * wpb + wib;
+    long long m0 = 0, m1 = 0;
+    if (i < n) {
+        m0 = S.mc_off[i];
+        m1 = S.mc_off[i + 1];
+    }
+    for (; i < n; i += stride) {
+        const double a = S.alpha[i], cx = S.cx[i], cy = S.cy[i], u = S.u[i], v = S.v[i], xi = S.xi[i];
+        const double ar = S.area[i], mass = S.mass[i];
+        const int inext = i + stride;
+        long long m0n = 0, m1n = 0;
+        if (inext < n) {
+            m0n = S.mc_off[inext];
+            m1n = S.mc_off[inext + 1];
+        }
+        double sa, ca;
+        sincos(a, &sa, &ca);
+        const double mf = mass / ar * c.f;
+        CpAcc acc = {0.0, 0.0, 0.0, 0.0, 0};
+        long long k = m0;
+        const double rm = fmax(S.rmax[i], S.mc_r[i]) * (1.0 + 1e-9) + 1e-6;
+        const bool interior = cx - rm > c.x0 && cx + rm < c.xf && cy - rm > c.y0 && cy + rm < c.yf;
+        const int nchunk = (int)((m1 - m0 + 127) >> 7);
+        if (!have && nchunk > 0 && lane == 0) {
+            const long long cntp = m1 - k < 128 ? m1 - k : 128;
+            cp_bulk_load(&sbuf[stage][wib][0], S.mc + k, (unsigned)(cntp * 16), &mbar[stage][wib]);
+        }
+        have = false;
+        for (int cch = 0; cch < nchunk; ++cch, k += 128) {
+            const int nxt = stage ^ 1;
+            __syncwarp();  // every lane has consumed what the previous iteration read from stage `nxt`
+            if (cch + 1 < nchunk) {
+                if (lane == 0) {
+                    const long long rest = m1 - (k + 128), cntp = rest < 128 ? rest : 128;
+                    cp_bulk_load(&sbuf[nxt][wib][0], S.mc + k + 128, (unsigned)(cntp * 16), &mbar[nxt][wib]);
+                }
+            } else if (m1n > m0n) {  // behind the last chunk: the first chunk of the warp's next floe
+                if (lane == 0) {
+                    const long long rest = m1n - m0n, cntp = rest < 128 ? rest : 128;
+                    cp_bulk_load(&sbuf[nxt][wib][0], S.mc + m0n, (unsigned)(cntp * 16), &mbar[nxt][wib]);
+                }
+                have = true;
+            }
+            if (stage == 0) { cp_bar_wait(&mbar[0][wib], ph0); ph0 ^= 1u; }
+            else { cp_bar_wait(&mbar[1][wib], ph1); ph1 ^= 1u; }
+            const double2 *sb = &sbuf[stage][wib][lane];
+            if (interior && k + 128 <= m1) {
+                cp_point<false, ATM, HFLX, true>(c, F, sb[0], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, sb[32], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, sb[64], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+                cp_point<false, ATM, HFLX, true>(c, F, sb[96], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            } else if (interior) {
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j)
+                    if (k + lane + 32 * j < m1)
+                        cp_point<false, ATM, HFLX, true>(c, F, sb[32 * j], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            } else {  // floes at the edge of the grid (about 1 % of a large field): the general path, not unrolled
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j)
+                    if (k + lane + 32 * j < m1)
+                        cp_point<false, ATM, HFLX, false>(c, F, sb[32 * j], ca, sa, cx, cy, u, v, xi, mf, acc, nullptr);
+            }
+            stage = nxt;
+        }
+        m0 = m0n;
+        m1 = m1n;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            acc.tx += __shfl_xor_sync(FULLMASK, acc.tx, o);
+            acc.ty += __shfl_xor_sync(FULLMASK, acc.ty, o);
+            acc.trq += __shfl_xor_sync(FULLMASK, acc.trq, o);
+            acc.hf += __shfl_xor_sync(FULLMASK, acc.hf, o);
+            acc.n += __shfl_xor_sync(FULLMASK, acc.n, o);
+        }
+        if (lane == 0) {
+            if (acc.n == 0) {
+                S.cpl_remove[i] = 1;  // coupling.jl:1507-1508; applied to status.tag by k_apply_coupling_tags
+            } else {
+                S.cpl_remove[i] = 0;
+                double np_ = (double)acc.n;
+                double tot_x = np_ * (mf * v) + acc.tx, tot_y = -np_ * (mf * u) + acc.ty;  // Coriolis, :1522-1525
+                S.fxOA[i] = tot_x / np_ * ar;  // :1583-1586
+                S.fyOA[i] = tot_y / np_ * ar;
+                S.trqOA[i] = acc.trq / np_ * ar;
+                S.hflx[i] = acc.hf / np_;
+            }
+        }
+    }
 }
 
 // The same integration plus the floe -> cell registry (grid.floe_locations / ocean.scells): the points of a
@@ -522,10 +678,18 @@ void szk_coupling(const Launch &L, const Store &S, const Params &P) {
     long long cap = (long long)L.sms * (L.coupling_blocks_per_sm > 0 ? L.coupling_blocks_per_sm : 48);
     const int g = (int)(blocks < cap ? blocks : cap);
     const bool atm = P.atm_nonzero, hf = P.hflx_nonzero;
-    if (atm && hf) k_coupling<true, true><<<g, 128, 0, L.stream>>>(S, c);
-    else if (atm) k_coupling<true, false><<<g, 128, 0, L.stream>>>(S, c);
-    else if (hf) k_coupling<false, true><<<g, 128, 0, L.stream>>>(S, c);
-    else k_coupling<false, false><<<g, 128, 0, L.stream>>>(S, c);
+    static const bool ldgsts = getenv("SZ_COUPLING_LDGSTS") != nullptr;  // A/B: the cp.async (LDGSTS) ring of round 1
+    if (ldgsts) {
+        if (atm && hf) k_coupling<true, true><<<g, 128, 0, L.stream>>>(S, c);
+        else if (atm) k_coupling<true, false><<<g, 128, 0, L.stream>>>(S, c);
+        else if (hf) k_coupling<false, true><<<g, 128, 0, L.stream>>>(S, c);
+        else k_coupling<false, false><<<g, 128, 0, L.stream>>>(S, c);
+    } else {
+        if (atm && hf) k_coupling_bulk<true, true><<<g, 128, 0, L.stream>>>(S, c);
+        else if (atm) k_coupling_bulk<true, false><<<g, 128, 0, L.stream>>>(S, c);
+        else if (hf) k_coupling_bulk<false, true><<<g, 128, 0, L.stream>>>(S, c);
+        else k_coupling_bulk<false, false><<<g, 128, 0, L.stream>>>(S, c);
+    }
     szk_count_launches(1);
 }
 

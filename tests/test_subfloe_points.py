@@ -173,3 +173,26 @@ def test_points_cuda_equal_oracle_bit_for_bit(kind, product_lib, oracle_lib):
             assert np.array_equal(u, v), (kind, name, "subset")
         hg.close()
         ho.close()
+
+
+@pytest.mark.gpu
+def test_points_outside_the_ring_at_the_domain_edge(product_lib, oracle_lib):
+    """The sub-grid generator's shifted edge points may lie OUTSIDE the ring (the reference shifts x by a positive amount
+    whatever the edge's direction, coupling.jl:277-283), i.e. beyond rmax: for a floe next to a non-periodic domain edge
+    such a point is out of bounds and is dropped (coupling.jl:494-597).  The coupling kernel's "floe strictly inside the
+    grid" fast path must not be taken on rmax alone (round-1 advisor finding; found by this round's install test)."""
+    from parity_util import rel_err
+    f = synth.make_field(400, scale=0.98, walls="collision", npoints=30, cache=False)
+    hg, ho = synth.setup_handle(f, product_lib), synth.setup_handle(f, oracle_lib)
+    a = hg.generate_subfloe_points(capi.POINTS_SUB_GRID, delta_g=400.0, install=True)
+    b = ho.generate_subfloe_points(capi.POINTS_SUB_GRID, delta_g=400.0, install=True)
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    r = np.hypot(a[1], a[2])
+    rmax_of_point = np.repeat(f.floes.rmax, np.diff(a[0]))
+    assert (r > rmax_of_point * (1 + 1e-9)).any()  # the situation exists in this field
+    for h in (hg, ho):
+        h.step_coupling()
+    A, O = hg.download_floes(mc=False), ho.download_floes(mc=False)
+    for name in ("fxOA", "fyOA", "trqOA", "hflx_factor"):
+        assert rel_err(getattr(A, name), getattr(O, name)) < 1e-9, name
+    assert np.array_equal(A.status_tag, O.status_tag)
