@@ -514,3 +514,75 @@ def test_in_bounds_truth_tables(oracle_lib):  # :180-195; in_bounds(x, y, grid, 
         assert bool(fn(h.h, x[k], y[k], 1, 0)) == open_periodic[k]   # per_x = E-W periodic
         assert bool(fn(h.h, x[k], y[k], 0, 1)) == periodic_open[k]   # per_y = N-S periodic
         assert bool(fn(h.h, x[k], y[k], 1, 1))
+
+
+# ---- hand-derived known answers for what NO reference test reaches (round-1 verdict: "pin what is unpinned") -----------
+# The reference cannot run here (no Julia on the build image or on the GPU box: profiles/r2/r2a_julia_probe.txt), so these
+# cases are worked out by hand from the reference's formulas (collisions.jl:30-119,149-188,243-283) plus ONE stated
+# assumption each about GeometryOps 0.1.x, the un-vendored clipper.  They pin the oracle and the CUDA kernels on
+# configurations where a shared misreading would otherwise be invisible; the assumption is what remains unverified.
+COMB = [[[0.0, 2.7e4], [0.0, 3.5e4], [5e4, 3.5e4], [5e4, 2.7e4], [4e4, 2.7e4], [4e4, 3e4], [3e4, 3e4], [3e4, 2.7e4],
+         [2e4, 2.7e4], [2e4, 3e4], [1e4, 3e4], [1e4, 2.7e4], [0.0, 2.7e4]]]
+LONG_RECT = [[[-1e4, 2.5e4], [-1e4, 2.9e4], [6e4, 2.9e4], [6e4, 2.5e4], [-1e4, 2.5e4]]]
+
+
+def test_three_regions_are_ordered_by_first_crossing_along_polygon_one(lib):
+    """A comb with three teeth dipping into a long rectangle: three overlap regions of 1e4 x 0.2e4 m each.
+    ASSUMPTION (GeometryOps): output rings are started at the first not-yet-visited crossing met walking along polygon 1
+    from its first vertex — the rule that the reference's own two-region answer pins (test_collisions.jl:64-81).  Walking
+    the comb from (0, 2.7e4): exit at x = 0 (tooth 1), entry / exit at x = 5e4 / 4e4 (tooth 3), entry / exit at
+    x = 3e4 / 2e4 (tooth 2), entry at x = 1e4 (tooth 1): regions in the order tooth 1, tooth 3, tooth 2."""
+    c, rect = Floe(COMB, 0.25), Floe(LONG_RECT, 0.25)
+    rect.v = -0.1
+    ff = host.floe_floe_interaction(c, 1, rect, 2, Constants(), 10, 0.55, backend=lib)
+    r = ff.interactions[0]
+    assert len(r) == 3
+    assert np.allclose(r[:, XPOINT], [0.5e4, 4.5e4, 2.5e4], rtol=0, atol=1e-6)   # contact point = region centroid (:178)
+    assert np.allclose(r[:, YPOINT], [2.8e4] * 3, rtol=0, atol=1e-6)
+    assert np.allclose(r[:, OVERLAP], [2e7] * 3, rtol=0, atol=1e-3)
+    # each tooth has two crossing points on y = 2.9e4, 1e4 apart: normal force along -y ... flipped to +y because moving the
+    # comb DOWN would deepen the overlap (:59-67); magnitude = area * force_factor (:69), force_factor of :375-379
+    ai, aj = c.area, rect.area
+    ffac = 6e6 * (0.25 * 0.25) / (0.25 * np.sqrt(aj) + 0.25 * np.sqrt(ai))
+    assert np.allclose(np.abs(r[:, XFORCE]), 0.0, atol=1e-6 * 2e7 * ffac)  # friction (the rectangle moves in y only) has no x part
+    # normal part +y; friction: relative velocity (0, -0.1) - 0 at the contact => along -y on the comb, capped by mu |N|
+    normal = 2e7 * ffac
+    G = 6e6 / (2 * (1 + 0.3))
+    fric = min(G * 1e4 * 10 * normal * 0.1, 0.2 * normal)   # :253-278 with dl = 1e4, dt = 10, |dv| = 0.1
+    assert np.allclose(r[:, YFORCE], [normal - fric] * 3, rtol=1e-12)
+
+
+def test_exactly_shared_edge_is_no_overlap(lib):
+    """Two rectangles that share one whole edge, and two that touch in one corner.
+    ASSUMPTION (GeometryOps): `intersection(...; target = PolygonTrait)` returns no polygon when the interiors do not
+    overlap, so no row, no fuse tag, overarea unchanged (collisions.jl:356-364: total area 0)."""
+    a = Floe(CORNER_RECT, 0.25)
+    for dx, dy in ((2e4, 0.0), (2e4, 0.4e4)):
+        b = Floe(translate(CORNER_RECT, dx, dy), 0.25)
+        a.v, b.v = -0.1, 0.2
+        ff = host.floe_floe_interaction(a, 1, b, 2, Constants(), 10, 0.55, backend=lib)
+        assert len(ff.interactions[0]) == 0 and len(ff.interactions[1]) == 0
+        assert ff.status_tag[0] == capi.STATUS_ACTIVE and ff.status_tag[1] == capi.STATUS_ACTIVE
+        assert ff.overarea[0] == 0.0 and ff.overarea[1] == 0.0
+
+
+def test_collinear_overlapping_edges_take_the_many_intersection_path(lib):
+    """Two equal rectangles shifted by half their length along x: the top and bottom edges overlap COLLINEARLY, the
+    overlap region is [1e4, 2e4] x [2.5e4, 2.9e4] (50 % of either area: no fusing).
+    ASSUMPTION (GeometryOps): `intersection_points` returns the end points of the two collinear overlaps, de-duplicated:
+    the four corners of the region, so m = 4 and `_many_intersect_normal_force!` runs (collisions.jl:50-52,78-119).
+    By hand: three of the region's four edges lie on rectangle 1 (top 1e4, right 0.4e4, bottom 1e4; the left edge is
+    interior to it), each contributes its inward normal times its length: (0, -1e4) + (-0.4e4, 0) + (0, 1e4) =
+    (-0.4e4, 0) => direction (-1, 0), dl = (1e4 + 0.4e4 + 1e4) / 3 = 8000; moving rectangle 1 by (-1, 0) shrinks the
+    overlap, so no flip (:59-67).  Equal velocities: no friction."""
+    a, b = Floe(CORNER_RECT, 0.25), Floe(translate(CORNER_RECT, 1e4, 0.0), 0.25)
+    a.v = b.v = -0.1
+    ff = host.floe_floe_interaction(a, 1, b, 2, Constants(), 10, 0.55, backend=lib)
+    r = ff.interactions[0]
+    assert len(r) == 1 and ff.status_tag[0] == capi.STATUS_ACTIVE
+    ffac = 6e6 * (0.25 * 0.25) / (2 * 0.25 * np.sqrt(8e7))
+    assert r[0, OVERLAP] == pytest.approx(4e7, abs=1e-3)
+    assert r[0, XPOINT] == pytest.approx(1.5e4, abs=1e-6) and r[0, YPOINT] == pytest.approx(2.7e4, abs=1e-6)
+    assert r[0, XFORCE] == pytest.approx(-4e7 * ffac, rel=1e-12) and abs(r[0, YFORCE]) <= 1e-6 * 4e7 * ffac
+    m = ff.interactions[1]
+    assert len(m) == 1 and m[0, XFORCE] == -r[0, XFORCE]
