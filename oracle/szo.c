@@ -1635,22 +1635,28 @@ int32_t szo_generate_subfloe_points(sz_handle *h, const sz_points_generator *g, 
     return rc;
 }
 
-/* calc_eulerian_data!, output.jl:794-919 (no topography: the cell polygon list is the cell box) */
+/* calc_eulerian_data!, output.jl:794-919.  Topography (:826-829: cell_poly_list = cell box minus the topography polygons,
+ * floe areas and si_frac measured on that list) is evaluated WITHOUT a polygon-difference operator, from intersections
+ * only:  area(floe ∩ (cell ∖ topo)) = area(floe ∩ cell) − Σ_k area((floe ∩ cell) ∩ topo_k)  and
+ * area(cell ∖ topo) = area(cell) − Σ_k area(cell ∩ topo_k), which is exact for topography elements that do not overlap one
+ * another (they are separate land masses; overlapping elements would be subtracted twice).  A remainder below 1e-12 of
+ * the uncut area counts as zero (the reference's list would be empty / the floe's piece absent). */
 int32_t szo_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg, const double *yg, int32_t n_out,
                           const int32_t *kinds, double *data) {
     if (!h || nx < 1 || ny < 1 || !xg || !yg || n_out < 0 || (n_out > 0 && (!kinds || !data))) return SZ_ERR_INVALID;
     for (int k = 0; k < n_out; ++k)
         if (kinds[k] < 0 || kinds[k] >= SZ_GRID_NKINDS) return fail(h, SZ_ERR_INVALID, "eulerian_data: unknown output kind");
-    if (h->n_topo > 0) return fail(h, SZ_ERR_UNSUPPORTED, "eulerian_data: topography (diff_polys of the cell polygons) stays on the host");
     const double dx = xg[1] - xg[0], dy = yg[1] - yg[0];      /* :796-797 */
     const double cell_rmax = sqrt(dx * dx + dy * dy);         /* :798 */
 #pragma omp parallel
     {
-        szo_regions R;
+        szo_regions R, R2;
         szo_regions_init(&R);
+        szo_regions_init(&R2);
         int capf = 64, nf;
         int64_t *fidx = (int64_t *)malloc(sizeof(int64_t) * (size_t)capf);
         double *pic = (double *)malloc(sizeof(double) * (size_t)capf);
+        int *tk = (int *)malloc(sizeof(int) * (size_t)(h->n_topo > 0 ? h->n_topo : 1));
 #pragma omp for schedule(dynamic, 4) collapse(2)
         for (int i = 0; i < ny; ++i) {
             for (int j = 0; j < nx; ++j) {
@@ -1658,6 +1664,22 @@ int32_t szo_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg
                 double b[4] = {xg[j], xg[j + 1], yg[i], yg[i + 1]};
                 szo_pt cell[5];
                 make_wall_ring(cell, b);                      /* _make_bounding_box_polygon, :825 */
+                /* topography elements that can reach this cell, and the cell's area without them (:826-829) */
+                int ntk = 0;
+                double cell_area = szo_ring_area(cell, 5), cut = 0.0;
+                for (int k = 0; k < h->n_topo; ++k) {
+                    double ddx = xc - h->topo_cx[k], ddy = yc - h->topo_cy[k];
+                    if (!(sqrt(ddx * ddx + ddy * ddy) < h->topo_rmax[k] + cell_rmax)) continue;
+                    szo_clip(cell, 5, h->topo_ring[k], h->topo_np[k], &R);
+                    double a = 0.0;
+                    for (int g = 0; g < R.nreg; ++g) a += szo_ring_area(R.pts + R.off[g], R.off[g + 1] - R.off[g]);
+                    if (a > 0) { tk[ntk++] = k; cut += a; }
+                }
+                double cell_free = cell_area - cut;
+                if (ntk > 0 && !(cell_free > 1e-12 * cell_area)) {   /* length(cell_poly_list) == 0, :831-834 */
+                    for (int k = 0; k < n_out; ++k) data[(size_t)j + (size_t)nx * ((size_t)i + (size_t)ny * (size_t)k)] = 0.0;
+                    continue;
+                }
                 nf = 0;
                 for (int64_t f = 0; f < h->n; ++f) {          /* mask :808-818, areas :838-846 */
                     double ddx = xc - h->cx[f], ddy = yc - h->cy[f];
@@ -1666,6 +1688,15 @@ int32_t szo_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg
                     szo_clip(h->ring[f], h->npts[f], cell, 5, &R);
                     double a = 0.0;
                     for (int g = 0; g < R.nreg; ++g) a += szo_ring_area(R.pts + R.off[g], R.off[g + 1] - R.off[g]);
+                    if (ntk > 0 && a > 0) {
+                        double sub = 0.0;
+                        for (int q = 0; q < ntk; ++q)
+                            for (int g = 0; g < R.nreg; ++g) {
+                                szo_clip(R.pts + R.off[g], R.off[g + 1] - R.off[g], h->topo_ring[tk[q]], h->topo_np[tk[q]], &R2);
+                                for (int g2 = 0; g2 < R2.nreg; ++g2) sub += szo_ring_area(R2.pts + R2.off[g2], R2.off[g2 + 1] - R2.off[g2]);
+                            }
+                        a = (a - sub > 1e-12 * a) ? a - sub : 0.0;
+                    }
                     if (a > 0) {                              /* :848-849 */
                         if (nf == capf) {
                             capf *= 2;
@@ -1705,7 +1736,7 @@ int32_t szo_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg
                         acc[SZ_GRID_STRAIN_VY] += st[3] * ma;
                         over += h->overarea[f];
                     }
-                    acc[SZ_GRID_SI_FRAC] = area_tot / szo_ring_area(cell, 5);
+                    acc[SZ_GRID_SI_FRAC] = area_tot / cell_free;
                     acc[SZ_GRID_OVERAREA] = over / (double)nf;
                     acc[SZ_GRID_MASS] = mass_tot;
                     acc[SZ_GRID_AREA] = area_tot;
@@ -1723,7 +1754,9 @@ int32_t szo_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg
         }
         free(fidx);
         free(pic);
+        free(tk);
         szo_regions_free(&R);
+        szo_regions_free(&R2);
     }
     return SZ_OK;
 }

@@ -5,6 +5,7 @@
 // retry loop.  No numerical work of the hot path happens here and there is no CPU fallback: when
 // no CUDA device is usable sz_create fails with SZ_ERR_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -62,6 +63,7 @@ struct SlabState {
     int pushed;     // last epoch published to the partners
     int max_send, max_recv;
     long long send_bytes_total;
+    long long cap_lists, cap_owned;  // capacities of the grow-only list arrays
 };
 
 // the step in flight between step_enqueue and step_finish
@@ -96,7 +98,11 @@ struct sz_handle {
     bool graph_off;
     int graph_max_floes;
     double2 *mc_spare;              // second Monte-Carlo array of a slab rank (rebuilds gather into it and swap)
-    long long mc_spare_cap;
+    long long mc_spare_cap, mc_off_cap;
+    double *rb_tx, *rb_ty;          // grow-only scratch of a rebuild: migrants' points, per-floe source offsets
+    double2 *rb_extra;
+    long long *rb_src;
+    long long rb_extra_cap, rb_src_cap;
     unsigned long long tables_gen;  // finish_host_tables: the offset tables were last written for this floe list ...
     const void *tables_ptr[3];      // ... into these caller arrays
     long long tables_mid[2];
@@ -352,6 +358,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->slab.d_owned = nullptr; h->slab.d_refx = h->slab.d_refy = nullptr; h->slab.arena = nullptr; h->slab.arena_bytes = 0;
     h->slab.epoch = 1; h->slab.pushed = 0; h->slab.max_send = h->slab.max_recv = 0; h->slab.send_bytes_total = 0;
     h->slab.arena_gen = 0;
+    h->slab.cap_lists = h->slab.cap_owned = 0;
     memset(&h->cur, 0, sizeof(h->cur));
     memset(&h->hD, 0, sizeof(h->hD));
     memset(&h->P, 0, sizeof(h->P));
@@ -391,7 +398,9 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->L.no_phase_events = getenv("SZ_GRAPH_NO_EVENTS") != nullptr;
     h->L.chain_v2 = getenv("SZ_CHAIN_V1") == nullptr;
     h->mc_spare = nullptr;
-    h->mc_spare_cap = 0;
+    h->mc_spare_cap = h->mc_off_cap = 0;
+    h->rb_tx = h->rb_ty = nullptr; h->rb_extra = nullptr; h->rb_src = nullptr;
+    h->rb_extra_cap = h->rb_src_cap = 0;
     h->tables_gen = 0;
     h->tables_ptr[0] = h->tables_ptr[1] = h->tables_ptr[2] = nullptr;
     h->graph_max_floes = getenv("SZ_GRAPH_MAX_FLOES") ? atoi(getenv("SZ_GRAPH_MAX_FLOES")) : SZ_GRAPH_MAX_FLOES;
@@ -430,7 +439,7 @@ extern "C" void sz_destroy(sz_handle *h) {
     dfree(B.lb_desc); dfree(B.lb_ticket); dfree(B.nb_scratch);
     dfree(B.low_pair); dfree(B.keep); dfree(B.dom_floe); dfree(B.dom_elem); dfree(B.item_nrows); dfree(B.item_row0);
     dfree(B.item_flags); dfree(B.large_items); dfree(B.mid_items); dfree(B.order); dfree(B.order_cls); dfree(B.force_items); dfree(B.force_meta); dfree(B.force_pts); dfree(B.class_count); dfree(B.pool); dfree(B.rows); dfree(B.fuse_pairs);
-    dfree(h->d_hl_idx); dfree(h->d_hl_voff); dfree(h->mc_spare);
+    dfree(h->d_hl_idx); dfree(h->d_hl_voff); dfree(h->mc_spare); dfree(h->rb_tx); dfree(h->rb_ty); dfree(h->rb_extra); dfree(h->rb_src);
     for (auto &m : h->slab.ipc_open) cudaIpcCloseMemHandle(m.ptr);
     h->slab.ipc_open.clear();
     for (unsigned char *p : h->slab.retired) cudaFree(p);
@@ -680,8 +689,22 @@ static int32_t upload_scalars(sz_handle *h, const sz_floe_soa *s, int n) {
 // mc_src != NULL (sz_slab_rebuild): the points of floe i are already on the device — at offset mc_src[i] of the resident
 // array when mc_src[i] >= 0 — or arrive in the COMPACT host arrays s->mc_x / s->mc_y at offset -1 - mc_src[i]
 // (n_extra points in total: migrants); the new array is gathered on the device.
+struct DbgTimer {  // SZ_SLAB_DEBUG: wall clock of the stages of an upload on stderr
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    int dev;
+    explicit DbgTimer(int d) : on(getenv("SZ_SLAB_DEBUG") != nullptr), t0(std::chrono::steady_clock::now()), dev(d) {}
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[upload dev %d]   %-26s %8.2f ms\n", dev, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64_t *mc_src, int64_t n_extra) {
     if (!h || !s || s->n < 0 || s->n_init < 0 || s->n_init > s->n) return fail(h, SZ_ERR_INVALID, "upload_floes: bad sizes");
+    DbgTimer dbg(h->cfg.device);
     if (s->n > 0 && (!s->centroid_x || !s->centroid_y || !s->area || !s->rmax || !s->vert_offsets || !s->vert_xy))
         return fail(h, SZ_ERR_INVALID, "upload_floes: geometry arrays are required");
     if (s->n > (1ll << 28)) return fail(h, SZ_ERR_UNSUPPORTED, "upload_floes: too many floes");
@@ -748,13 +771,18 @@ static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64
         h->mc_spare = nullptr;
         h->mc_spare_cap = 0;
         h->gen++;
+        dbg.lap("Monte-Carlo spare array");
     } else if (M > S.cap_mc || !S.mc) {
         dfree(S.mc);
         CK(dalloc(&S.mc, (size_t)M));
         S.cap_mc = M;
     }
-    dfree(S.mc_off);
-    CK(dalloc(&S.mc_off, (size_t)n_init + 2));
+    dbg.lap("host tables + capacities");
+    if (h->mc_off_cap < (long long)n_init + 2 || !S.mc_off) {
+        dfree(S.mc_off);
+        h->mc_off_cap = (long long)n_init + n_init / 8 + 1024;
+        CK(dalloc(&S.mc_off, (size_t)h->mc_off_cap));
+    }
     StepBuf &B = h->B;
     int ppf = h->cfg.max_pairs_per_floe > 0 ? h->cfg.max_pairs_per_floe : 24;
     long long want_pairs = (long long)ppf * S.cap_floes / 2 + 1024, want_domc = (long long)S.cap_floes / 2 + 4096 + 4ll * n;
@@ -796,26 +824,34 @@ static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64
     if (s->mc_offsets) for (int i = 0; i <= n_init; ++i) mo[i] = s->mc_offsets[i];
     CK(cudaMemcpyAsync(S.mc_off, mo.data(), sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyHostToDevice, st));
     long long Mi = mo[n_init];
+    dbg.lap("per-floe arrays + rings");
     if (mc_src) {
-        double2 *extra = nullptr;
-        long long *dsrc = nullptr;
-        double *tx = nullptr, *ty = nullptr;
-        if (n_extra > 0) {
-            CK(dalloc(&tx, (size_t)n_extra)); CK(dalloc(&ty, (size_t)n_extra)); CK(dalloc(&extra, (size_t)n_extra));
-            CK(cudaMemcpyAsync(tx, s->mc_x, sizeof(double) * n_extra, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(ty, s->mc_y, sizeof(double) * n_extra, cudaMemcpyHostToDevice, st));
-            szk_interleave(h->L, tx, ty, extra, n_extra);
+        // grow-only scratch: no allocation in a rebuild once the sizes have settled
+        if (h->rb_extra_cap < n_extra) {
+            dfree(h->rb_tx); dfree(h->rb_ty); dfree(h->rb_extra);
+            h->rb_extra_cap = n_extra + n_extra / 2 + 65536;
+            CK(dalloc(&h->rb_tx, (size_t)h->rb_extra_cap)); CK(dalloc(&h->rb_ty, (size_t)h->rb_extra_cap));
+            CK(dalloc(&h->rb_extra, (size_t)h->rb_extra_cap));
         }
-        CK(dalloc(&dsrc, (size_t)n_init + 1));
+        if (h->rb_src_cap < (long long)n_init + 1) {
+            dfree(h->rb_src);
+            h->rb_src_cap = (long long)n_init + n_init / 8 + 1024;
+            CK(dalloc(&h->rb_src, (size_t)h->rb_src_cap));
+        }
+        if (n_extra > 0) {
+            CK(cudaMemcpyAsync(h->rb_tx, s->mc_x, sizeof(double) * n_extra, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(h->rb_ty, s->mc_y, sizeof(double) * n_extra, cudaMemcpyHostToDevice, st));
+            szk_interleave(h->L, h->rb_tx, h->rb_ty, h->rb_extra, n_extra);
+        }
         std::vector<long long> hs((size_t)n_init + 1, 0);
         for (int i = 0; i < n_init; ++i) hs[i] = mc_src[i];
-        CK(cudaMemcpyAsync(dsrc, hs.data(), sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyHostToDevice, st));
-        szk_mc_regather(h->L, S.mc, S.mc_off, old_mc, extra, dsrc, n_init);
+        CK(cudaMemcpyAsync(h->rb_src, hs.data(), sizeof(long long) * ((size_t)n_init + 1), cudaMemcpyHostToDevice, st));
+        szk_mc_regather(h->L, S.mc, S.mc_off, old_mc, h->rb_extra, h->rb_src, n_init);
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
-        cudaFree(tx); cudaFree(ty); cudaFree(extra); cudaFree(dsrc);
         h->mc_spare = old_mc;  // the next rebuild gathers into it
         h->mc_spare_cap = old_cap;
+        dbg.lap("Monte-Carlo regather");
     } else if (Mi > 0) {
         double *tx = nullptr, *ty = nullptr;
         CK(dalloc(&tx, (size_t)Mi)); CK(dalloc(&ty, (size_t)Mi));
@@ -838,6 +874,7 @@ static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64
     h->h_vstart = vstart;
     h->h_vcount = vcount;
     h->h_mc_off = mo;
+    dbg.lap("rest");
     h->have_floes = true;
     h->slab.on = false;  // a new floe list: the halo lists must be configured again
     h->gen++;
@@ -1679,10 +1716,7 @@ int32_t szb_release_peers(sz_handle *h, int32_t final) {
 }
 
 static void slab_free(sz_handle *h) {
-    SlabState &B = h->slab;
-    dfree(B.d_send_idx); dfree(B.d_recv_idx); dfree(B.d_send_voff); dfree(B.d_recv_voff); dfree(B.d_owned); dfree(B.d_refx);
-    dfree(B.d_refy);
-    B.on = false;  // the arena stays (see SlabState)
+    h->slab.on = false;  // the arena and the (grow-only) list arrays stay
 }
 
 int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
@@ -1749,9 +1783,17 @@ int32_t szb_configure(sz_handle *h, const SlabLists *l, SlabWire *wire_out) {
         B.arena_gen++;
     }
     CK(cudaMemset(B.arena, 0, FLAGS));
-    CK(dalloc(&B.d_send_idx, (size_t)ns)); CK(dalloc(&B.d_recv_idx, (size_t)nr));
-    CK(dalloc(&B.d_send_voff, (size_t)ns)); CK(dalloc(&B.d_recv_voff, (size_t)nr));
-    CK(dalloc(&B.d_owned, (size_t)n)); CK(dalloc(&B.d_refx, (size_t)n)); CK(dalloc(&B.d_refy, (size_t)n));
+    if (B.cap_lists < std::max(ns, nr) || !B.d_send_idx) {
+        dfree(B.d_send_idx); dfree(B.d_recv_idx); dfree(B.d_send_voff); dfree(B.d_recv_voff);
+        B.cap_lists = std::max(ns, nr) * 2 + 4096;
+        CK(dalloc(&B.d_send_idx, (size_t)B.cap_lists)); CK(dalloc(&B.d_recv_idx, (size_t)B.cap_lists));
+        CK(dalloc(&B.d_send_voff, (size_t)B.cap_lists)); CK(dalloc(&B.d_recv_voff, (size_t)B.cap_lists));
+    }
+    if (B.cap_owned < n || !B.d_owned) {
+        dfree(B.d_owned); dfree(B.d_refx); dfree(B.d_refy);
+        B.cap_owned = (long long)n + n / 8 + 1024;
+        CK(dalloc(&B.d_owned, (size_t)B.cap_owned)); CK(dalloc(&B.d_refx, (size_t)B.cap_owned)); CK(dalloc(&B.d_refy, (size_t)B.cap_owned));
+    }
     if (ns > 0) {
         CK(cudaMemcpy(B.d_send_idx, sidx.data(), sizeof(int) * ns, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B.d_send_voff, svoff.data(), sizeof(long long) * ns, cudaMemcpyHostToDevice));
