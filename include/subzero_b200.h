@@ -46,7 +46,7 @@ extern "C" {
 #define SZ_ERR_INVALID (-1)     /* bad argument / call order */
 #define SZ_ERR_CUDA (-2)        /* CUDA runtime failure */
 #define SZ_ERR_CAPACITY (-3)    /* a device buffer overflowed (pairs, regions, rows, ghosts) */
-#define SZ_ERR_UNSUPPORTED (-4) /* outside the scope or the workspace (a ring of > 1024 points, gridded output with topography) */
+#define SZ_ERR_UNSUPPORTED (-4) /* outside the workspace (a ring of > 1024 points, a floe in > 2080 grid cells) */
 #define SZ_ERR_NOMEM (-5)
 
 /* Status tags, src/simulation_components/floe.jl:8-12 */
@@ -350,8 +350,10 @@ int32_t SZ_FN(pair_overlap_areas)(sz_handle *h, int64_t n_pairs, const int64_t *
  * outputs (SZ_GRID_*, the symbols of output.jl:859-905); data is [nx][ny][n_out] in Julia's column-major order,
  * data[j + nx*(i + ny*k)] == writer.data[j+1, i+1, k+1] (x index first).  All floes in the store take part
  * (the reference calls it between add_ghosts! and timestep_collisions!, simulation.jl:102-105, so ghosts are
- * included when present).  Topography (cell polygons minus topography, output.jl:826-829) is outside the scope:
- * with n_topo > 0 the call returns SZ_ERR_UNSUPPORTED and the host keeps its own implementation. */
+ * included when present).  Topography (cell_poly_list = cell minus the topography polygons, output.jl:826-829) is
+ * evaluated from intersections only: area(floe ∩ (cell ∖ topo)) = area(floe ∩ cell) − Σ_k area((floe ∩ cell) ∩ topo_k),
+ * area(cell ∖ topo) = area(cell) − Σ_k area(cell ∩ topo_k) — exact for topography elements that do not overlap each
+ * other; a remainder below 1e-12 of the uncut area counts as zero (empty cell_poly_list: all outputs 0, :831-834). */
 #define SZ_GRID_U 0
 #define SZ_GRID_V 1
 #define SZ_GRID_DUDT 2

@@ -1673,8 +1673,10 @@ int32_t szo_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const double *xg
                     szo_clip(cell, 5, h->topo_ring[k], h->topo_np[k], &R);
                     double a = 0.0;
                     for (int g = 0; g < R.nreg; ++g) a += szo_ring_area(R.pts + R.off[g], R.off[g + 1] - R.off[g]);
-                    if (a > 0) { tk[ntk++] = k; cut += a; }
+                    tk[ntk++] = k;
+                    cut += a;
                 }
+                if (!(cut > 0)) ntk = 0;                              /* nothing to cut out of this cell */
                 double cell_free = cell_area - cut;
                 if (ntk > 0 && !(cell_free > 1e-12 * cell_area)) {   /* length(cell_poly_list) == 0, :831-834 */
                     for (int k = 0; k < n_out; ++k) data[(size_t)j + (size_t)nx * ((size_t)i + (size_t)ny * (size_t)k)] = 0.0;

@@ -276,10 +276,63 @@ static inline int szo_point_in_ring_p(szo_pt q, const szo_pt *r, int n) {
 }
 typedef struct {
     int e, f;
-    double t, s;
+    double t, s;   /* RANKING parameters along P / Q (szo_rank_params); the point itself is a + t0 (b - a) */
     szo_pt p;
     int entry, rankP, rankQ, visited;
 } szo_xing;
+
+/* Parameters that order the crossings along P (t) and along Q (s).  In general position they are the intersection
+ * parameters o1 / (o1 - o2) and o3 / (o3 - o4).  When the crossing sits exactly AT a vertex — a P vertex lying exactly on
+ * the Q edge's line (o1 == 0 or o2 == 0), a Q vertex exactly on the P edge's line (o3 == 0 or o4 == 0) — the two P (Q)
+ * edges that meet in that vertex both cross there, and their parameters along the OTHER polygon's edge are two different
+ * roundings of one number: they are replaced by ONE expression of the vertex itself (its projection on the edge), so that
+ * the two compare equal and the tie is broken by the perturbation (szo_sym_before) instead of by rounding noise. */
+static inline void szo_rank_params(szo_pt a, szo_pt b, szo_pt c, szo_pt d, double o1, double o2, double o3, double o4,
+                                   double *t, double *s) {
+    *t = o1 / (o1 - o2);
+    *s = o3 / (o3 - o4);
+    if (o1 == 0.0 || o2 == 0.0) {
+        szo_pt w = o1 == 0.0 ? a : b;
+        double vx = d.x - c.x, vy = d.y - c.y;
+        *s = ((w.x - c.x) * vx + (w.y - c.y) * vy) / (vx * vx + vy * vy);
+    }
+    if (o3 == 0.0 || o4 == 0.0) {
+        szo_pt w = o3 == 0.0 ? c : d;
+        double ux = b.x - a.x, uy = b.y - a.y;
+        *t = ((w.x - a.x) * ux + (w.y - a.y) * uy) / (ux * ux + uy * uy);
+    }
+}
+/* Two crossings on the same edge with the same ranking parameter — they sit at ONE vertex w of the other ring that lies
+ * exactly on this edge's line: which comes first once Q is translated by delta = (eps, eps^2)?
+ * Along a Q edge (direction v; the two P edges u_m, u_k meet in w):  the P line w + tau u meets the shifted Q line at
+ * s = s0 + [(delta x v) cot(u, v) - delta . v] / |v|^2, cot(u, v) = (u . v) / (u x v), so
+ *     s_m < s_k  <=>  sign(delta x v) cot(u_m, v) < sign(delta x v) cot(u_k, v),   delta x v = eps v_y - eps^2 v_x.
+ * Along a P edge (direction u; the two Q edges v_m, v_k meet in the shifted vertex w + delta):
+ *     t = t0 + [delta . u - (delta x u) cot(v, u)] / |u|^2   =>   t_m < t_k  <=>  sign(delta x u) cot(v_m, u) > sign(delta x u) cot(v_k, u).
+ * One division per crossing and no term that is mathematically common to both sides, so equal first-order shifts (a
+ * horizontal or vertical edge) cannot be decided by rounding noise.  Returns 1 when crossing m comes before crossing k. */
+static inline int szo_sym_before(const szo_pt *P, const szo_pt *Q, int em, int fm, int ek, int fk, int along_p, int m_lt_k) {
+    double cot[2];
+    const int e[2] = {em, ek}, f[2] = {fm, fk};
+    for (int i = 0; i < 2; ++i) {
+        double ux = P[e[i] + 1].x - P[e[i]].x, uy = P[e[i] + 1].y - P[e[i]].y;
+        double vx = Q[f[i] + 1].x - Q[f[i]].x, vy = Q[f[i] + 1].y - Q[f[i]].y;
+        double dot = ux * vx + uy * vy;
+        double crs = along_p ? vx * uy - vy * ux : ux * vy - uy * vx; /* v x u along P, u x v along Q */
+        if (crs == 0.0) return m_lt_k;
+        cot[i] = dot / crs;
+    }
+    if (cot[0] == cot[1]) return m_lt_k;
+    if (along_p) {
+        double ux = P[em + 1].x - P[em].x, uy = P[em + 1].y - P[em].y; /* the shared P edge */
+        int sg = uy != 0.0 ? (uy > 0.0) : (ux < 0.0);                  /* sign(eps u_y - eps^2 u_x) > 0 */
+        return sg ? cot[0] > cot[1] : cot[0] < cot[1];
+    } else {
+        double vx = Q[fm + 1].x - Q[fm].x, vy = Q[fm + 1].y - Q[fm].y; /* the shared Q edge */
+        int sg = vy != 0.0 ? (vy > 0.0) : (vx < 0.0);
+        return sg ? cot[0] < cot[1] : cot[0] > cot[1];
+    }
+}
 
 static inline void szo_push_pt(szo_regions *R, int *n, szo_pt p, int start) {
     if (*n > start && R->pts[*n - 1].x == p.x && R->pts[*n - 1].y == p.y) return;
@@ -315,10 +368,10 @@ static inline int szo_clip(const szo_pt *P, int npp, const szo_pt *Q, int nqp, s
             szo_xing *x = &X[K++];
             x->e = e;
             x->f = f;
-            x->t = o1 / (o1 - o2);
-            x->s = o3 / (o3 - o4);
-            x->p.x = a.x + x->t * (b.x - a.x);
-            x->p.y = a.y + x->t * (b.y - a.y);
+            double t0 = o1 / (o1 - o2);
+            szo_rank_params(a, b, c, d, o1, o2, o3, o4, &x->t, &x->s);
+            x->p.x = a.x + t0 * (b.x - a.x);
+            x->p.y = a.y + t0 * (b.y - a.y);
             x->entry = (sb == q_ccw);
             x->visited = 0;
         }
@@ -349,8 +402,10 @@ static inline int szo_clip(const szo_pt *P, int npp, const szo_pt *Q, int nqp, s
         int rp = 0, rq = 0;
         for (int m = 0; m < K; ++m) {
             if (m == k) continue;
-            if (X[m].e < X[k].e || (X[m].e == X[k].e && (X[m].t < X[k].t || (X[m].t == X[k].t && m < k)))) rp++;
-            if (X[m].f < X[k].f || (X[m].f == X[k].f && (X[m].s < X[k].s || (X[m].s == X[k].s && m < k)))) rq++;
+            if (X[m].e < X[k].e || (X[m].e == X[k].e && (X[m].t < X[k].t || (X[m].t == X[k].t &&
+                    szo_sym_before(P, Q, X[m].e, X[m].f, X[k].e, X[k].f, 1, m < k))))) rp++;
+            if (X[m].f < X[k].f || (X[m].f == X[k].f && (X[m].s < X[k].s || (X[m].s == X[k].s &&
+                    szo_sym_before(P, Q, X[m].e, X[m].f, X[k].e, X[k].f, 0, m < k))))) rq++;
         }
         X[k].rankP = rp;
         X[k].rankQ = rq;

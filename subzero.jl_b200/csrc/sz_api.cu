@@ -30,6 +30,7 @@ struct SvcBuf {
     int *rec_count, *rec_off, *cell_start, *rec_floe, *rec_cell, *val_in, *val_out;
     unsigned long long *key_in, *key_out;
     unsigned char *sort_tmp;
+    double *cell_free; unsigned char *cell_topo; size_t cap_cfree, cap_ctopo;
     size_t cap_pairs, cap_area, cap_inter, cap_big, cap_xg, cap_yg, cap_data, cap_ra, cap_rc, cap_ro, cap_cs, cap_rf, cap_rcell,
         cap_vi, cap_vo, cap_ki, cap_ko, cap_sort;
 };
@@ -453,7 +454,7 @@ extern "C" void sz_destroy(sz_handle *h) {
         SvcBuf &V = h->svc;
         dfree(V.pairs); dfree(V.area); dfree(V.inter); dfree(V.big); dfree(V.xg); dfree(V.yg); dfree(V.data); dfree(V.rec_area);
         dfree(V.rec_count); dfree(V.rec_off); dfree(V.cell_start); dfree(V.rec_floe); dfree(V.rec_cell); dfree(V.val_in);
-        dfree(V.val_out); dfree(V.key_in); dfree(V.key_out); dfree(V.sort_tmp);
+        dfree(V.val_out); dfree(V.key_in); dfree(V.key_out); dfree(V.sort_tmp); dfree(V.cell_free); dfree(V.cell_topo);
     }
     {
         CouplingBuf &C = h->CB;
@@ -785,7 +786,8 @@ static int32_t upload_floes_impl(sz_handle *h, const sz_floe_soa *s, const int64
     }
     StepBuf &B = h->B;
     int ppf = h->cfg.max_pairs_per_floe > 0 ? h->cfg.max_pairs_per_floe : 24;
-    long long want_pairs = (long long)ppf * S.cap_floes / 2 + 1024, want_domc = (long long)S.cap_floes / 2 + 4096 + 4ll * n;
+    // sized from the floe CAPACITY, not from n: a list that grows by a few floes (slab rebuilds) must not re-allocate them
+    long long want_pairs = (long long)ppf * S.cap_floes / 2 + 1024, want_domc = (long long)S.cap_floes / 2 + 4096 + 4ll * S.cap_floes;
     if (h->n_topo > 0) want_domc += (long long)S.cap_floes;
     want_pairs = std::min<long long>(want_pairs, 1ll << 30);
     want_domc = std::min<long long>(want_domc, 1ll << 30);
@@ -2198,7 +2200,6 @@ extern "C" int32_t sz_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const 
     if (n_out > SZ_GRID_NKINDS) return fail(h, SZ_ERR_INVALID, "eulerian_data: more outputs than kinds");
     for (int k = 0; k < n_out; ++k)
         if (kinds[k] < 0 || kinds[k] >= SZ_GRID_NKINDS) return fail(h, SZ_ERR_INVALID, "eulerian_data: unknown output kind");
-    if (h->n_topo > 0) return fail(h, SZ_ERR_UNSUPPORTED, "eulerian_data: topography (diff_polys of the cell polygons) stays on the host");
     if ((long long)nx * ny > (1ll << 28)) return fail(h, SZ_ERR_UNSUPPORTED, "eulerian_data: too many cells");
     if (n_out == 0) return SZ_OK;
     cudaSetDevice(h->cfg.device);
@@ -2209,6 +2210,7 @@ extern "C" int32_t sz_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const 
     CK(ensure(V.rec_count, V.cap_rc, (size_t)nf + 2)); CK(ensure(V.rec_off, V.cap_ro, (size_t)nf + 2));
     CK(ensure(V.cell_start, V.cap_cs, (size_t)ncell + 2)); CK(ensure(V.data, V.cap_data, (size_t)ncell * n_out));
     CK(ensure(V.big, V.cap_big, 2));
+    if (h->n_topo > 0) { CK(ensure(V.cell_free, V.cap_cfree, (size_t)ncell)); CK(ensure(V.cell_topo, V.cap_ctopo, (size_t)ncell)); }
     CK(cudaMemcpyAsync(V.xg, xg, sizeof(double) * (nx + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(V.yg, yg, sizeof(double) * (ny + 1), cudaMemcpyHostToDevice, st));
     const double dx = xg[1] - xg[0], dy = yg[1] - yg[0];  // output.jl:796-797
@@ -2232,6 +2234,7 @@ extern "C" int32_t sz_eulerian_data(sz_handle *h, int32_t nx, int32_t ny, const 
     A.rec_count = V.rec_count; A.rec_off = V.rec_off; A.rec_floe = V.rec_floe; A.rec_cell = V.rec_cell; A.val_in = V.val_in;
     A.val_out = V.val_out; A.cell_start = V.cell_start; A.big = V.big + 1; A.n_big = V.big; A.rec_area = V.rec_area;
     A.key_in = V.key_in; A.key_out = V.key_out; A.sort_tmp = V.sort_tmp; A.kinds = kinds; A.d_data = V.data;
+    A.cell_free = V.cell_free; A.cell_topo = V.cell_topo; A.n_topo = h->n_topo;
     if (szk_eul_run(h->L, h->S, A) != 0) return fail(h, SZ_ERR_CUDA, "eulerian_data: sort failed");
     CK(cudaMemcpyAsync(data, V.data, sizeof(double) * (size_t)ncell * n_out, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->h_cnt, h->S.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));

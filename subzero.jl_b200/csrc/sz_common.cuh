@@ -293,6 +293,9 @@ struct SzkEulArgs {
     size_t sort_bytes;
     const int *kinds;  // host
     double *d_data;
+    double *cell_free;         // [ncell] topography: free area of every cell
+    unsigned char *cell_topo;  // [ncell]
+    int n_topo;
 };
 
 int szk_eul_run(const Launch &L, const Store &S, const SzkEulArgs &A);

@@ -269,6 +269,46 @@ enum { CLIP_OK = 0, CLIP_FAIL = 1, CLIP_OVERFLOW = 2 };
 //  3. from each entry in P order: follow P to the next crossing (an exit), then Q (forward if P
 //     and Q have the same orientation, else backward) to the next crossing, until closed;
 //  4. no crossings: P inside Q -> P; Q inside P -> Q; else nothing.
+// ranking parameters of a crossing and the perturbation tie-break: see szo_rank_params / szo_sym_before in
+// oracle/szo_geom.h (the same expressions, hence the same bits)
+__device__ __forceinline__ void rank_params(double2 a, double2 b, double2 c, double2 d, double o1, double o2, double o3, double o4,
+                                            double &t, double &s) {
+    t = o1 / (o1 - o2);
+    s = o3 / (o3 - o4);
+    if (o1 == 0.0 || o2 == 0.0) {
+        const double2 wv = o1 == 0.0 ? a : b;
+        const double vx = d.x - c.x, vy = d.y - c.y;
+        s = ((wv.x - c.x) * vx + (wv.y - c.y) * vy) / (vx * vx + vy * vy);
+    }
+    if (o3 == 0.0 || o4 == 0.0) {
+        const double2 wv = o3 == 0.0 ? c : d;
+        const double ux = b.x - a.x, uy = b.y - a.y;
+        t = ((wv.x - a.x) * ux + (wv.y - a.y) * uy) / (ux * ux + uy * uy);
+    }
+}
+__device__ __noinline__ bool sym_before(const double2 *P, const double2 *Q, int em, int fm, int ek, int fk, bool along_p, bool m_lt_k) {
+    double ct[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int e = i == 0 ? em : ek, f = i == 0 ? fm : fk;
+        const double ux = P[e + 1].x - P[e].x, uy = P[e + 1].y - P[e].y;
+        const double vx = Q[f + 1].x - Q[f].x, vy = Q[f + 1].y - Q[f].y;
+        const double dot = ux * vx + uy * vy;
+        const double crs = along_p ? vx * uy - vy * ux : ux * vy - uy * vx;  // v x u along P, u x v along Q
+        if (crs == 0.0) return m_lt_k;
+        ct[i] = dot / crs;
+    }
+    if (ct[0] == ct[1]) return m_lt_k;
+    if (along_p) {
+        const double ux = P[em + 1].x - P[em].x, uy = P[em + 1].y - P[em].y;  // the shared P edge
+        const bool sg = uy != 0.0 ? (uy > 0.0) : (ux < 0.0);                  // sign(eps u_y - eps^2 u_x) > 0
+        return sg ? ct[0] > ct[1] : ct[0] < ct[1];
+    }
+    const double vx = Q[fm + 1].x - Q[fm].x, vy = Q[fm + 1].y - Q[fm].y;  // the shared Q edge
+    const bool sg = vy != 0.0 ? (vy > 0.0) : (vx < 0.0);
+    return sg ? ct[0] < ct[1] : ct[0] > ct[1];
+}
+
 __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *Q, int nqp, double2 *R, short *rs,
                          short *re, int &status) {
     const int RCAP = w.rcap, MAXREG = w.maxreg, MAXX = w.maxx;
@@ -301,10 +341,10 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
                 bool sc = side_p(o3, a, b), sd = side_p(o4, a, b);
                 if (sc != sd) {
                     hit = true;
-                    t = o1 / (o1 - o2);
-                    s = o3 / (o3 - o4);
-                    xp.x = a.x + t * (b.x - a.x);
-                    xp.y = a.y + t * (b.y - a.y);
+                    const double t0 = o1 / (o1 - o2);
+                    rank_params(a, b, c, d, o1, o2, o3, o4, t, s);  // ranking parameters; the point uses t0
+                    xp.x = a.x + t0 * (b.x - a.x);
+                    xp.y = a.y + t0 * (b.y - a.y);
                     ent = (sb == q_ccw);
                 }
             }
@@ -361,8 +401,8 @@ __device__ int warp_clip(const Ws &w, const double2 *P, int npp, const double2 *
             if (m == k) continue;
             int em = w.xe[m], fm = w.xf[m];
             double tm = w.xt[m], sm = w.xs[m];
-            if (em < ek || (em == ek && (tm < tk || (tm == tk && m < k)))) rp++;
-            if (fm < fk || (fm == fk && (sm < sk || (sm == sk && m < k)))) rq++;
+            if (em < ek || (em == ek && (tm < tk || (tm == tk && sym_before(P, Q, em, fm, ek, fk, true, m < k))))) rp++;
+            if (fm < fk || (fm == fk && (sm < sk || (sm == sk && sym_before(P, Q, em, fm, ek, fk, false, m < k))))) rq++;
         }
         w.rankP[k] = (short)rp;
         w.rankQ[k] = (short)rq;

@@ -289,6 +289,9 @@ __device__ TN_FN unsigned long long t_clip(const TRing P, const TRing Q, double2
         }
     }
     if (fail) return TC_PACK(0, TN_DEFER, 0, 0, 0, 0, 0, 0);
+    // a vertex exactly on the other ring's edge: two crossings may coincide there and their order along that edge is
+    // decided by the perturbation (sym_before in sz_geom.cuh), which only the warp kernel implements
+    if (anyzero && K > 1) return TC_PACK(0, TN_DEFER, 0, 0, 0, 0, 0, 0);
     bool gen = false;
     if (xp_out) {
         bool dup = false;

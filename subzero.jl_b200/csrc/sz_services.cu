@@ -108,6 +108,10 @@ struct EulGrid {
     int nx, ny, n_floes;
     const double *xg, *yg;  // device copies of the writer's grid lines
     double dx, dy;
+    // topography (output.jl:826-829): free area of every cell (cell minus topography), 1 where something was cut out
+    double *cell_free;
+    unsigned char *cell_topo;
+    int n_topo;
 };
 struct EulBuf {
     int *rec_count, *rec_off;  // [n_floes + 1]
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(TN_NT, 2) k_eul_area(Store S, EulGrid G, EulBu
     double2 *sP = base, *sQ = sP + TN_MAXV * TN_NT, *sR = sQ + TN_MAXV * TN_NT;
     for (int r = blockIdx.x * TN_NT + threadIdx.x; r < B.n_rec; r += gridDim.x * TN_NT) {
         const int f = B.rec_floe[r], np = S.vcount[f];
-        bool big = np > TN_MAXV;
+        bool big = np > TN_MAXV || (G.n_topo > 0 && G.cell_topo[B.rec_cell[r]]);
         double area = 0.0;
         if (!big) {
             double b[4];
@@ -243,8 +247,89 @@ __global__ void k_eul_area_warp(Store S, EulGrid G, EulBuf B, int maxv, int maxx
             if (lane == 0) atomicOr(&S.cnt->error, ERR_POLY_TOO_LARGE);
         } else {
             for (int g = 0; g < nreg; ++g) area += ring_area_seq(w.R1 + w.rs1[g], w.re1[g] - w.rs1[g]);
+            if (G.n_topo > 0 && G.cell_topo[B.rec_cell[r]] && area > 0) {
+                // area(floe ∩ (cell ∖ topo)) = area(floe ∩ cell) − Σ_k area((floe ∩ cell) ∩ topo_k): every region of clip #1
+                // against every topography element that reaches the cell (same circle test, same order as the oracle)
+                const double cell_rmax = sqrt(G.dx * G.dx + G.dy * G.dy);
+                const double xc = b[0] + 0.5 * G.dx, yc = b[2] + 0.5 * G.dy;
+                double sub = 0.0;
+                for (int k = 0; k < G.n_topo; ++k) {
+                    const double ddx = xc - S.topo_cx[k], ddy = yc - S.topo_cy[k];
+                    if (!(sqrt(ddx * ddx + ddy * ddy) < S.topo_rmax[k] + cell_rmax)) continue;
+                    const int nq = S.topo_vcount[k];
+                    const double2 *gQ = S.topo_verts + S.topo_vstart[k];
+                    __syncwarp();
+                    for (int v = lane; v < nq; v += 32) w.Q[v] = gQ[v];
+                    for (int g = 0; g < nreg; ++g) {
+                        const int a0 = w.rs1[g], nr = w.re1[g] - a0;
+                        if (nr > w.maxv) {
+                            if (lane == 0) atomicOr(&S.cnt->error, ERR_POLY_TOO_LARGE);
+                            continue;
+                        }
+                        __syncwarp();
+                        for (int v = lane; v < nr; v += 32) w.P2[v] = w.R1[a0 + v];
+                        __syncwarp();
+                        int st2;
+                        const int n2 = warp_clip(w, w.P2, nr, w.Q, nq, w.R2, w.rs2, w.re2, st2);
+                        if (st2 == CLIP_OVERFLOW) {
+                            if (lane == 0) atomicOr(&S.cnt->error, ERR_POLY_TOO_LARGE);
+                            continue;
+                        }
+                        for (int g2 = 0; g2 < n2; ++g2) sub += ring_area_seq(w.R2 + w.rs2[g2], w.re2[g2] - w.rs2[g2]);
+                    }
+                }
+                area = (area - sub > 1e-12 * area) ? area - sub : 0.0;
+            }
         }
         if (lane == 0) B.rec_area[r] = area;
+        __syncwarp();
+    }
+}
+
+// free area of every cell: area(cell) − Σ_k area(cell ∩ topo_k) (output.jl:826-829 without a difference operator);
+// cell_topo = 1 where something was cut out; a cell that is (all but 1e-12) covered gets free area 0 => all outputs 0
+__global__ void k_eul_cell_topo(Store S, EulGrid G, int maxv, int maxx) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = lane_id(), wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    Ws w = ws_carve(smem + (size_t)wib * ws_bytes(maxv, maxx), maxv, maxx);
+    const int ncell = G.nx * G.ny;
+    const double cell_rmax = sqrt(G.dx * G.dx + G.dy * G.dy);
+    for (int c = blockIdx.x * wpb + wib; c < ncell; c += gridDim.x * wpb) {
+        double b[4];
+        eul_box(G, c, b);
+        const double2 q0 = make_double2(b[0], b[2]), q1 = make_double2(b[0], b[3]), q2 = make_double2(b[1], b[3]), q3 = make_double2(b[1], b[2]);
+        double a2 = 0.0;
+        a2 += q0.x * q1.y - q0.y * q1.x;
+        a2 += q1.x * q2.y - q1.y * q2.x;
+        a2 += q2.x * q3.y - q2.y * q3.x;
+        a2 += q3.x * q0.y - q3.y * q0.x;
+        const double cell_area = fabs(a2 / 2.0);
+        const double xc = b[0] + 0.5 * G.dx, yc = b[2] + 0.5 * G.dy;
+        double cut = 0.0;
+        for (int k = 0; k < G.n_topo; ++k) {
+            const double ddx = xc - S.topo_cx[k], ddy = yc - S.topo_cy[k];
+            if (!(sqrt(ddx * ddx + ddy * ddy) < S.topo_rmax[k] + cell_rmax)) continue;
+            const int nq = S.topo_vcount[k];
+            const double2 *gQ = S.topo_verts + S.topo_vstart[k];
+            __syncwarp();
+            if (lane == 0) { w.P[0] = q0; w.P[1] = q1; w.P[2] = q2; w.P[3] = q3; w.P[4] = q0; }
+            for (int v = lane; v < nq; v += 32) w.Q[v] = gQ[v];
+            __syncwarp();
+            int status;
+            const int nreg = warp_clip(w, w.P, 5, w.Q, nq, w.R1, w.rs1, w.re1, status);
+            if (status == CLIP_OVERFLOW) {
+                if (lane == 0) atomicOr(&S.cnt->error, ERR_POLY_TOO_LARGE);
+                continue;
+            }
+            for (int g = 0; g < nreg; ++g) cut += ring_area_seq(w.R1 + w.rs1[g], w.re1[g] - w.rs1[g]);
+        }
+        if (lane == 0) {
+            const bool any = cut > 0;
+            double fr = cell_area - cut;
+            if (any && !(fr > 1e-12 * cell_area)) fr = 0.0;
+            G.cell_free[c] = fr;
+            G.cell_topo[c] = any ? 1 : 0;
+        }
         __syncwarp();
     }
 }
@@ -304,7 +389,8 @@ __global__ void k_eul_cells(Store S, EulGrid G, EulBuf B, EulOut O) {
         double acc[SZ_GRID_NKINDS];
 #pragma unroll
         for (int k = 0; k < SZ_GRID_NKINDS; ++k) acc[k] = 0.0;
-        if (mass_tot > 0) {
+        const bool cell_gone = G.n_topo > 0 && G.cell_topo[c] && !(G.cell_free[c] > 0.0);  // length(cell_poly_list) == 0, output.jl:831-834
+        if (mass_tot > 0 && !cell_gone) {
             for (int q = a + lane; q < b; q += 32) {
                 const int r = B.val_out[q];
                 const double pic = B.rec_area[r];
@@ -339,7 +425,7 @@ __global__ void k_eul_cells(Store S, EulGrid G, EulBuf B, EulOut O) {
             a2 += q1.x * q2.y - q1.y * q2.x;
             a2 += q2.x * q3.y - q2.y * q3.x;
             a2 += q3.x * q0.y - q3.y * q0.x;
-            acc[SZ_GRID_SI_FRAC] = area_tot / fabs(a2 / 2.0);
+            acc[SZ_GRID_SI_FRAC] = area_tot / (G.n_topo > 0 ? G.cell_free[c] : fabs(a2 / 2.0));
             acc[SZ_GRID_OVERAREA] = over / (double)cnt;
             acc[SZ_GRID_MASS] = mass_tot;
             acc[SZ_GRID_AREA] = area_tot;
@@ -366,7 +452,7 @@ __global__ void k_eul_cells(Store S, EulGrid G, EulBuf B, EulOut O) {
 // pass 1: count the (floe, cell) records; *n_rec is read back by the caller after a synchronisation
 void szk_eul_count(const Launch &L, const Store &S, int n_floes, int nx, int ny, const double *d_xg, const double *d_yg, double dx,
                    double dy, int *rec_count, int *rec_off) {
-    EulGrid G = {nx, ny, n_floes, d_xg, d_yg, dx, dy};
+    EulGrid G = {nx, ny, n_floes, d_xg, d_yg, dx, dy, nullptr, nullptr, 0};
     EulBuf B = {};
     B.rec_count = rec_count;
     B.rec_off = rec_off;
@@ -384,7 +470,7 @@ size_t szk_eul_sort_bytes(int n_rec) {
 
 // pass 2: records, areas, (cell, floe) sort, per-cell reduction
 int szk_eul_run(const Launch &L, const Store &S, const SzkEulArgs &A) {
-    EulGrid G = {A.nx, A.ny, A.n_floes, A.d_xg, A.d_yg, A.dx, A.dy};
+    EulGrid G = {A.nx, A.ny, A.n_floes, A.d_xg, A.d_yg, A.dx, A.dy, A.cell_free, A.cell_topo, A.n_topo};
     EulBuf B = {};
     B.rec_count = A.rec_count; B.rec_off = A.rec_off; B.n_rec = A.n_rec; B.rec_floe = A.rec_floe; B.rec_cell = A.rec_cell;
     B.rec_area = A.rec_area; B.key_in = A.key_in; B.key_out = A.key_out; B.val_in = A.val_in; B.val_out = A.val_out;
@@ -395,6 +481,10 @@ int szk_eul_run(const Launch &L, const Store &S, const SzkEulArgs &A) {
     O.data = A.d_data;
     cudaStream_t st = L.stream;
     const int ncell = A.nx * A.ny;
+    if (A.n_topo > 0) {
+        k_eul_cell_topo<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, G, L.maxv_large, L.maxx_large);
+        szk_count_launches(1);
+    }
     if (A.n_rec > 0) {
         cudaMemsetAsync(A.n_big, 0, sizeof(int), st);
         k_eul_records<true><<<sv_grid(L, A.n_floes, 128), 128, 0, st>>>(S, G, B);
@@ -420,6 +510,7 @@ int szk_services_configure(const Launch &L) {
     if (cudaFuncSetAttribute(k_eul_area, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM_C) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_pair_area_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_eul_area_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_eul_cell_topo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb) != cudaSuccess) return -1;
     return 0;
 }
 

@@ -523,7 +523,7 @@ def test_in_bounds_truth_tables(oracle_lib):  # :180-195; in_bounds(x, y, grid, 
 # configurations where a shared misreading would otherwise be invisible; the assumption is what remains unverified.
 COMB = [[[0.0, 2.7e4], [0.0, 3.5e4], [5e4, 3.5e4], [5e4, 2.7e4], [4e4, 2.7e4], [4e4, 3e4], [3e4, 3e4], [3e4, 2.7e4],
          [2e4, 2.7e4], [2e4, 3e4], [1e4, 3e4], [1e4, 2.7e4], [0.0, 2.7e4]]]
-LONG_RECT = [[[-1e4, 2.5e4], [-1e4, 2.9e4], [6e4, 2.9e4], [6e4, 2.5e4], [-1e4, 2.5e4]]]
+COMB_RECT = [[[-1e4, 2.5e4], [-1e4, 2.9e4], [6e4, 2.9e4], [6e4, 2.5e4], [-1e4, 2.5e4]]]
 
 
 def test_three_regions_are_ordered_by_first_crossing_along_polygon_one(lib):
@@ -532,7 +532,7 @@ def test_three_regions_are_ordered_by_first_crossing_along_polygon_one(lib):
     from its first vertex — the rule that the reference's own two-region answer pins (test_collisions.jl:64-81).  Walking
     the comb from (0, 2.7e4): exit at x = 0 (tooth 1), entry / exit at x = 5e4 / 4e4 (tooth 3), entry / exit at
     x = 3e4 / 2e4 (tooth 2), entry at x = 1e4 (tooth 1): regions in the order tooth 1, tooth 3, tooth 2."""
-    c, rect = Floe(COMB, 0.25), Floe(LONG_RECT, 0.25)
+    c, rect = Floe(COMB, 0.25), Floe(COMB_RECT, 0.25)
     rect.v = -0.1
     ff = host.floe_floe_interaction(c, 1, rect, 2, Constants(), 10, 0.55, backend=lib)
     r = ff.interactions[0]
@@ -586,3 +586,51 @@ def test_collinear_overlapping_edges_take_the_many_intersection_path(lib):
     assert r[0, XFORCE] == pytest.approx(-4e7 * ffac, rel=1e-12) and abs(r[0, YFORCE]) <= 1e-6 * 4e7 * ffac
     m = ff.interactions[1]
     assert len(m) == 1 and m[0, XFORCE] == -r[0, XFORCE]
+
+
+# A vertex of one ring lying EXACTLY on an edge of the other (floes cut by the domain wall, writer cells that end on the
+# wall): the two ring edges that meet in the vertex both cross the other ring's edge at that point, and the order of the
+# two coincident crossings along that edge must come from the perturbation, not from rounding — otherwise the trace walks
+# all the way round the other polygon and returns "cell + floe" (found in round 2 through the gridded output: cell areas
+# of 2.0; in the collision step the same mis-trace against a wall rectangle tagged floes of an exactly packed field for
+# removal).  Rings taken from synth.make_field(200 / 2000, scale = 1.0, collision walls).
+TOUCH_CASES = [
+    # floe ring, cell box (xmin, xmax, ymin, ymax)
+    ([[0.0, 1.1378211036468638e+04], [9.3351619109063267e+02, 1.0247514716945245e+04], [2.2737367544323206e-13, 9.5258943684869191e+03],
+      [0.0, 1.1378211036468638e+04]], (0.0, 7500.0, 7500.0, 15000.0)),
+    ([[3.6053980784869505e+04, 2.6135673163098036e+03], [3.7328998928432207e+04, 2.7849060063884131e+03],
+      [3.7461388812657264e+04, 2.7112724623584427e+03], [3.7564493061034278e+04, 2.5345229846931297e+03],
+      [3.8203156761207458e+04, 6.8212102632969618e-13], [3.4632370257829061e+04, 0.0], [3.6053980784869505e+04, 2.6135673163098036e+03]],
+     (22500.0, 45000.0, 0.0, 22500.0)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(TOUCH_CASES)))
+def test_vertex_exactly_on_the_other_rings_edge(case, lib):
+    ring, (x0, x1, y0, y1) = TOUCH_CASES[case]
+    ring = np.array(ring)
+    box = np.array([[x0, y0], [x0, y1], [x1, y1], [x1, y0], [x0, y0]])
+    a2 = np.sum(ring[:-1, 0] * ring[1:, 1] - ring[1:, 0] * ring[:-1, 1])
+    h = capi.Handle(lib)
+    for p, q in ((ring, box), (box, ring)):
+        regs, areas = h.clip_polygons(p, q)
+        assert len(regs) == 1 and areas[0] == pytest.approx(abs(a2) / 2, rel=1e-12)   # the floe lies inside the box
+    h.close()
+
+
+def test_exactly_packed_field_touches_the_walls_without_overlap(lib):
+    """Voronoi cells cut by the collision walls (scale 1.0: the floes tile the domain exactly, vertices ON the walls): no
+    wall contact, nobody removed or fused, and the gridded area of a writer grid that ends on the walls is the domain's."""
+    from subzero_jl_b200 import synth
+    for n in (200, 2000):
+        f = synth.make_field(n, scale=1.0, walls="collision", npoints=10, cache=False)
+        h = synth.setup_handle(f, lib)
+        st0 = f.floes.status_tag.copy()
+        h.step_collisions()
+        fa = h.download_floes(mc=False)
+        offs, rows = h.interactions()
+        assert np.array_equal(fa.status_tag, st0) and not (rows[:, 0] < 0).any()
+        xg = np.linspace(0.0, f.L, 5)
+        d = h.eulerian_data(xg, xg, [capi.GRID_OUTPUTS.index("area_grid"), capi.GRID_OUTPUTS.index("si_frac_grid")])
+        assert d[..., 0].sum() == pytest.approx(f.L ** 2, rel=1e-12) and d[..., 1].max() < 1.0 + 1e-9
+        h.close()

@@ -182,16 +182,71 @@ def topo_field():
     return f
 
 
-def test_oracle_eulerian_topography_is_refused(oracle_lib):
+def hand_topo_case(lib):
+    """Hand-computed: grid of 2 x 1 cells of 10 km; topography = the right half of cell A, [5, 10] x [0, 10] km; one floe
+    [2, 12] x [4, 6] km (20 km^2).  Cell A: the floe's piece [2, 10] x [4, 6] = 16 km^2, of which [5, 10] x [4, 6] = 10 km^2 lie
+    under the topography -> 6 km^2 on a free cell area of 50 km^2 (output.jl:826-846: cell_poly_list = cell minus
+    topography); cell B: 4 km^2 on 100 km^2.  A second set-up covers cell A completely: every output of A is 0 (:831-834)."""
+    km = 1e3
+    grid = host.RegRectilinearGrid(0.0, 20 * km, 0.0, 10 * km, dx=10 * km, dy=10 * km)
+    floe = host.Floe([[[2 * km, 4 * km], [2 * km, 6 * km], [12 * km, 6 * km], [12 * km, 4 * km], [2 * km, 4 * km]]], 0.5, 0.0,
+                     rng=np.random.default_rng(1))
+    floe.u, floe.v = 0.3, -0.1
+    out = {}
+    for name, topo_ring in (("half", [[5 * km, 0.0], [5 * km, 10 * km], [10 * km, 10 * km], [10 * km, 0.0], [5 * km, 0.0]]),
+                            ("all", [[-1 * km, -1 * km], [-1 * km, 11 * km], [10 * km, 11 * km], [10 * km, -1 * km], [-1 * km, -1 * km]])):
+        topo = host.initialize_topography_field([[topo_ring]])
+        dom = host.Domain(*[host.OpenBoundary(d, grid) for d in (host.North, host.South, host.East, host.West)], topography=topo)
+        h = capi.Handle(lib)
+        h.set_grid(grid.Nx, grid.Ny, grid.x0, grid.xf, grid.y0, grid.yf)
+        dom.push(h)
+        ff = host.FloeField([floe])
+        h.upload_floes(ff)
+        kinds = [capi.GRID_OUTPUTS.index(k) for k in ("area_grid", "si_frac_grid", "mass_grid", "u_grid", "v_grid")]
+        out[name] = (h.eulerian_data(np.array([0.0, 10 * km, 20 * km]), np.array([0.0, 10 * km]), kinds), float(ff.mass[0]))
+        h.close()
+    d, mass = out["half"]
+    assert d[0, 0, 0] == pytest.approx(6e6, rel=1e-12) and d[1, 0, 0] == pytest.approx(4e6, rel=1e-12)
+    assert d[0, 0, 1] == pytest.approx(6e6 / 50e6, rel=1e-12) and d[1, 0, 1] == pytest.approx(0.04, rel=1e-12)
+    assert d[0, 0, 2] == pytest.approx(mass * 6 / 20, rel=1e-12) and d[1, 0, 2] == pytest.approx(mass * 4 / 20, rel=1e-12)
+    assert d[0, 0, 3] == pytest.approx(0.3, rel=1e-12) and d[1, 0, 4] == pytest.approx(-0.1, rel=1e-12)  # one floe: its own velocity
+    d, mass = out["all"]
+    assert np.all(d[0, 0, :] == 0.0)
+    assert d[1, 0, 0] == pytest.approx(4e6, rel=1e-12) and d[1, 0, 1] == pytest.approx(0.04, rel=1e-12)
+
+
+def test_oracle_eulerian_topography_hand_case(oracle_lib):
+    hand_topo_case(oracle_lib)
+
+
+def test_oracle_eulerian_topography_conserves_the_ice_outside_the_land(oracle_lib):
+    """Voronoi field with two floes' rings turned into topography: the gridded area is the floe area minus what lies under
+    the land, and never exceeds the free cell area."""
     f = topo_field()
     h = synth.setup_handle(f, oracle_lib)
-    with pytest.raises(capi.SubzeroError):
-        h.eulerian_data(np.linspace(0, f.L, 3), np.linspace(0, f.L, 3), [0])
+    xg = yg = np.linspace(0.0, f.L, 5)
+    d = h.eulerian_data(xg, yg, [capi.GRID_OUTPUTS.index("area_grid"), capi.GRID_OUTPUTS.index("si_frac_grid")])
+    h0 = synth.setup_handle(synth.make_field(200, scale=1.0, walls="collision", npoints=10, cache=False), oracle_lib)
+    d0 = h0.eulerian_data(xg, yg, [capi.GRID_OUTPUTS.index("area_grid"), capi.GRID_OUTPUTS.index("si_frac_grid")])
+    assert d[..., 0].sum() < d0[..., 0].sum() and d[..., 0].sum() > 0.95 * d0[..., 0].sum()   # a 4 km x 4 km island in 28 km x 28 km
+    assert np.all(d[..., 1] <= 1.0 + 1e-9) and np.all(d[..., 0] <= d0[..., 0] + 1e-6)
 
 
 @pytest.mark.gpu
-def test_eulerian_data_topography_is_refused(product_lib):
+def test_eulerian_data_topography_hand_case_cuda(product_lib):
+    hand_topo_case(product_lib)
+
+
+@pytest.mark.gpu
+def test_eulerian_data_with_topography_matches_oracle(product_lib, oracle_lib):
     f = topo_field()
-    h = synth.setup_handle(f, product_lib)
-    with pytest.raises(capi.SubzeroError):
-        h.eulerian_data(np.linspace(0, f.L, 3), np.linspace(0, f.L, 3), [0])
+    fields.perturb_state(f.floes)
+    hg, ho = synth.setup_handle(f, product_lib), synth.setup_handle(f, oracle_lib)
+    for h in (hg, ho):
+        h.step(0, True)
+    for dims in ((4, 4), (9, 7), (28, 28)):
+        xg, yg = np.linspace(0.0, f.L, dims[0] + 1), np.linspace(0.0, f.L, dims[1] + 1)
+        dg, do = hg.eulerian_data(xg, yg, KINDS), ho.eulerian_data(xg, yg, KINDS)
+        for k, name in enumerate(capi.GRID_OUTPUTS):
+            assert grid_err(dg, do, k) < TOL, (dims, name)
+        assert np.array_equal(dg[..., 7] > 0, do[..., 7] > 0)
