@@ -167,3 +167,80 @@ def test_synth_generator_properties():
         m = host.points_in_ring(fa.mc_x[fa.mc_offsets[i]:fa.mc_offsets[i + 1]],
                                 fa.mc_y[fa.mc_offsets[i]:fa.mc_offsets[i + 1]], r - fa.centroid(i))
         assert m.all()
+
+
+# ---- find_interp_knots (coupling.jl:702-797): the knot window never changes a bilinear result ------------------------------
+def find_interp_knots(point_idx, ncells, glines, L, dd, periodic):
+    """Python restatement of both methods (1-based indices like the reference)."""
+    glines = np.asarray(glines, dtype=float)
+    lo, hi = min(point_idx) - (dd + 1), max(point_idx) + (dd + 1)
+    if not periodic:
+        lo, hi = max(lo, 1), min(hi, ncells + 1)
+        idx = np.arange(lo, hi + 1)
+        return glines[idx - 1], idx
+    low = np.arange(0)
+    high = np.arange(0)
+    if lo < 1 and hi > ncells:
+        low, high, inb = np.arange(lo + ncells, ncells + 1), np.arange(1, hi - ncells + 1), np.arange(1, ncells + 1)
+    elif lo < 1:
+        low, inb = np.arange(lo + ncells, ncells + 1), np.arange(1, hi + 1)
+    elif hi > ncells:
+        high, inb = np.arange(1, hi - ncells + 1), np.arange(lo, ncells + 1)
+    else:
+        inb = np.arange(lo, hi + 1)
+    idx = np.concatenate([low, inb, high])
+    knots = np.concatenate([glines[low - 1] - L, glines[inb - 1], glines[high - 1] + L])
+    return knots, idx
+
+
+def test_find_interp_knots_reference_values():
+    """test_coupling.jl:197-274, all nine cases."""
+    g = np.arange(0.0, 81.0, 10.0)
+    r = lambda a, b, c=1: np.arange(a, b + (1 if c > 0 else -1), c)
+    cases = [
+        ([4], 2, False, r(0, 60, 10), r(1, 7)), ([4], 2, True, r(0, 60, 10), r(1, 7)),
+        ([0, 1], 2, False, r(0, 30, 10), r(1, 4)), ([0, 1], 2, True, r(-40, 30, 10), np.concatenate([r(5, 8), r(1, 4)])),
+        ([8, 9], 1, False, r(50, 80, 10), r(6, 9)), ([8, 9], 1, True, r(50, 100, 10), np.concatenate([r(6, 8), r(1, 3)])),
+        (list(range(1, 9)), 2, False, r(0, 80, 10), r(1, 9)),
+        (list(range(1, 9)), 2, True, r(-30, 100, 10), np.concatenate([r(6, 8), r(1, 8), r(1, 3)])),
+        (list(range(0, 10)), 2, False, r(0, 80, 10), r(1, 9)),
+    ]
+    for pidx, dd, per, knots, kidx in cases:
+        k, i = find_interp_knots(pidx, 8, g, 80.0, dd, per)
+        assert np.array_equal(k, knots) and np.array_equal(i, kidx), (pidx, dd, per)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_knot_buffer_does_not_change_the_bilinear_result(periodic):
+    """mc_interpolation (coupling.jl:845-902) interpolates on the window of knots around the floe; the library (and the
+    oracle) interpolate on the full grid, wrapping periodic axes on lines 1..N.  For every buffer dd in {0, 1, 3} the
+    windowed result equals the full-grid one exactly — which is why sz_config.coupling_dd is carried but not used."""
+    rng = np.random.default_rng(5)
+    N, dx = 8, 10.0
+    g = np.arange(0.0, N * dx + 1, dx)
+    field = rng.normal(size=N + 1)
+    if periodic:
+        field[N] = field[0]  # the reference never reads line N+1 on a periodic axis; make the comparison well defined
+    xs = rng.uniform(-15.0, 95.0, 400) if periodic else rng.uniform(0.0, 80.0, 400)
+
+    def full(x):
+        gx = (x - g[0]) / dx
+        i0 = int(np.floor(gx))
+        w = gx - i0
+        if periodic:
+            a, b = i0 % N, (i0 + 1) % N
+        else:
+            if i0 >= N:
+                i0, w = N - 1, 1.0
+            a, b = i0, i0 + 1
+        return field[a] + w * (field[b] - field[a])
+
+    for dd in (0, 1, 3):
+        for x in xs:
+            nearest = int(np.floor((x - g[0]) / dx + 0.5)) + 1  # find_center_cell_index-style nearest grid line, 1-based
+            knots, idx = find_interp_knots([nearest], N, g, N * dx, dd, periodic)
+            vals = field[idx - 1]
+            k = np.searchsorted(knots, x, side="right") - 1
+            k = min(max(k, 0), len(knots) - 2)
+            w = (x - knots[k]) / (knots[k + 1] - knots[k])
+            assert abs((vals[k] + w * (vals[k + 1] - vals[k])) - full(x)) < 1e-12, (dd, x)
