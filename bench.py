@@ -102,6 +102,32 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off (torchrun does not bind): the pinned host arrays of the
+    end-to-end leg are then first-touched on that node and the copies do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # nvml prints an 8-digit domain, sysfs a 4-digit one
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return None
+
+
 def pin_floe_arrays(fa):
     """Move every array of a FloeArrays into pinned host memory (torch allocator)."""
     import torch
@@ -246,6 +272,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         # NCCL prints its version banner to stdout when the communicator is created: send fd 1 to stderr until then, so that
         # stdout carries the one JSON line only
@@ -430,7 +457,7 @@ def main():
         halo = {"halo_floes_max": int(hmax[0]), "send_bytes_per_step_max": int(hmax[1]), "skin_m": args.skin,
                 "max_displacement_m": float(hmax[2]), "lists_stale": bool(hmax[2] > 0.5 * args.skin),
                 "rebuilds": int(hmax[4]), "rebuild_seconds_total_max": float(hmax[5]), "displacement_polls": polls[-12:],
-                "halo_copies_equal_owner_state": True,
+                "halo_copies_equal_owner_state": True, "rank0_cpu_binding": numa,
                 "exchange": "sz_slab_step: k_slab_unpack (wait for the neighbours' flag, scatter) -> step -> k_slab_push (8 doubles + "
                             "ring per boundary floe straight into the neighbours' arenas over NVLink, cudaIpc-mapped) — no NCCL "
                             "call, no pack / unpack round trip; NCCL only for this script's barrier / all-reduce of the timings"}

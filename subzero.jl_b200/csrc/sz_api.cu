@@ -1341,7 +1341,10 @@ static int32_t step_enqueue_direct(sz_handle *h) {
                 forked = true;
             }
             // (host arrays every step: step_setup has already published what the host uploaded)
-            if (io) CK(cudaStreamWaitEvent(st, h->ev_up[3], 0));  // the halo update lands on top of the uploaded (stale) copies
+            // the halo update lands on top of the uploaded (stale) copies: everything it overwrites (centroid, velocities,
+            // status, height, alpha, rings) is in upload groups 0-2; group 3 (17 MB of AB2 history and tensors) may still be
+            // in flight
+            if (io) CK(cudaStreamWaitEvent(st, h->ev_up[2], 0));
             slab_unpack(h);
         }
         if (!cur.keep_ghosts) enqueue_ghosts(h);
@@ -1541,7 +1544,7 @@ static int32_t step_setup(sz_handle *h, int32_t do_coupling, const HostIO *io, b
     // host arrays: what the host uploaded is what the neighbours must see.  Device-resident: the previous step published
     // behind its update — unless that step ran on host arrays (or this is the first step after a refresh-less rebuild)
     if (h->slab.on && (slab_host_mode || h->slab.pushed < h->slab.epoch)) {
-        if (io && io->in) CK(cudaStreamWaitEvent(h->L.stream, h->ev_up[3], 0));
+        if (io && io->in) CK(cudaStreamWaitEvent(h->L.stream, h->ev_up[2], 0));  // what k_slab_push reads is in groups 0-2
         slab_push(h, h->slab.epoch);
         h->slab.pushed = h->slab.epoch;
     }
