@@ -202,6 +202,12 @@ int32_t SZ_FN(step)(sz_handle *h, int64_t tstep, int32_t do_coupling);
  * and, when do_coupling != 0, fxOA / fyOA / trqOA / hflx_factor (coupling.jl:1583-1586). */
 int32_t SZ_FN(step_host)(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in,
                          sz_floe_soa *out);
+/* sz_step_host for a shim that knows which fields its host processes touched this step (simulation.jl:121-214: most steps
+ * none of them runs): a NULL pointer in `in` KEEPS the device-resident value of that field (sz_step_host zero-fills it;
+ * vert_xy NULL = the rings did not change on the host), a NULL pointer in `out` skips that download.  in == NULL: nothing
+ * is uploaded at all.  Same results as sz_step_host for the fields that are exchanged. */
+int32_t SZ_FN(step_host_partial)(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in,
+                                 sz_floe_soa *out);
 /* The upload half of sz_step_host on its own, for a slab rank: sz_upload_state_begin(in) enqueues the uploads and
  * returns at once, the halo exchange follows (sz_halo_pack_on waits on the device for the uploads, so the halo
  * update lands on top of the uploaded copies), then sz_step_host(h, tstep, do_coupling, NULL, out) runs the step

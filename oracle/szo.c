@@ -1451,6 +1451,42 @@ int32_t szo_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
 
 /* the host-buffer form of the timestep: no overlap to exploit on the CPU, the three calls back to back */
 /* an overlap hint for the CUDA product; the oracle's step does its coupling in order */
+/* sz_step_host_partial: NULL input fields keep the resident value, NULL output fields are not written */
+int32_t szo_step_host_partial(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
+    if (!h || !out) return SZ_ERR_INVALID;
+    if (in) {
+        if (in->n != h->n || in->n_init != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host_partial: floe count differs from the resident store");
+#define UP(src, dst) if (in->src) for (int64_t i = 0; i < h->n; ++i) h->dst[i] = in->src[i];
+        UP(centroid_x, cx) UP(centroid_y, cy) UP(height, height) UP(area, area) UP(mass, mass) UP(rmax, rmax) UP(moment, moment)
+        UP(alpha, alpha) UP(u, u) UP(v, v) UP(xi, xi) UP(overarea, overarea) UP(p_dxdt, p_dxdt) UP(p_dydt, p_dydt) UP(p_dudt, p_dudt)
+        UP(p_dvdt, p_dvdt) UP(p_dxidt, p_dxidt) UP(p_dalphadt, p_dalphadt) UP(status_tag, status)
+        if (!do_coupling) { UP(fxOA, fxOA) UP(fyOA, fyOA) UP(trqOA, trqOA) UP(hflx_factor, hflx) }
+#undef UP
+        for (int64_t i = 0; i < h->n; ++i)
+            for (int k = 0; k < 4; ++k) {
+                if (in->stress_accum) h->stress_accum[4 * i + k] = in->stress_accum[4 * i + k];
+                if (in->stress_instant) h->stress_instant[4 * i + k] = in->stress_instant[4 * i + k];
+                if (in->strain) h->strain[4 * i + k] = in->strain[4 * i + k];
+            }
+        if (in->vert_xy) {
+            int64_t vo = 0;
+            for (int64_t i = 0; i < h->n; ++i) {
+                memcpy(h->ring[i], in->vert_xy + 2 * vo, sizeof(szo_pt) * (size_t)h->npts[i]);
+                vo += h->npts[i];
+            }
+        }
+    }
+    int32_t rc = szo_step(h, tstep, do_coupling);
+    if (rc != SZ_OK) return rc;
+    sz_floe_soa o = *out;
+    o.mc_x = o.mc_y = NULL;
+    o.ghost_index = NULL;
+    rc = szo_download_floes(h, &o);
+    out->n = o.n;
+    out->n_init = o.n_init;
+    return rc;
+}
+
 int32_t szo_coupling_begin(sz_handle *h) { return h ? SZ_OK : SZ_ERR_INVALID; }
 int32_t szo_upload_state_begin(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in) {
     (void)do_coupling;

@@ -117,6 +117,7 @@ class Library:
         "step_floe_properties": (C.c_int32, [C.c_void_p, C.c_int64]),
         "step": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32]),
         "step_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(FloeSoA), C.POINTER(FloeSoA)]),
+        "step_host_partial": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(FloeSoA), C.POINTER(FloeSoA)]),
         "upload_state_begin": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FloeSoA)]),
         "coupling_begin": (C.c_int32, [C.c_void_p]),
         "get_interactions": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
@@ -440,6 +441,22 @@ class Handle:
         o = s if out is None or out is fa else out.as_struct()
         self._ck(self.lib.step_host(self.h, tstep, 1 if do_coupling else 0, C.byref(s), C.byref(o)))
         return fa if out is None else out
+
+    def step_host_partial(self, fa, tstep=0, do_coupling=True, upload=(), download=()):
+        """One timestep exchanging only the named fields with the host arrays `fa` (FloeSoA field names): the others keep
+        their device-resident values / are not downloaded."""
+        def masked(names):
+            full = fa.as_struct()
+            m = FloeSoA()
+            m.n, m.n_init = full.n, full.n_init
+            for name in names:
+                setattr(m, name, getattr(full, name))
+            m._keep = full
+            return m
+        i = masked(upload) if upload else None
+        o = masked(download)
+        self._ck(self.lib.step_host_partial(self.h, tstep, 1 if do_coupling else 0, C.byref(i) if i is not None else None, C.byref(o)))
+        return fa
 
     def coupling_begin(self):
         """Slab ranks: start the coming step's one-way coupling before the halo exchange (no-op where the order matters)."""

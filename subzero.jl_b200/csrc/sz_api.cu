@@ -75,6 +75,7 @@ struct StepCur {
     bool keep_ghosts;       // repeat from the collisions, the ghosts of the failed attempt stay
     bool coupling_only;     // repeat from the (two-way) coupling: the collisions of this step are complete
     bool slab_host_mode;    // slab rank stepping on host arrays: publish at the start, not behind the update
+    bool partial;           // sz_step_host_partial: NULL input fields keep their device-resident values
     int attempt;
 };
 
@@ -104,6 +105,7 @@ struct sz_handle {
     double2 *rb_extra;
     long long *rb_src;
     long long rb_extra_cap, rb_src_cap;
+    bool next_partial;              // the step being set up is a sz_step_host_partial
     unsigned long long tables_gen;  // finish_host_tables: the offset tables were last written for this floe list ...
     const void *tables_ptr[3];      // ... into these caller arrays
     long long tables_mid[2];
@@ -402,6 +404,7 @@ extern "C" int32_t sz_create(const sz_config *cfg, sz_handle **out) {
     h->mc_spare_cap = h->mc_off_cap = 0;
     h->rb_tx = h->rb_ty = nullptr; h->rb_extra = nullptr; h->rb_src = nullptr;
     h->rb_extra_cap = h->rb_src_cap = 0;
+    h->next_partial = false;
     h->tables_gen = 0;
     h->tables_ptr[0] = h->tables_ptr[1] = h->tables_ptr[2] = nullptr;
     h->graph_max_floes = getenv("SZ_GRAPH_MAX_FLOES") ? atoi(getenv("SZ_GRAPH_MAX_FLOES")) : SZ_GRAPH_MAX_FLOES;
@@ -1221,12 +1224,13 @@ extern "C" int32_t sz_step_floe_properties(sz_handle *h, int64_t tstep) {
 // The downloads go to stream_dn as soon as the producing kernel is done (collision totals after the row
 // assembly, coupling outputs after the join, the rest after the update).
 
-static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s, bool coupling_runs) {
+static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s, bool coupling_runs, bool partial = false) {
     Store &S = h->S;
     const int n = h->n_total;
     cudaStream_t st = h->stream_up;
     auto up = [&](double *dst, const double *src, size_t w) -> cudaError_t {
         if (src) return cudaMemcpyAsync(dst, src, sizeof(double) * w * n, cudaMemcpyHostToDevice, st);
+        if (partial) return cudaSuccess;  // sz_step_host_partial: the device-resident value stands
         return cudaMemsetAsync(dst, 0, sizeof(double) * w * n, st);
     };
     CK(cudaEventRecord(h->ev_up_start, st));
@@ -1239,7 +1243,7 @@ static int32_t enqueue_uploads(sz_handle *h, const sz_floe_soa *s, bool coupling
     if (s->status_tag) CK(cudaMemcpyAsync(S.status, s->status_tag, sizeof(int) * n, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(h->ev_up[1], st));
     // group 2
-    if (h->n_verts > 0) CK(cudaMemcpyAsync(S.verts, s->vert_xy, sizeof(double2) * (size_t)h->n_verts, cudaMemcpyHostToDevice, st));
+    if (h->n_verts > 0 && s->vert_xy) CK(cudaMemcpyAsync(S.verts, s->vert_xy, sizeof(double2) * (size_t)h->n_verts, cudaMemcpyHostToDevice, st));
     CK(up(S.height, s->height, 1));
     CK(cudaEventRecord(h->ev_up[2], st));
     // group 3
@@ -1535,11 +1539,16 @@ static int32_t step_setup(sz_handle *h, int32_t do_coupling, const HostIO *io, b
     if (io) cur.io = *io;
     cur.keep_ghosts = cur.coupling_only = false;
     cur.slab_host_mode = slab_host_mode;
+    cur.partial = h->next_partial;
+    h->next_partial = false;
     cur.attempt = 0;
     if (h->slab.on && slab_host_mode && h->slab.pushed >= h->slab.epoch) h->slab.epoch = h->slab.pushed + 1;  // a fresh epoch for the re-publication
     if (io && io->in) {
-        int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0);
+        int32_t rc = enqueue_uploads(h, io->in, do_coupling != 0, cur.partial);
         if (rc) return rc;
+    } else if (io && cur.partial) {  // nothing to upload: the events the kernels wait for are recorded at once
+        CK(cudaEventRecord(h->ev_up_start, h->stream_up));
+        for (int g = 0; g < 4; ++g) CK(cudaEventRecord(h->ev_up[g], h->stream_up));
     }
     // host arrays: what the host uploaded is what the neighbours must see.  Device-resident: the previous step published
     // behind its update — unless that step ran on host arrays (or this is the first step after a refresh-less rebuild)
@@ -1686,6 +1695,36 @@ extern "C" int32_t sz_step_host(sz_handle *h, int64_t tstep, int32_t do_coupling
     if (rc) return rc;
     HostIO io = {in, out};
     rc = step_impl(h, do_coupling, &io);
+    if (rc) {
+        cudaStreamSynchronize(h->stream_up);
+        cudaStreamSynchronize(h->stream_dn);
+        return rc;
+    }
+    finish_host_tables(h, out);
+    return SZ_OK;
+}
+
+extern "C" int32_t sz_step_host_partial(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
+    (void)tstep;
+    if (!h || !out) return SZ_ERR_INVALID;
+    if (h->slab.on) return fail(h, SZ_ERR_INVALID, "this handle is a slab rank: step it with sz_slab_step_host");
+    if (!h->have_domain || !h->have_floes) return fail(h, SZ_ERR_INVALID, "step_host_partial before set_domain/upload_floes");
+    if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step_host_partial with coupling before set_fields");
+    if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host_partial with ghosts present (call remove_ghosts)");
+    if (h->up_pending || h->cpl_prelaunched) return fail(h, SZ_ERR_INVALID, "step_host_partial: an upload or a coupling of the split calls is pending");
+    if (in && (in->n != h->n_total || in->n_init != h->n_init)) return fail(h, SZ_ERR_INVALID, "step_host_partial: floe count differs from the resident store");
+    if ((int)h->h_vcount.size() != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host_partial: no ring table of the resident floes");
+    cudaSetDevice(h->cfg.device);
+    const int n = h->n_init;
+    if (h->cf_cap < n) {
+        dfree(h->d_cf_dn);
+        CK(dalloc(&h->d_cf_dn, (size_t)n));
+        h->cf_cap = n;
+    }
+    HostIO io = {in, out};
+    h->next_partial = true;
+    int32_t rc = step_impl(h, do_coupling, &io);
+    h->next_partial = false;
     if (rc) {
         cudaStreamSynchronize(h->stream_up);
         cudaStreamSynchronize(h->stream_dn);

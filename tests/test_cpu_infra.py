@@ -244,3 +244,38 @@ def test_knot_buffer_does_not_change_the_bilinear_result(periodic):
             k = min(max(k, 0), len(knots) - 2)
             w = (x - knots[k]) / (knots[k + 1] - knots[k])
             assert abs((vals[k] + w * (vals[k + 1] - vals[k])) - full(x)) < 1e-12, (dd, x)
+
+
+def check_step_host_partial(lib):
+    """sz_step_host_partial: only the named fields cross the boundary; the others keep their device-resident values.
+    Same bits as the device-resident sz_step (nothing uploaded) and as sz_step_host (a host edit of u and the status)."""
+    f = synth.make_field(600, scale=1.01, walls="periodic", npoints=40, cache=False)
+    fields.perturb_state(f.floes)
+    ha, hb = synth.setup_handle(f, lib), synth.setup_handle(f, lib)
+    fb = hb.download_floes(mc=False)
+    down = ("centroid_x", "centroid_y", "alpha", "u", "v", "xi", "collision_force", "collision_trq", "status_tag", "fxOA")
+    for t in range(2):
+        ha.step(t, True)
+        hb.step_host_partial(fb, t, True, upload=(), download=down)
+    fa = ha.download_floes(mc=False)
+    for name in down:
+        assert np.array_equal(getattr(fa, name), getattr(fb, name)), name
+    # a host process edits u and tags a floe: only those two fields go up
+    fa_full = ha.download_floes(mc=False)
+    fa_full.u[:50] *= 0.5
+    fa_full.status_tag[3] = capi.STATUS_REMOVE
+    fb.u[:50] *= 0.5
+    fb.status_tag[3] = capi.STATUS_REMOVE
+    ha.step_host(fa_full, 2, True)
+    hb.step_host_partial(fb, 2, True, upload=("u", "status_tag"), download=down)
+    for name in down:
+        assert np.array_equal(getattr(fa_full, name), getattr(fb, name)), name
+
+
+def test_step_host_partial_oracle(oracle_lib):
+    check_step_host_partial(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_step_host_partial_cuda(product_lib):
+    check_step_host_partial(product_lib)
