@@ -354,11 +354,16 @@ def main():
     phase = np.zeros(8)
     launches = 0
     t0 = time.perf_counter()
+    step_wall = np.zeros(args.steps)
+    tp = t0
     for t in range(args.steps):
         do_step(args.warmup + t)
         ms = h.timings_raw()
         phase += ms
         launches += int(ms[7])
+        tn = time.perf_counter()
+        step_wall[t] = tn - tp
+        tp = tn
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -564,6 +569,8 @@ def main():
         "contacts_per_s": steps_per_s * c["n_overlap"] * world, "candidate_pairs_per_s": steps_per_s * c["n_candidates"] * world,
         "mc_points_per_s": steps_per_s * M * world, "parity": parity,
         "device_ms_per_step": 1e3 * dev_max / args.steps,
+        "step_wall_ms_rank0": {"p50": 1e3 * float(np.percentile(step_wall, 50)), "p90": 1e3 * float(np.percentile(step_wall, 90)),
+                               "p99": 1e3 * float(np.percentile(step_wall, 99)), "max": 1e3 * float(step_wall.max())},
         "counts": {k: c[k] for k in ("n_init", "n_candidates", "n_pairs", "n_overlap", "n_rows", "n_mc", "n_vertices")},
         "halo": halo, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -1468,6 +1468,7 @@ static int32_t step_finish(sz_handle *h) {
         Counters c = *h->h_cnt;
         h->n_total = c.n_total;
         h->n_verts = c.n_verts;
+        if (getenv("SZ_DEBUG_RETRY")) fprintf(stderr, "[dev %d] step repeated: error bits 0x%x (attempt %d)\n", h->cfg.device, c.error, cur.attempt);
         if (cur.attempt >= 6) return fail(h, SZ_ERR_CAPACITY, "step: capacity retry limit");
         int32_t rc = handle_overflow(h, c);
         if (rc) return rc;
