@@ -1579,18 +1579,32 @@ __global__ void k_neighbours2(Store S, StepBuf B) {
         const int i = (int)__double_as_longlong(me1.y);
         const double xi = me0.x, yi = me0.y, ri = me1.x;
         int up = 0, low = 0, ub = 0, lb = 0, db = 0;
-        bool research = true;
+        bool research = true, sorted = false;
         if (WRITE) {
             ub = B.up_off[i];
             lb = B.low_off[i];
             db = B.dom_off[i];
             const int tot = (B.up_off[i + 1] - ub) + (B.low_off[i + 1] - lb);
             if (tot <= NB_K) {
+                // sorted in thread-local storage (one sort of the whole list: j < i first, then j > i), stored once
                 research = false;
+                sorted = true;
+                int nb[NB_K];
                 for (int k = 0; k < tot; ++k) {
-                    const int j = B.nb_scratch[(size_t)k * cap + t];
-                    if (j > i) B.pair_j[ub + up++] = j;
-                    else B.low_pair[lb + low++] = j;
+                    const int v = B.nb_scratch[(size_t)k * cap + t];
+                    int b = k - 1;
+                    while (b >= 0 && nb[b] > v) {
+                        nb[b + 1] = nb[b];
+                        --b;
+                    }
+                    nb[b + 1] = v;
+                }
+                low = B.low_off[i + 1] - lb;
+                up = tot - low;
+                for (int k = 0; k < low; ++k) B.low_pair[lb + k] = nb[k];
+                for (int k = 0; k < up; ++k) {
+                    B.pair_j[ub + k] = nb[low + k];
+                    B.pair_i[ub + k] = i;
                 }
             }
         }
@@ -1642,7 +1656,7 @@ __global__ void k_neighbours2(Store S, StepBuf B) {
             B.low_count[i] = low;
             B.dom_count[i] = dc;
             if (checks) atomicAdd(&cnt->n_domchecks, checks);
-        } else {
+        } else if (!sorted) {
             // ascending j (own pairs) and ascending i (mirrored rows): the reference's loop order
             for (int a = 1; a < up; ++a) {
                 int v = B.pair_j[ub + a], b = a - 1;
