@@ -347,6 +347,9 @@ def main():
     # ---- device-resident throughput ---------------------------------------------------------------
     for t in range(args.warmup):
         do_step(t)
+    if world > 1:  # the collectives the timed region uses (displacement poll) have run once before it starts
+        d = torch.zeros(1, dtype=torch.float64, device="cuda")
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -374,6 +377,11 @@ def main():
     if world > 1:
         dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
     wall_max, dev_max = float(t_rank[0]), float(t_rank[1])
+    wall_ranks = [wall]
+    if world > 1:
+        g = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor([wall], dtype=torch.float64, device="cuda"))
+        wall_ranks = [float(x[0]) for x in g]
     steps_per_s = args.steps / wall_max
     norm = N * world / NORM_FLOES
     value = steps_per_s * norm
@@ -417,21 +425,30 @@ def main():
         e2e_sps = time_e2e(True)
         # the same loop for a shim that knows what its host processes touched (sz_step_host_partial): here an observer that
         # tags floes and reads positions, velocities and forces every step — reported BESIDE the all-fields number
-        masked = None
-        if sl is None:
-            up_f, dn_f = ("status_tag",), ("centroid_x", "centroid_y", "alpha", "u", "v", "xi", "collision_force", "collision_trq",
-                                          "fxOA", "fyOA", "trqOA", "status_tag")
-            for t in range(3):
+        up_f, dn_f = ("status_tag",), ("centroid_x", "centroid_y", "alpha", "u", "v", "xi", "collision_force", "collision_trq",
+                                      "fxOA", "fyOA", "trqOA", "status_tag")
+
+        def masked_step(t):
+            if sl is not None:
+                sl.step_host_partial([host_fa], t, True, upload=up_f, download=dn_f)
+            else:
                 h.step_host_partial(host_fa, t, True, upload=up_f, download=dn_f)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            ne = max(3, min(args.steps, 20))
-            for t in range(ne):
-                h.step_host_partial(host_fa, t, True, upload=up_f, download=dn_f)
-            masked = {"value": ne / (time.perf_counter() - t0) * norm, "unit": "steps/s",
-                      "h2d_bytes_per_step": int(sum(getattr(host_fa, k).nbytes for k in up_f)),
-                      "d2h_bytes_per_step": int(sum(getattr(host_fa, k).nbytes for k in dn_f)),
-                      "upload": list(up_f), "download": list(dn_f)}
+
+        for t in range(3):
+            masked_step(t)
+        barrier()
+        t0 = time.perf_counter()
+        ne = max(3, min(args.steps, 20))
+        for t in range(ne):
+            masked_step(t)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        masked = {"value": ne / float(te[0]) * norm, "unit": "steps/s", "steps_per_s": ne / float(te[0]),
+                  "h2d_bytes_per_step": int(sum(getattr(host_fa, k).nbytes for k in up_f)),
+                  "d2h_bytes_per_step": int(sum(getattr(host_fa, k).nbytes for k in dn_f)),
+                  "upload": list(up_f), "download": list(dn_f)}
         e2e = {"value": e2e_sps * norm, "unit": "steps/s", "steps_per_s": e2e_sps,
                "h2d_bytes_per_step": int(h2d_fused), "d2h_bytes_per_step": int(d2h),
                "call": ("sz_step_host on pinned host arrays (upload of every per-floe input scalar + rings, step, download "
@@ -439,9 +456,12 @@ def main():
                         "sz_slab_step_host on pinned host arrays of every rank's local list (uploads, publication of the "
                         "uploaded boundary floes to the neighbours, step, overlapped downloads)"),
                "separate_calls_steps_per_s": sep, "masked": masked,
-               "floor": "PCIe: the 33 MB that only exist after the state update leave in 0.8 ms (41 GB/s measured) behind 1.13 ms of "
-                        "kernels that cannot start before the first upload group has landed (0.16 ms): 2.1 ms = 475 steps/s is the "
-                        "floor of an all-fields synchronous step on this box (profiles/README.md)"}
+               "floor": ("PCIe: the 33 MB that only exist after the state update leave in 0.8 ms (41 GB/s measured) behind 1.13 ms of "
+                         "kernels that cannot start before the first upload group has landed (0.16 ms): 2.1 ms = 475 steps/s is the "
+                         "floor of an all-fields synchronous step on this box (profiles/README.md)" if world == 1 else
+                         "host bandwidth: with 8 ranks copying at once this box gives each rank 17-23 GB/s (88 GB/s alone; "
+                         "tools/pcie_concurrency.py, profiles/r2/r3a_pcie_n8.json): the 79 MB of an all-fields step take 3.7-5.0 ms "
+                         "whatever the library does; `masked` (10 MB per step) is what a shim that names its fields gets")}
 
     # ---- parity of the benchmark field against the oracle (one step, after the timed region) --------------------
     parity = None
@@ -572,7 +592,7 @@ def main():
         "step_wall_ms_rank0": {"p50": 1e3 * float(np.percentile(step_wall, 50)), "p90": 1e3 * float(np.percentile(step_wall, 90)),
                                "p99": 1e3 * float(np.percentile(step_wall, 99)), "max": 1e3 * float(step_wall.max())},
         "counts": {k: c[k] for k in ("n_init", "n_candidates", "n_pairs", "n_overlap", "n_rows", "n_mc", "n_vertices")},
-        "halo": halo, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "halo": halo, "wall_ms_per_step_ranks": [round(w / args.steps * 1e3, 4) for w in wall_ranks], "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:

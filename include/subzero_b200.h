@@ -319,6 +319,11 @@ int32_t SZ_FN(slab_step)(sz_slab *s, int64_t tstep, int32_t do_coupling);
  * of the uploaded (stale) halo copies, step, download.  in[k] == out[k] is allowed. */
 int32_t SZ_FN(slab_step_host)(sz_slab *s, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in,
                               sz_floe_soa *const *out);
+/* sz_step_host_partial on every local rank: in == NULL or in[k] == NULL or a NULL field = the device-resident value stands,
+ * a NULL field of out[k] is not downloaded.  The boundary floes are published AFTER the uploads, so a field the host
+ * changed reaches the neighbours' halo copies in the same step. */
+int32_t SZ_FN(slab_step_host_partial)(sz_slab *s, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in,
+                                      sz_floe_soa *const *out);
 /* Largest distance an owned floe of the local ranks travelled since the lists were built (periodic wrap taken out);
  * the lists are valid while it stays below skin / 2.  No device synchronisation (the step reads it back). */
 int32_t SZ_FN(slab_max_displacement)(sz_slab *s, double *metres);

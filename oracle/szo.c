@@ -1452,8 +1452,9 @@ int32_t szo_step(sz_handle *h, int64_t tstep, int32_t do_coupling) {
 /* the host-buffer form of the timestep: no overlap to exploit on the CPU, the three calls back to back */
 /* an overlap hint for the CUDA product; the oracle's step does its coupling in order */
 /* sz_step_host_partial: NULL input fields keep the resident value, NULL output fields are not written */
-int32_t szo_step_host_partial(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
-    if (!h || !out) return SZ_ERR_INVALID;
+/* the upload half of szo_step_host_partial (also used by the slab restatement, which exchanges the halo in between) */
+int32_t szo_upload_partial(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in) {
+    if (!h) return SZ_ERR_INVALID;
     if (in) {
         if (in->n != h->n || in->n_init != h->n_init) return fail(h, SZ_ERR_INVALID, "step_host_partial: floe count differs from the resident store");
 #define UP(src, dst) if (in->src) for (int64_t i = 0; i < h->n; ++i) h->dst[i] = in->src[i];
@@ -1476,7 +1477,14 @@ int32_t szo_step_host_partial(sz_handle *h, int64_t tstep, int32_t do_coupling, 
             }
         }
     }
-    int32_t rc = szo_step(h, tstep, do_coupling);
+    return SZ_OK;
+}
+
+int32_t szo_step_host_partial(sz_handle *h, int64_t tstep, int32_t do_coupling, const sz_floe_soa *in, sz_floe_soa *out) {
+    if (!h || !out) return SZ_ERR_INVALID;
+    int32_t rc = szo_upload_partial(h, do_coupling, in);
+    if (rc != SZ_OK) return rc;
+    rc = szo_step(h, tstep, do_coupling);
     if (rc != SZ_OK) return rc;
     sz_floe_soa o = *out;
     o.mc_x = o.mc_y = NULL;

@@ -154,6 +154,8 @@ class Library:
         "slab_step": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32]),
         "slab_step_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.POINTER(FloeSoA)),
                                        C.POINTER(C.POINTER(FloeSoA))]),
+        "slab_step_host_partial": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.POINTER(FloeSoA)),
+                                               C.POINTER(C.POINTER(FloeSoA))]),
         "slab_max_displacement": (C.c_int32, [C.c_void_p, c_double_p]),
         "slab_rebuild": (C.c_int32, [C.c_void_p]),
         "slab_refresh_halo": (C.c_int32, [C.c_void_p]),

@@ -1448,7 +1448,8 @@ static int32_t step_finish(sz_handle *h) {
             CK(cudaEventRecord(h->ev_dn_end, h->stream_dn));
             CK(cudaStreamSynchronize(h->stream_dn));
             if (getenv("SZ_DEBUG_HOSTIO")) {
-                float t[12] = {0};
+                float t[13] = {0};
+                cudaEventElapsedTime(&t[12], h->ev_up_start, h->ev[1]);
                 for (int g = 0; g < 4; ++g) cudaEventElapsedTime(&t[g], h->ev_up_start, h->ev_up[g]);
                 cudaEventElapsedTime(&t[4], h->ev_up_start, h->ev[0]);
                 cudaEventElapsedTime(&t[5], h->ev_up_start, h->ev[2]);
@@ -1458,8 +1459,8 @@ static int32_t step_finish(sz_handle *h) {
                 cudaEventElapsedTime(&t[9], h->ev_up_start, h->ev_dn_end);
                 cudaEventElapsedTime(&t[10], h->ev_up_start, h->ev_c0);
                 cudaEventElapsedTime(&t[11], h->ev_up_start, h->ev_c1);
-                fprintf(stderr, "hostio ms: up groups %.3f %.3f %.3f %.3f | step start %.3f broad end %.3f narrow end %.3f rows end %.3f update end %.3f | coupling %.3f..%.3f | last download %.3f\n",
-                        t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[10], t[11], t[9]);
+                fprintf(stderr, "[dev %d] hostio ms: up groups %.3f %.3f %.3f %.3f | step start %.3f ghosts end %.3f broad end %.3f narrow end %.3f rows end %.3f update end %.3f | coupling %.3f..%.3f | last download %.3f\n",
+                        h->cfg.device, t[0], t[1], t[2], t[3], t[4], t[12], t[5], t[6], t[7], t[8], t[10], t[11], t[9]);
             }
         }
         CK(cudaGetLastError());
@@ -1963,6 +1964,23 @@ int32_t szb_step_publish(sz_handle *h, int64_t tstep, int32_t do_coupling, const
     if (do_coupling && !h->have_fields) return fail(h, SZ_ERR_INVALID, "step with coupling before set_fields");
     if (h->n_total != h->n_init) return fail(h, SZ_ERR_INVALID, "step with ghosts present (call remove_ghosts)");
     cudaSetDevice(h->cfg.device);
+    if (host_mode == 2) {  // sz_slab_step_host_partial: NULL fields of `in` keep the resident values, NULL fields of `out` stay behind
+        if (!out) return SZ_ERR_INVALID;
+        if (h->up_pending || h->cpl_prelaunched) return fail(h, SZ_ERR_INVALID, "slab_step_host_partial: an upload or a coupling of the split calls is pending");
+        if (in && (in->n != h->n_total || in->n_init != h->n_init)) return fail(h, SZ_ERR_INVALID, "slab_step_host_partial: floe count differs from the resident store");
+        if ((int)h->h_vcount.size() != h->n_init) return fail(h, SZ_ERR_INVALID, "slab_step_host_partial: no ring table of the resident floes");
+        const int n = h->n_init;
+        if (h->cf_cap < n) {
+            dfree(h->d_cf_dn);
+            CK(dalloc(&h->d_cf_dn, (size_t)n));
+            h->cf_cap = n;
+        }
+        HostIO io = {in, out};
+        h->next_partial = true;
+        int32_t rc = step_setup(h, do_coupling, &io, true);
+        h->next_partial = false;
+        return rc;
+    }
     if (host_mode) {
         int32_t rc = prepare_step_host(h, do_coupling, in, out);
         if (rc) return rc;

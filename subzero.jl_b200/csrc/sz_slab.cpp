@@ -27,6 +27,10 @@
 
 #define FN(name) SZ_FN(name)
 
+#ifdef SZ_ORACLE_BUILD
+extern "C" int32_t szo_upload_partial(sz_handle *h, int32_t do_coupling, const sz_floe_soa *in);  // oracle/szo.c
+#endif
+
 namespace {
 
 constexpr int W = 40;  // doubles per floe record
@@ -903,7 +907,8 @@ int32_t FN(slab_local_index)(sz_slab *S, int32_t k, int64_t *gidx, int32_t *owne
     return SZ_OK;
 }
 
-static int32_t slab_step_common(sz_slab *S, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in, sz_floe_soa *const *out) {
+static int32_t slab_step_common(sz_slab *S, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in, sz_floe_soa *const *out,
+                                bool partial = false) {
     if (!S) return SZ_ERR_INVALID;
     for (Rank &R : S->ranks) if (!R.built) return sfail(S, SZ_ERR_INVALID, "slab: step before sz_slab_build");
     const bool host_mode = out != nullptr;
@@ -911,7 +916,8 @@ static int32_t slab_step_common(sz_slab *S, int64_t tstep, int32_t do_coupling, 
     // one host thread drives every local device: uploads + publication everywhere, kernels everywhere, wait everywhere
     for (int k = 0; k < S->n_local; ++k) {
         Rank &R = S->ranks[k];
-        HCK(szb_step_publish(R.h, tstep, do_coupling, host_mode ? in[k] : nullptr, host_mode ? out[k] : nullptr, host_mode), "step");
+        HCK(szb_step_publish(R.h, tstep, do_coupling, host_mode && in ? in[k] : nullptr, host_mode ? out[k] : nullptr,
+                             host_mode ? (partial ? 2 : 1) : 0), "step");
     }
     for (int k = 0; k < S->n_local; ++k) {
         Rank &R = S->ranks[k];
@@ -922,11 +928,17 @@ static int32_t slab_step_common(sz_slab *S, int64_t tstep, int32_t do_coupling, 
         HCK(szb_step_end(R.h, host_mode), "step");
     }
 #else
-    if (host_mode)
+    if (host_mode && !partial)
         for (int k = 0; k < S->n_local; ++k) {
             Rank &R = S->ranks[k];
             HCK(FN(upload_state)(R.h, in[k]), "upload_state");
         }
+    if (partial) {  // the CPU restatement: sz_step_host_partial's upload half (kernels none), then the exchange
+        for (int k = 0; k < S->n_local; ++k) {
+            Rank &R = S->ranks[k];
+            HCK(szo_upload_partial(R.h, do_coupling, in ? in[k] : nullptr), "upload_partial");
+        }
+    }
     {
         int32_t rc = host_exchange(S);
         if (rc) return rc;
@@ -958,6 +970,13 @@ int32_t FN(slab_step_host)(sz_slab *S, int64_t tstep, int32_t do_coupling, const
     for (int k = 0; k < S->n_local; ++k)
         if (!in[k] || !out[k]) return sfail(S, SZ_ERR_INVALID, "slab_step_host: arrays of every local rank are required");
     return slab_step_common(S, tstep, do_coupling, in, out);
+}
+
+int32_t FN(slab_step_host_partial)(sz_slab *S, int64_t tstep, int32_t do_coupling, const sz_floe_soa *const *in, sz_floe_soa *const *out) {
+    if (!S || !out) return SZ_ERR_INVALID;
+    for (int k = 0; k < S->n_local; ++k)
+        if (!out[k]) return sfail(S, SZ_ERR_INVALID, "slab_step_host_partial: output arrays of every local rank are required");
+    return slab_step_common(S, tstep, do_coupling, in, out, true);
 }
 
 int32_t FN(slab_max_displacement)(sz_slab *S, double *metres) {

@@ -152,6 +152,30 @@ class Slab:
             ptr[k] = C.pointer(s)
         self._ck(self.lib.slab_step_host(self.s, tstep, 1 if do_coupling else 0, ptr, ptr))
 
+    def step_host_partial(self, arrays, tstep=0, do_coupling=True, upload=(), download=()):
+        """step_host exchanging only the named fields (FloeSoA field names) of every local rank's arrays: the others keep
+        their device-resident values / are not downloaded (sz_slab_step_host_partial)."""
+        def masked(fa, names):
+            full = fa.as_struct()
+            m = capi.FloeSoA()
+            m.n, m.n_init = full.n, full.n_init
+            for name in names:
+                setattr(m, name, getattr(full, name))
+            m._keep = full
+            return m
+        pin = (C.POINTER(capi.FloeSoA) * self.n_local)()
+        pout = (C.POINTER(capi.FloeSoA) * self.n_local)()
+        keep = []
+        for k in range(self.n_local):
+            o = masked(arrays[k], download)
+            keep.append(o)
+            pout[k] = C.pointer(o)
+            if upload:
+                i = masked(arrays[k], upload)
+                keep.append(i)
+                pin[k] = C.pointer(i)
+        self._ck(self.lib.slab_step_host_partial(self.s, tstep, 1 if do_coupling else 0, pin if upload else None, pout))
+
     def max_displacement(self):
         d = C.c_double(0.0)
         self._ck(self.lib.slab_max_displacement(self.s, C.byref(d)))

@@ -105,6 +105,53 @@ def test_emulated_ranks_through_host_arrays_oracle(walls, world, oracle_lib):
     check_against_single(f, oracle_lib, s, single_rank_reference(f, oracle_lib, 3))
 
 
+def run_partial(f, lib, world):
+    """Three sz_slab_step_host_partial steps: the host halves every velocity and uploads ONLY u, v on the first step (the
+    neighbours' halo copies must see it), later steps upload the status only; positions, velocities and forces come back."""
+    s = slab.Slab(lib, f, world, skin=200.0)
+    s.build(f.floes)
+    arrays = [s.handles[k].download_floes(mc=False) for k in range(world)]
+    for a in arrays:
+        a.u *= 0.5
+        a.v *= 0.5
+    down = ("centroid_x", "centroid_y", "alpha", "u", "v", "xi", "collision_force", "collision_trq", "fxOA", "fyOA", "trqOA", "status_tag")
+    for a in arrays:
+        a.height[:] = -1.0  # not exchanged in either direction: must neither reach the device nor be overwritten
+    s.step_host_partial(arrays, 0, True, upload=("u", "v"), download=down)
+    s.step_host_partial(arrays, 1, True, upload=("status_tag",), download=down)
+    s.step_host_partial(arrays, 2, True, upload=(), download=down)
+    for k, a in enumerate(arrays):
+        assert np.all(a.height == -1.0)
+        dev = s.handles[k].download_floes(mc=False)
+        assert np.all(dev.height > 0.0)
+        own = s.local_index(k)[1] == k
+        for name in down:
+            assert np.array_equal(getattr(a, name)[own], getattr(dev, name)[own]), name
+    return s
+
+
+@pytest.mark.parametrize("walls,world", [("periodic", 2), ("collision", 3)])
+def test_partial_host_arrays_oracle(walls, world, oracle_lib):
+    f = synth.make_field(1200, scale=1.02, walls=walls, npoints=30, cache=False)
+    fields.perturb_state(f.floes)
+    s = run_partial(f, oracle_lib, world)
+    f.floes.u *= 0.5
+    f.floes.v *= 0.5
+    check_against_single(f, oracle_lib, s, single_rank_reference(f, oracle_lib, 3))
+
+
+@pytest.mark.gpu
+def test_partial_host_arrays_on_one_gpu(product_lib):
+    f = synth.make_field(3000, scale=1.01, walls="periodic", npoints=40, cache=False)
+    fields.perturb_state(f.floes)
+    s = run_partial(f, product_lib, 3)
+    f.floes.u *= 0.5
+    f.floes.v *= 0.5
+    check_against_single(f, product_lib, s, single_rank_reference(f, product_lib, 3))
+    s.step(3, True)  # a device-resident step behind a host step re-publishes
+    check_against_single(f, product_lib, s, single_rank_reference(f, product_lib, 4))
+
+
 @pytest.mark.parametrize("walls,world", [("periodic", 3), ("collision", 2)])
 def test_rebuild_migrates_ownership_and_keeps_results(walls, world, oracle_lib):
     """Fast floes + a small skin: the halo lists go stale, the library rebuilds by itself (ownership migrates to the
