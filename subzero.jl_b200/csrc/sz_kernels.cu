@@ -1975,11 +1975,9 @@ __device__ __forceinline__ void center_cell_box(const Params &P, int ix, int iy,
 // floe_area_in_cell = sum(area.(intersect_polys(cell_poly, translated floe_poly))), coupling.jl:1652-1660.
 // One thread per record (rings of <= 10 edges); larger rings go to the warp kernel below.
 __global__ void __launch_bounds__(TN_NT, 2) k_crec_area(Store S, CouplingBuf CB, Params P) {
-    extern __shared__ __align__(16) unsigned char smem[];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
-    double2 *base = (double2 *)smem + threadIdx.x;
-    double2 *sP = base, *sQ = sP + TN_MAXV * TN_NT, *sR = sQ + TN_MAXV * TN_NT;
+    const TSp sP = tsp(threadIdx.x), sQ = sP + TN_MAXV * TN_NT, sR = sQ + TN_MAXV * TN_NT;
     for (int r = blockIdx.x * TN_NT + threadIdx.x; r < cnt->n_crec; r += gridDim.x * TN_NT) {
         const int f = CB.rec_floe[r], cell = CB.rec_cell[r], nq = S.vcount[f];
         bool big = nq > TN_MAXV;
@@ -1998,7 +1996,7 @@ __global__ void __launch_bounds__(TN_NT, 2) k_crec_area(Store S, CouplingBuf CB,
                 double2 v = gQ[k];
                 sQ[k * TN_NT] = make_double2(v.x + d.x, v.y + d.y);
             }
-            const unsigned long long cr = t_clip<false>(tring(sP, 5), tring(sQ, nq), sR, TN_RCAP, nullptr);
+            const unsigned long long cr = t_clip<false>(tring(sP, 5), tring(sQ, nq), sR, TN_RCAP, tsp(TSP_NONE));
             if (TC_STATUS(cr) != TN_OK) big = true;
             else
                 for (int g = 0; g < TC_NREG(cr); ++g) area += t_area(tring(sR + TC_RS(cr, g) * TN_NT, TC_RE(cr, g) - TC_RS(cr, g)));

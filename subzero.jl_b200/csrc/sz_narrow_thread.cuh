@@ -42,8 +42,22 @@ enum { TN_OK = 0, TN_DEFER = 1 };
 
 // a ring in [point][thread] shared memory, optionally translated on the fly (P2 = P + dir is
 // never stored: reading P[k] + dir yields the same bits every time)
+// A position in the block's dynamic shared memory, in double2 units from its base.  Rings used to be passed to the
+// __noinline__ helpers as generic pointers: every read inside them was a generic LD.E.128 behind a 64-bit address
+// computation and a descriptor move (ncu r2t: 2.06 M of them per launch of k_narrow_ab<1> against 0.2 M LDS).  Through
+// this 32-bit index the compiler knows the address space and emits LDS / STS with an immediate row offset.
+extern __shared__ __align__(16) double2 tn_sm[];
+#define TSP_NONE 0xffffffffu
+struct TSp {
+    unsigned a;
+    __device__ __forceinline__ double2 &operator[](int k) const { return tn_sm[a + (unsigned)k]; }
+    __device__ __forceinline__ TSp operator+(int k) const { TSp r; r.a = a + (unsigned)k; return r; }
+    __device__ __forceinline__ bool none() const { return a == TSP_NONE; }
+};
+__device__ __forceinline__ TSp tsp(unsigned a) { TSp r; r.a = a; return r; }
+
 struct TRing {
-    const double2 *b;
+    TSp b;
     int n;
     double sx, sy;
     bool shifted;
@@ -59,7 +73,7 @@ __device__ __forceinline__ double2 tgets(const TRing r, int k) {
     }
     return v;
 }
-__device__ __forceinline__ TRing tring(const double2 *b, int n) {
+__device__ __forceinline__ TRing tring(TSp b, int n) {
     TRing r;
     r.b = b;
     r.n = n;
@@ -195,7 +209,7 @@ __device__ TN_FN bool t_rings_intersect(const TRing A, const TRing B, bool &nohi
 #define TC_K(v) ((int)(((v) >> 48) & 0xffu))
 #define TC_GENERIC(v) ((bool)(((v) >> 56) & 1u))
 template <bool SHIFT>
-__device__ TN_FN unsigned long long t_clip(const TRing P, const TRing Q, double2 *R, int rcap, double2 *xp_out) {
+__device__ TN_FN unsigned long long t_clip(const TRing P, const TRing Q, TSp R, int rcap, TSp xp_out) {
     static_assert(TN_MAXREG == 2, "the packed result holds two regions");
     const int np = P.n - 1, nq = Q.n - 1;
     if (np < 3 || nq < 3) return TC_PACK(0, TN_OK, 0, 0, 0, 0, 0, 0);
@@ -293,7 +307,7 @@ __device__ TN_FN unsigned long long t_clip(const TRing P, const TRing Q, double2
     // decided by the perturbation (sym_before in sz_geom.cuh), which only the warp kernel implements
     if (anyzero && K > 1) return TC_PACK(0, TN_DEFER, 0, 0, 0, 0, 0, 0);
     bool gen = false;
-    if (xp_out) {
+    if (!xp_out.none()) {
         bool dup = false;
 #pragma unroll
         for (int k = 0; k < TN_MAXX; ++k) {
@@ -444,7 +458,7 @@ __device__ TN_FN unsigned long long t_clip(const TRing P, const TRing Q, double2
 //     a d2 within a few ulp above the minimum (then the two roots may tie and the earlier index wins).  That
 //     near-tie (never seen on the bench fields) sets `rare`: the item is left to the warp kernel, which evaluates
 //     the roots.  ncu r1k: the two divergent DSQRT expansions were 7 % of the instructions of k_narrow_ab<1>.
-__device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing reg, int *idx, bool &rare) {
+__device__ TN_FN int t_match_vertices(TSp ip, int nip, const TRing reg, int *idx, bool &rare) {
     int m = 0, npoints = nip;
     if (nip > 0) {
         double2 f = ip[0], l = ip[(nip - 1) * TN_NT];
@@ -484,7 +498,7 @@ __device__ TN_FN int t_match_vertices(const double2 *ip, int nip, const TRing re
 }
 
 struct TWs {
-    double2 *P, *Q, *R1, *R2, *ip;  // [cap][TN_NT], already offset by the thread index
+    TSp P, Q, R1, R2, ip;  // [cap][TN_NT], already offset by the thread index
     int rcap;                       // rows of the region buffer (clip #1 and clip #2 share it)
     int r2cap;                      // R2 = the part of the region buffer clip #1 left free
 };
@@ -513,7 +527,7 @@ __device__ __forceinline__ double t_normal_force(const TWs w, const TRing P, con
         P2.shifted = true;
         P2.sx = dir[0];
         P2.sy = dir[1];
-        const unsigned long long c2 = t_clip<true>(P2, Q, w.R2, w.r2cap, nullptr);
+        const unsigned long long c2 = t_clip<true>(P2, Q, w.R2, w.r2cap, tsp(TSP_NONE));
         defer |= TC_STATUS(c2) != TN_OK;
         const int nreg2 = defer ? 0 : TC_NREG(c2);
 #pragma unroll
@@ -882,10 +896,9 @@ __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
 
 template <int PHASE>
 __global__ void __launch_bounds__(TN_NT, 3) k_narrow_ab(Store S, StepBuf B, Params P) {
-    extern __shared__ __align__(16) unsigned char smem[];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
-    double2 *base = (double2 *)smem + threadIdx.x;
+    const TSp base = tsp(threadIdx.x);
     TWs w;
     w.P = base;
     w.Q = w.R1 = w.R2 = w.ip = base;

@@ -40,9 +40,7 @@ struct PairQuery {
 };
 
 __global__ void __launch_bounds__(TN_NT, 2) k_pair_area(Store S, PairQuery Q) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double2 *base = (double2 *)smem + threadIdx.x;
-    double2 *sP = base, *sQ = sP + TN_MAXV * TN_NT, *sR = sQ + TN_MAXV * TN_NT;
+    const TSp sP = tsp(threadIdx.x), sQ = sP + TN_MAXV * TN_NT, sR = sQ + TN_MAXV * TN_NT;
     for (int k = blockIdx.x * TN_NT + threadIdx.x; k < Q.n; k += gridDim.x * TN_NT) {
         const int2 pr = Q.pairs[k];
         const bool pot = sv_potential_interaction(S.cx[pr.x], S.cy[pr.x], S.rmax[pr.x], S.cx[pr.y], S.cy[pr.y], S.rmax[pr.y]);
@@ -56,7 +54,7 @@ __global__ void __launch_bounds__(TN_NT, 2) k_pair_area(Store S, PairQuery Q) {
                 const double2 *gP = S.verts + S.vstart[pr.x], *gQ = S.verts + S.vstart[pr.y];
                 for (int v = 0; v < np; ++v) sP[v * TN_NT] = gP[v];
                 for (int v = 0; v < nq; ++v) sQ[v * TN_NT] = gQ[v];
-                const unsigned long long cr = t_clip<false>(tring(sP, np), tring(sQ, nq), sR, TN_RCAP, nullptr);
+                const unsigned long long cr = t_clip<false>(tring(sP, np), tring(sQ, nq), sR, TN_RCAP, tsp(TSP_NONE));
                 if (TC_STATUS(cr) != TN_OK) big = true;
                 else
                     for (int g = 0; g < TC_NREG(cr); ++g) area += t_area(tring(sR + TC_RS(cr, g) * TN_NT, TC_RE(cr, g) - TC_RS(cr, g)));
@@ -191,9 +189,7 @@ __device__ __forceinline__ void eul_box(const EulGrid &G, int cell, double b[4])
 
 // pic_area = sum(GO.area, intersect_polys(floe_poly, cell_poly)), output.jl:845
 __global__ void __launch_bounds__(TN_NT, 2) k_eul_area(Store S, EulGrid G, EulBuf B) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double2 *base = (double2 *)smem + threadIdx.x;
-    double2 *sP = base, *sQ = sP + TN_MAXV * TN_NT, *sR = sQ + TN_MAXV * TN_NT;
+    const TSp sP = tsp(threadIdx.x), sQ = sP + TN_MAXV * TN_NT, sR = sQ + TN_MAXV * TN_NT;
     for (int r = blockIdx.x * TN_NT + threadIdx.x; r < B.n_rec; r += gridDim.x * TN_NT) {
         const int f = B.rec_floe[r], np = S.vcount[f];
         bool big = np > TN_MAXV || (G.n_topo > 0 && G.cell_topo[B.rec_cell[r]]);
@@ -208,7 +204,7 @@ __global__ void __launch_bounds__(TN_NT, 2) k_eul_area(Store S, EulGrid G, EulBu
             sQ[2 * TN_NT] = make_double2(b[1], b[3]);
             sQ[3 * TN_NT] = make_double2(b[1], b[2]);
             sQ[4 * TN_NT] = make_double2(b[0], b[2]);
-            const unsigned long long cr = t_clip<false>(tring(sP, np), tring(sQ, 5), sR, TN_RCAP, nullptr);
+            const unsigned long long cr = t_clip<false>(tring(sP, np), tring(sQ, 5), sR, TN_RCAP, tsp(TSP_NONE));
             if (TC_STATUS(cr) != TN_OK) big = true;
             else
                 for (int g = 0; g < TC_NREG(cr); ++g) area += t_area(tring(sR + TC_RS(cr, g) * TN_NT, TC_RE(cr, g) - TC_RS(cr, g)));

@@ -889,7 +889,17 @@ int32_t FN(slab_build)(sz_slab *S, const sz_floe_soa *const *floes, const int64_
 #ifndef SZ_ORACLE_BUILD
     for (Rank &R : S->ranks) if (R.built) HCK(szb_release_peers(R.h, 0), "release partners");
 #endif
-    return repartition(S, own);
+    int32_t rc = repartition(S, own);
+#ifndef SZ_ORACLE_BUILD
+    // A rebuild right away (nothing moved: same lists) makes every first-time allocation of the rebuild path — the second
+    // Monte-Carlo array of the on-device regather, the page-locked staging, the gather scratch — part of the set-up
+    // instead of the first rebuild of the run (0.35 s there against ~45 ms for the later ones).
+    if (rc == SZ_OK && S->world > 1 && !getenv("SZ_SLAB_NO_PREWARM")) {
+        rc = do_rebuild(S);
+        S->rebuilds = 0;
+    }
+#endif
+    return rc;
 }
 
 int32_t FN(slab_local_count)(sz_slab *S, int32_t k, int64_t *n, int64_t *n_owned) {
