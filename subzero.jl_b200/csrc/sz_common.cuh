@@ -229,6 +229,7 @@ struct Launch {
     int maxv_large, maxx_large;  // workspace of the large-polygon kernels
     int coupling_blocks_per_sm;  // 0 = fill the GPU; > 0 = persistent grid of that many blocks per SM
     bool capturing;              // the stream is being captured into a CUDA graph (sz_step)
+    int pdl;                     // programmatic dependent launch in the collision chain (see sz_pdl below)
     bool chain_v2;               // fused broad-phase / row chain with single-pass scans (SZ_CHAIN_V1 selects the old one)
     bool no_phase_events;        // experiment (SZ_GRAPH_NO_EVENTS): no timing-event nodes inside a captured graph
 };
@@ -306,3 +307,29 @@ void szk_points_write(const Launch &L, const Store &S, const sz_points_generator
                       double2 *out);
 long long szk_launch_count(bool reset);
 void szk_count_launches(int n);
+
+// ---- programmatic dependent launch (PDL) for the chains of small dependent kernels --------------------------------
+// Every kernel of the collision chain starts with sz_pdl(): it lets the NEXT kernel of the stream be launched at once
+// (its blocks become resident and run up to their own sz_pdl() while this grid is still working) and then waits until
+// the PREVIOUS grid has completed and its writes are visible.  Launched without the attribute both instructions are
+// no-ops, so the same kernels serve the plain launches (CUDA-graph capture, the v1 chain, SZ_NO_PDL=1).
+#ifdef __CUDACC__
+__device__ __forceinline__ void sz_pdl() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline void sz_launch_pdl(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = on ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif

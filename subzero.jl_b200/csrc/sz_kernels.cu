@@ -234,6 +234,7 @@ struct ScanLB {
     int stride;
 };
 __global__ void __launch_bounds__(SCAN_T) k_scan_lb(ScanLB a, const int *len_ptr, int len_add, const Counters *cnt) {
+    sz_pdl();
     if (cnt->error) return;
     __shared__ int s_tile, s_excl;
     const int y = blockIdx.y;
@@ -306,7 +307,7 @@ static void scan_lb(const Launch &L, const Store &S, const StepBuf &B, int slot,
     a.ticket = B.lb_ticket + slot * 3;
     int tiles = sz_div_up((long long)max_len, SCAN_TILE);
     if (tiles < 1) tiles = 1;
-    k_scan_lb<<<dim3(tiles, narr), SCAN_T, 0, L.stream>>>(a, len_ptr, len_add, S.cnt);
+    sz_launch_pdl(L.chain_v2 && L.pdl != 0, k_scan_lb, dim3(tiles, narr), dim3(SCAN_T), 0, L.stream, a, len_ptr, len_add, (const Counters *)S.cnt);
     g_launch_count += 1;
 }
 
@@ -890,6 +891,7 @@ __global__ void k_cell_count(Store S, StepBuf B) {
 // so the neighbour search below reads contiguous 32-byte records cell by cell instead of gathering
 // three scalars per candidate
 __global__ void k_cell_fill(Store S, StepBuf B) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     int n = cnt->n_total;
@@ -1234,6 +1236,7 @@ __device__ void narrow_item(const Ws &w, const Store &S, const StepBuf &B, const
 }
 
 __global__ void k_narrow(Store S, StepBuf B, Params P, int maxv, int maxx, int large) {
+    sz_pdl();
     extern __shared__ __align__(16) unsigned char smem[];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -1271,6 +1274,7 @@ __global__ void k_status(Store S, StepBuf B) {
 // fuse_idx; since partners recorded by the pair loop are always j > i the serial result is the
 // closure of "i fused => j fused" over the fuse pairs, computed here as a fixed point.
 __global__ void k_fuse_propagate(Store S, StepBuf B) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     int nf = min(cnt->n_fuse, B.cap_fuse);
@@ -1309,6 +1313,7 @@ __global__ void k_row_count(Store S, StepBuf B) {
 }
 
 __global__ void k_row_total(Store S, StepBuf B) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     int n = cnt->n_total;
@@ -1448,6 +1453,7 @@ __global__ void k_update_boundaries(Store S, Params P) {
 // k_bbox2: k_step_reset's per-floe zeroing + k_bbox.  The bounding-box words and the step counters are reset by
 // k_cell_count2 (after the last reader of the box) for the NEXT collision step; k_set_counts initialises them.
 __global__ void k_bbox2(Store S) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     int n = cnt->n_total;
@@ -1513,6 +1519,7 @@ __device__ __forceinline__ GridGeom grid_geom(const Counters *cnt, int cap_cells
 
 // k_grid_setup + k_cell_zero + the reset of every look-back scan of this step
 __global__ void k_grid_zero(Store S, StepBuf B) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const GridGeom g = grid_geom(cnt, B.cap_cells);
@@ -1536,6 +1543,7 @@ __global__ void k_grid_zero(Store S, StepBuf B) {
 
 // k_cell_count; thread 0 then resets what k_step_reset used to reset (the box has no reader left in this step)
 __global__ void k_cell_count2(Store S, StepBuf B) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const int n = cnt->n_total, gnx = cnt->gnx, gny = cnt->gny;
@@ -1563,6 +1571,7 @@ __global__ void k_cell_count2(Store S, StepBuf B) {
 #define NB_K 20
 template <bool WRITE>
 __global__ void k_neighbours2(Store S, StepBuf B) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     if (WRITE && (cnt->n_cand > B.cap_pairs || cnt->n_dom > B.cap_dom)) {  // k_pair_check: every thread backs off, one reports
@@ -1681,6 +1690,7 @@ __global__ void k_neighbours2(Store S, StepBuf B) {
 
 // k_low_link (blocks [0, nb_link)) and k_filter (the rest) in one launch: both only read the sorted own-pair lists
 __global__ void k_link_filter(Store S, StepBuf B, int nb_link) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     if ((int)blockIdx.x < nb_link) {
@@ -1729,6 +1739,7 @@ __global__ void k_link_filter(Store S, StepBuf B, int nb_link) {
 
 // k_pool_check + k_status + k_row_count
 __global__ void k_status_rowcount(Store S, StepBuf B) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (cnt->n_pool > B.cap_pool) cnt->want_pool = cnt->n_pool;
@@ -1758,6 +1769,7 @@ __global__ void k_status_rowcount(Store S, StepBuf B) {
 
 // k_row_check + k_row_write + k_update_boundaries
 __global__ void k_row_write2(Store S, StepBuf B, Params P) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     if (cnt->n_rows > B.cap_rows) {  // every thread backs off, one reports
@@ -1815,47 +1827,48 @@ __global__ void k_row_write2(Store S, StepBuf B, Params P) {
 static void collisions_v2(const Launch &L, const Store &S, const StepBuf &B, const Params &P, int n_hint, int pairs_hint,
                           cudaEvent_t *ev, const cudaEvent_t *waits) {
     cudaStream_t st = L.stream;
+    const bool pdl = L.pdl != 0;
     const int gf = grid_for(L, n_hint, TPB);
-    k_bbox2<<<gf, TPB, 0, st>>>(S);
-    k_grid_zero<<<grid_for(L, B.cap_cells, TPB), TPB, 0, st>>>(S, B);
-    k_cell_count2<<<gf, TPB, 0, st>>>(S, B);
+    sz_launch_pdl(false, k_bbox2, dim3(gf), dim3(TPB), 0, st, S);
+    sz_launch_pdl(pdl, k_grid_zero, dim3(grid_for(L, B.cap_cells, TPB)), dim3(TPB), 0, st, S, B);
+    sz_launch_pdl(pdl, k_cell_count2, dim3(gf), dim3(TPB), 0, st, S, B);
     {
         const int *in[1] = {B.cell_count};
         int *out[1] = {B.cell_start}, *tot[1] = {nullptr};
         scan_lb(L, S, B, 0, 1, in, out, tot, &S.cnt->n_cells, 0, B.cap_cells);
     }
-    k_cell_fill<<<gf, TPB, 0, st>>>(S, B);
-    k_neighbours2<false><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
+    sz_launch_pdl(pdl, k_cell_fill, dim3(gf), dim3(TPB), 0, st, S, B);
+    sz_launch_pdl(pdl, k_neighbours2<false>, dim3(sz_div_up(n_hint, 128)), dim3(128), 0, st, S, B);
     {
         const int *in[3] = {B.up_count, B.low_count, B.dom_count};
         int *out[3] = {B.up_off, B.low_off, B.dom_off}, *tot[3] = {&S.cnt->n_cand, nullptr, &S.cnt->n_dom};
         scan_lb(L, S, B, 1, 3, in, out, tot, &S.cnt->n_total, 0, S.cap_floes);
     }
-    k_neighbours2<true><<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B);
+    sz_launch_pdl(pdl, k_neighbours2<true>, dim3(sz_div_up(n_hint, 128)), dim3(128), 0, st, S, B);
     const int gp = grid_for(L, pairs_hint, TPB);
-    k_link_filter<<<gf + gp, TPB, 0, st>>>(S, B, gf);
+    sz_launch_pdl(pdl, k_link_filter, dim3(gf + gp), dim3(TPB), 0, st, S, B, gf);
     if (ev) sz_record(L, ev[0], st);
     if (waits) cudaStreamWaitEvent(st, waits[0], 0);  // sz_step_host: rings and height have landed
     const int maxv_s = 32, maxx_s = 16, wpb = 4;
     int gi = grid_for(L, (long long)pairs_hint + n_hint / 8 + 64, 256);
-    k_item_count<<<gi, 256, 0, st>>>(S, B);
-    k_class_scan<<<1, 32, 0, st>>>(S, B);
-    k_item_scatter<<<gi, 256, 0, st>>>(S, B);
-    k_narrow_ab<0><<<3 * L.sms, TN_NT, TN_SMEM_A, st>>>(S, B, P);
-    k_narrow_ab<1><<<3 * L.sms, TN_NT, TN_SMEM_B, st>>>(S, B, P);
-    k_narrow<<<L.sms * 4, wpb * 32, wpb * ws_bytes(maxv_s, maxx_s), st>>>(S, B, P, maxv_s, maxx_s, 0);
-    k_narrow<<<L.sms, 32, ws_bytes(L.maxv_large, L.maxx_large), st>>>(S, B, P, L.maxv_large, L.maxx_large, 1);
+    sz_launch_pdl(pdl, k_item_count, dim3(gi), dim3(256), 0, st, S, B);
+    sz_launch_pdl(pdl, k_class_scan, dim3(1), dim3(32), 0, st, S, B);
+    sz_launch_pdl(pdl, k_item_scatter, dim3(gi), dim3(256), 0, st, S, B);
+    sz_launch_pdl(pdl, k_narrow_ab<0>, dim3(3 * L.sms), dim3(TN_NT), TN_SMEM_A, st, S, B, P);
+    sz_launch_pdl(pdl, k_narrow_ab<1>, dim3(3 * L.sms), dim3(TN_NT), TN_SMEM_B, st, S, B, P);
+    sz_launch_pdl(pdl, k_narrow, dim3(L.sms * 4), dim3(wpb * 32), wpb * ws_bytes(maxv_s, maxx_s), st, S, B, P, maxv_s, maxx_s, 0);
+    sz_launch_pdl(pdl, k_narrow, dim3(L.sms), dim3(32), ws_bytes(L.maxv_large, L.maxx_large), st, S, B, P, L.maxv_large, L.maxx_large, 1);
     if (ev) sz_record(L, ev[1], st);
     if (waits) cudaStreamWaitEvent(st, waits[1], 0);  // sz_step_host: everything else (overarea is accumulated by k_row_write)
-    k_status_rowcount<<<gf, TPB, 0, st>>>(S, B);
-    k_fuse_propagate<<<1, 1024, 0, st>>>(S, B);
-    k_row_total<<<gf, TPB, 0, st>>>(S, B);
+    sz_launch_pdl(pdl, k_status_rowcount, dim3(gf), dim3(TPB), 0, st, S, B);
+    sz_launch_pdl(pdl, k_fuse_propagate, dim3(1), dim3(1024), 0, st, S, B);
+    sz_launch_pdl(pdl, k_row_total, dim3(gf), dim3(TPB), 0, st, S, B);
     {
         const int *in[1] = {B.row_count};
         int *out[1] = {B.row_off}, *tot[1] = {&S.cnt->n_rows};
         scan_lb(L, S, B, 2, 1, in, out, tot, &S.cnt->n_total, 0, S.cap_floes);
     }
-    k_row_write2<<<sz_div_up(n_hint, 128), 128, 0, st>>>(S, B, P);
+    sz_launch_pdl(pdl, k_row_write2, dim3(sz_div_up(n_hint, 128)), dim3(128), 0, st, S, B, P);
     if (ev) sz_record(L, ev[2], st);
     g_launch_count += 18;  // + the three look-back scans counted in scan_lb
 }

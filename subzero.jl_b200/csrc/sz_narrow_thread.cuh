@@ -811,6 +811,7 @@ __device__ __forceinline__ int item_class(const Store &S, const StepBuf &B, int 
 }
 
 __global__ void __launch_bounds__(256) k_item_count(Store S, StepBuf B) {
+    sz_pdl();
     __shared__ int hist[TN_NCLASS];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -835,7 +836,8 @@ __global__ void __launch_bounds__(256) k_item_count(Store S, StepBuf B) {
         if (hist[k]) atomicAdd(&B.class_count[k], hist[k]);
 }
 
-__global__ void k_class_scan(Store S, StepBuf B) {  // one warp, four classes per lane
+__global__ void k_class_scan(Store S, StepBuf B) {
+    sz_pdl();  // one warp, four classes per lane
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const int lane = threadIdx.x & 31;
@@ -866,6 +868,7 @@ __global__ void k_class_scan(Store S, StepBuf B) {  // one warp, four classes pe
 }
 
 __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
+    sz_pdl();
     __shared__ int hist[TN_NCLASS], base[TN_NCLASS];
     Counters *cnt = S.cnt;
     if (cnt->error) return;
@@ -896,6 +899,7 @@ __global__ void __launch_bounds__(256) k_item_scatter(Store S, StepBuf B) {
 
 template <int PHASE>
 __global__ void __launch_bounds__(TN_NT, 3) k_narrow_ab(Store S, StepBuf B, Params P) {
+    sz_pdl();
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const TSp base = tsp(threadIdx.x);
