@@ -42,7 +42,7 @@ void szk_pack_fields(const Launch &L, const Store &S, int n) {
 // rad cos(theta) = xc, so the reference's u - xi rad sin(theta) (:1534-1537) and
 // (-tx sin + ty cos) rad (:1562) need no transcendental call.
 struct CpConst {
-    double x0, y0, xf, yf, inv_dx, inv_dy, dx, dy, ct, sn, ka, ko, f;
+    double x0, y0, xf, yf, inv_dx, inv_dy, dx, dy, ct, sn, ka, ko, f, koct, kosn;
     int Nx, Ny, per_x, per_y;
 };
 
@@ -65,8 +65,11 @@ struct CpReg {
 __device__ __forceinline__ double cp_norm(double s) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
-    r = r * (1.5 - (0.5 * s) * r * r);
-    return s > 2.2250738585072014e-308 ? s * r : 0.0;  // ftz: a denormal argument gives +inf, its norm is 0 to 1e-154
+    // one Newton step written on the root itself: y = s r, sqrt(s) ~ y + (r / 2)(s - y y) — four dependent FP64
+    // instructions instead of five
+    const double y = s * r;
+    const double root = fma(0.5 * r, fma(-y, y, s), y);
+    return s > 2.2250738585072014e-308 ? root : 0.0;  // ftz: a denormal argument gives +inf, its norm is 0 to 1e-154
 }
 
 // largest distance of a floe's sub-floe points from its centroid (body frame): warp per floe
@@ -185,9 +188,10 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     double na = cp_norm(dua * dua + dva * dva);
     double duo = uocn - up, dvo = vocn - vp;  // calc_ocean_forcing!, coupling.jl:1277-1299
     double no = cp_norm(duo * duo + dvo * dvo);
-    double tox = c.ko * no * (c.ct * duo - c.sn * dvo), toy = c.ko * no * (c.sn * duo + c.ct * dvo);
-    double tx = c.ka * na * dua - mf * vocn + tox;
-    double ty = c.ka * na * dva + mf * uocn + toy;
+    double tox = no * (c.koct * duo - c.kosn * dvo), toy = no * (c.kosn * duo + c.koct * dvo);  // ko (cos, sin) folded on the host
+    double kna = c.ka * na;
+    double tx = fma(kna, dua, fma(-mf, vocn, tox));
+    double ty = fma(kna, dva, fma(mf, uocn, toy));
     if (REG) {
         // find_center_cell_index (coupling.jl:466-470) and shift_cell_idx (:1155-1182), 0-based here
         int xi0 = (int)floor(gx + 0.5), yi0 = (int)floor(gy + 0.5);
@@ -202,7 +206,7 @@ __device__ __forceinline__ void cp_point(const CpConst &c, const double *__restr
     }
     acc.tx += tx;
     acc.ty += ty;
-    acc.trq += ty * xr - tx * yr;
+    acc.trq = fma(ty, xr, fma(-tx, yr, acc.trq));
     acc.hf += hfl;
 }
 
@@ -337,8 +341,11 @@ __device__ __forceinline__ void cp_bar_wait(unsigned long long *bar, unsigned pa
     } while (!ok);
 }
 
+#ifndef CP_MINB
+#define CP_MINB 6  // blocks per SM the register allocation aims at (A/B: tools/ab_coupling_minb.sh)
+#endif
 template <bool ATM, bool HFLX>
-__global__ void __launch_bounds__(128, 6) k_coupling_bulk(Store S, CpConst c) {
+__global__ void __launch_bounds__(128, CP_MINB) k_coupling_bulk(Store S, CpConst c) {
     Counters *cnt = S.cnt;
     if (cnt->error) return;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
@@ -627,6 +634,7 @@ void szk_coupling_reg(const Launch &L, const Store &S, const CouplingBuf &CB, co
     c.dx = P.dx; c.dy = P.dy;
     c.ct = cos(P.cfg.turn_theta); c.sn = sin(P.cfg.turn_theta);
     c.ka = P.cfg.rho_a * P.cfg.Cd_ia; c.ko = P.cfg.rho_o * P.cfg.Cd_io; c.f = P.cfg.f;
+    c.koct = c.ko * c.ct; c.kosn = c.ko * c.sn;
     c.Nx = P.Nx; c.Ny = P.Ny;
     c.per_x = P.per_x; c.per_y = P.per_y;
     long long blocks = ((long long)S.n_init + 3) / 4, cap = (long long)L.sms * 48;
@@ -685,6 +693,7 @@ void szk_coupling(const Launch &L, const Store &S, const Params &P) {
     c.dx = P.dx; c.dy = P.dy;
     c.ct = cos(P.cfg.turn_theta); c.sn = sin(P.cfg.turn_theta);
     c.ka = P.cfg.rho_a * P.cfg.Cd_ia; c.ko = P.cfg.rho_o * P.cfg.Cd_io; c.f = P.cfg.f;
+    c.koct = c.ko * c.ct; c.kosn = c.ko * c.sn;
     c.Nx = P.Nx; c.Ny = P.Ny;
     c.per_x = P.per_x; c.per_y = P.per_y;
     // 128-thread blocks: small enough to share an SM with the narrow-phase blocks when the two run on
