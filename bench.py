@@ -350,14 +350,16 @@ def main():
     if world > 1:  # the collectives the timed region uses (displacement poll) have run once before it starts
         d = torch.zeros(1, dtype=torch.float64, device="cuda")
         dist.all_reduce(d, op=dist.ReduceOp.MAX)
-    barrier()
+    # everything that takes host time (NVML initialisation of the clock sampler: milliseconds) happens BEFORE the barrier:
+    # a rank that enters the timed loop late makes its neighbours wait for its boundary floes inside THEIR timed region
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     phase = np.zeros(8)
     launches = 0
-    t0 = time.perf_counter()
     step_wall = np.zeros(args.steps)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
     tp = t0
     for t in range(args.steps):
         do_step(args.warmup + t)
@@ -590,7 +592,8 @@ def main():
         "mc_points_per_s": steps_per_s * M * world, "parity": parity,
         "device_ms_per_step": 1e3 * dev_max / args.steps,
         "step_wall_ms_rank0": {"p50": 1e3 * float(np.percentile(step_wall, 50)), "p90": 1e3 * float(np.percentile(step_wall, 90)),
-                               "p99": 1e3 * float(np.percentile(step_wall, 99)), "max": 1e3 * float(step_wall.max())},
+                               "p99": 1e3 * float(np.percentile(step_wall, 99)), "max": 1e3 * float(step_wall.max()),
+                               "first10_mean": 1e3 * float(step_wall[:10].mean()), "last10_mean": 1e3 * float(step_wall[-10:].mean())},
         "counts": {k: c[k] for k in ("n_init", "n_candidates", "n_pairs", "n_overlap", "n_rows", "n_mc", "n_vertices")},
         "halo": halo, "wall_ms_per_step_ranks": [round(w / args.steps * 1e3, 4) for w in wall_ranks], "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
