@@ -41,11 +41,21 @@ def gloo_worker(rank, world, port, q):
             if t == 2:
                 s.rebuild()  # collective: migration + fresh halo lists
             s.step(t, True)
+        # host arrays of the local list (sz_slab_step_host), then a field-masked step (sz_slab_step_host_partial): the
+        # uploaded boundary floes reach the other PROCESS before its step
+        arrays = [s.handles[0].download_floes(mc=False)]
+        s.step_host(arrays, 3, True)
+        s.step_host_partial(arrays, 4, True, upload=("status_tag",), download=("centroid_x", "centroid_y", "u", "v", "xi", "alpha", "status_tag"))
         h = synth.setup_handle(f, lib, threads=1)
-        for t in range(3):
+        for t in range(5):
             h.step(t, True)
         bad = _compare_owned(s, h.download_floes(mc=False))
         g, o = s.local_index(0)
+        own = o == rank
+        dev = s.handles[0].download_floes(mc=False)
+        for name in ("centroid_x", "u", "alpha"):
+            if not np.array_equal(getattr(arrays[0], name)[own], getattr(dev, name)[own]):
+                bad.append("masked download of %s differs from the device state" % name)
         if not (o != rank).any() or len(g) >= f.floes.n:
             bad.append("no decomposition happened")
         if s.stale():
