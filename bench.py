@@ -477,8 +477,8 @@ def main():
                         "sz_slab_step_host on pinned host arrays of every rank's local list (uploads, publication of the "
                         "uploaded boundary floes to the neighbours, step, overlapped downloads)"),
                "separate_calls_steps_per_s": sep, "masked": masked,
-               "floor": ("PCIe: the 33 MB that only exist after the state update leave in 0.8 ms (41 GB/s measured) behind 1.13 ms of "
-                         "kernels that cannot start before the first upload group has landed (0.16 ms): 2.1 ms = 475 steps/s is the "
+               "floor": ("PCIe: the 33 MB that only exist after the state update leave in 0.8 ms (41 GB/s measured) behind 1.08 ms of "
+                         "kernels that cannot start before the first upload group has landed (0.16 ms): 2.04 ms = 490 steps/s is the "
                          "floor of an all-fields synchronous step on this box (profiles/README.md)" if world == 1 else
                          "host bandwidth: with 8 ranks copying at once this box gives each rank 17-23 GB/s (88 GB/s alone; "
                          "tools/pcie_concurrency.py, profiles/r2/r3a_pcie_n8.json): the 79 MB of an all-fields step take 3.7-5.0 ms "
@@ -561,11 +561,11 @@ def main():
     except Exception:
         pass
     notes = {"k_narrow": "narrow phase = k_item_count/scatter + k_narrow_ab<0> (clip, decisions) + k_narrow_ab<1> (forces) + k_narrow "
-                         "(warp kernel: large rings and every rare path): FP64 latency bound, not bandwidth bound (ncu r1m: 4 % of DRAM "
-                         "peak, 25 % issue slots, 12 warps per SM, 23 of 32 lanes active); the HBM fraction is reported because the "
+                         "(warp kernel: large rings and every rare path): FP64 latency bound, not bandwidth bound (ncu r3g: 2-4 % of DRAM "
+                         "peak, 29-36 % issue slots, 12 warps per SM, 20-24 of 32 lanes active, FP64 pipe 14-16 %); the HBM fraction is reported because the "
                          "contract asks for it, roofline.fp64 gives the FP64 view (profiles/README.md)",
-             "k_coupling": "streams 16 B per Monte-Carlo point once (ncu: 962 MB = the algorithmic bytes) through a cp.async ring; FP64 pipe "
-                           "54 % busy; inside sz_step it runs on a second stream beside the broad phase",
+             "k_coupling": "streams 16 B per Monte-Carlo point once (ncu: 962 MB = the algorithmic bytes) through cp.async.bulk; FP64 pipe "
+                           "55 % busy, issue slots 65 %; inside sz_step it runs on a second stream beside the broad phase",
              "k_update": "", "broad": "chain of small dependent kernels (uniform grid, neighbour lists, image filter): latency bound",
              "rows": "per-floe row assembly + sequential sums in the reference's row order (deterministic, no float atomics)"}
     roofline = {"kernel": dom if dom != "k_narrow" else "k_narrow_ab", "bound": "hbm", "achieved": achieved, "peak": hbm,
